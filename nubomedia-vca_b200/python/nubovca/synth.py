@@ -1,0 +1,100 @@
+"""Deterministic synthetic frames for parity tests and bench.py.
+
+Procedurally composited high-contrast face patches on a blurred-noise background; the patch
+is built to fire haarcascade_frontalface_alt and to push windows through every stage, so that
+stage-exit depth maps are exercised at all depths.  Pure numpy (no cv2) so that the generator
+behaves identically wherever it runs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _blur(img: np.ndarray, sigma: float) -> np.ndarray:
+    """Separable Gaussian blur, reflect-101 borders, float64 accumulate."""
+    if sigma <= 0:
+        return img.astype(np.float64)
+    r = max(1, int(np.ceil(3 * sigma)))
+    k = np.exp(-0.5 * (np.arange(-r, r + 1) / sigma) ** 2)
+    k /= k.sum()
+    out = img.astype(np.float64)
+    for axis in (0, 1):
+        pad = [(0, 0), (0, 0)]
+        pad[axis] = (r, r)
+        p = np.pad(out, pad, mode="reflect")
+        acc = np.zeros_like(out)
+        n = out.shape[axis]
+        for i, kv in enumerate(k):
+            sl = [slice(None), slice(None)]
+            sl[axis] = slice(i, i + n)
+            acc += kv * p[tuple(sl)]
+        out = acc
+    return out
+
+
+def _ellipse(xx, yy, cx, cy, rx, ry):
+    return ((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2 <= 1.0
+
+
+def face_patch(s: int) -> np.ndarray:
+    """s x s float patch (SURVEY.md §8d recipe)."""
+    yy, xx = (np.mgrid[0:s, 0:s] + 0.5) / s
+    p = np.full((s, s), 90.0)
+    p[_ellipse(xx, yy, .5, .52, .38, .48)] = 185
+    p[yy < .18] = 70
+    for ex in (.33, .67):
+        p[_ellipse(xx, yy, ex, .39, .14, .08)] = 140
+        p[_ellipse(xx, yy, ex, .31, .13, .025)] = 75
+        p[_ellipse(xx, yy, ex, .40, .10, .045)] = 45
+    p[(np.abs(xx - .5) < .045) & (yy > .36) & (yy < .62)] = 205
+    for nx in (.45, .55):
+        p[_ellipse(xx, yy, nx, .64, .03, .02)] = 95
+    for cx in (.3, .7):
+        p[_ellipse(xx, yy, cx, .58, .10, .08)] = 200
+    p[_ellipse(xx, yy, .5, .77, .16, .035)] = 80
+    p[yy > .9] = 130
+    return _blur(p, s / 60.0)
+
+
+def frame(width: int, height: int, k: int, seed: int, channels: int = 3, tint: bool = True,
+          smin: float = 0.10, smax: float = 1 / 3) -> np.ndarray:
+    """One BGR (channels=3) or BGRA (channels=4) frame with k faces."""
+    rng = np.random.default_rng(seed)
+    bg = np.clip(110 + 25 * rng.standard_normal((height, width)), 0, 255)
+    g = _blur(bg, 1.5)
+    for _ in range(k):
+        s = int(rng.uniform(height * smin, height * smax))
+        x = int(rng.integers(0, max(1, width - s)))
+        y = int(rng.integers(0, max(1, height - s)))
+        g[y:y + s, x:x + s] = face_patch(s)
+    g8 = np.clip(np.rint(g), 0, 255).astype(np.uint8)
+    out = np.empty((height, width, channels), np.uint8)
+    tints = (5, 0, -5) if tint else (0, 0, 0)
+    for c in range(3):
+        out[..., c] = np.clip(g8.astype(np.int16) + tints[c], 0, 255).astype(np.uint8)
+    if channels == 4:
+        out[..., 3] = 255
+    return out
+
+
+def tracker_sequence(width: int, height: int, nframes: int, seed: int = 4, nsq: int = 3,
+                     noise: int = 0) -> list[np.ndarray]:
+    """cfg4: static background + bright squares translating 4 px/frame, BGRA."""
+    rng = np.random.default_rng(seed)
+    bg = np.clip(np.rint(_blur(np.clip(110 + 25 * rng.standard_normal((height, width)), 0, 255), 1.5)), 0, 255)
+    sq = [(int(rng.integers(40, 121)), int(rng.integers(0, width // 2)), int(rng.integers(0, height - 130)),
+           int(rng.choice([-4, 4])) if i else 4) for i in range(nsq)]
+    frames = []
+    for f in range(nframes):
+        g = bg.copy()
+        for (s, x0, y0, vx) in sq:
+            x = (x0 + vx * f) % (width - s)
+            g[y0:y0 + s, x:x + s] = 235
+        if noise:
+            idx = rng.integers(0, width * height, noise)
+            g.reshape(-1)[idx] = 255
+        out = np.empty((height, width, 4), np.uint8)
+        out[..., 0] = out[..., 1] = out[..., 2] = g.astype(np.uint8)
+        out[..., 3] = 255
+        frames.append(out)
+    return frames

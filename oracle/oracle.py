@@ -1,0 +1,319 @@
+"""ctypes front-end of the CPU oracle (oracle/nubo_oracle.c).
+
+TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs, never by the product under nubomedia-vca_b200/.
+
+The cascade XML is parsed here with xml.etree (an independent parser from the product's C++
+loader in nubomedia-vca_b200/csrc/cascade_xml.cpp, so the two cross-check each other).
+XML grammar: OpenCV "opencv-cascade-classifier" new format, the files the reference loads
+with CascadeClassifier::load (kmsfacedetect.cpp:163-177).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libnubo_oracle.so")
+
+DEPTH_VARREJ = -100
+DEPTH_SKIPPED = -32768
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "nubo_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+class _CCascade(C.Structure):
+    _fields_ = [
+        ("win_w", C.c_int), ("win_h", C.c_int), ("nstages", C.c_int), ("nstumps", C.c_int),
+        ("stage_ntrees", C.POINTER(C.c_int)), ("stage_thr", C.POINTER(C.c_float)),
+        ("stump_feat", C.POINTER(C.c_int)), ("stump_thr", C.POINTER(C.c_float)),
+        ("stump_left", C.POINTER(C.c_float)), ("stump_right", C.POINTER(C.c_float)),
+        ("nfeatures", C.c_int),
+        ("feat_rect", C.POINTER(C.c_int)), ("feat_weight", C.POINTER(C.c_float)),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.ora_scales.restype = C.c_int
+        _lib.ora_scales.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_void_p, C.c_int]
+        _lib.ora_eval_level.restype = C.c_int
+        _lib.ora_eval_level.argtypes = [C.POINTER(_CCascade), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _lib.ora_row_limit.restype = C.c_int
+        _lib.ora_row_limit.argtypes = [C.c_int, C.c_int, C.c_int]
+        _lib.ora_feature_value.restype = C.c_int
+        _lib.ora_feature_value.argtypes = [C.POINTER(_CCascade), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_void_p]
+        _lib.ora_group_rectangles.restype = C.c_int
+        _lib.ora_group_rectangles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
+        _lib.ora_detect_multiscale.restype = C.c_int
+        _lib.ora_detect_multiscale.argtypes = [C.POINTER(_CCascade), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _lib.ora_face_process.restype = C.c_int
+        _lib.ora_face_process.argtypes = [C.POINTER(_CCascade), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_int, C.c_void_p]
+        _lib.ora_segment_motion.restype = C.c_int
+        _lib.ora_segment_motion.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                            C.c_void_p, C.c_void_p, C.c_int]
+        _lib.ora_join_objects.restype = C.c_int
+        _lib.ora_join_objects.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_int]
+        _lib.ora_tracker_process.restype = C.c_int
+        _lib.ora_tracker_process.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_long, C.c_int,
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _lib.ora_update_mhi.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double]
+        _lib.ora_absdiff_threshold.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+# ------------------------------------------------------------------------------------------
+# cascade model
+# ------------------------------------------------------------------------------------------
+def parse_cascade_xml(path: str) -> dict:
+    """Parse a new-format stump cascade.  Raises NotImplementedError for trees/tilted/LBP."""
+    root = ET.parse(path).getroot()
+    casc = root.find("cascade")
+    if casc is None or casc.findtext("featureType", "").strip() != "HAAR":
+        raise NotImplementedError("only HAAR new-format cascades")
+    win_w, win_h = int(casc.findtext("width")), int(casc.findtext("height"))
+    stage_ntrees, stage_thr, feat, thr, left, right = [], [], [], [], [], []
+    for st in casc.find("stages"):
+        weak = st.find("weakClassifiers")
+        stage_thr.append(float(st.findtext("stageThreshold")))
+        n = 0
+        for wc in weak:
+            nodes = wc.findtext("internalNodes").split()
+            leaves = wc.findtext("leafValues").split()
+            if len(nodes) != 4 or len(leaves) != 2:
+                raise NotImplementedError("tree weak classifiers (depth>1)")
+            feat.append(int(nodes[2])); thr.append(float(nodes[3]))
+            left.append(float(leaves[0])); right.append(float(leaves[1]))
+            n += 1
+        stage_ntrees.append(n)
+    rects, weights = [], []
+    for f in casc.find("features"):
+        if int((f.findtext("tilted") or "0").strip()) != 0:
+            raise NotImplementedError("tilted features")
+        r = np.zeros((3, 4), np.int32); w = np.zeros(3, np.float32)
+        for k, rc in enumerate(f.find("rects")):
+            t = rc.text.split()
+            r[k] = [int(t[0]), int(t[1]), int(t[2]), int(t[3])]; w[k] = np.float32(float(t[4]))
+        rects.append(r); weights.append(w)
+    return dict(
+        win_w=win_w, win_h=win_h,
+        stage_ntrees=np.array(stage_ntrees, np.int32), stage_thr=np.array(stage_thr, np.float64).astype(np.float32),
+        stump_feat=np.array(feat, np.int32), stump_thr=np.array(thr, np.float64).astype(np.float32),
+        stump_left=np.array(left, np.float64).astype(np.float32),
+        stump_right=np.array(right, np.float64).astype(np.float32),
+        feat_rect=np.ascontiguousarray(np.stack(rects)), feat_weight=np.ascontiguousarray(np.stack(weights)),
+    )
+
+
+class Cascade:
+    def __init__(self, path_or_dict):
+        d = parse_cascade_xml(path_or_dict) if isinstance(path_or_dict, str) else path_or_dict
+        self.d = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+        d = self.d
+        self.win_w, self.win_h = d["win_w"], d["win_h"]
+        self.nstages, self.nstumps = len(d["stage_ntrees"]), len(d["stump_feat"])
+        ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+        self.c = _CCascade(
+            d["win_w"], d["win_h"], self.nstages, self.nstumps,
+            d["stage_ntrees"].ctypes.data_as(ip), d["stage_thr"].ctypes.data_as(fp),
+            d["stump_feat"].ctypes.data_as(ip), d["stump_thr"].ctypes.data_as(fp),
+            d["stump_left"].ctypes.data_as(fp), d["stump_right"].ctypes.data_as(fp),
+            len(d["feat_rect"]), d["feat_rect"].ctypes.data_as(ip), d["feat_weight"].ctypes.data_as(fp))
+
+
+# ------------------------------------------------------------------------------------------
+# image ops
+# ------------------------------------------------------------------------------------------
+def bgr2gray(img):
+    img = _u8(img); h, w, cn = img.shape
+    out = np.empty((h, w), np.uint8)
+    lib().ora_bgr2gray(_p(img), w, h, img.strides[0], cn, _p(out), w)
+    return out
+
+
+def resize_linear(img, dw, dh):
+    img = _u8(img)
+    h, w = img.shape[:2]; cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty((dh, dw) if img.ndim == 2 else (dh, dw, cn), np.uint8)
+    lib().ora_resize_linear(_p(img), w, h, img.strides[0], cn, _p(out), dw, dh, dw * cn)
+    return out
+
+
+def equalize_hist(img):
+    img = _u8(img); h, w = img.shape
+    out = np.empty_like(img)
+    lib().ora_equalize_hist(_p(img), w, h, img.strides[0], _p(out), w)
+    return out
+
+
+def resize_linear_exact(img, dw, dh):
+    img = _u8(img); h, w = img.shape
+    out = np.empty((dh, dw), np.uint8)
+    lib().ora_resize_linear_exact(_p(img), w, h, img.strides[0], _p(out), dw, dh, dw)
+    return out
+
+
+def integral(img):
+    img = _u8(img); h, w = img.shape
+    s = np.empty((h + 1, w + 1), np.int32); q = np.empty((h + 1, w + 1), np.uint32)
+    lib().ora_integral(_p(img), w, h, img.strides[0], _p(s), _p(q))
+    return s, q
+
+
+# ------------------------------------------------------------------------------------------
+# cascade
+# ------------------------------------------------------------------------------------------
+def scales(W, H, casc: Cascade, scale_factor, min_size=(0, 0), max_size=(0, 0)):
+    buf = np.empty(256, np.float32)
+    n = lib().ora_scales(W, H, casc.win_w, casc.win_h, float(scale_factor), min_size[0], min_size[1],
+                         max_size[0], max_size[1], _p(buf), 256)
+    return buf[:min(n, 256)].copy()
+
+
+def level_size(W, H, sc):
+    lw, lh = C.c_int(), C.c_int()
+    lib().ora_level_size(W, H, C.c_float(sc), C.byref(lw), C.byref(lh))
+    return lw.value, lh.value
+
+
+def eval_pyramid(gray, casc: Cascade, scale_factor, min_size=(0, 0), max_size=(0, 0), keep_integrals=False):
+    """Per-level artefacts the GPU path must match bit-exactly.
+
+    Returns a list of dicts: scale, ystep, lw, lh, image, (sum, sqsum), depth [ny, nx] int16,
+    cand [k,4] (un-clipped candidate rects in y -> x order).
+    """
+    gray = _u8(gray); H, W = gray.shape
+    out = []
+    scs = scales(W, H, casc, scale_factor, min_size, max_size)
+    nstripes = 1
+    if len(scs):
+        nstripes = (max(level_size(W, H, scs[0])[0] + 1 - casc.win_w, 0) + 31) // 32
+    for sc in scs:
+        lw, lh = level_size(W, H, sc)
+        rx, ry = lw + 1 - casc.win_w, lh + 1 - casc.win_h
+        if rx <= 0 or ry <= 0:
+            continue
+        img = gray.copy() if (lw, lh) == (W, H) else resize_linear_exact(gray, lw, lh)
+        s, q = integral(img)
+        ystep = 1 if sc >= 2 else 2
+        ry = lib().ora_row_limit(ry, ystep, nstripes)
+        nx, ny = (rx + ystep - 1) // ystep, (ry + ystep - 1) // ystep
+        depth = np.empty((ny, nx), np.int16)
+        cand = np.empty((nx * ny, 4), np.int32)
+        nc = C.c_int(0)
+        lib().ora_eval_level(C.byref(casc.c), _p(s), _p(q), lw, lh, ystep, C.c_float(sc), nstripes, _p(depth),
+                             _p(cand), nx * ny, C.byref(nc))
+        lv = dict(scale=float(sc), ystep=ystep, lw=lw, lh=lh, image=img, depth=depth, cand=cand[:nc.value].copy())
+        if keep_integrals:
+            lv["sum"], lv["sqsum"] = s, q
+        out.append(lv)
+    return out
+
+
+def feature_value(casc: Cascade, s, q, x, y, f):
+    """Normalised value of feature f at window (x, y) of a level, or None if variance-rejected."""
+    out = C.c_float(0)
+    ok = lib().ora_feature_value(C.byref(casc.c), _p(s), _p(q), s.shape[1], x, y, f, C.byref(out))
+    return np.float32(out.value) if ok else None
+
+
+def group_rectangles(rects, thr, eps=0.2):
+    r = np.ascontiguousarray(np.asarray(rects, np.int32).reshape(-1, 4)).copy()
+    w = np.zeros(max(len(r), 1), np.int32)
+    n = lib().ora_group_rectangles(_p(r), len(r), thr, eps, _p(w))
+    return r[:n].copy(), w[:n].copy()
+
+
+def detect_multiscale(gray, casc: Cascade, scale_factor=1.1, min_neighbors=3, min_size=(0, 0), max_size=(0, 0),
+                      cap=1 << 20, return_nwindows=False):
+    gray = _u8(gray); H, W = gray.shape
+    out = np.empty((cap, 4), np.int32)
+    nwin = C.c_longlong(0)
+    n = lib().ora_detect_multiscale(C.byref(casc.c), _p(gray), W, H, gray.strides[0], float(scale_factor),
+                                    min_neighbors, min_size[0], min_size[1], max_size[0], max_size[1],
+                                    _p(out), cap, None, C.byref(nwin))
+    res = out[:min(n, cap)].copy()
+    return (res, nwin.value) if return_nwindows else res
+
+
+def face_process(bgr, casc: Cascade, width_to_process=160, scale_factor=1.25, min_neighbors=3, min_size=None,
+                 cap=4096):
+    """kmsfacedetect.cpp:770-811 end to end.  Returns (rects, equalised gray at processing size)."""
+    bgr = _u8(bgr); H, W, _ = bgr.shape
+    iscale = W // width_to_process
+    sc = float(iscale) if iscale > 0 else 1.0
+    rows = int(np.rint(H / sc)) or H; cols = int(np.rint(W / sc)) or W
+    geq = np.empty((rows, cols), np.uint8)
+    out = np.empty((cap, 4), np.int32)
+    mw, mh = (-1, -1) if min_size is None else min_size
+    n = lib().ora_face_process(C.byref(casc.c), _p(bgr), W, H, bgr.strides[0], width_to_process,
+                               float(scale_factor), min_neighbors, mw, mh, _p(out), cap, _p(geq))
+    return out[:n].copy(), geq
+
+
+# ------------------------------------------------------------------------------------------
+# tracker
+# ------------------------------------------------------------------------------------------
+def segment_motion(mhi, ts, seg_thresh=32.0, cap=65536):
+    mhi = np.ascontiguousarray(mhi, np.float32); h, w = mhi.shape
+    labels = np.empty((h, w), np.int32); rects = np.empty((cap, 4), np.int32)
+    n = lib().ora_segment_motion(_p(mhi), w, h, float(ts), float(seg_thresh), _p(labels), _p(rects), cap)
+    return rects[:min(n, cap)].copy(), labels
+
+
+def join_objects(rects, min_area, max_area, distance):
+    r = np.ascontiguousarray(np.asarray(rects, np.int32).reshape(-1, 4)).copy()
+    n = lib().ora_join_objects(_p(r), len(r), min_area, max_area, distance)
+    return r[:n].copy()
+
+
+class TrackerState:
+    """Per-element temporal state of gst_nubo_tracker_process (gstnubotracker.cpp:339-421)."""
+
+    def __init__(self, w, h):
+        self.w, self.h = w, h
+        self.prev = np.zeros((h, w), np.uint8)
+        self.mhi = np.zeros((h, w), np.float32)
+        self.num_frames = 0
+
+    def process(self, bgra, ts, threshold=20, min_area=50, max_area=30000, distance=35, cap=65536):
+        bgra = _u8(bgra)
+        rects = np.empty((cap, 4), np.int32); nraw = C.c_int(0)
+        mask = np.zeros((self.h, self.w), np.uint8)
+        n = lib().ora_tracker_process(_p(bgra), self.w, self.h, bgra.strides[0], int(self.num_frames == 0),
+                                      _p(self.prev), _p(self.mhi), float(ts), threshold, min_area, max_area,
+                                      distance, _p(rects), cap, C.byref(nraw), _p(mask))
+        self.num_frames += 1
+        return rects[:n].copy(), nraw.value, mask

@@ -1,0 +1,45 @@
+"""Writes tiny purpose-built cascades in OpenCV's new XML format (black-box probes)."""
+
+
+def write_cascade(path, w, h, stages, features):
+    """stages: [(stage_thr, [(feature_idx, thr, left, right), ...])]; features: [[(x,y,w,h,weight), ...]]"""
+    s = ['<?xml version="1.0"?>', '<opencv_storage>',
+         '<cascade type_id="opencv-cascade-classifier"><stageType>BOOST</stageType>',
+         '<featureType>HAAR</featureType>', f'<height>{h}</height>', f'<width>{w}</width>',
+         f'<stageParams><maxWeakCount>{max(len(t) for _, t in stages)}</maxWeakCount></stageParams>',
+         '<featureParams><maxCatCount>0</maxCatCount></featureParams>', f'<stageNum>{len(stages)}</stageNum>',
+         '<stages>']
+    for thr, trees in stages:
+        s.append(f'<_><maxWeakCount>{len(trees)}</maxWeakCount><stageThreshold>{float(thr)!r}</stageThreshold>'
+                 '<weakClassifiers>')
+        for (fi, t, l, r) in trees:
+            s.append(f'<_><internalNodes>0 -1 {fi} {float(t)!r}</internalNodes>'
+                     f'<leafValues>{float(l)!r} {float(r)!r}</leafValues></_>')
+        s.append('</weakClassifiers></_>')
+    s.append('</stages><features>')
+    for rects in features:
+        s.append('<_><rects>' + ''.join(f'<_>{x} {y} {ww} {hh} {float(wt)!r}</_>' for (x, y, ww, hh, wt) in rects)
+                 + '</rects><tilted>0</tilted></_>')
+    s.append('</features></cascade></opencv_storage>')
+    with open(path, 'w') as f:
+        f.write('\n'.join(s))
+
+
+def random_cascade(path, rng, w=20, h=20, nstages=4, max_trees=6, nfeat=24):
+    """A random multi-stage stump cascade whose stages reject roughly half of the windows each."""
+    import numpy as np
+    feats = []
+    for _ in range(nfeat):
+        nr = int(rng.integers(2, 4)); rects = []
+        for k in range(nr):
+            x = int(rng.integers(0, w - 2)); y = int(rng.integers(0, h - 2))
+            ww = int(rng.integers(1, w - x + 1)); hh = int(rng.integers(1, h - y + 1))
+            rects.append((x, y, ww, hh, float(np.float32(rng.uniform(-2, 2)))))
+        feats.append(rects)
+    stages = []
+    for _ in range(nstages):
+        nt = int(rng.integers(1, max_trees + 1))
+        trees = [(int(rng.integers(0, nfeat)), float(np.float32(rng.normal(0, 0.05))),
+                  float(np.float32(rng.uniform(-1, 1))), float(np.float32(rng.uniform(-1, 1)))) for _ in range(nt)]
+        stages.append((float(np.float32(rng.uniform(-0.4, 0.1) * nt)), trees))
+    write_cascade(path, w, h, stages, feats)

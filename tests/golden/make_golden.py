@@ -1,0 +1,92 @@
+"""Generates tests/golden/*.json from cv2 4.13 (the library the reference calls for every
+arithmetic step of the hot path).  Run here, in the build container:
+
+    python tests/golden/make_golden.py
+
+The fixtures hold, for seeded synthetic frames (nubovca.synth): sha256 of cv2's gray /
+resized / equalised images and cv2's detectMultiScale rectangles (single-thread order) for
+the element parameter sets of BASELINE.json configs, plus tracker component rectangles from
+cv2.connectedComponentsWithStats.  Tests compare the oracle (and, on the GPU box, the CUDA
+path) with these files without needing cv2.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import cv2
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "nubomedia-vca_b200", "python"))
+from nubovca import synth  # noqa: E402
+
+CASC = os.path.join(ROOT, "nubomedia-vca_b200", "cascades")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def face_case(W, H, k, seed, w2p, sf, mn, min_size, cascade="haarcascade_frontalface_alt.xml"):
+    """kmsfacedetect.cpp:770-811 through cv2."""
+    fr = synth.frame(W, H, k, seed)
+    iscale = W // w2p
+    rows, cols = int(np.rint(H / iscale)), int(np.rint(W / iscale))
+    aux = cv2.resize(fr, (cols, rows), interpolation=cv2.INTER_LINEAR)
+    gray = cv2.cvtColor(aux, cv2.COLOR_BGR2GRAY)
+    eq = cv2.equalizeHist(gray)
+    ms = (cols // 20, rows // 20) if min_size is None else tuple(min_size)
+    cc = cv2.CascadeClassifier(os.path.join(CASC, cascade))
+    raw = np.asarray(cc.detectMultiScale(eq, scaleFactor=sf, minNeighbors=0, minSize=ms)).reshape(-1, 4)
+    grp = np.asarray(cc.detectMultiScale(eq, scaleFactor=sf, minNeighbors=mn, minSize=ms)).reshape(-1, 4)
+    return dict(W=W, H=H, k=k, seed=seed, width_to_process=w2p, scale_factor=sf, min_neighbors=mn,
+                min_size=list(ms), cascade=cascade, frame_sha=sha(fr), resized_sha=sha(aux), gray_sha=sha(gray),
+                eq_sha=sha(eq), raw=raw.tolist(), grouped=grp.tolist())
+
+
+def tracker_case(W, H, nframes, seed, thr, noise):
+    frames = synth.tracker_sequence(W, H, nframes, seed, noise=noise)
+    prev = None
+    out = []
+    for f in frames:
+        gray = cv2.cvtColor(f, cv2.COLOR_BGRA2GRAY)
+        rects = []
+        if prev is not None:
+            mask = cv2.threshold(cv2.absdiff(gray, prev), thr, 255, cv2.THRESH_BINARY)[1]
+            n, lab, stats, _ = cv2.connectedComponentsWithStats(mask, connectivity=4)
+            first = {}
+            flat = lab.reshape(-1)
+            idx = np.flatnonzero(flat)
+            for i in idx:   # raster order of first pixel
+                first.setdefault(int(flat[i]), int(i))
+            for l in sorted(first, key=first.get):
+                rects.append([int(stats[l, 0]), int(stats[l, 1]), int(stats[l, 2]), int(stats[l, 3])])
+        out.append(dict(gray_sha=sha(gray), rects=rects))
+        prev = gray
+    return dict(W=W, H=H, nframes=nframes, seed=seed, threshold=thr, noise=noise, frames=out)
+
+
+def main():
+    cv2.setNumThreads(1)
+    faces = [
+        face_case(640, 480, 4, 1, 160, 1.25, 3, None),                       # cfg1: element defaults
+        face_case(640, 480, 4, 1, 640, 1.25, 3, None),
+        face_case(1280, 720, 3, 1000, 640, 1.25, 3, None),                   # cfg5 stream 0
+        face_case(1280, 720, 5, 2, 160, 1.25, 3, (30, 30)),                  # cfg2 face stage (eye element)
+        face_case(1280, 720, 5, 2, 160, 1.25, 2, (3, 3)),                    # cfg2 face stage (mouth/nose)
+        face_case(640, 360, 6, 3, 640, 1.1, 3, (24, 24)),                    # cfg3 parameters, reduced size
+        face_case(640, 480, 4, 9, 320, 1.1, 2, (0, 0), "haarcascade_profileface.xml"),
+        face_case(640, 480, 4, 9, 320, 1.1, 2, (20, 20), "haarcascade_eye.xml"),
+    ]
+    with open(os.path.join(HERE, "face_golden.json"), "w") as f:
+        json.dump(dict(cv2=cv2.__version__, cases=faces), f)
+    trk = [tracker_case(320, 180, 6, 4, 20, 40), tracker_case(640, 360, 4, 5, 20, 0)]
+    with open(os.path.join(HERE, "tracker_golden.json"), "w") as f:
+        json.dump(dict(cv2=cv2.__version__, cases=trk), f)
+    print("wrote", len(faces), "face cases,", len(trk), "tracker cases")
+
+
+if __name__ == "__main__":
+    main()
