@@ -1,0 +1,189 @@
+/*
+ * nubovca.h — C ABI of libnubovca.so: the B200-native (sm_100a) per-frame detection hot path of
+ * NUBOMEDIA-VCA.  Each entry point replaces the OpenCV call block one reference element makes
+ * per video buffer; the reference file:line it stands in for is cited beside it
+ * (paths relative to /root/reference/modules/<mod>/<mod-dir>/src/gst-plugins/).
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every function returns NV_OK (0) or a negative
+ *     nv_status, and nv_last_error() gives a thread-local message for the last failure.
+ *   - the caller owns input frames and output arrays; the library owns all device and pinned
+ *     memory inside nv_ctx.  Host input is fully consumed before a synchronous call returns
+ *     (the element unmaps the GstBuffer right after, kmsfacedetect.cpp:888).
+ *   - one nv_ctx per element instance (it carries the element's per-stream state: CUDA stream,
+ *     scratch, tracker history).  A ctx is not thread-safe; the element shell serialises calls
+ *     with its own mutex exactly as the reference does (kmsfacedetect.cpp:873-885).  Any number
+ *     of contexts may run concurrently on one GPU and across GPUs.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     NV_ERR_NO_DEVICE.
+ */
+#ifndef NUBOVCA_H
+#define NUBOVCA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NV_API __attribute__((visibility("default")))
+
+typedef enum {
+    NV_OK = 0,
+    NV_ERR_ARG = -1,          /* bad pointer / size / parameter                               */
+    NV_ERR_CUDA = -2,         /* a CUDA runtime call failed (message in nv_last_error)        */
+    NV_ERR_IO = -3,           /* cascade file unreadable                                      */
+    NV_ERR_FORMAT = -4,       /* cascade XML malformed                                        */
+    NV_ERR_UNSUPPORTED = -5,  /* cascade uses tilted features / trees / LBP     */
+    NV_ERR_CAPACITY = -6,     /* frame larger than the ctx was created for, or too many levels */
+    NV_ERR_NO_DEVICE = -7,    /* no CUDA device: the library never computes on the CPU        */
+    NV_ERR_STATE = -8         /* call order violated (collect without submit, ...)            */
+} nv_status;
+
+typedef struct nv_ctx nv_ctx;
+typedef struct nv_cascade nv_cascade;
+
+/* cv::Rect as the elements store it (vector<Rect>, kmsfacedetect.cpp:792) */
+typedef struct { int x, y, width, height; } nv_rect;
+
+NV_API const char *nv_version(void);
+NV_API const char *nv_last_error(void);
+NV_API int nv_device_count(void);                       /* 0 when no CUDA device is visible */
+
+/* ---- cascade model: replaces cv::CascadeClassifier::load (kmsfacedetect.cpp:163-177,
+ *      kmseyedetect.cpp:171-183, kmsmouthdetect.cpp:157-163, kmsnosedetect.cpp:166-172,
+ *      kmseardetect.cpp:173-186).  Host-side parse only; usable without a GPU. ---------------- */
+typedef struct {
+    int win_w, win_h;        /* training window                                   */
+    int nstages, nstumps;    /* boosted stages / weak classifiers (stumps)        */
+    int nfeatures;           /* Haar features (<= 3 rects each)                   */
+    int n3rect;              /* features that use the third rectangle             */
+    int order_free_sums;     /* 1: every stage sum is exact in double in any order */
+} nv_cascade_info;
+
+NV_API int nv_cascade_load(const char *xml_path, nv_cascade **out);
+NV_API int nv_cascade_get_info(const nv_cascade *c, nv_cascade_info *info);
+NV_API void nv_cascade_free(nv_cascade *c);
+
+/* ---- context ------------------------------------------------------------------------------ */
+NV_API int nv_ctx_create(int gpu, int max_width, int max_height, nv_ctx **out);
+NV_API void nv_ctx_destroy(nv_ctx *ctx);
+/* debug != 0 makes the cascade kernels also write per-window stage-exit depth maps
+ * (same kernels, same arithmetic — a template flag adds the stores). */
+NV_API int nv_ctx_set_debug(nv_ctx *ctx, int debug);
+
+/* ---- CascadeClassifier::detectMultiScale on an 8-bit gray image
+ *      (kmsfacedetect.cpp:809-811, kmseyedetect.cpp:958-960,991-993,1003-1005,
+ *       kmsmouthdetect.cpp:845-848,870-873, kmsnosedetect.cpp:843-846,870-873,
+ *       kmseardetect.cpp:656-659,712-715).  `flags` is accepted and ignored, as OpenCV >= 3
+ *      ignores it for new-format cascades.  max_w/max_h == 0 means "image size". ---------------- */
+typedef struct {
+    double scale_factor;
+    int min_neighbors;
+    int flags;
+    int min_w, min_h;
+    int max_w, max_h;
+} nv_detect_params;
+
+NV_API int nv_detect_multiscale(nv_ctx *ctx, const nv_cascade *c, const uint8_t *gray, int width, int height,
+                                int stride_bytes, const nv_detect_params *p, nv_rect *out, int cap, int *n);
+
+/* ---- the nubofacedetector hot block, kmsfacedetect.cpp:770-811:
+ *      scale = width / width_to_process (integer), cv::resize(BGR, INTER_LINEAR), BGR2GRAY,
+ *      equalizeHist, detectMultiScale(scale_factor, min_neighbors, 0, Size(min_w, min_h)).
+ *      min_w < 0 selects the element's own rule Size(cols/20, rows/20) (:811).
+ *      Rectangles are in processing-size coordinates, like the reference's current_faces. ------ */
+typedef struct {
+    int width_to_process;
+    double scale_factor;      /* MULTI_SCALE_FACTOR(prop) = 1 + prop/100, kmsfacedetect.cpp:142 */
+    int min_neighbors;        /* 3 in the reference                                            */
+    int min_w, min_h;
+} nv_face_params;
+
+NV_API int nv_face_detect(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, int width, int height,
+                          int stride_bytes, const nv_face_params *p, nv_rect *out, int cap, int *n);
+
+/* Asynchronous halves of nv_face_detect, so that one host thread can keep many per-stream
+ * contexts in flight (BASELINE config 5: 32 streams per GPU).  submit() copies the frame into the
+ * ctx's pinned staging buffer (after which the caller may reuse it) and enqueues copy + kernels
+ * on the ctx's CUDA stream; collect() waits for that stream and returns the rectangles. */
+NV_API int nv_face_submit(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, int width, int height,
+                          int stride_bytes, const nv_face_params *p);
+NV_API int nv_face_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n);
+
+/* Same pipeline with the frame already resident in device memory (bench.py `value`: inputs in
+ * HBM when the timed region starts).  d_bgr must stay valid until collect. */
+NV_API int nv_face_submit_device(nv_ctx *ctx, const nv_cascade *c, const uint8_t *d_bgr, int width, int height,
+                                 int stride_bytes, const nv_face_params *p);
+
+/* ---- the nubotracker per-frame block, gstnubotracker.cpp:356-380: BGRA->gray, absdiff with the
+ *      previous frame, threshold, updateMotionHistory(ts, 0.2), segmentMotion(ts, 32),
+ *      __join_objects.  The reference's timestamp is clock() in ms (:349); it is injected here.
+ *      The first frame after create only primes the history (num_frames == 0, :360). ---------- */
+typedef struct {
+    int threshold;            /* set_threshold, default 20    */
+    int min_area;             /* set_min_area, default 50     */
+    long max_area;            /* set_max_area, default 30000  */
+    int distance;             /* set_distance, default 35     */
+} nv_tracker_params;
+
+NV_API int nv_tracker_process(nv_ctx *ctx, const uint8_t *bgra, int width, int height, int stride_bytes,
+                              double timestamp_ms, const nv_tracker_params *p, nv_rect *out, int cap, int *n);
+NV_API int nv_tracker_reset(nv_ctx *ctx);
+
+/* ---- image ops used by the nested elements (eye/mouth/nose/ear) on host images:
+ *      cvtColor BGR2GRAY (kmseyedetect.cpp:949), equalizeHist (:950,964), cv::resize INTER_LINEAR
+ *      (:956,963), cv::flip(…,1) (kmseardetect.cpp:800). ------------------------------------- */
+NV_API int nv_bgr2gray(nv_ctx *ctx, const uint8_t *src, int width, int height, int stride_bytes, int channels,
+                       uint8_t *dst_gray, int dst_stride);
+NV_API int nv_equalize_hist(nv_ctx *ctx, const uint8_t *src, int width, int height, int stride_bytes,
+                            uint8_t *dst, int dst_stride);
+NV_API int nv_resize_linear(nv_ctx *ctx, const uint8_t *src, int width, int height, int stride_bytes, int channels,
+                            uint8_t *dst, int dst_width, int dst_height, int dst_stride);
+NV_API int nv_flip_horizontal(nv_ctx *ctx, const uint8_t *src, int width, int height, int stride_bytes,
+                              uint8_t *dst, int dst_stride);
+
+/* ---- device-side timing (bench.py): CUDA events on the ctx's own stream.  With profiling on, every
+ *      pipeline stage of a detect call is bracketed by events; times are read after collect.
+ *      Stage slots: see nv_stage_name(). ------------------------------------------------------ */
+#define NV_NUM_STAGES 8
+NV_API const char *nv_stage_name(int slot);
+NV_API int nv_ctx_set_profile(nv_ctx *ctx, int on);
+NV_API int nv_ctx_get_stage_times(nv_ctx *ctx, float *ms, int cap, int *n);   /* last collected call */
+NV_API int nv_event_create(void **ev);
+NV_API int nv_event_record(nv_ctx *ctx, void *ev);                             /* on the ctx's stream */
+NV_API int nv_event_elapsed_ms(void *ev_start, void *ev_end, float *ms);       /* waits for ev_end   */
+NV_API void nv_event_destroy(void *ev);
+
+/* ---- parity taps (tests only): artefacts of the LAST detect call on this ctx ---------------- */
+typedef struct {
+    float scale;
+    int width, height;        /* level image size                                   */
+    int ystep;
+    int nx, ny;               /* window grid actually visited (x and y in ystep units) */
+} nv_level_info;
+
+#define NV_DEPTH_PASS 1
+#define NV_DEPTH_VARREJ (-100)     /* OpenCV result -1 from the variance test                 */
+#define NV_DEPTH_SKIPPED (-32768)  /* never evaluated: stage-0 skip rule                      */
+/* other values: 0 = failed stage 0, -k = failed stage k                                       */
+
+/* model taps: what the XML loader produced (cross-checked against an independent parser in tests) */
+NV_API int nv_debug_cascade_stage(const nv_cascade *c, int stage, int *ntrees, float *threshold_used);
+NV_API int nv_debug_cascade_stump(const nv_cascade *c, int stump, int rects12[12], float weights3[3],
+                                  float thr_left_right[3]);
+
+NV_API int nv_debug_num_levels(nv_ctx *ctx);
+NV_API int nv_debug_level_info(nv_ctx *ctx, int level, nv_level_info *info);
+NV_API int nv_debug_get_gray(nv_ctx *ctx, uint8_t *dst, int cap_bytes, int *width, int *height);
+NV_API int nv_debug_get_integral(nv_ctx *ctx, int level, int32_t *sum, uint32_t *sqsum);     /* (h+1)*(w+1) each */
+NV_API int nv_debug_get_depth_map(nv_ctx *ctx, int level, int16_t *depth);                    /* ny*nx           */
+NV_API int nv_debug_get_candidates(nv_ctx *ctx, nv_rect *out, int cap, int *n);               /* raw, canonical order */
+/* counters of the last call: [0] windows visited, [1] windows alive after stage 0,
+ * [2] raw candidates, [3] kernels launched, [4..7] reserved */
+NV_API int nv_debug_get_counters(nv_ctx *ctx, long long *out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUBOVCA_H */

@@ -1,0 +1,835 @@
+// context.cu — the C ABI of libnubovca.so (include/nubovca.h): cascade objects, per-element contexts, the
+// per-frame plan (scale list, level geometry, coefficient tables), and the stream-ordered pipelines that
+// replace the OpenCV call blocks of the reference elements.  No host decision is taken between the H2D copy
+// of a frame and the D2H copy of its rectangles: candidate counts stay on the device.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "internal.h"
+
+#define NV_VERSION_STR "nubovca-b200 0.1 (sm_100a)"
+#define CAND_CAP 8192
+#define RESULT_CAP 16384
+
+extern "C" const char *nv_version(void) { return NV_VERSION_STR; }
+
+extern "C" int nv_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cascade
+// ------------------------------------------------------------------------------------------------
+extern "C" int nv_cascade_load(const char *xml_path, nv_cascade **out)
+{
+    if (!xml_path || !out) { nv_set_error("nv_cascade_load: null argument"); return NV_ERR_ARG; }
+    *out = nullptr;
+    nv_cascade *c = new nv_cascade();
+    int rc = nv_parse_cascade_xml(xml_path, &c->h);
+    if (rc != NV_OK) { delete c; return rc; }
+    const HostCascade &h = c->h;
+    memset(&c->meta, 0, sizeof c->meta);
+    c->meta.win_w = h.win_w; c->meta.win_h = h.win_h;
+    c->meta.nstages = (int)h.stage_ntrees.size(); c->meta.nstumps = (int)h.stump_feat.size();
+    int acc = 0;
+    for (int s = 0; s < c->meta.nstages; s++) {
+        c->meta.stage_first[s] = acc;
+        acc += h.stage_ntrees[s];
+        c->meta.stage_thr[s] = h.stage_thr[s] - 1e-5f;            // THRESHOLD_EPS, float arithmetic
+    }
+    c->meta.stage_first[c->meta.nstages] = acc;
+    c->stumps.resize(h.stump_feat.size());
+    for (size_t i = 0; i < h.stump_feat.size(); i++) {
+        DevStump &d = c->stumps[i];
+        memset(&d, 0, sizeof d);
+        const int *r = &h.feat_rect[(size_t)h.stump_feat[i] * 12];
+        const float *w = &h.feat_weight[(size_t)h.stump_feat[i] * 3];
+        for (int k = 0; k < 3; k++) {
+            d.r[k] = (uint32_t)r[4 * k] | ((uint32_t)r[4 * k + 1] << 8) | ((uint32_t)r[4 * k + 2] << 16) |
+                     ((uint32_t)r[4 * k + 3] << 24);
+            d.w[k] = w[k];
+        }
+        d.thr = h.stump_thr[i]; d.left = h.stump_left[i]; d.right = h.stump_right[i];
+    }
+    *out = c;
+    return NV_OK;
+}
+
+extern "C" int nv_cascade_get_info(const nv_cascade *c, nv_cascade_info *info)
+{
+    if (!c || !info) { nv_set_error("nv_cascade_get_info: null argument"); return NV_ERR_ARG; }
+    info->win_w = c->h.win_w; info->win_h = c->h.win_h;
+    info->nstages = (int)c->h.stage_ntrees.size(); info->nstumps = (int)c->h.stump_feat.size();
+    info->nfeatures = (int)c->h.feat_weight.size() / 3; info->n3rect = c->h.n3rect;
+    info->order_free_sums = c->h.order_free;
+    return NV_OK;
+}
+
+extern "C" int nv_debug_cascade_stage(const nv_cascade *c, int stage, int *ntrees, float *threshold_used)
+{
+    if (!c || stage < 0 || stage >= c->meta.nstages) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    if (ntrees) *ntrees = c->meta.stage_first[stage + 1] - c->meta.stage_first[stage];
+    if (threshold_used) *threshold_used = c->meta.stage_thr[stage];
+    return NV_OK;
+}
+
+extern "C" int nv_debug_cascade_stump(const nv_cascade *c, int stump, int rects12[12], float weights3[3],
+                                      float thr_left_right[3])
+{
+    if (!c || stump < 0 || stump >= c->meta.nstumps || !rects12 || !weights3 || !thr_left_right) {
+        nv_set_error("bad argument");
+        return NV_ERR_ARG;
+    }
+    const DevStump &d = c->stumps[stump];
+    for (int k = 0; k < 3; k++) {
+        rects12[4 * k] = d.r[k] & 255; rects12[4 * k + 1] = (d.r[k] >> 8) & 255;
+        rects12[4 * k + 2] = (d.r[k] >> 16) & 255; rects12[4 * k + 3] = d.r[k] >> 24;
+        weights3[k] = d.w[k];
+    }
+    thr_left_right[0] = d.thr; thr_left_right[1] = d.left; thr_left_right[2] = d.right;
+    return NV_OK;
+}
+
+extern "C" void nv_cascade_free(nv_cascade *c)
+{
+    if (!c) return;
+    for (auto &kv : c->d_stumps) { cudaSetDevice(kv.first); cudaFree(kv.second); }
+    for (auto &kv : c->d_meta) { cudaSetDevice(kv.first); cudaFree(kv.second); }
+    delete c;
+}
+
+static int cascade_on_device(nv_cascade *c, int gpu, cudaStream_t st, const DevStump **stumps, const DevCascade **meta)
+{
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->d_stumps.find(gpu);
+    if (it == c->d_stumps.end()) {
+        DevStump *ds = nullptr; DevCascade *dm = nullptr;
+        NV_CUDA(cudaMalloc(&ds, c->stumps.size() * sizeof(DevStump)));
+        NV_CUDA(cudaMalloc(&dm, sizeof(DevCascade)));
+        NV_CUDA(cudaMemcpy(ds, c->stumps.data(), c->stumps.size() * sizeof(DevStump), cudaMemcpyHostToDevice));
+        NV_CUDA(cudaMemcpy(dm, &c->meta, sizeof(DevCascade), cudaMemcpyHostToDevice));
+        c->d_stumps[gpu] = ds; c->d_meta[gpu] = dm;
+    }
+    *stumps = c->d_stumps[gpu]; *meta = c->d_meta[gpu];
+    (void)st;
+    return NV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int ensure(T **p, size_t *cap, size_t need, bool zero = false)
+{
+    if (*p && *cap >= need) return NV_OK;
+    if (*p) { NV_CUDA(cudaFree(*p)); *p = nullptr; }
+    size_t n = need + need / 8 + 64;
+    NV_CUDA(cudaMalloc(p, n * sizeof(T)));
+    if (zero) NV_CUDA(cudaMemset(*p, 0, n * sizeof(T)));
+    *cap = n;
+    return NV_OK;
+}
+
+extern "C" int nv_ctx_create(int gpu, int max_width, int max_height, nv_ctx **out)
+{
+    if (!out || max_width <= 0 || max_height <= 0 || max_width > 16384 || max_height > 16384) {
+        nv_set_error("nv_ctx_create: bad argument");
+        return NV_ERR_ARG;
+    }
+    *out = nullptr;
+    int ndev = nv_device_count();
+    if (ndev <= 0) { nv_set_error("no CUDA device visible: libnubovca has no CPU path"); return NV_ERR_NO_DEVICE; }
+    if (gpu < 0 || gpu >= ndev) { nv_set_error("gpu ordinal %d out of range (0..%d)", gpu, ndev - 1); return NV_ERR_ARG; }
+    NV_CUDA(cudaSetDevice(gpu));
+    nv_ctx *c = new nv_ctx();
+    c->gpu = gpu; c->max_w = max_width; c->max_h = max_height;
+    int rc = [&]() -> int {
+        NV_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        NV_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+        c->frame_cap = (size_t)max_width * max_height * 4 + 4096;
+        NV_CUDA(cudaMallocHost(&c->h_frame, c->frame_cap));
+        NV_CUDA(cudaMalloc(&c->d_frame, c->frame_cap));
+        c->gray_cap = (size_t)max_width * max_height + 256;
+        NV_CUDA(cudaMalloc(&c->d_gray, c->gray_cap));
+        NV_CUDA(cudaMalloc(&c->d_hist, 256 * sizeof(int)));
+        NV_CUDA(cudaMemset(c->d_hist, 0, 256 * sizeof(int)));
+        NV_CUDA(cudaMalloc(&c->d_lut, 512));
+        uint8_t ident[256];
+        for (int i = 0; i < 256; i++) ident[i] = (uint8_t)i;
+        NV_CUDA(cudaMemcpy(c->d_lut + 256, ident, 256, cudaMemcpyHostToDevice));     // identity LUT
+        NV_CUDA(cudaMalloc(&c->d_plan, sizeof(PlanDev)));
+        NV_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(int)));
+        c->cand_cap = CAND_CAP; c->result_cap = RESULT_CAP;
+        NV_CUDA(cudaMalloc(&c->d_cand, c->cand_cap * sizeof(uint32_t)));
+        NV_CUDA(cudaMalloc(&c->d_cand_sorted, c->cand_cap * sizeof(uint32_t)));
+        NV_CUDA(cudaMalloc(&c->d_cand_rects, c->cand_cap * sizeof(int4)));
+        size_t adj_words = (size_t)c->cand_cap * ((c->cand_cap + 31) / 32) + 8 * (size_t)c->cand_cap;
+        NV_CUDA(cudaMalloc(&c->d_adj, adj_words * sizeof(uint32_t)));
+        size_t rbytes = sizeof(ResultHeader) + (size_t)c->result_cap * sizeof(nv_rect);
+        NV_CUDA(cudaMalloc(&c->d_result, rbytes));
+        NV_CUDA(cudaMallocHost(&c->h_result, rbytes));
+        return NV_OK;
+    }();
+    if (rc != NV_OK) { nv_ctx_destroy(c); return rc; }
+    *out = c;
+    return NV_OK;
+}
+
+extern "C" void nv_ctx_destroy(nv_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->gpu);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFreeHost(c->h_frame); cudaFree(c->d_frame); cudaFree(c->d_gray); cudaFree(c->d_hist); cudaFree(c->d_lut);
+    cudaFree(c->d_aux); cudaFree(c->d_rtab); cudaFree(c->d_plan); cudaFree(c->d_ptab); cudaFree(c->d_sum);
+    cudaFree(c->d_sq); cudaFree(c->d_pyr); cudaFree(c->d_vnf); cudaFree(c->d_depth); cudaFree(c->d_bits_fail);
+    cudaFree(c->d_bits_ok); cudaFree(c->d_queue); cudaFree(c->d_counters); cudaFree(c->d_cand);
+    cudaFree(c->d_cand_sorted); cudaFree(c->d_cand_rects); cudaFree(c->d_adj); cudaFree(c->d_result);
+    cudaFreeHost(c->h_result);
+    cudaFree(c->d_trk_prev); cudaFree(c->d_trk_mhi); cudaFree(c->d_trk_labels); cudaFree(c->d_trk_mask);
+    cudaFree(c->d_trk_boxes); cudaFree(c->d_trk_misc); cudaFreeHost(c->h_trk);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
+    for (int i = 0; i <= NV_NUM_STAGES; i++) if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+}
+
+extern "C" int nv_ctx_set_debug(nv_ctx *ctx, int debug)
+{
+    if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }
+    ctx->debug = debug ? 1 : 0;
+    ctx->plan_valid = false;       // debug buffers are sized with the plan
+    return NV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side timing
+// ------------------------------------------------------------------------------------------------
+static const char *k_stage_names[NV_NUM_STAGES] = {"face_prep", "hist_lut", "pyramid_rowscan", "integral_colscan",
+                                                   "cascade_stage0", "skip_compact", "cascade_stages", "group_rectangles"};
+extern "C" const char *nv_stage_name(int slot) { return slot >= 0 && slot < NV_NUM_STAGES ? k_stage_names[slot] : ""; }
+
+static inline void prof_mark(nv_ctx *ctx, int idx)
+{
+    if (!ctx->profile) return;
+    cudaEventRecord(ctx->prof_ev[idx], ctx->stream);
+    ctx->prof_set[idx] = true;
+}
+
+extern "C" int nv_ctx_set_profile(nv_ctx *ctx, int on)
+{
+    if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    if (on && !ctx->prof_ev[0])
+        for (int i = 0; i <= NV_NUM_STAGES; i++) NV_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+    ctx->profile = on ? 1 : 0;
+    return NV_OK;
+}
+
+extern "C" int nv_ctx_get_stage_times(nv_ctx *ctx, float *ms, int cap, int *n)
+{
+    if (!ctx || !ms) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    if (!ctx->profile || ctx->pending) { nv_set_error("profiling off or call still pending"); return NV_ERR_STATE; }
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    int m = std::min(cap, NV_NUM_STAGES);
+    for (int i = 0; i < m; i++) {
+        ms[i] = 0.f;
+        if (ctx->prof_set[i] && ctx->prof_set[i + 1]) NV_CUDA(cudaEventElapsedTime(&ms[i], ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+    }
+    if (n) *n = m;
+    return NV_OK;
+}
+
+extern "C" int nv_event_create(void **ev)
+{
+    if (!ev) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    cudaEvent_t e;
+    NV_CUDA(cudaEventCreate(&e));
+    *ev = e;
+    return NV_OK;
+}
+extern "C" int nv_event_record(nv_ctx *ctx, void *ev)
+{
+    if (!ctx || !ev) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    NV_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx->stream));
+    return NV_OK;
+}
+extern "C" int nv_event_elapsed_ms(void *e0, void *e1, float *ms)
+{
+    if (!e0 || !e1 || !ms) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    NV_CUDA(cudaEventSynchronize((cudaEvent_t)e1));
+    NV_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)e0, (cudaEvent_t)e1));
+    return NV_OK;
+}
+extern "C" void nv_event_destroy(void *ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
+
+// ------------------------------------------------------------------------------------------------
+// plan: scale list, level geometry (SURVEY.md A.4 + the oracle's probes), coefficient tables
+// ------------------------------------------------------------------------------------------------
+static inline int cv_round(double v) { return (int)lrint(v); }
+static inline int cv_roundf(float v) { return (int)lrintf(v); }
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+static void exact_coefs(int ssize, int dsize, int2 *tab)
+{
+    double scale = 1.0 / ((double)dsize / ssize);
+    for (int d = 0; d < dsize; d++) {
+        double f = scale * (d + 0.5) - 0.5;
+        int i = (int)floor(f);
+        if (i >= 0 && i < ssize - 1) tab[d] = make_int2(i, cv_round((f - i) * 256.0));
+        else if (i < 0) tab[d] = make_int2(0, -1);
+        else tab[d] = make_int2(ssize - 1, -1);
+    }
+}
+
+static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const nv_detect_params *p)
+{
+    if (!(p->scale_factor > 1.0)) {
+        nv_set_error("scale_factor must be > 1 (got %g): OpenCV would never terminate", p->scale_factor);
+        return NV_ERR_ARG;
+    }
+    PlanKey key;
+    key.W = W; key.H = H; key.win_w = casc->h.win_w; key.win_h = casc->h.win_h;
+    key.min_w = p->min_w; key.min_h = p->min_h; key.max_w = p->max_w; key.max_h = p->max_h; key.sf = p->scale_factor;
+    if (ctx->plan_valid && key == ctx->pkey) return NV_OK;
+
+    PlanDev &P = ctx->plan;
+    memset(&P, 0, sizeof P);
+    P.W = W; P.H = H; P.win_w = key.win_w; P.win_h = key.win_h;
+    int max_w = p->max_w, max_h = p->max_h;
+    if (max_w == 0 || max_h == 0) { max_w = W; max_h = H; }
+    std::vector<float> scales;
+    for (double f = 1;; f *= p->scale_factor) {
+        int ww = cv_round(key.win_w * f), wh = cv_round(key.win_h * f);
+        if (ww > max_w || wh > max_h || ww > W || wh > H) break;
+        if (ww < p->min_w || wh < p->min_h) continue;
+        scales.push_back((float)f);
+        if (scales.size() > 4096) break;
+    }
+    int nstripes = 1;
+    long long iofs = 0, wofs = 0, bofs = 0, tofs = 0, pofs = 0;
+    int nl = 0;
+    for (size_t k = 0; k < scales.size(); k++) {
+        float sc = scales[k];
+        int lw = cv_roundf((float)W / sc), lh = cv_roundf((float)H / sc);       // float division, as OpenCV
+        int rx = lw + 1 - key.win_w, ry = lh + 1 - key.win_h;
+        if (k == 0) nstripes = std::max((std::max(rx, 0) + 31) / 32, 1);
+        if (rx <= 0 || ry <= 0) continue;
+        int ystep = sc >= 2.f ? 1 : 2;
+        // stripe split of detectMultiScale: the last stripe is clamped, an odd tail row may be lost
+        int stripe = std::max((ry / ystep + nstripes - 1) / nstripes, 1) * ystep;
+        long long lim = (long long)stripe * nstripes;
+        if (lim < ry) ry = (int)lim;
+        if (nl >= NV_MAX_LEVELS) { nv_set_error("more than %d pyramid levels", NV_MAX_LEVELS); return NV_ERR_CAPACITY; }
+        LevelDesc &L = P.lv[nl++];
+        L.scale = sc; L.lw = lw; L.lh = lh; L.ystep = ystep;
+        L.nx = (rx + ystep - 1) / ystep; L.ny = (ry + ystep - 1) / ystep; L.nxw = (L.nx + 31) / 32;
+        if (L.nx > 8191 || L.ny > 8191) { nv_set_error("level too large for 13-bit window ids"); return NV_ERR_CAPACITY; }
+        L.iplane = align_up((lw + 1 + ystep - 1) / ystep, 4);
+        L.ipitch = L.iplane * ystep;
+        L.iofs = (int)iofs; iofs += (long long)L.ipitch * (lh + 1);
+        L.wofs = (int)wofs; wofs += (long long)L.nx * L.ny;
+        L.bofs = (int)bofs; bofs += (long long)L.nxw * L.ny;
+        L.xtab = (int)tofs; L.ytab = (int)tofs + lw; tofs += lw + lh;
+        L.pofs = (int)pofs; pofs += (long long)lw * lh;
+        L.rowblk0 = P.total_rowblk; P.total_rowblk += (lh + 7) / 8;
+        L.colblk0 = P.total_colblk; P.total_colblk += (L.ipitch + 31) / 32;
+        L.chunk0 = P.total_chunks; P.total_chunks += L.nxw * L.ny;
+        L.row0 = P.total_rows; P.total_rows += L.ny;
+        if (iofs > 0x7fffffffLL || wofs > 0x7fffffffLL) { nv_set_error("frame too large"); return NV_ERR_CAPACITY; }
+    }
+    P.nlevels = nl;
+    P.total_windows = (int)wofs;
+
+    NV_CUDA(cudaStreamSynchronize(ctx->stream));      // previous frame may still read the old plan
+    if (nl > 0) {
+        std::vector<int2> tab((size_t)tofs);
+        for (int l = 0; l < nl; l++) {
+            exact_coefs(W, P.lv[l].lw, &tab[P.lv[l].xtab]);
+            exact_coefs(H, P.lv[l].lh, &tab[P.lv[l].ytab]);
+        }
+        int rc;
+        if ((rc = ensure(&ctx->d_ptab, &ctx->ptab_cap, (size_t)tofs * 2)) != NV_OK) return rc;
+        NV_CUDA(cudaMemcpy(ctx->d_ptab, tab.data(), (size_t)tofs * sizeof(int2), cudaMemcpyHostToDevice));
+        size_t icap = ctx->integ_cap;
+        if ((rc = ensure(&ctx->d_sum, &icap, (size_t)iofs, true)) != NV_OK) return rc;
+        if ((rc = ensure(&ctx->d_sq, &ctx->integ_cap, (size_t)iofs, true)) != NV_OK) return rc;
+        size_t wcap = ctx->win_cap;
+        if ((rc = ensure(&ctx->d_vnf, &wcap, (size_t)wofs)) != NV_OK) return rc;
+        if ((rc = ensure(&ctx->d_queue, &ctx->queue_cap, (size_t)wofs)) != NV_OK) return rc;
+        ctx->win_cap = wcap;
+        size_t bcap = ctx->bits_cap;
+        if ((rc = ensure(&ctx->d_bits_fail, &bcap, (size_t)bofs)) != NV_OK) return rc;
+        if ((rc = ensure(&ctx->d_bits_ok, &ctx->bits_cap, (size_t)bofs)) != NV_OK) return rc;
+        if (ctx->debug) {
+            if ((rc = ensure(&ctx->d_depth, &ctx->depth_cap, (size_t)wofs)) != NV_OK) return rc;
+            if ((rc = ensure(&ctx->d_pyr, &ctx->pyr_cap, (size_t)pofs)) != NV_OK) return rc;
+        }
+    }
+    NV_CUDA(cudaMemcpy(ctx->d_plan, &P, sizeof(PlanDev), cudaMemcpyHostToDevice));
+    ctx->pkey = key;
+    ctx->plan_valid = true;
+    return NV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// detectMultiScale on a device-resident gray image (+ LUT), everything stream-ordered
+// ------------------------------------------------------------------------------------------------
+static int detect_on_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W, int H, int gstride,
+                            const uint8_t *d_lut, const nv_detect_params *p)
+{
+    int rc = ensure_plan(ctx, casc, W, H, p);
+    if (rc != NV_OK) return rc;
+    const DevStump *stumps; const DevCascade *meta;
+    if ((rc = cascade_on_device(casc, ctx->gpu, ctx->stream, &stumps, &meta)) != NV_OK) return rc;
+    const PlanDev &P = ctx->plan;
+    cudaStream_t st = ctx->stream;
+    int nl = 0;
+    for (int i = 2; i <= NV_NUM_STAGES; i++) ctx->prof_set[i] = false;
+    NV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int), st));
+    if (P.nlevels > 0) {
+        int16_t *depth = ctx->debug ? ctx->d_depth : nullptr;
+        prof_mark(ctx, 2);
+        NV_CUDA(launch_pyr_rowscan(ctx->d_plan, P.total_rowblk, d_gray, gstride, d_lut, ctx->d_ptab, ctx->d_sum, ctx->d_sq,
+                                   ctx->debug ? ctx->d_pyr : nullptr, st));
+        prof_mark(ctx, 3);
+        NV_CUDA(launch_colscan(ctx->d_plan, P.total_colblk, ctx->d_sum, ctx->d_sq, st));
+        prof_mark(ctx, 4);
+        NV_CUDA(launch_stage0(ctx->d_plan, P.total_chunks, meta, stumps, ctx->d_sum, ctx->d_sq, ctx->d_vnf,
+                              ctx->d_bits_fail, ctx->d_bits_ok, st));
+        prof_mark(ctx, 5);
+        NV_CUDA(launch_skip_compact(ctx->d_plan, P.total_rows, ctx->d_vnf, ctx->d_bits_fail, ctx->d_bits_ok, ctx->d_queue,
+                                    ctx->d_counters, (int)std::min<size_t>(ctx->queue_cap, 0x7fffffff), depth, st));
+        prof_mark(ctx, 6);
+        NV_CUDA(launch_queue_stages(ctx->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
+                                    ctx->cand_cap, depth, 148 * 8, st));
+        nl += 5;
+    }
+    prof_mark(ctx, 7);
+    NV_CUDA(launch_group(ctx->d_plan, ctx->d_counters, ctx->d_cand, ctx->cand_cap, ctx->d_cand_sorted, ctx->d_cand_rects,
+                         ctx->d_adj, p->min_neighbors, 0.2, W, H, ctx->d_result, ctx->result_cap, 148 * 2, st, &nl));
+    prof_mark(ctx, 8);
+    NV_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(ResultHeader) + NV_RESULT_INLINE * sizeof(nv_rect),
+                            cudaMemcpyDeviceToHost, st));
+    ctx->launches += nl;
+    ctx->last_min_neighbors = p->min_neighbors;
+    ctx->tap_gray = d_gray; ctx->tap_lut = d_lut; ctx->tap_stride = gstride;
+    ctx->pending = true;
+    return NV_OK;
+}
+
+static int collect(nv_ctx *ctx, nv_rect *out, int cap, int *n)
+{
+    if (!ctx->pending) { nv_set_error("collect without a pending submit"); return NV_ERR_STATE; }
+    NV_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->pending = false;
+    const ResultHeader *h = reinterpret_cast<const ResultHeader *>(ctx->h_result);
+    int total = h->n_out;
+    if (total > NV_RESULT_INLINE) {
+        NV_CUDA(cudaMemcpy(ctx->h_result + sizeof(ResultHeader) + NV_RESULT_INLINE * sizeof(nv_rect),
+                           ctx->d_result + sizeof(ResultHeader) + NV_RESULT_INLINE * sizeof(nv_rect),
+                           (size_t)(total - NV_RESULT_INLINE) * sizeof(nv_rect), cudaMemcpyDeviceToHost));
+    }
+    int m = std::min(total, cap);
+    if (out && m > 0) memcpy(out, ctx->h_result + sizeof(ResultHeader), (size_t)m * sizeof(nv_rect));
+    if (n) *n = m;
+    if (h->overflow) {
+        nv_set_error("internal capacity exceeded (%d raw candidates, cap %d)", h->n_cand, ctx->cand_cap);
+        return NV_ERR_CAPACITY;
+    }
+    return NV_OK;
+}
+
+static int check_frame(nv_ctx *ctx, const void *img, int w, int h, int stride, int cn)
+{
+    if (!ctx || !img) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    if (w <= 0 || h <= 0 || stride < w * cn) { nv_set_error("bad frame geometry %dx%d stride %d", w, h, stride); return NV_ERR_ARG; }
+    if (w > ctx->max_w || h > ctx->max_h || (size_t)stride * h > ctx->frame_cap) {
+        nv_set_error("frame %dx%d exceeds the context's %dx%d", w, h, ctx->max_w, ctx->max_h);
+        return NV_ERR_CAPACITY;
+    }
+    return NV_OK;
+}
+
+extern "C" int nv_detect_multiscale(nv_ctx *ctx, const nv_cascade *c, const uint8_t *gray, int width, int height,
+                                    int stride_bytes, const nv_detect_params *p, nv_rect *out, int cap, int *n)
+{
+    int rc = check_frame(ctx, gray, width, height, stride_bytes, 1);
+    if (rc != NV_OK) return rc;
+    if (!c || !p) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    if (ctx->pending) NV_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->h_frame, gray, (size_t)stride_bytes * height);
+    NV_CUDA(cudaMemcpyAsync(ctx->d_frame, ctx->h_frame, (size_t)stride_bytes * height, cudaMemcpyHostToDevice, ctx->stream));
+    rc = detect_on_device(ctx, const_cast<nv_cascade *>(c), ctx->d_frame, width, height, stride_bytes, ctx->d_lut + 256, p);
+    if (rc != NV_OK) return rc;
+    return collect(ctx, out, cap, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// face element hot block
+// ------------------------------------------------------------------------------------------------
+static int ensure_rtab(nv_ctx *ctx, int sw, int sh, int dw, int dh)
+{
+    ResizeKey k;
+    k.sw = sw; k.sh = sh; k.dw = dw; k.dh = dh;
+    if (ctx->d_rtab && k == ctx->rkey) return NV_OK;
+    std::vector<int> tab;
+    build_resize_tables(sw, sh, dw, dh, tab);
+    NV_CUDA(cudaStreamSynchronize(ctx->stream));
+    int rc = ensure(&ctx->d_rtab, &ctx->rtab_cap, tab.size());
+    if (rc != NV_OK) return rc;
+    NV_CUDA(cudaMemcpy(ctx->d_rtab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+    ctx->rkey = k;
+    return NV_OK;
+}
+
+static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, bool on_device, int width, int height,
+                            int stride, const nv_face_params *p)
+{
+    if (!ctx || !c || !bgr || !p) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    if (p->width_to_process <= 0) { nv_set_error("width_to_process must be > 0 (kmsfacedetect.cpp:304 divides by it)"); return NV_ERR_ARG; }
+    int rc;
+    if (!on_device) { if ((rc = check_frame(ctx, bgr, width, height, stride, 3)) != NV_OK) return rc; }
+    else if (width <= 0 || height <= 0 || width > ctx->max_w || height > ctx->max_h || stride < 3 * width) {
+        nv_set_error("bad device frame geometry"); return NV_ERR_ARG;
+    }
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    if (ctx->pending) NV_CUDA(cudaStreamSynchronize(ctx->stream));
+    // kmsfacedetect.cpp:304 (integer division) and :770-777
+    int iscale = width / p->width_to_process;
+    double scale = iscale;
+    int rows = height, cols = width;
+    if (iscale > 0 && cv_round(height / scale) > 0) rows = cv_round(height / scale); else scale = 1;
+    if (scale > 0 && cv_round(width / scale) > 0) cols = cv_round(width / scale); else scale = 1;
+    if ((rc = ensure_rtab(ctx, width, height, cols, rows)) != NV_OK) return rc;
+    const uint8_t *d_src = bgr;
+    if (!on_device) {
+        memcpy(ctx->h_frame, bgr, (size_t)stride * height);
+        NV_CUDA(cudaMemcpyAsync(ctx->d_frame, ctx->h_frame, (size_t)stride * height, cudaMemcpyHostToDevice, ctx->stream));
+        d_src = ctx->d_frame;
+    }
+    ctx->prof_set[0] = ctx->prof_set[1] = false;
+    prof_mark(ctx, 0);
+    NV_CUDA(launch_face_prep(d_src, width, height, stride, 3, ctx->d_gray, cols, rows, ctx->d_rtab, ctx->d_hist, ctx->stream));
+    prof_mark(ctx, 1);
+    NV_CUDA(launch_lut(ctx->d_hist, cols * rows, ctx->d_lut, ctx->stream));
+    ctx->launches += 2;
+    nv_detect_params dp;
+    dp.scale_factor = p->scale_factor; dp.min_neighbors = p->min_neighbors; dp.flags = 0;
+    dp.min_w = p->min_w < 0 ? cols / 20 : p->min_w;           // kmsfacedetect.cpp:811
+    dp.min_h = p->min_w < 0 ? rows / 20 : p->min_h;
+    dp.max_w = dp.max_h = 0;
+    return detect_on_device(ctx, const_cast<nv_cascade *>(c), ctx->d_gray, cols, rows, cols, ctx->d_lut, &dp);
+}
+
+extern "C" int nv_face_submit(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, int width, int height,
+                              int stride_bytes, const nv_face_params *p)
+{
+    return face_submit_impl(ctx, c, bgr, false, width, height, stride_bytes, p);
+}
+
+extern "C" int nv_face_submit_device(nv_ctx *ctx, const nv_cascade *c, const uint8_t *d_bgr, int width, int height,
+                                     int stride_bytes, const nv_face_params *p)
+{
+    return face_submit_impl(ctx, c, d_bgr, true, width, height, stride_bytes, p);
+}
+
+extern "C" int nv_face_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n)
+{
+    if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    return collect(ctx, out, cap, n);
+}
+
+extern "C" int nv_face_detect(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, int width, int height,
+                              int stride_bytes, const nv_face_params *p, nv_rect *out, int cap, int *n)
+{
+    int rc = nv_face_submit(ctx, c, bgr, width, height, stride_bytes, p);
+    if (rc != NV_OK) return rc;
+    return nv_face_collect(ctx, out, cap, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone image ops (host in, host out) for the nested elements
+// ------------------------------------------------------------------------------------------------
+static int upload(nv_ctx *ctx, const uint8_t *src, size_t bytes)
+{
+    if (bytes > ctx->frame_cap) { nv_set_error("image larger than the context"); return NV_ERR_CAPACITY; }
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    if (ctx->pending) { NV_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    memcpy(ctx->h_frame, src, bytes);
+    NV_CUDA(cudaMemcpyAsync(ctx->d_frame, ctx->h_frame, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return NV_OK;
+}
+
+static int download(nv_ctx *ctx, const uint8_t *d_src, int row_bytes, int rows, uint8_t *dst, int dstride)
+{
+    NV_CUDA(cudaMemcpy2DAsync(dst, dstride, d_src, row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    NV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NV_OK;
+}
+
+extern "C" int nv_bgr2gray(nv_ctx *ctx, const uint8_t *src, int width, int height, int stride_bytes, int channels,
+                           uint8_t *dst_gray, int dst_stride)
+{
+    if (channels != 3 && channels != 4) { nv_set_error("channels must be 3 or 4"); return NV_ERR_ARG; }
+    int rc = check_frame(ctx, src, width, height, stride_bytes, channels);
+    if (rc != NV_OK) return rc;
+    if (!dst_gray || dst_stride < width) { nv_set_error("bad destination"); return NV_ERR_ARG; }
+    if ((rc = upload(ctx, src, (size_t)stride_bytes * height)) != NV_OK) return rc;
+    NV_CUDA(launch_bgr2gray(ctx->d_frame, width, height, stride_bytes, channels, ctx->d_gray, width, ctx->stream));
+    ctx->launches++;
+    return download(ctx, ctx->d_gray, width, height, dst_gray, dst_stride);
+}
+
+extern "C" int nv_equalize_hist(nv_ctx *ctx, const uint8_t *src, int width, int height, int stride_bytes, uint8_t *dst,
+                                int dst_stride)
+{
+    int rc = check_frame(ctx, src, width, height, stride_bytes, 1);
+    if (rc != NV_OK) return rc;
+    if (!dst || dst_stride < width) { nv_set_error("bad destination"); return NV_ERR_ARG; }
+    if ((rc = upload(ctx, src, (size_t)stride_bytes * height)) != NV_OK) return rc;
+    NV_CUDA(launch_hist(ctx->d_frame, width, height, stride_bytes, ctx->d_hist, ctx->stream));
+    NV_CUDA(launch_lut(ctx->d_hist, width * height, ctx->d_lut, ctx->stream));
+    NV_CUDA(launch_apply_lut(ctx->d_frame, width, height, stride_bytes, ctx->d_lut, ctx->d_gray, width, ctx->stream));
+    ctx->launches += 3;
+    return download(ctx, ctx->d_gray, width, height, dst, dst_stride);
+}
+
+extern "C" int nv_resize_linear(nv_ctx *ctx, const uint8_t *src, int width, int height, int stride_bytes, int channels,
+                                uint8_t *dst, int dst_width, int dst_height, int dst_stride)
+{
+    if (channels < 1 || channels > 4) { nv_set_error("channels must be 1..4"); return NV_ERR_ARG; }
+    int rc = check_frame(ctx, src, width, height, stride_bytes, channels);
+    if (rc != NV_OK) return rc;
+    if (!dst || dst_width <= 0 || dst_height <= 0 || dst_stride < dst_width * channels) { nv_set_error("bad destination"); return NV_ERR_ARG; }
+    if ((rc = upload(ctx, src, (size_t)stride_bytes * height)) != NV_OK) return rc;
+    if ((rc = ensure_rtab(ctx, width, height, dst_width, dst_height)) != NV_OK) return rc;
+    if ((rc = ensure(&ctx->d_aux, &ctx->aux_cap, (size_t)dst_width * dst_height * channels)) != NV_OK) return rc;
+    NV_CUDA(launch_resize_linear(ctx->d_frame, width, height, stride_bytes, channels, ctx->d_aux, dst_width, dst_height,
+                                 dst_width * channels, ctx->d_rtab, ctx->stream));
+    ctx->launches++;
+    return download(ctx, ctx->d_aux, dst_width * channels, dst_height, dst, dst_stride);
+}
+
+extern "C" int nv_flip_horizontal(nv_ctx *ctx, const uint8_t *src, int width, int height, int stride_bytes, uint8_t *dst,
+                                  int dst_stride)
+{
+    int rc = check_frame(ctx, src, width, height, stride_bytes, 1);
+    if (rc != NV_OK) return rc;
+    if (!dst || dst_stride < width) { nv_set_error("bad destination"); return NV_ERR_ARG; }
+    if ((rc = upload(ctx, src, (size_t)stride_bytes * height)) != NV_OK) return rc;
+    NV_CUDA(launch_flip(ctx->d_frame, width, height, stride_bytes, ctx->d_gray, width, ctx->stream));
+    ctx->launches++;
+    return download(ctx, ctx->d_gray, width, height, dst, dst_stride);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tracker
+// ------------------------------------------------------------------------------------------------
+#define TRK_MAX_COMPONENTS 16384
+
+// gstnubotracker.cpp:119-200 — host-side, a handful of rectangles
+static float trk_calc_dist(const nv_rect &a, const nv_rect &b)
+{
+    int c1x = a.x + a.width / 2, c1y = a.y + a.height / 2, c2x = b.x + b.width / 2, c2y = b.y + b.height / 2;
+    return (float)sqrt((double)((c1x - c2x) * (c1x - c2x) + (c1y - c2y) * (c1y - c2y)));
+}
+static bool trk_inside(int px, int py, const nv_rect &r)
+{
+    return r.x <= px && px < r.x + r.width && r.y <= py && py < r.y + r.height;
+}
+static nv_rect trk_merge(const nv_rect &r1, const nv_rect &r2)
+{
+    int b1x = r1.x + r1.width, b1y = r1.y + r1.height, b2x = r2.x + r2.width, b2y = r2.y + r2.height;
+    if (trk_inside(r2.x, r2.y, r1) && trk_inside(b2x, b2y, r1)) return r1;
+    if (trk_inside(r1.x, r1.y, r2) && trk_inside(b1x, b1y, r2)) return r2;
+    nv_rect o;
+    o.x = std::min(r1.x, r2.x); o.y = std::min(r1.y, r2.y);
+    o.width = std::max(b1x, b2x) - o.x; o.height = std::max(b1y, b2y) - o.y;
+    return o;
+}
+static void trk_join_objects(std::vector<nv_rect> &v, int min_area, long max_area, int distance)
+{
+    auto area_ok = [&](const nv_rect &r) { long a = (long)r.width * r.height; return a > min_area && a < max_area; };
+    for (int a = (int)v.size() - 1; a >= 0; a--) {
+        if (area_ok(v[a])) {
+            for (int b = a - 1; b >= 0; b--)
+                if (area_ok(v[b]) && (float)distance > trk_calc_dist(v[a], v[b])) {
+                    v[b] = trk_merge(v[a], v[b]);
+                    v.erase(v.begin() + a);
+                    break;
+                }
+        } else
+            v.erase(v.begin() + a);
+    }
+}
+
+extern "C" int nv_tracker_reset(nv_ctx *ctx)
+{
+    if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }
+    ctx->trk_frames = 0;
+    if (ctx->d_trk_mhi) {
+        NV_CUDA(cudaSetDevice(ctx->gpu));
+        NV_CUDA(cudaMemsetAsync(ctx->d_trk_mhi, 0, (size_t)ctx->trk_w * ctx->trk_h * sizeof(float), ctx->stream));
+    }
+    return NV_OK;
+}
+
+extern "C" int nv_tracker_process(nv_ctx *ctx, const uint8_t *bgra, int width, int height, int stride_bytes,
+                                  double timestamp_ms, const nv_tracker_params *p, nv_rect *out, int cap, int *n)
+{
+    int rc = check_frame(ctx, bgra, width, height, stride_bytes, 4);
+    if (rc != NV_OK) return rc;
+    if (!p) { nv_set_error("null params"); return NV_ERR_ARG; }
+    if (stride_bytes % 4) { nv_set_error("BGRA stride must be a multiple of 4"); return NV_ERR_ARG; }
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    if (ctx->pending) NV_CUDA(cudaStreamSynchronize(ctx->stream));
+    size_t np = (size_t)width * height;
+    if (ctx->trk_w != width || ctx->trk_h != height) {        // (re)configure: gstnubotracker.cpp:202-237
+        NV_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_trk_prev); cudaFree(ctx->d_trk_mhi); cudaFree(ctx->d_trk_labels); cudaFree(ctx->d_trk_mask);
+        cudaFree(ctx->d_trk_boxes); cudaFree(ctx->d_trk_misc); cudaFreeHost(ctx->h_trk);
+        ctx->d_trk_prev = nullptr; ctx->d_trk_mhi = nullptr; ctx->d_trk_labels = nullptr; ctx->d_trk_mask = nullptr;
+        ctx->d_trk_boxes = nullptr; ctx->d_trk_misc = nullptr; ctx->h_trk = nullptr;
+        NV_CUDA(cudaMalloc(&ctx->d_trk_prev, np));
+        NV_CUDA(cudaMalloc(&ctx->d_trk_mhi, np * sizeof(float)));
+        NV_CUDA(cudaMemset(ctx->d_trk_mhi, 0, np * sizeof(float)));
+        NV_CUDA(cudaMalloc(&ctx->d_trk_labels, (2 * np + TRK_MAX_COMPONENTS) * sizeof(int)));
+        NV_CUDA(cudaMalloc(&ctx->d_trk_mask, np));
+        NV_CUDA(cudaMalloc(&ctx->d_trk_boxes, (np + 2 * TRK_MAX_COMPONENTS + 1) * sizeof(int4)));
+        NV_CUDA(cudaMalloc(&ctx->d_trk_misc, 4 * sizeof(int)));
+        NV_CUDA(cudaMallocHost(&ctx->h_trk, (TRK_MAX_COMPONENTS + 1) * sizeof(int4)));
+        ctx->trk_w = width; ctx->trk_h = height; ctx->trk_frames = 0;
+    }
+    memcpy(ctx->h_frame, bgra, (size_t)stride_bytes * height);
+    NV_CUDA(cudaMemcpyAsync(ctx->d_frame, ctx->h_frame, (size_t)stride_bytes * height, cudaMemcpyHostToDevice, ctx->stream));
+    int first = ctx->trk_frames == 0, nl = 0;
+    float ts = (float)timestamp_ms, del = (float)(timestamp_ms - 0.2);          // MHI_DURATION, :28
+    NV_CUDA(launch_tracker(ctx, ctx->d_frame, width, height, stride_bytes, first, ts, del, p->threshold, &nl));
+    ctx->launches += nl;
+    ctx->trk_frames++;
+    int total = 0;
+    std::vector<nv_rect> v;
+    if (!first) {
+        const int4 *d_out = ctx->d_trk_boxes + np + TRK_MAX_COMPONENTS;
+        NV_CUDA(cudaMemcpyAsync(ctx->h_trk, d_out, (1 + 1024) * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
+        NV_CUDA(cudaStreamSynchronize(ctx->stream));
+        const int4 *h = reinterpret_cast<const int4 *>(ctx->h_trk);
+        total = h[0].x;
+        int m = std::min(total, TRK_MAX_COMPONENTS);
+        if (m > 1024)
+            NV_CUDA(cudaMemcpy(ctx->h_trk + (1 + 1024) * sizeof(int4), d_out + 1 + 1024, (size_t)(m - 1024) * sizeof(int4),
+                               cudaMemcpyDeviceToHost));
+        v.resize(m);
+        for (int i = 0; i < m; i++) { v[i].x = h[1 + i].x; v[i].y = h[1 + i].y; v[i].width = h[1 + i].z; v[i].height = h[1 + i].w; }
+        trk_join_objects(v, p->min_area, p->max_area, p->distance);
+    } else
+        NV_CUDA(cudaStreamSynchronize(ctx->stream));
+    int m = std::min((int)v.size(), cap);
+    if (out && m > 0) memcpy(out, v.data(), (size_t)m * sizeof(nv_rect));
+    if (n) *n = m;
+    if (total > TRK_MAX_COMPONENTS) { nv_set_error("more than %d motion components", TRK_MAX_COMPONENTS); return NV_ERR_CAPACITY; }
+    return NV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity taps
+// ------------------------------------------------------------------------------------------------
+static int tap_ready(nv_ctx *ctx, int level, bool need_level)
+{
+    if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }
+    if (!ctx->plan_valid) { nv_set_error("no detect call has run on this context"); return NV_ERR_STATE; }
+    if (need_level && (level < 0 || level >= ctx->plan.nlevels)) { nv_set_error("level out of range"); return NV_ERR_ARG; }
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    NV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NV_OK;
+}
+
+extern "C" int nv_debug_num_levels(nv_ctx *ctx) { return ctx && ctx->plan_valid ? ctx->plan.nlevels : 0; }
+
+extern "C" int nv_debug_level_info(nv_ctx *ctx, int level, nv_level_info *info)
+{
+    if (!ctx || !info || !ctx->plan_valid || level < 0 || level >= ctx->plan.nlevels) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    const LevelDesc &L = ctx->plan.lv[level];
+    info->scale = L.scale; info->width = L.lw; info->height = L.lh; info->ystep = L.ystep; info->nx = L.nx; info->ny = L.ny;
+    return NV_OK;
+}
+
+extern "C" int nv_debug_get_gray(nv_ctx *ctx, uint8_t *dst, int cap_bytes, int *width, int *height)
+{
+    int rc = tap_ready(ctx, 0, false);
+    if (rc != NV_OK) return rc;
+    int W = ctx->plan.W, H = ctx->plan.H;
+    if (width) *width = W;
+    if (height) *height = H;
+    if (!dst || cap_bytes < W * H) { nv_set_error("destination too small"); return NV_ERR_ARG; }
+    uint8_t lut[256];
+    NV_CUDA(cudaMemcpy2D(dst, W, ctx->tap_gray, ctx->tap_stride, W, H, cudaMemcpyDeviceToHost));
+    NV_CUDA(cudaMemcpy(lut, ctx->tap_lut, 256, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < W * H; i++) dst[i] = lut[dst[i]];
+    return NV_OK;
+}
+
+extern "C" int nv_debug_get_integral(nv_ctx *ctx, int level, int32_t *sum, uint32_t *sqsum)
+{
+    int rc = tap_ready(ctx, level, true);
+    if (rc != NV_OK) return rc;
+    const LevelDesc &L = ctx->plan.lv[level];
+    size_t ne = (size_t)L.ipitch * (L.lh + 1);
+    std::vector<uint32_t> tmp(ne);
+    for (int a = 0; a < 2; a++) {
+        uint32_t *dst = a == 0 ? reinterpret_cast<uint32_t *>(sum) : sqsum;
+        if (!dst) continue;
+        NV_CUDA(cudaMemcpy(tmp.data(), (a == 0 ? ctx->d_sum : ctx->d_sq) + L.iofs, ne * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (int r = 0; r <= L.lh; r++)
+            for (int c = 0; c <= L.lw; c++) {
+                int pc = L.ystep == 2 ? (c & 1) * L.iplane + (c >> 1) : c;
+                dst[(size_t)r * (L.lw + 1) + c] = tmp[(size_t)r * L.ipitch + pc];
+            }
+    }
+    return NV_OK;
+}
+
+extern "C" int nv_debug_get_depth_map(nv_ctx *ctx, int level, int16_t *depth)
+{
+    int rc = tap_ready(ctx, level, true);
+    if (rc != NV_OK) return rc;
+    if (!ctx->debug || !ctx->d_depth || !depth) { nv_set_error("depth maps need nv_ctx_set_debug(ctx, 1) before the detect call"); return NV_ERR_STATE; }
+    const LevelDesc &L = ctx->plan.lv[level];
+    NV_CUDA(cudaMemcpy(depth, ctx->d_depth + L.wofs, (size_t)L.nx * L.ny * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    return NV_OK;
+}
+
+extern "C" int nv_debug_get_candidates(nv_ctx *ctx, nv_rect *out, int cap, int *n)
+{
+    int rc = tap_ready(ctx, 0, false);
+    if (rc != NV_OK) return rc;
+    const ResultHeader *h = reinterpret_cast<const ResultHeader *>(ctx->h_result);
+    int m = std::min(std::min(h->n_cand, ctx->cand_cap), cap);
+    if (out && m > 0) NV_CUDA(cudaMemcpy(out, ctx->d_cand_rects, (size_t)m * sizeof(nv_rect), cudaMemcpyDeviceToHost));
+    if (n) *n = m;
+    return NV_OK;
+}
+
+extern "C" int nv_debug_get_counters(nv_ctx *ctx, long long *o)
+{
+    if (!ctx || !o) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    const ResultHeader *h = reinterpret_cast<const ResultHeader *>(ctx->h_result);
+    memset(o, 0, 8 * sizeof(long long));
+    o[0] = ctx->plan_valid ? ctx->plan.total_windows : 0;
+    o[1] = h ? h->n_alive : 0;
+    o[2] = h ? h->n_cand : 0;
+    o[3] = ctx->launches;
+    return NV_OK;
+}

@@ -1,0 +1,218 @@
+// internal.h — shared declarations of libnubovca (not part of the public C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "nubovca.h"
+
+#define NV_MAX_LEVELS 64          // level index is packed in 6 bits of a window id
+#define NV_MAX_STAGES 64
+#define NV_RESULT_INLINE 1024     // rects copied back with the header in one D2H
+
+// ----------------------------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------------------------
+void nv_set_error(const char *fmt, ...);
+#define NV_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            nv_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return NV_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// cascade model
+// ----------------------------------------------------------------------------------------------
+struct HostCascade {
+    int win_w = 0, win_h = 0;
+    std::vector<int> stage_ntrees;
+    std::vector<float> stage_thr;          // raw XML thresholds
+    std::vector<int> stump_feat;
+    std::vector<float> stump_thr, stump_left, stump_right;
+    std::vector<int> feat_rect;            // nfeatures * 12 : x,y,w,h for 3 rects (w==0: unused)
+    std::vector<float> feat_weight;        // nfeatures * 3
+    int n3rect = 0;
+    int order_free = 0;
+};
+
+int nv_parse_cascade_xml(const char *path, HostCascade *out);   // cascade_xml.cpp
+
+// One weak classifier as the kernels read it: 48 bytes = 3 x 16-byte loads, warp-uniform.
+struct __align__(16) DevStump {
+    uint32_t r[3];      // x | y<<8 | w<<16 | h<<24
+    float w[3];         // w[2]==0: two-rect feature
+    float thr, left, right;
+    uint32_t pad[3];
+};
+
+struct DevCascade {
+    int win_w, win_h, nstages, nstumps;
+    int stage_first[NV_MAX_STAGES + 1];   // prefix of stump counts
+    float stage_thr[NV_MAX_STAGES];       // (float)xml - 1e-5f
+};
+
+struct nv_cascade {
+    HostCascade h;
+    std::vector<DevStump> stumps;
+    DevCascade meta;
+    std::mutex mu;
+    std::map<int, DevStump *> d_stumps;   // per GPU ordinal
+    std::map<int, DevCascade *> d_meta;
+};
+
+// ----------------------------------------------------------------------------------------------
+// per-frame plan (host builds it once per (size, cascade window, parameters) key)
+// ----------------------------------------------------------------------------------------------
+struct LevelDesc {
+    float scale;
+    int lw, lh;            // level image size
+    int ystep;             // 1 or 2; also the column de-interleave factor of the integral layout
+    int nx, ny, nxw;       // window grid (after the stripe row limit), nxw = ceil(nx/32)
+    int ipitch;            // integral row pitch, elements (all planes)
+    int iplane;            // plane width, elements: physical col = (c % ystep) * iplane + c / ystep
+    int iofs;              // element offset of this level in the sum / sqsum buffers
+    int wofs;              // offset into per-window arrays (vnf, depth)
+    int bofs;              // offset into per-32-window bit-word arrays
+    int xtab, ytab;        // offsets into the pyramid coefficient tables
+    int pofs;              // byte offset of the u8 level image (debug)
+    int rowblk0;           // first row-block (8 rows) of this level in k_pyr_rowscan's grid
+    int colblk0;           // first column-block (32 physical cols) in k_colscan's grid (per array)
+    int chunk0;            // first 32-window chunk in k_stage0's grid
+    int row0;              // first window row in k_skip_compact's grid
+};
+
+struct PlanDev {
+    int nlevels;
+    int W, H;              // processing-size image (the pyramid base)
+    int win_w, win_h;
+    int total_rowblk, total_colblk, total_chunks, total_rows, total_windows;
+    LevelDesc lv[NV_MAX_LEVELS];
+};
+
+struct PlanKey {
+    int W = 0, H = 0, win_w = 0, win_h = 0, min_w = 0, min_h = 0, max_w = 0, max_h = 0;
+    double sf = 0;
+    bool operator==(const PlanKey &o) const {
+        return W == o.W && H == o.H && win_w == o.win_w && win_h == o.win_h && min_w == o.min_w &&
+               min_h == o.min_h && max_w == o.max_w && max_h == o.max_h && sf == o.sf;
+    }
+};
+
+// resize tables for cv::resize(INTER_LINEAR) (element-level resize, A.2)
+struct ResizeKey {
+    int sw = 0, sh = 0, dw = 0, dh = 0;
+    bool operator==(const ResizeKey &o) const { return sw == o.sw && sh == o.sh && dw == o.dw && dh == o.dh; }
+};
+
+// header of the device result block (then rects follow)
+struct ResultHeader {
+    int n_out;          // rects written after grouping + clipping
+    int n_cand;         // raw candidates (before the cap)
+    int n_alive;        // windows alive after stage 0 + skip rule
+    int overflow;       // 1 if a capacity was hit
+};
+
+struct nv_ctx {
+    int gpu = 0;
+    int max_w = 0, max_h = 0;
+    int debug = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_done = nullptr;
+
+    // pinned staging + device frame
+    uint8_t *h_frame = nullptr;  size_t frame_cap = 0;     // pinned
+    uint8_t *d_frame = nullptr;
+    // processing-size gray (before equalisation) and its histogram / LUT
+    uint8_t *d_gray = nullptr;   size_t gray_cap = 0;
+    int *d_hist = nullptr;       // 256
+    uint8_t *d_lut = nullptr;    // 256
+    uint8_t *d_aux = nullptr;    size_t aux_cap = 0;       // scratch image for standalone ops
+
+    // resize tables (element-level resize)
+    ResizeKey rkey;
+    int *d_rtab = nullptr;       size_t rtab_cap = 0;
+
+    // plan
+    PlanKey pkey;  bool plan_valid = false;
+    PlanDev plan;                                            // host copy
+    PlanDev *d_plan = nullptr;
+    int *d_ptab = nullptr;       size_t ptab_cap = 0;       // pyramid coefficient tables
+    uint32_t *d_sum = nullptr, *d_sq = nullptr;  size_t integ_cap = 0;   // elements
+    uint8_t *d_pyr = nullptr;    size_t pyr_cap = 0;        // debug level images
+    float *d_vnf = nullptr;      size_t win_cap = 0;
+    int16_t *d_depth = nullptr;  size_t depth_cap = 0;      // debug only
+    uint32_t *d_bits_fail = nullptr, *d_bits_ok = nullptr;  size_t bits_cap = 0;
+    uint2 *d_queue = nullptr;    size_t queue_cap = 0;
+    int *d_counters = nullptr;                              // [0] queue count, [1] cand count, [2] overflow
+    uint32_t *d_cand = nullptr;  int cand_cap = 0;          // packed window ids
+    uint32_t *d_cand_sorted = nullptr;
+    int4 *d_cand_rects = nullptr;
+    uint32_t *d_adj = nullptr;   size_t adj_cap = 0;
+    uint8_t *d_result = nullptr; uint8_t *h_result = nullptr;   // ResultHeader + rects
+    int result_cap = 0;                                     // rects
+
+    // last-call bookkeeping
+    const uint8_t *tap_gray = nullptr, *tap_lut = nullptr;  int tap_stride = 0;
+    bool pending = false;
+    int profile = 0;  cudaEvent_t prof_ev[NV_NUM_STAGES + 1] = {};  bool prof_set[NV_NUM_STAGES + 1] = {};
+    int last_min_neighbors = 0;
+    long long launches = 0;
+
+    // tracker state (gstnubotracker.cpp:88-106 priv + the file-static img_prev :108, made per-ctx)
+    uint8_t *d_trk_prev = nullptr;  float *d_trk_mhi = nullptr;  int *d_trk_labels = nullptr;
+    uint8_t *d_trk_mask = nullptr;  int4 *d_trk_boxes = nullptr;  int *d_trk_misc = nullptr;
+    int trk_w = 0, trk_h = 0;  long long trk_frames = 0;
+    uint8_t *h_trk = nullptr;
+};
+
+// ----------------------------------------------------------------------------------------------
+// kernel launchers (each returns cudaGetLastError())
+// ----------------------------------------------------------------------------------------------
+// kernels_prep.cu
+cudaError_t launch_face_prep(const uint8_t *src, int sw, int sh, int sstride, int cn, uint8_t *gray, int dw, int dh,
+                             const int *rtab, int *hist, cudaStream_t st);
+cudaError_t launch_bgr2gray(const uint8_t *src, int w, int h, int sstride, int cn, uint8_t *dst, int dstride,
+                            cudaStream_t st);
+cudaError_t launch_resize_linear(const uint8_t *src, int sw, int sh, int sstride, int cn, uint8_t *dst, int dw, int dh,
+                                 int dstride, const int *rtab, cudaStream_t st);
+cudaError_t launch_hist(const uint8_t *src, int w, int h, int stride, int *hist, cudaStream_t st);
+cudaError_t launch_lut(int *hist, int total, uint8_t *lut, cudaStream_t st);
+cudaError_t launch_apply_lut(const uint8_t *src, int w, int h, int sstride, const uint8_t *lut, uint8_t *dst, int dstride,
+                             cudaStream_t st);
+cudaError_t launch_flip(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride, cudaStream_t st);
+// host-side table builders (exact OpenCV coefficient arithmetic)
+void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<int> &tab);
+// layout of rtab: [0]=mode(0 copy,1 box2,2 linear); then xofs[dw], xa[dw] (a0 | a1<<16), y0[dh], y1[dh], yb[dh]
+enum { RT_COPY = 0, RT_BOX2 = 1, RT_LINEAR = 2 };
+
+// kernels_pyramid.cu
+cudaError_t launch_pyr_rowscan(const PlanDev *plan, int total_rowblk, const uint8_t *gray, int gstride, const uint8_t *lut,
+                               const int *ptab, uint32_t *sum, uint32_t *sq, uint8_t *pyr_debug, cudaStream_t st);
+cudaError_t launch_colscan(const PlanDev *plan, int total_colblk, uint32_t *sum, uint32_t *sq, cudaStream_t st);
+
+// kernels_cascade.cu
+cudaError_t launch_stage0(const PlanDev *plan, int total_chunks, const DevCascade *meta, const DevStump *stumps,
+                          const uint32_t *sum, const uint32_t *sq, float *vnf, uint32_t *bits_fail, uint32_t *bits_ok,
+                          cudaStream_t st);
+cudaError_t launch_skip_compact(const PlanDev *plan, int total_rows, const float *vnf, const uint32_t *bits_fail,
+                                const uint32_t *bits_ok, uint2 *queue, int *counters, int queue_cap, int16_t *depth,
+                                cudaStream_t st);
+cudaError_t launch_queue_stages(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,
+                                const uint2 *queue, int *counters, uint32_t *cand, int cand_cap, int16_t *depth,
+                                int nblocks, cudaStream_t st);
+
+// kernels_group.cu
+cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *cand, int cand_cap, uint32_t *cand_sorted,
+                         int4 *cand_rects, uint32_t *adj, int min_neighbors, double eps, int img_w, int img_h,
+                         uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch);
+
+// kernels_tracker.cu
+cudaError_t launch_tracker(nv_ctx *ctx, const uint8_t *d_bgra, int w, int h, int stride, int first, float ts, float del,
+                           int thr, int *nlaunch);

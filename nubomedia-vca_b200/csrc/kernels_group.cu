@@ -1,0 +1,214 @@
+// kernels_group.cu — K8: on-device cv::groupRectangles(minNeighbors, 0.2) + the final clip of
+// CascadeClassifier::detectMultiScale (call sites kmsfacedetect.cpp:809-811 etc.).
+//
+// cv::partition's class labels depend only on the connected components of the SimilarRects graph and on
+// the order of first members, so the union-find with rank is replaced by: canonical ordering of the
+// candidates (rank sort on the packed window id = scale -> y -> x, OpenCV's single-thread order), an
+// adjacency bit-matrix built by many blocks, then min-label propagation in one block.
+#include "internal.h"
+
+__device__ __forceinline__ bool similar_rects(const int4 &a, const int4 &b, double eps)
+{
+    double delta = eps * (double)(min(a.z, b.z) + min(a.w, b.w)) * 0.5;
+    return (double)abs(a.x - b.x) <= delta && (double)abs(a.y - b.y) <= delta &&
+           (double)abs(a.x + a.z - b.x - b.z) <= delta && (double)abs(a.y + a.w - b.y - b.w) <= delta;
+}
+
+// rank sort + candidate rectangles (A.6: cvRound of FLOAT products)
+__global__ void __launch_bounds__(256)
+k_cand_sort(const PlanDev *__restrict__ plan, const int *__restrict__ counters, const uint32_t *__restrict__ cand,
+            int cand_cap, uint32_t *__restrict__ sorted, int4 *__restrict__ rects)
+{
+    int n = min(counters[1], cand_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t key = cand[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) rank += __ldg(cand + j) < key;
+        int l = key >> 26, iy = (key >> 13) & 8191, ix = key & 8191;
+        const LevelDesc &L = plan->lv[l];
+        float sc = L.scale;
+        int4 r;
+        r.x = __float2int_rn(__fmul_rn(__int2float_rn(ix * L.ystep), sc));
+        r.y = __float2int_rn(__fmul_rn(__int2float_rn(iy * L.ystep), sc));
+        r.z = __float2int_rn(__fmul_rn(__int2float_rn(plan->win_w), sc));
+        r.w = __float2int_rn(__fmul_rn(__int2float_rn(plan->win_h), sc));
+        sorted[rank] = key;
+        rects[rank] = r;
+    }
+}
+
+// adjacency bit-matrix: word (i, w) holds the similarity of candidate i with candidates 32w .. 32w+31
+__global__ void __launch_bounds__(256)
+k_adj(const int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects, uint32_t *__restrict__ adj,
+      double eps)
+{
+    int n = min(counters[1], cand_cap), nw = (n + 31) >> 5;
+    long long total = (long long)n * nw;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(t / nw), w = (int)(t - (long long)i * nw);
+        int4 a = rects[i];
+        uint32_t m = 0;
+        int j0 = w * 32, j1 = min(n, j0 + 32);
+        for (int j = j0; j < j1; j++)
+            if (j != i && similar_rects(a, rects[j], eps)) m |= 1u << (j - j0);
+        adj[t] = m;
+    }
+}
+
+// exclusive rank of a 0/1 flag across a 1024-thread block, with a running carry
+__device__ __forceinline__ int block_flag_rank(bool flag, int &carry, int *s_warp)
+{
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int k = 0; k < 32; k++) { int c = s_warp[k]; if (k < warp) before += c; total += c; }
+    int pos = carry + before + __popc(m & ((1u << lane) - 1u));
+    carry += total;
+    __syncthreads();
+    return pos;
+}
+
+// grp scratch layout (ints): label[cap] | cls[cap] | acc[5*cap] (x,y,w,h,count) | keep[cap]
+__global__ void __launch_bounds__(1024)
+k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects, const uint32_t *__restrict__ adj,
+        int *__restrict__ grp, int min_neighbors, double eps, int img_w, int img_h, uint8_t *__restrict__ result,
+        int result_cap)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_changed;
+    int tid = threadIdx.x;
+    int n = min(counters[1], cand_cap), nw = (n + 31) >> 5;
+    ResultHeader *hdr = reinterpret_cast<ResultHeader *>(result);
+    int4 *out = reinterpret_cast<int4 *>(result + sizeof(ResultHeader));
+    volatile int *label = grp;
+    int *cls = grp + cand_cap, *acc = grp + 2 * cand_cap, *keep = grp + 7 * cand_cap;
+    int nout = 0;
+
+    if (min_neighbors <= 0) {
+        // no grouping: canonical-order candidates, clipped; empty intersections are dropped (A.8)
+        int carry = 0;
+        for (int i0 = 0; i0 < n; i0 += 1024) {
+            int i = i0 + tid;
+            int4 r = make_int4(0, 0, 0, 0);
+            bool k = false;
+            if (i < n) {
+                r = rects[i];
+                int x0 = max(r.x, 0), y0 = max(r.y, 0), x1 = min(r.x + r.z, img_w), y1 = min(r.y + r.w, img_h);
+                k = x1 > x0 && y1 > y0;
+                r = make_int4(x0, y0, x1 - x0, y1 - y0);
+            }
+            int pos = block_flag_rank(k, carry, s_warp);
+            if (k && pos < result_cap) out[pos] = r;
+        }
+        nout = carry;
+    } else {
+        for (int i = tid; i < n; i += 1024) label[i] = i;
+        __syncthreads();
+        // min-label propagation over the similarity graph until a fixed point
+        for (;;) {
+            if (tid == 0) s_changed = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += 1024) {
+                int m = label[i];
+                const uint32_t *row = adj + (size_t)i * nw;
+                for (int w = 0; w < nw; w++) {
+                    uint32_t b = row[w];
+                    while (b) {
+                        int j = w * 32 + __ffs(b) - 1;
+                        b &= b - 1;
+                        m = min(m, label[j]);
+                    }
+                }
+                m = min(m, label[m]);
+                if (m < label[i]) { label[i] = m; s_changed = 1; }
+            }
+            __syncthreads();
+            int ch = s_changed;
+            __syncthreads();
+            if (!ch) break;
+        }
+        // classes numbered by their first member (= the component's minimum index)
+        int carry = 0;
+        for (int i0 = 0; i0 < n; i0 += 1024) {
+            int i = i0 + tid;
+            bool root = i < n && label[i] == i;
+            int pos = block_flag_rank(root, carry, s_warp);
+            if (root) cls[i] = pos;
+        }
+        int ncls = carry;
+        for (int i = tid; i < 5 * ncls; i += 1024) acc[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += 1024) {
+            int c = cls[label[i]];
+            int4 r = rects[i];
+            atomicAdd(&acc[5 * c + 0], r.x); atomicAdd(&acc[5 * c + 1], r.y);
+            atomicAdd(&acc[5 * c + 2], r.z); atomicAdd(&acc[5 * c + 3], r.w);
+            atomicAdd(&acc[5 * c + 4], 1);
+        }
+        __syncthreads();
+        for (int c = tid; c < ncls; c += 1024) {
+            float s = __fdiv_rn(1.f, __int2float_rn(acc[5 * c + 4]));
+            for (int k = 0; k < 4; k++) acc[5 * c + k] = __float2int_rn(__fmul_rn(__int2float_rn(acc[5 * c + k]), s));
+        }
+        __syncthreads();
+        for (int i = tid; i < ncls; i += 1024) {
+            int n1 = acc[5 * i + 4];
+            bool k = n1 > min_neighbors;
+            if (k) {
+                int x1 = acc[5 * i], y1 = acc[5 * i + 1], w1 = acc[5 * i + 2], h1 = acc[5 * i + 3];
+                for (int j = 0; j < ncls; j++) {
+                    int n2 = acc[5 * j + 4];
+                    if (j == i || n2 <= min_neighbors) continue;
+                    int x2 = acc[5 * j], y2 = acc[5 * j + 1], w2 = acc[5 * j + 2], h2 = acc[5 * j + 3];
+                    int dx = __double2int_rn(__dmul_rn((double)w2, eps)), dy = __double2int_rn(__dmul_rn((double)h2, eps));
+                    if (x1 >= x2 - dx && y1 >= y2 - dy && x1 + w1 <= x2 + w2 + dx && y1 + h1 <= y2 + h2 + dy &&
+                        (n2 > max(3, n1) || n1 < 3)) { k = false; break; }
+                }
+            }
+            keep[i] = k;
+        }
+        __syncthreads();
+        carry = 0;
+        for (int i0 = 0; i0 < ncls; i0 += 1024) {
+            int i = i0 + tid;
+            bool k = false;
+            int4 r = make_int4(0, 0, 0, 0);
+            if (i < ncls && keep[i]) {
+                int x0 = max(acc[5 * i], 0), y0 = max(acc[5 * i + 1], 0);
+                int x1 = min(acc[5 * i] + acc[5 * i + 2], img_w), y1 = min(acc[5 * i + 1] + acc[5 * i + 3], img_h);
+                k = x1 > x0 && y1 > y0;
+                r = make_int4(x0, y0, x1 - x0, y1 - y0);
+            }
+            int pos = block_flag_rank(k, carry, s_warp);
+            if (k && pos < result_cap) out[pos] = r;
+        }
+        nout = carry;
+    }
+    if (tid == 0) {
+        hdr->n_out = min(nout, result_cap);
+        hdr->n_cand = counters[1];
+        hdr->n_alive = counters[0];
+        hdr->overflow = counters[2] | (nout > result_cap) | (counters[1] > cand_cap);
+    }
+}
+
+cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *cand, int cand_cap, uint32_t *cand_sorted,
+                         int4 *cand_rects, uint32_t *adj, int min_neighbors, double eps, int img_w, int img_h,
+                         uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch)
+{
+    // adj buffer: [bit-matrix words: cap * cap/32][group scratch ints: 8 * cap]
+    size_t adj_words = (size_t)cand_cap * ((cand_cap + 31) / 32);
+    int *grp = reinterpret_cast<int *>(adj + adj_words);
+    k_cand_sort<<<nblocks, 256, 0, st>>>(plan, counters, cand, cand_cap, cand_sorted, cand_rects);
+    (*nlaunch)++;
+    if (min_neighbors > 0) {
+        k_adj<<<nblocks, 256, 0, st>>>(counters, cand_cap, cand_rects, adj, eps);
+        (*nlaunch)++;
+    }
+    k_group<<<1, 1024, 0, st>>>(counters, cand_cap, cand_rects, adj, grp, min_neighbors, eps, img_w, img_h, result,
+                                result_cap);
+    (*nlaunch)++;
+    return cudaGetLastError();
+}

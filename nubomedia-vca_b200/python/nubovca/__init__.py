@@ -1,0 +1,327 @@
+"""ctypes binding of libnubovca.so (include/nubovca.h) for tests and bench.py.
+
+The product is the C-ABI library; this module only marshals numpy arrays across it.  There is no
+CPU implementation behind it: if the shared library is missing the import fails, and without a
+CUDA device every compute call raises NuboError(NV_ERR_NO_DEVICE).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+LIB_PATH = os.path.join(_PKG, "lib", "libnubovca.so")
+CASCADE_DIR = os.path.join(_PKG, "cascades")
+
+NV_OK = 0
+NV_ERR_NO_DEVICE = -7
+DEPTH_PASS, DEPTH_VARREJ, DEPTH_SKIPPED = 1, -100, -32768
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} is missing: build it with `make -C {_PKG}` (or __graft_entry__.build()); "
+                      "nubovca has no CPU fallback")
+
+_lib = C.CDLL(LIB_PATH)
+
+
+class Rect(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("width", C.c_int), ("height", C.c_int)]
+
+
+class CascadeInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("win_w", "win_h", "nstages", "nstumps", "nfeatures", "n3rect", "order_free_sums")]
+
+
+class DetectParams(C.Structure):
+    _fields_ = [("scale_factor", C.c_double), ("min_neighbors", C.c_int), ("flags", C.c_int), ("min_w", C.c_int),
+                ("min_h", C.c_int), ("max_w", C.c_int), ("max_h", C.c_int)]
+
+
+class FaceParams(C.Structure):
+    _fields_ = [("width_to_process", C.c_int), ("scale_factor", C.c_double), ("min_neighbors", C.c_int),
+                ("min_w", C.c_int), ("min_h", C.c_int)]
+
+
+class TrackerParams(C.Structure):
+    _fields_ = [("threshold", C.c_int), ("min_area", C.c_int), ("max_area", C.c_long), ("distance", C.c_int)]
+
+
+class LevelInfo(C.Structure):
+    _fields_ = [("scale", C.c_float), ("width", C.c_int), ("height", C.c_int), ("ystep", C.c_int), ("nx", C.c_int),
+                ("ny", C.c_int)]
+
+
+_vp, _i, _ip = C.c_void_p, C.c_int, C.POINTER(C.c_int)
+_SIGS = {
+    "nv_version": (C.c_char_p, []),
+    "nv_last_error": (C.c_char_p, []),
+    "nv_device_count": (_i, []),
+    "nv_cascade_load": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "nv_cascade_get_info": (_i, [_vp, C.POINTER(CascadeInfo)]),
+    "nv_cascade_free": (None, [_vp]),
+    "nv_ctx_create": (_i, [_i, _i, _i, C.POINTER(_vp)]),
+    "nv_ctx_destroy": (None, [_vp]),
+    "nv_ctx_set_debug": (_i, [_vp, _i]),
+    "nv_detect_multiscale": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(DetectParams), _vp, _i, _ip]),
+    "nv_face_detect": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(FaceParams), _vp, _i, _ip]),
+    "nv_face_submit": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(FaceParams)]),
+    "nv_face_submit_device": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(FaceParams)]),
+    "nv_face_collect": (_i, [_vp, _vp, _i, _ip]),
+    "nv_tracker_process": (_i, [_vp, _vp, _i, _i, _i, C.c_double, C.POINTER(TrackerParams), _vp, _i, _ip]),
+    "nv_tracker_reset": (_i, [_vp]),
+    "nv_bgr2gray": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i]),
+    "nv_equalize_hist": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
+    "nv_resize_linear": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i]),
+    "nv_flip_horizontal": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
+    "nv_stage_name": (C.c_char_p, [_i]),
+    "nv_ctx_set_profile": (_i, [_vp, _i]),
+    "nv_ctx_get_stage_times": (_i, [_vp, C.POINTER(C.c_float), _i, _ip]),
+    "nv_event_create": (_i, [C.POINTER(_vp)]),
+    "nv_event_record": (_i, [_vp, _vp]),
+    "nv_event_elapsed_ms": (_i, [_vp, _vp, C.POINTER(C.c_float)]),
+    "nv_event_destroy": (None, [_vp]),
+    "nv_debug_cascade_stage": (_i, [_vp, _i, _ip, C.POINTER(C.c_float)]),
+    "nv_debug_cascade_stump": (_i, [_vp, _i, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "nv_debug_num_levels": (_i, [_vp]),
+    "nv_debug_level_info": (_i, [_vp, _i, C.POINTER(LevelInfo)]),
+    "nv_debug_get_gray": (_i, [_vp, _vp, _i, _ip, _ip]),
+    "nv_debug_get_integral": (_i, [_vp, _i, _vp, _vp]),
+    "nv_debug_get_depth_map": (_i, [_vp, _i, _vp]),
+    "nv_debug_get_candidates": (_i, [_vp, _vp, _i, _ip]),
+    "nv_debug_get_counters": (_i, [_vp, C.POINTER(C.c_longlong)]),
+}
+EXPORTS = sorted(_SIGS)
+for _name, (_res, _args) in _SIGS.items():
+    _f = getattr(_lib, _name)          # AttributeError here = a declared symbol is not exported
+    _f.restype, _f.argtypes = _res, _args
+
+
+class NuboError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        super().__init__(f"{where}: nv_status {code}: {_lib.nv_last_error().decode(errors='replace')}")
+
+
+def _check(rc, where):
+    if rc != NV_OK:
+        raise NuboError(rc, where)
+
+
+def version() -> str:
+    return _lib.nv_version().decode()
+
+
+def device_count() -> int:
+    return _lib.nv_device_count()
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _rects(buf, n):
+    return np.frombuffer(buf, dtype=np.int32, count=4 * n).reshape(n, 4).copy()
+
+
+NUM_STAGES = 8
+STAGE_NAMES = [_lib.nv_stage_name(i).decode() for i in range(NUM_STAGES)]
+
+
+class Event:
+    """A CUDA event recorded on a context's own stream (torch.cuda.Event only sees torch's stream)."""
+
+    def __init__(self):
+        self.handle = _vp()
+        _check(_lib.nv_event_create(C.byref(self.handle)), "nv_event_create")
+
+    def elapsed_ms(self, end: "Event") -> float:
+        ms = C.c_float(0)
+        _check(_lib.nv_event_elapsed_ms(self.handle, end.handle, C.byref(ms)), "nv_event_elapsed_ms")
+        return ms.value
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            _lib.nv_event_destroy(self.handle)
+            self.handle = None
+
+
+class Cascade:
+    """cv::CascadeClassifier::load replacement (kmsfacedetect.cpp:163-177)."""
+
+    def __init__(self, path: str):
+        if not os.path.isabs(path) and not os.path.exists(path):
+            path = os.path.join(CASCADE_DIR, path)
+        self.handle = _vp()
+        _check(_lib.nv_cascade_load(path.encode(), C.byref(self.handle)), f"nv_cascade_load({path})")
+        self.info = CascadeInfo()
+        _check(_lib.nv_cascade_get_info(self.handle, C.byref(self.info)), "nv_cascade_get_info")
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            _lib.nv_cascade_free(self.handle)
+            self.handle = None
+
+    def stage(self, s):
+        nt, thr = C.c_int(0), C.c_float(0)
+        _check(_lib.nv_debug_cascade_stage(self.handle, s, C.byref(nt), C.byref(thr)), "nv_debug_cascade_stage")
+        return nt.value, np.float32(thr.value)
+
+    def stump(self, i):
+        r, w, t = (C.c_int * 12)(), (C.c_float * 3)(), (C.c_float * 3)()
+        _check(_lib.nv_debug_cascade_stump(self.handle, i, r, w, t), "nv_debug_cascade_stump")
+        return np.array(r[:], np.int32).reshape(3, 4), np.array(w[:], np.float32), np.array(t[:], np.float32)
+
+
+class Context:
+    """One per element instance / video stream."""
+
+    def __init__(self, gpu: int = 0, max_width: int = 1920, max_height: int = 1080, debug: bool = False):
+        self.handle = _vp()
+        _check(_lib.nv_ctx_create(gpu, max_width, max_height, C.byref(self.handle)), "nv_ctx_create")
+        self._cap = 16384
+        self._out = (Rect * self._cap)()
+        if debug:
+            self.set_debug(True)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.nv_ctx_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def set_debug(self, on: bool):
+        _check(_lib.nv_ctx_set_debug(self.handle, int(on)), "nv_ctx_set_debug")
+
+    # ---- device-side timing ------------------------------------------------------------------
+    def set_profile(self, on: bool):
+        _check(_lib.nv_ctx_set_profile(self.handle, int(on)), "nv_ctx_set_profile")
+
+    def stage_times(self):
+        """{stage name: ms} of the last collected detect call (CUDA events on this ctx's stream)."""
+        ms = (C.c_float * NUM_STAGES)(); n = C.c_int(0)
+        _check(_lib.nv_ctx_get_stage_times(self.handle, ms, NUM_STAGES, C.byref(n)), "nv_ctx_get_stage_times")
+        return {STAGE_NAMES[i]: ms[i] for i in range(n.value)}
+
+    def record(self, ev: "Event"):
+        _check(_lib.nv_event_record(self.handle, ev.handle), "nv_event_record")
+
+    # ---- detection -------------------------------------------------------------------------
+    def detect_multiscale(self, casc: Cascade, gray, scale_factor=1.1, min_neighbors=3, min_size=(0, 0), max_size=(0, 0)):
+        gray = _u8(gray); h, w = gray.shape
+        p = DetectParams(scale_factor, min_neighbors, 0, min_size[0], min_size[1], max_size[0], max_size[1])
+        n = C.c_int(0)
+        _check(_lib.nv_detect_multiscale(self.handle, casc.handle, _p(gray), w, h, gray.strides[0], C.byref(p),
+                                         self._out, self._cap, C.byref(n)), "nv_detect_multiscale")
+        return _rects(self._out, n.value)
+
+    @staticmethod
+    def _face_params(width_to_process, scale_factor, min_neighbors, min_size):
+        mw, mh = (-1, -1) if min_size is None else min_size
+        return FaceParams(width_to_process, scale_factor, min_neighbors, mw, mh)
+
+    def face_detect(self, casc: Cascade, bgr, width_to_process=160, scale_factor=1.25, min_neighbors=3, min_size=None):
+        bgr = _u8(bgr); h, w, _ = bgr.shape
+        p = self._face_params(width_to_process, scale_factor, min_neighbors, min_size)
+        n = C.c_int(0)
+        _check(_lib.nv_face_detect(self.handle, casc.handle, _p(bgr), w, h, bgr.strides[0], C.byref(p), self._out,
+                                   self._cap, C.byref(n)), "nv_face_detect")
+        return _rects(self._out, n.value)
+
+    def face_submit(self, casc: Cascade, bgr, width_to_process=160, scale_factor=1.25, min_neighbors=3, min_size=None):
+        h, w, _ = bgr.shape
+        p = self._face_params(width_to_process, scale_factor, min_neighbors, min_size)
+        _check(_lib.nv_face_submit(self.handle, casc.handle, _p(bgr), w, h, bgr.strides[0], C.byref(p)), "nv_face_submit")
+
+    def face_submit_device(self, casc: Cascade, dev_ptr: int, w: int, h: int, stride: int, width_to_process=160,
+                           scale_factor=1.25, min_neighbors=3, min_size=None):
+        p = self._face_params(width_to_process, scale_factor, min_neighbors, min_size)
+        _check(_lib.nv_face_submit_device(self.handle, casc.handle, _vp(dev_ptr), w, h, stride, C.byref(p)),
+               "nv_face_submit_device")
+
+    def face_collect(self):
+        n = C.c_int(0)
+        _check(_lib.nv_face_collect(self.handle, self._out, self._cap, C.byref(n)), "nv_face_collect")
+        return _rects(self._out, n.value)
+
+    # ---- tracker ---------------------------------------------------------------------------
+    def tracker_process(self, bgra, ts_ms, threshold=20, min_area=50, max_area=30000, distance=35):
+        bgra = _u8(bgra); h, w, _ = bgra.shape
+        p = TrackerParams(threshold, min_area, max_area, distance)
+        n = C.c_int(0)
+        _check(_lib.nv_tracker_process(self.handle, _p(bgra), w, h, bgra.strides[0], float(ts_ms), C.byref(p),
+                                       self._out, self._cap, C.byref(n)), "nv_tracker_process")
+        return _rects(self._out, n.value)
+
+    def tracker_reset(self):
+        _check(_lib.nv_tracker_reset(self.handle), "nv_tracker_reset")
+
+    # ---- image ops -------------------------------------------------------------------------
+    def bgr2gray(self, img):
+        img = _u8(img); h, w, cn = img.shape
+        out = np.empty((h, w), np.uint8)
+        _check(_lib.nv_bgr2gray(self.handle, _p(img), w, h, img.strides[0], cn, _p(out), w), "nv_bgr2gray")
+        return out
+
+    def equalize_hist(self, img):
+        img = _u8(img); h, w = img.shape
+        out = np.empty((h, w), np.uint8)
+        _check(_lib.nv_equalize_hist(self.handle, _p(img), w, h, img.strides[0], _p(out), w), "nv_equalize_hist")
+        return out
+
+    def resize_linear(self, img, dw, dh):
+        img = _u8(img); h, w = img.shape[:2]; cn = 1 if img.ndim == 2 else img.shape[2]
+        out = np.empty((dh, dw) if img.ndim == 2 else (dh, dw, cn), np.uint8)
+        _check(_lib.nv_resize_linear(self.handle, _p(img), w, h, img.strides[0], cn, _p(out), dw, dh, dw * cn),
+               "nv_resize_linear")
+        return out
+
+    def flip_horizontal(self, img):
+        img = _u8(img); h, w = img.shape
+        out = np.empty((h, w), np.uint8)
+        _check(_lib.nv_flip_horizontal(self.handle, _p(img), w, h, img.strides[0], _p(out), w), "nv_flip_horizontal")
+        return out
+
+    # ---- parity taps -----------------------------------------------------------------------
+    def levels(self):
+        out = []
+        for i in range(_lib.nv_debug_num_levels(self.handle)):
+            li = LevelInfo()
+            _check(_lib.nv_debug_level_info(self.handle, i, C.byref(li)), "nv_debug_level_info")
+            out.append(dict(scale=li.scale, lw=li.width, lh=li.height, ystep=li.ystep, nx=li.nx, ny=li.ny))
+        return out
+
+    def gray(self):
+        w, h = C.c_int(0), C.c_int(0)
+        buf = np.empty(16384 * 16384 // 64, np.uint8)
+        _check(_lib.nv_debug_get_gray(self.handle, _p(buf), buf.size, C.byref(w), C.byref(h)), "nv_debug_get_gray")
+        return buf[:w.value * h.value].reshape(h.value, w.value).copy()
+
+    def integral(self, level):
+        lv = self.levels()[level]
+        s = np.empty((lv["lh"] + 1, lv["lw"] + 1), np.int32); q = np.empty((lv["lh"] + 1, lv["lw"] + 1), np.uint32)
+        _check(_lib.nv_debug_get_integral(self.handle, level, _p(s), _p(q)), "nv_debug_get_integral")
+        return s, q
+
+    def depth_map(self, level):
+        lv = self.levels()[level]
+        d = np.empty((lv["ny"], lv["nx"]), np.int16)
+        _check(_lib.nv_debug_get_depth_map(self.handle, level, _p(d)), "nv_debug_get_depth_map")
+        return d
+
+    def candidates(self):
+        n = C.c_int(0)
+        buf = (Rect * 16384)()
+        _check(_lib.nv_debug_get_candidates(self.handle, buf, 16384, C.byref(n)), "nv_debug_get_candidates")
+        return _rects(buf, n.value)
+
+    def counters(self):
+        o = (C.c_longlong * 8)()
+        _check(_lib.nv_debug_get_counters(self.handle, o), "nv_debug_get_counters")
+        return dict(windows=o[0], alive_after_stage0=o[1], candidates=o[2], launches=o[3])

@@ -482,14 +482,14 @@ ORA_API int ora_detect_multiscale(const ora_cascade *c, const uint8_t *gray, int
     if (nwindows) *nwindows = nwin;
     if (ncand > capc) ncand = capc;
     int n = ora_group_rectangles(cand, ncand, min_neighbors, 0.2, weights && ncand <= cap ? weights : NULL);
-    /* A.8 clip to the image */
+    /* A.8 clip to the image; empty intersections are dropped (clipObjects) */
     int m = 0;
     for (int i = 0; i < n; i++) {
         int x0 = ora_max(cand[4 * i], 0), y0 = ora_max(cand[4 * i + 1], 0);
         int x1 = ora_min(cand[4 * i] + cand[4 * i + 2], W), y1 = ora_min(cand[4 * i + 1] + cand[4 * i + 3], H);
+        if (x1 <= x0 || y1 <= y0) continue;
         if (m < cap) {
-            if (x1 <= x0 || y1 <= y0) { out[4 * m] = out[4 * m + 1] = out[4 * m + 2] = out[4 * m + 3] = 0; }
-            else { out[4 * m] = x0; out[4 * m + 1] = y0; out[4 * m + 2] = x1 - x0; out[4 * m + 3] = y1 - y0; }
+            out[4 * m] = x0; out[4 * m + 1] = y0; out[4 * m + 2] = x1 - x0; out[4 * m + 3] = y1 - y0;
             if (weights && m != i) weights[m] = weights[i];
         }
         m++;

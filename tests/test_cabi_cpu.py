@@ -1,0 +1,104 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/nubovca.h
+declares, parses cascades exactly like the oracle's independent parser, reports errors without
+throwing, and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nubovca as nv
+import oracle as O
+from cascade_xml_util import random_cascade, write_cascade
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported():
+    hdr = open(os.path.join(ROOT, "include", "nubovca.h")).read()
+    declared = set(re.findall(r"NV_API\s+[\w\s\*]+?\b(nv_\w+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = C.CDLL(nv.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in nubovca.h but not exported"
+    assert declared == set(nv.EXPORTS), declared ^ set(nv.EXPORTS)
+    assert nv.version().startswith("nubovca-b200")
+
+
+@pytest.mark.parametrize("name", ["haarcascade_frontalface_alt.xml", "haarcascade_profileface.xml",
+                                  "haarcascade_eye.xml", "haarcascade_frontalface_default.xml"])
+def test_cascade_loader_matches_independent_parser(name, cascade_dir):
+    path = os.path.join(cascade_dir, name)
+    c = nv.Cascade(path); d = O.parse_cascade_xml(path)
+    assert (c.info.win_w, c.info.win_h) == (d["win_w"], d["win_h"])
+    assert c.info.nstages == len(d["stage_ntrees"]) and c.info.nstumps == len(d["stump_feat"])
+    assert c.info.nfeatures == len(d["feat_rect"])
+    assert c.info.n3rect == int((d["feat_weight"][:, 2] != 0).sum())
+    for s in range(c.info.nstages):
+        nt, thr = c.stage(s)
+        assert nt == d["stage_ntrees"][s]
+        assert thr == np.float32(d["stage_thr"][s]) - np.float32(1e-5)
+    for i in range(c.info.nstumps):
+        r, w, t = c.stump(i)
+        f = d["stump_feat"][i]
+        assert (r == d["feat_rect"][f]).all() and (w == d["feat_weight"][f]).all()
+        assert (t == np.array([d["stump_thr"][i], d["stump_left"][i], d["stump_right"][i]], np.float32)).all()
+
+
+def test_frontalface_alt_shape(cascade_dir):
+    # 20x20, 22 stages, 2135 stumps, 360 three-rect features
+    c = nv.Cascade(os.path.join(cascade_dir, "haarcascade_frontalface_alt.xml"))
+    assert (c.info.win_w, c.info.win_h, c.info.nstages, c.info.nstumps, c.info.n3rect) == (20, 20, 22, 2135, 360)
+    assert [c.stage(s)[0] for s in range(22)] == [3, 16, 21, 39, 33, 44, 50, 51, 56, 71, 80, 103, 111, 102, 135, 137,
+                                                  140, 160, 177, 182, 211, 213]
+    assert c.info.order_free_sums == 1
+
+
+def test_order_free_certificate(tmp_path):
+    p = str(tmp_path / "a.xml")
+    write_cascade(p, 20, 20, [(0.5, [(0, 1e30, 1e8, 1e8), (0, 1e30, 1.0, 1.0), (0, 1e30, -1e8, -1e8)])],
+                  [[(2, 2, 10, 10, -1.0), (4, 4, 5, 5, 2.0)]])
+    assert nv.Cascade(p).info.order_free_sums == 1          # 1e8 + 1 is exact in double
+    write_cascade(p, 20, 20, [(0.5, [(0, 1e30, 1e30, 1e30), (0, 1e30, 1.0, 1.0)])],
+                  [[(2, 2, 10, 10, -1.0), (4, 4, 5, 5, 2.0)]])
+    assert nv.Cascade(p).info.order_free_sums == 0          # 1e30 + 1 rounds: order matters
+
+
+def test_random_cascade_roundtrip(tmp_path):
+    p = str(tmp_path / "r.xml")
+    random_cascade(p, np.random.default_rng(0), nstages=5, max_trees=7)
+    c = nv.Cascade(p); d = O.parse_cascade_xml(p)
+    assert c.info.nstumps == len(d["stump_feat"])
+    for i in range(c.info.nstumps):
+        r, w, t = c.stump(i)
+        assert (r == d["feat_rect"][d["stump_feat"][i]]).all() and (w == d["feat_weight"][d["stump_feat"][i]]).all()
+
+
+def test_cascade_error_paths(tmp_path):
+    with pytest.raises(nv.NuboError) as e:
+        nv.Cascade(str(tmp_path / "missing.xml"))
+    assert e.value.code == -3
+    bad = tmp_path / "bad.xml"
+    bad.write_text("<opencv_storage><cascade><stageType>BOOST</stageType>")
+    with pytest.raises(nv.NuboError) as e:
+        nv.Cascade(str(bad))
+    assert e.value.code == -4
+    bad.write_text("this is not xml")
+    with pytest.raises(nv.NuboError) as e:
+        nv.Cascade(str(bad))
+    assert e.value.code == -4
+    import cv2  # tilted / tree cascades ship with cv2: loader must refuse them, not mis-evaluate them
+    for name, code in [("haarcascade_smile.xml", -5), ("haarcascade_lefteye_2splits.xml", -5),
+                       ("haarcascade_license_plate_rus_16stages.xml", -4)]:
+        with pytest.raises(nv.NuboError) as e:
+            nv.Cascade(os.path.join(cv2.data.haarcascades, name))
+        assert e.value.code in (code, -4, -5)
+
+
+@pytest.mark.skipif(nv.device_count() > 0, reason="a GPU is visible")
+def test_no_cpu_fallback():
+    with pytest.raises(nv.NuboError) as e:
+        nv.Context()
+    assert e.value.code == nv.NV_ERR_NO_DEVICE
+    assert "no CPU path" in str(e.value)

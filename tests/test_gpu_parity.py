@@ -1,0 +1,240 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs and against the committed cv2 golden fixtures.  Bit-exact everywhere: gray/equalised
+images, every level's integral and squared integral, every level's stage-exit depth map, raw
+candidates (canonical order) and grouped rectangles.  The north-star tolerance (disagreement only for
+windows whose stage sum is within 1e-5 relative of a threshold) is therefore never used."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import nubovca as nv
+import oracle as O
+from cascade_xml_util import random_cascade
+from nubovca import synth
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+FACE_XML = "haarcascade_frontalface_alt.xml"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = nv.Context(0, 1920, 1080, debug=True)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def face(cascade_dir):
+    p = os.path.join(cascade_dir, FACE_XML)
+    return nv.Cascade(p), O.Cascade(p)
+
+
+def rects_equal(a, b):
+    a = np.asarray(a, np.int32).reshape(-1, 4); b = np.asarray(b, np.int32).reshape(-1, 4)
+    return a.shape == b.shape and bool((a == b).all())
+
+
+def check_levels(ctx, eq, ocasc, sf, ms):
+    """integrals, depth maps and candidates of the last detect call vs the oracle; returns #windows checked."""
+    levels = O.eval_pyramid(eq, ocasc, sf, ms, keep_integrals=True)
+    got = ctx.levels()
+    assert len(got) == len(levels)
+    nwin = 0
+    cands = []
+    for i, (g, o) in enumerate(zip(got, levels)):
+        assert (g["lw"], g["lh"], g["ystep"]) == (o["lw"], o["lh"], o["ystep"]), i
+        assert g["scale"] == np.float32(o["scale"])
+        assert (g["ny"], g["nx"]) == o["depth"].shape, i
+        s, q = ctx.integral(i)
+        assert (s == o["sum"]).all(), f"level {i} integral"
+        assert (q == o["sqsum"]).all(), f"level {i} squared integral"
+        d = ctx.depth_map(i)
+        bad = np.argwhere(d != o["depth"])
+        assert len(bad) == 0, f"level {i}: {len(bad)} depth mismatches, first {bad[:3]} gpu {d[tuple(bad[0])]} ora {o['depth'][tuple(bad[0])]}"
+        nwin += d.size
+        cands.append(o["cand"])
+    cand = np.concatenate(cands) if cands else np.zeros((0, 4), np.int32)
+    assert rects_equal(ctx.candidates(), cand)
+    return nwin, levels
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("idx", range(6))
+def test_face_golden_cases(ctx, face, idx):
+    """cfg1 / cfg5 / cfg2-face-stage / cfg3-parameter cases of tests/golden (cv2 4.13 outputs)."""
+    c = json.load(open(os.path.join(HERE, "golden", "face_golden.json")))["cases"][idx]
+    ncasc, ocasc = face
+    fr = synth.frame(c["W"], c["H"], c["k"], c["seed"])
+    ms = tuple(c["min_size"])
+    got = ctx.face_detect(ncasc, fr, c["width_to_process"], c["scale_factor"], c["min_neighbors"], ms)
+    assert rects_equal(got, c["grouped"])
+    exp, eq = O.face_process(fr, ocasc, c["width_to_process"], c["scale_factor"], c["min_neighbors"], ms)
+    assert rects_equal(got, exp)
+    assert (ctx.gray() == eq).all()
+    nwin, _ = check_levels(ctx, eq, ocasc, c["scale_factor"], ms)
+    assert nwin > 1000
+    raw = ctx.face_detect(ncasc, fr, c["width_to_process"], c["scale_factor"], 0, ms)
+    assert rects_equal(raw, c["raw"])
+
+
+def test_face_element_min_size_rule(ctx, face):
+    # min_size=None -> Size(cols/20, rows/20), kmsfacedetect.cpp:811
+    ncasc, ocasc = face
+    fr = synth.frame(640, 480, 4, 1)
+    got = ctx.face_detect(ncasc, fr, 160, 1.25, 3, None)
+    exp, _ = O.face_process(fr, ocasc, 160, 1.25, 3, None)
+    assert rects_equal(got, exp) and len(got) >= 1
+
+
+def test_depth_maps_reach_every_stage(ctx, face):
+    """The procedurally composited patches drive windows through all 22 stages."""
+    ncasc, ocasc = face
+    fr = synth.frame(480, 360, 10, 5)
+    ctx.face_detect(ncasc, fr, 480, 1.1, 3, (0, 0))
+    _, eq = O.face_process(fr, ocasc, 480, 1.1, 3, (0, 0))
+    nwin, levels = check_levels(ctx, eq, ocasc, 1.1, (0, 0))
+    codes = np.concatenate([l["depth"].ravel() for l in levels])
+    for st in range(1, 22):
+        assert (codes == -st).any(), f"no window exits at stage {st}"
+    assert (codes == 0).any() and (codes == 1).any() and (codes == O.DEPTH_SKIPPED).any() and (codes == O.DEPTH_VARREJ).any()
+    assert ctx.counters()["windows"] == nwin
+
+
+@pytest.mark.parametrize("name,sf,ms", [("haarcascade_profileface.xml", 1.25, (3, 3)),
+                                        ("haarcascade_eye.xml", 1.1, (20, 20)),
+                                        ("haarcascade_frontalface_default.xml", 1.2, (0, 0))])
+def test_other_cascades(ctx, cascade_dir, name, sf, ms):
+    """profileface = the ear element's face stage (kmseardetect.cpp:656-659); eye = stand-in for the absent
+    mcs_* feature cascades; frontalface_default = a 24x24 window."""
+    p = os.path.join(cascade_dir, name)
+    ncasc, ocasc = nv.Cascade(p), O.Cascade(p)
+    g = O.equalize_hist(O.bgr2gray(synth.frame(320, 240, 4, 9)))
+    for mn in (0, 2):
+        assert rects_equal(ctx.detect_multiscale(ncasc, g, sf, mn, ms), O.detect_multiscale(g, ocasc, sf, mn, ms))
+    check_levels(ctx, g, ocasc, sf, ms)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_cascades_and_ragged_sizes(ctx, tmp_path, seed):
+    """Random stump cascades (stage-0 skip rule, 3-rect features, odd window sizes) on odd image sizes."""
+    rng = np.random.default_rng(300 + seed)
+    p = str(tmp_path / "rand.xml")
+    w, h = [(20, 20), (24, 24), (25, 15), (18, 15), (12, 30), (33, 9)][seed]
+    random_cascade(p, rng, w=w, h=h, nstages=int(rng.integers(1, 7)), max_trees=8)
+    W, H = int(rng.integers(w + 1, 500)), int(rng.integers(h + 1, 400))
+    g = synth.frame(W, H, 2, seed)[..., 1] if seed % 2 else rng.integers(0, 256, (H, W), dtype=np.uint8)
+    sf = float(rng.choice([1.1, 1.25, 1.4]))
+    ncasc, ocasc = nv.Cascade(p), O.Cascade(p)
+    for mn in (0, 2):
+        assert rects_equal(ctx.detect_multiscale(ncasc, g, sf, mn), O.detect_multiscale(g, ocasc, sf, mn)), (seed, mn)
+    check_levels(ctx, g, ocasc, sf, (0, 0))
+
+
+def test_edge_cases(ctx, face):
+    ncasc, ocasc = face
+    rng = np.random.default_rng(1)
+    # image smaller than the window: empty result, no error (A.9)
+    assert len(ctx.detect_multiscale(ncasc, rng.integers(0, 256, (15, 19), dtype=np.uint8), 1.1, 3)) == 0
+    # exactly one window
+    g = rng.integers(0, 256, (20, 20), dtype=np.uint8)
+    assert rects_equal(ctx.detect_multiscale(ncasc, g, 1.1, 0), O.detect_multiscale(g, ocasc, 1.1, 0))
+    # flat image: every window variance-rejected
+    assert len(ctx.detect_multiscale(ncasc, np.full((100, 100), 128, np.uint8), 1.1, 0)) == 0
+    # padded stride (GStreamer rows are 4-byte aligned: stride != 3*width)
+    fr = synth.frame(322, 241, 3, 11)
+    pad = np.zeros((241, 322 * 3 + 2), np.uint8); pad[:, :966] = fr.reshape(241, -1)
+    view = pad[:, :966].reshape(241, 322, 3)
+    a = nv.Context._face_params(161, 1.25, 3, None)
+    import ctypes as C
+    n = C.c_int(0)
+    rc = nv._lib.nv_face_detect(ctx.handle, ncasc.handle, pad.ctypes.data_as(C.c_void_p), 322, 241, pad.strides[0],
+                                C.byref(a), ctx._out, ctx._cap, C.byref(n))
+    assert rc == 0
+    exp, _ = O.face_process(np.ascontiguousarray(view), ocasc, 161, 1.25, 3, None)
+    assert rects_equal(nv._rects(ctx._out, n.value), exp)
+    # bad parameters are reported, not crashed on
+    with pytest.raises(nv.NuboError):
+        ctx.detect_multiscale(ncasc, g, 1.0, 3)
+    with pytest.raises(nv.NuboError):
+        ctx.face_detect(ncasc, fr, 0)
+    with pytest.raises(nv.NuboError):
+        ctx.face_detect(ncasc, np.zeros((2000, 3000, 3), np.uint8), 160)
+
+
+def test_cfg3_full_size_1080p(ctx, face):
+    """BASELINE config 3 at full size: 1920x1080, processing width 1920, sf 1.1, min 24x24.
+    Full oracle comparison (a few seconds of CPU) including every depth map."""
+    ncasc, ocasc = face
+    fr = synth.frame(1920, 1080, 6, 3)
+    got = ctx.face_detect(ncasc, fr, 1920, 1.1, 3, (24, 24))
+    exp, eq = O.face_process(fr, ocasc, 1920, 1.1, 3, (24, 24))
+    assert rects_equal(got, exp) and len(got) >= 4
+    assert (ctx.gray() == eq).all()
+    nwin, _ = check_levels(ctx, eq, ocasc, 1.1, (24, 24))
+    assert nwin > 3_000_000
+    assert len(ctx.levels()) == 40
+
+
+def test_async_streams_are_independent(face):
+    """cfg5 mechanics: many contexts in flight give the same per-stream results as one at a time."""
+    ncasc, ocasc = face
+    ctxs = [nv.Context(0, 1280, 720) for _ in range(4)]
+    frames = [synth.frame(1280, 720, 3, 1000 + i) for i in range(4)]
+    for c, f in zip(ctxs, frames):
+        c.face_submit(ncasc, f, 640, 1.25, 3, None)
+    outs = [c.face_collect() for c in ctxs]
+    for f, o in zip(frames, outs):
+        exp, _ = O.face_process(f, ocasc, 640, 1.25, 3, None)
+        assert rects_equal(o, exp)
+    for c in ctxs:
+        c.close()
+
+
+# ------------------------------------------------------------------------------------------
+def test_image_ops(ctx):
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, (217, 333, 3), dtype=np.uint8)
+    assert (ctx.bgr2gray(img) == O.bgr2gray(img)).all()
+    img4 = rng.integers(0, 256, (45, 67, 4), dtype=np.uint8)
+    assert (ctx.bgr2gray(img4) == O.bgr2gray(img4)).all()
+    g = img[..., 0].copy()
+    assert (ctx.equalize_hist(g) == O.equalize_hist(g)).all()
+    assert (ctx.equalize_hist(np.full((10, 10), 7, np.uint8)) == 7).all()
+    for (dw, dh) in [(160, 104), (166, 108), (333, 217), (400, 300), (100, 300), (666, 434)]:
+        assert (ctx.resize_linear(img, dw, dh) == O.resize_linear(img, dw, dh)).all(), (dw, dh)
+        assert (ctx.resize_linear(g, dw, dh) == O.resize_linear(g, dw, dh)).all(), (dw, dh)
+    big = rng.integers(0, 256, (720, 1280), dtype=np.uint8)
+    assert (ctx.resize_linear(big, 640, 360) == O.resize_linear(big, 640, 360)).all()      # 2x fast path
+    assert (ctx.flip_horizontal(g) == g[:, ::-1]).all()
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("idx", range(2))
+def test_tracker_golden(idx):
+    c = json.load(open(os.path.join(HERE, "golden", "tracker_golden.json")))["cases"][idx]
+    frames = synth.tracker_sequence(c["W"], c["H"], c["nframes"], c["seed"], noise=c["noise"])
+    t = nv.Context(0, c["W"], c["H"])
+    for i, (f, g) in enumerate(zip(frames, c["frames"])):
+        r = t.tracker_process(f, 33.3 * (i + 1), c["threshold"], -1, 1 << 40, 0)
+        assert rects_equal(r, g["rects"]), i
+    t.close()
+
+
+def test_tracker_vs_oracle_with_join_and_stale_history():
+    """cfg4 parameters at 720p; timestamps closer than MHI_DURATION keep stale history alive, which
+    exercises the floating-range connectivity beyond plain connected components."""
+    W, H = 1280, 720
+    frames = synth.tracker_sequence(W, H, 6, seed=4, noise=300)
+    t = nv.Context(0, W, H)
+    st = O.TrackerState(W, H)
+    for i, f in enumerate(frames):
+        ts = 1000.0 + (0.1 * i if i < 3 else 33.3 * i)
+        got = t.tracker_process(f, ts, 20, 50, 30000, 35)
+        exp, nraw, _ = st.process(f, ts, 20, 50, 30000, 35)
+        assert rects_equal(got, exp), i
+    t.tracker_reset()
+    assert len(t.tracker_process(frames[0], 5000.0)) == 0       # first frame after reset only primes
+    t.close()
