@@ -12,8 +12,9 @@
 #include "internal.h"
 
 #define NV_VERSION_STR "nubovca-b200 0.1 (sm_100a)"
-#define CAND_CAP 8192
-#define RESULT_CAP 16384
+#define CAND_CAP 8192              // initial raw-candidate capacity; grows on demand (collect() re-runs the call)
+#define CAND_CAP_GROUPED 32768     // hard limits: the similarity bit-matrix is cap^2/8 bytes
+#define CAND_CAP_RAW 131072
 
 extern "C" const char *nv_version(void) { return NV_VERSION_STR; }
 
@@ -137,6 +138,27 @@ static int ensure(T **p, size_t *cap, size_t need, bool zero = false)
     return NV_OK;
 }
 
+// candidate-side buffers: ids, sorted ids, rects, similarity bit-matrix (+ group scratch), result block
+static int alloc_candidates(nv_ctx *c, int cap, bool with_adj)
+{
+    cudaFree(c->d_cand); cudaFree(c->d_cand_sorted); cudaFree(c->d_cand_rects); cudaFree(c->d_adj); cudaFree(c->d_result);
+    cudaFreeHost(c->h_result);
+    c->d_cand = c->d_cand_sorted = nullptr; c->d_cand_rects = nullptr; c->d_adj = nullptr; c->d_result = c->h_result = nullptr;
+    c->cand_cap = cap; c->result_cap = cap; c->adj_cap = 0;
+    NV_CUDA(cudaMalloc(&c->d_cand, (size_t)cap * sizeof(uint32_t)));
+    NV_CUDA(cudaMalloc(&c->d_cand_sorted, (size_t)cap * sizeof(uint32_t)));
+    NV_CUDA(cudaMalloc(&c->d_cand_rects, (size_t)cap * sizeof(int4)));
+    size_t adj_words = (with_adj ? (size_t)cap * ((cap + 31) / 32) : 0) + 8 * (size_t)cap;
+    NV_CUDA(cudaMalloc(&c->d_adj, adj_words * sizeof(uint32_t)));
+    c->adj_cap = with_adj ? cap : 0;
+    c->d_grp = reinterpret_cast<int *>(c->d_adj + (adj_words - 8 * (size_t)cap));
+    size_t rbytes = sizeof(ResultHeader) + (size_t)c->result_cap * sizeof(nv_rect);
+    NV_CUDA(cudaMalloc(&c->d_result, rbytes));
+    NV_CUDA(cudaMallocHost(&c->h_result, rbytes));
+    memset(c->h_result, 0, sizeof(ResultHeader));
+    return NV_OK;
+}
+
 extern "C" int nv_ctx_create(int gpu, int max_width, int max_height, nv_ctx **out)
 {
     if (!out || max_width <= 0 || max_height <= 0 || max_width > 16384 || max_height > 16384) {
@@ -166,16 +188,7 @@ extern "C" int nv_ctx_create(int gpu, int max_width, int max_height, nv_ctx **ou
         NV_CUDA(cudaMemcpy(c->d_lut + 256, ident, 256, cudaMemcpyHostToDevice));     // identity LUT
         NV_CUDA(cudaMalloc(&c->d_plan, sizeof(PlanDev)));
         NV_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(int)));
-        c->cand_cap = CAND_CAP; c->result_cap = RESULT_CAP;
-        NV_CUDA(cudaMalloc(&c->d_cand, c->cand_cap * sizeof(uint32_t)));
-        NV_CUDA(cudaMalloc(&c->d_cand_sorted, c->cand_cap * sizeof(uint32_t)));
-        NV_CUDA(cudaMalloc(&c->d_cand_rects, c->cand_cap * sizeof(int4)));
-        size_t adj_words = (size_t)c->cand_cap * ((c->cand_cap + 31) / 32) + 8 * (size_t)c->cand_cap;
-        NV_CUDA(cudaMalloc(&c->d_adj, adj_words * sizeof(uint32_t)));
-        size_t rbytes = sizeof(ResultHeader) + (size_t)c->result_cap * sizeof(nv_rect);
-        NV_CUDA(cudaMalloc(&c->d_result, rbytes));
-        NV_CUDA(cudaMallocHost(&c->h_result, rbytes));
-        return NV_OK;
+        return alloc_candidates(c, CAND_CAP, true);
     }();
     if (rc != NV_OK) { nv_ctx_destroy(c); return rc; }
     *out = c;
@@ -393,6 +406,10 @@ static int detect_on_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray
     if ((rc = cascade_on_device(casc, ctx->gpu, ctx->stream, &stumps, &meta)) != NV_OK) return rc;
     const PlanDev &P = ctx->plan;
     cudaStream_t st = ctx->stream;
+    if (p->min_neighbors > 0 && ctx->adj_cap < (size_t)ctx->cand_cap) {      // grown earlier for an ungrouped call
+        NV_CUDA(cudaStreamSynchronize(st));
+        if ((rc = alloc_candidates(ctx, std::min(ctx->cand_cap, CAND_CAP_GROUPED), true)) != NV_OK) return rc;
+    }
     int nl = 0;
     for (int i = 2; i <= NV_NUM_STAGES; i++) ctx->prof_set[i] = false;
     NV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int), st));
@@ -416,12 +433,13 @@ static int detect_on_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray
     }
     prof_mark(ctx, 7);
     NV_CUDA(launch_group(ctx->d_plan, ctx->d_counters, ctx->d_cand, ctx->cand_cap, ctx->d_cand_sorted, ctx->d_cand_rects,
-                         ctx->d_adj, p->min_neighbors, 0.2, W, H, ctx->d_result, ctx->result_cap, 148 * 2, st, &nl));
+                         ctx->d_adj, ctx->d_grp, p->min_neighbors, 0.2, W, H, ctx->d_result, ctx->result_cap, 148 * 2, st, &nl));
     prof_mark(ctx, 8);
     NV_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(ResultHeader) + NV_RESULT_INLINE * sizeof(nv_rect),
                             cudaMemcpyDeviceToHost, st));
     ctx->launches += nl;
     ctx->last_min_neighbors = p->min_neighbors;
+    ctx->last_casc = casc; ctx->last_params = *p; ctx->last_W = W; ctx->last_H = H;
     ctx->tap_gray = d_gray; ctx->tap_lut = d_lut; ctx->tap_stride = gstride;
     ctx->pending = true;
     return NV_OK;
@@ -433,6 +451,22 @@ static int collect(nv_ctx *ctx, nv_rect *out, int cap, int *n)
     NV_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->pending = false;
     const ResultHeader *h = reinterpret_cast<const ResultHeader *>(ctx->h_result);
+    if (h->overflow) {
+        // raw candidates outgrew the buffers: grow them and run the same call again (inputs are still on the device)
+        int need = h->n_cand, lim = ctx->last_min_neighbors > 0 ? CAND_CAP_GROUPED : CAND_CAP_RAW;
+        if (need > lim || need <= ctx->cand_cap) {
+            nv_set_error("%d raw candidates exceed the supported maximum of %d", need, lim);
+            return NV_ERR_CAPACITY;
+        }
+        int rc = alloc_candidates(ctx, std::min(lim, need + need / 4 + 64), ctx->last_min_neighbors > 0);
+        if (rc != NV_OK) return rc;
+        nv_detect_params p = ctx->last_params;
+        rc = detect_on_device(ctx, ctx->last_casc, ctx->tap_gray, ctx->last_W, ctx->last_H, ctx->tap_stride, ctx->tap_lut, &p);
+        if (rc != NV_OK) return rc;
+        NV_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->pending = false;
+        h = reinterpret_cast<const ResultHeader *>(ctx->h_result);
+    }
     int total = h->n_out;
     if (total > NV_RESULT_INLINE) {
         NV_CUDA(cudaMemcpy(ctx->h_result + sizeof(ResultHeader) + NV_RESULT_INLINE * sizeof(nv_rect),
@@ -446,6 +480,7 @@ static int collect(nv_ctx *ctx, nv_rect *out, int cap, int *n)
         nv_set_error("internal capacity exceeded (%d raw candidates, cap %d)", h->n_cand, ctx->cand_cap);
         return NV_ERR_CAPACITY;
     }
+    if (total > cap) { nv_set_error("%d rectangles, caller capacity %d", total, cap); return NV_ERR_CAPACITY; }
     return NV_OK;
 }
 

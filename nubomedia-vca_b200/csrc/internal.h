@@ -154,11 +154,12 @@ struct nv_ctx {
     uint32_t *d_cand = nullptr;  int cand_cap = 0;          // packed window ids
     uint32_t *d_cand_sorted = nullptr;
     int4 *d_cand_rects = nullptr;
-    uint32_t *d_adj = nullptr;   size_t adj_cap = 0;
+    uint32_t *d_adj = nullptr;   size_t adj_cap = 0;  int *d_grp = nullptr;   // similarity bit-matrix, group scratch
     uint8_t *d_result = nullptr; uint8_t *h_result = nullptr;   // ResultHeader + rects
     int result_cap = 0;                                     // rects
 
-    // last-call bookkeeping
+    // last-call bookkeeping (kept so that collect() can re-run a call whose candidate buffers overflowed)
+    nv_cascade *last_casc = nullptr;  nv_detect_params last_params = {};  int last_W = 0, last_H = 0;
     const uint8_t *tap_gray = nullptr, *tap_lut = nullptr;  int tap_stride = 0;
     bool pending = false;
     int profile = 0;  cudaEvent_t prof_ev[NV_NUM_STAGES + 1] = {};  bool prof_set[NV_NUM_STAGES + 1] = {};
@@ -210,7 +211,7 @@ cudaError_t launch_queue_stages(const PlanDev *plan, const DevCascade *meta, con
 
 // kernels_group.cu
 cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *cand, int cand_cap, uint32_t *cand_sorted,
-                         int4 *cand_rects, uint32_t *adj, int min_neighbors, double eps, int img_w, int img_h,
+                         int4 *cand_rects, uint32_t *adj, int *grp, int min_neighbors, double eps, int img_w, int img_h,
                          uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch);
 
 // kernels_tracker.cu

@@ -195,12 +195,9 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
 }
 
 cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *cand, int cand_cap, uint32_t *cand_sorted,
-                         int4 *cand_rects, uint32_t *adj, int min_neighbors, double eps, int img_w, int img_h,
+                         int4 *cand_rects, uint32_t *adj, int *grp, int min_neighbors, double eps, int img_w, int img_h,
                          uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch)
 {
-    // adj buffer: [bit-matrix words: cap * cap/32][group scratch ints: 8 * cap]
-    size_t adj_words = (size_t)cand_cap * ((cand_cap + 31) / 32);
-    int *grp = reinterpret_cast<int *>(adj + adj_words);
     k_cand_sort<<<nblocks, 256, 0, st>>>(plan, counters, cand, cand_cap, cand_sorted, cand_rects);
     (*nlaunch)++;
     if (min_neighbors > 0) {

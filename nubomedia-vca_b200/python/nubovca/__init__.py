@@ -184,7 +184,7 @@ class Context:
     def __init__(self, gpu: int = 0, max_width: int = 1920, max_height: int = 1080, debug: bool = False):
         self.handle = _vp()
         _check(_lib.nv_ctx_create(gpu, max_width, max_height, C.byref(self.handle)), "nv_ctx_create")
-        self._cap = 16384
+        self._cap = 131072
         self._out = (Rect * self._cap)()
         if debug:
             self.set_debug(True)
@@ -317,8 +317,8 @@ class Context:
 
     def candidates(self):
         n = C.c_int(0)
-        buf = (Rect * 16384)()
-        _check(_lib.nv_debug_get_candidates(self.handle, buf, 16384, C.byref(n)), "nv_debug_get_candidates")
+        buf = (Rect * 131072)()
+        _check(_lib.nv_debug_get_candidates(self.handle, buf, 131072, C.byref(n)), "nv_debug_get_candidates")
         return _rects(buf, n.value)
 
     def counters(self):
