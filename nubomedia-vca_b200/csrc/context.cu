@@ -227,7 +227,7 @@ extern "C" int nv_ctx_set_debug(nv_ctx *ctx, int debug)
 // device-side timing
 // ------------------------------------------------------------------------------------------------
 static const char *k_stage_names[NV_NUM_STAGES] = {"face_prep", "hist_lut", "pyramid_rowscan", "integral_colscan",
-                                                   "cascade_stage0", "skip_compact", "cascade_stages", "group_rectangles"};
+                                                   "cascade_stage0", "cascade_tiles", "cascade_tail", "group_rectangles"};
 extern "C" const char *nv_stage_name(int slot) { return slot >= 0 && slot < NV_NUM_STAGES ? k_stage_names[slot] : ""; }
 
 static inline void prof_mark(nv_ctx *ctx, int idx)
@@ -358,6 +358,9 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         L.colblk0 = P.total_colblk; P.total_colblk += (L.ipitch + 31) / 32;
         L.chunk0 = P.total_chunks; P.total_chunks += L.nxw * L.ny;
         L.row0 = P.total_rows; P.total_rows += L.ny;
+        L.nty = (L.ny + NV_TILE - 1) / NV_TILE;
+        if (ystep == 2) { L.tile0 = P.tiles2; P.tiles2 += L.nty * L.nxw; P.nlv2 = nl; }
+        else { L.tile0 = P.tiles1; P.tiles1 += L.nty * L.nxw; }
         if (iofs > 0x7fffffffLL || wofs > 0x7fffffffLL) { nv_set_error("frame too large"); return NV_ERR_CAPACITY; }
     }
     P.nlevels = nl;
@@ -391,6 +394,62 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
     NV_CUDA(cudaMemcpy(ctx->d_plan, &P, sizeof(PlanDev), cudaMemcpyHostToDevice));
     ctx->pkey = key;
     ctx->plan_valid = true;
+    ctx->tp_casc = nullptr;            // tensor maps and tile geometry follow the plan
+    return NV_OK;
+}
+
+// ---- tile-kernel parameters: tensor maps over each level's sum integral + bulk-stage classifiers ----
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_tiled()
+{
+    static encode_tiled_fn fn = []() -> encode_tiled_fn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+        return (encode_tiled_fn)p;
+    }();
+    return fn;
+}
+
+static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
+{
+    if (ctx->tp_casc == casc) return NV_OK;
+    const PlanDev &P = ctx->plan;
+    const DevCascade &m = casc->meta;
+    ctx->tp_casc = casc;
+    ctx->use_tiles = false;
+    encode_tiled_fn enc = get_encode_tiled();
+    if (!enc || m.win_w > 32 || m.win_h > 32 || P.nlevels == 0) return NV_OK;
+    // bulk stages: as many as fit the parameter bank
+    int end = 1;
+    while (end < m.nstages && end < NV_BULK_MAX_STAGES && m.stage_first[end + 1] - m.stage_first[1] <= NV_BULK_MAX_STUMPS) end++;
+    ctx->bulk_end = end;
+    for (int c = 0; c < 2; c++) {
+        int ys = c == 0 ? 2 : 1;
+        TileParams &tp = ctx->tp[c];
+        tp.cp = align_up(NV_TILE + (ys == 2 ? m.win_w / 2 : m.win_w) + 1, 4);
+        tp.rt = (NV_TILE - 1) * ys + m.win_h + 1;
+        tp.ps = align_up(tp.rt * tp.cp, 32);
+        tp.level_begin = c == 0 ? 0 : P.nlv2;
+        tp.level_end = c == 0 ? P.nlv2 : P.nlevels;
+        fill_bulk_stumps(casc, ys, tp.cp, tp.ps, end, &tp);
+        for (int l = tp.level_begin; l < tp.level_end; l++) {
+            const LevelDesc &L = P.lv[l];
+            cuuint64_t gdim[2] = {(cuuint64_t)L.ipitch, (cuuint64_t)(L.lh + 1)};
+            cuuint64_t gstr[1] = {(cuuint64_t)L.ipitch * 4};
+            cuuint32_t box[2] = {(cuuint32_t)tp.cp, (cuuint32_t)tp.rt};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = enc(&tp.maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, ctx->d_sum + L.iofs, gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return NV_OK;       // keep the generic queue path for this plan
+        }
+    }
+    ctx->use_tiles = true;
     return NV_OK;
 }
 
@@ -404,6 +463,7 @@ static int detect_on_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray
     if (rc != NV_OK) return rc;
     const DevStump *stumps; const DevCascade *meta;
     if ((rc = cascade_on_device(casc, ctx->gpu, ctx->stream, &stumps, &meta)) != NV_OK) return rc;
+    if ((rc = ensure_tile_params(ctx, casc)) != NV_OK) return rc;
     const PlanDev &P = ctx->plan;
     cudaStream_t st = ctx->stream;
     if (p->min_neighbors > 0 && ctx->adj_cap < (size_t)ctx->cand_cap) {      // grown earlier for an ungrouped call
@@ -421,15 +481,36 @@ static int detect_on_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray
         prof_mark(ctx, 3);
         NV_CUDA(launch_colscan(ctx->d_plan, P.total_colblk, ctx->d_sum, ctx->d_sq, st));
         prof_mark(ctx, 4);
-        NV_CUDA(launch_stage0(ctx->d_plan, P.total_chunks, meta, stumps, ctx->d_sum, ctx->d_sq, ctx->d_vnf,
-                              ctx->d_bits_fail, ctx->d_bits_ok, st));
+        NV_CUDA(launch_stage0_rows(ctx->d_plan, P.total_rows, meta, stumps, ctx->d_sum, ctx->d_sq, ctx->d_vnf,
+                                   ctx->d_bits_ok, ctx->d_counters, depth, st));
         prof_mark(ctx, 5);
-        NV_CUDA(launch_skip_compact(ctx->d_plan, P.total_rows, ctx->d_vnf, ctx->d_bits_fail, ctx->d_bits_ok, ctx->d_queue,
-                                    ctx->d_counters, (int)std::min<size_t>(ctx->queue_cap, 0x7fffffff), depth, st));
-        prof_mark(ctx, 6);
-        NV_CUDA(launch_queue_stages(ctx->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
-                                    ctx->cand_cap, depth, 148 * 8, st));
-        nl += 5;
+        nl += 3;
+        int qcap = (int)std::min<size_t>(ctx->queue_cap, 0x7fffffff);
+        if (ctx->use_tiles) {
+            for (int c = 0; c < 2; c++) {
+                TileParams &tp = ctx->tp[c];
+                int ntiles = c == 0 ? P.tiles2 : P.tiles1;
+                if (ntiles == 0) continue;
+                tp.plan = ctx->d_plan; tp.bits_alive = ctx->d_bits_ok; tp.vnf = ctx->d_vnf; tp.depth = depth;
+                tp.tail = ctx->d_queue; tp.cand = ctx->d_cand; tp.counters = ctx->d_counters;
+                tp.tail_cap = qcap; tp.cand_cap = ctx->cand_cap;
+                NV_CUDA(launch_cascade_tiles(tp, c == 0 ? 2 : 1, ntiles, st));
+                nl++;
+            }
+            prof_mark(ctx, 6);
+            if (ctx->bulk_end < casc->meta.nstages) {
+                NV_CUDA(launch_cascade_tail(ctx->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
+                                            ctx->cand_cap, depth, ctx->bulk_end, casc->h.order_free, 148 * 4, st));
+                nl++;
+            }
+        } else {
+            NV_CUDA(launch_alive_to_queue(ctx->d_plan, P.total_rows, ctx->d_vnf, ctx->d_bits_ok, ctx->d_queue, ctx->d_counters,
+                                          qcap, st));
+            prof_mark(ctx, 6);
+            NV_CUDA(launch_queue_stages(ctx->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
+                                        ctx->cand_cap, depth, 148 * 8, st));
+            nl += 2;
+        }
     }
     prof_mark(ctx, 7);
     NV_CUDA(launch_group(ctx->d_plan, ctx->d_counters, ctx->d_cand, ctx->cand_cap, ctx->d_cand_sorted, ctx->d_cand_rects,

@@ -1,5 +1,6 @@
 // internal.h — shared declarations of libnubovca (not part of the public C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -85,7 +86,9 @@ struct LevelDesc {
     int rowblk0;           // first row-block (8 rows) of this level in k_pyr_rowscan's grid
     int colblk0;           // first column-block (32 physical cols) in k_colscan's grid (per array)
     int chunk0;            // first 32-window chunk in k_stage0's grid
-    int row0;              // first window row in k_skip_compact's grid
+    int row0;              // first window row in k_stage0_rows' grid
+    int tile0;             // first 32x32-window tile of this level within its ystep class (k_cascade_tiles)
+    int nty;               // tile rows = ceil(ny/32); tile columns = nxw
 };
 
 struct PlanDev {
@@ -93,6 +96,8 @@ struct PlanDev {
     int W, H;              // processing-size image (the pyramid base)
     int win_w, win_h;
     int total_rowblk, total_colblk, total_chunks, total_rows, total_windows;
+    int nlv2;              // levels [0, nlv2) have ystep 2, [nlv2, nlevels) ystep 1 (scales ascend)
+    int tiles2, tiles1;    // tile counts of the two classes
     LevelDesc lv[NV_MAX_LEVELS];
 };
 
@@ -110,6 +115,38 @@ struct ResizeKey {
     int sw = 0, sh = 0, dw = 0, dh = 0;
     bool operator==(const ResizeKey &o) const { return sw == o.sw && sh == o.sh && dw == o.dw && dh == o.dh; }
 };
+
+// ---- k_cascade_tiles parameters (passed by value as a __grid_constant__: tensor maps and the bulk
+// stages' weak classifiers live in the constant bank, so they cost no load/store-unit bandwidth) ----
+#define NV_BULK_MAX_STUMPS 400
+#define NV_BULK_MAX_STAGES 16
+#define NV_TILE 32                 // windows per tile side
+
+struct __align__(16) BulkStump {   // 48 bytes
+    uint16_t o[3][4];              // shared-memory word offsets of the rect corners: sum = a - b - c + d
+    float w[3];
+    float thr, left, right;
+};
+
+struct TileParams {
+    CUtensorMap maps[NV_MAX_LEVELS];
+    BulkStump stumps[NV_BULK_MAX_STUMPS];
+    int stage_first[NV_BULK_MAX_STAGES + 1];
+    float stage_thr[NV_BULK_MAX_STAGES];
+    int stage_begin, stage_end;    // bulk stages [begin, end)
+    int final_stage;               // 1: stage_end == nstages, survivors are candidates
+    int level_begin, level_end;
+    int cp, rt, ps;                // tile plane geometry: columns, rows, plane stride (words)
+    const PlanDev *plan;
+    const uint32_t *bits_alive;
+    const float *vnf;
+    int16_t *depth;
+    uint2 *tail;                   // (window id, vnf) of windows that outlive the bulk stages
+    uint32_t *cand;
+    int *counters;
+    int tail_cap, cand_cap;
+};
+static_assert(sizeof(TileParams) <= 32000, "kernel parameter space is 32764 bytes");
 
 // header of the device result block (then rects follow)
 struct ResultHeader {
@@ -148,7 +185,8 @@ struct nv_ctx {
     uint8_t *d_pyr = nullptr;    size_t pyr_cap = 0;        // debug level images
     float *d_vnf = nullptr;      size_t win_cap = 0;
     int16_t *d_depth = nullptr;  size_t depth_cap = 0;      // debug only
-    uint32_t *d_bits_fail = nullptr, *d_bits_ok = nullptr;  size_t bits_cap = 0;
+    uint32_t *d_bits_fail = nullptr, *d_bits_ok = nullptr;  size_t bits_cap = 0;   // [bits_ok doubles as bits_alive]
+    TileParams tp[2];  bool use_tiles = false;  int bulk_end = 0;  const nv_cascade *tp_casc = nullptr;
     uint2 *d_queue = nullptr;    size_t queue_cap = 0;
     int *d_counters = nullptr;                              // [0] queue count, [1] cand count, [2] overflow
     uint32_t *d_cand = nullptr;  int cand_cap = 0;          // packed window ids
@@ -208,6 +246,17 @@ cudaError_t launch_skip_compact(const PlanDev *plan, int total_rows, const float
 cudaError_t launch_queue_stages(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,
                                 const uint2 *queue, int *counters, uint32_t *cand, int cand_cap, int16_t *depth,
                                 int nblocks, cudaStream_t st);
+
+cudaError_t launch_stage0_rows(const PlanDev *plan, int total_rows, const DevCascade *meta, const DevStump *stumps,
+                               const uint32_t *sum, const uint32_t *sq, float *vnf, uint32_t *bits_alive, int *counters,
+                               int16_t *depth, cudaStream_t st);
+cudaError_t launch_cascade_tiles(const TileParams &tp, int ystep, int ntiles, cudaStream_t st);
+cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,
+                                const uint2 *tail, int *counters, uint32_t *cand, int cand_cap, int16_t *depth,
+                                int stage_begin, int order_free, int nblocks, cudaStream_t st);
+cudaError_t launch_alive_to_queue(const PlanDev *plan, int total_rows, const float *vnf, const uint32_t *bits_alive,
+                                  uint2 *queue, int *counters, int queue_cap, cudaStream_t st);
+void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_end, TileParams *tp);
 
 // kernels_group.cu
 cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *cand, int cand_cap, uint32_t *cand_sorted,

@@ -196,6 +196,351 @@ k_queue_stages(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ 
     }
 }
 
+// ================================================================================================
+// v2 pass structure (all levels per launch):
+//   k_stage0_rows      one warp per window ROW: variance + stage 0 for each 32-window chunk, the skip
+//                      automaton carried along the row in a register, one "alive" bit-word per chunk.
+//   k_cascade_tiles    one block per 32x32-window tile: the integral tile (+halo) is staged in shared
+//                      memory by TMA (one 2-D box per column plane), the tile's alive windows form a
+//                      queue, and stages 1..B-1 run with one lane per queued window and warp-ballot
+//                      compaction into the next queue between stages.  The weak classifiers of these
+//                      stages and the tensor maps sit in the kernel's parameter (constant) bank.
+//   k_cascade_tail     the few windows that outlive the bulk stages: one warp per window, the 32 lanes
+//                      evaluate 32 different weak classifiers of the stage on a private copy of the
+//                      window's integral patch; exact because the double stage sum is order-free for the
+//                      cascade (certificate computed at load), sequential shuffles otherwise.
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+k_stage0_rows(const PlanDev *__restrict__ plan, int total_rows, const DevCascade *__restrict__ meta,
+              const DevStump *__restrict__ stumps, const uint32_t *__restrict__ sum, const uint32_t *__restrict__ sq,
+              float *__restrict__ vnf_out, uint32_t *__restrict__ bits_alive, int *__restrict__ counters,
+              int16_t *__restrict__ depth)
+{
+    int lane = threadIdx.x & 31;
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    int l = find_level_c(plan, row, &LevelDesc::row0);
+    const LevelDesc &L = plan->lv[l];
+    int iy = row - L.row0;
+    LevelView v{sum + L.iofs, L.ipitch, L.iplane, L.ystep};
+    int ww = plan->win_w, wh = plan->win_h;
+    int c00 = corner(v, 1, 1), c10 = corner(v, ww - 1, 1), c01 = corner(v, 1, wh - 1), c11 = corner(v, ww - 1, wh - 1);
+    double area = (double)((ww - 2) * (wh - 2));
+    int n0 = meta->stage_first[1];
+    double thr0 = (double)meta->stage_thr[0];
+    size_t rowbase = (size_t)iy * L.ystep * L.ipitch;
+    bool e = true;                                   // is the next window visited?  (x = 0 always is)
+    int nalive = 0;
+    for (int cx = 0; cx < L.nxw; cx++) {
+        int ix = cx * 32 + lane;
+        bool valid = ix < L.nx;
+        int ixc = valid ? ix : L.nx - 1;
+        const uint32_t *wb = v.sum + rowbase + ixc, *qb = sq + L.iofs + rowbase + ixc;
+        int valsum = (int)(__ldg(wb + c00) - __ldg(wb + c10) - __ldg(wb + c01) + __ldg(wb + c11));
+        uint32_t valsq = __ldg(qb + c00) - __ldg(qb + c10) - __ldg(qb + c01) + __ldg(qb + c11);
+        double nf = __dsub_rn(__dmul_rn(area, (double)valsq), __dmul_rn((double)valsum, (double)valsum));
+        float vnf = 0.f;
+        bool ok = false;
+        if (nf > 0.) {
+            vnf = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn(nf)));
+            ok = __dmul_rn(area, (double)vnf) < 1e-1;
+        }
+        bool fail = false;
+        if (ok) {
+            double tmp = 0.;
+            for (int i = 0; i < n0; i++) {
+                StumpRegs s = load_stump(stumps + i);
+                tmp = __dadd_rn(tmp, (double)stump_leaf(wb, v, s, vnf));
+            }
+            fail = tmp < thr0;
+        }
+        ok = ok && valid;
+        fail = fail && ok;
+        uint32_t f = __ballot_sync(0xffffffffu, fail);
+        // e[i+1] = !(e[i] && stage0_failed[i]); every lane runs the same 32-step automaton
+        uint32_t em = 0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            em |= (uint32_t)e << i;
+            e = !(e && ((f >> i) & 1u));
+        }
+        bool visited = (em >> lane) & 1u;
+        bool alive = visited && ok && !fail;
+        uint32_t am = __ballot_sync(0xffffffffu, alive);
+        nalive += __popc(am);
+        if (lane == 0) bits_alive[L.bofs + iy * L.nxw + cx] = am;
+        if (alive) vnf_out[L.wofs + iy * L.nx + ix] = vnf;
+        if (depth && valid && !alive)
+            depth[L.wofs + iy * L.nx + ix] = (int16_t)(!visited ? NV_DEPTH_SKIPPED : (!ok ? NV_DEPTH_VARREJ : 0));
+    }
+    if (lane == 0 && nalive) atomicAdd(&counters[0], nalive);
+}
+
+// expands alive bit-words into a window queue (fallback path for cascades the tile kernel cannot take)
+__global__ void __launch_bounds__(256)
+k_alive_to_queue(const PlanDev *__restrict__ plan, int total_rows, const float *__restrict__ vnf,
+                 const uint32_t *__restrict__ bits_alive, uint2 *__restrict__ queue, int *__restrict__ counters,
+                 int queue_cap)
+{
+    int lane = threadIdx.x & 31;
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    int l = find_level_c(plan, row, &LevelDesc::row0);
+    const LevelDesc &L = plan->lv[l];
+    int iy = row - L.row0;
+    for (int cx = 0; cx < L.nxw; cx++) {
+        uint32_t am = bits_alive[L.bofs + iy * L.nxw + cx];
+        if (!am) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&counters[4], __popc(am));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((am >> lane) & 1u) {
+            int ix = cx * 32 + lane, pos = base + __popc(am & ((1u << lane) - 1u));
+            if (pos < queue_cap)
+                queue[pos] = make_uint2(((uint32_t)l << 26) | ((uint32_t)iy << 13) | (uint32_t)ix,
+                                        __float_as_uint(vnf[L.wofs + iy * L.nx + ix]));
+            else
+                counters[2] = 1;
+        }
+    }
+}
+
+// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+
+template <int YS>
+__global__ void __launch_bounds__(256) k_cascade_tiles(const __grid_constant__ TileParams P)
+{
+    extern __shared__ __align__(128) uint32_t tile[];           // [YS planes][rt][cp], plane stride ps
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ unsigned short q[2][NV_TILE * NV_TILE];
+    __shared__ float s_vnf[NV_TILE * NV_TILE];
+    __shared__ int s_cnt[3];
+    __shared__ int s_rowoff[33];
+    __shared__ int s_base;
+    const PlanDev *__restrict__ plan = P.plan;
+    int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    int t = blockIdx.x, l = P.level_begin;
+    while (l + 1 < P.level_end && plan->lv[l + 1].tile0 <= t) l++;
+    const LevelDesc &L = plan->lv[l];
+    int rel = t - L.tile0, ty = rel / L.nxw, tx = rel - ty * L.nxw;
+    int iy0 = ty * NV_TILE, ix0 = tx * NV_TILE;
+    const int CP = P.cp, PS = P.ps;
+    uint32_t bar = smem_u32(&mbar);
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {                                              // stage the integral tile: one box per plane
+        mbar_expect_tx(bar, (uint32_t)(YS * P.rt * CP * 4));
+#pragma unroll
+        for (int p = 0; p < YS; p++)
+            tma_load_2d(smem_u32(tile + p * PS), &P.maps[l], ix0 + p * L.iplane, iy0 * YS, bar);
+    }
+    // meanwhile: queue of the tile's alive windows, raster order
+    int nrows = min(NV_TILE, L.ny - iy0);
+    const uint32_t *aw = P.bits_alive + L.bofs + (size_t)iy0 * L.nxw + tx;
+    if (tid < 32) {
+        uint32_t w = tid < nrows ? aw[(size_t)tid * L.nxw] : 0u;
+        int c = __popc(w), inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += v;
+        }
+        s_rowoff[tid + 1] = inc;
+        if (tid == 0) s_rowoff[0] = 0;
+    }
+    __syncthreads();
+    for (int r = warp; r < nrows; r += 8) {
+        uint32_t w = aw[(size_t)r * L.nxw];
+        if ((w >> lane) & 1u) {
+            int id = (r << 5) | lane;
+            q[0][s_rowoff[r] + __popc(w & ((1u << lane) - 1u))] = (unsigned short)id;
+            s_vnf[id] = P.vnf[L.wofs + (iy0 + r) * L.nx + ix0 + lane];
+        }
+    }
+    int n = s_rowoff[32];
+    __syncthreads();
+    mbar_wait(bar, 0);                                           // also before an early exit: the copy targets this CTA's smem
+    if (n == 0) return;                                          // uniform: nothing alive in this tile
+
+    int cur = 0;
+    for (int st = P.stage_begin; st < P.stage_end && n > 0; st++) {
+        int k0 = P.stage_first[st - P.stage_begin], k1 = P.stage_first[st - P.stage_begin + 1];
+        double thr = (double)P.stage_thr[st - P.stage_begin];
+        int ci = st % 3, co = (st + 1) % 3, cz = (st + 2) % 3;   // rotating counters: in / out / to reset
+        if (tid == 0) s_cnt[cz] = 0;
+        (void)ci;
+        for (int b = warp * 32; b < n; b += 256) {
+            int i = b + lane;
+            bool active = i < n;
+            int id = q[cur][active ? i : b];
+            int ly = id >> 5, lx = id & 31;
+            const uint32_t *wb = tile + ly * YS * CP + lx;
+            float vnf = s_vnf[id];
+            double tmp = 0.;
+            for (int k = k0; k < k1; k++) {
+                const BulkStump &s = P.stumps[k];
+                int r0 = (int)(wb[s.o[0][0]] - wb[s.o[0][1]] - wb[s.o[0][2]] + wb[s.o[0][3]]);
+                int r1 = (int)(wb[s.o[1][0]] - wb[s.o[1][1]] - wb[s.o[1][2]] + wb[s.o[1][3]]);
+                float f = __fadd_rn(__fmul_rn(s.w[0], __int2float_rn(r0)), __fmul_rn(s.w[1], __int2float_rn(r1)));
+                if (s.w[2] != 0.f) {
+                    int r2 = (int)(wb[s.o[2][0]] - wb[s.o[2][1]] - wb[s.o[2][2]] + wb[s.o[2][3]]);
+                    f = __fadd_rn(f, __fmul_rn(s.w[2], __int2float_rn(r2)));
+                }
+                f = __fmul_rn(f, vnf);
+                tmp = __dadd_rn(tmp, (double)(f < s.thr ? s.left : s.right));
+            }
+            bool pass = active && !(tmp < thr);
+            uint32_t pm = __ballot_sync(0xffffffffu, pass);
+            if (pm) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_cnt[co], __popc(pm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) q[cur ^ 1][base + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)id;
+            }
+            if (P.depth && active && !pass) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = (int16_t)(-st);
+        }
+        __syncthreads();
+        n = s_cnt[co];
+        cur ^= 1;
+    }
+    if (n == 0) return;
+    // survivors: candidates if the bulk stages were the whole cascade, else the tail queue
+    int *counter = P.counters + (P.final_stage ? 1 : 3);
+    int cap = P.final_stage ? P.cand_cap : P.tail_cap;
+    if (tid == 0) s_base = atomicAdd(counter, n);
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        int id = q[cur][i], ly = id >> 5, lx = id & 31, pos = s_base + i;
+        uint32_t key = ((uint32_t)l << 26) | ((uint32_t)(iy0 + ly) << 13) | (uint32_t)(ix0 + lx);
+        if (pos >= cap) { P.counters[2] = 1; continue; }
+        if (P.final_stage) {
+            P.cand[pos] = key;
+            if (P.depth) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = NV_DEPTH_PASS;
+        } else
+            P.tail[pos] = make_uint2(key, __float_as_uint(s_vnf[id]));
+    }
+}
+
+#define TAIL_MAX_WIN 32
+__global__ void __launch_bounds__(256)
+k_cascade_tail(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ meta, const DevStump *__restrict__ stumps,
+               const uint32_t *__restrict__ sum, const uint2 *__restrict__ tail, int *__restrict__ counters,
+               uint32_t *__restrict__ cand, int cand_cap, int16_t *__restrict__ depth, int stage_begin, int order_free)
+{
+    __shared__ uint32_t s_win[8][(TAIL_MAX_WIN + 1) * (TAIL_MAX_WIN + 1)];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *win = s_win[warp];
+    int n = counters[3], nstages = meta->nstages;
+    int ww = plan->win_w, wh = plan->win_h, LP = ww + 1, npatch = (wh + 1) * LP;
+    for (int e = blockIdx.x * 8 + warp; e < n; e += gridDim.x * 8) {
+        uint2 q = tail[e];
+        int l = q.x >> 26, iy = (q.x >> 13) & 8191, ix = q.x & 8191;
+        float vnf = __uint_as_float(q.y);
+        const LevelDesc &L = plan->lv[l];
+        const uint32_t *wb = sum + L.iofs + (size_t)iy * L.ystep * L.ipitch + ix;
+        __syncwarp();
+        for (int idx = lane; idx < npatch; idx += 32) {          // private copy of the window's integral patch
+            int r = idx / LP, c = idx - r * LP;
+            int pc = L.ystep == 2 ? (c & 1) * L.iplane + (c >> 1) : c;
+            win[idx] = __ldg(wb + (size_t)r * L.ipitch + pc);
+        }
+        __syncwarp();
+        int code = NV_DEPTH_PASS;
+        for (int st = stage_begin; st < nstages; st++) {
+            int k0 = meta->stage_first[st], k1 = meta->stage_first[st + 1];
+            double tmp = 0.;
+            for (int kb = k0; kb < k1; kb += 32) {               // 32 weak classifiers per round, one per lane
+                int k = kb + lane;
+                double leaf = 0.;
+                if (k < k1) {
+                    StumpRegs s = load_stump(stumps + k);
+                    float f = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        uint32_t pr = j == 0 ? s.r0 : (j == 1 ? s.r1 : s.r2);
+                        float wj = j == 0 ? s.w0 : (j == 1 ? s.w1 : s.w2);
+                        if (j == 2 && wj == 0.f) break;
+                        int x = pr & 255, y = (pr >> 8) & 255, w = (pr >> 16) & 255, h = pr >> 24;
+                        int rs = (int)(win[y * LP + x] - win[y * LP + x + w] - win[(y + h) * LP + x] + win[(y + h) * LP + x + w]);
+                        float t = __fmul_rn(wj, __int2float_rn(rs));
+                        f = j == 0 ? t : __fadd_rn(f, t);
+                    }
+                    f = __fmul_rn(f, vnf);
+                    leaf = (double)(f < s.thr ? s.left : s.right);
+                }
+                if (order_free) tmp = __dadd_rn(tmp, leaf);       // per-lane partial, reduced below
+                else
+                    for (int j = 0; j < 32; j++) tmp = __dadd_rn(tmp, __shfl_sync(0xffffffffu, leaf, j));   // in XML order
+            }
+            if (order_free)
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) tmp = __dadd_rn(tmp, __shfl_xor_sync(0xffffffffu, tmp, d));
+            if (tmp < (double)meta->stage_thr[st]) { code = -st; break; }
+        }
+        if (lane == 0) {
+            if (depth) depth[L.wofs + iy * L.nx + ix] = (int16_t)code;
+            if (code == NV_DEPTH_PASS) {
+                int pos = atomicAdd(&counters[1], 1);
+                if (pos < cand_cap) cand[pos] = q.x;
+                else counters[2] = 1;
+            }
+        }
+    }
+}
+
+// host: bulk-stage weak classifiers with shared-memory corner offsets for one ystep class
+void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_end, TileParams *tp)
+{
+    const DevCascade &m = c->meta;
+    tp->stage_begin = 1;
+    tp->stage_end = stage_end;
+    tp->final_stage = stage_end == m.nstages;
+    int base = m.stage_first[1];
+    for (int s = 1; s <= stage_end; s++) tp->stage_first[s - 1] = m.stage_first[s] - base;
+    for (int s = 1; s < stage_end; s++) tp->stage_thr[s - 1] = m.stage_thr[s];
+    auto off = [&](int dx, int dy) { return ystep == 2 ? (dx & 1) * ps + dy * cp + (dx >> 1) : dy * cp + dx; };
+    for (int k = m.stage_first[1]; k < m.stage_first[stage_end]; k++) {
+        const DevStump &d = c->stumps[k];
+        BulkStump &b = tp->stumps[k - base];
+        for (int j = 0; j < 3; j++) {
+            int x = d.r[j] & 255, y = (d.r[j] >> 8) & 255, w = (d.r[j] >> 16) & 255, h = d.r[j] >> 24;
+            b.o[j][0] = (uint16_t)off(x, y); b.o[j][1] = (uint16_t)off(x + w, y);
+            b.o[j][2] = (uint16_t)off(x, y + h); b.o[j][3] = (uint16_t)off(x + w, y + h);
+            b.w[j] = d.w[j];
+        }
+        b.thr = d.thr; b.left = d.left; b.right = d.right;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_stage0(const PlanDev *plan, int total_chunks, const DevCascade *meta, const DevStump *stumps,
                           const uint32_t *sum, const uint32_t *sq, float *vnf, uint32_t *bits_fail, uint32_t *bits_ok,
@@ -219,5 +564,37 @@ cudaError_t launch_queue_stages(const PlanDev *plan, const DevCascade *meta, con
                                 int nblocks, cudaStream_t st)
 {
     k_queue_stages<<<nblocks, 256, 0, st>>>(plan, meta, stumps, sum, queue, counters, cand, cand_cap, depth);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stage0_rows(const PlanDev *plan, int total_rows, const DevCascade *meta, const DevStump *stumps,
+                               const uint32_t *sum, const uint32_t *sq, float *vnf, uint32_t *bits_alive, int *counters,
+                               int16_t *depth, cudaStream_t st)
+{
+    k_stage0_rows<<<(total_rows + 7) / 8, 256, 0, st>>>(plan, total_rows, meta, stumps, sum, sq, vnf, bits_alive, counters, depth);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_alive_to_queue(const PlanDev *plan, int total_rows, const float *vnf, const uint32_t *bits_alive,
+                                  uint2 *queue, int *counters, int queue_cap, cudaStream_t st)
+{
+    k_alive_to_queue<<<(total_rows + 7) / 8, 256, 0, st>>>(plan, total_rows, vnf, bits_alive, queue, counters, queue_cap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cascade_tiles(const TileParams &tp, int ystep, int ntiles, cudaStream_t st)
+{
+    size_t smem = (size_t)ystep * tp.ps * sizeof(uint32_t);
+    if (ystep == 2) k_cascade_tiles<2><<<ntiles, 256, smem, st>>>(tp);
+    else k_cascade_tiles<1><<<ntiles, 256, smem, st>>>(tp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,
+                                const uint2 *tail, int *counters, uint32_t *cand, int cand_cap, int16_t *depth,
+                                int stage_begin, int order_free, int nblocks, cudaStream_t st)
+{
+    k_cascade_tail<<<nblocks, 256, 0, st>>>(plan, meta, stumps, sum, tail, counters, cand, cand_cap, depth, stage_begin,
+                                            order_free);
     return cudaGetLastError();
 }
