@@ -206,7 +206,7 @@ extern "C" void nv_ctx_destroy(nv_ctx *c)
     cudaFree(c->d_bits_ok); cudaFree(c->d_queue); cudaFree(c->d_counters); cudaFree(c->d_cand);
     cudaFree(c->d_cand_sorted); cudaFree(c->d_cand_rects); cudaFree(c->d_adj); cudaFree(c->d_result);
     cudaFreeHost(c->h_result);
-    cudaFree(c->d_trk_prev); cudaFree(c->d_trk_mhi); cudaFree(c->d_trk_labels); cudaFree(c->d_trk_mask);
+    cudaFree(c->d_maps); cudaFree(c->d_trk_prev); cudaFree(c->d_trk_mhi); cudaFree(c->d_trk_labels); cudaFree(c->d_trk_mask);
     cudaFree(c->d_trk_boxes); cudaFree(c->d_trk_misc); cudaFreeHost(c->h_trk);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     for (int i = 0; i <= NV_NUM_STAGES; i++) if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
@@ -428,10 +428,16 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
     int end = 1;
     while (end < m.nstages && end < NV_BULK_MAX_STAGES && m.stage_first[end + 1] - m.stage_first[1] <= NV_BULK_MAX_STUMPS) end++;
     ctx->bulk_end = end;
+    static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+    alignas(64) CUtensorMap maps[NV_MAX_LEVELS];
+    memset(maps, 0, sizeof maps);
+    if (!ctx->d_maps) NV_CUDA(cudaMalloc(&ctx->d_maps, sizeof maps));
     for (int c = 0; c < 2; c++) {
         int ys = c == 0 ? 2 : 1;
         TileParams &tp = ctx->tp[c];
-        tp.cp = align_up(NV_TILE + (ys == 2 ? m.win_w / 2 : m.win_w) + 1, 4);
+        // columns per plane; ys*cp is a multiple of 32 words so that windows of different rows with different
+        // lx never share a bank (a raster-ordered batch of 32 alive windows is then conflict-free)
+        tp.cp = align_up(NV_TILE + (ys == 2 ? m.win_w / 2 : m.win_w) + 1, 32 / ys);
         tp.rt = (NV_TILE - 1) * ys + m.win_h + 1;
         tp.ps = align_up(tp.rt * tp.cp, 32);
         tp.level_begin = c == 0 ? 0 : P.nlv2;
@@ -443,12 +449,14 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
             cuuint64_t gstr[1] = {(cuuint64_t)L.ipitch * 4};
             cuuint32_t box[2] = {(cuuint32_t)tp.cp, (cuuint32_t)tp.rt};
             cuuint32_t estr[2] = {1, 1};
-            CUresult r = enc(&tp.maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, ctx->d_sum + L.iofs, gdim, gstr, box, estr,
+            CUresult r = enc(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, ctx->d_sum + L.iofs, gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return NV_OK;       // keep the generic queue path for this plan
         }
     }
+    NV_CUDA(cudaStreamSynchronize(ctx->stream));
+    NV_CUDA(cudaMemcpy(ctx->d_maps, maps, sizeof maps, cudaMemcpyHostToDevice));
     ctx->use_tiles = true;
     return NV_OK;
 }
@@ -492,7 +500,7 @@ static int detect_on_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray
                 int ntiles = c == 0 ? P.tiles2 : P.tiles1;
                 if (ntiles == 0) continue;
                 tp.plan = ctx->d_plan; tp.bits_alive = ctx->d_bits_ok; tp.vnf = ctx->d_vnf; tp.depth = depth;
-                tp.tail = ctx->d_queue; tp.cand = ctx->d_cand; tp.counters = ctx->d_counters;
+                tp.tail = ctx->d_queue; tp.cand = ctx->d_cand; tp.counters = ctx->d_counters; tp.maps = ctx->d_maps;
                 tp.tail_cap = qcap; tp.cand_cap = ctx->cand_cap;
                 NV_CUDA(launch_cascade_tiles(tp, c == 0 ? 2 : 1, ntiles, st));
                 nl++;

@@ -122,21 +122,17 @@ struct ResizeKey {
 #define NV_BULK_MAX_STAGES 16
 #define NV_TILE 32                 // windows per tile side
 
-struct __align__(16) BulkStump {   // 48 bytes
-    uint16_t o[3][4];              // shared-memory word offsets of the rect corners: sum = a - b - c + d
-    float w[3];
-    float thr, left, right;
-};
-
 struct TileParams {
-    CUtensorMap maps[NV_MAX_LEVELS];
-    BulkStump stumps[NV_BULK_MAX_STUMPS];
+    uint4 off[NV_BULK_MAX_STUMPS][3];   // per rect: BYTE offsets of the corners a, b, c, d in the shared-memory tile
+    float2 cf[NV_BULK_MAX_STUMPS][3];   // (w0, w1), (w2, threshold), (left, right)
     int stage_first[NV_BULK_MAX_STAGES + 1];
     float stage_thr[NV_BULK_MAX_STAGES];
     int stage_begin, stage_end;    // bulk stages [begin, end)
     int final_stage;               // 1: stage_end == nstages, survivors are candidates
+    int order_free;                // stage sums may be split across warps (cascade certificate)
     int level_begin, level_end;
     int cp, rt, ps;                // tile plane geometry: columns, rows, plane stride (words)
+    const CUtensorMap *maps;       // one per level, in global memory (written by the host before launch)
     const PlanDev *plan;
     const uint32_t *bits_alive;
     const float *vnf;
@@ -186,7 +182,7 @@ struct nv_ctx {
     float *d_vnf = nullptr;      size_t win_cap = 0;
     int16_t *d_depth = nullptr;  size_t depth_cap = 0;      // debug only
     uint32_t *d_bits_fail = nullptr, *d_bits_ok = nullptr;  size_t bits_cap = 0;   // [bits_ok doubles as bits_alive]
-    TileParams tp[2];  bool use_tiles = false;  int bulk_end = 0;  const nv_cascade *tp_casc = nullptr;
+    TileParams tp[2];  CUtensorMap *d_maps = nullptr;  bool use_tiles = false;  int bulk_end = 0;  const nv_cascade *tp_casc = nullptr;
     uint2 *d_queue = nullptr;    size_t queue_cap = 0;
     int *d_counters = nullptr;                              // [0] queue count, [1] cand count, [2] overflow
     uint32_t *d_cand = nullptr;  int cand_cap = 0;          // packed window ids

@@ -331,6 +331,38 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y) : "memory");
 }
 
+// A value that is the same in every lane, rebuilt from warp votes so that the compiler can PROVE it is
+// warp-uniform (vote results are) and keep loop control on the uniform datapath.
+__device__ __forceinline__ int uniformize(int v, int bits)
+{
+    int r = 0;
+    for (int k = 0; k < bits; k++) r |= (int)(__ballot_sync(0xffffffffu, (v >> k) & 1) & (1u << k));
+    return r;
+}
+
+// one stage slice [ka, kb) of weak classifiers for the window whose tile origin is byte pointer wb
+__device__ __forceinline__ double bulk_stage_sum(const TileParams &P, const uint8_t *wb, float vnf, int ka, int kb)
+{
+    double tmp = 0.;
+    for (int k = ka; k < kb; k++) {
+        uint4 o0 = P.off[k][0], o1 = P.off[k][1];
+        float2 w01 = P.cf[k][0], w2t = P.cf[k][1], lr = P.cf[k][2];
+#define TILE_AT(o) (*reinterpret_cast<const uint32_t *>(wb + (o)))
+        int r0 = (int)(TILE_AT(o0.x) - TILE_AT(o0.y) - TILE_AT(o0.z) + TILE_AT(o0.w));
+        int r1 = (int)(TILE_AT(o1.x) - TILE_AT(o1.y) - TILE_AT(o1.z) + TILE_AT(o1.w));
+        float f = __fadd_rn(__fmul_rn(w01.x, __int2float_rn(r0)), __fmul_rn(w01.y, __int2float_rn(r1)));
+        if (w2t.x != 0.f) {
+            uint4 o2 = P.off[k][2];
+            int r2 = (int)(TILE_AT(o2.x) - TILE_AT(o2.y) - TILE_AT(o2.z) + TILE_AT(o2.w));
+            f = __fadd_rn(f, __fmul_rn(w2t.x, __int2float_rn(r2)));
+        }
+#undef TILE_AT
+        f = __fmul_rn(f, vnf);
+        tmp = __dadd_rn(tmp, (double)(f < w2t.y ? lr.x : lr.y));
+    }
+    return tmp;
+}
+
 template <int YS>
 __global__ void __launch_bounds__(256) k_cascade_tiles(const __grid_constant__ TileParams P)
 {
@@ -338,11 +370,13 @@ __global__ void __launch_bounds__(256) k_cascade_tiles(const __grid_constant__ T
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ unsigned short q[2][NV_TILE * NV_TILE];
     __shared__ float s_vnf[NV_TILE * NV_TILE];
+    __shared__ double s_part[8][32];
     __shared__ int s_cnt[3];
     __shared__ int s_rowoff[33];
     __shared__ int s_base;
     const PlanDev *__restrict__ plan = P.plan;
-    int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = uniformize(tid >> 5, 3);
 
     int t = blockIdx.x, l = P.level_begin;
     while (l + 1 < P.level_end && plan->lv[l + 1].tile0 <= t) l++;
@@ -361,14 +395,14 @@ __global__ void __launch_bounds__(256) k_cascade_tiles(const __grid_constant__ T
         mbar_expect_tx(bar, (uint32_t)(YS * P.rt * CP * 4));
 #pragma unroll
         for (int p = 0; p < YS; p++)
-            tma_load_2d(smem_u32(tile + p * PS), &P.maps[l], ix0 + p * L.iplane, iy0 * YS, bar);
+            tma_load_2d(smem_u32(tile + p * PS), P.maps + l, ix0 + p * L.iplane, iy0 * YS, bar);
     }
     // meanwhile: queue of the tile's alive windows, raster order
     int nrows = min(NV_TILE, L.ny - iy0);
     const uint32_t *aw = P.bits_alive + L.bofs + (size_t)iy0 * L.nxw + tx;
     if (tid < 32) {
         uint32_t w = tid < nrows ? aw[(size_t)tid * L.nxw] : 0u;
-        int c = __popc(w), inc = c;
+        int inc = __popc(w);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             int v = __shfl_up_sync(0xffffffffu, inc, d);
@@ -386,50 +420,66 @@ __global__ void __launch_bounds__(256) k_cascade_tiles(const __grid_constant__ T
             s_vnf[id] = P.vnf[L.wofs + (iy0 + r) * L.nx + ix0 + lane];
         }
     }
-    int n = s_rowoff[32];
+    int n = uniformize(s_rowoff[32], 11);
     __syncthreads();
     mbar_wait(bar, 0);                                           // also before an early exit: the copy targets this CTA's smem
     if (n == 0) return;                                          // uniform: nothing alive in this tile
 
+    const uint8_t *tile8 = reinterpret_cast<const uint8_t *>(tile);
     int cur = 0;
     for (int st = P.stage_begin; st < P.stage_end && n > 0; st++) {
         int k0 = P.stage_first[st - P.stage_begin], k1 = P.stage_first[st - P.stage_begin + 1];
         double thr = (double)P.stage_thr[st - P.stage_begin];
-        int ci = st % 3, co = (st + 1) % 3, cz = (st + 2) % 3;   // rotating counters: in / out / to reset
+        int co = (st + 1) % 3, cz = (st + 2) % 3;                // rotating counters: out / to reset
         if (tid == 0) s_cnt[cz] = 0;
-        (void)ci;
-        for (int b = warp * 32; b < n; b += 256) {
-            int i = b + lane;
-            bool active = i < n;
-            int id = q[cur][active ? i : b];
-            int ly = id >> 5, lx = id & 31;
-            const uint32_t *wb = tile + ly * YS * CP + lx;
-            float vnf = s_vnf[id];
-            double tmp = 0.;
-            for (int k = k0; k < k1; k++) {
-                const BulkStump &s = P.stumps[k];
-                int r0 = (int)(wb[s.o[0][0]] - wb[s.o[0][1]] - wb[s.o[0][2]] + wb[s.o[0][3]]);
-                int r1 = (int)(wb[s.o[1][0]] - wb[s.o[1][1]] - wb[s.o[1][2]] + wb[s.o[1][3]]);
-                float f = __fadd_rn(__fmul_rn(s.w[0], __int2float_rn(r0)), __fmul_rn(s.w[1], __int2float_rn(r1)));
-                if (s.w[2] != 0.f) {
-                    int r2 = (int)(wb[s.o[2][0]] - wb[s.o[2][1]] - wb[s.o[2][2]] + wb[s.o[2][3]]);
-                    f = __fadd_rn(f, __fmul_rn(s.w[2], __int2float_rn(r2)));
+        int B = (n + 31) >> 5;                                   // 32-window batches in this stage
+        int S = (P.order_free && B < 8) ? 8 / B : 1;             // warps per batch: the stage's classifiers are split
+        if (S == 1) {
+            for (int b = warp * 32; b < n; b += 256) {
+                int i = b + lane;
+                bool active = i < n;
+                int id = q[cur][active ? i : b];
+                int ly = id >> 5, lx = id & 31;
+                double tmp = bulk_stage_sum(P, tile8 + (ly * YS * CP + lx) * 4, s_vnf[id], k0, k1);
+                bool pass = active && !(tmp < thr);
+                uint32_t pm = __ballot_sync(0xffffffffu, pass);
+                if (pm) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_cnt[co], __popc(pm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (pass) q[cur ^ 1][base + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)id;
                 }
-                f = __fmul_rn(f, vnf);
-                tmp = __dadd_rn(tmp, (double)(f < s.thr ? s.left : s.right));
+                if (P.depth && active && !pass) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = (int16_t)(-st);
             }
-            bool pass = active && !(tmp < thr);
-            uint32_t pm = __ballot_sync(0xffffffffu, pass);
-            if (pm) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_cnt[co], __popc(pm));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) q[cur ^ 1][base + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)id;
+        } else {
+            // few windows left: batch bt is shared by S warps, each summing a slice of the stage (exact: the
+            // double sum is order-free for this cascade), partial sums meet in shared memory
+            bool wact = warp < B * S;
+            int bt = warp % B, sl = warp / B;
+            int len = (k1 - k0 + S - 1) / S, ka = min(k1, k0 + sl * len), kb = min(k1, ka + len);
+            int i = bt * 32 + lane;
+            bool active = wact && i < n;
+            int id = q[cur][active ? i : 0];
+            int ly = id >> 5, lx = id & 31;
+            double tmp = 0.;
+            if (wact) tmp = bulk_stage_sum(P, tile8 + (ly * YS * CP + lx) * 4, s_vnf[id], ka, kb);
+            if (wact && sl > 0) s_part[warp][lane] = tmp;
+            __syncthreads();
+            if (wact && sl == 0) {
+                for (int j = 1; j < S; j++) tmp = __dadd_rn(tmp, s_part[bt + j * B][lane]);
+                bool pass = active && !(tmp < thr);
+                uint32_t pm = __ballot_sync(0xffffffffu, pass);
+                if (pm) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_cnt[co], __popc(pm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (pass) q[cur ^ 1][base + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)id;
+                }
+                if (P.depth && active && !pass) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = (int16_t)(-st);
             }
-            if (P.depth && active && !pass) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = (int16_t)(-st);
         }
         __syncthreads();
-        n = s_cnt[co];
+        n = uniformize(s_cnt[co], 11);
         cur ^= 1;
     }
     if (n == 0) return;
@@ -517,27 +567,28 @@ k_cascade_tail(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ 
     }
 }
 
-// host: bulk-stage weak classifiers with shared-memory corner offsets for one ystep class
+// host: bulk-stage weak classifiers with shared-memory corner BYTE offsets for one ystep class
 void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_end, TileParams *tp)
 {
     const DevCascade &m = c->meta;
     tp->stage_begin = 1;
     tp->stage_end = stage_end;
     tp->final_stage = stage_end == m.nstages;
+    tp->order_free = c->h.order_free;
     int base = m.stage_first[1];
     for (int s = 1; s <= stage_end; s++) tp->stage_first[s - 1] = m.stage_first[s] - base;
     for (int s = 1; s < stage_end; s++) tp->stage_thr[s - 1] = m.stage_thr[s];
-    auto off = [&](int dx, int dy) { return ystep == 2 ? (dx & 1) * ps + dy * cp + (dx >> 1) : dy * cp + dx; };
+    auto off = [&](int dx, int dy) { return 4u * (uint32_t)(ystep == 2 ? (dx & 1) * ps + dy * cp + (dx >> 1) : dy * cp + dx); };
     for (int k = m.stage_first[1]; k < m.stage_first[stage_end]; k++) {
         const DevStump &d = c->stumps[k];
-        BulkStump &b = tp->stumps[k - base];
+        int i = k - base;
         for (int j = 0; j < 3; j++) {
             int x = d.r[j] & 255, y = (d.r[j] >> 8) & 255, w = (d.r[j] >> 16) & 255, h = d.r[j] >> 24;
-            b.o[j][0] = (uint16_t)off(x, y); b.o[j][1] = (uint16_t)off(x + w, y);
-            b.o[j][2] = (uint16_t)off(x, y + h); b.o[j][3] = (uint16_t)off(x + w, y + h);
-            b.w[j] = d.w[j];
+            tp->off[i][j] = make_uint4(off(x, y), off(x + w, y), off(x, y + h), off(x + w, y + h));
         }
-        b.thr = d.thr; b.left = d.left; b.right = d.right;
+        tp->cf[i][0] = make_float2(d.w[0], d.w[1]);
+        tp->cf[i][1] = make_float2(d.w[2], d.thr);
+        tp->cf[i][2] = make_float2(d.left, d.right);
     }
 }
 
