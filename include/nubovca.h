@@ -143,6 +143,51 @@ NV_API int nv_resize_linear(nv_ctx *ctx, const uint8_t *src, int width, int heig
 NV_API int nv_flip_horizontal(nv_ctx *ctx, const uint8_t *src, int width, int height, int stride_bytes,
                               uint8_t *dst, int dst_stride);
 
+/* ---- element mirrors: the per-frame logic of the six GStreamer elements without GStreamer.
+ *      Same factory names (kmsfacedetect.cpp:21, kmseyedetect.cpp:23, kmsmouthdetect.cpp:19,
+ *      kmsnosedetect.cpp:24, kmseardetect.cpp:24, gstnubotracker.cpp:22), same GObject property names,
+ *      ranges and defaults (kmsfacedetect.cpp:1043-1102, kmseyedetect.cpp:1274-1320, kmsmouthdetect.cpp:
+ *      1078-1121, kmsnosedetect.cpp:1090-1133, kmseardetect.cpp:995-1038, gstnubotracker.cpp:504-542),
+ *      same frame gating, ROI arithmetic, temporal smoothing, downstream "message" structures and
+ *      signal strings.  A GStreamer shell only has to forward properties, sink events and buffers
+ *      (INTEGRATION.md).  nv_element_transform_frame_ip stands in for GstVideoFilterClass::
+ *      transform_frame_ip (kmsfacedetect.cpp:857-898, kmseyedetect.cpp:1107-1141,
+ *      kmsmouthdetect.cpp:912-946, kmsnosedetect.cpp:915-955, kmseardetect.cpp:830-866,
+ *      gstnubotracker.cpp:423-445); it always succeeds from the pipeline's point of view
+ *      (the reference always returns GST_FLOW_OK): failures are reported through the return code and
+ *      the frame passes through untouched. ------------------------------------------------------- */
+typedef struct nv_element nv_element;
+
+/* one sub-structure of the downstream custom event ("message"/"noses" GstStructure) */
+typedef struct {
+    char name[16];            /* structure name: "face", "eye_left", "eye_right", "mouth", "noses", "face_profile", "ear" */
+    char type[16];            /* its "type" field: "face", "eye", "mouth", "nose", "face_profile", "ear"               */
+    unsigned x, y, width, height;
+} nv_meta_rect;
+
+NV_API int nv_element_create(const char *factory_name, int gpu, const char *cascade_dir, nv_element **out);
+NV_API void nv_element_destroy(nv_element *e);
+NV_API int nv_element_set_property(nv_element *e, const char *name, long value);
+NV_API int nv_element_get_property(nv_element *e, const char *name, long *value);
+/* sink_event: a queued upstream "message" carrying face rectangles (kmseyedetect.cpp:192-218,680-724),
+ * or the "motion" event the face element waits for in detect-event mode (kmsfacedetect.cpp:698-707) */
+NV_API int nv_element_push_faces_event(nv_element *e, const nv_rect *faces, int n);
+NV_API int nv_element_push_motion_event(nv_element *e);
+/* one video buffer.  frame: BGR (detectors) or BGRA (tracker), modified in place only when a view-*
+ * property asks for it (drawing is not implemented yet: SURVEY K13).  now_ms < 0 uses gettimeofday for
+ * the events-ms rate limit; the tracker's MHI timestamp is pts_ns / 1e6 unless now_ms >= 0. */
+NV_API int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int width, int height, int stride_bytes,
+                                         uint64_t pts_ns, double now_ms);
+/* what the last frame produced: the downstream event's sub-structures (pushed != 0 if the element
+ * pushed the event; the ear element builds it but never pushes, kmseardetect.cpp:210-290) and the
+ * signal payload ("x:..,y:..,width:..,height:..;" repeated) if the signal fired */
+NV_API int nv_element_get_message(nv_element *e, nv_meta_rect *out, int cap, int *n, int *pushed);
+NV_API int nv_element_get_signal(nv_element *e, char *buf, int cap, int *emitted);
+/* host-logic taps for unit tests: Faces::track_faces (Faces.cpp:78-153) on explicit lists */
+NV_API int nv_debug_track_faces(const nv_rect *prev, const int *prev_ids, int nprev, int next_id, const nv_rect *cur,
+                                int ncur, int track_threshold, int pos_threshold, int area_threshold, nv_rect *out,
+                                int *out_ids, int cap, int *n, int *next_id_out);
+
 /* ---- device-side timing (bench.py): CUDA events on the ctx's own stream.  With profiling on, every
  *      pipeline stage of a detect call is bracketed by events; times are read after collect.
  *      Stage slots: see nv_stage_name(). ------------------------------------------------------ */

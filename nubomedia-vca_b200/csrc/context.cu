@@ -201,7 +201,7 @@ extern "C" void nv_ctx_destroy(nv_ctx *c)
     cudaSetDevice(c->gpu);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_frame); cudaFree(c->d_frame); cudaFree(c->d_gray); cudaFree(c->d_hist); cudaFree(c->d_lut);
-    cudaFree(c->d_aux); cudaFree(c->d_rtab); cudaFree(c->d_plan); cudaFree(c->d_ptab); cudaFree(c->d_sum);
+    cudaFree(c->d_aux); for (auto &e : c->rtabs) cudaFree(e.d); cudaFree(c->d_plan); cudaFree(c->d_ptab); cudaFree(c->d_sum);
     cudaFree(c->d_sq); cudaFree(c->d_pyr); cudaFree(c->d_vnf); cudaFree(c->d_depth); cudaFree(c->d_bits_fail);
     cudaFree(c->d_bits_ok); cudaFree(c->d_queue); cudaFree(c->d_counters); cudaFree(c->d_cand);
     cudaFree(c->d_cand_sorted); cudaFree(c->d_cand_rects); cudaFree(c->d_adj); cudaFree(c->d_result);
@@ -464,7 +464,7 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
 // ------------------------------------------------------------------------------------------------
 // detectMultiScale on a device-resident gray image (+ LUT), everything stream-ordered
 // ------------------------------------------------------------------------------------------------
-static int detect_on_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W, int H, int gstride,
+int nv_detect_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W, int H, int gstride,
                             const uint8_t *d_lut, const nv_detect_params *p)
 {
     int rc = ensure_plan(ctx, casc, W, H, p);
@@ -534,7 +534,7 @@ static int detect_on_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray
     return NV_OK;
 }
 
-static int collect(nv_ctx *ctx, nv_rect *out, int cap, int *n)
+int nv_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n)
 {
     if (!ctx->pending) { nv_set_error("collect without a pending submit"); return NV_ERR_STATE; }
     NV_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -550,7 +550,7 @@ static int collect(nv_ctx *ctx, nv_rect *out, int cap, int *n)
         int rc = alloc_candidates(ctx, std::min(lim, need + need / 4 + 64), ctx->last_min_neighbors > 0);
         if (rc != NV_OK) return rc;
         nv_detect_params p = ctx->last_params;
-        rc = detect_on_device(ctx, ctx->last_casc, ctx->tap_gray, ctx->last_W, ctx->last_H, ctx->tap_stride, ctx->tap_lut, &p);
+        rc = nv_detect_device(ctx, ctx->last_casc, ctx->tap_gray, ctx->last_W, ctx->last_H, ctx->tap_stride, ctx->tap_lut, &p);
         if (rc != NV_OK) return rc;
         NV_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->pending = false;
@@ -594,26 +594,34 @@ extern "C" int nv_detect_multiscale(nv_ctx *ctx, const nv_cascade *c, const uint
     if (ctx->pending) NV_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(ctx->h_frame, gray, (size_t)stride_bytes * height);
     NV_CUDA(cudaMemcpyAsync(ctx->d_frame, ctx->h_frame, (size_t)stride_bytes * height, cudaMemcpyHostToDevice, ctx->stream));
-    rc = detect_on_device(ctx, const_cast<nv_cascade *>(c), ctx->d_frame, width, height, stride_bytes, ctx->d_lut + 256, p);
+    rc = nv_detect_device(ctx, const_cast<nv_cascade *>(c), ctx->d_frame, width, height, stride_bytes, ctx->d_lut + 256, p);
     if (rc != NV_OK) return rc;
-    return collect(ctx, out, cap, n);
+    return nv_collect(ctx, out, cap, n);
 }
 
 // ------------------------------------------------------------------------------------------------
 // face element hot block
 // ------------------------------------------------------------------------------------------------
-static int ensure_rtab(nv_ctx *ctx, int sw, int sh, int dw, int dh)
+int nv_get_rtab(nv_ctx *ctx, int sw, int sh, int dw, int dh, const int **d_tab)
 {
     ResizeKey k;
     k.sw = sw; k.sh = sh; k.dw = dw; k.dh = dh;
-    if (ctx->d_rtab && k == ctx->rkey) return NV_OK;
+    for (auto &e : ctx->rtabs)
+        if (e.d && e.k == k) { *d_tab = e.d; return NV_OK; }
     std::vector<int> tab;
     build_resize_tables(sw, sh, dw, dh, tab);
-    NV_CUDA(cudaStreamSynchronize(ctx->stream));
-    int rc = ensure(&ctx->d_rtab, &ctx->rtab_cap, tab.size());
-    if (rc != NV_OK) return rc;
-    NV_CUDA(cudaMemcpy(ctx->d_rtab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
-    ctx->rkey = k;
+    nv_ctx::RtabEntry &e = ctx->rtabs[ctx->rtab_next];
+    ctx->rtab_next = (ctx->rtab_next + 1) % 16;
+    if (e.d) {
+        NV_CUDA(cudaStreamSynchronize(ctx->stream));       // an in-flight kernel may still read the evicted table
+        NV_CUDA(cudaFree(e.d));
+        e.d = nullptr;
+    }
+    NV_CUDA(cudaMalloc(&e.d, tab.size() * sizeof(int)));
+    NV_CUDA(cudaMemcpyAsync(e.d, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    NV_CUDA(cudaStreamSynchronize(ctx->stream));           // tab is a local
+    e.k = k;
+    *d_tab = e.d;
     return NV_OK;
 }
 
@@ -635,7 +643,8 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
     int rows = height, cols = width;
     if (iscale > 0 && cv_round(height / scale) > 0) rows = cv_round(height / scale); else scale = 1;
     if (scale > 0 && cv_round(width / scale) > 0) cols = cv_round(width / scale); else scale = 1;
-    if ((rc = ensure_rtab(ctx, width, height, cols, rows)) != NV_OK) return rc;
+    const int *d_rtab;
+    if ((rc = nv_get_rtab(ctx, width, height, cols, rows, &d_rtab)) != NV_OK) return rc;
     const uint8_t *d_src = bgr;
     if (!on_device) {
         memcpy(ctx->h_frame, bgr, (size_t)stride * height);
@@ -644,7 +653,7 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
     }
     ctx->prof_set[0] = ctx->prof_set[1] = false;
     prof_mark(ctx, 0);
-    NV_CUDA(launch_face_prep(d_src, width, height, stride, 3, ctx->d_gray, cols, rows, ctx->d_rtab, ctx->d_hist, ctx->stream));
+    NV_CUDA(launch_face_prep(d_src, width, height, stride, 3, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream));
     prof_mark(ctx, 1);
     NV_CUDA(launch_lut(ctx->d_hist, cols * rows, ctx->d_lut, ctx->stream));
     ctx->launches += 2;
@@ -653,7 +662,7 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
     dp.min_w = p->min_w < 0 ? cols / 20 : p->min_w;           // kmsfacedetect.cpp:811
     dp.min_h = p->min_w < 0 ? rows / 20 : p->min_h;
     dp.max_w = dp.max_h = 0;
-    return detect_on_device(ctx, const_cast<nv_cascade *>(c), ctx->d_gray, cols, rows, cols, ctx->d_lut, &dp);
+    return nv_detect_device(ctx, const_cast<nv_cascade *>(c), ctx->d_gray, cols, rows, cols, ctx->d_lut, &dp);
 }
 
 extern "C" int nv_face_submit(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, int width, int height,
@@ -672,7 +681,7 @@ extern "C" int nv_face_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n)
 {
     if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }
     NV_CUDA(cudaSetDevice(ctx->gpu));
-    return collect(ctx, out, cap, n);
+    return nv_collect(ctx, out, cap, n);
 }
 
 extern "C" int nv_face_detect(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, int width, int height,
@@ -738,10 +747,11 @@ extern "C" int nv_resize_linear(nv_ctx *ctx, const uint8_t *src, int width, int 
     if (rc != NV_OK) return rc;
     if (!dst || dst_width <= 0 || dst_height <= 0 || dst_stride < dst_width * channels) { nv_set_error("bad destination"); return NV_ERR_ARG; }
     if ((rc = upload(ctx, src, (size_t)stride_bytes * height)) != NV_OK) return rc;
-    if ((rc = ensure_rtab(ctx, width, height, dst_width, dst_height)) != NV_OK) return rc;
+    const int *d_rtab;
+    if ((rc = nv_get_rtab(ctx, width, height, dst_width, dst_height, &d_rtab)) != NV_OK) return rc;
     if ((rc = ensure(&ctx->d_aux, &ctx->aux_cap, (size_t)dst_width * dst_height * channels)) != NV_OK) return rc;
     NV_CUDA(launch_resize_linear(ctx->d_frame, width, height, stride_bytes, channels, ctx->d_aux, dst_width, dst_height,
-                                 dst_width * channels, ctx->d_rtab, ctx->stream));
+                                 dst_width * channels, d_rtab, ctx->stream));
     ctx->launches++;
     return download(ctx, ctx->d_aux, dst_width * channels, dst_height, dst, dst_stride);
 }

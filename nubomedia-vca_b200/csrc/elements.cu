@@ -1,0 +1,802 @@
+// elements.cu — host-side mirrors of the six reference GStreamer elements (no GStreamer needed): per-frame
+// gating, ROI arithmetic, temporal smoothing and event payloads restated from the reference's
+// *_process_frame / *_send_event functions, with every OpenCV call replaced by the CUDA pipeline of this
+// library.  Citations: FACE = nubo_face/.../kmsfacedetect.cpp, FACES = Faces.cpp, EYE = kmseyedetect.cpp,
+// MOUTH = kmsmouthdetect.cpp, NOSE = kmsnosedetect.cpp, EAR = kmseardetect.cpp, TRK = gstnubotracker.cpp.
+//
+// Deliberate deviations: ROIs are clamped to the feature frame instead of letting
+// cv::Mat::operator() throw (EYE:988, MOUTH:867, NOSE:869); nose does not append to /tmp/nose.log; all
+// state is per element (NOSE:151-152 and TRK:108 are process-global in the reference); stdout chatter is
+// dropped (FACES:63).  view-* drawing (K13) is not implemented yet: the property is stored, nothing is drawn.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/time.h>
+
+#include <algorithm>
+#include <deque>
+#include <string>
+
+#include "internal.h"
+
+namespace {
+
+enum Kind { K_FACE, K_EYE, K_MOUTH, K_NOSE, K_EAR, K_TRACKER };
+
+struct Prop { const char *name; long lo, hi, def; long value; };
+
+struct DevImg {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    int w = 0, h = 0;
+};
+
+inline int cv_round(double v) { return (int)lrint(v); }
+inline int cv_roundf(float v) { return (int)lrintf(v); }
+inline double wall_ms()
+{
+    struct timeval t;
+    gettimeofday(&t, nullptr);
+    return t.tv_sec * 1000.0 + t.tv_usec / 1000.0;
+}
+
+struct TrackedFace { nv_rect r; int id; };        // BaseFace (BaseFace.cpp): rect + id, centre = x + w/2, y + h/2
+
+}  // namespace
+
+struct nv_element {
+    Kind kind;
+    std::string factory, dir;
+    nv_ctx *ctx = nullptr;  int gpu = 0;
+    std::vector<Prop> props;
+    nv_cascade *c_face = nullptr, *c_a = nullptr, *c_b = nullptr;     // face / (right eye, mouth, nose, "lear") / (left eye, "rear")
+    // shared detector state (FACE:87-126 and the analogous priv structs)
+    int num_frame = 0, num_frames_to_process = 0, num_iter = 0;
+    std::deque<std::vector<nv_rect>> events_queue;                     // queued upstream face messages
+    std::deque<int> motion_queue;
+    double time_events_ms = 0;
+    // face
+    std::vector<TrackedFace> faces_tracked;  int faces_id = 0;  int frames_with_no_detection = 0;
+    // eye / mouth / nose / ear
+    std::vector<nv_rect> faces, feat_a, feat_b;                        // faces; eyes_r | mouths | noses | lear ; eyes_l | rear
+    int no_det_a = 0, no_det_b = 0;
+    // device images
+    DevImg gray, face_img, feat_img, flip_img;
+    // outputs of the last frame
+    std::vector<nv_meta_rect> msg;  bool pushed = false;
+    std::string signal;  bool emitted = false;
+
+    long get(const char *n) const
+    {
+        for (auto &p : props) if (!strcmp(p.name, n)) return p.value;
+        return 0;
+    }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// device helpers (all stream-ordered on the element's context)
+// ------------------------------------------------------------------------------------------------
+int img_ensure(DevImg &im, int w, int h)
+{
+    size_t need = (size_t)w * h;
+    if (!im.p || im.cap < need) {
+        if (im.p) NV_CUDA(cudaFree(im.p));
+        im.p = nullptr;
+        NV_CUDA(cudaMalloc(&im.p, need + 256));
+        im.cap = need;
+    }
+    im.w = w; im.h = h;
+    return NV_OK;
+}
+
+int dev_equalize(nv_ctx *ctx, DevImg &im)
+{
+    NV_CUDA(launch_hist(im.p, im.w, im.h, im.w, ctx->d_hist, ctx->stream));
+    NV_CUDA(launch_lut(ctx->d_hist, im.w * im.h, ctx->d_lut, ctx->stream));
+    NV_CUDA(launch_apply_lut(im.p, im.w, im.h, im.w, ctx->d_lut, im.p, im.w, ctx->stream));   // element-wise: in place is safe
+    ctx->launches += 3;
+    return NV_OK;
+}
+
+int dev_resize(nv_ctx *ctx, const DevImg &src, DevImg &dst, int dw, int dh)
+{
+    int rc = img_ensure(dst, dw, dh);
+    if (rc != NV_OK) return rc;
+    const int *tab;
+    if ((rc = nv_get_rtab(ctx, src.w, src.h, dw, dh, &tab)) != NV_OK) return rc;
+    NV_CUDA(launch_resize_linear(src.p, src.w, src.h, src.w, 1, dst.p, dw, dh, dw, tab, ctx->stream));
+    ctx->launches++;
+    return NV_OK;
+}
+
+// CascadeClassifier::detectMultiScale on a (sub-)image resident on the device; blocks for the rectangles
+int dev_detect(nv_ctx *ctx, nv_cascade *c, const uint8_t *d_img, int w, int h, int stride, double sf, int mn, int minw,
+               int minh, std::vector<nv_rect> &out)
+{
+    out.clear();
+    if (!c || w <= 0 || h <= 0) return NV_OK;             // empty classifier / empty ROI: no detections
+    nv_detect_params p;
+    p.scale_factor = sf; p.min_neighbors = mn; p.flags = 0; p.min_w = minw; p.min_h = minh; p.max_w = p.max_h = 0;
+    int rc = nv_detect_device(ctx, c, d_img, w, h, stride, ctx->d_lut + 256, &p);
+    if (rc != NV_OK) return rc;
+    out.resize(4096);
+    int n = 0;
+    rc = nv_collect(ctx, out.data(), (int)out.size(), &n);
+    out.resize(rc == NV_OK ? n : 0);
+    return rc;
+}
+
+// cv::Mat::operator()(Rect) with the rectangle clamped to the image (the reference does not check)
+bool clamp_roi(nv_rect &r, int W, int H)
+{
+    int x0 = std::max(r.x, 0), y0 = std::max(r.y, 0), x1 = std::min(r.x + r.width, W), y1 = std::min(r.y + r.height, H);
+    if (x1 <= x0 || y1 <= y0) return false;
+    r.x = x0; r.y = y0; r.width = x1 - x0; r.height = y1 - y0;
+    return true;
+}
+
+int upload_frame(nv_ctx *ctx, const uint8_t *frame, int stride, int h)
+{
+    if ((size_t)stride * h > ctx->frame_cap) { nv_set_error("frame larger than the element's context"); return NV_ERR_CAPACITY; }
+    if (ctx->pending) NV_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->h_frame, frame, (size_t)stride * h);
+    NV_CUDA(cudaMemcpyAsync(ctx->d_frame, ctx->h_frame, (size_t)stride * h, cudaMemcpyHostToDevice, ctx->stream));
+    return NV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared logic
+// ------------------------------------------------------------------------------------------------
+// frame gate common to the five detectors (FACE:797-802, EYE:939-945, MOUTH:827-832, NOSE:825-830, EAR:777-782)
+bool gate_runs(nv_element *e)
+{
+    long p = e->get("process-x-every-4-frames");
+    e->num_frame++;
+    return (p == 2 && e->num_frame % 2 == 1) || (p != 2 && e->num_frame <= p);
+}
+void gate_end(nv_element *e) { if (e->num_frame == 4) e->num_frame = 0; }       // GOP
+
+void add_meta(nv_element *e, const char *name, const char *type, unsigned x, unsigned y, unsigned w, unsigned h)
+{
+    nv_meta_rect m;
+    memset(&m, 0, sizeof m);
+    snprintf(m.name, sizeof m.name, "%s", name);
+    snprintf(m.type, sizeof m.type, "%s", type);
+    m.x = x; m.y = y; m.width = w; m.height = h;
+    e->msg.push_back(m);
+}
+void add_signal(std::string &s, unsigned x, unsigned y, unsigned w, unsigned h)
+{
+    char b[96];
+    snprintf(b, sizeof b, "x:%u,y:%u,width:%u,height:%u;", x, y, w, h);
+    s += b;
+}
+// g_signal_emit rate limit (FACE:228-241 and the analogous blocks)
+void maybe_emit(nv_element *e, const std::string &payload, bool any, double now_ms)
+{
+    if (!any) return;
+    double now = now_ms >= 0 ? now_ms : wall_ms();
+    if (e->get("activate-events") == 1 && now - e->time_events_ms > (double)e->get("events-ms")) {
+        e->time_events_ms = now;
+        e->signal = payload;
+        e->emitted = true;
+    }
+}
+
+// __receive_event for eye/mouth/nose (EYE:726-764): pops one queued upstream message, keeps its faces
+bool receive_faces_event(nv_element *e)
+{
+    if (e->get("detect-event") == 0) return true;
+    if (e->events_queue.empty()) return false;
+    e->faces = e->events_queue.front();          // __get_event_message clears faces, then fills (EYE:691,706-718)
+    e->events_queue.pop_front();
+    e->num_frames_to_process = 10 / (5 - (int)e->get("process-x-every-4-frames"));   // NUM_FRAMES_TO_PROCESS / (5 - p)
+    return true;
+}
+
+// ---- Faces::track_faces (FACES:78-153) ---------------------------------------------------------
+int calc_distance(int x1, int y1, int x2, int y2) { return (int)sqrt(pow((double)(x2 - x1), 2) + pow((double)(y2 - y1), 2)); }
+int distance_limit(int a1, int a2) { int b = std::max(a1, a2); return b > 5000 ? 8 : (b > 2500 ? 5 : 3); }     // FACES:166-181
+inline int cx(const nv_rect &r) { return r.x + r.width / 2; }
+inline int cy(const nv_rect &r) { return r.y + r.height / 2; }
+
+void track_faces(std::vector<TrackedFace> &faces, int &faces_id, std::vector<TrackedFace> cf, int track_threshold,
+                 int /*pos_threshold*/, int /*area_threshold*/)
+{
+    std::vector<TrackedFace> nv;
+    for (auto &f : faces) {
+        int t_distance = track_threshold, pos = -1;
+        for (size_t k = 0; k < cf.size(); k++) {
+            int d = calc_distance(cx(cf[k].r), cy(cf[k].r), cx(f.r), cy(f.r));
+            if (t_distance > d) { pos = (int)k; t_distance = d; }
+        }
+        if (pos >= 0) {
+            TrackedFace &c = cf[pos];
+            int d = calc_distance(cx(f.r), cy(f.r), cx(c.r), cy(c.r));
+            int a_old = f.r.width * f.r.height, a_new = c.r.width * c.r.height;
+            if (distance_limit(a_old, a_new) < d) { c.id = f.id; nv.push_back(c); }              // moved: take the new face
+            else if (15 < (abs(a_old - a_new) * 100) / a_new) {                                   // AREA_PERCENTAGE: resized
+                TrackedFace t;
+                t.r.x = f.r.x; t.r.y = f.r.y; t.r.width = c.r.width; t.r.height = c.r.height; t.id = f.id;
+                nv.push_back(t);
+            } else nv.push_back(f);                                                               // keep the old face
+            cf.erase(cf.begin() + pos);
+        }
+    }
+    for (auto &c : cf) { c.id = faces_id++; nv.push_back(c); }
+    faces.swap(nv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// nubofacedetector (FACE:757-853 + 179-249)
+// ------------------------------------------------------------------------------------------------
+int face_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, double now_ms)
+{
+    long w2p = e->get("width-to-process");
+    if (w2p <= 0) { nv_set_error("width-to-process=0 divides by zero in the reference (FACE:304)"); return NV_ERR_ARG; }
+    // __receive_event (FACE:722-755): detect-event waits for an upstream "motion" event
+    bool got = true;
+    if (e->get("detect-event") != 0) {
+        got = !e->motion_queue.empty();
+        if (got) { e->motion_queue.pop_front(); e->num_frames_to_process = 10; }
+    }
+    int rc = NV_OK;
+    if (got || e->num_frames_to_process > 0) {
+        e->num_iter++;
+        if (gate_runs(e)) {
+            e->num_frames_to_process--;
+            nv_face_params p;
+            p.width_to_process = (int)w2p;
+            p.scale_factor = 1.0 + (double)e->get("multi-scale-factor") / 100.0;     // MULTI_SCALE_FACTOR, FACE:142
+            p.min_neighbors = 3; p.min_w = -1; p.min_h = -1;                          // FACE:809-811
+            std::vector<nv_rect> cur(4096);
+            int n = 0;
+            rc = e->c_face ? nv_face_detect(e->ctx, e->c_face, frame, W, H, stride, &p, cur.data(), (int)cur.size(), &n) : NV_OK;
+            cur.resize(rc == NV_OK ? n : 0);
+            if (!cur.empty()) {
+                std::vector<TrackedFace> cf;
+                int id = 0;
+                for (auto &r : cur) cf.push_back({r, id++});                          // Faces(vector<Rect>&), FACES:27-39
+                track_faces(e->faces_tracked, e->faces_id, cf, (int)e->get("track-threshold"),
+                            (int)e->get("euclidean-distance"), (int)e->get("area-threshold"));
+            } else if (e->frames_with_no_detection < 1) e->frames_with_no_detection += 1;   // MAX_NUM_FPS_WITH_NO_DETECTION
+            else { e->frames_with_no_detection = 0; e->faces_tracked.clear(); }
+        }
+        gate_end(e);
+    }
+    // kms_face_send_event (FACE:179-249): runs every frame, also on skipped ones
+    unsigned norm = (unsigned)(W / w2p);
+    std::string s;
+    for (auto &f : e->faces_tracked) {
+        unsigned x = (unsigned)f.r.x * norm, y = (unsigned)f.r.y * norm, w = (unsigned)f.r.width * norm, h = (unsigned)f.r.height * norm;
+        add_meta(e, "face", "face", x, y, w, h);
+        add_signal(s, x, y, w, h);
+    }
+    e->pushed = true;
+    maybe_emit(e, s, !e->faces_tracked.empty(), now_ms);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nuboeyedetector (EYE:916-1102 + 220-308)
+// ------------------------------------------------------------------------------------------------
+bool contain_bb(int px, int py, const nv_rect &r)       // EYE:766-776 (inclusive on both sides)
+{
+    return py >= r.y && py <= r.y + r.height && px >= r.x && px <= r.x + r.width;
+}
+
+// EYE:778-862, restated literally (including its index arithmetic)
+void merge_eyes_current_frame(const nv_rect &face_bb, const std::vector<nv_rect> *eye_r, std::vector<nv_rect> &eyes, int scale,
+                              bool eye_left)
+{
+    for (int i = (int)eyes.size() - 1; i > 0; i--) {
+        int ecx = eyes[i].x + eyes[i].width / 2, ecy = eyes[i].y + eyes[i].height / 2;
+        if (contain_bb(ecx, ecy, eyes[i - 1]) && eyes[i].width * eyes[i].height < eyes[i - 1].width * eyes[i - 1].height)
+            eyes.erase(eyes.end() - i - 1);
+        else {
+            ecx = eyes[i - 1].x + eyes[i - 1].width / 2; ecy = eyes[i - 1].y + eyes[i - 1].height / 2;
+            if (contain_bb(ecx, ecy, eyes[i]) && eyes[i - 1].width * eyes[i - 1].height < eyes[i].width * eyes[i].height)
+                eyes.erase(eyes.end() - i);
+        }
+    }
+    // eyes found at the top of the ROI are eyebrows
+    for (int i = (int)eyes.size() - 1; i >= 0; i--) {
+        if (i >= (int)eyes.size()) continue;
+        int y_aux = face_bb.y * scale + face_bb.height * scale * 60 / 100;
+        if (face_bb.y * scale + eyes[i].y < y_aux) {
+            if (i == 0 && eyes.size() == 1) { if (eye_r->size() > 0 && eye_left) eyes[i].y = eye_r->at(0).y; }
+            else eyes.erase(eyes.begin() + i);
+        }
+    }
+    if (eyes.size() > 1) {
+        int middle_y = face_bb.x * scale + face_bb.height * scale / 2;      // x/y swapped in the reference, kept
+        int middle_x = face_bb.y * scale + face_bb.width * scale / 2;
+        for (int i = (int)eyes.size() - 1; i > 0; i--) {
+            int c1y = eyes[i].y + eyes[i].height / 2, c1x = eyes[i].x + eyes[i].width / 2;
+            int c2y = eyes[i - 1].y + eyes[i - 1].height / 2, c2x = eyes[i - 1].x + eyes[i - 1].width / 2;
+            float s1 = (float)sqrt(pow((double)(middle_x - c1x), 2) + pow((double)(middle_y - c1y), 2));
+            float s2 = (float)sqrt(pow((double)(middle_x - c2x), 2) + pow((double)(middle_y - c2y), 2));
+            if (s1 < s2) eyes.erase(eyes.end() - i - 1);
+            else eyes.erase(eyes.end() - i);
+        }
+    }
+    if (eye_left && eye_r->size() > 0 && eyes.size() > 0) eyes[0].y = eye_r->at(0).y;
+}
+
+// EYE:864-900 / the common shape of MOUTH:750-796 and NOSE:745-790 (those transform while merging)
+std::vector<nv_rect> merge_consecutive(std::vector<nv_rect> &cur, const std::vector<nv_rect> &prev, double limit,
+                                       bool local, const nv_rect &face, int scale)
+{
+    std::vector<nv_rect> res;
+    for (auto &o : prev) {
+        int ox = o.x + o.width / 2, oy = o.y + o.height / 2;
+        for (size_t j = 0; j < cur.size(); j++) {
+            int nx, ny;
+            if (local) {
+                nx = (cur[j].x + face.x) * scale + (cur[j].width * scale) / 2;
+                ny = (cur[j].y + face.y) * scale + (cur[j].height * scale) / 2;
+            } else { nx = cur[j].x + cur[j].width / 2; ny = cur[j].y + cur[j].height / 2; }
+            double h2 = sqrt(pow((double)(nx - ox), 2) + pow((double)(ny - oy), 2));
+            if (h2 < limit) { res.push_back(o); cur.erase(cur.begin() + j); break; }       // keep the previous rect: no jitter
+        }
+    }
+    for (auto c : cur) {
+        if (local) {       // new value: move to original-image coordinates (MOUTH:782-791, NOSE:776-785)
+            c.x = cv_round((double)((face.x + c.x) * scale)); c.y = cv_round((double)((face.y + c.y) * scale));
+            c.width = (c.width - 1) * scale; c.height = (c.height - 1) * scale;
+        }
+        res.push_back(c);
+    }
+    return res;
+}
+
+void hold(std::vector<nv_rect> &state, int &counter, const std::vector<nv_rect> &res, int max_empty)
+{
+    if (res.empty()) {
+        if (counter < max_empty) counter += 1;
+        else { counter = 0; state.clear(); }
+    } else { counter = 0; state = res; }
+}
+
+struct Scales { double o2f, o2x, f2x; };
+// conf_images of eye/mouth/nose (EYE:311-341, MOUTH:285-315, NOSE:275-308): float fields read back as double
+Scales detector_scales(nv_element *e, int W)
+{
+    float o2f = e->get("detect-event") ? (float)W / (float)W : (float)W / 160.f;       // FACE_WIDTH
+    float o2x = (float)W / (float)e->get("width-to-process");
+    float f2x = o2f / o2x;
+    return {(double)o2f, (double)o2x, (double)f2x};
+}
+
+int eye_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, double now_ms)
+{
+    if (e->get("width-to-process") <= 0) { nv_set_error("width-to-process must be > 0"); return NV_ERR_ARG; }
+    Scales sc = detector_scales(e, W);
+    nv_ctx *ctx = e->ctx;
+    int rc = NV_OK;
+    if (receive_faces_event(e) || e->num_frames_to_process > 0) {
+        if (gate_runs(e)) {
+            e->num_frames_to_process--;
+            std::vector<nv_rect> res_r, res_l;
+            rc = [&]() -> int {
+                int r;
+                if ((r = upload_frame(ctx, frame, stride, H)) != NV_OK) return r;
+                if ((r = img_ensure(e->gray, W, H)) != NV_OK) return r;
+                NV_CUDA(launch_bgr2gray(ctx->d_frame, W, H, stride, 3, e->gray.p, W, ctx->stream));     // EYE:949
+                ctx->launches++;
+                if ((r = dev_equalize(ctx, e->gray)) != NV_OK) return r;                                 // EYE:950 (full resolution)
+                if (e->get("detect-event") == 0) {
+                    if ((r = dev_resize(ctx, e->gray, e->face_img, cv_round(W / sc.o2f), cv_round(H / sc.o2f))) != NV_OK) return r;
+                    e->faces.clear();
+                    if ((r = dev_detect(ctx, e->c_face, e->face_img.p, e->face_img.w, e->face_img.h, e->face_img.w,
+                                        1.0 + e->get("multi-scale-factor") / 100.0, 3, 30, 30, e->faces)) != NV_OK) return r;   // EYE:958-960
+                }
+                if ((r = dev_resize(ctx, e->gray, e->feat_img, cv_round(W / sc.o2x), cv_round(H / sc.o2x))) != NV_OK) return r;  // EYE:963
+                if ((r = dev_equalize(ctx, e->feat_img)) != NV_OK) return r;                                                     // EYE:964
+                int iscale = (int)sc.o2x;                                  // `int scale` parameters of the helpers
+                for (auto &f : e->faces) {
+                    nv_rect ra;
+                    ra.x = (int)(f.x * sc.f2x); ra.y = (int)(f.y * sc.f2x); ra.width = (int)(f.width * sc.f2x); ra.height = (int)(f.height * sc.f2x);
+                    int down = cv_roundf((float)ra.height * 40 / 100), top = cv_roundf((float)ra.height * 25 / 100);   // EYE:979-980
+                    nv_rect fr = {ra.x, ra.y + top, ra.width / 2, ra.height - top - down};
+                    nv_rect fl = {ra.x + ra.width / 2, ra.y + top, ra.width / 2, ra.height - top - down};
+                    std::vector<nv_rect> eye_r, eye_l;
+                    nv_rect roi = fr;
+                    if (clamp_roi(roi, e->feat_img.w, e->feat_img.h) &&
+                        (r = dev_detect(ctx, e->c_a, e->feat_img.p + (size_t)roi.y * e->feat_img.w + roi.x, roi.width, roi.height,
+                                        e->feat_img.w, 1.1, 2, 20, 20, eye_r)) != NV_OK) return r;                      // EYE:991-993
+                    fr = roi;
+                    roi = fl;
+                    if (clamp_roi(roi, e->feat_img.w, e->feat_img.h) &&
+                        (r = dev_detect(ctx, e->c_b, e->feat_img.p + (size_t)roi.y * e->feat_img.w + roi.x, roi.width, roi.height,
+                                        e->feat_img.w, 1.1, 2, 20, 20, eye_l)) != NV_OK) return r;                      // EYE:1003-1005
+                    fl = roi;
+                    for (auto *v : {&eye_r, &eye_l}) {                      // transform_2_global_coordinates, EYE:902-913
+                        const nv_rect &fc = v == &eye_r ? fr : fl;
+                        for (auto &q : *v) { q.x = (fc.x + q.x) * iscale; q.y = (fc.y + q.y) * iscale; q.width = (q.width - 1) * iscale; q.height = (q.height - 1) * iscale; }
+                    }
+                    if (!eye_r.empty()) {
+                        merge_eyes_current_frame(fr, &eye_r, eye_r, iscale, false);
+                        auto m = merge_consecutive(eye_r, e->feat_a, 7, false, fr, iscale);
+                        res_r.insert(res_r.end(), m.begin(), m.end());
+                    }
+                    if (!eye_l.empty()) {
+                        merge_eyes_current_frame(fl, &res_r, eye_l, iscale, true);
+                        auto m = merge_consecutive(eye_l, e->feat_b, 7, false, fl, iscale);
+                        res_l.insert(res_l.end(), m.begin(), m.end());
+                    }
+                }
+                return NV_OK;
+            }();
+            hold(e->feat_a, e->no_det_a, res_r, 1);                        // EYE:1034-1064
+            hold(e->feat_b, e->no_det_b, res_l, 1);
+        }
+        gate_end(e);
+    }
+    // kms_eye_send_event (EYE:220-308): left eyes first, then right eyes
+    std::string s;
+    for (auto &m : e->feat_b) { add_meta(e, "eye_left", "eye", m.x, m.y, m.width, m.height); add_signal(s, m.x, m.y, m.width, m.height); }
+    for (auto &m : e->feat_a) { add_meta(e, "eye_right", "eye", m.x, m.y, m.width, m.height); add_signal(s, m.x, m.y, m.width, m.height); }
+    e->pushed = true;
+    maybe_emit(e, s, !e->feat_a.empty() || !e->feat_b.empty(), now_ms);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nubomouthdetector (MOUTH:798-908 + 198-275) and nubonosedetector (NOSE:792-911 + 208-268)
+// ------------------------------------------------------------------------------------------------
+int mouth_nose_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, double now_ms)
+{
+    if (e->get("width-to-process") <= 0) { nv_set_error("width-to-process must be > 0"); return NV_ERR_ARG; }
+    const bool mouth = e->kind == K_MOUTH;
+    Scales sc = detector_scales(e, W);
+    nv_ctx *ctx = e->ctx;
+    int rc = NV_OK;
+    std::vector<nv_rect> res;
+    bool processed = false;
+    if (receive_faces_event(e) || e->num_frames_to_process > 0) {
+        processed = true;
+        if (gate_runs(e)) {
+            e->num_frames_to_process--;
+            rc = [&]() -> int {
+                int r;
+                if ((r = upload_frame(ctx, frame, stride, H)) != NV_OK) return r;
+                if ((r = img_ensure(e->gray, W, H)) != NV_OK) return r;
+                NV_CUDA(launch_bgr2gray(ctx->d_frame, W, H, stride, 3, e->gray.p, W, ctx->stream));     // MOUTH:836, NOSE:834
+                ctx->launches++;
+                if (e->get("detect-event") == 0) {
+                    if ((r = dev_resize(ctx, e->gray, e->face_img, cv_round(W / sc.o2f), cv_round(H / sc.o2f))) != NV_OK) return r;
+                    if ((r = dev_equalize(ctx, e->face_img)) != NV_OK) return r;
+                    e->faces.clear();
+                    if ((r = dev_detect(ctx, e->c_face, e->face_img.p, e->face_img.w, e->face_img.h, e->face_img.w,
+                                        1.0 + e->get("multi-scale-factor") / 100.0, 2, 3, 3, e->faces)) != NV_OK) return r;   // MOUTH:845-848
+                }
+                if ((r = dev_resize(ctx, e->gray, e->feat_img, cv_round(W / sc.o2x), cv_round(H / sc.o2x))) != NV_OK) return r;
+                if ((r = dev_equalize(ctx, e->feat_img)) != NV_OK) return r;
+                int iscale = (int)sc.o2x;
+                for (auto &f : e->faces) {
+                    nv_rect ra;
+                    if (mouth) {                                            // MOUTH:859-867: lower part of the face
+                        const int half = cv_round((double)(float)f.height / 1.8);     // (float)h / 1.8: double division
+                        ra.y = (int)((f.y + half) * sc.f2x); ra.x = (int)(f.x * sc.f2x);
+                        ra.height = (int)(half * sc.f2x); ra.width = (int)(f.width * sc.f2x);
+                    } else {                                                // NOSE:858-869
+                        const int top = cv_roundf((float)f.height * 25 / 100), down = cv_roundf((float)f.height * 10 / 100);
+                        const int side = cv_roundf((float)f.width * 25 / 100);
+                        ra.y = (int)((f.y + top) * sc.f2x); ra.x = (int)((f.x + side) * sc.f2x);
+                        ra.height = (int)((f.height - down - top) * sc.f2x); ra.width = (int)((f.width - side) * sc.f2x);
+                    }
+                    std::vector<nv_rect> found;
+                    if (!clamp_roi(ra, e->feat_img.w, e->feat_img.h)) continue;
+                    if ((r = dev_detect(ctx, e->c_a, e->feat_img.p + (size_t)ra.y * e->feat_img.w + ra.x, ra.width, ra.height,
+                                        e->feat_img.w, 1.1, 3, 1, 1, found)) != NV_OK) return r;          // MOUTH:870-873, NOSE:870-873
+                    if (!found.empty()) {
+                        auto m = merge_consecutive(found, e->feat_a, mouth ? 4 : 6, true, ra, iscale);
+                        res.insert(res.end(), m.begin(), m.end());
+                    }
+                }
+                return NV_OK;
+            }();
+        }
+    }
+    if (processed) {                     // MOUTH:883-890 / NOSE:886-893: the list is rebuilt on every non-gated-out frame
+        e->feat_a = res;
+        gate_end(e);
+    }
+    std::string s;
+    if (mouth) {                          // kms_mouth_send_event: faces (x int(scale_o2f)) then mouths
+        unsigned norm = (unsigned)(int)sc.o2f;
+        for (auto &f : e->faces) add_meta(e, "face", "face", (unsigned)f.x * norm, (unsigned)f.y * norm, (unsigned)f.width * norm, (unsigned)f.height * norm);
+        for (auto &m : e->feat_a) { add_meta(e, "mouth", "mouth", m.x, m.y, m.width, m.height); add_signal(s, m.x, m.y, m.width, m.height); }
+    } else
+        for (auto &m : e->feat_a) { add_meta(e, "noses", "nose", m.x, m.y, m.width, m.height); add_signal(s, m.x, m.y, m.width, m.height); }
+    e->pushed = true;
+    maybe_emit(e, s, !e->feat_a.empty(), now_ms);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nuboeardetector (EAR:644-729, 767-822, 192-290)
+// ------------------------------------------------------------------------------------------------
+int ear_find(nv_element *e, const DevImg &face_img, nv_cascade *ear_cascade, double f2e, double e2o, int face_cols, int side)
+{
+    nv_ctx *ctx = e->ctx;
+    int r;
+    if ((r = dev_detect(ctx, e->c_face, face_img.p, face_img.w, face_img.h, face_img.w, 1.0 + e->get("multi-scale-factor") / 100.0,
+                        2, 3, 3, e->faces)) != NV_OK) return r;                                           // EAR:656-659
+    if (e->faces.empty()) return NV_OK;
+    std::vector<nv_rect> &ears = side == 0 ? e->feat_a : e->feat_b;                                         // lear : rear
+    if (!ears.empty()) ears.clear();
+    else if (e->no_det_a < 4) e->no_det_a += 1;                                                             // MAX_NUM_FPS_WITH_NO_DETECTION
+    else { e->no_det_a = 0; ears.clear(); }
+    for (auto &f : e->faces) {
+        const int top = cv_roundf((float)f.height * 20 / 100), down = cv_roundf((float)f.height * 20 / 100);
+        if (side == 0) {                                                                                    // LEFT_SIDE, EAR:688-697
+            f.y = (int)((f.y + top) * f2e); f.x = (int)((f.x + f.width / 2) * f2e);
+            f.height = (int)((f.height - down) * f2e); f.width = (int)((f.width / 2) * f2e + 50);           // EXTRA_ROI
+            if (f.x + f.width > e->feat_img.w) f.width = e->feat_img.w - f.x - 1;
+        } else {                                                                                            // EAR:699-707
+            f.y = (int)((f.y + top) * f2e); f.x = (int)((face_cols - f.x - f.width) * f2e - 50);
+            f.height = (int)((f.height - down) * f2e); f.width = (int)((f.width / 2) * f2e);
+            if (f.x < 0) f.x = 0;
+        }
+        nv_rect roi = f;
+        std::vector<nv_rect> found;
+        if (!clamp_roi(roi, e->feat_img.w, e->feat_img.h)) continue;
+        if ((r = dev_detect(ctx, ear_cascade, e->feat_img.p + (size_t)roi.y * e->feat_img.w + roi.x, roi.width, roi.height,
+                            e->feat_img.w, 1.1, 3, 1, 1, found)) != NV_OK) return r;                       // EAR:712-715
+        for (auto &q : found) {
+            nv_rect a;
+            a.x = cv_round((roi.x + q.x) * e2o); a.y = cv_round((roi.y + q.y) * e2o);
+            a.width = (int)((q.width - 1) * e2o); a.height = (int)((q.height - 1) * e2o);
+            ears.push_back(a);
+        }
+    }
+    return NV_OK;
+}
+
+int ear_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, double now_ms)
+{
+    if (e->get("width-to-process") <= 0) { nv_set_error("width-to-process must be > 0"); return NV_ERR_ARG; }
+    float f2o_f = (float)W / 160.f, e2o_f = (float)W / (float)e->get("width-to-process"), f2e_f = f2o_f / e2o_f;   // EAR:314-316
+    double f2o = f2o_f, e2o = e2o_f, f2e = f2e_f;
+    nv_ctx *ctx = e->ctx;
+    int rc = NV_OK;
+    if (gate_runs(e)) {
+        e->num_frames_to_process--;
+        rc = [&]() -> int {
+            int r;
+            if ((r = upload_frame(ctx, frame, stride, H)) != NV_OK) return r;
+            if ((r = img_ensure(e->gray, W, H)) != NV_OK) return r;
+            NV_CUDA(launch_bgr2gray(ctx->d_frame, W, H, stride, 3, e->gray.p, W, ctx->stream));             // EAR:786
+            ctx->launches++;
+            if ((r = dev_resize(ctx, e->gray, e->face_img, cv_round(W / f2o), cv_round(H / f2o))) != NV_OK) return r;
+            if ((r = dev_equalize(ctx, e->face_img)) != NV_OK) return r;
+            if ((r = dev_resize(ctx, e->gray, e->feat_img, cv_round(W / e2o), cv_round(H / e2o))) != NV_OK) return r;
+            if ((r = dev_equalize(ctx, e->feat_img)) != NV_OK) return r;
+            if ((r = ear_find(e, e->face_img, e->c_a, f2e, e2o, e->face_img.w, 0)) != NV_OK) return r;       // lecascade, LEFT_SIDE
+            if ((r = img_ensure(e->flip_img, e->face_img.w, e->face_img.h)) != NV_OK) return r;
+            NV_CUDA(launch_flip(e->face_img.p, e->face_img.w, e->face_img.h, e->face_img.w, e->flip_img.p, e->face_img.w, ctx->stream));   // EAR:800
+            ctx->launches++;
+            return ear_find(e, e->flip_img, e->c_b, f2e, e2o, e->face_img.w, 1);                             // recascade, RIGHT_SIDE
+        }();
+    }
+    gate_end(e);
+    // kms_ear_send_event (EAR:192-290): builds the message (profile faces, right ears, left ears) but never pushes it
+    std::string s;
+    for (auto &f : e->faces) add_meta(e, "face_profile", "face_profile", f.x, f.y, f.width, f.height);
+    for (auto &m : e->feat_b) { add_meta(e, "ear", "ear", m.x, m.y, m.width, m.height); add_signal(s, m.x, m.y, m.width, m.height); }
+    for (auto &m : e->feat_a) { add_meta(e, "ear", "ear", m.x, m.y, m.width, m.height); add_signal(s, m.x, m.y, m.width, m.height); }
+    e->pushed = false;
+    maybe_emit(e, s, !e->feat_a.empty() || !e->feat_b.empty(), now_ms);
+    e->faces.clear();                                                                                        // EAR:858
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nubotracker (TRK:339-421)
+// ------------------------------------------------------------------------------------------------
+int tracker_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, uint64_t pts_ns, double now_ms)
+{
+    nv_tracker_params p;
+    p.threshold = (int)e->get("set_threshold"); p.min_area = (int)e->get("set_min_area");
+    p.max_area = e->get("set_max_area"); p.distance = (int)e->get("set_distance");
+    std::vector<nv_rect> out(16384);
+    int n = 0;
+    double ts = now_ms >= 0 ? now_ms : (double)pts_ns / 1e6;        // the reference uses clock() in ms (TRK:349)
+    int rc = nv_tracker_process(e->ctx, frame, W, H, stride, ts, &p, out.data(), (int)out.size(), &n);
+    if (rc != NV_OK) n = 0;
+    std::string s;
+    bool build = e->get("set_visual_mode") > 0 || e->get("activate-events") == 1;      // TRK:383
+    for (int i = 0; i < n; i++) {
+        add_meta(e, "object", "object", out[i].x, out[i].y, out[i].width, out[i].height);
+        if (build && e->get("activate-events") == 1) add_signal(s, out[i].x, out[i].y, out[i].width, out[i].height);
+    }
+    e->pushed = false;                                                 // the tracker pushes no downstream event
+    maybe_emit(e, s, n > 0, now_ms);
+    return rc;
+}
+
+void add_props(nv_element *e, std::initializer_list<Prop> l) { for (auto &p : l) { e->props.push_back(p); e->props.back().value = p.def; } }
+
+nv_cascade *try_load(const std::string &dir, const char *file)
+{
+    nv_cascade *c = nullptr;
+    std::string path = dir + "/" + file;
+    if (nv_cascade_load(path.c_str(), &c) != NV_OK) return nullptr;      // the reference logs and carries on (FACE:167-171)
+    return c;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int nv_element_create(const char *factory_name, int gpu, const char *cascade_dir, nv_element **out)
+{
+    if (!factory_name || !out) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    *out = nullptr;
+    static const char *names[] = {"nubofacedetector", "nuboeyedetector", "nubomouthdetector", "nubonosedetector", "nuboeardetector", "nubotracker"};
+    int kind = -1;
+    for (int i = 0; i < 6; i++) if (!strcmp(factory_name, names[i])) kind = i;
+    if (kind < 0) { nv_set_error("unknown element factory '%s'", factory_name); return NV_ERR_ARG; }
+    nv_element *e = new nv_element();
+    e->kind = (Kind)kind; e->factory = factory_name;
+    const char *env = getenv("NUBOVCA_CASCADE_DIR");
+    e->dir = cascade_dir ? cascade_dir : (env ? env : "/usr/share/opencv/haarcascades");        // FACE:40
+    e->gpu = gpu;                            // the CUDA context is created with the first buffer (caps are known then)
+    const Prop common[] = {{"detect-event", 0, 1, 0, 0}, {"send-meta-data", 0, 1, 0, 0}, {"width-to-process", 0, 640, 320, 0},
+                           {"process-x-every-4-frames", 0, 4, 4, 0}, {"multi-scale-factor", 0, 51, 25, 0},
+                           {"activate-events", 0, 1, 0, 0}, {"events-ms", 0, 30000, 30001, 0}};
+    auto add_common = [&](const char *view, const char *meta_name) {
+        add_props(e, {{view, 0, 1, 0, 0}});
+        for (auto p : common) { if (!strcmp(p.name, "send-meta-data")) p.name = meta_name; add_props(e, {p}); }
+    };
+    switch (e->kind) {
+    case K_FACE:
+        add_common("view-faces", "send-meta-data");
+        for (auto &p : e->props) if (!strcmp(p.name, "width-to-process")) p.value = p.def = 160;            // FACE:26,991
+        add_props(e, {{"euclidean-distance", 0, 20, 8, 0}, {"track-threshold", 0, 100, 40, 0}, {"area-threshold", 0, 1000, 500, 0}});
+        e->c_face = try_load(e->dir, "haarcascade_frontalface_alt.xml");
+        break;
+    case K_EYE:
+        add_common("view-eyes", "send-meta-data");
+        e->c_face = try_load(e->dir, "haarcascade_frontalface_alt.xml");
+        e->c_a = try_load(e->dir, "haarcascade_mcs_righteye.xml");                                            // eyes_rcascade, EYE:29
+        e->c_b = try_load(e->dir, "haarcascade_mcs_lefteye.xml");                                             // eyes_lcascade, EYE:28
+        break;
+    case K_MOUTH:
+        add_common("view-mouths", "send-meta-data");
+        e->c_face = try_load(e->dir, "haarcascade_frontalface_alt.xml");
+        e->c_a = try_load(e->dir, "haarcascade_mcs_mouth.xml");
+        break;
+    case K_NOSE:
+        add_common("view-noses", "send-meta-data");
+        e->c_face = try_load(e->dir, "haarcascade_frontalface_alt.xml");
+        e->c_a = try_load(e->dir, "haarcascade_mcs_nose.xml");
+        break;
+    case K_EAR:
+        add_common("view-ears", "meta-data");                                                                 // EAR:1006 (not send-meta-data)
+        e->c_face = try_load(e->dir, "haarcascade_profileface.xml");
+        e->c_a = try_load(e->dir, "haarcascade_mcs_rightear.xml");      // lecascade <- LEAR_CONF_FILE = mcs_rightear (EAR:30-31,179,186)
+        e->c_b = try_load(e->dir, "haarcascade_mcs_leftear.xml");       // recascade <- REAR_CONF_FILE = mcs_leftear
+        break;
+    case K_TRACKER:
+        add_props(e, {{"set_threshold", 0, 255, 20, 0}, {"set_min_area", 0, 10000, 50, 0}, {"set_max_area", 0, 300000, 30000, 0},
+                      {"set_distance", 0, 2000, 35, 0}, {"set_visual_mode", 0, 4, 0, 0}, {"activate-events", 0, 1, 0, 0},
+                      {"events-ms", 0, 30000, 30001, 0}});
+        break;
+    }
+    *out = e;
+    return NV_OK;
+}
+
+extern "C" void nv_element_destroy(nv_element *e)
+{
+    if (!e) return;
+    if (e->ctx) { cudaSetDevice(e->ctx->gpu); cudaStreamSynchronize(e->ctx->stream); }
+    for (DevImg *im : {&e->gray, &e->face_img, &e->feat_img, &e->flip_img}) cudaFree(im->p);
+    nv_ctx_destroy(e->ctx);
+    nv_cascade_free(e->c_face); nv_cascade_free(e->c_a); nv_cascade_free(e->c_b);
+    delete e;
+}
+
+extern "C" int nv_element_set_property(nv_element *e, const char *name, long value)
+{
+    if (!e || !name) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    for (auto &p : e->props)
+        if (!strcmp(p.name, name)) {
+            if (value < p.lo || value > p.hi) { nv_set_error("%s: %ld outside [%ld, %ld]", name, value, p.lo, p.hi); return NV_ERR_ARG; }
+            if (e->kind == K_FACE && !strcmp(name, "track-threshold")) {       // reference bug kept: the setter writes
+                for (auto &q : e->props) if (!strcmp(q.name, "euclidean-distance")) q.value = value;   // euclidean_threshold (FACE:548-550)
+                return NV_OK;
+            }
+            p.value = value;
+            if (!strcmp(name, "activate-events")) e->time_events_ms = wall_ms();                      // FACE:556-560
+            return NV_OK;
+        }
+    nv_set_error("%s has no property '%s'", e->factory.c_str(), name);
+    return NV_ERR_ARG;
+}
+
+extern "C" int nv_element_get_property(nv_element *e, const char *name, long *value)
+{
+    if (!e || !name || !value) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    for (auto &p : e->props) if (!strcmp(p.name, name)) { *value = p.value; return NV_OK; }
+    nv_set_error("%s has no property '%s'", e->factory.c_str(), name);
+    return NV_ERR_ARG;
+}
+
+extern "C" int nv_element_push_faces_event(nv_element *e, const nv_rect *faces, int n)
+{
+    if (!e || (n > 0 && !faces) || n < 0) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    e->events_queue.emplace_back(faces, faces + n);
+    return NV_OK;
+}
+
+extern "C" int nv_element_push_motion_event(nv_element *e)
+{
+    if (!e) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    e->motion_queue.push_back(1);
+    return NV_OK;
+}
+
+extern "C" int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int width, int height, int stride_bytes,
+                                             uint64_t pts_ns, double now_ms)
+{
+    if (!e || !frame || width <= 0 || height <= 0) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    int cn = e->kind == K_TRACKER ? 4 : 3;
+    if (stride_bytes < width * cn) { nv_set_error("stride smaller than a row"); return NV_ERR_ARG; }
+    if (!e->ctx || width > e->ctx->max_w || height > e->ctx->max_h) {       // first buffer / caps renegotiation
+        nv_ctx_destroy(e->ctx); e->ctx = nullptr;
+        int rc = nv_ctx_create(e->gpu, std::max(width, 1920), std::max(height, 1080), &e->ctx);
+        if (rc != NV_OK) return rc;
+    }
+    NV_CUDA(cudaSetDevice(e->ctx->gpu));
+    e->msg.clear(); e->signal.clear(); e->emitted = false; e->pushed = false;
+    switch (e->kind) {
+    case K_FACE: return face_frame(e, frame, width, height, stride_bytes, now_ms);
+    case K_EYE: return eye_frame(e, frame, width, height, stride_bytes, now_ms);
+    case K_MOUTH:
+    case K_NOSE: return mouth_nose_frame(e, frame, width, height, stride_bytes, now_ms);
+    case K_EAR: return ear_frame(e, frame, width, height, stride_bytes, now_ms);
+    case K_TRACKER: return tracker_frame(e, frame, width, height, stride_bytes, pts_ns, now_ms);
+    }
+    return NV_ERR_ARG;
+}
+
+extern "C" int nv_element_get_message(nv_element *e, nv_meta_rect *out, int cap, int *n, int *pushed)
+{
+    if (!e) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    int m = std::min((int)e->msg.size(), cap);
+    if (out && m > 0) memcpy(out, e->msg.data(), (size_t)m * sizeof(nv_meta_rect));
+    if (n) *n = m;
+    if (pushed) *pushed = e->pushed ? 1 : 0;
+    return NV_OK;
+}
+
+extern "C" int nv_element_get_signal(nv_element *e, char *buf, int cap, int *emitted)
+{
+    if (!e) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    if (emitted) *emitted = e->emitted ? 1 : 0;
+    if (buf && cap > 0) snprintf(buf, (size_t)cap, "%s", e->emitted ? e->signal.c_str() : "");
+    return NV_OK;
+}
+
+extern "C" int nv_debug_track_faces(const nv_rect *prev, const int *prev_ids, int nprev, int next_id, const nv_rect *cur,
+                                    int ncur, int track_threshold, int pos_threshold, int area_threshold, nv_rect *out,
+                                    int *out_ids, int cap, int *n, int *next_id_out)
+{
+    if ((nprev > 0 && (!prev || !prev_ids)) || (ncur > 0 && !cur) || !n) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    std::vector<TrackedFace> faces, cf;
+    for (int i = 0; i < nprev; i++) faces.push_back({prev[i], prev_ids[i]});
+    for (int i = 0; i < ncur; i++) cf.push_back({cur[i], i});
+    track_faces(faces, next_id, cf, track_threshold, pos_threshold, area_threshold);
+    int m = std::min((int)faces.size(), cap);
+    for (int i = 0; i < m; i++) { if (out) out[i] = faces[i].r; if (out_ids) out_ids[i] = faces[i].id; }
+    *n = m;
+    if (next_id_out) *next_id_out = next_id;
+    return NV_OK;
+}

@@ -168,9 +168,9 @@ struct nv_ctx {
     uint8_t *d_lut = nullptr;    // 256
     uint8_t *d_aux = nullptr;    size_t aux_cap = 0;       // scratch image for standalone ops
 
-    // resize tables (element-level resize)
-    ResizeKey rkey;
-    int *d_rtab = nullptr;       size_t rtab_cap = 0;
+    // resize tables (element-level resize), small cache keyed by (src, dst) size
+    struct RtabEntry { ResizeKey k; int *d = nullptr; };
+    RtabEntry rtabs[16];  int rtab_next = 0;
 
     // plan
     PlanKey pkey;  bool plan_valid = false;
@@ -253,6 +253,12 @@ cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, con
 cudaError_t launch_alive_to_queue(const PlanDev *plan, int total_rows, const float *vnf, const uint32_t *bits_alive,
                                   uint2 *queue, int *counters, int queue_cap, cudaStream_t st);
 void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_end, TileParams *tp);
+
+// context.cu internals shared with elements.cu
+int nv_detect_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W, int H, int gstride, const uint8_t *d_lut,
+                     const nv_detect_params *p);
+int nv_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n);
+int nv_get_rtab(nv_ctx *ctx, int sw, int sh, int dw, int dh, const int **d_tab);
 
 // kernels_group.cu
 cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *cand, int cand_cap, uint32_t *cand_sorted,

@@ -75,6 +75,16 @@ _SIGS = {
     "nv_equalize_hist": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     "nv_resize_linear": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i]),
     "nv_flip_horizontal": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
+    "nv_element_create": (_i, [C.c_char_p, _i, C.c_char_p, C.POINTER(_vp)]),
+    "nv_element_destroy": (None, [_vp]),
+    "nv_element_set_property": (_i, [_vp, C.c_char_p, C.c_long]),
+    "nv_element_get_property": (_i, [_vp, C.c_char_p, C.POINTER(C.c_long)]),
+    "nv_element_push_faces_event": (_i, [_vp, _vp, _i]),
+    "nv_element_push_motion_event": (_i, [_vp]),
+    "nv_element_transform_frame_ip": (_i, [_vp, _vp, _i, _i, _i, C.c_uint64, C.c_double]),
+    "nv_element_get_message": (_i, [_vp, _vp, _i, _ip, _ip]),
+    "nv_element_get_signal": (_i, [_vp, C.c_char_p, _i, _ip]),
+    "nv_debug_track_faces": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _ip, _ip]),
     "nv_stage_name": (C.c_char_p, [_i]),
     "nv_ctx_set_profile": (_i, [_vp, _i]),
     "nv_ctx_get_stage_times": (_i, [_vp, C.POINTER(C.c_float), _i, _ip]),
@@ -176,6 +186,68 @@ class Cascade:
         r, w, t = (C.c_int * 12)(), (C.c_float * 3)(), (C.c_float * 3)()
         _check(_lib.nv_debug_cascade_stump(self.handle, i, r, w, t), "nv_debug_cascade_stump")
         return np.array(r[:], np.int32).reshape(3, 4), np.array(w[:], np.float32), np.array(t[:], np.float32)
+
+
+class MetaRect(C.Structure):
+    _fields_ = [("name", C.c_char * 16), ("type", C.c_char * 16), ("x", C.c_uint), ("y", C.c_uint), ("width", C.c_uint),
+                ("height", C.c_uint)]
+
+
+class Element:
+    """Mirror of one reference GStreamer element (same factory name, properties, per-frame behaviour)."""
+
+    def __init__(self, factory: str, gpu: int = 0, cascade_dir: str | None = None):
+        self.handle = _vp()
+        _check(_lib.nv_element_create(factory.encode(), gpu, cascade_dir.encode() if cascade_dir else None,
+                                      C.byref(self.handle)), f"nv_element_create({factory})")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.nv_element_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def set(self, name: str, value: int):
+        _check(_lib.nv_element_set_property(self.handle, name.encode(), value), f"set {name}")
+
+    def get(self, name: str) -> int:
+        v = C.c_long(0)
+        _check(_lib.nv_element_get_property(self.handle, name.encode(), C.byref(v)), f"get {name}")
+        return v.value
+
+    def push_faces(self, rects):
+        r = np.ascontiguousarray(np.asarray(rects, np.int32).reshape(-1, 4))
+        _check(_lib.nv_element_push_faces_event(self.handle, _p(r), len(r)), "nv_element_push_faces_event")
+
+    def push_motion(self):
+        _check(_lib.nv_element_push_motion_event(self.handle), "nv_element_push_motion_event")
+
+    def process(self, frame, pts_ns: int = 0, now_ms: float = -1.0):
+        """One buffer through transform_frame_ip.  Returns (message [(name, type, x, y, w, h)], pushed, signal or None)."""
+        frame = _u8(frame); h, w = frame.shape[:2]
+        _check(_lib.nv_element_transform_frame_ip(self.handle, _p(frame), w, h, frame.strides[0], pts_ns, now_ms),
+               "nv_element_transform_frame_ip")
+        buf = (MetaRect * 4096)(); n = C.c_int(0); pushed = C.c_int(0)
+        _check(_lib.nv_element_get_message(self.handle, buf, 4096, C.byref(n), C.byref(pushed)), "nv_element_get_message")
+        msg = [(buf[i].name.decode(), buf[i].type.decode(), buf[i].x, buf[i].y, buf[i].width, buf[i].height)
+               for i in range(n.value)]
+        sbuf = C.create_string_buffer(1 << 16); em = C.c_int(0)
+        _check(_lib.nv_element_get_signal(self.handle, sbuf, len(sbuf), C.byref(em)), "nv_element_get_signal")
+        return msg, bool(pushed.value), (sbuf.value.decode() if em.value else None)
+
+
+def track_faces(prev, prev_ids, next_id, cur, track_threshold=40, pos_threshold=8, area_threshold=500):
+    """Faces::track_faces (Faces.cpp:78-153) on explicit lists; returns (rects, ids, next_id)."""
+    prev = np.ascontiguousarray(np.asarray(prev, np.int32).reshape(-1, 4))
+    ids = np.ascontiguousarray(np.asarray(prev_ids, np.int32).reshape(-1))
+    cur = np.ascontiguousarray(np.asarray(cur, np.int32).reshape(-1, 4))
+    out = np.zeros((len(prev) + len(cur) + 1, 4), np.int32); oid = np.zeros(len(out), np.int32)
+    n = C.c_int(0); nid = C.c_int(0)
+    _check(_lib.nv_debug_track_faces(_p(prev), _p(ids), len(prev), next_id, _p(cur), len(cur), track_threshold,
+                                     pos_threshold, area_threshold, _p(out), _p(oid), len(out), C.byref(n), C.byref(nid)),
+           "nv_debug_track_faces")
+    return out[:n.value].copy(), oid[:n.value].copy(), nid.value
 
 
 class Context:

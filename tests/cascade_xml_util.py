@@ -43,3 +43,22 @@ def random_cascade(path, rng, w=20, h=20, nstages=4, max_trees=6, nfeat=24):
                   float(np.float32(rng.uniform(-1, 1))), float(np.float32(rng.uniform(-1, 1)))) for _ in range(nt)]
         stages.append((float(np.float32(rng.uniform(-0.4, 0.1) * nt)), trees))
     write_cascade(path, w, h, stages, feats)
+
+
+def permissive_cascade(path, rng, w, h, nstages=2, ntrees=3, nfeat=12, bias=0.35):
+    """A stump cascade that accepts a large share of windows (stand-in for absent feature models)."""
+    import numpy as np
+    feats = []
+    for _ in range(nfeat):
+        rects = []
+        for _k in range(2):
+            x = int(rng.integers(0, w - 3)); y = int(rng.integers(0, h - 3))
+            rects.append((x, y, int(rng.integers(2, w - x + 1)), int(rng.integers(2, h - y + 1)),
+                          float(np.float32(rng.uniform(-2, 2)))))
+        feats.append(rects)
+    stages = []
+    for _ in range(nstages):
+        trees = [(int(rng.integers(0, nfeat)), float(np.float32(rng.normal(0, 0.05))),
+                  float(np.float32(rng.uniform(-1, 1))), float(np.float32(rng.uniform(-1, 1)))) for _ in range(ntrees)]
+        stages.append((float(np.float32(-bias * ntrees)), trees))
+    write_cascade(path, w, h, stages, feats)

@@ -1,0 +1,87 @@
+"""CPU-side checks of the element mirrors: factory names, GObject property surface (names, ranges,
+effective defaults and the reference's quirks) and the host-side face tracking."""
+import numpy as np
+import pytest
+
+import nubovca as nv
+from element_ref import track_faces as ref_track_faces
+
+COMMON = {"detect-event": (0, 1, 0), "width-to-process": (0, 640, 320), "process-x-every-4-frames": (0, 4, 4),
+          "multi-scale-factor": (0, 51, 25), "activate-events": (0, 1, 0), "events-ms": (0, 30000, 30001)}
+SURFACE = {
+    "nubofacedetector": dict(COMMON, **{"view-faces": (0, 1, 0), "send-meta-data": (0, 1, 0), "width-to-process": (0, 640, 160),
+                                         "euclidean-distance": (0, 20, 8), "track-threshold": (0, 100, 40),
+                                         "area-threshold": (0, 1000, 500)}),
+    "nuboeyedetector": dict(COMMON, **{"view-eyes": (0, 1, 0), "send-meta-data": (0, 1, 0)}),
+    "nubomouthdetector": dict(COMMON, **{"view-mouths": (0, 1, 0), "send-meta-data": (0, 1, 0)}),
+    "nubonosedetector": dict(COMMON, **{"view-noses": (0, 1, 0), "send-meta-data": (0, 1, 0)}),
+    "nuboeardetector": dict(COMMON, **{"view-ears": (0, 1, 0), "meta-data": (0, 1, 0)}),           # kmseardetect.cpp:1006
+    "nubotracker": {"set_threshold": (0, 255, 20), "set_min_area": (0, 10000, 50), "set_max_area": (0, 300000, 30000),
+                    "set_distance": (0, 2000, 35), "set_visual_mode": (0, 4, 0), "activate-events": (0, 1, 0),
+                    "events-ms": (0, 30000, 30001)},
+}
+
+
+@pytest.mark.parametrize("factory", sorted(SURFACE))
+def test_property_surface(factory, tmp_path):
+    e = nv.Element(factory, 0, str(tmp_path))          # cascades missing: non-fatal, like the reference
+    for name, (lo, hi, default) in SURFACE[factory].items():
+        assert e.get(name) == default, name
+        for bad in (lo - 1, hi + 1):
+            with pytest.raises(nv.NuboError):
+                e.set(name, bad)
+        assert e.get(name) == default
+        e.set(name, hi)
+        if not (factory == "nubofacedetector" and name == "track-threshold"):
+            assert e.get(name) == hi
+    with pytest.raises(nv.NuboError):
+        e.get("no-such-property")
+    if factory == "nuboeardetector":
+        with pytest.raises(nv.NuboError):
+            e.set("send-meta-data", 1)                 # the server-side name does not exist on the element
+    e.close()
+
+
+def test_track_threshold_setter_quirk(tmp_path):
+    # kmsfacedetect.cpp:548-550: the track-threshold setter writes euclidean_threshold
+    e = nv.Element("nubofacedetector", 0, str(tmp_path))
+    e.set("track-threshold", 17)
+    assert e.get("track-threshold") == 40 and e.get("euclidean-distance") == 17
+    e.close()
+
+
+def test_unknown_factory():
+    with pytest.raises(nv.NuboError):
+        nv.Element("nubosomethingelse")
+
+
+def test_track_faces_cases():
+    # same place, same size: the old rectangle is kept (no jitter), id preserved
+    r, ids, nid = nv.track_faces([[100, 100, 50, 50]], [0], 1, [[101, 101, 50, 50]])
+    assert r.tolist() == [[100, 100, 50, 50]] and ids.tolist() == [0] and nid == 1
+    # moved beyond the size-dependent limit (area 2500 -> 3 px): the new rectangle replaces it
+    r, ids, nid = nv.track_faces([[100, 100, 50, 50]], [0], 1, [[110, 100, 50, 50]])
+    assert r.tolist() == [[110, 100, 50, 50]] and ids.tolist() == [0]
+    # same centre, area changed by more than 15 %: old position, new size
+    r, ids, nid = nv.track_faces([[100, 100, 50, 50]], [0], 1, [[95, 95, 60, 60]])
+    assert r.tolist() == [[100, 100, 60, 60]] and ids.tolist() == [0]
+    # farther than track-threshold: the old face is dropped, the new one gets a fresh id
+    r, ids, nid = nv.track_faces([[100, 100, 50, 50]], [0], 1, [[300, 100, 50, 50]])
+    assert r.tolist() == [[300, 100, 50, 50]] and ids.tolist() == [1] and nid == 2
+
+
+def test_track_faces_random_against_restatement():
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        nprev, ncur = int(rng.integers(0, 5)), int(rng.integers(0, 5))
+        prev = [[int(rng.integers(0, 200)), int(rng.integers(0, 200)), int(rng.integers(10, 90)), int(rng.integers(10, 90))]
+                for _ in range(nprev)]
+        cur = [[p[0] + int(rng.integers(-12, 13)), p[1] + int(rng.integers(-12, 13)), p[2] + int(rng.integers(-8, 9)),
+                p[3] + int(rng.integers(-8, 9))] for p in prev[:ncur]]
+        cur += [[int(rng.integers(0, 200)), int(rng.integers(0, 200)), int(rng.integers(10, 90)), int(rng.integers(10, 90))]
+                for _ in range(ncur - len(cur))]
+        ids = list(range(3, 3 + nprev))
+        thr = int(rng.integers(5, 60))
+        r, oid, nid = nv.track_faces(prev, ids, 10, cur, thr)
+        exp, enid = ref_track_faces(list(zip(prev, ids)), 10, cur, thr)
+        assert r.tolist() == [list(x[0]) for x in exp] and oid.tolist() == [x[1] for x in exp] and nid == enid

@@ -1,0 +1,155 @@
+"""GPU tests of the element mirrors (BASELINE config 2: nested facial features inside face ROIs, plus the
+face element over a frame sequence): the CUDA-backed elements against the oracle-backed restatement
+(tests/element_ref.py) on the same synthetic frames, message by message.
+
+The six haarcascade_mcs_*.xml files the feature elements load are absent from this image,
+so the cascade directory of the test holds stand-ins under the reference's file names: random stump cascades
+with the real models' window sizes that fire often (content-agnostic, never vacuous)."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import nubovca as nv
+import oracle as O
+from cascade_xml_util import permissive_cascade
+from element_ref import EarRef, FaceRef, FeatureRef
+from nubovca import synth
+
+pytestmark = pytest.mark.gpu
+
+STANDINS = {"haarcascade_mcs_righteye.xml": (18, 12, 0), "haarcascade_mcs_lefteye.xml": (18, 12, 1),
+            "haarcascade_mcs_mouth.xml": (25, 15, 4), "haarcascade_mcs_nose.xml": (18, 15, 5),
+            "haarcascade_mcs_rightear.xml": (12, 20, 0), "haarcascade_mcs_leftear.xml": (12, 20, 1)}
+
+
+@pytest.fixture(scope="module")
+def cdir(tmp_path_factory, cascade_dir):
+    d = tmp_path_factory.mktemp("cascades")
+    shutil.copy(os.path.join(cascade_dir, "haarcascade_frontalface_alt.xml"), d / "haarcascade_frontalface_alt.xml")
+    # the synthetic faces are frontal: the frontal model also stands in for the profile model of the ear element
+    shutil.copy(os.path.join(cascade_dir, "haarcascade_frontalface_alt.xml"), d / "haarcascade_profileface.xml")
+    for name, (w, h, seed) in STANDINS.items():
+        permissive_cascade(str(d / name), np.random.default_rng(seed), w, h)
+    return str(d)
+
+
+def oc(cdir, name):
+    return O.Cascade(os.path.join(cdir, name))
+
+
+def sequence(W, H, k, seed, n, **kw):
+    """n frames of the same scene with a little per-frame sensor noise (drives the temporal logic)."""
+    base = synth.frame(W, H, k, seed, **kw)
+    rng = np.random.default_rng(seed + 77)
+    out = []
+    for i in range(n):
+        f = base.astype(np.int16) + rng.integers(-3, 4, base.shape, dtype=np.int16)
+        out.append(np.clip(f, 0, 255).astype(np.uint8))
+    return out
+
+
+def test_face_element_sequence(cdir):
+    frames = sequence(640, 480, 4, 1, 6) + [np.full((480, 640, 3), 90, np.uint8)] * 3
+    for x4 in (4, 2):
+        e = nv.Element("nubofacedetector", 0, cdir)
+        ref = FaceRef(oc(cdir, "haarcascade_frontalface_alt.xml"))
+        e.set("process-x-every-4-frames", x4); ref.p["x4"] = x4
+        seen = 0
+        for i, f in enumerate(frames):
+            msg, pushed, sig = e.process(f, pts_ns=i * 33_000_000)
+            assert pushed and sig is None
+            assert msg == ref.process(f), (x4, i)
+            seen += len(msg)
+        assert seen > 0
+        e.close()
+
+
+def test_face_element_signal_and_detect_event(cdir):
+    e = nv.Element("nubofacedetector", 0, cdir)
+    f = synth.frame(640, 480, 4, 1)
+    e.set("activate-events", 1); e.set("events-ms", 1000)
+    msg, _, sig = e.process(f, now_ms=1e15)
+    assert sig == "".join(f"x:{m[2]},y:{m[3]},width:{m[4]},height:{m[5]};" for m in msg) and len(msg) >= 1
+    assert e.process(f, now_ms=1e15 + 500)[2] is None                 # rate limited
+    assert e.process(f, now_ms=1e15 + 1501)[2] is not None
+    e.close()
+    e = nv.Element("nubofacedetector", 0, cdir)
+    e.set("detect-event", 1)
+    assert e.process(f)[0] == []                                      # waits for an upstream "motion" event
+    e.push_motion()
+    assert len(e.process(f)[0]) >= 1
+    e.close()
+
+
+@pytest.mark.parametrize("kind,factory,files", [
+    ("eye", "nuboeyedetector", ("haarcascade_mcs_righteye.xml", "haarcascade_mcs_lefteye.xml")),
+    ("mouth", "nubomouthdetector", ("haarcascade_mcs_mouth.xml",)),
+    ("nose", "nubonosedetector", ("haarcascade_mcs_nose.xml",))])
+def test_feature_elements_cfg2(cdir, kind, factory, files):
+    """BASELINE config 2: one 1280x720 stream, face stage at 160 wide, features at 320 wide inside the faces."""
+    frames = sequence(1280, 720, 3, 2, 5, smin=0.4, smax=0.6)      # faces >= 30 px at the 160-wide face stage
+    e = nv.Element(factory, 0, cdir)
+    ref = FeatureRef(kind, oc(cdir, "haarcascade_frontalface_alt.xml"), *[oc(cdir, f) for f in files])
+    total = 0
+    for i, f in enumerate(frames):
+        msg, pushed, _ = e.process(f, pts_ns=i * 33_000_000)
+        exp = ref.process(f)
+        assert pushed and msg == exp, (kind, i, msg[:4], exp[:4])
+        total += sum(1 for m in msg if m[1] != "face")
+    assert total > 0, "stand-in cascade never fired: the test would be vacuous"
+    e.close()
+
+
+def test_feature_element_faces_from_upstream_event(cdir):
+    """ROI nesting through the downstream metadata event: the face element's rectangles (original-image
+    coordinates) feed the mouth element in detect-event mode (kmseyedetect.cpp:954-961 pattern)."""
+    frames = sequence(1280, 720, 3, 2, 3, smin=0.4, smax=0.6)
+    face = nv.Element("nubofacedetector", 0, cdir)
+    mouth = nv.Element("nubomouthdetector", 0, cdir)
+    mouth.set("detect-event", 1)
+    ref = FeatureRef("mouth", None, oc(cdir, "haarcascade_mcs_mouth.xml"))
+    ref.p["detect_event"] = 1
+    assert mouth.process(frames[0])[0] == []                          # nothing queued: frame skipped
+    total = 0
+    for f in frames:
+        fmsg, _, _ = face.process(f)
+        rects = [[m[2], m[3], m[4], m[5]] for m in fmsg if m[1] == "face"]
+        mouth.push_faces(rects); ref.queue.append(rects)
+        msg, _, _ = mouth.process(f)
+        assert msg == ref.process(f)
+        total += sum(1 for m in msg if m[1] == "mouth")
+    assert total > 0
+    face.close(); mouth.close()
+
+
+def test_ear_element(cdir):
+    frames = sequence(1280, 720, 3, 2, 3, smin=0.4, smax=0.6)
+    e = nv.Element("nuboeardetector", 0, cdir)
+    ref = EarRef(oc(cdir, "haarcascade_profileface.xml"), oc(cdir, "haarcascade_mcs_rightear.xml"),
+                 oc(cdir, "haarcascade_mcs_leftear.xml"))
+    for x in (e,):
+        x.set("multi-scale-factor", 10)
+    ref.p["sf"] = 10
+    total = 0
+    for i, f in enumerate(frames):
+        msg, pushed, _ = e.process(f)
+        assert not pushed                                             # built but never pushed (kmseardetect.cpp:210-290)
+        assert msg == ref.process(f), i
+        total += sum(1 for m in msg if m[1] == "ear")
+    assert total > 0
+    e.close()
+
+
+def test_tracker_element(cdir):
+    frames = synth.tracker_sequence(640, 360, 5, seed=5)
+    e = nv.Element("nubotracker", 0, cdir)
+    st = O.TrackerState(640, 360)
+    e.set("activate-events", 1); e.set("events-ms", 0)
+    for i, f in enumerate(frames):
+        msg, pushed, sig = e.process(f, now_ms=1e15 + 40.0 * i)
+        exp, _, _ = st.process(f, 1e15 + 40.0 * i)
+        assert [list(m[2:]) for m in msg] == exp.tolist(), i
+        assert (sig is not None) == (len(exp) > 0)
+    e.close()
