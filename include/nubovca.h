@@ -104,9 +104,12 @@ NV_API int nv_face_detect(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, 
                           int stride_bytes, const nv_face_params *p, nv_rect *out, int cap, int *n);
 
 /* Asynchronous halves of nv_face_detect, so that one host thread can keep many per-stream
- * contexts in flight (BASELINE config 5: 32 streams per GPU).  submit() copies the frame into the
- * ctx's pinned staging buffer (after which the caller may reuse it) and enqueues copy + kernels
- * on the ctx's CUDA stream; collect() waits for that stream and returns the rectangles. */
+ * contexts in flight (BASELINE config 5: 32 streams per GPU).  submit() enqueues copy + kernels on the
+ * ctx's CUDA stream; collect() waits for that stream and returns the rectangles.  A pageable frame is
+ * first copied into the ctx's pinned staging buffer (the caller may reuse it as soon as submit returns); a
+ * frame in page-locked memory (cudaHostAlloc / cudaHostRegister) is read directly by the DMA engine and
+ * must stay untouched until collect.  Once a context sees the same call shape twice, the whole per-frame
+ * kernel sequence is replayed as a single CUDA graph launch. */
 NV_API int nv_face_submit(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, int width, int height,
                           int stride_bytes, const nv_face_params *p);
 NV_API int nv_face_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n);

@@ -144,7 +144,7 @@ static int alloc_candidates(nv_ctx *c, int cap, bool with_adj)
     cudaFree(c->d_cand); cudaFree(c->d_cand_sorted); cudaFree(c->d_cand_rects); cudaFree(c->d_adj); cudaFree(c->d_result);
     cudaFreeHost(c->h_result);
     c->d_cand = c->d_cand_sorted = nullptr; c->d_cand_rects = nullptr; c->d_adj = nullptr; c->d_result = c->h_result = nullptr;
-    c->cand_cap = cap; c->result_cap = cap; c->adj_cap = 0;
+    c->cand_cap = cap; c->result_cap = cap; c->adj_cap = 0; c->epoch++;
     NV_CUDA(cudaMalloc(&c->d_cand, (size_t)cap * sizeof(uint32_t)));
     NV_CUDA(cudaMalloc(&c->d_cand_sorted, (size_t)cap * sizeof(uint32_t)));
     NV_CUDA(cudaMalloc(&c->d_cand_rects, (size_t)cap * sizeof(int4)));
@@ -208,6 +208,7 @@ extern "C" void nv_ctx_destroy(nv_ctx *c)
     cudaFreeHost(c->h_result);
     cudaFree(c->d_maps); cudaFree(c->d_trk_prev); cudaFree(c->d_trk_mhi); cudaFree(c->d_trk_labels); cudaFree(c->d_trk_mask);
     cudaFree(c->d_trk_boxes); cudaFree(c->d_trk_misc); cudaFreeHost(c->h_trk);
+    if (c->gexec) cudaGraphExecDestroy(c->gexec);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     for (int i = 0; i <= NV_NUM_STAGES; i++) if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -219,6 +220,7 @@ extern "C" int nv_ctx_set_debug(nv_ctx *ctx, int debug)
 {
     if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }
     ctx->debug = debug ? 1 : 0;
+    ctx->epoch++;
     ctx->plan_valid = false;       // debug buffers are sized with the plan
     return NV_OK;
 }
@@ -395,6 +397,7 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
     ctx->pkey = key;
     ctx->plan_valid = true;
     ctx->tp_casc = nullptr;            // tensor maps and tile geometry follow the plan
+    ctx->epoch++;
     return NV_OK;
 }
 
@@ -422,6 +425,7 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
     const DevCascade &m = casc->meta;
     ctx->tp_casc = casc;
     ctx->use_tiles = false;
+    ctx->epoch++;
     encode_tiled_fn enc = get_encode_tiled();
     if (!enc || m.win_w > 32 || m.win_h > 32 || P.nlevels == 0) return NV_OK;
     // bulk stages: as many as fit the parameter bank
@@ -464,20 +468,28 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
 // ------------------------------------------------------------------------------------------------
 // detectMultiScale on a device-resident gray image (+ LUT), everything stream-ordered
 // ------------------------------------------------------------------------------------------------
-int nv_detect_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W, int H, int gstride,
-                            const uint8_t *d_lut, const nv_detect_params *p)
+// host-side preparation (may allocate, copy tables and synchronise): plan, cascade upload, tile parameters
+static int detect_prepare(nv_ctx *ctx, nv_cascade *casc, int W, int H, const nv_detect_params *p)
 {
     int rc = ensure_plan(ctx, casc, W, H, p);
     if (rc != NV_OK) return rc;
-    const DevStump *stumps; const DevCascade *meta;
-    if ((rc = cascade_on_device(casc, ctx->gpu, ctx->stream, &stumps, &meta)) != NV_OK) return rc;
+    if ((rc = cascade_on_device(casc, ctx->gpu, ctx->stream, &ctx->cur_stumps, &ctx->cur_meta)) != NV_OK) return rc;
     if ((rc = ensure_tile_params(ctx, casc)) != NV_OK) return rc;
-    const PlanDev &P = ctx->plan;
-    cudaStream_t st = ctx->stream;
     if (p->min_neighbors > 0 && ctx->adj_cap < (size_t)ctx->cand_cap) {      // grown earlier for an ungrouped call
-        NV_CUDA(cudaStreamSynchronize(st));
+        NV_CUDA(cudaStreamSynchronize(ctx->stream));
         if ((rc = alloc_candidates(ctx, std::min(ctx->cand_cap, CAND_CAP_GROUPED), true)) != NV_OK) return rc;
     }
+    return NV_OK;
+}
+
+// the stream-ordered part: only asynchronous work on ctx->stream, so it can be captured into a CUDA graph
+static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W, int H, int gstride,
+                          const uint8_t *d_lut, const nv_detect_params *p, int *nlaunch)
+{
+    const DevStump *stumps = ctx->cur_stumps;
+    const DevCascade *meta = ctx->cur_meta;
+    const PlanDev &P = ctx->plan;
+    cudaStream_t st = ctx->stream;
     int nl = 0;
     for (int i = 2; i <= NV_NUM_STAGES; i++) ctx->prof_set[i] = false;
     NV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int), st));
@@ -526,11 +538,28 @@ int nv_detect_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W
     prof_mark(ctx, 8);
     NV_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(ResultHeader) + NV_RESULT_INLINE * sizeof(nv_rect),
                             cudaMemcpyDeviceToHost, st));
-    ctx->launches += nl;
+    *nlaunch += nl;
+    return NV_OK;
+}
+
+static void detect_bookkeeping(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W, int H, int gstride,
+                               const uint8_t *d_lut, const nv_detect_params *p)
+{
     ctx->last_min_neighbors = p->min_neighbors;
     ctx->last_casc = casc; ctx->last_params = *p; ctx->last_W = W; ctx->last_H = H;
     ctx->tap_gray = d_gray; ctx->tap_lut = d_lut; ctx->tap_stride = gstride;
     ctx->pending = true;
+}
+
+int nv_detect_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W, int H, int gstride,
+                     const uint8_t *d_lut, const nv_detect_params *p)
+{
+    int rc = detect_prepare(ctx, casc, W, H, p);
+    if (rc != NV_OK) return rc;
+    int nl = 0;
+    if ((rc = detect_enqueue(ctx, casc, d_gray, W, H, gstride, d_lut, p, &nl)) != NV_OK) return rc;
+    ctx->launches += nl;
+    detect_bookkeeping(ctx, casc, d_gray, W, H, gstride, d_lut, p);
     return NV_OK;
 }
 
@@ -645,24 +674,68 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
     if (scale > 0 && cv_round(width / scale) > 0) cols = cv_round(width / scale); else scale = 1;
     const int *d_rtab;
     if ((rc = nv_get_rtab(ctx, width, height, cols, rows, &d_rtab)) != NV_OK) return rc;
-    const uint8_t *d_src = bgr;
-    if (!on_device) {
-        memcpy(ctx->h_frame, bgr, (size_t)stride * height);
-        NV_CUDA(cudaMemcpyAsync(ctx->d_frame, ctx->h_frame, (size_t)stride * height, cudaMemcpyHostToDevice, ctx->stream));
-        d_src = ctx->d_frame;
-    }
-    ctx->prof_set[0] = ctx->prof_set[1] = false;
-    prof_mark(ctx, 0);
-    NV_CUDA(launch_face_prep(d_src, width, height, stride, 3, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream));
-    prof_mark(ctx, 1);
-    NV_CUDA(launch_lut(ctx->d_hist, cols * rows, ctx->d_lut, ctx->stream));
-    ctx->launches += 2;
+    nv_cascade *casc = const_cast<nv_cascade *>(c);
     nv_detect_params dp;
     dp.scale_factor = p->scale_factor; dp.min_neighbors = p->min_neighbors; dp.flags = 0;
     dp.min_w = p->min_w < 0 ? cols / 20 : p->min_w;           // kmsfacedetect.cpp:811
     dp.min_h = p->min_w < 0 ? rows / 20 : p->min_h;
     dp.max_w = dp.max_h = 0;
-    return nv_detect_device(ctx, const_cast<nv_cascade *>(c), ctx->d_gray, cols, rows, cols, ctx->d_lut, &dp);
+    if ((rc = detect_prepare(ctx, casc, cols, rows, &dp)) != NV_OK) return rc;
+
+    const uint8_t *d_src = bgr;
+    if (!on_device) {
+        // page-locked caller memory is copied straight from the caller; anything else goes through the pinned staging buffer
+        cudaPointerAttributes at;
+        bool pinned = cudaPointerGetAttributes(&at, bgr) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        if (!pinned) { cudaGetLastError(); memcpy(ctx->h_frame, bgr, (size_t)stride * height); }
+        NV_CUDA(cudaMemcpyAsync(ctx->d_frame, pinned ? bgr : ctx->h_frame, (size_t)stride * height, cudaMemcpyHostToDevice,
+                                ctx->stream));
+        d_src = ctx->d_frame;
+    }
+    auto enqueue = [&](int *nl) -> int {
+        ctx->prof_set[0] = ctx->prof_set[1] = false;
+        prof_mark(ctx, 0);
+        NV_CUDA(launch_face_prep(d_src, width, height, stride, 3, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream));
+        prof_mark(ctx, 1);
+        NV_CUDA(launch_lut(ctx->d_hist, cols * rows, ctx->d_lut, ctx->stream));
+        *nl += 2;
+        return detect_enqueue(ctx, casc, ctx->d_gray, cols, rows, cols, ctx->d_lut, &dp, nl);
+    };
+    // A context that sees the same call shape again replays it as ONE CUDA graph launch (the per-stream steady
+    // state of an element); debug / profiling runs keep individual launches so that their events and taps work.
+    nv_ctx::GraphKey key = {d_src, width, height, stride, cols, rows, d_rtab, casc, dp.scale_factor, dp.min_neighbors,
+                            dp.min_w, dp.min_h, ctx->epoch};
+    bool graphable = !ctx->debug && !ctx->profile && !ctx->no_graph;
+    int nl = 0;
+    if (graphable && ctx->gexec && key == ctx->gkey) {
+        NV_CUDA(cudaGraphLaunch(ctx->gexec, ctx->stream));
+        nl = ctx->g_nl;
+    } else if (graphable && key == ctx->gkey_seen) {
+        if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
+        cudaGraph_t g = nullptr;
+        NV_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue(&nl);
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        if (rc != NV_OK || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            ctx->no_graph = true;                      // capture is not possible here: stay on plain launches
+            nl = 0;
+            if ((rc = enqueue(&nl)) != NV_OK) return rc;
+        } else {
+            ce = cudaGraphInstantiate(&ctx->gexec, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) { ctx->gexec = nullptr; nv_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce)); return NV_ERR_CUDA; }
+            ctx->gkey = key; ctx->g_nl = nl;
+            NV_CUDA(cudaGraphLaunch(ctx->gexec, ctx->stream));
+        }
+    } else {
+        ctx->gkey_seen = key;
+        if ((rc = enqueue(&nl)) != NV_OK) return rc;
+    }
+    ctx->launches += nl;
+    detect_bookkeeping(ctx, casc, ctx->d_gray, cols, rows, cols, ctx->d_lut, &dp);
+    return NV_OK;
 }
 
 extern "C" int nv_face_submit(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, int width, int height,

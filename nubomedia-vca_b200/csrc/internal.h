@@ -192,6 +192,20 @@ struct nv_ctx {
     uint8_t *d_result = nullptr; uint8_t *h_result = nullptr;   // ResultHeader + rects
     int result_cap = 0;                                     // rects
 
+    // CUDA graph of the steady-state face pipeline (one launch per frame once a call shape repeats)
+    struct GraphKey {
+        const void *src = nullptr; int w = 0, h = 0, stride = 0, cols = 0, rows = 0; const int *rtab = nullptr;
+        const nv_cascade *casc = nullptr; double sf = 0; int mn = 0, min_w = 0, min_h = 0; unsigned long long epoch = 0;
+        bool operator==(const GraphKey &o) const {
+            return src == o.src && w == o.w && h == o.h && stride == o.stride && cols == o.cols && rows == o.rows &&
+                   rtab == o.rtab && casc == o.casc && sf == o.sf && mn == o.mn && min_w == o.min_w && min_h == o.min_h &&
+                   epoch == o.epoch;
+        }
+    };
+    const DevStump *cur_stumps = nullptr;  const DevCascade *cur_meta = nullptr;   // device copies of the cascade in use
+    cudaGraphExec_t gexec = nullptr;  GraphKey gkey, gkey_seen;  int g_nl = 0;  bool no_graph = false;
+    unsigned long long epoch = 1;     // bumped whenever a buffer the pipeline binds is re-allocated or re-planned
+
     // last-call bookkeeping (kept so that collect() can re-run a call whose candidate buffers overflowed)
     nv_cascade *last_casc = nullptr;  nv_detect_params last_params = {};  int last_W = 0, last_H = 0;
     const uint8_t *tap_gray = nullptr, *tap_lut = nullptr;  int tap_stride = 0;
