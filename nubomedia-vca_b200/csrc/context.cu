@@ -426,6 +426,7 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
     ctx->tp_casc = casc;
     ctx->use_tiles = false;
     ctx->epoch++;
+    ctx->use_s0p = P.nlevels > 0 && fill_stage0_params(casc, P, &ctx->s0p);
     encode_tiled_fn enc = get_encode_tiled();
     if (!enc || m.win_w > 32 || m.win_h > 32 || P.nlevels == 0) return NV_OK;
     // bulk stages: as many as fit the parameter bank
@@ -501,8 +502,14 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         prof_mark(ctx, 3);
         NV_CUDA(launch_colscan(ctx->d_plan, P.total_colblk, ctx->d_sum, ctx->d_sq, st));
         prof_mark(ctx, 4);
-        NV_CUDA(launch_stage0_rows(ctx->d_plan, P.total_rows, meta, stumps, ctx->d_sum, ctx->d_sq, ctx->d_vnf,
-                                   ctx->d_bits_ok, ctx->d_counters, depth, st));
+        if (ctx->use_s0p) {
+            Stage0Params &sp = ctx->s0p;
+            sp.sum = ctx->d_sum; sp.sq = ctx->d_sq; sp.vnf = ctx->d_vnf; sp.bits_alive = ctx->d_bits_ok;
+            sp.counters = ctx->d_counters; sp.depth = depth;
+            NV_CUDA(launch_stage0_rows_p(sp, st));
+        } else
+            NV_CUDA(launch_stage0_rows(ctx->d_plan, P.total_rows, meta, stumps, ctx->d_sum, ctx->d_sq, ctx->d_vnf,
+                                       ctx->d_bits_ok, ctx->d_counters, depth, st));
         prof_mark(ctx, 5);
         nl += 3;
         int qcap = (int)std::min<size_t>(ctx->queue_cap, 0x7fffffff);
@@ -520,7 +527,8 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
             prof_mark(ctx, 6);
             if (ctx->bulk_end < casc->meta.nstages) {
                 NV_CUDA(launch_cascade_tail(ctx->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
-                                            ctx->cand_cap, depth, ctx->bulk_end, casc->h.order_free, 148 * 4, st));
+                                            ctx->cand_cap, depth, ctx->bulk_end, casc->h.order_free, 148 * 8, st,
+                                            8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));
                 nl++;
             }
         } else {

@@ -144,6 +144,25 @@ struct TileParams {
 };
 static_assert(sizeof(TileParams) <= 32000, "kernel parameter space is 32764 bytes");
 
+// ---- k_stage0_rows_p parameters: per-level corner offsets of the stage-0 classifiers, so that the whole
+// address arithmetic of stage 0 is warp-uniform and lives in the constant bank ----
+#define NV_S0_MAX_STUMPS 8
+struct Stage0Params {
+    uint4 off[NV_MAX_LEVELS][NV_S0_MAX_STUMPS][3];   // word offsets of the rect corners a, b, c, d in the level's integral layout
+    int4 var[NV_MAX_LEVELS];                         // corners of the variance-normalisation rect
+    int4 lv_a[NV_MAX_LEVELS];                        // row0, nxw, nx, ystep * ipitch
+    int4 lv_b[NV_MAX_LEVELS];                        // iofs, wofs, bofs, unused
+    float2 cf[NV_S0_MAX_STUMPS][3];                  // (w0, w1), (w2, threshold), (left, right)
+    int nlevels, total_rows, n0, win_w, win_h;
+    float thr0;
+    const uint32_t *sum, *sq;
+    float *vnf;
+    uint32_t *bits_alive;
+    int *counters;
+    int16_t *depth;
+};
+static_assert(sizeof(Stage0Params) <= 32000, "kernel parameter space is 32764 bytes");
+
 // header of the device result block (then rects follow)
 struct ResultHeader {
     int n_out;          // rects written after grouping + clipping
@@ -182,7 +201,7 @@ struct nv_ctx {
     float *d_vnf = nullptr;      size_t win_cap = 0;
     int16_t *d_depth = nullptr;  size_t depth_cap = 0;      // debug only
     uint32_t *d_bits_fail = nullptr, *d_bits_ok = nullptr;  size_t bits_cap = 0;   // [bits_ok doubles as bits_alive]
-    TileParams tp[2];  CUtensorMap *d_maps = nullptr;  bool use_tiles = false;  int bulk_end = 0;  const nv_cascade *tp_casc = nullptr;
+    TileParams tp[2];  Stage0Params s0p;  bool use_s0p = false;  CUtensorMap *d_maps = nullptr;  bool use_tiles = false;  int bulk_end = 0;  const nv_cascade *tp_casc = nullptr;
     uint2 *d_queue = nullptr;    size_t queue_cap = 0;
     int *d_counters = nullptr;                              // [0] queue count, [1] cand count, [2] overflow
     uint32_t *d_cand = nullptr;  int cand_cap = 0;          // packed window ids
@@ -261,9 +280,11 @@ cudaError_t launch_stage0_rows(const PlanDev *plan, int total_rows, const DevCas
                                const uint32_t *sum, const uint32_t *sq, float *vnf, uint32_t *bits_alive, int *counters,
                                int16_t *depth, cudaStream_t st);
 cudaError_t launch_cascade_tiles(const TileParams &tp, int ystep, int ntiles, cudaStream_t st);
+cudaError_t launch_stage0_rows_p(const Stage0Params &sp, cudaStream_t st);
+bool fill_stage0_params(const nv_cascade *c, const PlanDev &P, Stage0Params *sp);
 cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,
                                 const uint2 *tail, int *counters, uint32_t *cand, int cand_cap, int16_t *depth,
-                                int stage_begin, int order_free, int nblocks, cudaStream_t st);
+                                int stage_begin, int order_free, int nblocks, cudaStream_t st, int smem_bytes);
 cudaError_t launch_alive_to_queue(const PlanDev *plan, int total_rows, const float *vnf, const uint32_t *bits_alive,
                                   uint2 *queue, int *counters, int queue_cap, cudaStream_t st);
 void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_end, TileParams *tp);

@@ -21,6 +21,14 @@ __device__ __forceinline__ int find_level_c(const PlanDev *__restrict__ plan, in
     return l;
 }
 
+// warp-uniform warp index, rebuilt from votes so that the compiler can prove it (see uniformize below)
+__device__ __forceinline__ int uniformize_s0(int v)
+{
+    int r = 0;
+    for (int k = 0; k < 3; k++) r |= (int)(__ballot_sync(0xffffffffu, (v >> k) & 1) & (1u << k));
+    return r;
+}
+
 struct LevelView {
     const uint32_t *sum;
     int pitch, plane, ys;
@@ -276,6 +284,111 @@ k_stage0_rows(const PlanDev *__restrict__ plan, int total_rows, const DevCascade
     if (lane == 0 && nalive) atomicAdd(&counters[0], nalive);
 }
 
+// Same pass with every level-dependent offset precomputed on the host and passed in the parameter bank: the
+// address arithmetic is warp-uniform (uniform datapath), and the 32-step automaton is replaced by its closed
+// form on bit-words.  Let g[i] = "window i was visited and failed stage 0"; then g[i+1] = f[i+1] & !g[i], i.e. inside
+// every run of consecutive failures g is set at even offsets from the run start (a carry-in skip just removes
+// bit 0 from the first run); visited[i+1] = !g[i].  Runs starting at even / odd positions are isolated with one
+// addition each (the carry clears exactly the run it enters).
+__device__ __forceinline__ uint32_t skip_rule_word(uint32_t f, bool &e)
+{
+    uint32_t fp = e ? f : (f & ~1u);
+    uint32_t s = fp & ~(fp << 1);
+    uint32_t me = fp & ~(fp + (s & 0x55555555u)), mo = fp & ~(fp + (s & 0xAAAAAAAAu));
+    uint32_t g = (me & 0x55555555u) | (mo & 0xAAAAAAAAu);
+    uint32_t em = (~(g << 1) & ~1u) | (e ? 1u : 0u);
+    e = !(g >> 31);
+    return em;
+}
+
+__global__ void __launch_bounds__(256) k_stage0_rows_p(const __grid_constant__ Stage0Params P)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + uniformize_s0(threadIdx.x >> 5);
+    if (row >= P.total_rows) return;
+    int l = 0;
+    while (l + 1 < P.nlevels && P.lv_a[l + 1].x <= row) l++;
+    const int4 la = P.lv_a[l], lb = P.lv_b[l], vr = P.var[l];
+    const int iy = row - la.x, nxw = la.y, nx = la.z;
+    const uint32_t *srow = P.sum + lb.x + (size_t)iy * la.w, *qrow = P.sq + lb.x + (size_t)iy * la.w;
+    const double area = (double)((P.win_w - 2) * (P.win_h - 2));
+    const double thr0 = (double)P.thr0;
+    bool e = true;                                   // is the next window visited?  (x = 0 always is)
+    int nalive = 0;
+    for (int cx = 0; cx < nxw; cx++) {
+        int ix = cx * 32 + lane;
+        bool valid = ix < nx;
+        int ixc = valid ? ix : nx - 1;
+        const uint32_t *wb = srow + ixc, *qb = qrow + ixc;
+        int valsum = (int)(__ldg(wb + vr.x) - __ldg(wb + vr.y) - __ldg(wb + vr.z) + __ldg(wb + vr.w));
+        uint32_t valsq = __ldg(qb + vr.x) - __ldg(qb + vr.y) - __ldg(qb + vr.z) + __ldg(qb + vr.w);
+        double nf = __dsub_rn(__dmul_rn(area, (double)valsq), __dmul_rn((double)valsum, (double)valsum));
+        float vnf = 0.f;
+        bool ok = false;
+        if (nf > 0.) {
+            vnf = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn(nf)));
+            ok = __dmul_rn(area, (double)vnf) < 1e-1;
+        }
+        double tmp = 0.;
+        for (int k = 0; k < P.n0; k++) {
+            uint4 o0 = P.off[l][k][0], o1 = P.off[l][k][1];
+            float2 w01 = P.cf[k][0], w2t = P.cf[k][1], lr = P.cf[k][2];
+            int r0 = (int)(__ldg(wb + o0.x) - __ldg(wb + o0.y) - __ldg(wb + o0.z) + __ldg(wb + o0.w));
+            int r1 = (int)(__ldg(wb + o1.x) - __ldg(wb + o1.y) - __ldg(wb + o1.z) + __ldg(wb + o1.w));
+            float f = __fadd_rn(__fmul_rn(w01.x, __int2float_rn(r0)), __fmul_rn(w01.y, __int2float_rn(r1)));
+            if (w2t.x != 0.f) {
+                uint4 o2 = P.off[l][k][2];
+                int r2 = (int)(__ldg(wb + o2.x) - __ldg(wb + o2.y) - __ldg(wb + o2.z) + __ldg(wb + o2.w));
+                f = __fadd_rn(f, __fmul_rn(w2t.x, __int2float_rn(r2)));
+            }
+            f = __fmul_rn(f, vnf);
+            tmp = __dadd_rn(tmp, (double)(f < w2t.y ? lr.x : lr.y));
+        }
+        ok = ok && valid;
+        bool fail = ok && tmp < thr0;
+        uint32_t fm = __ballot_sync(0xffffffffu, fail);
+        uint32_t em = skip_rule_word(fm, e);
+        bool visited = (em >> lane) & 1u;
+        bool alive = visited && ok && !fail;
+        uint32_t am = __ballot_sync(0xffffffffu, alive);
+        nalive += __popc(am);
+        if (lane == 0) P.bits_alive[lb.z + iy * nxw + cx] = am;
+        if (alive) P.vnf[lb.y + iy * nx + ix] = vnf;
+        if (P.depth && valid && !alive)
+            P.depth[lb.y + iy * nx + ix] = (int16_t)(!visited ? NV_DEPTH_SKIPPED : (!ok ? NV_DEPTH_VARREJ : 0));
+    }
+    if (lane == 0 && nalive) atomicAdd(&P.counters[0], nalive);
+}
+
+bool fill_stage0_params(const nv_cascade *c, const PlanDev &P, Stage0Params *sp)
+{
+    const DevCascade &m = c->meta;
+    int n0 = m.stage_first[1];
+    if (n0 > NV_S0_MAX_STUMPS || P.nlevels > NV_MAX_LEVELS) return false;
+    sp->nlevels = P.nlevels; sp->total_rows = P.total_rows; sp->n0 = n0; sp->win_w = m.win_w; sp->win_h = m.win_h;
+    sp->thr0 = m.stage_thr[0];
+    for (int k = 0; k < n0; k++) {
+        const DevStump &d = c->stumps[k];
+        sp->cf[k][0] = make_float2(d.w[0], d.w[1]);
+        sp->cf[k][1] = make_float2(d.w[2], d.thr);
+        sp->cf[k][2] = make_float2(d.left, d.right);
+    }
+    for (int l = 0; l < P.nlevels; l++) {
+        const LevelDesc &L = P.lv[l];
+        auto off = [&](int dx, int dy) { return (uint32_t)(dy * L.ipitch + (L.ystep == 2 ? (dx & 1) * L.iplane + (dx >> 1) : dx)); };
+        for (int k = 0; k < n0; k++)
+            for (int j = 0; j < 3; j++) {
+                uint32_t r = c->stumps[k].r[j];
+                int x = r & 255, y = (r >> 8) & 255, w = (r >> 16) & 255, h = r >> 24;
+                sp->off[l][k][j] = make_uint4(off(x, y), off(x + w, y), off(x, y + h), off(x + w, y + h));
+            }
+        sp->var[l] = make_int4((int)off(1, 1), (int)off(m.win_w - 1, 1), (int)off(1, m.win_h - 1), (int)off(m.win_w - 1, m.win_h - 1));
+        sp->lv_a[l] = make_int4(L.row0, L.nxw, L.nx, L.ystep * L.ipitch);
+        sp->lv_b[l] = make_int4(L.iofs, L.wofs, L.bofs, 0);
+    }
+    return true;
+}
+
 // expands alive bit-words into a window queue (fallback path for cascades the tile kernel cannot take)
 __global__ void __launch_bounds__(256)
 k_alive_to_queue(const PlanDev *__restrict__ plan, int total_rows, const float *__restrict__ vnf,
@@ -506,12 +619,16 @@ k_cascade_tail(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ 
                const uint32_t *__restrict__ sum, const uint2 *__restrict__ tail, int *__restrict__ counters,
                uint32_t *__restrict__ cand, int cand_cap, int16_t *__restrict__ depth, int stage_begin, int order_free)
 {
-    __shared__ uint32_t s_win[8][(TAIL_MAX_WIN + 1) * (TAIL_MAX_WIN + 1)];
+    extern __shared__ uint32_t s_win[];                          // 8 warps x (win_h+1) x (win_w+1) words
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *win = s_win[warp];
     int n = counters[3], nstages = meta->nstages;
     int ww = plan->win_w, wh = plan->win_h, LP = ww + 1, npatch = (wh + 1) * LP;
-    for (int e = blockIdx.x * 8 + warp; e < n; e += gridDim.x * 8) {
+    uint32_t *win = s_win + warp * npatch;
+    for (;;) {                                                   // windows are handed out one at a time: depths are very uneven
+        int e = 0;
+        if (lane == 0) e = atomicAdd(&counters[5], 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= n) break;
         uint2 q = tail[e];
         int l = q.x >> 26, iy = (q.x >> 13) & 8191, ix = q.x & 8191;
         float vnf = __uint_as_float(q.y);
@@ -643,9 +760,16 @@ cudaError_t launch_cascade_tiles(const TileParams &tp, int ystep, int ntiles, cu
 
 cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,
                                 const uint2 *tail, int *counters, uint32_t *cand, int cand_cap, int16_t *depth,
-                                int stage_begin, int order_free, int nblocks, cudaStream_t st)
+                                int stage_begin, int order_free, int nblocks, cudaStream_t st, int smem_bytes)
 {
-    k_cascade_tail<<<nblocks, 256, 0, st>>>(plan, meta, stumps, sum, tail, counters, cand, cand_cap, depth, stage_begin,
-                                            order_free);
+    (void)nblocks;
+    k_cascade_tail<<<148 * 8, 256, smem_bytes, st>>>(plan, meta, stumps, sum, tail, counters, cand, cand_cap, depth, stage_begin,
+                                                     order_free);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stage0_rows_p(const Stage0Params &sp, cudaStream_t st)
+{
+    k_stage0_rows_p<<<(sp.total_rows + 7) / 8, 256, 0, st>>>(sp);
     return cudaGetLastError();
 }

@@ -2,10 +2,14 @@
 // CascadeClassifier::detectMultiScale (call sites kmsfacedetect.cpp:809-811 etc.).
 //
 // cv::partition's class labels depend only on the connected components of the SimilarRects graph and on
-// the order of first members, so the union-find with rank is replaced by: canonical ordering of the
-// candidates (rank sort on the packed window id = scale -> y -> x, OpenCV's single-thread order), an
-// adjacency bit-matrix built by many blocks, then min-label propagation in one block.
+// the order of first members, so its sequential union-find with rank is replaced by: canonical ordering of
+// the candidates (rank sort on the packed window id = scale -> y -> x, OpenCV's single-thread order), a
+// similarity bit-matrix built by many blocks, then min-label propagation in one block (labels in shared
+// memory, one warp per matrix row, rows prefetched) — dense clusters converge in two or three sweeps, and
+// every component ends up labelled by its first member.
 #include "internal.h"
+
+#define GROUP_SMEM_LABELS 8192
 
 __device__ __forceinline__ bool similar_rects(const int4 &a, const int4 &b, double eps)
 {
@@ -37,7 +41,7 @@ k_cand_sort(const PlanDev *__restrict__ plan, const int *__restrict__ counters, 
     }
 }
 
-// adjacency bit-matrix: word (i, w) holds the similarity of candidate i with candidates 32w .. 32w+31
+// similarity bit-matrix: word (i, w) holds the similarity of candidate i with candidates 32w .. 32w+31
 __global__ void __launch_bounds__(256)
 k_adj(const int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects, uint32_t *__restrict__ adj,
       double eps)
@@ -77,12 +81,13 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
         int result_cap)
 {
     __shared__ int s_warp[32];
-    __shared__ int s_changed;
     int tid = threadIdx.x;
     int n = min(counters[1], cand_cap), nw = (n + 31) >> 5;
     ResultHeader *hdr = reinterpret_cast<ResultHeader *>(result);
     int4 *out = reinterpret_cast<int4 *>(result + sizeof(ResultHeader));
-    volatile int *label = grp;
+    extern __shared__ int s_label[];                 // min(n, GROUP_SMEM_LABELS) labels; global scratch beyond that
+    __shared__ int s_changed;
+    volatile int *label = n <= GROUP_SMEM_LABELS ? s_label : grp;
     int *cls = grp + cand_cap, *acc = grp + 2 * cand_cap, *keep = grp + 7 * cand_cap;
     int nout = 0;
 
@@ -106,23 +111,45 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
     } else {
         for (int i = tid; i < n; i += 1024) label[i] = i;
         __syncthreads();
-        // min-label propagation over the similarity graph until a fixed point
+        // min-label propagation until a fixed point: one warp per candidate row, lanes over the row's adjacency
+        // words (the next row is fetched while the current one is reduced)
+        const int lane = tid & 31, warp = tid >> 5;
+        const int wpl = (nw + 31) >> 5;                  // words per lane (<= 8 for n <= 8192)
         for (;;) {
             if (tid == 0) s_changed = 0;
             __syncthreads();
-            for (int i = tid; i < n; i += 1024) {
-                int m = label[i];
-                const uint32_t *row = adj + (size_t)i * nw;
-                for (int w = 0; w < nw; w++) {
-                    uint32_t b = row[w];
-                    while (b) {
-                        int j = w * 32 + __ffs(b) - 1;
-                        b &= b - 1;
-                        m = min(m, label[j]);
+            uint32_t nxt[8];
+            if (wpl <= 8 && warp < n)
+#pragma unroll
+                for (int q = 0; q < 8; q++) { int w = lane + 32 * q; nxt[q] = (q < wpl && w < nw) ? adj[(size_t)warp * nw + w] : 0u; }
+            for (int i = warp; i < n; i += 32) {
+                int m = 0x7fffffff;
+                if (wpl <= 8) {
+                    uint32_t cur[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) cur[q] = nxt[q];
+                    if (i + 32 < n)
+#pragma unroll
+                        for (int q = 0; q < 8; q++) { int w = lane + 32 * q; nxt[q] = (q < wpl && w < nw) ? adj[(size_t)(i + 32) * nw + w] : 0u; }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        uint32_t b = cur[q];
+                        int w = lane + 32 * q;
+                        while (b) { int j = w * 32 + __ffs(b) - 1; b &= b - 1; m = min(m, label[j]); }
+                    }
+                } else {
+                    for (int w = lane; w < nw; w += 32) {
+                        uint32_t b = adj[(size_t)i * nw + w];
+                        while (b) { int j = w * 32 + __ffs(b) - 1; b &= b - 1; m = min(m, label[j]); }
                     }
                 }
-                m = min(m, label[m]);
-                if (m < label[i]) { label[i] = m; s_changed = 1; }
+                m = __reduce_min_sync(0xffffffffu, m);
+                if (lane == 0) {
+                    int c = label[i];
+                    m = min(m, c);
+                    m = min(m, label[m]);
+                    if (m < c) { label[i] = m; s_changed = 1; }
+                }
             }
             __syncthreads();
             int ch = s_changed;
@@ -153,29 +180,41 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
             for (int k = 0; k < 4; k++) acc[5 * c + k] = __float2int_rn(__fmul_rn(__int2float_rn(acc[5 * c + k]), s));
         }
         __syncthreads();
-        for (int i = tid; i < ncls; i += 1024) {
-            int n1 = acc[5 * i + 4];
-            bool k = n1 > min_neighbors;
-            if (k) {
-                int x1 = acc[5 * i], y1 = acc[5 * i + 1], w1 = acc[5 * i + 2], h1 = acc[5 * i + 3];
-                for (int j = 0; j < ncls; j++) {
-                    int n2 = acc[5 * j + 4];
-                    if (j == i || n2 <= min_neighbors) continue;
-                    int x2 = acc[5 * j], y2 = acc[5 * j + 1], w2 = acc[5 * j + 2], h2 = acc[5 * j + 3];
-                    int dx = __double2int_rn(__dmul_rn((double)w2, eps)), dy = __double2int_rn(__dmul_rn((double)h2, eps));
-                    if (x1 >= x2 - dx && y1 >= y2 - dy && x1 + w1 <= x2 + w2 + dx && y1 + h1 <= y2 + h2 + dy &&
-                        (n2 > max(3, n1) || n1 < 3)) { k = false; break; }
-                }
+        // classes with enough members, in class order (the containment test only ever looks at those)
+        int nk = 0;
+        for (int i0 = 0; i0 < ncls; i0 += 1024) {
+            int i = i0 + tid;
+            bool k = i < ncls && acc[5 * i + 4] > min_neighbors;
+            int pos = block_flag_rank(k, nk, s_warp);
+            if (k) keep[pos] = i;
+        }
+        __syncthreads();
+        // drop a class that lies inside a clearly stronger one (A.7)
+        int *alive = cls;                                   // cls[] is no longer needed: reuse as the survivor flags
+        __syncthreads();
+        for (int a = tid; a < nk; a += 1024) {
+            int i = keep[a];
+            int n1 = acc[5 * i + 4], x1 = acc[5 * i], y1 = acc[5 * i + 1], w1 = acc[5 * i + 2], h1 = acc[5 * i + 3];
+            bool k = true;
+            for (int b = 0; b < nk && k; b++) {
+                int j = keep[b];
+                if (j == i) continue;
+                int n2 = acc[5 * j + 4];
+                int x2 = acc[5 * j], y2 = acc[5 * j + 1], w2 = acc[5 * j + 2], h2 = acc[5 * j + 3];
+                int dx = __double2int_rn(__dmul_rn((double)w2, eps)), dy = __double2int_rn(__dmul_rn((double)h2, eps));
+                if (x1 >= x2 - dx && y1 >= y2 - dy && x1 + w1 <= x2 + w2 + dx && y1 + h1 <= y2 + h2 + dy &&
+                    (n2 > max(3, n1) || n1 < 3)) k = false;
             }
-            keep[i] = k;
+            alive[a] = k;
         }
         __syncthreads();
         carry = 0;
-        for (int i0 = 0; i0 < ncls; i0 += 1024) {
-            int i = i0 + tid;
+        for (int a0 = 0; a0 < nk; a0 += 1024) {
+            int a = a0 + tid;
             bool k = false;
             int4 r = make_int4(0, 0, 0, 0);
-            if (i < ncls && keep[i]) {
+            if (a < nk && alive[a]) {
+                int i = keep[a];
                 int x0 = max(acc[5 * i], 0), y0 = max(acc[5 * i + 1], 0);
                 int x1 = min(acc[5 * i] + acc[5 * i + 2], img_w), y1 = min(acc[5 * i + 1] + acc[5 * i + 3], img_h);
                 k = x1 > x0 && y1 > y0;
@@ -204,8 +243,8 @@ cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *can
         k_adj<<<nblocks, 256, 0, st>>>(counters, cand_cap, cand_rects, adj, eps);
         (*nlaunch)++;
     }
-    k_group<<<1, 1024, 0, st>>>(counters, cand_cap, cand_rects, adj, grp, min_neighbors, eps, img_w, img_h, result,
-                                result_cap);
+    k_group<<<1, 1024, GROUP_SMEM_LABELS * sizeof(int), st>>>(counters, cand_cap, cand_rects, adj, grp, min_neighbors, eps,
+                                                              img_w, img_h, result, result_cap);
     (*nlaunch)++;
     return cudaGetLastError();
 }
