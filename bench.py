@@ -331,10 +331,20 @@ def main():
         med = {k: statistics.median(v) for k, v in stage_acc.items()}
         iso = {k: statistics.median(v) for k, v in iso_acc.items()}
         iso_casc = iso.get("cascade_stage0", 0) + iso.get("cascade_tiles", 0) + iso.get("cascade_tail", 0)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")          # dram__bytes_read+write from the ncu --set full capture
+        traffic, onchip = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")          # counters from the committed ncu --set full capture
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("cascade_dram_bytes_per_frame")
+            tj = json.load(open(tpath))
+            traffic = tj.get("cascade_dram_bytes_per_frame")
+            wf = tj.get("tile_shared_wavefronts_per_frame")
+            if wf and iso.get("cascade_tiles", 0) > 0:
+                # what actually bounds the dominant kernel: shared-memory wavefronts (128 B each) of the tile kernels
+                smem_peak = 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+                ach = wf * 128 / (iso["cascade_tiles"] * 1e-3) / 1e12
+                onchip = {"bound": "shared-memory pipe (LSU wavefronts)", "achieved": ach, "peak": smem_peak, "unit": "TB/s",
+                          "frac": ach / smem_peak, "wavefronts_per_frame": wf,
+                          "conflict_replays_per_frame": tj.get("tile_shared_bank_conflict_wavefronts_per_frame"),
+                          "source": "wavefront counts from profiles/traffic.json (ncu), time = stage_ms_isolated.cascade_tiles"}
         casc_ms = med.get("cascade_stage0", 0) + med.get("cascade_tiles", 0) + med.get("cascade_tail", 0)
         frame_ms = sum(med.values())
         achieved = ab["cascade"] / (casc_ms * 1e-3) / 1e9 if casc_ms > 0 else None
@@ -366,6 +376,8 @@ def main():
             "stage_ms_median": med,
             "stage_ms_isolated": iso,
         }
+        if onchip:
+            line["roofline"]["onchip"] = onchip
         if aux:
             line["aux"] = aux
         if not args.no_cpu_baseline and world == 1:
