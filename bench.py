@@ -180,6 +180,106 @@ def algorithmic_bytes(levels, src_px, channels, proc_px, win=(20, 20)):
     return dict(frame_total=total, cascade=cascade, pyramid_px=P, integral_px=Pp)
 
 
+# ------------------------------------------------------------------------------------------------
+# auxiliary measurements: the other BASELINE configs, each beside the same op sequence through cv2
+# ------------------------------------------------------------------------------------------------
+def _timeit(fn, n, warm=2):
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    return n / (time.perf_counter() - t0)
+
+
+def _pin(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+
+def aux_other_configs(nv, local, world):
+    """cfg1 (element defaults, one 640x480 stream), cfg2 (nested eye detection on one 720p stream, stand-in eye
+    model: the mcs_* files are absent from this image) and cfg4 (tracker, 720p BGRA), frames/s of ONE stream
+    through the element mirrors (page-locked host frames in, metadata out, one frame in flight: this is
+    per-stream latency, not box throughput), next to cv2 on all host cores."""
+    import shutil
+    import tempfile
+    from nubovca import synth
+    out = {}
+    cdir = tempfile.mkdtemp(prefix="nubovca_casc_")
+    src = os.path.join(ROOT, "nubomedia-vca_b200", "cascades")
+    shutil.copy(os.path.join(src, "haarcascade_frontalface_alt.xml"), cdir)
+    for f in ("haarcascade_mcs_lefteye.xml", "haarcascade_mcs_righteye.xml"):
+        shutil.copy(os.path.join(src, "haarcascade_eye.xml"), os.path.join(cdir, f))
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count() or 1)
+    except Exception:
+        cv2 = None
+
+    # cfg1
+    f1 = _pin(synth.frame(640, 480, 4, 1))
+    e = nv.Element("nubofacedetector", local, cdir)
+    out["cfg1_face_640x480_defaults"] = {"frames_per_s": _timeit(lambda: e.process(f1), 300)}
+    e.close()
+    if cv2 is not None:
+        cc = cv2.CascadeClassifier(os.path.join(cdir, "haarcascade_frontalface_alt.xml"))
+
+        def cpu1():
+            g = cv2.equalizeHist(cv2.cvtColor(cv2.resize(f1, (160, 120), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY))
+            return cc.detectMultiScale(g, scaleFactor=1.25, minNeighbors=3, flags=0, minSize=(8, 6))
+        out["cfg1_face_640x480_defaults"]["cpu_frames_per_s"] = _timeit(cpu1, 200)
+
+    # cfg2: eye element, faces large enough for the 30x30 minimum at the 160-wide face stage
+    f2 = _pin(synth.frame(1280, 720, 3, 2, smin=0.4, smax=0.6))
+    e = nv.Element("nuboeyedetector", local, cdir)
+    out["cfg2_eyes_in_faces_1280x720"] = {"frames_per_s": _timeit(lambda: e.process(f2), 100),
+                                          "note": "haarcascade_eye.xml stands in for the absent mcs_lefteye/righteye models"}
+    e.close()
+    if cv2 is not None:
+        ce = cv2.CascadeClassifier(os.path.join(cdir, "haarcascade_mcs_lefteye.xml"))
+
+        def cpu2():
+            g = cv2.equalizeHist(cv2.cvtColor(f2, cv2.COLOR_BGR2GRAY))
+            faces = cc.detectMultiScale(cv2.resize(g, (160, 90), interpolation=cv2.INTER_LINEAR), scaleFactor=1.25,
+                                        minNeighbors=3, flags=0, minSize=(30, 30))
+            ef = cv2.equalizeHist(cv2.resize(g, (320, 180), interpolation=cv2.INTER_LINEAR))
+            n = 0
+            for (x, y, w, h) in faces:
+                x, y, w, h = int(x * 2), int(y * 2), int(w * 2), int(h * 2)
+                top, down = int(round(h * 0.25)), int(round(h * 0.40))
+                for roi in (ef[y + top:y + h - down, x:x + w // 2], ef[y + top:y + h - down, x + w // 2:x + w]):
+                    if roi.size:
+                        n += len(ce.detectMultiScale(roi, scaleFactor=1.1, minNeighbors=2, flags=0, minSize=(20, 20)))
+            return n
+        out["cfg2_eyes_in_faces_1280x720"]["cpu_frames_per_s"] = _timeit(cpu2, 60)
+
+    # cfg4: tracker
+    seq = [_pin(f) for f in synth.tracker_sequence(1280, 720, 8, seed=4)]
+    e = nv.Element("nubotracker", local, cdir)
+    st = {"i": 0}
+
+    def trk():
+        st["i"] += 1
+        return e.process(seq[st["i"] % len(seq)], now_ms=33.3 * st["i"])
+    out["cfg4_tracker_1280x720_bgra"] = {"frames_per_s": _timeit(trk, 300)}
+    e.close()
+    if cv2 is not None:
+        prev = {"g": cv2.cvtColor(seq[0], cv2.COLOR_BGRA2GRAY), "i": 0}
+
+        def cpu4():
+            prev["i"] += 1
+            g = cv2.cvtColor(seq[prev["i"] % len(seq)], cv2.COLOR_BGRA2GRAY)
+            m = cv2.threshold(cv2.absdiff(g, prev["g"]), 20, 255, cv2.THRESH_BINARY)[1]
+            r = cv2.connectedComponentsWithStats(m, connectivity=4)
+            prev["g"] = g
+            return r
+        out["cfg4_tracker_1280x720_bgra"]["cpu_frames_per_s"] = _timeit(cpu4, 200)
+        out["cpu"] = {"cores": cv2.getNumThreads(), "via": "cv2 %s, the reference's call sequences" % cv2.__version__}
+    shutil.rmtree(cdir, ignore_errors=True)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -315,6 +415,8 @@ def main():
                "timing": "host wall clock, H2D + D2H included"}
         for c in c5:
             c.close()
+        if rank == 0 and world == 1:
+            aux["other_configs_one_stream"] = aux_other_configs(nv, local, world)
 
     total_frames = B * args.steps
     value, ms_dev = shard.aggregate_throughput(total_frames, ms_dev, dist, "cuda")

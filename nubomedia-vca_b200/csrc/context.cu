@@ -610,6 +610,17 @@ int nv_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n)
     return NV_OK;
 }
 
+// host -> device copy of an input image on the ctx's stream: page-locked caller memory is read directly by the
+// DMA engine, pageable memory goes through the ctx's pinned staging buffer
+int nv_h2d(nv_ctx *ctx, const uint8_t *src, size_t bytes)
+{
+    cudaPointerAttributes at;
+    bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    if (!pinned) { cudaGetLastError(); memcpy(ctx->h_frame, src, bytes); }
+    NV_CUDA(cudaMemcpyAsync(ctx->d_frame, pinned ? src : ctx->h_frame, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return NV_OK;
+}
+
 static int check_frame(nv_ctx *ctx, const void *img, int w, int h, int stride, int cn)
 {
     if (!ctx || !img) { nv_set_error("null argument"); return NV_ERR_ARG; }
@@ -629,8 +640,7 @@ extern "C" int nv_detect_multiscale(nv_ctx *ctx, const nv_cascade *c, const uint
     if (!c || !p) { nv_set_error("null argument"); return NV_ERR_ARG; }
     NV_CUDA(cudaSetDevice(ctx->gpu));
     if (ctx->pending) NV_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(ctx->h_frame, gray, (size_t)stride_bytes * height);
-    NV_CUDA(cudaMemcpyAsync(ctx->d_frame, ctx->h_frame, (size_t)stride_bytes * height, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = nv_h2d(ctx, gray, (size_t)stride_bytes * height)) != NV_OK) return rc;
     rc = nv_detect_device(ctx, const_cast<nv_cascade *>(c), ctx->d_frame, width, height, stride_bytes, ctx->d_lut + 256, p);
     if (rc != NV_OK) return rc;
     return nv_collect(ctx, out, cap, n);
@@ -693,11 +703,7 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
     const uint8_t *d_src = bgr;
     if (!on_device) {
         // page-locked caller memory is copied straight from the caller; anything else goes through the pinned staging buffer
-        cudaPointerAttributes at;
-        bool pinned = cudaPointerGetAttributes(&at, bgr) == cudaSuccess && at.type == cudaMemoryTypeHost;
-        if (!pinned) { cudaGetLastError(); memcpy(ctx->h_frame, bgr, (size_t)stride * height); }
-        NV_CUDA(cudaMemcpyAsync(ctx->d_frame, pinned ? bgr : ctx->h_frame, (size_t)stride * height, cudaMemcpyHostToDevice,
-                                ctx->stream));
+        if ((rc = nv_h2d(ctx, bgr, (size_t)stride * height)) != NV_OK) return rc;
         d_src = ctx->d_frame;
     }
     auto enqueue = [&](int *nl) -> int {
@@ -781,9 +787,7 @@ static int upload(nv_ctx *ctx, const uint8_t *src, size_t bytes)
     if (bytes > ctx->frame_cap) { nv_set_error("image larger than the context"); return NV_ERR_CAPACITY; }
     NV_CUDA(cudaSetDevice(ctx->gpu));
     if (ctx->pending) { NV_CUDA(cudaStreamSynchronize(ctx->stream)); }
-    memcpy(ctx->h_frame, src, bytes);
-    NV_CUDA(cudaMemcpyAsync(ctx->d_frame, ctx->h_frame, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    return NV_OK;
+    return nv_h2d(ctx, src, bytes);
 }
 
 static int download(nv_ctx *ctx, const uint8_t *d_src, int row_bytes, int rows, uint8_t *dst, int dstride)
@@ -927,8 +931,7 @@ extern "C" int nv_tracker_process(nv_ctx *ctx, const uint8_t *bgra, int width, i
         NV_CUDA(cudaMallocHost(&ctx->h_trk, (TRK_MAX_COMPONENTS + 1) * sizeof(int4)));
         ctx->trk_w = width; ctx->trk_h = height; ctx->trk_frames = 0;
     }
-    memcpy(ctx->h_frame, bgra, (size_t)stride_bytes * height);
-    NV_CUDA(cudaMemcpyAsync(ctx->d_frame, ctx->h_frame, (size_t)stride_bytes * height, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = nv_h2d(ctx, bgra, (size_t)stride_bytes * height)) != NV_OK) return rc;
     int first = ctx->trk_frames == 0, nl = 0;
     float ts = (float)timestamp_ms, del = (float)(timestamp_ms - 0.2);          // MHI_DURATION, :28
     NV_CUDA(launch_tracker(ctx, ctx->d_frame, width, height, stride_bytes, first, ts, del, p->threshold, &nl));

@@ -141,9 +141,7 @@ int upload_frame(nv_ctx *ctx, const uint8_t *frame, int stride, int h)
 {
     if ((size_t)stride * h > ctx->frame_cap) { nv_set_error("frame larger than the element's context"); return NV_ERR_CAPACITY; }
     if (ctx->pending) NV_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(ctx->h_frame, frame, (size_t)stride * h);
-    NV_CUDA(cudaMemcpyAsync(ctx->d_frame, ctx->h_frame, (size_t)stride * h, cudaMemcpyHostToDevice, ctx->stream));
-    return NV_OK;
+    return nv_h2d(ctx, frame, (size_t)stride * h);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -293,6 +293,7 @@ void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_
 int nv_detect_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W, int H, int gstride, const uint8_t *d_lut,
                      const nv_detect_params *p);
 int nv_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n);
+int nv_h2d(nv_ctx *ctx, const uint8_t *src, size_t bytes);
 int nv_get_rtab(nv_ctx *ctx, int sw, int sh, int dw, int dh, const int **d_tab);
 
 // kernels_group.cu
