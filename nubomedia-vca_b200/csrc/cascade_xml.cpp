@@ -112,6 +112,29 @@ bool parse_floats(const std::string &s, std::vector<double> &out)
     }
 }
 
+static int finish_cascade(HostCascade *hc)
+{
+    // Exactness certificate for parallel stage sums: OpenCV adds the float leaves one by one into a
+    // double.  If, for every stage, (sum of |leaf|) / (smallest unit-in-last-place of any leaf) fits in
+    // 2^52, no addition can round, so any summation order gives the same double.
+    hc->order_free = 1;
+    size_t si = 0;
+    for (int nt : hc->stage_ntrees) {
+        double mag = 0, min_ulp = INFINITY;
+        for (int i = 0; i < nt; i++, si++)
+            for (float leaf : {hc->stump_left[si], hc->stump_right[si]}) {
+                if (leaf == 0.f) continue;
+                if (!isfinite(leaf)) { hc->order_free = 0; continue; }
+                int e;
+                frexp((double)leaf, &e);                 // |leaf| in [2^(e-1), 2^e)
+                mag += fabs((double)leaf);
+                min_ulp = fmin(min_ulp, ldexp(1.0, e - 24));
+            }
+        if (mag > 0 && mag / min_ulp >= 4503599627370496.0) hc->order_free = 0;
+    }
+    return NV_OK;
+}
+
 }  // namespace
 
 int nv_parse_cascade_xml(const char *path, HostCascade *hc)
@@ -131,11 +154,74 @@ int nv_parse_cascade_xml(const char *path, HostCascade *hc)
         return NV_ERR_FORMAT;
     }
     const Node *c = root->child("cascade");
-    if (!c || !c->child("stages") || !c->child("features")) {
-        nv_set_error("%s: old-format or incomplete cascade (no <cascade>/<stages>/<features>)", path);
+    std::vector<double> v;
+    if (!c) {
+        // OpenCV 1.x/2.x "opencv-haar-classifier" layout — what /usr/share/opencv/haarcascades held on the OpenCV 2.4
+        // systems the reference was deployed on.  OpenCV >= 3 converts it to the new layout on load and evaluates
+        // it identically (checked against cv2 4.13 in tests/test_oracle_vs_cv2.py), so it maps onto the same model:
+        // one feature per tree node, <left_val>/<right_val> leaves.
+        const Node *o = nullptr;
+        for (auto &k : root->kids)
+            if (k->child("stages") && k->child("size")) { o = k.get(); break; }
+        if (!o) { nv_set_error("%s: neither a new-format <cascade> nor an old-format haar classifier", path); return NV_ERR_FORMAT; }
+        if (!parse_floats(o->child_text("size"), v) || v.size() != 2) { nv_set_error("%s: malformed <size>", path); return NV_ERR_FORMAT; }
+        hc->win_w = (int)v[0]; hc->win_h = (int)v[1];
+        if (hc->win_w < 3 || hc->win_h < 3 || hc->win_w > 255 || hc->win_h > 255) { nv_set_error("%s: window out of range", path); return NV_ERR_FORMAT; }
+        for (auto &st : o->child("stages")->kids) {
+            const Node *trees = st->child("trees");
+            if (!trees || !parse_floats(st->child_text("stage_threshold"), v) || v.size() != 1) { nv_set_error("%s: malformed stage", path); return NV_ERR_FORMAT; }
+            hc->stage_thr.push_back((float)v[0]);
+            int nt = 0;
+            for (auto &tree : trees->kids) {
+                if (tree->kids.size() != 1) { nv_set_error("%s: tree weak classifiers (depth > 1) are not supported yet", path); return NV_ERR_UNSUPPORTED; }
+                const Node *node = tree->kids[0].get();
+                const Node *ft = node->child("feature");
+                if (!ft || !ft->child("rects") || !node->child("left_val") || !node->child("right_val")) {
+                    nv_set_error("%s: malformed or non-stump tree node", path);
+                    return node->child("left_node") || node->child("right_node") ? NV_ERR_UNSUPPORTED : NV_ERR_FORMAT;
+                }
+                if (atoi(ft->child_text("tilted").c_str()) != 0) { nv_set_error("%s: tilted features are not supported yet", path); return NV_ERR_UNSUPPORTED; }
+                int r[12] = {0};
+                float w[3] = {0, 0, 0};
+                int k = 0;
+                for (auto &rc : ft->child("rects")->kids) {
+                    if (k >= 3 || !parse_floats(rc->text, v) || v.size() != 5) { nv_set_error("%s: malformed feature rectangle", path); return NV_ERR_FORMAT; }
+                    for (int i = 0; i < 4; i++) r[4 * k + i] = (int)v[i];
+                    w[k] = (float)v[4];
+                    if (r[4 * k] < 0 || r[4 * k + 1] < 0 || r[4 * k + 2] <= 0 || r[4 * k + 3] <= 0 ||
+                        r[4 * k] + r[4 * k + 2] > hc->win_w || r[4 * k + 1] + r[4 * k + 3] > hc->win_h) {
+                        nv_set_error("%s: feature rectangle outside the window", path);
+                        return NV_ERR_FORMAT;
+                    }
+                    k++;
+                }
+                if (k < 2) { nv_set_error("%s: feature with fewer than two rects", path); return NV_ERR_FORMAT; }
+                std::vector<double> t, l, rr;
+                if (!parse_floats(node->child_text("threshold"), t) || t.size() != 1 || !parse_floats(node->child_text("left_val"), l) ||
+                    l.size() != 1 || !parse_floats(node->child_text("right_val"), rr) || rr.size() != 1) {
+                    nv_set_error("%s: malformed tree node", path);
+                    return NV_ERR_FORMAT;
+                }
+                if (w[2] != 0.f) hc->n3rect++;
+                hc->stump_feat.push_back((int)hc->feat_weight.size() / 3);
+                hc->feat_rect.insert(hc->feat_rect.end(), r, r + 12);
+                hc->feat_weight.insert(hc->feat_weight.end(), w, w + 3);
+                hc->stump_thr.push_back((float)t[0]); hc->stump_left.push_back((float)l[0]); hc->stump_right.push_back((float)rr[0]);
+                nt++;
+            }
+            if (nt == 0) { nv_set_error("%s: empty stage", path); return NV_ERR_FORMAT; }
+            hc->stage_ntrees.push_back(nt);
+        }
+        if (hc->stage_ntrees.empty() || hc->stage_ntrees.size() > NV_MAX_STAGES) {
+            nv_set_error("%s: %zu stages (supported: 1..%d)", path, hc->stage_ntrees.size(), NV_MAX_STAGES);
+            return hc->stage_ntrees.empty() ? NV_ERR_FORMAT : NV_ERR_UNSUPPORTED;
+        }
+        return finish_cascade(hc);
+    }
+    if (!c->child("stages") || !c->child("features")) {
+        nv_set_error("%s: incomplete cascade (no <stages>/<features>)", path);
         return NV_ERR_FORMAT;
     }
-    std::vector<double> v;
     auto trimmed = [](std::string s) {
         size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
         return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
@@ -214,23 +300,5 @@ int nv_parse_cascade_xml(const char *path, HostCascade *hc)
     for (int fi : hc->stump_feat)
         if (fi < 0 || fi >= nfeat) { nv_set_error("%s: feature index out of range", path); return NV_ERR_FORMAT; }
 
-    // Exactness certificate for parallel stage sums: OpenCV adds the float leaves one by one into a
-    // double.  If, for every stage, (sum of |leaf|) / (smallest unit-in-last-place of any leaf) fits in
-    // 2^52, no addition can round, so any summation order gives the same double.
-    hc->order_free = 1;
-    size_t si = 0;
-    for (int nt : hc->stage_ntrees) {
-        double mag = 0, min_ulp = INFINITY;
-        for (int i = 0; i < nt; i++, si++)
-            for (float leaf : {hc->stump_left[si], hc->stump_right[si]}) {
-                if (leaf == 0.f) continue;
-                if (!isfinite(leaf)) { hc->order_free = 0; continue; }
-                int e;
-                frexp((double)leaf, &e);                 // |leaf| in [2^(e-1), 2^e)
-                mag += fabs((double)leaf);
-                min_ulp = fmin(min_ulp, ldexp(1.0, e - 24));
-            }
-        if (mag > 0 && mag / min_ulp >= 4503599627370496.0) hc->order_free = 0;
-    }
-    return NV_OK;
+    return finish_cascade(hc);
 }

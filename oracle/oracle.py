@@ -101,8 +101,10 @@ def parse_cascade_xml(path: str) -> dict:
     """Parse a new-format stump cascade.  Raises NotImplementedError for trees/tilted/LBP."""
     root = ET.parse(path).getroot()
     casc = root.find("cascade")
-    if casc is None or casc.findtext("featureType", "").strip() != "HAAR":
-        raise NotImplementedError("only HAAR new-format cascades")
+    if casc is None:
+        return _parse_old_format(root)
+    if casc.findtext("featureType", "").strip() != "HAAR":
+        raise NotImplementedError("only HAAR cascades")
     win_w, win_h = int(casc.findtext("width")), int(casc.findtext("height"))
     stage_ntrees, stage_thr, feat, thr, left, right = [], [], [], [], [], []
     for st in casc.find("stages"):
@@ -135,6 +137,38 @@ def parse_cascade_xml(path: str) -> dict:
         stump_right=np.array(right, np.float64).astype(np.float32),
         feat_rect=np.ascontiguousarray(np.stack(rects)), feat_weight=np.ascontiguousarray(np.stack(weights)),
     )
+
+
+def _parse_old_format(root) -> dict:
+    """OpenCV 1.x/2.x "opencv-haar-classifier" layout (what OpenCV 2.4 shipped; cv2 4.13 converts it on load)."""
+    old = next((k for k in root if k.find("stages") is not None and k.find("size") is not None), None)
+    if old is None:
+        raise NotImplementedError("not a haar cascade")
+    win_w, win_h = (int(t) for t in old.findtext("size").split())
+    stage_ntrees, stage_thr, thr, left, right, rects, weights = [], [], [], [], [], [], []
+    for st in old.find("stages"):
+        stage_thr.append(float(st.findtext("stage_threshold")))
+        n = 0
+        for tree in st.find("trees"):
+            nodes = list(tree)
+            if len(nodes) != 1 or nodes[0].find("left_val") is None or nodes[0].find("right_val") is None:
+                raise NotImplementedError("tree weak classifiers (depth>1)")
+            node = nodes[0]; ft = node.find("feature")
+            if int((ft.findtext("tilted") or "0").strip()) != 0:
+                raise NotImplementedError("tilted features")
+            r = np.zeros((3, 4), np.int32); w = np.zeros(3, np.float32)
+            for k, rc in enumerate(ft.find("rects")):
+                t = rc.text.split()
+                r[k] = [int(t[0]), int(t[1]), int(t[2]), int(t[3])]; w[k] = np.float32(float(t[4]))
+            rects.append(r); weights.append(w)
+            thr.append(float(node.findtext("threshold"))); left.append(float(node.findtext("left_val")))
+            right.append(float(node.findtext("right_val")))
+            n += 1
+        stage_ntrees.append(n)
+    f32 = lambda a: np.array(a, np.float64).astype(np.float32)      # noqa: E731
+    return dict(win_w=win_w, win_h=win_h, stage_ntrees=np.array(stage_ntrees, np.int32), stage_thr=f32(stage_thr),
+                stump_feat=np.arange(len(thr), dtype=np.int32), stump_thr=f32(thr), stump_left=f32(left), stump_right=f32(right),
+                feat_rect=np.ascontiguousarray(np.stack(rects)), feat_weight=np.ascontiguousarray(np.stack(weights)))
 
 
 class Cascade:

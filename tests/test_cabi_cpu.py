@@ -10,7 +10,7 @@ import pytest
 
 import nubovca as nv
 import oracle as O
-from cascade_xml_util import random_cascade, write_cascade
+from cascade_xml_util import random_cascade, write_cascade, write_old_format
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -75,6 +75,34 @@ def test_random_cascade_roundtrip(tmp_path):
         assert (r == d["feat_rect"][d["stump_feat"][i]]).all() and (w == d["feat_weight"][d["stump_feat"][i]]).all()
 
 
+def test_old_format_cascade(tmp_path, cascade_dir):
+    """The OpenCV 2.4 systems the reference ran on ship opencv-haar-classifier XML; it must load to the same model."""
+    src = os.path.join(cascade_dir, "haarcascade_frontalface_alt.xml")
+    d = O.parse_cascade_xml(src)
+    p = str(tmp_path / "old.xml")
+    write_old_format(p, d)
+    new, old, od = nv.Cascade(src), nv.Cascade(p), O.parse_cascade_xml(p)
+    assert (old.info.win_w, old.info.nstages, old.info.nstumps, old.info.n3rect) == (20, 22, 2135, 360)
+    for s_ in range(22):
+        assert new.stage(s_) == old.stage(s_)
+    for i in range(0, 2135, 7):
+        a, b = new.stump(i), old.stump(i)
+        assert all((x == y).all() for x, y in zip(a, b))
+        assert (od["feat_rect"][od["stump_feat"][i]] == a[0]).all() and od["stump_thr"][i] == a[2][0]
+
+
+def test_shipped_old_format_file():
+    # cv2 ships one genuine OpenCV-1.x-layout file: 64x16 window, 16 stages, 91 stumps
+    import cv2
+    p = os.path.join(cv2.data.haarcascades, "haarcascade_license_plate_rus_16stages.xml")
+    c = nv.Cascade(p); d = O.parse_cascade_xml(p)
+    assert (c.info.win_w, c.info.win_h, c.info.nstages, c.info.nstumps) == (64, 16, 16, 91)
+    assert [c.stage(s_)[0] for s_ in range(16)] == d["stage_ntrees"].tolist()
+    for i in range(91):
+        r, w, t = c.stump(i)
+        assert (r == d["feat_rect"][i]).all() and (w == d["feat_weight"][i]).all() and t[0] == d["stump_thr"][i]
+
+
 def test_cascade_error_paths(tmp_path):
     with pytest.raises(nv.NuboError) as e:
         nv.Cascade(str(tmp_path / "missing.xml"))
@@ -89,8 +117,7 @@ def test_cascade_error_paths(tmp_path):
         nv.Cascade(str(bad))
     assert e.value.code == -4
     import cv2  # tilted / tree cascades ship with cv2: loader must refuse them, not mis-evaluate them
-    for name, code in [("haarcascade_smile.xml", -5), ("haarcascade_lefteye_2splits.xml", -5),
-                       ("haarcascade_license_plate_rus_16stages.xml", -4)]:
+    for name, code in [("haarcascade_smile.xml", -5), ("haarcascade_lefteye_2splits.xml", -5)]:
         with pytest.raises(nv.NuboError) as e:
             nv.Cascade(os.path.join(cv2.data.haarcascades, name))
         assert e.value.code in (code, -4, -5)

@@ -133,6 +133,28 @@ def test_random_cascades_and_ragged_sizes(ctx, tmp_path, seed):
     check_levels(ctx, g, ocasc, sf, (0, 0))
 
 
+def test_old_format_and_wide_window_cascade(ctx, tmp_path, cascade_dir):
+    """(1) frontalface_alt rewritten in the OpenCV-2.x layout detects exactly like the new layout;
+    (2) cv2's genuine old-layout 64x16 plate cascade: wider than the tile kernel's 32x32 limit, so this also
+    covers the generic queue path (k_alive_to_queue + k_queue_stages)."""
+    from cascade_xml_util import write_old_format
+    src = os.path.join(cascade_dir, FACE_XML)
+    p = str(tmp_path / "old.xml")
+    write_old_format(p, O.parse_cascade_xml(src))
+    g = O.equalize_hist(O.bgr2gray(synth.frame(480, 360, 10, 5)))
+    a = ctx.detect_multiscale(nv.Cascade(p), g, 1.25, 3)
+    assert len(a) >= 3 and rects_equal(a, ctx.detect_multiscale(nv.Cascade(src), g, 1.25, 3))
+    assert rects_equal(a, O.detect_multiscale(g, O.Cascade(p), 1.25, 3))
+    cv2 = pytest.importorskip("cv2")
+    plate = os.path.join(cv2.data.haarcascades, "haarcascade_license_plate_rus_16stages.xml")
+    rng = np.random.default_rng(21)
+    g2 = O.equalize_hist(cv2.GaussianBlur(rng.integers(0, 256, (240, 400), dtype=np.uint8), (0, 0), 1.2))
+    ncasc, ocasc = nv.Cascade(plate), O.Cascade(plate)
+    for mn in (0, 2):
+        assert rects_equal(ctx.detect_multiscale(ncasc, g2, 1.1, mn), O.detect_multiscale(g2, ocasc, 1.1, mn))
+    check_levels(ctx, g2, ocasc, 1.1, (0, 0))
+
+
 def test_edge_cases(ctx, face):
     ncasc, ocasc = face
     rng = np.random.default_rng(1)

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import oracle as O
-from cascade_xml_util import random_cascade, write_cascade
+from cascade_xml_util import random_cascade, write_cascade, write_old_format
 from nubovca import synth
 
 try:
@@ -254,6 +254,37 @@ def test_real_cascades_live(name, cascade_dir):
         for mn in (0, 3):
             a = cc.detectMultiScale(g, scaleFactor=sf, minNeighbors=mn, minSize=ms)
             assert rects_equal(a, O.detect_multiscale(g, oc, sf, mn, ms)), (name, W, H, mn)
+
+
+@needs_cv2
+def test_old_format_cascade_live(tmp_path, cascade_dir):
+    """cv2 4.13 converts OpenCV-2.x "opencv-haar-classifier" files on load and evaluates them exactly like the
+    new layout, whatever the flags: the old-format parser must therefore give the same detections."""
+    src = os.path.join(cascade_dir, "haarcascade_frontalface_alt.xml")
+    p = str(tmp_path / "old.xml")
+    write_old_format(p, O.parse_cascade_xml(src))
+    g = cv2.equalizeHist(cv2.cvtColor(synth.frame(480, 360, 10, 5), cv2.COLOR_BGR2GRAY))
+    cc = cv2.CascadeClassifier(p)
+    assert not cc.empty()
+    exp = O.detect_multiscale(g, O.Cascade(p), 1.25, 0)
+    assert len(exp) > 10 and rects_equal(exp, O.detect_multiscale(g, O.Cascade(src), 1.25, 0))
+    for flags in (0, cv2.CASCADE_SCALE_IMAGE, cv2.CASCADE_FIND_BIGGEST_OBJECT):
+        assert rects_equal(cc.detectMultiScale(g, scaleFactor=1.25, minNeighbors=0, flags=flags), exp)
+
+
+@needs_cv2
+def test_shipped_old_format_file_live():
+    """haarcascade_license_plate_rus_16stages.xml is a genuine old-layout file with a 64x16 window."""
+    p = os.path.join(cv2.data.haarcascades, "haarcascade_license_plate_rus_16stages.xml")
+    cc = cv2.CascadeClassifier(p); oc = O.Cascade(p)
+    rng = np.random.default_rng(21)
+    g = cv2.equalizeHist(cv2.GaussianBlur(rng.integers(0, 256, (240, 400), dtype=np.uint8), (0, 0), 1.2))
+    n = 0
+    for mn in (0, 2):
+        a = cc.detectMultiScale(g, scaleFactor=1.1, minNeighbors=mn)
+        assert rects_equal(a, O.detect_multiscale(g, oc, 1.1, mn))
+        n += len(a)
+    assert n > 0
 
 
 @needs_cv2
