@@ -202,7 +202,7 @@ extern "C" void nv_ctx_destroy(nv_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_frame); cudaFree(c->d_frame); cudaFree(c->d_gray); cudaFree(c->d_hist); cudaFree(c->d_lut);
     cudaFree(c->d_aux); for (auto &e : c->rtabs) cudaFree(e.d); cudaFree(c->d_plan); cudaFree(c->d_ptab); cudaFree(c->d_sum);
-    cudaFree(c->d_sq); cudaFree(c->d_pyr); cudaFree(c->d_vnf); cudaFree(c->d_depth); cudaFree(c->d_bits_fail);
+    cudaFree(c->d_sq); cudaFree(c->d_pyr); cudaFree(c->d_vnf); cudaFree(c->d_depth);
     cudaFree(c->d_bits_ok); cudaFree(c->d_queue); cudaFree(c->d_counters); cudaFree(c->d_cand);
     cudaFree(c->d_cand_sorted); cudaFree(c->d_cand_rects); cudaFree(c->d_adj); cudaFree(c->d_result);
     cudaFreeHost(c->h_result);
@@ -385,8 +385,6 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         if ((rc = ensure(&ctx->d_vnf, &wcap, (size_t)wofs)) != NV_OK) return rc;
         if ((rc = ensure(&ctx->d_queue, &ctx->queue_cap, (size_t)wofs)) != NV_OK) return rc;
         ctx->win_cap = wcap;
-        size_t bcap = ctx->bits_cap;
-        if ((rc = ensure(&ctx->d_bits_fail, &bcap, (size_t)bofs)) != NV_OK) return rc;
         if ((rc = ensure(&ctx->d_bits_ok, &ctx->bits_cap, (size_t)bofs)) != NV_OK) return rc;
         if (ctx->debug) {
             if ((rc = ensure(&ctx->d_depth, &ctx->depth_cap, (size_t)wofs)) != NV_OK) return rc;

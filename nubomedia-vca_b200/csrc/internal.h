@@ -85,7 +85,7 @@ struct LevelDesc {
     int pofs;              // byte offset of the u8 level image (debug)
     int rowblk0;           // first row-block (8 rows) of this level in k_pyr_rowscan's grid
     int colblk0;           // first column-block (32 physical cols) in k_colscan's grid (per array)
-    int chunk0;            // first 32-window chunk in k_stage0's grid
+    int chunk0;            // first 32-window chunk (row-major over levels)
     int row0;              // first window row in k_stage0_rows' grid
     int tile0;             // first 32x32-window tile of this level within its ystep class (k_cascade_tiles)
     int nty;               // tile rows = ceil(ny/32); tile columns = nxw
@@ -200,7 +200,7 @@ struct nv_ctx {
     uint8_t *d_pyr = nullptr;    size_t pyr_cap = 0;        // debug level images
     float *d_vnf = nullptr;      size_t win_cap = 0;
     int16_t *d_depth = nullptr;  size_t depth_cap = 0;      // debug only
-    uint32_t *d_bits_fail = nullptr, *d_bits_ok = nullptr;  size_t bits_cap = 0;   // [bits_ok doubles as bits_alive]
+    uint32_t *d_bits_ok = nullptr;  size_t bits_cap = 0;         // one "alive after stage 0" bit per window
     TileParams tp[2];  Stage0Params s0p;  bool use_s0p = false;  CUtensorMap *d_maps = nullptr;  bool use_tiles = false;  int bulk_end = 0;  const nv_cascade *tp_casc = nullptr;
     uint2 *d_queue = nullptr;    size_t queue_cap = 0;
     int *d_counters = nullptr;                              // [0] queue count, [1] cand count, [2] overflow
@@ -266,12 +266,6 @@ cudaError_t launch_pyr_rowscan(const PlanDev *plan, int total_rowblk, const uint
 cudaError_t launch_colscan(const PlanDev *plan, int total_colblk, uint32_t *sum, uint32_t *sq, cudaStream_t st);
 
 // kernels_cascade.cu
-cudaError_t launch_stage0(const PlanDev *plan, int total_chunks, const DevCascade *meta, const DevStump *stumps,
-                          const uint32_t *sum, const uint32_t *sq, float *vnf, uint32_t *bits_fail, uint32_t *bits_ok,
-                          cudaStream_t st);
-cudaError_t launch_skip_compact(const PlanDev *plan, int total_rows, const float *vnf, const uint32_t *bits_fail,
-                                const uint32_t *bits_ok, uint2 *queue, int *counters, int queue_cap, int16_t *depth,
-                                cudaStream_t st);
 cudaError_t launch_queue_stages(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,
                                 const uint2 *queue, int *counters, uint32_t *cand, int cand_cap, int16_t *depth,
                                 int nblocks, cudaStream_t st);
