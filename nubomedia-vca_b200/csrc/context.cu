@@ -360,9 +360,10 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         L.colblk0 = P.total_colblk; P.total_colblk += (L.ipitch + 31) / 32;
         L.chunk0 = P.total_chunks; P.total_chunks += L.nxw * L.ny;
         L.row0 = P.total_rows; P.total_rows += L.ny;
-        L.nty = (L.ny + NV_TILE - 1) / NV_TILE;
-        if (ystep == 2) { L.tile0 = P.tiles2; P.tiles2 += L.nty * L.nxw; P.nlv2 = nl; }
-        else { L.tile0 = P.tiles1; P.tiles1 += L.nty * L.nxw; }
+        L.cntx = (L.nx + NV_CTX - 1) / NV_CTX;
+        int cnt = L.cntx * ((L.ny + NV_CTY - 1) / NV_CTY);
+        if (ystep == 2) { L.ctile0 = P.ctiles2; P.ctiles2 += cnt; P.nlv2 = nl; }
+        else { L.ctile0 = P.ctiles1; P.ctiles1 += cnt; }
         if (iofs > 0x7fffffffLL || wofs > 0x7fffffffLL) { nv_set_error("frame too large"); return NV_ERR_CAPACITY; }
     }
     P.nlevels = nl;
@@ -440,8 +441,12 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
         TileParams &tp = ctx->tp[c];
         // columns per plane; ys*cp is a multiple of 32 words so that windows of different rows with different
         // lx never share a bank (a raster-ordered batch of 32 alive windows is then conflict-free)
-        tp.cp = align_up(NV_TILE + (ys == 2 ? m.win_w / 2 : m.win_w) + 1, 32 / ys);
-        tp.rt = (NV_TILE - 1) * ys + m.win_h + 1;
+        // the pitch is 4 (mod 8) words, so that the bank class (lx + kskew * ly) & 31 of a window moves by a
+        // multiple of 4 that is not a multiple of 32 from one window row to the next
+        tp.cp = align_up(NV_CTX + (ys == 2 ? m.win_w / 2 : m.win_w) + 1, 4);
+        if (tp.cp % 8 == 0) tp.cp += 4;
+        tp.rt = (NV_CTY - 1) * ys + m.win_h + 1;
+        tp.kskew = (ys * tp.cp) & 31;
         tp.ps = align_up(tp.rt * tp.cp, 32);
         tp.level_begin = c == 0 ? 0 : P.nlv2;
         tp.level_end = c == 0 ? P.nlv2 : P.nlevels;
@@ -514,12 +519,12 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         if (ctx->use_tiles) {
             for (int c = 0; c < 2; c++) {
                 TileParams &tp = ctx->tp[c];
-                int ntiles = c == 0 ? P.tiles2 : P.tiles1;
+                int ntiles = c == 0 ? P.ctiles2 : P.ctiles1;
                 if (ntiles == 0) continue;
                 tp.plan = ctx->d_plan; tp.bits_alive = ctx->d_bits_ok; tp.vnf = ctx->d_vnf; tp.depth = depth;
                 tp.tail = ctx->d_queue; tp.cand = ctx->d_cand; tp.counters = ctx->d_counters; tp.maps = ctx->d_maps;
                 tp.tail_cap = qcap; tp.cand_cap = ctx->cand_cap;
-                NV_CUDA(launch_cascade_tiles(tp, c == 0 ? 2 : 1, ntiles, st));
+                NV_CUDA(launch_cascade_classes(tp, c == 0 ? 2 : 1, ntiles, st));
                 nl++;
             }
             prof_mark(ctx, 6);

@@ -87,8 +87,7 @@ struct LevelDesc {
     int colblk0;           // first column-block (32 physical cols) in k_colscan's grid (per array)
     int chunk0;            // first 32-window chunk (row-major over levels)
     int row0;              // first window row in k_stage0_rows' grid
-    int tile0;             // first 32x32-window tile of this level within its ystep class (k_cascade_tiles)
-    int nty;               // tile rows = ceil(ny/32); tile columns = nxw
+    int ctile0, cntx;      // k_cascade_classes: first 64x32-window tile within the ystep class, tile columns = ceil(nx/64)
 };
 
 struct PlanDev {
@@ -97,7 +96,7 @@ struct PlanDev {
     int win_w, win_h;
     int total_rowblk, total_colblk, total_chunks, total_rows, total_windows;
     int nlv2;              // levels [0, nlv2) have ystep 2, [nlv2, nlevels) ystep 1 (scales ascend)
-    int tiles2, tiles1;    // tile counts of the two classes
+    int ctiles2, ctiles1;  // 64x32-window tile counts of the two ystep classes
     LevelDesc lv[NV_MAX_LEVELS];
 };
 
@@ -116,22 +115,35 @@ struct ResizeKey {
     bool operator==(const ResizeKey &o) const { return sw == o.sw && sh == o.sh && dw == o.dw && dh == o.dh; }
 };
 
-// ---- k_cascade_tiles parameters (passed by value as a __grid_constant__: tensor maps and the bulk
+// ---- k_cascade_classes parameters (passed by value as a __grid_constant__: tensor maps and the bulk
 // stages' weak classifiers live in the constant bank, so they cost no load/store-unit bandwidth) ----
-#define NV_BULK_MAX_STUMPS 400
+#define NV_BULK_MAX_STUMPS 384
 #define NV_BULK_MAX_STAGES 16
-#define NV_TILE 32                 // windows per tile side
+#define NV_CTX 64                  // tile width and height in windows
+#define NV_CTY 32
+
+// One bulk-stage weak classifier, 64 bytes, warp-uniform.  Offsets are BYTE offsets of the rect corners a, b, c, d
+// from the window's origin in the shared-memory tile.
+struct __align__(16) BulkStump {
+    uint4 o0, o1;                  // rects 0 and 1
+    uint32_t w0, w1, w2, thr;      // weights (float bits, or int32 in the exact-integer variant), node threshold (float bits)
+    uint32_t d_lo, d_hi;           // order-free variant: (double)left - (double)right
+    uint32_t left, right;          // in-order variant: leaves (float bits)
+};
 
 struct TileParams {
-    uint4 off[NV_BULK_MAX_STUMPS][3];   // per rect: BYTE offsets of the corners a, b, c, d in the shared-memory tile
-    float2 cf[NV_BULK_MAX_STUMPS][3];   // (w0, w1), (w2, threshold), (left, right)
-    int stage_first[NV_BULK_MAX_STAGES + 1];
+    BulkStump s[NV_BULK_MAX_STUMPS];
+    uint4 o2[NV_BULK_MAX_STUMPS];  // rect 2 (a copy of rect 0 with weight 0 for two-rect features)
+    int stage_first[NV_BULK_MAX_STAGES + 1];   // stage s: two-rect classifiers [first[s], mid[s]), three-rect [mid[s], first[s+1])
+    int stage_mid[NV_BULK_MAX_STAGES];
     float stage_thr[NV_BULK_MAX_STAGES];
+    double stage_base[NV_BULK_MAX_STAGES];     // order-free variant: sum of the stage's right leaves
     int stage_begin, stage_end;    // bulk stages [begin, end)
     int final_stage;               // 1: stage_end == nstages, survivors are candidates
-    int order_free;                // stage sums may be split across warps (cascade certificate)
+    int fast;                      // 1: order-free stage sums and exact integer feature arithmetic (certificates in fill_bulk_stumps)
     int level_begin, level_end;
     int cp, rt, ps;                // tile plane geometry: columns, rows, plane stride (words)
+    int kskew;                     // bank class of window (lx, ly) = (lx + kskew * ly) & 31
     const CUtensorMap *maps;       // one per level, in global memory (written by the host before launch)
     const PlanDev *plan;
     const uint32_t *bits_alive;
@@ -273,7 +285,7 @@ cudaError_t launch_queue_stages(const PlanDev *plan, const DevCascade *meta, con
 cudaError_t launch_stage0_rows(const PlanDev *plan, int total_rows, const DevCascade *meta, const DevStump *stumps,
                                const uint32_t *sum, const uint32_t *sq, float *vnf, uint32_t *bits_alive, int *counters,
                                int16_t *depth, cudaStream_t st);
-cudaError_t launch_cascade_tiles(const TileParams &tp, int ystep, int ntiles, cudaStream_t st);
+cudaError_t launch_cascade_classes(const TileParams &tp, int ystep, int ntiles, cudaStream_t st);
 cudaError_t launch_stage0_rows_p(const Stage0Params &sp, cudaStream_t st);
 bool fill_stage0_params(const nv_cascade *c, const PlanDev &P, Stage0Params *sp);
 cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,

@@ -105,14 +105,13 @@ k_queue_stages(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ 
 }
 
 // ================================================================================================
-// v2 pass structure (all levels per launch):
+// pass structure (all levels per launch):
 //   k_stage0_rows      one warp per window ROW: variance + stage 0 for each 32-window chunk, the skip
 //                      automaton carried along the row in a register, one "alive" bit-word per chunk.
-//   k_cascade_tiles    one block per 32x32-window tile: the integral tile (+halo) is staged in shared
-//                      memory by TMA (one 2-D box per column plane), the tile's alive windows form a
-//                      queue, and stages 1..B-1 run with one lane per queued window and warp-ballot
-//                      compaction into the next queue between stages.  The weak classifiers of these
-//                      stages and the tensor maps sit in the kernel's parameter (constant) bank.
+//   k_cascade_classes  one block per 64x32-window tile: the integral tile (+halo) is staged in shared
+//                      memory by TMA, stages 1..B-1 run with each lane bound to one shared-memory bank
+//                      class of windows (see the kernel).  The weak classifiers of these stages and the
+//                      tensor maps sit in the kernel's parameter (constant) bank.
 //   k_cascade_tail     the few windows that outlive the bulk stages: one warp per window, the 32 lanes
 //                      evaluate 32 different weak classifiers of the stage on a private copy of the
 //                      window's integral patch; exact because the double stage sum is order-free for the
@@ -353,55 +352,120 @@ __device__ __forceinline__ int uniformize(int v, int bits)
     return r;
 }
 
-// one stage slice [ka, kb) of weak classifiers for the window whose tile origin is byte pointer wb
-__device__ __forceinline__ double bulk_stage_sum(const TileParams &P, const uint8_t *wb, float vnf, int ka, int kb)
+// ================================================================================================
+// k_cascade_classes — the bulk stages, free of shared-memory bank conflicts.
+// A tile is NV_CTX x NV_CTY = 64 x 32 windows; its integral patch (+halo) is staged in shared memory by TMA, one
+// 2-D box per column plane.  The tile's pitch makes the bank of every corner read of window (lx, ly) equal to
+// (lx + kskew * ly + const) mod 32, so the 2048 windows fall into 32 bank classes of 64 members (member index =
+// 2 * ly + lx / 32).  Lane c of every warp only ever evaluates windows of class c: the 32 lanes of a corner load hit
+// 32 different banks whatever the alive pattern is (the compacted-queue kernel this replaces spent 59 % of its
+// shared-memory wavefronts on conflict replays, profiles/r1_v2_summary.md).  The alive set of a class is a 64-bit
+// mask; in every stage warp w takes the set bits of rank w, w + 8, ..., so no queue and no compaction is needed, and
+// the surviving bits are OR-ed into the next stage's mask.  The price is imbalance between classes (a round runs as
+// long as the fullest class has members left): on config 3, 6.8 M warp rounds per frame against 5.1 M for perfect
+// compaction, but each weak classifier costs 8.7 wavefronts instead of 22.
+//
+// FAST variant (certificates computed by fill_bulk_stumps): the cascade's stage sums are order-free and its feature
+// weights are small integers.  Then (a) w0*r0 + w1*r1 (+ w2*r2) is evaluated in int32 and converted once — every
+// float operation of the reference is exact on such values, so the result is the same float; (b) the stage sum starts
+// at the sum of all right leaves and a classifier whose feature is below its threshold adds (left - right), one
+// predicated DADD; (c) two-rect classifiers run before three-rect ones, each in a branch-free loop.  The general
+// variant keeps the reference's float operations and XML order.
+// ================================================================================================
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
-    double tmp = 0.;
-    for (int k = ka; k < kb; k++) {
-        uint4 o0 = P.off[k][0], o1 = P.off[k][1];
-        float2 w01 = P.cf[k][0], w2t = P.cf[k][1], lr = P.cf[k][2];
-#define TILE_AT(o) (*reinterpret_cast<const uint32_t *>(wb + (o)))
-        int r0 = (int)(TILE_AT(o0.x) - TILE_AT(o0.y) - TILE_AT(o0.z) + TILE_AT(o0.w));
-        int r1 = (int)(TILE_AT(o1.x) - TILE_AT(o1.y) - TILE_AT(o1.z) + TILE_AT(o1.w));
-        float f = __fadd_rn(__fmul_rn(w01.x, __int2float_rn(r0)), __fmul_rn(w01.y, __int2float_rn(r1)));
-        if (w2t.x != 0.f) {
-            uint4 o2 = P.off[k][2];
-            int r2 = (int)(TILE_AT(o2.x) - TILE_AT(o2.y) - TILE_AT(o2.z) + TILE_AT(o2.w));
-            f = __fadd_rn(f, __fmul_rn(w2t.x, __int2float_rn(r2)));
-        }
-#undef TILE_AT
-        f = __fmul_rn(f, vnf);
-        tmp = __dadd_rn(tmp, (double)(f < w2t.y ? lr.x : lr.y));
-    }
-    return tmp;
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// tmp += d if f < thr, as one predicated DADD (the compiler's own if-conversion is DADD + two selects)
+__device__ __forceinline__ void dadd_if_lt(double &tmp, float f, float thr, double d)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.rn.f64 %0, %0, %3;\n\t}" : "+d"(tmp) : "f"(f), "f"(thr), "d"(d));
+}
+__device__ __forceinline__ int rect4(uint32_t wa, const uint4 &o)
+{
+    return (int)(lds_u32(wa + o.x) - lds_u32(wa + o.y) - lds_u32(wa + o.z) + lds_u32(wa + o.w));
 }
 
-template <int YS>
-__global__ void __launch_bounds__(256) k_cascade_tiles(const __grid_constant__ TileParams P)
+// NW windows (1 or 2) of one lane through one stage; returns "stage passed" per window
+template <bool FAST, int NW>
+__device__ __forceinline__ void class_stage(const TileParams &P, int si, const uint32_t (&wa)[NW], const float (&vnf)[NW],
+                                            bool (&pass)[NW])
+{
+    const int k0 = P.stage_first[si], km = P.stage_mid[si], k1 = P.stage_first[si + 1];
+    const double thr = (double)P.stage_thr[si];
+    double tmp[NW];
+    if (FAST) {
+#pragma unroll
+        for (int i = 0; i < NW; i++) tmp[i] = P.stage_base[si];
+        for (int k = k0; k < km; k++) {                         // two-rect classifiers
+            const BulkStump &S = P.s[k];
+            const double d = __hiloint2double((int)S.d_hi, (int)S.d_lo);
+            const float sthr = __uint_as_float(S.thr);
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                int r = (int)S.w0 * rect4(wa[i], S.o0) + (int)S.w1 * rect4(wa[i], S.o1);
+                dadd_if_lt(tmp[i], __fmul_rn(__int2float_rn(r), vnf[i]), sthr, d);
+            }
+        }
+        for (int k = km; k < k1; k++) {                         // three-rect classifiers
+            const BulkStump &S = P.s[k];
+            const double d = __hiloint2double((int)S.d_hi, (int)S.d_lo);
+            const float sthr = __uint_as_float(S.thr);
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                int r = (int)S.w0 * rect4(wa[i], S.o0) + (int)S.w1 * rect4(wa[i], S.o1) + (int)S.w2 * rect4(wa[i], P.o2[k]);
+                dadd_if_lt(tmp[i], __fmul_rn(__int2float_rn(r), vnf[i]), sthr, d);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NW; i++) tmp[i] = 0.;
+        for (int k = k0; k < k1; k++) {                         // XML order, the reference's float operations
+            const BulkStump &S = P.s[k];
+            const float w0 = __uint_as_float(S.w0), w1 = __uint_as_float(S.w1), w2 = __uint_as_float(S.w2);
+            const float sthr = __uint_as_float(S.thr), left = __uint_as_float(S.left), right = __uint_as_float(S.right);
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                float f = __fadd_rn(__fmul_rn(w0, __int2float_rn(rect4(wa[i], S.o0))),
+                                    __fmul_rn(w1, __int2float_rn(rect4(wa[i], S.o1))));
+                if (w2 != 0.f) f = __fadd_rn(f, __fmul_rn(w2, __int2float_rn(rect4(wa[i], P.o2[k]))));
+                f = __fmul_rn(f, vnf[i]);
+                tmp[i] = __dadd_rn(tmp[i], (double)(f < sthr ? left : right));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NW; i++) pass[i] = !(tmp[i] < thr);
+}
+
+template <int YS, bool FAST>
+__global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__ TileParams P)
 {
     extern __shared__ __align__(128) uint32_t tile[];           // [YS planes][rt][cp], plane stride ps
     __shared__ __align__(8) unsigned long long mbar;
-    __shared__ unsigned short q[2][NV_TILE * NV_TILE];
-    __shared__ float s_vnf[NV_TILE * NV_TILE];
-    __shared__ double s_part[8][32];
-    __shared__ int s_cnt[3];
-    __shared__ int s_rowoff[33];
-    __shared__ int s_base;
+    __shared__ float s_vnf[64 * 32];                             // [member][class]
+    __shared__ uint32_t s_mask[3][2][32];                        // rotating alive masks: [buffer][member / 32][class]
+    __shared__ uint32_t s_words[NV_CTY][2];
     const PlanDev *__restrict__ plan = P.plan;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = uniformize(tid >> 5, 3);
 
     int t = blockIdx.x, l = P.level_begin;
-    while (l + 1 < P.level_end && plan->lv[l + 1].tile0 <= t) l++;
+    while (l + 1 < P.level_end && plan->lv[l + 1].ctile0 <= t) l++;
     const LevelDesc &L = plan->lv[l];
-    int rel = t - L.tile0, ty = rel / L.nxw, tx = rel - ty * L.nxw;
-    int iy0 = ty * NV_TILE, ix0 = tx * NV_TILE;
-    const int CP = P.cp, PS = P.ps;
+    int rel = t - L.ctile0, ty = rel / L.cntx, tx = rel - ty * L.cntx;
+    int iy0 = ty * NV_CTY, ix0 = tx * NV_CTX;
+    const int CP = P.cp, PS = P.ps, K = P.kskew;
     uint32_t bar = smem_u32(&mbar);
 
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0;
+    if (tid == 0) mbar_init(bar, 1);
+    if (tid < 64) {                                              // the tile's alive words, two per window row
+        int ly = tid >> 1, cx = 2 * tx + (tid & 1);
+        s_words[ly][tid & 1] = (iy0 + ly < L.ny && cx < L.nxw) ? P.bits_alive[L.bofs + (size_t)(iy0 + ly) * L.nxw + cx] : 0u;
+    } else {
+        (&s_mask[0][0][0])[tid - 64] = 0u;
     }
     __syncthreads();
     if (tid == 0) {                                              // stage the integral tile: one box per plane
@@ -410,106 +474,101 @@ __global__ void __launch_bounds__(256) k_cascade_tiles(const __grid_constant__ T
         for (int p = 0; p < YS; p++)
             tma_load_2d(smem_u32(tile + p * PS), P.maps + l, ix0 + p * L.iplane, iy0 * YS, bar);
     }
-    // meanwhile: queue of the tile's alive windows, raster order
-    int nrows = min(NV_TILE, L.ny - iy0);
-    const uint32_t *aw = P.bits_alive + L.bofs + (size_t)iy0 * L.nxw + tx;
-    if (tid < 32) {
-        uint32_t w = tid < nrows ? aw[(size_t)tid * L.nxw] : 0u;
-        int inc = __popc(w);
+    {   // class masks: warp w transposes window rows 4w .. 4w+3 (8 members, all in the same mask half)
+        uint32_t part = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += v;
+        for (int i = 0; i < 8; i++) {
+            int ly = warp * 4 + (i >> 1), h = i & 1;
+            uint32_t b = (s_words[ly][h] >> ((lane - K * ly) & 31)) & 1u;
+            part |= b << ((ly * 2 + h) & 31);
         }
-        s_rowoff[tid + 1] = inc;
-        if (tid == 0) s_rowoff[0] = 0;
+        if (part) atomicOr(&s_mask[0][warp >> 2][lane], part);
     }
-    __syncthreads();
-    for (int r = warp; r < nrows; r += 8) {
-        uint32_t w = aw[(size_t)r * L.nxw];
-        if ((w >> lane) & 1u) {
-            int id = (r << 5) | lane;
-            q[0][s_rowoff[r] + __popc(w & ((1u << lane) - 1u))] = (unsigned short)id;
-            s_vnf[id] = P.vnf[L.wofs + (iy0 + r) * L.nx + ix0 + lane];
-        }
+    for (int i = tid; i < NV_CTX * NV_CTY; i += 256) {
+        int ly = i >> 6, lx = i & 63;
+        if ((s_words[ly][lx >> 5] >> (lx & 31)) & 1u)
+            s_vnf[((ly * 2 + (lx >> 5)) << 5) + ((lx + K * ly) & 31)] = P.vnf[L.wofs + (iy0 + ly) * L.nx + ix0 + lx];
     }
-    int n = uniformize(s_rowoff[32], 11);
     __syncthreads();
     mbar_wait(bar, 0);                                           // also before an early exit: the copy targets this CTA's smem
-    if (n == 0) return;                                          // uniform: nothing alive in this tile
 
-    const uint8_t *tile8 = reinterpret_cast<const uint8_t *>(tile);
+    const uint32_t tile_sa = smem_u32(tile);
+    const int rowb = YS * CP * 4;                                // bytes from one window row to the next
     int cur = 0;
-    for (int st = P.stage_begin; st < P.stage_end && n > 0; st++) {
-        int k0 = P.stage_first[st - P.stage_begin], k1 = P.stage_first[st - P.stage_begin + 1];
-        double thr = (double)P.stage_thr[st - P.stage_begin];
-        int co = (st + 1) % 3, cz = (st + 2) % 3;                // rotating counters: out / to reset
-        if (tid == 0) s_cnt[cz] = 0;
-        int B = (n + 31) >> 5;                                   // 32-window batches in this stage
-        int S = (P.order_free && B < 8) ? 8 / B : 1;             // warps per batch: the stage's classifiers are split
-        if (S == 1) {
-            for (int b = warp * 32; b < n; b += 256) {
-                int i = b + lane;
-                bool active = i < n;
-                int id = q[cur][active ? i : b];
-                int ly = id >> 5, lx = id & 31;
-                double tmp = bulk_stage_sum(P, tile8 + (ly * YS * CP + lx) * 4, s_vnf[id], k0, k1);
-                bool pass = active && !(tmp < thr);
-                uint32_t pm = __ballot_sync(0xffffffffu, pass);
-                if (pm) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_cnt[co], __popc(pm));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (pass) q[cur ^ 1][base + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)id;
-                }
-                if (P.depth && active && !pass) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = (int16_t)(-st);
+    for (int st = P.stage_begin; st < P.stage_end; st++) {
+        const int si = st - P.stage_begin;
+        uint32_t mlo = s_mask[cur][0][lane], mhi = s_mask[cur][1][lane];
+        int maxc = uniformize(__reduce_max_sync(0xffffffffu, __popc(mlo) + __popc(mhi)), 7);
+        if (maxc == 0) return;                                   // block-uniform: every warp reads the same masks
+        int nxt = cur == 2 ? 0 : cur + 1, zer = nxt == 2 ? 0 : nxt + 1;
+        if (warp == 0) { s_mask[zer][0][lane] = 0u; s_mask[zer][1][lane] = 0u; }
+        unsigned long long rem = ((unsigned long long)mhi << 32) | mlo, pass_bits = 0ull;
+        for (int i = 0; i < warp; i++) rem &= rem - 1ull;        // warp w takes the set bits of rank w, w + 8, ...
+        int j = warp;
+        for (; j + 8 < maxc; j += 16) {                          // two windows per lane and round
+            int bit[2]; bool active[2], pass[2]; uint32_t wa[2]; float vnf[2]; int ly[2], lx[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                active[i] = rem != 0ull;
+                bit[i] = active[i] ? __ffsll((long long)rem) - 1 : 0;
+                ly[i] = bit[i] >> 1; lx[i] = ((lane - K * ly[i]) & 31) + ((bit[i] & 1) << 5);
+                wa[i] = tile_sa + (uint32_t)(ly[i] * rowb + lx[i] * 4);
+                vnf[i] = s_vnf[(bit[i] << 5) + lane];
+#pragma unroll
+                for (int q = 0; q < 8; q++) rem &= rem - 1ull;
             }
-        } else {
-            // few windows left: batch bt is shared by S warps, each summing a slice of the stage (exact: the
-            // double sum is order-free for this cascade), partial sums meet in shared memory
-            bool wact = warp < B * S;
-            int bt = warp % B, sl = warp / B;
-            int len = (k1 - k0 + S - 1) / S, ka = min(k1, k0 + sl * len), kb = min(k1, ka + len);
-            int i = bt * 32 + lane;
-            bool active = wact && i < n;
-            int id = q[cur][active ? i : 0];
-            int ly = id >> 5, lx = id & 31;
-            double tmp = 0.;
-            if (wact) tmp = bulk_stage_sum(P, tile8 + (ly * YS * CP + lx) * 4, s_vnf[id], ka, kb);
-            if (wact && sl > 0) s_part[warp][lane] = tmp;
-            __syncthreads();
-            if (wact && sl == 0) {
-                for (int j = 1; j < S; j++) tmp = __dadd_rn(tmp, s_part[bt + j * B][lane]);
-                bool pass = active && !(tmp < thr);
-                uint32_t pm = __ballot_sync(0xffffffffu, pass);
-                if (pm) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_cnt[co], __popc(pm));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (pass) q[cur ^ 1][base + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)id;
-                }
-                if (P.depth && active && !pass) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = (int16_t)(-st);
+            class_stage<FAST, 2>(P, si, wa, vnf, pass);
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (active[i] && pass[i]) pass_bits |= 1ull << bit[i];
+                if (P.depth && active[i] && !pass[i]) P.depth[L.wofs + (iy0 + ly[i]) * L.nx + ix0 + lx[i]] = (int16_t)(-st);
             }
         }
+        for (; j < maxc; j += 8) {                               // at most one single-window round
+            bool active = rem != 0ull;
+            int bit = active ? __ffsll((long long)rem) - 1 : 0;
+            int ly = bit >> 1, lx = ((lane - K * ly) & 31) + ((bit & 1) << 5);
+            uint32_t wa[1] = {tile_sa + (uint32_t)(ly * rowb + lx * 4)};
+            float vnf[1] = {s_vnf[(bit << 5) + lane]};
+            bool pass[1];
+            class_stage<FAST, 1>(P, si, wa, vnf, pass);
+            if (active && pass[0]) pass_bits |= 1ull << bit;
+            if (P.depth && active && !pass[0]) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = (int16_t)(-st);
+#pragma unroll
+            for (int q = 0; q < 8; q++) rem &= rem - 1ull;
+        }
+        if ((uint32_t)pass_bits) atomicOr(&s_mask[nxt][0][lane], (uint32_t)pass_bits);
+        if ((uint32_t)(pass_bits >> 32)) atomicOr(&s_mask[nxt][1][lane], (uint32_t)(pass_bits >> 32));
         __syncthreads();
-        n = uniformize(s_cnt[co], 11);
-        cur ^= 1;
+        cur = nxt;
     }
-    if (n == 0) return;
     // survivors: candidates if the bulk stages were the whole cascade, else the tail queue
+    if (warp != 0) return;
+    uint32_t mlo = s_mask[cur][0][lane], mhi = s_mask[cur][1][lane];
+    int cnt = __popc(mlo) + __popc(mhi), inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+    }
+    int total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0) return;
     int *counter = P.counters + (P.final_stage ? 1 : 3);
     int cap = P.final_stage ? P.cand_cap : P.tail_cap;
-    if (tid == 0) s_base = atomicAdd(counter, n);
-    __syncthreads();
-    for (int i = tid; i < n; i += 256) {
-        int id = q[cur][i], ly = id >> 5, lx = id & 31, pos = s_base + i;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 0) + inc - cnt;
+    unsigned long long rem = ((unsigned long long)mhi << 32) | mlo;
+    for (; rem; rem &= rem - 1ull, base++) {
+        int bit = __ffsll((long long)rem) - 1;
+        int ly = bit >> 1, lx = ((lane - K * ly) & 31) + ((bit & 1) << 5);
         uint32_t key = ((uint32_t)l << 26) | ((uint32_t)(iy0 + ly) << 13) | (uint32_t)(ix0 + lx);
-        if (pos >= cap) { P.counters[2] = 1; continue; }
+        if (base >= cap) { P.counters[2] = 1; continue; }
         if (P.final_stage) {
-            P.cand[pos] = key;
+            P.cand[base] = key;
             if (P.depth) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = NV_DEPTH_PASS;
         } else
-            P.tail[pos] = make_uint2(key, __float_as_uint(s_vnf[id]));
+            P.tail[base] = make_uint2(key, __float_as_uint(s_vnf[(bit << 5) + lane]));
     }
 }
 
@@ -584,29 +643,66 @@ k_cascade_tail(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ 
     }
 }
 
-// host: bulk-stage weak classifiers with shared-memory corner BYTE offsets for one ystep class
+// host: bulk-stage weak classifiers with shared-memory corner BYTE offsets for one ystep class, plus the two
+// certificates of the FAST variant:
+//   order-free — cascade_xml.cpp proves that no addition of a stage's leaves can round in double, so any order and the
+//     "sum of right leaves + (left - right) of the classifiers below threshold" form give the reference's stage sum
+//     (every partial sum is a sum of one leaf per classifier, a multiple of the smallest leaf ulp below 2^52 ulps);
+//   integer features — all weights of the bulk stages are integers and sum_j |w_j| * area_j * 255 < 2^24, so every
+//     float product and sum of the reference's feature evaluation is exact and equals the int32 evaluation.
 void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_end, TileParams *tp)
 {
     const DevCascade &m = c->meta;
     tp->stage_begin = 1;
     tp->stage_end = stage_end;
     tp->final_stage = stage_end == m.nstages;
-    tp->order_free = c->h.order_free;
-    int base = m.stage_first[1];
-    for (int s = 1; s <= stage_end; s++) tp->stage_first[s - 1] = m.stage_first[s] - base;
-    for (int s = 1; s < stage_end; s++) tp->stage_thr[s - 1] = m.stage_thr[s];
-    auto off = [&](int dx, int dy) { return 4u * (uint32_t)(ystep == 2 ? (dx & 1) * ps + dy * cp + (dx >> 1) : dy * cp + dx); };
-    for (int k = m.stage_first[1]; k < m.stage_first[stage_end]; k++) {
+    bool fast = c->h.order_free != 0;
+    for (int k = m.stage_first[1]; k < m.stage_first[stage_end] && fast; k++) {
         const DevStump &d = c->stumps[k];
-        int i = k - base;
+        double bound = 0;
         for (int j = 0; j < 3; j++) {
-            int x = d.r[j] & 255, y = (d.r[j] >> 8) & 255, w = (d.r[j] >> 16) & 255, h = d.r[j] >> 24;
-            tp->off[i][j] = make_uint4(off(x, y), off(x + w, y), off(x, y + h), off(x + w, y + h));
+            if (d.w[j] != rintf(d.w[j]) || fabsf(d.w[j]) > 4096.f) fast = false;
+            bound += fabs((double)d.w[j]) * ((d.r[j] >> 16) & 255) * (d.r[j] >> 24) * 255.0;
         }
-        tp->cf[i][0] = make_float2(d.w[0], d.w[1]);
-        tp->cf[i][1] = make_float2(d.w[2], d.thr);
-        tp->cf[i][2] = make_float2(d.left, d.right);
+        if (bound >= 16777216.0) fast = false;
     }
+    tp->fast = fast ? 1 : 0;
+    auto off = [&](int dx, int dy) { return 4u * (uint32_t)(ystep == 2 ? (dx & 1) * ps + dy * cp + (dx >> 1) : dy * cp + dx); };
+    auto f2u = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    int n = 0;
+    for (int s = 1; s < stage_end; s++) {
+        int si = s - 1;
+        tp->stage_first[si] = n;
+        tp->stage_thr[si] = m.stage_thr[s];
+        double rsum = 0;
+        // FAST: two-rect classifiers first, then three-rect ones; otherwise XML order with mid == first
+        for (int pass = 0; pass < (fast ? 2 : 1); pass++) {
+            if (pass == 1 || !fast) tp->stage_mid[si] = fast ? n : tp->stage_first[si];
+            for (int k = m.stage_first[s]; k < m.stage_first[s + 1]; k++) {
+                const DevStump &d = c->stumps[k];
+                bool three = d.w[2] != 0.f;
+                if (fast && three != (pass == 1)) continue;
+                BulkStump &b = tp->s[n];
+                uint4 o[3];
+                for (int j = 0; j < 3; j++) {
+                    uint32_t r = three || j < 2 ? d.r[j] : d.r[0];
+                    int x = r & 255, y = (r >> 8) & 255, w = (r >> 16) & 255, h = r >> 24;
+                    o[j] = make_uint4(off(x, y), off(x + w, y), off(x, y + h), off(x + w, y + h));
+                }
+                b.o0 = o[0]; b.o1 = o[1]; tp->o2[n] = o[2];
+                if (fast) { b.w0 = (uint32_t)(int)d.w[0]; b.w1 = (uint32_t)(int)d.w[1]; b.w2 = (uint32_t)(int)d.w[2]; }
+                else { b.w0 = f2u(d.w[0]); b.w1 = f2u(d.w[1]); b.w2 = f2u(d.w[2]); }
+                b.thr = f2u(d.thr); b.left = f2u(d.left); b.right = f2u(d.right);
+                double dd = (double)d.left - (double)d.right;
+                uint64_t u; memcpy(&u, &dd, 8);
+                b.d_lo = (uint32_t)u; b.d_hi = (uint32_t)(u >> 32);
+                rsum += (double)d.right;
+                n++;
+            }
+        }
+        tp->stage_base[si] = rsum;
+    }
+    tp->stage_first[stage_end - 1] = n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -633,11 +729,28 @@ cudaError_t launch_alive_to_queue(const PlanDev *plan, int total_rows, const flo
     return cudaGetLastError();
 }
 
-cudaError_t launch_cascade_tiles(const TileParams &tp, int ystep, int ntiles, cudaStream_t st)
+cudaError_t launch_cascade_classes(const TileParams &tp, int ystep, int ntiles, cudaStream_t st)
 {
     size_t smem = (size_t)ystep * tp.ps * sizeof(uint32_t);
-    if (ystep == 2) k_cascade_tiles<2><<<ntiles, 256, smem, st>>>(tp);
-    else k_cascade_tiles<1><<<ntiles, 256, smem, st>>>(tp);
+    static std::mutex mu;
+    static unsigned long long attr_set = 0ull;                   // per device: the attribute belongs to the device's function
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!((attr_set >> (dev & 63)) & 1ull)) {
+        cudaFuncSetAttribute(k_cascade_classes<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_cascade_classes<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_cascade_classes<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_cascade_classes<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set |= 1ull << (dev & 63);
+    }
+    if (ystep == 2) {
+        if (tp.fast) k_cascade_classes<2, true><<<ntiles, 256, smem, st>>>(tp);
+        else k_cascade_classes<2, false><<<ntiles, 256, smem, st>>>(tp);
+    } else {
+        if (tp.fast) k_cascade_classes<1, true><<<ntiles, 256, smem, st>>>(tp);
+        else k_cascade_classes<1, false><<<ntiles, 256, smem, st>>>(tp);
+    }
     return cudaGetLastError();
 }
 
