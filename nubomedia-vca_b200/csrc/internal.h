@@ -127,14 +127,15 @@ struct ResizeKey {
 struct __align__(16) BulkStump {
     uint4 o0, o1;                  // rects 0 and 1
     uint32_t w0, w1, w2, thr;      // weights (float bits, or int32 in the exact-integer variant), node threshold (float bits)
-    uint32_t d_lo, d_hi;           // order-free variant: (double)left - (double)right
+    uint32_t d_lo, d_hi;           // order-free variant: 128 * ((double)left - (double)right)
     uint32_t left, right;          // in-order variant: leaves (float bits)
 };
 
 struct TileParams {
     BulkStump s[NV_BULK_MAX_STUMPS];
     uint4 o2[NV_BULK_MAX_STUMPS];  // rect 2 (a copy of rect 0 with weight 0 for two-rect features)
-    int stage_first[NV_BULK_MAX_STAGES + 1];   // stage s: two-rect classifiers [first[s], mid[s]), three-rect [mid[s], first[s+1])
+    int stage_first[NV_BULK_MAX_STAGES + 1];   // stage s (FAST order): six-load two-rect classifiers [first[s], mid6[s]),
+    int stage_mid6[NV_BULK_MAX_STAGES];        // eight-load two-rect [mid6[s], mid[s]), three-rect [mid[s], first[s+1])
     int stage_mid[NV_BULK_MAX_STAGES];
     float stage_thr[NV_BULK_MAX_STAGES];
     double stage_base[NV_BULK_MAX_STAGES];     // order-free variant: sum of the stage's right leaves

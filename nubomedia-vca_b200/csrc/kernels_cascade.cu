@@ -378,45 +378,65 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-// tmp += d if f < thr, as one predicated DADD (the compiler's own if-conversion is DADD + two selects)
-__device__ __forceinline__ void dadd_if_lt(double &tmp, float f, float thr, double d)
-{
-    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.rn.f64 %0, %0, %3;\n\t}" : "+d"(tmp) : "f"(f), "f"(thr), "d"(d));
-}
 __device__ __forceinline__ int rect4(uint32_t wa, const uint4 &o)
 {
     return (int)(lds_u32(wa + o.x) - lds_u32(wa + o.y) - lds_u32(wa + o.z) + lds_u32(wa + o.w));
 }
+// minus the rect sum: b + c - a - d
+__device__ __forceinline__ int nrect4(uint32_t wa, const uint4 &o)
+{
+    return (int)(lds_u32(wa + o.y) + lds_u32(wa + o.z) - lds_u32(wa + o.x) - lds_u32(wa + o.w));
+}
+// tmp += d if f < thr, in two instructions: FSET.BF yields the bits of 1.0f or 0, which as the HIGH word of a double
+// (low word 0) read 2^-7 or 0.0; d128 = 128 * d, so the fused multiply-add adds exactly d or exactly 0.
+__device__ __forceinline__ void add_if_lt(double &tmp, float f, float thr, double d128)
+{
+    float m = f < thr ? 1.0f : 0.0f;
+    tmp = __fma_rn(d128, __hiloint2double(__float_as_int(m), 0), tmp);
+}
 
-// NW windows (1 or 2) of one lane through one stage; returns "stage passed" per window
+// NW windows (1 or 2) of one lane through one stage; pass[i] = "stage passed"
 template <bool FAST, int NW>
 __device__ __forceinline__ void class_stage(const TileParams &P, int si, const uint32_t (&wa)[NW], const float (&vnf)[NW],
                                             bool (&pass)[NW])
 {
-    const int k0 = P.stage_first[si], km = P.stage_mid[si], k1 = P.stage_first[si + 1];
+    const int k0 = P.stage_first[si], k1 = P.stage_first[si + 1];
     const double thr = (double)P.stage_thr[si];
     double tmp[NW];
     if (FAST) {
+        const int k6 = P.stage_mid6[si], km = P.stage_mid[si];
 #pragma unroll
         for (int i = 0; i < NW; i++) tmp[i] = P.stage_base[si];
-        for (int k = k0; k < km; k++) {                         // two-rect classifiers
+        for (int k = k0; k < k6; k++) {                         // two rects sharing two corners: six loads (fill_bulk_stumps)
             const BulkStump &S = P.s[k];
             const double d = __hiloint2double((int)S.d_hi, (int)S.d_lo);
             const float sthr = __uint_as_float(S.thr);
 #pragma unroll
             for (int i = 0; i < NW; i++) {
-                int r = (int)S.w0 * rect4(wa[i], S.o0) + (int)S.w1 * rect4(wa[i], S.o1);
-                dadd_if_lt(tmp[i], __fmul_rn(__int2float_rn(r), vnf[i]), sthr, d);
+                int u = (int)(lds_u32(wa[i] + S.o0.x) - lds_u32(wa[i] + S.o0.y));
+                int nr0 = (int)(lds_u32(wa[i] + S.o0.z) - lds_u32(wa[i] + S.o0.w)) - u;
+                int r1 = u - (int)lds_u32(wa[i] + S.o1.x) + (int)lds_u32(wa[i] + S.o1.y);
+                add_if_lt(tmp[i], __fmul_rn(__int2float_rn((int)S.w1 * r1 + nr0), vnf[i]), sthr, d);
             }
         }
-        for (int k = km; k < k1; k++) {                         // three-rect classifiers
+        for (int k = k6; k < km; k++) {                         // two rects, eight loads
             const BulkStump &S = P.s[k];
             const double d = __hiloint2double((int)S.d_hi, (int)S.d_lo);
             const float sthr = __uint_as_float(S.thr);
 #pragma unroll
             for (int i = 0; i < NW; i++) {
-                int r = (int)S.w0 * rect4(wa[i], S.o0) + (int)S.w1 * rect4(wa[i], S.o1) + (int)S.w2 * rect4(wa[i], P.o2[k]);
-                dadd_if_lt(tmp[i], __fmul_rn(__int2float_rn(r), vnf[i]), sthr, d);
+                int r = (int)S.w1 * rect4(wa[i], S.o1) + nrect4(wa[i], S.o0);
+                add_if_lt(tmp[i], __fmul_rn(__int2float_rn(r), vnf[i]), sthr, d);
+            }
+        }
+        for (int k = km; k < k1; k++) {                         // three rects
+            const BulkStump &S = P.s[k];
+            const double d = __hiloint2double((int)S.d_hi, (int)S.d_lo);
+            const float sthr = __uint_as_float(S.thr);
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                int r = (int)S.w1 * rect4(wa[i], S.o1) + (int)S.w2 * rect4(wa[i], P.o2[k]) + nrect4(wa[i], S.o0);
+                add_if_lt(tmp[i], __fmul_rn(__int2float_rn(r), vnf[i]), sthr, d);
             }
         }
     } else {
@@ -643,13 +663,21 @@ k_cascade_tail(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ 
     }
 }
 
-// host: bulk-stage weak classifiers with shared-memory corner BYTE offsets for one ystep class, plus the two
+// host: bulk-stage weak classifiers with shared-memory corner BYTE offsets for one ystep class, plus the
 // certificates of the FAST variant:
 //   order-free — cascade_xml.cpp proves that no addition of a stage's leaves can round in double, so any order and the
 //     "sum of right leaves + (left - right) of the classifiers below threshold" form give the reference's stage sum
 //     (every partial sum is a sum of one leaf per classifier, a multiple of the smallest leaf ulp below 2^52 ulps);
-//   integer features — all weights of the bulk stages are integers and sum_j |w_j| * area_j * 255 < 2^24, so every
-//     float product and sum of the reference's feature evaluation is exact and equals the int32 evaluation.
+//   integer features — the first rect of every bulk-stage feature weighs -1, the other weights are integers and
+//     sum_j |w_j| * area_j * 255 < 2^24, so every float product and sum of the reference's feature evaluation is
+//     exact and equals the int32 evaluation w1*r1 (+ w2*r2) - r0.
+// FAST order inside a stage: two-rect features whose rects share two corners (one rect is a half of the other),
+// other two-rect features, three-rect features.  For the first group r0 = U - V and r1 = U - V' with a common
+// difference U of two corner values: six loads instead of eight.  o0 = (p0, p1, p2, p3), o1 = (p4, p5) with
+//   U = p0 - p1,  -r0 = (p2 - p3) - U,  r1 = U - p4 + p5
+// which covers the four sharing patterns by the choice of p (a, b, c, d = corners of rect 0; a1.. of rect 1):
+//   left half  (a = a1, c = c1): p = a, c, b, d, b1, d1        right half  (b = b1, d = d1): p = d, b, c, a, c1, a1
+//   top half   (a = a1, b = b1): p = a, b, c, d, c1, d1        bottom half (c = c1, d = d1): p = d, c, b, a, b1, a1
 void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_end, TileParams *tp)
 {
     const DevCascade &m = c->meta;
@@ -664,41 +692,59 @@ void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_
             if (d.w[j] != rintf(d.w[j]) || fabsf(d.w[j]) > 4096.f) fast = false;
             bound += fabs((double)d.w[j]) * ((d.r[j] >> 16) & 255) * (d.r[j] >> 24) * 255.0;
         }
-        if (bound >= 16777216.0) fast = false;
+        if (bound >= 16777216.0 || d.w[0] != -1.f) fast = false;
     }
     tp->fast = fast ? 1 : 0;
     auto off = [&](int dx, int dy) { return 4u * (uint32_t)(ystep == 2 ? (dx & 1) * ps + dy * cp + (dx >> 1) : dy * cp + dx); };
     auto f2u = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    struct Corners { uint32_t a, b, c, d; bool eq(const Corners &o, int i) const { return (&a)[i] == (&o.a)[i]; } };
+    auto corners = [&](uint32_t r) {
+        int x = r & 255, y = (r >> 8) & 255, w = (r >> 16) & 255, h = r >> 24;
+        return Corners{off(x, y), off(x + w, y), off(x, y + h), off(x + w, y + h)};
+    };
+    // sharing pattern of a two-rect feature: 0 none, 1 left half, 2 right half, 3 top half, 4 bottom half
+    auto pattern = [&](const DevStump &d) {
+        if (d.w[2] != 0.f) return 0;
+        Corners p = corners(d.r[0]), q = corners(d.r[1]);
+        bool e[4] = {p.eq(q, 0), p.eq(q, 1), p.eq(q, 2), p.eq(q, 3)};
+        if (e[0] && e[2] && !e[1] && !e[3]) return 1;
+        if (e[1] && e[3] && !e[0] && !e[2]) return 2;
+        if (e[0] && e[1] && !e[2] && !e[3]) return 3;
+        if (e[2] && e[3] && !e[0] && !e[1]) return 4;
+        return 0;
+    };
     int n = 0;
     for (int s = 1; s < stage_end; s++) {
         int si = s - 1;
         tp->stage_first[si] = n;
         tp->stage_thr[si] = m.stage_thr[s];
+        tp->stage_mid6[si] = tp->stage_mid[si] = n;
         double rsum = 0;
-        // FAST: two-rect classifiers first, then three-rect ones; otherwise XML order with mid == first
-        for (int pass = 0; pass < (fast ? 2 : 1); pass++) {
-            if (pass == 1 || !fast) tp->stage_mid[si] = fast ? n : tp->stage_first[si];
+        // FAST: group 0 = six-load two-rect, 1 = eight-load two-rect, 2 = three-rect; otherwise XML order in one group
+        for (int grp = 0; grp < (fast ? 3 : 1); grp++) {
             for (int k = m.stage_first[s]; k < m.stage_first[s + 1]; k++) {
                 const DevStump &d = c->stumps[k];
                 bool three = d.w[2] != 0.f;
-                if (fast && three != (pass == 1)) continue;
+                int pat = pattern(d);
+                if (fast && (three ? 2 : (pat ? 0 : 1)) != grp) continue;
                 BulkStump &b = tp->s[n];
-                uint4 o[3];
-                for (int j = 0; j < 3; j++) {
-                    uint32_t r = three || j < 2 ? d.r[j] : d.r[0];
-                    int x = r & 255, y = (r >> 8) & 255, w = (r >> 16) & 255, h = r >> 24;
-                    o[j] = make_uint4(off(x, y), off(x + w, y), off(x, y + h), off(x + w, y + h));
-                }
-                b.o0 = o[0]; b.o1 = o[1]; tp->o2[n] = o[2];
+                Corners p = corners(d.r[0]), q = corners(d.r[1]), t = corners(three ? d.r[2] : d.r[0]);
+                b.o0 = make_uint4(p.a, p.b, p.c, p.d); b.o1 = make_uint4(q.a, q.b, q.c, q.d); tp->o2[n] = make_uint4(t.a, t.b, t.c, t.d);
+                if (fast && pat == 1) { b.o0 = make_uint4(p.a, p.c, p.b, p.d); b.o1 = make_uint4(q.b, q.d, 0, 0); }
+                if (fast && pat == 2) { b.o0 = make_uint4(p.d, p.b, p.c, p.a); b.o1 = make_uint4(q.c, q.a, 0, 0); }
+                if (fast && pat == 3) { b.o0 = make_uint4(p.a, p.b, p.c, p.d); b.o1 = make_uint4(q.c, q.d, 0, 0); }
+                if (fast && pat == 4) { b.o0 = make_uint4(p.d, p.c, p.b, p.a); b.o1 = make_uint4(q.b, q.a, 0, 0); }
                 if (fast) { b.w0 = (uint32_t)(int)d.w[0]; b.w1 = (uint32_t)(int)d.w[1]; b.w2 = (uint32_t)(int)d.w[2]; }
                 else { b.w0 = f2u(d.w[0]); b.w1 = f2u(d.w[1]); b.w2 = f2u(d.w[2]); }
                 b.thr = f2u(d.thr); b.left = f2u(d.left); b.right = f2u(d.right);
-                double dd = (double)d.left - (double)d.right;
+                double dd = 128.0 * ((double)d.left - (double)d.right);          // see add_if_lt
                 uint64_t u; memcpy(&u, &dd, 8);
                 b.d_lo = (uint32_t)u; b.d_hi = (uint32_t)(u >> 32);
                 rsum += (double)d.right;
                 n++;
             }
+            if (grp == 0 && fast) tp->stage_mid6[si] = n;
+            if (grp == 1 && fast) tp->stage_mid[si] = n;
         }
         tp->stage_base[si] = rsum;
     }
