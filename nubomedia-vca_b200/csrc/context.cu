@@ -59,6 +59,7 @@ extern "C" int nv_cascade_load(const char *xml_path, nv_cascade **out)
         }
         d.thr = h.stump_thr[i]; d.left = h.stump_left[i]; d.right = h.stump_right[i];
     }
+    build_tail_stumps(c);
     *out = c;
     return NV_OK;
 }
@@ -117,6 +118,14 @@ static int cascade_on_device(nv_cascade *c, int gpu, cudaStream_t st, const DevS
         NV_CUDA(cudaMemcpy(ds, c->stumps.data(), c->stumps.size() * sizeof(DevStump), cudaMemcpyHostToDevice));
         NV_CUDA(cudaMemcpy(dm, &c->meta, sizeof(DevCascade), cudaMemcpyHostToDevice));
         c->d_stumps[gpu] = ds; c->d_meta[gpu] = dm;
+        if (c->tail_fast) {
+            TailStump *dt = nullptr; double *db = nullptr;
+            NV_CUDA(cudaMalloc(&dt, c->tail_stumps.size() * sizeof(TailStump)));
+            NV_CUDA(cudaMalloc(&db, c->tail_base.size() * sizeof(double)));
+            NV_CUDA(cudaMemcpy(dt, c->tail_stumps.data(), c->tail_stumps.size() * sizeof(TailStump), cudaMemcpyHostToDevice));
+            NV_CUDA(cudaMemcpy(db, c->tail_base.data(), c->tail_base.size() * sizeof(double), cudaMemcpyHostToDevice));
+            c->d_tail[gpu] = dt; c->d_tail_base[gpu] = db;
+        }
     }
     *stumps = c->d_stumps[gpu]; *meta = c->d_meta[gpu];
     (void)st;
@@ -478,6 +487,11 @@ static int detect_prepare(nv_ctx *ctx, nv_cascade *casc, int W, int H, const nv_
     int rc = ensure_plan(ctx, casc, W, H, p);
     if (rc != NV_OK) return rc;
     if ((rc = cascade_on_device(casc, ctx->gpu, ctx->stream, &ctx->cur_stumps, &ctx->cur_meta)) != NV_OK) return rc;
+    ctx->cur_tail = nullptr; ctx->cur_tail_base = nullptr;
+    if (casc->tail_fast) {
+        std::lock_guard<std::mutex> lk(casc->mu);
+        ctx->cur_tail = casc->d_tail[ctx->gpu]; ctx->cur_tail_base = casc->d_tail_base[ctx->gpu];
+    }
     if ((rc = ensure_tile_params(ctx, casc)) != NV_OK) return rc;
     if (p->min_neighbors > 0 && ctx->adj_cap < (size_t)ctx->cand_cap) {      // grown earlier for an ungrouped call
         NV_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -528,7 +542,12 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
                 nl++;
             }
             prof_mark(ctx, 6);
-            if (ctx->bulk_end < casc->meta.nstages) {
+            if (ctx->bulk_end < casc->meta.nstages && ctx->cur_tail) {
+                NV_CUDA(launch_cascade_tail_fast(ctx->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
+                                                 ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, ctx->bulk_end, st,
+                                                 8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));
+                nl++;
+            } else if (ctx->bulk_end < casc->meta.nstages) {
                 NV_CUDA(launch_cascade_tail(ctx->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
                                             ctx->cand_cap, depth, ctx->bulk_end, casc->h.order_free, 148 * 8, st,
                                             8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));

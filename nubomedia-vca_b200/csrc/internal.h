@@ -59,13 +59,30 @@ struct DevCascade {
     float stage_thr[NV_MAX_STAGES];       // (float)xml - 1e-5f
 };
 
+// One weak classifier as k_cascade_tail_fast reads it (one lane per classifier): corner BYTE offsets into the window's
+// private (win_h+1) x (win_w+1) integral patch, integer weights, 128 * (left - right).  Inside a stage the two-rect
+// classifiers come first.  Only built when the cascade holds the exactness certificates (nv_cascade::tail_fast).
+struct __align__(16) TailStump {
+    uint16_t o[12];     // rect 0: a, b, c, d; rect 1; rect 2 (unused for two-rect features)
+    float thr;
+    int16_t w1, w2;     // w0 is -1
+    double d128;
+    uint32_t pad[2];
+};
+static_assert(sizeof(TailStump) == 48, "three 16-byte loads");
+
 struct nv_cascade {
     HostCascade h;
     std::vector<DevStump> stumps;
     DevCascade meta;
+    int tail_fast = 0;                    // order-free sums + exact integer features for EVERY stage (see fill_bulk_stumps)
+    std::vector<TailStump> tail_stumps;
+    std::vector<double> tail_base;        // per stage: sum of the right leaves
     std::mutex mu;
     std::map<int, DevStump *> d_stumps;   // per GPU ordinal
     std::map<int, DevCascade *> d_meta;
+    std::map<int, TailStump *> d_tail;
+    std::map<int, double *> d_tail_base;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -235,6 +252,7 @@ struct nv_ctx {
         }
     };
     const DevStump *cur_stumps = nullptr;  const DevCascade *cur_meta = nullptr;   // device copies of the cascade in use
+    const TailStump *cur_tail = nullptr;  const double *cur_tail_base = nullptr;
     cudaGraphExec_t gexec = nullptr;  GraphKey gkey, gkey_seen;  int g_nl = 0;  bool no_graph = false;
     unsigned long long epoch = 1;     // bumped whenever a buffer the pipeline binds is re-allocated or re-planned
 
@@ -295,6 +313,10 @@ cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, con
 cudaError_t launch_alive_to_queue(const PlanDev *plan, int total_rows, const float *vnf, const uint32_t *bits_alive,
                                   uint2 *queue, int *counters, int queue_cap, cudaStream_t st);
 void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_end, TileParams *tp);
+void build_tail_stumps(nv_cascade *c);
+cudaError_t launch_cascade_tail_fast(const PlanDev *plan, const DevCascade *meta, const TailStump *tstumps, const double *tbase,
+                                     const uint32_t *sum, const uint2 *tail, int *counters, uint32_t *cand, int cand_cap,
+                                     int16_t *depth, int stage_begin, cudaStream_t st, int smem_bytes);
 
 // context.cu internals shared with elements.cu
 int nv_detect_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W, int H, int gstride, const uint8_t *d_lut,

@@ -663,6 +663,128 @@ k_cascade_tail(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_cascade_tail_fast: k_cascade_tail for cascades with the exactness certificates.  One warp per window, one lane per
+// weak classifier of the stage, records prefetched one round ahead, integer feature arithmetic, the stage sum as
+// base + sum of (left - right) over the lanes below threshold (DFMA, see add_if_lt) reduced by shuffles.
+// ------------------------------------------------------------------------------------------------
+struct TailRec { uint4 a, b, c; };
+__device__ __forceinline__ TailRec load_tail(const TailStump *__restrict__ t, int k)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(t + k);
+    return TailRec{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+}
+
+__global__ void __launch_bounds__(256)
+k_cascade_tail_fast(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ meta, const TailStump *__restrict__ ts,
+                    const double *__restrict__ tbase, const uint32_t *__restrict__ sum, const uint2 *__restrict__ tail,
+                    int *__restrict__ counters, uint32_t *__restrict__ cand, int cand_cap, int16_t *__restrict__ depth,
+                    int stage_begin)
+{
+    extern __shared__ uint32_t s_win[];                          // 8 warps x (win_h+1) x (win_w+1) words
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = counters[3], nstages = meta->nstages, nstumps = meta->nstumps;
+    const int ww = plan->win_w, wh = plan->win_h, LP = ww + 1, npatch = (wh + 1) * LP;
+    uint32_t *win = s_win + warp * npatch;
+    const uint32_t wsa = smem_u32(win);
+    for (;;) {                                                   // windows are handed out one at a time: depths are very uneven
+        int e = 0;
+        if (lane == 0) e = atomicAdd(&counters[5], 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= n) break;
+        uint2 q = tail[e];
+        int l = q.x >> 26, iy = (q.x >> 13) & 8191, ix = q.x & 8191;
+        float vnf = __uint_as_float(q.y);
+        const LevelDesc &L = plan->lv[l];
+        const uint32_t *wb = sum + L.iofs + (size_t)iy * L.ystep * L.ipitch + ix;
+        int k0 = meta->stage_first[stage_begin];
+        TailRec rec = load_tail(ts, min(k0 + lane, nstumps - 1));
+        __syncwarp();
+        for (int c = lane; c <= ww; c += 32) {                   // private copy of the window's integral patch, row by row
+            int pc = L.ystep == 2 ? (c & 1) * L.iplane + (c >> 1) : c;
+            for (int r = 0; r <= wh; r++) win[r * LP + c] = __ldg(wb + (size_t)r * L.ipitch + pc);
+        }
+        __syncwarp();
+        int code = NV_DEPTH_PASS;
+        for (int st = stage_begin; st < nstages; st++) {
+            int k1 = meta->stage_first[st + 1];
+            double tmp = 0.;
+            for (int kb = k0; kb < k1; kb += 32) {               // 32 weak classifiers per round, one per lane
+                TailRec cur = rec;
+                int nk = (kb + 32 < k1 ? kb + 32 : k1) + lane;   // next round: same stage, or the head of the next one
+                rec = load_tail(ts, min(nk, nstumps - 1));
+                if (kb + lane < k1) {
+#define TW(o) lds_u32(wsa + (o))
+                    int nr0 = (int)(TW(cur.a.x >> 16) + TW(cur.a.y & 0xffffu) - TW(cur.a.x & 0xffffu) - TW(cur.a.y >> 16));
+                    int r1 = (int)(TW(cur.a.z & 0xffffu) - TW(cur.a.z >> 16) - TW(cur.a.w & 0xffffu) + TW(cur.a.w >> 16));
+                    int w12 = (int)cur.b.w;
+                    int r = (int)(short)(w12 & 0xffff) * r1 + nr0;
+                    if (w12 >> 16) {
+                        int r2 = (int)(TW(cur.b.x & 0xffffu) - TW(cur.b.x >> 16) - TW(cur.b.y & 0xffffu) + TW(cur.b.y >> 16));
+                        r += (w12 >> 16) * r2;
+                    }
+#undef TW
+                    add_if_lt(tmp, __fmul_rn(__int2float_rn(r), vnf), __uint_as_float(cur.b.z),
+                              __hiloint2double((int)cur.c.y, (int)cur.c.x));
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) tmp = __dadd_rn(tmp, __shfl_xor_sync(0xffffffffu, tmp, d));
+            k0 = k1;
+            if (__dadd_rn(tbase[st], tmp) < (double)meta->stage_thr[st]) { code = -st; break; }
+        }
+        if (lane == 0) {
+            if (depth) depth[L.wofs + iy * L.nx + ix] = (int16_t)code;
+            if (code == NV_DEPTH_PASS) {
+                int pos = atomicAdd(&counters[1], 1);
+                if (pos < cand_cap) cand[pos] = q.x;
+                else counters[2] = 1;
+            }
+        }
+    }
+}
+
+// host: the TailStump table and the certificate over every stage (same conditions as fill_bulk_stumps' FAST variant)
+void build_tail_stumps(nv_cascade *c)
+{
+    const DevCascade &m = c->meta;
+    bool fast = c->h.order_free != 0 && m.win_w <= 32 && m.win_h <= 32;
+    for (int k = 0; k < m.nstumps && fast; k++) {
+        const DevStump &d = c->stumps[k];
+        double bound = 0;
+        for (int j = 0; j < 3; j++) {
+            if (d.w[j] != rintf(d.w[j]) || fabsf(d.w[j]) > 4096.f) fast = false;
+            bound += fabs((double)d.w[j]) * ((d.r[j] >> 16) & 255) * (d.r[j] >> 24) * 255.0;
+        }
+        if (bound >= 16777216.0 || d.w[0] != -1.f) fast = false;
+    }
+    c->tail_fast = fast ? 1 : 0;
+    if (!fast) return;
+    const int LP = m.win_w + 1;
+    c->tail_stumps.clear(); c->tail_base.assign(m.nstages, 0.0);
+    for (int s = 0; s < m.nstages; s++) {
+        double rsum = 0;
+        for (int grp = 0; grp < 2; grp++)
+            for (int k = m.stage_first[s]; k < m.stage_first[s + 1]; k++) {
+                const DevStump &d = c->stumps[k];
+                if ((d.w[2] != 0.f) != (grp == 1)) continue;
+                TailStump t;
+                memset(&t, 0, sizeof t);
+                for (int j = 0; j < 3; j++) {
+                    uint32_t r = (j < 2 || d.w[2] != 0.f) ? d.r[j] : d.r[0];
+                    int x = r & 255, y = (r >> 8) & 255, w = (r >> 16) & 255, h = r >> 24;
+                    t.o[4 * j + 0] = (uint16_t)(4 * (y * LP + x));       t.o[4 * j + 1] = (uint16_t)(4 * (y * LP + x + w));
+                    t.o[4 * j + 2] = (uint16_t)(4 * ((y + h) * LP + x)); t.o[4 * j + 3] = (uint16_t)(4 * ((y + h) * LP + x + w));
+                }
+                t.thr = d.thr; t.w1 = (int16_t)d.w[1]; t.w2 = (int16_t)d.w[2];
+                t.d128 = 128.0 * ((double)d.left - (double)d.right);
+                rsum += (double)d.right;
+                c->tail_stumps.push_back(t);
+            }
+        c->tail_base[s] = rsum;
+    }
+}
+
 // host: bulk-stage weak classifiers with shared-memory corner BYTE offsets for one ystep class, plus the
 // certificates of the FAST variant:
 //   order-free — cascade_xml.cpp proves that no addition of a stage's leaves can round in double, so any order and the
@@ -807,6 +929,15 @@ cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, con
     (void)nblocks;
     k_cascade_tail<<<148 * 8, 256, smem_bytes, st>>>(plan, meta, stumps, sum, tail, counters, cand, cand_cap, depth, stage_begin,
                                                      order_free);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cascade_tail_fast(const PlanDev *plan, const DevCascade *meta, const TailStump *tstumps, const double *tbase,
+                                     const uint32_t *sum, const uint2 *tail, int *counters, uint32_t *cand, int cand_cap,
+                                     int16_t *depth, int stage_begin, cudaStream_t st, int smem_bytes)
+{
+    k_cascade_tail_fast<<<148 * 8, 256, smem_bytes, st>>>(plan, meta, tstumps, tbase, sum, tail, counters, cand, cand_cap, depth,
+                                                          stage_begin);
     return cudaGetLastError();
 }
 
