@@ -439,14 +439,19 @@ def main():
             tj = json.load(open(tpath))
             traffic = tj.get("cascade_dram_bytes_per_frame")
             wf = tj.get("tile_shared_wavefronts_per_frame")
-            if wf and iso.get("cascade_tiles", 0) > 0:
-                # what actually bounds the dominant kernel: shared-memory wavefronts (128 B each) of the tile kernels
-                smem_peak = 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
-                ach = wf * 128 / (iso["cascade_tiles"] * 1e-3) / 1e12
-                onchip = {"bound": "shared-memory pipe (LSU wavefronts)", "achieved": ach, "peak": smem_peak, "unit": "TB/s",
-                          "frac": ach / smem_peak, "wavefronts_per_frame": wf,
-                          "conflict_replays_per_frame": tj.get("tile_shared_bank_conflict_wavefronts_per_frame"),
-                          "source": "wavefront counts from profiles/traffic.json (ncu), time = stage_ms_isolated.cascade_tiles"}
+            wi = tj.get("tile_warp_instructions_per_frame")
+            if wf and wi and iso.get("cascade_tiles", 0) > 0:
+                # what actually bounds the dominant kernel (k_cascade_classes): warp-instruction issue (4 per SM and
+                # clock) first, the shared-memory pipe (one 128-byte wavefront per SM and clock) second
+                clk = (clocks.get("sm_max_mhz") or 1965.0) * 1e6
+                t = iso["cascade_tiles"] * 1e-3
+                onchip = {"bound": "instruction issue", "achieved": wi / t / 1e9, "peak": 148 * 4 * clk / 1e9,
+                          "unit": "G warp-instructions/s", "frac": wi / t / (148 * 4 * clk),
+                          "warp_instructions_per_frame": wi,
+                          "shared_memory": {"achieved": wf * 128 / t / 1e12, "peak": 148 * 128 * clk / 1e12, "unit": "TB/s",
+                                            "frac": wf / t / (148 * clk), "wavefronts_per_frame": wf,
+                                            "conflict_replays_per_frame": tj.get("tile_shared_bank_conflict_wavefronts_per_frame")},
+                          "source": "counts from profiles/traffic.json (ncu), time = stage_ms_isolated.cascade_tiles"}
         casc_ms = med.get("cascade_stage0", 0) + med.get("cascade_tiles", 0) + med.get("cascade_tail", 0)
         frame_ms = sum(med.values())
         achieved = ab["cascade"] / (casc_ms * 1e-3) / 1e9 if casc_ms > 0 else None
@@ -463,15 +468,16 @@ def main():
                     "d2h_bytes_per_step": B * (16 + 1024 * 16), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "cascade (k_stage0_rows + k_cascade_tiles<2> + k_cascade_tiles<1> + k_cascade_tail)",
+            "roofline": {"bound": "hbm", "kernel": "cascade (k_stage0_rows_p + k_cascade_classes<2> + k_cascade_classes<1> + k_cascade_tail_fast)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms_isolated": iso_casc,
                          "achieved_isolated": ab["cascade"] / (iso_casc * 1e-3) / 1e9 if iso_casc > 0 else None,
                          "note": "kernel_ms is the median CUDA-event time inside the timed region, where the other "
                                  "contexts' kernels interleave on the GPU; kernel_ms_isolated is the same stage with one "
-                                 "stream in flight.  The cascade re-reads integral patches from shared memory, so its "
-                                 "HBM fraction is small by construction (DESIGN.md §4).",
+                                 "stream in flight.  The cascade re-reads integral patches from shared memory and is "
+                                 "bound by instruction issue, so its HBM fraction is small by construction (DESIGN.md §4); "
+                                 "`onchip` is the roofline that binds it.",
                          "algorithmic_bytes_per_launch": ab["cascade"], "kernel_ms": casc_ms,
                          "frame_algorithmic_bytes": ab["frame_total"], "frame_kernel_ms": frame_ms,
                          "frame_frac": ab["frame_total"] / (frame_ms * 1e-3) / 1e9 / peak if frame_ms > 0 else None},

@@ -52,13 +52,17 @@ NV_API int nv_device_count(void);                       /* 0 when no CUDA device
 
 /* ---- cascade model: replaces cv::CascadeClassifier::load (kmsfacedetect.cpp:163-177,
  *      kmseyedetect.cpp:171-183, kmsmouthdetect.cpp:157-163, kmsnosedetect.cpp:166-172,
- *      kmseardetect.cpp:173-186).  Host-side parse only; usable without a GPU. ---------------- */
+ *      kmseardetect.cpp:173-186).  Host-side parse only; usable without a GPU.  BOOST/HAAR cascades in
+ *      the new or the OpenCV 1.x/2.x XML layout: stumps or trees, upright or tilted features. -- */
 typedef struct {
     int win_w, win_h;        /* training window                                   */
     int nstages, nstumps;    /* boosted stages / weak classifiers (stumps)        */
     int nfeatures;           /* Haar features (<= 3 rects each)                   */
     int n3rect;              /* features that use the third rectangle             */
     int order_free_sums;     /* 1: every stage sum is exact in double in any order */
+    int general;             /* 1: trees of more than one node and/or tilted features (OpenCV's predictOrdered path) */
+    int has_tilted;          /* 1: some feature is evaluated on the tilted integral */
+    int nnodes;              /* internal tree nodes over all weak classifiers (== nstumps for stump cascades) */
 } nv_cascade_info;
 
 NV_API int nv_cascade_load(const char *xml_path, nv_cascade **out);
@@ -220,11 +224,18 @@ typedef struct {
 NV_API int nv_debug_cascade_stage(const nv_cascade *c, int stage, int *ntrees, float *threshold_used);
 NV_API int nv_debug_cascade_stump(const nv_cascade *c, int stump, int rects12[12], float weights3[3],
                                   float thr_left_right[3]);
+/* weak classifier `tree` of any cascade: internal nodes in file order (feature index, child on "<", child otherwise;
+ * child > 0: node of the tree, <= 0: leaf -child), node thresholds, nnodes + 1 leaves; feature f: 12 rect ints,
+ * 3 weights, tilted flag. */
+NV_API int nv_debug_cascade_tree(const nv_cascade *c, int tree, int cap_nodes, int *nnodes, int *feat_left_right,
+                                 float *node_thr, float *leaves);
+NV_API int nv_debug_cascade_feature(const nv_cascade *c, int feature, int rects12[12], float weights3[3], int *tilted);
 
 NV_API int nv_debug_num_levels(nv_ctx *ctx);
 NV_API int nv_debug_level_info(nv_ctx *ctx, int level, nv_level_info *info);
 NV_API int nv_debug_get_gray(nv_ctx *ctx, uint8_t *dst, int cap_bytes, int *width, int *height);
 NV_API int nv_debug_get_integral(nv_ctx *ctx, int level, int32_t *sum, uint32_t *sqsum);     /* (h+1)*(w+1) each */
+NV_API int nv_debug_get_tilted(nv_ctx *ctx, int level, int32_t *tilted);                      /* (h+1)*(w+1); cascades with tilted features */
 NV_API int nv_debug_get_depth_map(nv_ctx *ctx, int level, int16_t *depth);                    /* ny*nx           */
 NV_API int nv_debug_get_candidates(nv_ctx *ctx, nv_rect *out, int cap, int *n);               /* raw, canonical order */
 /* counters of the last call: [0] windows visited, [1] windows alive after stage 0,

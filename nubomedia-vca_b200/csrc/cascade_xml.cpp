@@ -2,7 +2,7 @@
 // reference elements pass to cv::CascadeClassifier::load (kmsfacedetect.cpp:40,163-177;
 // kmseyedetect.cpp:27-29,171-183; kmsmouthdetect.cpp:37-38; kmsnosedetect.cpp:31-32;
 // kmseardetect.cpp:29-31).  Host-only; no OpenCV, no libxml: the grammar is small enough for a
-// purpose-built tokenizer.  Supports HAAR features, upright rectangles, depth-1 trees (stumps).
+// purpose-built tokenizer.  Supports BOOST/HAAR cascades: stumps or trees, upright or tilted rectangles.
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -112,12 +112,73 @@ bool parse_floats(const std::string &s, std::vector<double> &out)
     }
 }
 
-static int finish_cascade(HostCascade *hc)
+// One weak classifier as parsed: internal nodes in file order and nnodes + 1 leaves.
+struct ParsedTree {
+    struct N { int feat; float thr; int left, right; };
+    std::vector<N> nodes;
+    std::vector<float> leaves;
+};
+
+static int parse_rects(const Node *rects, bool tilted, int win_w, int win_h, const char *path, int r[12], float w[3])
 {
+    std::vector<double> v;
+    int k = 0;
+    for (auto &rc : rects->kids) {
+        if (k >= 3 || !parse_floats(rc->text, v) || v.size() != 5) { nv_set_error("%s: malformed feature rectangle", path); return NV_ERR_FORMAT; }
+        for (int i = 0; i < 4; i++) r[4 * k + i] = (int)v[i];
+        w[k] = (float)v[4];
+        int x = r[4 * k], y = r[4 * k + 1], ww = r[4 * k + 2], hh = r[4 * k + 3];
+        // upright: the rect lies in the window.  tilted (x, y, w, h): the corners (x - h, y + h), (x + w, y + w) and
+        // (x + w - h, y + w + h) of the rotated rect must be elements of the window's tilted integral.
+        bool ok = x >= 0 && y >= 0 && ww > 0 && hh > 0 &&
+                  (tilted ? (x - hh >= 0 && x + ww <= win_w && y + ww + hh <= win_h) : (x + ww <= win_w && y + hh <= win_h));
+        if (!ok) { nv_set_error("%s: feature rectangle outside the window", path); return NV_ERR_FORMAT; }
+        k++;
+    }
+    if (k < 2) { nv_set_error("%s: feature with fewer than two rects", path); return NV_ERR_FORMAT; }
+    return NV_OK;
+}
+
+static int finish_cascade(HostCascade *hc, const std::vector<ParsedTree> &trees, const char *path)
+{
+    int nfeat = (int)hc->feat_weight.size() / 3;
+    hc->general = 0;
+    for (uint8_t t : hc->feat_tilted) if (t) { hc->general = 1; hc->has_tilted = 1; }
+    for (const ParsedTree &t : trees) {
+        int nn = (int)t.nodes.size();
+        if (nn < 1 || (int)t.leaves.size() != nn + 1) { nv_set_error("%s: malformed weak classifier", path); return NV_ERR_FORMAT; }
+        if (nn != 1) hc->general = 1;
+        for (const auto &n : t.nodes) {
+            if (n.feat < 0 || n.feat >= nfeat) { nv_set_error("%s: feature index out of range", path); return NV_ERR_FORMAT; }
+            for (int c : {n.left, n.right})
+                if (c >= nn || -c > nn) { nv_set_error("%s: tree child index out of range", path); return NV_ERR_FORMAT; }
+        }
+        // a child index must point forward, or the walk could loop for ever
+        for (int i = 0; i < nn; i++)
+            for (int c : {t.nodes[i].left, t.nodes[i].right})
+                if (c > 0 && c <= i) { nv_set_error("%s: tree child index points backwards", path); return NV_ERR_FORMAT; }
+        if (nn == 1 && (t.nodes[0].left != 0 || t.nodes[0].right != -1)) hc->general = 1;
+    }
+    for (const ParsedTree &t : trees) {
+        hc->tree_nnodes.push_back((int)t.nodes.size());
+        for (const auto &n : t.nodes) {
+            hc->node_feat.push_back(n.feat); hc->node_thr.push_back(n.thr);
+            hc->node_left.push_back(n.left); hc->node_right.push_back(n.right);
+        }
+        hc->leaves.insert(hc->leaves.end(), t.leaves.begin(), t.leaves.end());
+        // the stump arrays stay index-compatible with the weak classifiers; they are only meaningful when !general
+        hc->stump_feat.push_back(t.nodes[0].feat);
+        hc->stump_thr.push_back(t.nodes[0].thr);
+        hc->stump_left.push_back(t.leaves[0]);
+        hc->stump_right.push_back(t.leaves[1]);
+    }
+    for (size_t f = 0; f < hc->feat_weight.size() / 3; f++)
+        if (hc->feat_weight[3 * f + 2] != 0.f) hc->n3rect++;
+
     // Exactness certificate for parallel stage sums: OpenCV adds the float leaves one by one into a
     // double.  If, for every stage, (sum of |leaf|) / (smallest unit-in-last-place of any leaf) fits in
-    // 2^52, no addition can round, so any summation order gives the same double.
-    hc->order_free = 1;
+    // 2^52, no addition can round, so any summation order gives the same double.  (Stump cascades only.)
+    hc->order_free = hc->general ? 0 : 1;
     size_t si = 0;
     for (int nt : hc->stage_ntrees) {
         double mag = 0, min_ulp = INFINITY;
@@ -155,11 +216,13 @@ int nv_parse_cascade_xml(const char *path, HostCascade *hc)
     }
     const Node *c = root->child("cascade");
     std::vector<double> v;
+    std::vector<ParsedTree> trees;
     if (!c) {
         // OpenCV 1.x/2.x "opencv-haar-classifier" layout — what /usr/share/opencv/haarcascades held on the OpenCV 2.4
         // systems the reference was deployed on.  OpenCV >= 3 converts it to the new layout on load and evaluates
         // it identically (checked against cv2 4.13 in tests/test_oracle_vs_cv2.py), so it maps onto the same model:
-        // one feature per tree node, <left_val>/<right_val> leaves.
+        // one feature per tree node in file order; a <left_val>/<right_val> becomes the next leaf of its tree, a
+        // <left_node>/<right_node> the index of the child node.
         const Node *o = nullptr;
         for (auto &k : root->kids)
             if (k->child("stages") && k->child("size")) { o = k.get(); break; }
@@ -168,45 +231,42 @@ int nv_parse_cascade_xml(const char *path, HostCascade *hc)
         hc->win_w = (int)v[0]; hc->win_h = (int)v[1];
         if (hc->win_w < 3 || hc->win_h < 3 || hc->win_w > 255 || hc->win_h > 255) { nv_set_error("%s: window out of range", path); return NV_ERR_FORMAT; }
         for (auto &st : o->child("stages")->kids) {
-            const Node *trees = st->child("trees");
-            if (!trees || !parse_floats(st->child_text("stage_threshold"), v) || v.size() != 1) { nv_set_error("%s: malformed stage", path); return NV_ERR_FORMAT; }
+            const Node *tr = st->child("trees");
+            if (!tr || !parse_floats(st->child_text("stage_threshold"), v) || v.size() != 1) { nv_set_error("%s: malformed stage", path); return NV_ERR_FORMAT; }
             hc->stage_thr.push_back((float)v[0]);
             int nt = 0;
-            for (auto &tree : trees->kids) {
-                if (tree->kids.size() != 1) { nv_set_error("%s: tree weak classifiers (depth > 1) are not supported yet", path); return NV_ERR_UNSUPPORTED; }
-                const Node *node = tree->kids[0].get();
-                const Node *ft = node->child("feature");
-                if (!ft || !ft->child("rects") || !node->child("left_val") || !node->child("right_val")) {
-                    nv_set_error("%s: malformed or non-stump tree node", path);
-                    return node->child("left_node") || node->child("right_node") ? NV_ERR_UNSUPPORTED : NV_ERR_FORMAT;
-                }
-                if (atoi(ft->child_text("tilted").c_str()) != 0) { nv_set_error("%s: tilted features are not supported yet", path); return NV_ERR_UNSUPPORTED; }
-                int r[12] = {0};
-                float w[3] = {0, 0, 0};
-                int k = 0;
-                for (auto &rc : ft->child("rects")->kids) {
-                    if (k >= 3 || !parse_floats(rc->text, v) || v.size() != 5) { nv_set_error("%s: malformed feature rectangle", path); return NV_ERR_FORMAT; }
-                    for (int i = 0; i < 4; i++) r[4 * k + i] = (int)v[i];
-                    w[k] = (float)v[4];
-                    if (r[4 * k] < 0 || r[4 * k + 1] < 0 || r[4 * k + 2] <= 0 || r[4 * k + 3] <= 0 ||
-                        r[4 * k] + r[4 * k + 2] > hc->win_w || r[4 * k + 1] + r[4 * k + 3] > hc->win_h) {
-                        nv_set_error("%s: feature rectangle outside the window", path);
-                        return NV_ERR_FORMAT;
+            for (auto &tree : tr->kids) {
+                ParsedTree pt;
+                for (auto &nodep : tree->kids) {
+                    const Node *node = nodep.get();
+                    const Node *ft = node->child("feature");
+                    if (!ft || !ft->child("rects")) { nv_set_error("%s: malformed tree node", path); return NV_ERR_FORMAT; }
+                    bool tilted = atoi(ft->child_text("tilted").c_str()) != 0;
+                    int r[12] = {0};
+                    float w[3] = {0, 0, 0};
+                    int rc = parse_rects(ft->child("rects"), tilted, hc->win_w, hc->win_h, path, r, w);
+                    if (rc != NV_OK) return rc;
+                    std::vector<double> t;
+                    if (!parse_floats(node->child_text("threshold"), t) || t.size() != 1) { nv_set_error("%s: malformed tree node", path); return NV_ERR_FORMAT; }
+                    int child[2];
+                    const char *val[2] = {"left_val", "right_val"}, *nod[2] = {"left_node", "right_node"};
+                    for (int sd = 0; sd < 2; sd++) {
+                        std::vector<double> cv;
+                        if (node->child(val[sd])) {
+                            if (!parse_floats(node->child_text(val[sd]), cv) || cv.size() != 1) { nv_set_error("%s: malformed leaf", path); return NV_ERR_FORMAT; }
+                            child[sd] = -(int)pt.leaves.size();
+                            pt.leaves.push_back((float)cv[0]);
+                        } else if (node->child(nod[sd])) {
+                            if (!parse_floats(node->child_text(nod[sd]), cv) || cv.size() != 1) { nv_set_error("%s: malformed child index", path); return NV_ERR_FORMAT; }
+                            child[sd] = (int)cv[0];
+                        } else { nv_set_error("%s: tree node without children", path); return NV_ERR_FORMAT; }
                     }
-                    k++;
+                    pt.nodes.push_back({(int)hc->feat_weight.size() / 3, (float)t[0], child[0], child[1]});
+                    hc->feat_rect.insert(hc->feat_rect.end(), r, r + 12);
+                    hc->feat_weight.insert(hc->feat_weight.end(), w, w + 3);
+                    hc->feat_tilted.push_back(tilted ? 1 : 0);
                 }
-                if (k < 2) { nv_set_error("%s: feature with fewer than two rects", path); return NV_ERR_FORMAT; }
-                std::vector<double> t, l, rr;
-                if (!parse_floats(node->child_text("threshold"), t) || t.size() != 1 || !parse_floats(node->child_text("left_val"), l) ||
-                    l.size() != 1 || !parse_floats(node->child_text("right_val"), rr) || rr.size() != 1) {
-                    nv_set_error("%s: malformed tree node", path);
-                    return NV_ERR_FORMAT;
-                }
-                if (w[2] != 0.f) hc->n3rect++;
-                hc->stump_feat.push_back((int)hc->feat_weight.size() / 3);
-                hc->feat_rect.insert(hc->feat_rect.end(), r, r + 12);
-                hc->feat_weight.insert(hc->feat_weight.end(), w, w + 3);
-                hc->stump_thr.push_back((float)t[0]); hc->stump_left.push_back((float)l[0]); hc->stump_right.push_back((float)rr[0]);
+                trees.push_back(std::move(pt));
                 nt++;
             }
             if (nt == 0) { nv_set_error("%s: empty stage", path); return NV_ERR_FORMAT; }
@@ -216,7 +276,7 @@ int nv_parse_cascade_xml(const char *path, HostCascade *hc)
             nv_set_error("%s: %zu stages (supported: 1..%d)", path, hc->stage_ntrees.size(), NV_MAX_STAGES);
             return hc->stage_ntrees.empty() ? NV_ERR_FORMAT : NV_ERR_UNSUPPORTED;
         }
-        return finish_cascade(hc);
+        return finish_cascade(hc, trees, path);
     }
     if (!c->child("stages") || !c->child("features")) {
         nv_set_error("%s: incomplete cascade (no <stages>/<features>)", path);
@@ -246,18 +306,16 @@ int nv_parse_cascade_xml(const char *path, HostCascade *hc)
         int nt = 0;
         for (auto &wc : weak->kids) {
             std::vector<double> nodes, leaves;
-            if (!parse_floats(wc->child_text("internalNodes"), nodes) || !parse_floats(wc->child_text("leafValues"), leaves)) {
+            if (!parse_floats(wc->child_text("internalNodes"), nodes) || !parse_floats(wc->child_text("leafValues"), leaves) ||
+                nodes.empty() || nodes.size() % 4 != 0 || leaves.size() != nodes.size() / 4 + 1) {
                 nv_set_error("%s: malformed weak classifier", path);
                 return NV_ERR_FORMAT;
             }
-            if (nodes.size() != 4 || leaves.size() != 2 || nodes[0] != 0 || nodes[1] != -1) {
-                nv_set_error("%s: tree weak classifiers (depth > 1) are not supported yet", path);
-                return NV_ERR_UNSUPPORTED;
-            }
-            hc->stump_feat.push_back((int)nodes[2]);
-            hc->stump_thr.push_back((float)nodes[3]);
-            hc->stump_left.push_back((float)leaves[0]);
-            hc->stump_right.push_back((float)leaves[1]);
+            ParsedTree pt;
+            for (size_t i = 0; i < nodes.size(); i += 4)        // left right featureIdx threshold
+                pt.nodes.push_back({(int)nodes[i + 2], (float)nodes[i + 3], (int)nodes[i], (int)nodes[i + 1]});
+            for (double l : leaves) pt.leaves.push_back((float)l);
+            trees.push_back(std::move(pt));
             nt++;
         }
         if (nt == 0) { nv_set_error("%s: empty stage", path); return NV_ERR_FORMAT; }
@@ -270,35 +328,14 @@ int nv_parse_cascade_xml(const char *path, HostCascade *hc)
     for (auto &ft : c->child("features")->kids) {
         const Node *rects = ft->child("rects");
         if (!rects) { nv_set_error("%s: feature without rects", path); return NV_ERR_FORMAT; }
-        if (atoi(ft->child_text("tilted").c_str()) != 0) {
-            nv_set_error("%s: tilted features are not supported yet", path);
-            return NV_ERR_UNSUPPORTED;
-        }
+        bool tilted = atoi(ft->child_text("tilted").c_str()) != 0;
         int r[12] = {0};
         float w[3] = {0, 0, 0};
-        int k = 0;
-        for (auto &rc : rects->kids) {
-            if (k >= 3 || !parse_floats(rc->text, v) || v.size() != 5) {
-                nv_set_error("%s: malformed feature rectangle", path);
-                return NV_ERR_FORMAT;
-            }
-            for (int i = 0; i < 4; i++) r[4 * k + i] = (int)v[i];
-            w[k] = (float)v[4];
-            if (r[4 * k] < 0 || r[4 * k + 1] < 0 || r[4 * k + 2] <= 0 || r[4 * k + 3] <= 0 ||
-                r[4 * k] + r[4 * k + 2] > hc->win_w || r[4 * k + 1] + r[4 * k + 3] > hc->win_h) {
-                nv_set_error("%s: feature rectangle outside the window", path);
-                return NV_ERR_FORMAT;
-            }
-            k++;
-        }
-        if (k < 2) { nv_set_error("%s: feature with fewer than two rects", path); return NV_ERR_FORMAT; }
-        if (w[2] != 0.f) hc->n3rect++;
+        int rc = parse_rects(rects, tilted, hc->win_w, hc->win_h, path, r, w);
+        if (rc != NV_OK) return rc;
         hc->feat_rect.insert(hc->feat_rect.end(), r, r + 12);
         hc->feat_weight.insert(hc->feat_weight.end(), w, w + 3);
+        hc->feat_tilted.push_back(tilted ? 1 : 0);
     }
-    int nfeat = (int)hc->feat_weight.size() / 3;
-    for (int fi : hc->stump_feat)
-        if (fi < 0 || fi >= nfeat) { nv_set_error("%s: feature index out of range", path); return NV_ERR_FORMAT; }
-
-    return finish_cascade(hc);
+    return finish_cascade(hc, trees, path);
 }

@@ -71,6 +71,7 @@ extern "C" int nv_cascade_get_info(const nv_cascade *c, nv_cascade_info *info)
     info->nstages = (int)c->h.stage_ntrees.size(); info->nstumps = (int)c->h.stump_feat.size();
     info->nfeatures = (int)c->h.feat_weight.size() / 3; info->n3rect = c->h.n3rect;
     info->order_free_sums = c->h.order_free;
+    info->general = c->h.general; info->has_tilted = c->h.has_tilted; info->nnodes = (int)c->h.node_feat.size();
     return NV_OK;
 }
 
@@ -99,11 +100,46 @@ extern "C" int nv_debug_cascade_stump(const nv_cascade *c, int stump, int rects1
     return NV_OK;
 }
 
+extern "C" int nv_debug_cascade_tree(const nv_cascade *c, int tree, int cap_nodes, int *nnodes, int *feat_left_right,
+                                     float *node_thr, float *leaves)
+{
+    if (!c || tree < 0 || tree >= (int)c->h.tree_nnodes.size() || !nnodes) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    int n0 = 0, l0 = 0;
+    for (int t = 0; t < tree; t++) { n0 += c->h.tree_nnodes[t]; l0 += c->h.tree_nnodes[t] + 1; }
+    int nn = c->h.tree_nnodes[tree];
+    *nnodes = nn;
+    if (nn > cap_nodes) { nv_set_error("tree has %d nodes", nn); return NV_ERR_CAPACITY; }
+    for (int i = 0; i < nn; i++) {
+        if (feat_left_right) {
+            feat_left_right[3 * i] = c->h.node_feat[n0 + i]; feat_left_right[3 * i + 1] = c->h.node_left[n0 + i];
+            feat_left_right[3 * i + 2] = c->h.node_right[n0 + i];
+        }
+        if (node_thr) node_thr[i] = c->h.node_thr[n0 + i];
+    }
+    if (leaves) for (int i = 0; i <= nn; i++) leaves[i] = c->h.leaves[l0 + i];
+    return NV_OK;
+}
+
+extern "C" int nv_debug_cascade_feature(const nv_cascade *c, int feature, int rects12[12], float weights3[3], int *tilted)
+{
+    if (!c || feature < 0 || feature >= (int)c->h.feat_tilted.size() || !rects12 || !weights3) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    for (int i = 0; i < 12; i++) rects12[i] = c->h.feat_rect[(size_t)feature * 12 + i];
+    for (int i = 0; i < 3; i++) weights3[i] = c->h.feat_weight[(size_t)feature * 3 + i];
+    if (tilted) *tilted = c->h.feat_tilted[feature];
+    return NV_OK;
+}
+
 extern "C" void nv_cascade_free(nv_cascade *c)
 {
     if (!c) return;
     for (auto &kv : c->d_stumps) { cudaSetDevice(kv.first); cudaFree(kv.second); }
     for (auto &kv : c->d_meta) { cudaSetDevice(kv.first); cudaFree(kv.second); }
+    for (auto &kv : c->d_tail) { cudaSetDevice(kv.first); cudaFree(kv.second); }
+    for (auto &kv : c->d_tail_base) { cudaSetDevice(kv.first); cudaFree(kv.second); }
+    for (auto &kv : c->d_gen) {
+        cudaSetDevice(kv.first);
+        cudaFree((void *)kv.second.tree); cudaFree((void *)kv.second.node); cudaFree((void *)kv.second.leaf); cudaFree((void *)kv.second.feat);
+    }
     delete c;
 }
 
@@ -118,6 +154,38 @@ static int cascade_on_device(nv_cascade *c, int gpu, cudaStream_t st, const DevS
         NV_CUDA(cudaMemcpy(ds, c->stumps.data(), c->stumps.size() * sizeof(DevStump), cudaMemcpyHostToDevice));
         NV_CUDA(cudaMemcpy(dm, &c->meta, sizeof(DevCascade), cudaMemcpyHostToDevice));
         c->d_stumps[gpu] = ds; c->d_meta[gpu] = dm;
+        if (c->h.general) {
+            const HostCascade &h = c->h;
+            std::vector<int2> trees(h.tree_nnodes.size());
+            std::vector<int4> nodes(h.node_feat.size());
+            std::vector<GenFeat> feats(h.feat_tilted.size());
+            int n0 = 0, l0 = 0;
+            for (size_t t = 0; t < trees.size(); t++) { trees[t] = make_int2(n0, l0); n0 += h.tree_nnodes[t]; l0 += h.tree_nnodes[t] + 1; }
+            for (size_t i = 0; i < nodes.size(); i++) {
+                int tb; memcpy(&tb, &h.node_thr[i], 4);
+                nodes[i] = make_int4(h.node_feat[i], tb, h.node_left[i], h.node_right[i]);
+            }
+            for (size_t f = 0; f < feats.size(); f++) {
+                GenFeat &g = feats[f];
+                memset(&g, 0, sizeof g);
+                for (int k = 0; k < 3; k++) {
+                    const int *r = &h.feat_rect[f * 12 + 4 * k];
+                    g.r[k] = (uint32_t)r[0] | ((uint32_t)r[1] << 8) | ((uint32_t)r[2] << 16) | ((uint32_t)r[3] << 24);
+                    g.w[k] = h.feat_weight[f * 3 + k];
+                }
+                g.tilted = h.feat_tilted[f];
+            }
+            int2 *dtree = nullptr; int4 *dnode = nullptr; float *dleaf = nullptr; GenFeat *dfeat = nullptr;
+            NV_CUDA(cudaMalloc(&dtree, trees.size() * sizeof(int2)));
+            NV_CUDA(cudaMalloc(&dnode, nodes.size() * sizeof(int4)));
+            NV_CUDA(cudaMalloc(&dleaf, h.leaves.size() * sizeof(float)));
+            NV_CUDA(cudaMalloc(&dfeat, feats.size() * sizeof(GenFeat)));
+            NV_CUDA(cudaMemcpy(dtree, trees.data(), trees.size() * sizeof(int2), cudaMemcpyHostToDevice));
+            NV_CUDA(cudaMemcpy(dnode, nodes.data(), nodes.size() * sizeof(int4), cudaMemcpyHostToDevice));
+            NV_CUDA(cudaMemcpy(dleaf, h.leaves.data(), h.leaves.size() * sizeof(float), cudaMemcpyHostToDevice));
+            NV_CUDA(cudaMemcpy(dfeat, feats.data(), feats.size() * sizeof(GenFeat), cudaMemcpyHostToDevice));
+            c->d_gen[gpu] = GenModel{dtree, dnode, dleaf, dfeat};
+        }
         if (c->tail_fast) {
             TailStump *dt = nullptr; double *db = nullptr;
             NV_CUDA(cudaMalloc(&dt, c->tail_stumps.size() * sizeof(TailStump)));
@@ -211,7 +279,7 @@ extern "C" void nv_ctx_destroy(nv_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_frame); cudaFree(c->d_frame); cudaFree(c->d_gray); cudaFree(c->d_hist); cudaFree(c->d_lut);
     cudaFree(c->d_aux); for (auto &e : c->rtabs) cudaFree(e.d); cudaFree(c->d_plan); cudaFree(c->d_ptab); cudaFree(c->d_sum);
-    cudaFree(c->d_sq); cudaFree(c->d_pyr); cudaFree(c->d_vnf); cudaFree(c->d_depth);
+    cudaFree(c->d_sq); cudaFree(c->d_pyr); cudaFree(c->d_tilt); cudaFree(c->d_vnf); cudaFree(c->d_depth);
     cudaFree(c->d_bits_ok); cudaFree(c->d_queue); cudaFree(c->d_counters); cudaFree(c->d_cand);
     cudaFree(c->d_cand_sorted); cudaFree(c->d_cand_rects); cudaFree(c->d_adj); cudaFree(c->d_result);
     cudaFreeHost(c->h_result);
@@ -400,6 +468,12 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
             if ((rc = ensure(&ctx->d_depth, &ctx->depth_cap, (size_t)wofs)) != NV_OK) return rc;
             if ((rc = ensure(&ctx->d_pyr, &ctx->pyr_cap, (size_t)pofs)) != NV_OK) return rc;
         }
+        if (ctx->need_tilt) {
+            if ((rc = ensure(&ctx->d_tilt, &ctx->tilt_cap, ctx->integ_cap)) != NV_OK) return rc;
+            if ((rc = ensure(&ctx->d_pyr, &ctx->pyr_cap, (size_t)pofs)) != NV_OK) return rc;
+        }
+        ctx->max_lw = 0;
+        for (int l = 0; l < nl; l++) ctx->max_lw = std::max(ctx->max_lw, P.lv[l].lw);
     }
     NV_CUDA(cudaMemcpy(ctx->d_plan, &P, sizeof(PlanDev), cudaMemcpyHostToDevice));
     ctx->pkey = key;
@@ -434,9 +508,9 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
     ctx->tp_casc = casc;
     ctx->use_tiles = false;
     ctx->epoch++;
-    ctx->use_s0p = P.nlevels > 0 && fill_stage0_params(casc, P, &ctx->s0p);
+    ctx->use_s0p = !casc->h.general && P.nlevels > 0 && fill_stage0_params(casc, P, &ctx->s0p);
     encode_tiled_fn enc = get_encode_tiled();
-    if (!enc || m.win_w > 32 || m.win_h > 32 || P.nlevels == 0) return NV_OK;
+    if (casc->h.general || !enc || m.win_w > 32 || m.win_h > 32 || P.nlevels == 0) return NV_OK;
     // bulk stages: as many as fit the parameter bank
     int end = 1;
     while (end < m.nstages && end < NV_BULK_MAX_STAGES && m.stage_first[end + 1] - m.stage_first[1] <= NV_BULK_MAX_STUMPS) end++;
@@ -488,6 +562,23 @@ static int detect_prepare(nv_ctx *ctx, nv_cascade *casc, int W, int H, const nv_
     if (rc != NV_OK) return rc;
     if ((rc = cascade_on_device(casc, ctx->gpu, ctx->stream, &ctx->cur_stumps, &ctx->cur_meta)) != NV_OK) return rc;
     ctx->cur_tail = nullptr; ctx->cur_tail_base = nullptr;
+    ctx->use_gen = casc->h.general != 0;
+    if (ctx->use_gen) {
+        std::lock_guard<std::mutex> lk(casc->mu);
+        ctx->cur_gen = casc->d_gen[ctx->gpu];
+    }
+    if ((casc->h.has_tilted != 0) != ctx->need_tilt || (casc->h.has_tilted && ctx->tilt_cap < ctx->integ_cap)) {
+        // the tilted integral and the level images it is built from exist only while a cascade with tilted features is in use
+        NV_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->need_tilt = casc->h.has_tilted != 0;
+        if (ctx->need_tilt) {
+            if ((rc = ensure(&ctx->d_tilt, &ctx->tilt_cap, ctx->integ_cap)) != NV_OK) return rc;
+            size_t pyr_px = 0;
+            for (int l = 0; l < ctx->plan.nlevels; l++) pyr_px += (size_t)ctx->plan.lv[l].lw * ctx->plan.lv[l].lh;
+            if ((rc = ensure(&ctx->d_pyr, &ctx->pyr_cap, pyr_px)) != NV_OK) return rc;
+        }
+        ctx->epoch++;
+    }
     if (casc->tail_fast) {
         std::lock_guard<std::mutex> lk(casc->mu);
         ctx->cur_tail = casc->d_tail[ctx->gpu]; ctx->cur_tail_base = casc->d_tail_base[ctx->gpu];
@@ -514,12 +605,17 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
     if (P.nlevels > 0) {
         int16_t *depth = ctx->debug ? ctx->d_depth : nullptr;
         prof_mark(ctx, 2);
+        const uint32_t *tilt = ctx->use_gen && ctx->need_tilt ? ctx->d_tilt : nullptr;
         NV_CUDA(launch_pyr_rowscan(ctx->d_plan, P.total_rowblk, d_gray, gstride, d_lut, ctx->d_ptab, ctx->d_sum, ctx->d_sq,
-                                   ctx->debug ? ctx->d_pyr : nullptr, st));
+                                   ctx->debug || tilt ? ctx->d_pyr : nullptr, st));
         prof_mark(ctx, 3);
         NV_CUDA(launch_colscan(ctx->d_plan, P.total_colblk, ctx->d_sum, ctx->d_sq, st));
+        if (tilt) { NV_CUDA(launch_tilted(ctx->d_plan, P.nlevels, ctx->max_lw, ctx->d_pyr, ctx->d_tilt, st)); nl++; }
         prof_mark(ctx, 4);
-        if (ctx->use_s0p) {
+        if (ctx->use_gen) {
+            NV_CUDA(launch_stage0_rows_gen(ctx->d_plan, P.total_rows, meta, ctx->cur_gen, ctx->d_sum, ctx->d_sq, tilt, ctx->d_vnf,
+                                           ctx->d_bits_ok, ctx->d_counters, depth, st));
+        } else if (ctx->use_s0p) {
             Stage0Params &sp = ctx->s0p;
             sp.sum = ctx->d_sum; sp.sq = ctx->d_sq; sp.vnf = ctx->d_vnf; sp.bits_alive = ctx->d_bits_ok;
             sp.counters = ctx->d_counters; sp.depth = depth;
@@ -557,8 +653,12 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
             NV_CUDA(launch_alive_to_queue(ctx->d_plan, P.total_rows, ctx->d_vnf, ctx->d_bits_ok, ctx->d_queue, ctx->d_counters,
                                           qcap, st));
             prof_mark(ctx, 6);
-            NV_CUDA(launch_queue_stages(ctx->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
-                                        ctx->cand_cap, depth, 148 * 8, st));
+            if (ctx->use_gen)
+                NV_CUDA(launch_queue_stages_gen(ctx->d_plan, meta, ctx->cur_gen, ctx->d_sum, tilt, ctx->d_queue, ctx->d_counters,
+                                                ctx->d_cand, ctx->cand_cap, depth, 148 * 8, st));
+            else
+                NV_CUDA(launch_queue_stages(ctx->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
+                                            ctx->cand_cap, depth, 148 * 8, st));
             nl += 2;
         }
     }
@@ -1038,6 +1138,17 @@ extern "C" int nv_debug_get_integral(nv_ctx *ctx, int level, int32_t *sum, uint3
                 dst[(size_t)r * (L.lw + 1) + c] = tmp[(size_t)r * L.ipitch + pc];
             }
     }
+    return NV_OK;
+}
+
+extern "C" int nv_debug_get_tilted(nv_ctx *ctx, int level, int32_t *tilted)
+{
+    int rc = tap_ready(ctx, level, true);
+    if (rc != NV_OK) return rc;
+    if (!ctx->need_tilt || !ctx->d_tilt || !tilted) { nv_set_error("no tilted integral: the last cascade has no tilted features"); return NV_ERR_STATE; }
+    const LevelDesc &L = ctx->plan.lv[level];
+    NV_CUDA(cudaMemcpy2D(tilted, (size_t)(L.lw + 1) * 4, ctx->d_tilt + L.iofs, (size_t)L.ipitch * 4, (size_t)(L.lw + 1) * 4, L.lh + 1,
+                         cudaMemcpyDeviceToHost));
     return NV_OK;
 }
 

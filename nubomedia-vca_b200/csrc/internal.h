@@ -41,6 +41,13 @@ struct HostCascade {
     std::vector<float> feat_weight;        // nfeatures * 3
     int n3rect = 0;
     int order_free = 0;
+    // general model: weak classifiers that are trees of more than one node and/or tilted features.  general == 0: the
+    // stump arrays above describe the whole cascade (and the fast kernels apply).
+    int general = 0, has_tilted = 0;
+    std::vector<int> tree_nnodes;          // internal nodes per weak classifier
+    std::vector<int> node_feat, node_left, node_right;   // child > 0: node of the same tree; <= 0: leaf -child of the tree
+    std::vector<float> node_thr, leaves;   // nnodes + 1 leaves per tree
+    std::vector<uint8_t> feat_tilted;
 };
 
 int nv_parse_cascade_xml(const char *path, HostCascade *out);   // cascade_xml.cpp
@@ -51,6 +58,20 @@ struct __align__(16) DevStump {
     float w[3];         // w[2]==0: two-rect feature
     float thr, left, right;
     uint32_t pad[3];
+};
+
+// General model on the device (trees of more than one node and/or tilted features): see kernels_cascade.cu
+struct __align__(16) GenFeat {
+    uint32_t r[3];      // x | y<<8 | w<<16 | h<<24
+    float w[3];         // w[2]==0: two-rect feature
+    int tilted;
+    int pad;
+};
+struct GenModel {
+    const int2 *tree;   // per weak classifier: first node, first leaf
+    const int4 *node;   // feature, threshold (float bits), left, right (> 0: node of the tree; <= 0: leaf -idx)
+    const float *leaf;
+    const GenFeat *feat;
 };
 
 struct DevCascade {
@@ -83,6 +104,7 @@ struct nv_cascade {
     std::map<int, DevCascade *> d_meta;
     std::map<int, TailStump *> d_tail;
     std::map<int, double *> d_tail_base;
+    std::map<int, GenModel> d_gen;        // general cascades only
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -253,6 +275,8 @@ struct nv_ctx {
     };
     const DevStump *cur_stumps = nullptr;  const DevCascade *cur_meta = nullptr;   // device copies of the cascade in use
     const TailStump *cur_tail = nullptr;  const double *cur_tail_base = nullptr;
+    GenModel cur_gen = {};  bool use_gen = false;  bool need_tilt = false;   // general cascade in use / it has tilted features
+    uint32_t *d_tilt = nullptr;  size_t tilt_cap = 0;  int max_lw = 0;
     cudaGraphExec_t gexec = nullptr;  GraphKey gkey, gkey_seen;  int g_nl = 0;  bool no_graph = false;
     unsigned long long epoch = 1;     // bumped whenever a buffer the pipeline binds is re-allocated or re-planned
 
@@ -295,6 +319,7 @@ enum { RT_COPY = 0, RT_BOX2 = 1, RT_LINEAR = 2 };
 cudaError_t launch_pyr_rowscan(const PlanDev *plan, int total_rowblk, const uint8_t *gray, int gstride, const uint8_t *lut,
                                const int *ptab, uint32_t *sum, uint32_t *sq, uint8_t *pyr_debug, cudaStream_t st);
 cudaError_t launch_colscan(const PlanDev *plan, int total_colblk, uint32_t *sum, uint32_t *sq, cudaStream_t st);
+cudaError_t launch_tilted(const PlanDev *plan, int nlevels, int max_lw, const uint8_t *pyr, uint32_t *tilt, cudaStream_t st);
 
 // kernels_cascade.cu
 cudaError_t launch_queue_stages(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,
@@ -304,6 +329,12 @@ cudaError_t launch_queue_stages(const PlanDev *plan, const DevCascade *meta, con
 cudaError_t launch_stage0_rows(const PlanDev *plan, int total_rows, const DevCascade *meta, const DevStump *stumps,
                                const uint32_t *sum, const uint32_t *sq, float *vnf, uint32_t *bits_alive, int *counters,
                                int16_t *depth, cudaStream_t st);
+cudaError_t launch_stage0_rows_gen(const PlanDev *plan, int total_rows, const DevCascade *meta, const GenModel &g,
+                                   const uint32_t *sum, const uint32_t *sq, const uint32_t *tilt, float *vnf,
+                                   uint32_t *bits_alive, int *counters, int16_t *depth, cudaStream_t st);
+cudaError_t launch_queue_stages_gen(const PlanDev *plan, const DevCascade *meta, const GenModel &g, const uint32_t *sum,
+                                    const uint32_t *tilt, const uint2 *queue, int *counters, uint32_t *cand, int cand_cap,
+                                    int16_t *depth, int nblocks, cudaStream_t st);
 cudaError_t launch_cascade_classes(const TileParams &tp, int ystep, int ntiles, cudaStream_t st);
 cudaError_t launch_stage0_rows_p(const Stage0Params &sp, cudaStream_t st);
 bool fill_stage0_params(const nv_cascade *c, const PlanDev &P, Stage0Params *sp);

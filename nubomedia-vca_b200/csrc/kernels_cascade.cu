@@ -105,6 +105,135 @@ k_queue_stages(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ 
 }
 
 // ================================================================================================
+// General cascades (OpenCV's predictOrdered path): weak classifiers that are trees of more than one node and/or
+// features on the tilted integral.  One thread per window, plain early-exit loops; these models run in the nested
+// ROI stages of the eye / mouth / nose / ear elements, where a call has 10^3..10^4 windows.
+// ================================================================================================
+__device__ __forceinline__ uint32_t skip_rule_word(uint32_t f, bool &e);
+
+__device__ __forceinline__ float gen_feature(const GenModel &g, int f, const uint32_t *__restrict__ wb, const LevelView &v,
+                                             const uint32_t *__restrict__ tb, int tp)
+{
+    const GenFeat ft = g.feat[f];
+    float val = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (k == 2 && ft.w[2] == 0.f) break;
+        uint32_t pr = ft.r[k];
+        int rs;
+        if (ft.tilted) {                                         // (x, y), (x - h, y + h), (x + w, y + w), (x + w - h, y + w + h)
+            int x = pr & 255, y = (pr >> 8) & 255, w = (pr >> 16) & 255, h = pr >> 24;
+            rs = (int)(__ldg(tb + y * tp + x) - __ldg(tb + (y + h) * tp + x - h) - __ldg(tb + (y + w) * tp + x + w) +
+                       __ldg(tb + (y + w + h) * tp + x + w - h));
+        } else
+            rs = rect_sum(wb, v, pr);
+        float t = __fmul_rn(ft.w[k], __int2float_rn(rs));
+        val = k == 0 ? t : __fadd_rn(val, t);
+    }
+    return val;
+}
+
+__device__ __forceinline__ double gen_stage_sum(const GenModel &g, int t0, int t1, const uint32_t *__restrict__ wb,
+                                                const LevelView &v, const uint32_t *__restrict__ tb, int tp, float vnf)
+{
+    double tmp = 0.;
+    for (int t = t0; t < t1; t++) {
+        int2 tr = g.tree[t];                                     // first node, first leaf
+        int idx = 0;
+        do {
+            int4 n = g.node[tr.x + idx];                         // feature, threshold bits, left, right
+            float val = __fmul_rn(gen_feature(g, n.x, wb, v, tb, tp), vnf);
+            idx = val < __int_as_float(n.y) ? n.z : n.w;
+        } while (idx > 0);
+        tmp = __dadd_rn(tmp, (double)g.leaf[tr.y - idx]);
+    }
+    return tmp;
+}
+
+__global__ void __launch_bounds__(256)
+k_stage0_rows_gen(const PlanDev *__restrict__ plan, int total_rows, const DevCascade *__restrict__ meta, const GenModel g,
+                  const uint32_t *__restrict__ sum, const uint32_t *__restrict__ sq, const uint32_t *__restrict__ tilt,
+                  float *__restrict__ vnf_out, uint32_t *__restrict__ bits_alive, int *__restrict__ counters,
+                  int16_t *__restrict__ depth)
+{
+    int lane = threadIdx.x & 31;
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    int l = find_level_c(plan, row, &LevelDesc::row0);
+    const LevelDesc &L = plan->lv[l];
+    int iy = row - L.row0;
+    LevelView v{sum + L.iofs, L.ipitch, L.iplane, L.ystep};
+    int ww = plan->win_w, wh = plan->win_h;
+    int c00 = corner(v, 1, 1), c10 = corner(v, ww - 1, 1), c01 = corner(v, 1, wh - 1), c11 = corner(v, ww - 1, wh - 1);
+    double area = (double)((ww - 2) * (wh - 2));
+    int n0 = meta->stage_first[1];
+    double thr0 = (double)meta->stage_thr[0];
+    size_t rowbase = (size_t)iy * L.ystep * L.ipitch;
+    bool e = true;
+    int nalive = 0;
+    for (int cx = 0; cx < L.nxw; cx++) {
+        int ix = cx * 32 + lane;
+        bool valid = ix < L.nx;
+        int ixc = valid ? ix : L.nx - 1;
+        const uint32_t *wb = v.sum + rowbase + ixc, *qb = sq + L.iofs + rowbase + ixc;
+        const uint32_t *tb = tilt ? tilt + L.iofs + rowbase + ixc * L.ystep : nullptr;
+        int valsum = (int)(__ldg(wb + c00) - __ldg(wb + c10) - __ldg(wb + c01) + __ldg(wb + c11));
+        uint32_t valsq = __ldg(qb + c00) - __ldg(qb + c10) - __ldg(qb + c01) + __ldg(qb + c11);
+        double nf = __dsub_rn(__dmul_rn(area, (double)valsq), __dmul_rn((double)valsum, (double)valsum));
+        float vnf = 0.f;
+        bool ok = false;
+        if (nf > 0.) {
+            vnf = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn(nf)));
+            ok = __dmul_rn(area, (double)vnf) < 1e-1;
+        }
+        bool fail = false;
+        if (ok) fail = gen_stage_sum(g, 0, n0, wb, v, tb, L.ipitch, vnf) < thr0;
+        ok = ok && valid;
+        fail = fail && ok;
+        uint32_t f = __ballot_sync(0xffffffffu, fail);
+        uint32_t em = skip_rule_word(f, e);
+        bool visited = (em >> lane) & 1u;
+        bool alive = visited && ok && !fail;
+        uint32_t am = __ballot_sync(0xffffffffu, alive);
+        nalive += __popc(am);
+        if (lane == 0) bits_alive[L.bofs + iy * L.nxw + cx] = am;
+        if (alive) vnf_out[L.wofs + iy * L.nx + ix] = vnf;
+        if (depth && valid && !alive)
+            depth[L.wofs + iy * L.nx + ix] = (int16_t)(!visited ? NV_DEPTH_SKIPPED : (!ok ? NV_DEPTH_VARREJ : 0));
+    }
+    if (lane == 0 && nalive) atomicAdd(&counters[0], nalive);
+}
+
+__global__ void __launch_bounds__(256)
+k_queue_stages_gen(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ meta, const GenModel g,
+                   const uint32_t *__restrict__ sum, const uint32_t *__restrict__ tilt, const uint2 *__restrict__ queue,
+                   int *__restrict__ counters, uint32_t *__restrict__ cand, int cand_cap, int16_t *__restrict__ depth)
+{
+    int n = counters[0];
+    int nstages = meta->nstages;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint2 q = queue[i];
+        int l = q.x >> 26, iy = (q.x >> 13) & 8191, ix = q.x & 8191;
+        float vnf = __uint_as_float(q.y);
+        const LevelDesc &L = plan->lv[l];
+        LevelView v{sum + L.iofs, L.ipitch, L.iplane, L.ystep};
+        size_t rowbase = (size_t)iy * L.ystep * L.ipitch;
+        const uint32_t *wb = v.sum + rowbase + ix;
+        const uint32_t *tb = tilt ? tilt + L.iofs + rowbase + ix * L.ystep : nullptr;
+        int code = NV_DEPTH_PASS;
+        for (int st = 1; st < nstages; st++)
+            if (gen_stage_sum(g, meta->stage_first[st], meta->stage_first[st + 1], wb, v, tb, L.ipitch, vnf) <
+                (double)meta->stage_thr[st]) { code = -st; break; }
+        if (depth) depth[L.wofs + iy * L.nx + ix] = (int16_t)code;
+        if (code == NV_DEPTH_PASS) {
+            int pos = atomicAdd(&counters[1], 1);
+            if (pos < cand_cap) cand[pos] = q.x;
+            else counters[2] = 1;
+        }
+    }
+}
+
+// ================================================================================================
 // pass structure (all levels per launch):
 //   k_stage0_rows      one warp per window ROW: variance + stage 0 for each 32-window chunk, the skip
 //                      automaton carried along the row in a register, one "alive" bit-word per chunk.
@@ -938,6 +1067,22 @@ cudaError_t launch_cascade_tail_fast(const PlanDev *plan, const DevCascade *meta
 {
     k_cascade_tail_fast<<<148 * 8, 256, smem_bytes, st>>>(plan, meta, tstumps, tbase, sum, tail, counters, cand, cand_cap, depth,
                                                           stage_begin);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stage0_rows_gen(const PlanDev *plan, int total_rows, const DevCascade *meta, const GenModel &g,
+                                   const uint32_t *sum, const uint32_t *sq, const uint32_t *tilt, float *vnf,
+                                   uint32_t *bits_alive, int *counters, int16_t *depth, cudaStream_t st)
+{
+    k_stage0_rows_gen<<<(total_rows + 7) / 8, 256, 0, st>>>(plan, total_rows, meta, g, sum, sq, tilt, vnf, bits_alive, counters, depth);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_queue_stages_gen(const PlanDev *plan, const DevCascade *meta, const GenModel &g, const uint32_t *sum,
+                                    const uint32_t *tilt, const uint2 *queue, int *counters, uint32_t *cand, int cand_cap,
+                                    int16_t *depth, int nblocks, cudaStream_t st)
+{
+    k_queue_stages_gen<<<nblocks, 256, 0, st>>>(plan, meta, g, sum, tilt, queue, counters, cand, cand_cap, depth);
     return cudaGetLastError();
 }
 

@@ -111,6 +111,57 @@ k_colscan(const PlanDev *__restrict__ plan, int total_colblk, uint32_t *__restri
         }
 }
 
+// Tilted integral (cv::integral's third output; only for cascades with tilted features).  tilted(X,Y) = sum of the
+// level's pixels in the 45-degree triangle whose apex is pixel (X-1, Y-1); three-term recurrence over rows
+//   T(X,Y) = T(X-1,Y-1) + T(X+1,Y-1) - T(X,Y-2) + img(X-1,Y-1) + img(X-1,Y-2)
+// closed on the columns 0..lw by T(-1,Y) = T(0,Y-1) and T(lw+1,Y) = T(lw,Y-1) (the strips those triangles would add lie
+// outside the image).  Rows depend on the two rows above, so ONE block walks a level top to bottom, its threads
+// striding over the columns with the last two rows kept in shared memory; levels run in parallel blocks.  Plain row
+// layout (no column de-interleave), pitch and level offsets shared with the upright integrals.
+__global__ void __launch_bounds__(1024)
+k_tilted(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ pyr, uint32_t *__restrict__ tilt)
+{
+    extern __shared__ uint32_t s_rows[];                         // 3 x (lw + 1): rows Y-2, Y-1, Y (rotating)
+    const LevelDesc &L = plan->lv[blockIdx.x];
+    const int lw = L.lw, lh = L.lh, pitch = L.ipitch, n = lw + 1;
+    const uint8_t *img = pyr + L.pofs;
+    uint32_t *out = tilt + L.iofs;
+    uint32_t *r0 = s_rows, *r1 = s_rows + n, *r2 = s_rows + 2 * n;
+    for (int x = threadIdx.x; x < n; x += blockDim.x) { r0[x] = 0; r1[x] = 0; out[x] = 0; }
+    __syncthreads();
+    for (int Y = 1; Y <= lh; Y++) {
+        const uint8_t *i1 = img + (size_t)(Y - 1) * lw, *i2 = Y >= 2 ? img + (size_t)(Y - 2) * lw : nullptr;
+        for (int X = threadIdx.x; X < n; X += blockDim.x) {
+            uint32_t left = X > 0 ? r1[X - 1] : r0[0], right = X < lw ? r1[X + 1] : r0[lw];
+            uint32_t v = left + right - r0[X];
+            if (X > 0) v += (uint32_t)i1[X - 1] + (i2 ? (uint32_t)i2[X - 1] : 0u);
+            r2[X] = v;
+            out[(size_t)Y * pitch + X] = v;
+        }
+        __syncthreads();
+        uint32_t *t = r0; r0 = r1; r1 = r2; r2 = t;
+    }
+}
+
+cudaError_t launch_tilted(const PlanDev *plan, int nlevels, int max_lw, const uint8_t *pyr, uint32_t *tilt, cudaStream_t st)
+{
+    size_t smem = 3 * (size_t)(max_lw + 1) * sizeof(uint32_t);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    static std::mutex mu;
+    static unsigned long long attr_set = 0ull;
+    if (smem > 48 * 1024) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        if (!((attr_set >> (dev & 63)) & 1ull)) {
+            cudaFuncSetAttribute(k_tilted, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set |= 1ull << (dev & 63);
+        }
+    }
+    k_tilted<<<nlevels, 1024, smem, st>>>(plan, pyr, tilt);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pyr_rowscan(const PlanDev *plan, int total_rowblk, const uint8_t *gray, int gstride, const uint8_t *lut,
                                const int *ptab, uint32_t *sum, uint32_t *sq, uint8_t *pyr_debug, cudaStream_t st)
 {

@@ -31,7 +31,8 @@ class Rect(C.Structure):
 
 
 class CascadeInfo(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("win_w", "win_h", "nstages", "nstumps", "nfeatures", "n3rect", "order_free_sums")]
+    _fields_ = [(n, C.c_int) for n in ("win_w", "win_h", "nstages", "nstumps", "nfeatures", "n3rect", "order_free_sums",
+                                         "general", "has_tilted", "nnodes")]
 
 
 class DetectParams(C.Structure):
@@ -94,10 +95,13 @@ _SIGS = {
     "nv_event_destroy": (None, [_vp]),
     "nv_debug_cascade_stage": (_i, [_vp, _i, _ip, C.POINTER(C.c_float)]),
     "nv_debug_cascade_stump": (_i, [_vp, _i, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "nv_debug_cascade_tree": (_i, [_vp, _i, _i, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "nv_debug_cascade_feature": (_i, [_vp, _i, _ip, C.POINTER(C.c_float), _ip]),
     "nv_debug_num_levels": (_i, [_vp]),
     "nv_debug_level_info": (_i, [_vp, _i, C.POINTER(LevelInfo)]),
     "nv_debug_get_gray": (_i, [_vp, _vp, _i, _ip, _ip]),
     "nv_debug_get_integral": (_i, [_vp, _i, _vp, _vp]),
+    "nv_debug_get_tilted": (_i, [_vp, _i, _vp]),
     "nv_debug_get_depth_map": (_i, [_vp, _i, _vp]),
     "nv_debug_get_candidates": (_i, [_vp, _vp, _i, _ip]),
     "nv_debug_get_counters": (_i, [_vp, C.POINTER(C.c_longlong)]),
@@ -181,6 +185,19 @@ class Cascade:
         nt, thr = C.c_int(0), C.c_float(0)
         _check(_lib.nv_debug_cascade_stage(self.handle, s, C.byref(nt), C.byref(thr)), "nv_debug_cascade_stage")
         return nt.value, np.float32(thr.value)
+
+    def tree(self, t, cap=64):
+        """(nodes [n,3] int: feature, left, right), thresholds [n] f32, leaves [n+1] f32 of weak classifier t"""
+        nn = C.c_int(0)
+        flr, thr, lv = (C.c_int * (3 * cap))(), (C.c_float * cap)(), (C.c_float * (cap + 1))()
+        _check(_lib.nv_debug_cascade_tree(self.handle, t, cap, C.byref(nn), flr, thr, lv), "nv_debug_cascade_tree")
+        n = nn.value
+        return (np.array(flr[:3 * n], np.int32).reshape(n, 3), np.array(thr[:n], np.float32), np.array(lv[:n + 1], np.float32))
+
+    def feature(self, f):
+        r, w, t = (C.c_int * 12)(), (C.c_float * 3)(), C.c_int(0)
+        _check(_lib.nv_debug_cascade_feature(self.handle, f, r, w, C.byref(t)), "nv_debug_cascade_feature")
+        return np.array(r[:], np.int32).reshape(3, 4), np.array(w[:], np.float32), t.value
 
     def stump(self, i):
         r, w, t = (C.c_int * 12)(), (C.c_float * 3)(), (C.c_float * 3)()
@@ -380,6 +397,12 @@ class Context:
         s = np.empty((lv["lh"] + 1, lv["lw"] + 1), np.int32); q = np.empty((lv["lh"] + 1, lv["lw"] + 1), np.uint32)
         _check(_lib.nv_debug_get_integral(self.handle, level, _p(s), _p(q)), "nv_debug_get_integral")
         return s, q
+
+    def tilted(self, level):
+        lv = self.levels()[level]
+        t = np.empty((lv["lh"] + 1, lv["lw"] + 1), np.int32)
+        _check(_lib.nv_debug_get_tilted(self.handle, level, _p(t)), "nv_debug_get_tilted")
+        return t
 
     def depth_map(self, level):
         lv = self.levels()[level]

@@ -200,6 +200,30 @@ ORA_API void ora_integral(const uint8_t *src, int w, int h, int sstride,
     }
 }
 
+/* cv::integral's third output (tilted sums), CV_32S: tilted(X,Y) = sum of img(x,y) over y < Y, |x - X + 1| <= Y - y - 1,
+ * i.e. the 45-degree triangle whose apex is pixel (X-1, Y-1).  Restated through the three-term recurrence
+ *   T(X,Y) = T(X-1,Y-1) + T(X+1,Y-1) - T(X,Y-2) + img(X-1,Y-1) + img(X-1,Y-2)
+ * evaluated on a domain widened by h columns on both sides, where the triangles beyond the border are empty and the
+ * zero boundary is exact.  Pinned against cv2.integral3 in tests/test_oracle_vs_cv2.py.  tilted: [(h+1)*(w+1)]. */
+ORA_API void ora_integral_tilted(const uint8_t *img, int w, int h, int stride, int32_t *tilted)
+{
+    int pad = h + 1, ew = w + 1 + 2 * pad;                     /* extended X = -pad .. w + pad */
+    int32_t *r0 = (int32_t *)calloc((size_t)ew, sizeof(int32_t)), *r1 = (int32_t *)calloc((size_t)ew, sizeof(int32_t)),
+            *r2 = (int32_t *)calloc((size_t)ew, sizeof(int32_t));   /* rows Y-2, Y-1, Y */
+    for (int x = 0; x <= w; x++) tilted[x] = 0;
+    for (int Y = 1; Y <= h; Y++) {
+        for (int e = 1; e < ew - 1; e++) {
+            int X = e - pad, px = X - 1;
+            int32_t a = (px >= 0 && px < w) ? img[(size_t)(Y - 1) * stride + px] : 0;
+            int32_t b = (px >= 0 && px < w && Y >= 2) ? img[(size_t)(Y - 2) * stride + px] : 0;
+            r2[e] = r1[e - 1] + r1[e + 1] - r0[e] + a + b;
+        }
+        for (int x = 0; x <= w; x++) tilted[(size_t)Y * (w + 1) + x] = r2[x + pad];
+        int32_t *t = r0; r0 = r1; r1 = r2; r2 = t;
+    }
+    free(r0); free(r1); free(r2);
+}
+
 /* ---------------------------------------------------------------------------------------
  * Cascade model (flat arrays; filled from the XML by oracle/oracle.py)
  * ------------------------------------------------------------------------------------- */
@@ -215,6 +239,16 @@ typedef struct {
     int nfeatures;
     const int *feat_rect;        /* [nfeatures*3*4] x,y,w,h (w==0: unused rect) */
     const float *feat_weight;    /* [nfeatures*3] */
+    /* general model: weak classifiers that are trees of more than one node and/or tilted features (OpenCV's
+     * predictOrdered path).  general == 0: the stump arrays above describe the whole cascade. */
+    int general;
+    const int *tree_nnodes;      /* [nstumps] internal nodes per weak classifier */
+    const int *node_feat;        /* [sum nnodes] */
+    const float *node_thr;
+    const int *node_left;        /* > 0: next node of the same tree; <= 0: leaf -idx of the same tree */
+    const int *node_right;
+    const float *leaves;         /* [sum (nnodes + 1)] */
+    const unsigned char *feat_tilted;   /* [nfeatures] */
 } ora_cascade;
 
 #define ORA_DEPTH_VARREJ  (-100)    /* OpenCV result -1 from the variance test */
@@ -288,6 +322,69 @@ static int ora_run_at(const ora_cascade *c, const int32_t *sum, const uint32_t *
     return 1;
 }
 
+/* Feature value on the upright or the tilted integral.  Tilted rect (x, y, w, h): corners (x, y), (x - h, y + h),
+ * (x + w, y + w), (x + w - h, y + w + h) of the tilted integral, combined p0 - p1 - p2 + p3 (OpenCV CV_TILTED_OFS). */
+static float ora_feature(const ora_cascade *c, const int32_t *w0, const int32_t *t0, int p, int f)
+{
+    const int *r = c->feat_rect + (size_t)f * 12;
+    const float *wt = c->feat_weight + (size_t)f * 3;
+    int tilted = c->feat_tilted && c->feat_tilted[f];
+    float v = 0.f;
+    for (int k = 0; k < 3; k++) {
+        if (k == 2 && wt[2] == 0.f) break;
+        int x = r[4 * k], y = r[4 * k + 1], w = r[4 * k + 2], h = r[4 * k + 3], rs;
+        if (tilted)
+            rs = t0[(size_t)y * p + x] - t0[(size_t)(y + h) * p + x - h] - t0[(size_t)(y + w) * p + x + w]
+               + t0[(size_t)(y + w + h) * p + x + w - h];
+        else {
+            const int32_t *a = w0 + (size_t)y * p + x;
+            rs = a[0] - a[w] - a[(size_t)h * p] + a[(size_t)h * p + w];
+        }
+        float t = wt[k] * (float)rs;
+        v = (k == 0) ? t : v + t;
+    }
+    return v;
+}
+
+/* OpenCV predictOrdered<HaarEvaluator>: every weak classifier is walked from its root; the float feature value times
+ * the variance factor is compared with the node threshold; leaves accumulate in double. */
+static int ora_run_at_general(const ora_cascade *c, const int32_t *sum, const uint32_t *sq, const int32_t *tilt, int p,
+                              int x, int y)
+{
+    int nw = c->win_w - 2, nh = c->win_h - 2;
+    const int32_t *s = sum + (size_t)(y + 1) * p + (x + 1);
+    const uint32_t *q = sq + (size_t)(y + 1) * p + (x + 1);
+    int valsum = s[0] - s[nw] - s[(size_t)nh * p] + s[(size_t)nh * p + nw];
+    uint32_t valsq = q[0] - q[nw] - q[(size_t)nh * p] + q[(size_t)nh * p + nw];
+    double area = (double)nw * nh;
+    double nf = area * valsq - (double)valsum * valsum;
+    float vnf;
+    if (nf > 0.) {
+        nf = sqrt(nf);
+        vnf = (float)(1. / nf);
+        if (!(area * vnf < 1e-1)) return ORA_DEPTH_VARREJ;
+    } else
+        return ORA_DEPTH_VARREJ;
+    const int32_t *w0 = sum + (size_t)y * p + x, *t0 = tilt ? tilt + (size_t)y * p + x : NULL;
+    int ti = 0, node0 = 0, leaf0 = 0;
+    for (int st = 0; st < c->nstages; st++) {
+        double tmp = 0.;
+        for (int i = 0; i < c->stage_ntrees[st]; i++, ti++) {
+            int idx = 0;
+            do {
+                int n = node0 + idx;
+                float v = ora_feature(c, w0, t0, p, c->node_feat[n]) * vnf;
+                idx = v < c->node_thr[n] ? c->node_left[n] : c->node_right[n];
+            } while (idx > 0);
+            tmp += (double)c->leaves[leaf0 - idx];
+            node0 += c->tree_nnodes[ti]; leaf0 += c->tree_nnodes[ti] + 1;
+        }
+        float thr = c->stage_thr[st] - 1e-5f;
+        if (tmp < (double)thr) return -st;
+    }
+    return 1;
+}
+
 /* Debug tap for the pin tests: normalised value of feature `f` at window (x,y); returns 0 and
  * leaves *out untouched when the variance test rejects the window. */
 ORA_API int ora_feature_value(const ora_cascade *c, const int32_t *sum, const uint32_t *sq, int p,
@@ -331,7 +428,15 @@ ORA_API int ora_row_limit(int ry, int ystep, int nstripes)
     return lim < ry ? (int)lim : ry;
 }
 
-ORA_API int ora_eval_level(const ora_cascade *c, const int32_t *sum, const uint32_t *sq,
+ORA_API int ora_has_tilted(const ora_cascade *c)
+{
+    if (!c->feat_tilted) return 0;
+    for (int f = 0; f < c->nfeatures; f++)
+        if (c->feat_tilted[f]) return 1;
+    return 0;
+}
+
+ORA_API int ora_eval_level(const ora_cascade *c, const int32_t *sum, const uint32_t *sq, const int32_t *tilt,
                            int lw, int lh, int ystep, float sc, int nstripes, int16_t *depth,
                            int *cand, int cap, int *ncand_io)
 {
@@ -345,7 +450,7 @@ ORA_API int ora_eval_level(const ora_cascade *c, const int32_t *sum, const uint3
     for (int y = 0; y < ry; y += ystep, iy++) {
         if (depth) for (int i = 0; i < nx; i++) depth[(size_t)iy * nx + i] = ORA_DEPTH_SKIPPED;
         for (int x = 0; x < rx; x += ystep) {
-            int r = ora_run_at(c, sum, sq, p, x, y);
+            int r = c->general ? ora_run_at_general(c, sum, sq, tilt, p, x, y) : ora_run_at(c, sum, sq, p, x, y);
             if (depth) depth[(size_t)iy * nx + x / ystep] = (int16_t)r;
             if (r > 0) {
                 npass++;
@@ -473,8 +578,14 @@ ORA_API int ora_detect_multiscale(const ora_cascade *c, const uint8_t *gray, int
         else
             ora_resize_linear_exact(gray, W, H, stride, lvl, lw, lh, lw);
         ora_integral(lvl, lw, lh, lw, sum, sq);
+        int32_t *tilt = NULL;
+        if (c->general && ora_has_tilted(c)) {
+            tilt = (int32_t *)malloc(sizeof(int32_t) * (size_t)(lw + 1) * (lh + 1));
+            ora_integral_tilted(lvl, lw, lh, lw, tilt);
+        }
         int ystep = scales[k] >= 2.f ? 1 : 2;
-        ora_eval_level(c, sum, sq, lw, lh, ystep, scales[k], nstripes, NULL, cand, capc, &ncand);
+        ora_eval_level(c, sum, sq, tilt, lw, lh, ystep, scales[k], nstripes, NULL, cand, capc, &ncand);
+        free(tilt);
         nwin += (long long)((lw + 1 - c->win_w + ystep - 1) / ystep) *
                 ((ora_row_limit(lh + 1 - c->win_h, ystep, nstripes) + ystep - 1) / ystep);
         free(lvl); free(sum); free(sq);

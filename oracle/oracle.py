@@ -39,6 +39,10 @@ class _CCascade(C.Structure):
         ("stump_left", C.POINTER(C.c_float)), ("stump_right", C.POINTER(C.c_float)),
         ("nfeatures", C.c_int),
         ("feat_rect", C.POINTER(C.c_int)), ("feat_weight", C.POINTER(C.c_float)),
+        ("general", C.c_int),
+        ("tree_nnodes", C.POINTER(C.c_int)), ("node_feat", C.POINTER(C.c_int)), ("node_thr", C.POINTER(C.c_float)),
+        ("node_left", C.POINTER(C.c_int)), ("node_right", C.POINTER(C.c_int)), ("leaves", C.POINTER(C.c_float)),
+        ("feat_tilted", C.POINTER(C.c_ubyte)),
     ]
 
 
@@ -54,7 +58,8 @@ def lib():
         _lib.ora_scales.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p, C.c_int]
         _lib.ora_eval_level.restype = C.c_int
-        _lib.ora_eval_level.argtypes = [C.POINTER(_CCascade), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+        _lib.ora_integral_tilted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.ora_eval_level.argtypes = [C.POINTER(_CCascade), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                         C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.ora_row_limit.restype = C.c_int
         _lib.ora_row_limit.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -98,7 +103,10 @@ def _u8(a):
 # cascade model
 # ------------------------------------------------------------------------------------------
 def parse_cascade_xml(path: str) -> dict:
-    """Parse a new-format stump cascade.  Raises NotImplementedError for trees/tilted/LBP."""
+    """Parse a BOOST/HAAR cascade (new or old XML layout): stumps or trees, upright or tilted features.
+
+    The dict always holds the general model (tree_nnodes, node_*, leaves, feat_tilted); `general` is False when
+    every weak classifier is a stump and no feature is tilted, and then the stump_* arrays are filled too."""
     root = ET.parse(path).getroot()
     casc = root.find("cascade")
     if casc is None:
@@ -106,69 +114,92 @@ def parse_cascade_xml(path: str) -> dict:
     if casc.findtext("featureType", "").strip() != "HAAR":
         raise NotImplementedError("only HAAR cascades")
     win_w, win_h = int(casc.findtext("width")), int(casc.findtext("height"))
-    stage_ntrees, stage_thr, feat, thr, left, right = [], [], [], [], [], []
+    stage_ntrees, stage_thr, trees = [], [], []
     for st in casc.find("stages"):
         weak = st.find("weakClassifiers")
         stage_thr.append(float(st.findtext("stageThreshold")))
         n = 0
         for wc in weak:
             nodes = wc.findtext("internalNodes").split()
-            leaves = wc.findtext("leafValues").split()
-            if len(nodes) != 4 or len(leaves) != 2:
-                raise NotImplementedError("tree weak classifiers (depth>1)")
-            feat.append(int(nodes[2])); thr.append(float(nodes[3]))
-            left.append(float(leaves[0])); right.append(float(leaves[1]))
+            leaves = [float(v) for v in wc.findtext("leafValues").split()]
+            nn = len(nodes) // 4
+            if len(nodes) != 4 * nn or len(leaves) != nn + 1 or nn < 1:
+                raise ValueError("malformed weak classifier")
+            trees.append(([(int(nodes[4 * i + 2]), float(nodes[4 * i + 3]), int(nodes[4 * i]), int(nodes[4 * i + 1]))
+                           for i in range(nn)], leaves))
             n += 1
         stage_ntrees.append(n)
-    rects, weights = [], []
+    rects, weights, tilted = [], [], []
     for f in casc.find("features"):
-        if int((f.findtext("tilted") or "0").strip()) != 0:
-            raise NotImplementedError("tilted features")
+        tilted.append(1 if int((f.findtext("tilted") or "0").strip()) != 0 else 0)
         r = np.zeros((3, 4), np.int32); w = np.zeros(3, np.float32)
         for k, rc in enumerate(f.find("rects")):
             t = rc.text.split()
             r[k] = [int(t[0]), int(t[1]), int(t[2]), int(t[3])]; w[k] = np.float32(float(t[4]))
         rects.append(r); weights.append(w)
-    return dict(
-        win_w=win_w, win_h=win_h,
-        stage_ntrees=np.array(stage_ntrees, np.int32), stage_thr=np.array(stage_thr, np.float64).astype(np.float32),
-        stump_feat=np.array(feat, np.int32), stump_thr=np.array(thr, np.float64).astype(np.float32),
-        stump_left=np.array(left, np.float64).astype(np.float32),
-        stump_right=np.array(right, np.float64).astype(np.float32),
-        feat_rect=np.ascontiguousarray(np.stack(rects)), feat_weight=np.ascontiguousarray(np.stack(weights)),
-    )
+    return _model(win_w, win_h, stage_ntrees, stage_thr, trees, rects, weights, tilted)
+
+
+def _model(win_w, win_h, stage_ntrees, stage_thr, trees, rects, weights, tilted) -> dict:
+    """trees: list of ([(feat, thr, left, right), ...], [leaf, ...]) per weak classifier."""
+    f32 = lambda a: np.array(a, np.float64).astype(np.float32)      # noqa: E731
+    general = any(tilted) or any(len(nodes) != 1 for nodes, _ in trees)
+    d = dict(win_w=win_w, win_h=win_h, stage_ntrees=np.array(stage_ntrees, np.int32), stage_thr=f32(stage_thr),
+             feat_rect=np.ascontiguousarray(np.stack(rects)), feat_weight=np.ascontiguousarray(np.stack(weights)),
+             general=bool(general),
+             tree_nnodes=np.array([len(nodes) for nodes, _ in trees], np.int32),
+             node_feat=np.array([n[0] for nodes, _ in trees for n in nodes], np.int32),
+             node_thr=f32([n[1] for nodes, _ in trees for n in nodes]),
+             node_left=np.array([n[2] for nodes, _ in trees for n in nodes], np.int32),
+             node_right=np.array([n[3] for nodes, _ in trees for n in nodes], np.int32),
+             leaves=f32([v for _, lv in trees for v in lv]),
+             feat_tilted=np.array(tilted, np.uint8))
+    if not general:
+        if any(nodes[0][2] != 0 or nodes[0][3] != -1 for nodes, _ in trees):
+            raise ValueError("stump with unexpected leaf indices")
+        d.update(stump_feat=np.array([nodes[0][0] for nodes, _ in trees], np.int32),
+                 stump_thr=f32([nodes[0][1] for nodes, _ in trees]),
+                 stump_left=f32([lv[0] for _, lv in trees]), stump_right=f32([lv[1] for _, lv in trees]))
+    else:
+        z = np.zeros(len(trees), np.float32)
+        d.update(stump_feat=np.zeros(len(trees), np.int32), stump_thr=z, stump_left=z.copy(), stump_right=z.copy())
+    return d
 
 
 def _parse_old_format(root) -> dict:
-    """OpenCV 1.x/2.x "opencv-haar-classifier" layout (what OpenCV 2.4 shipped; cv2 4.13 converts it on load)."""
+    """OpenCV 1.x/2.x "opencv-haar-classifier" layout (what OpenCV 2.4 shipped; cv2 4.13 converts it on load:
+    one feature per node in file order, a <left_val>/<right_val> becomes the next leaf of its tree, a
+    <left_node>/<right_node> the index of the child node)."""
     old = next((k for k in root if k.find("stages") is not None and k.find("size") is not None), None)
     if old is None:
         raise NotImplementedError("not a haar cascade")
     win_w, win_h = (int(t) for t in old.findtext("size").split())
-    stage_ntrees, stage_thr, thr, left, right, rects, weights = [], [], [], [], [], [], []
+    stage_ntrees, stage_thr, trees, rects, weights, tilted = [], [], [], [], [], []
     for st in old.find("stages"):
         stage_thr.append(float(st.findtext("stage_threshold")))
         n = 0
         for tree in st.find("trees"):
-            nodes = list(tree)
-            if len(nodes) != 1 or nodes[0].find("left_val") is None or nodes[0].find("right_val") is None:
-                raise NotImplementedError("tree weak classifiers (depth>1)")
-            node = nodes[0]; ft = node.find("feature")
-            if int((ft.findtext("tilted") or "0").strip()) != 0:
-                raise NotImplementedError("tilted features")
-            r = np.zeros((3, 4), np.int32); w = np.zeros(3, np.float32)
-            for k, rc in enumerate(ft.find("rects")):
-                t = rc.text.split()
-                r[k] = [int(t[0]), int(t[1]), int(t[2]), int(t[3])]; w[k] = np.float32(float(t[4]))
-            rects.append(r); weights.append(w)
-            thr.append(float(node.findtext("threshold"))); left.append(float(node.findtext("left_val")))
-            right.append(float(node.findtext("right_val")))
+            nodes, leaves = [], []
+            for node in tree:
+                ft = node.find("feature")
+                tilted.append(1 if int((ft.findtext("tilted") or "0").strip()) != 0 else 0)
+                r = np.zeros((3, 4), np.int32); w = np.zeros(3, np.float32)
+                for k, rc in enumerate(ft.find("rects")):
+                    t = rc.text.split()
+                    r[k] = [int(t[0]), int(t[1]), int(t[2]), int(t[3])]; w[k] = np.float32(float(t[4]))
+                rects.append(r); weights.append(w)
+                child = []
+                for side in ("left", "right"):
+                    v = node.find(side + "_val")
+                    if v is not None:
+                        child.append(-len(leaves)); leaves.append(float(v.text))
+                    else:
+                        child.append(int(node.findtext(side + "_node")))
+                nodes.append((len(rects) - 1, float(node.findtext("threshold")), child[0], child[1]))
+            trees.append((nodes, leaves))
             n += 1
         stage_ntrees.append(n)
-    f32 = lambda a: np.array(a, np.float64).astype(np.float32)      # noqa: E731
-    return dict(win_w=win_w, win_h=win_h, stage_ntrees=np.array(stage_ntrees, np.int32), stage_thr=f32(stage_thr),
-                stump_feat=np.arange(len(thr), dtype=np.int32), stump_thr=f32(thr), stump_left=f32(left), stump_right=f32(right),
-                feat_rect=np.ascontiguousarray(np.stack(rects)), feat_weight=np.ascontiguousarray(np.stack(weights)))
+    return _model(win_w, win_h, stage_ntrees, stage_thr, trees, rects, weights, tilted)
 
 
 class Cascade:
@@ -178,13 +209,18 @@ class Cascade:
         d = self.d
         self.win_w, self.win_h = d["win_w"], d["win_h"]
         self.nstages, self.nstumps = len(d["stage_ntrees"]), len(d["stump_feat"])
+        self.general = bool(d["general"])
+        self.has_tilted = bool(d["feat_tilted"].any())
         ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
         self.c = _CCascade(
             d["win_w"], d["win_h"], self.nstages, self.nstumps,
             d["stage_ntrees"].ctypes.data_as(ip), d["stage_thr"].ctypes.data_as(fp),
             d["stump_feat"].ctypes.data_as(ip), d["stump_thr"].ctypes.data_as(fp),
             d["stump_left"].ctypes.data_as(fp), d["stump_right"].ctypes.data_as(fp),
-            len(d["feat_rect"]), d["feat_rect"].ctypes.data_as(ip), d["feat_weight"].ctypes.data_as(fp))
+            len(d["feat_rect"]), d["feat_rect"].ctypes.data_as(ip), d["feat_weight"].ctypes.data_as(fp),
+            int(d["general"]), d["tree_nnodes"].ctypes.data_as(ip), d["node_feat"].ctypes.data_as(ip),
+            d["node_thr"].ctypes.data_as(fp), d["node_left"].ctypes.data_as(ip), d["node_right"].ctypes.data_as(ip),
+            d["leaves"].ctypes.data_as(fp), d["feat_tilted"].ctypes.data_as(C.POINTER(C.c_ubyte)))
 
 
 # ------------------------------------------------------------------------------------------
@@ -226,6 +262,13 @@ def integral(img):
     return s, q
 
 
+def integral_tilted(img):
+    img = _u8(img); h, w = img.shape
+    t = np.empty((h + 1, w + 1), np.int32)
+    lib().ora_integral_tilted(_p(img), w, h, img.strides[0], _p(t))
+    return t
+
+
 # ------------------------------------------------------------------------------------------
 # cascade
 # ------------------------------------------------------------------------------------------
@@ -261,17 +304,18 @@ def eval_pyramid(gray, casc: Cascade, scale_factor, min_size=(0, 0), max_size=(0
             continue
         img = gray.copy() if (lw, lh) == (W, H) else resize_linear_exact(gray, lw, lh)
         s, q = integral(img)
+        t = integral_tilted(img) if casc.has_tilted else None
         ystep = 1 if sc >= 2 else 2
         ry = lib().ora_row_limit(ry, ystep, nstripes)
         nx, ny = (rx + ystep - 1) // ystep, (ry + ystep - 1) // ystep
         depth = np.empty((ny, nx), np.int16)
         cand = np.empty((nx * ny, 4), np.int32)
         nc = C.c_int(0)
-        lib().ora_eval_level(C.byref(casc.c), _p(s), _p(q), lw, lh, ystep, C.c_float(sc), nstripes, _p(depth),
+        lib().ora_eval_level(C.byref(casc.c), _p(s), _p(q), _p(t) if t is not None else None, lw, lh, ystep, C.c_float(sc), nstripes, _p(depth),
                              _p(cand), nx * ny, C.byref(nc))
         lv = dict(scale=float(sc), ystep=ystep, lw=lw, lh=lh, image=img, depth=depth, cand=cand[:nc.value].copy())
         if keep_integrals:
-            lv["sum"], lv["sqsum"] = s, q
+            lv["sum"], lv["sqsum"], lv["tilted"] = s, q, t
         out.append(lv)
     return out
 

@@ -65,23 +65,33 @@ def permissive_cascade(path, rng, w, h, nstages=2, ntrees=3, nfeat=12, bias=0.35
 
 
 def write_old_format(path, d, name="haarcascade_converted"):
-    """Writes a parsed stump cascade (oracle.parse_cascade_xml dict) in the OpenCV 1.x/2.x layout."""
+    """Writes a parsed cascade (oracle.parse_cascade_xml dict: stumps or trees, upright or tilted features) in the
+    OpenCV 1.x/2.x layout: one <feature> per node; a child is <left_val>/<right_val> (leaf) or <left_node>/<right_node>."""
     s = ['<?xml version="1.0"?>', '<opencv_storage>', f'<{name} type_id="opencv-haar-classifier">',
          f'  <size>{d["win_w"]} {d["win_h"]}</size>', '  <stages>']
-    k = 0
+    t = n0 = l0 = 0
     for si, nt in enumerate(d["stage_ntrees"]):
         s.append(f'    <_>\n      <!-- stage {si} -->\n      <trees>')
         for _ in range(int(nt)):
-            f = d["stump_feat"][k]; R = d["feat_rect"][f]; W = d["feat_weight"][f]
-            s.append('        <_>\n          <!-- tree -->\n          <_>\n            <!-- root node -->\n            <feature>\n              <rects>')
-            for j in range(3):
-                if j == 2 and W[2] == 0:
-                    break
-                s.append(f'                <_>{R[j][0]} {R[j][1]} {R[j][2]} {R[j][3]} {float(W[j])!r}</_>')
-            s.append('              </rects>\n              <tilted>0</tilted></feature>')
-            s.append(f'            <threshold>{float(d["stump_thr"][k])!r}</threshold>\n            <left_val>{float(d["stump_left"][k])!r}</left_val>'
-                     f'\n            <right_val>{float(d["stump_right"][k])!r}</right_val></_></_>')
-            k += 1
+            nn = int(d["tree_nnodes"][t])
+            s.append('        <_>\n          <!-- tree -->')
+            for i in range(nn):
+                f = d["node_feat"][n0 + i]; R = d["feat_rect"][f]; W = d["feat_weight"][f]
+                s.append('          <_>\n            <feature>\n              <rects>')
+                for j in range(3):
+                    if j == 2 and W[2] == 0:
+                        break
+                    s.append(f'                <_>{R[j][0]} {R[j][1]} {R[j][2]} {R[j][3]} {float(W[j])!r}</_>')
+                s.append(f'              </rects>\n              <tilted>{int(d["feat_tilted"][f])}</tilted></feature>')
+                s.append(f'            <threshold>{float(d["node_thr"][n0 + i])!r}</threshold>')
+                for side, c in (("left", int(d["node_left"][n0 + i])), ("right", int(d["node_right"][n0 + i]))):
+                    if c > 0:
+                        s.append(f'            <{side}_node>{c}</{side}_node>')
+                    else:
+                        s.append(f'            <{side}_val>{float(d["leaves"][l0 - c])!r}</{side}_val>')
+                s.append('          </_>')
+            s.append('        </_>')
+            t += 1; n0 += nn; l0 += nn + 1
         s.append(f'      </trees>\n      <stage_threshold>{float(d["stage_thr"][si])!r}</stage_threshold>\n      <parent>{si - 1}</parent>'
                  '\n      <next>-1</next></_>')
     s.append(f'  </stages></{name}>')

@@ -116,11 +116,53 @@ def test_cascade_error_paths(tmp_path):
     with pytest.raises(nv.NuboError) as e:
         nv.Cascade(str(bad))
     assert e.value.code == -4
-    import cv2  # tilted / tree cascades ship with cv2: loader must refuse them, not mis-evaluate them
-    for name, code in [("haarcascade_smile.xml", -5), ("haarcascade_lefteye_2splits.xml", -5)]:
-        with pytest.raises(nv.NuboError) as e:
-            nv.Cascade(os.path.join(cv2.data.haarcascades, name))
-        assert e.value.code in (code, -4, -5)
+    # a tree whose child index points backwards would loop for ever: refused at load
+    loop = tmp_path / "loop.xml"
+    loop.write_text('<opencv_storage><cascade><stageType>BOOST</stageType><featureType>HAAR</featureType><height>20</height>'
+                    '<width>20</width><stages><_><stageThreshold>0.</stageThreshold><weakClassifiers><_><internalNodes>'
+                    '1 0 0 0.5 1 -1 0 0.5</internalNodes><leafValues>1. 2. 3.</leafValues></_></weakClassifiers></_></stages>'
+                    '<features><_><rects><_>0 0 4 4 -1.</_><_>0 0 2 4 2.</_></rects><tilted>0</tilted></_></features>'
+                    '</cascade></opencv_storage>')
+    with pytest.raises(nv.NuboError) as e:
+        nv.Cascade(str(loop))
+    assert e.value.code == -4
+    # a tilted rect whose rotated corners leave the window
+    tl = tmp_path / "tilt.xml"
+    tl.write_text(loop.read_text().replace("1 0 0 0.5 1 -1 0 0.5", "0 -1 0 0.5").replace("1. 2. 3.", "1. 2.")
+                  .replace("<tilted>0</tilted>", "<tilted>1</tilted>"))
+    with pytest.raises(nv.NuboError) as e:
+        nv.Cascade(str(tl))
+    assert e.value.code == -4
+
+
+GENERAL = ["haarcascade_lefteye_2splits.xml", "haarcascade_righteye_2splits.xml", "haarcascade_smile.xml",
+           "haarcascade_eye_tree_eyeglasses.xml", "haarcascade_frontalface_alt2.xml"]
+
+
+@pytest.mark.parametrize("name", GENERAL)
+def test_general_cascade_loader(name, cascade_dir, tmp_path):
+    """Trees of more than one node and tilted features (OpenCV's predictOrdered path), new and old XML layout."""
+    path = os.path.join(cascade_dir, name)
+    d = O.parse_cascade_xml(path)
+    old = str(tmp_path / "old.xml")
+    write_old_format(old, d)
+    for p in (path, old):
+        c = nv.Cascade(p)
+        assert c.info.general == 1 and c.info.has_tilted == int(d["feat_tilted"].any())
+        assert c.info.nstumps == len(d["tree_nnodes"]) and c.info.nnodes == len(d["node_feat"])
+        assert c.info.order_free_sums == 0
+        n0 = l0 = 0
+        for t in range(c.info.nstumps):
+            nodes, thr, leaves = c.tree(t)
+            nn = int(d["tree_nnodes"][t])
+            assert len(nodes) == nn
+            assert (nodes[:, 1] == d["node_left"][n0:n0 + nn]).all() and (nodes[:, 2] == d["node_right"][n0:n0 + nn]).all()
+            assert (thr == d["node_thr"][n0:n0 + nn]).all() and (leaves == d["leaves"][l0:l0 + nn + 1]).all()
+            for i in range(nn):          # the old layout stores one feature per node: compare by content
+                r, w, tilted = c.feature(int(nodes[i, 0]))
+                f = d["node_feat"][n0 + i]
+                assert (r == d["feat_rect"][f]).all() and (w == d["feat_weight"][f]).all() and tilted == d["feat_tilted"][f]
+            n0 += nn; l0 += nn + 1
 
 
 @pytest.mark.skipif(nv.device_count() > 0, reason="a GPU is visible")

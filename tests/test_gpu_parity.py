@@ -51,6 +51,8 @@ def check_levels(ctx, eq, ocasc, sf, ms):
         s, q = ctx.integral(i)
         assert (s == o["sum"]).all(), f"level {i} integral"
         assert (q == o["sqsum"]).all(), f"level {i} squared integral"
+        if ocasc.has_tilted:
+            assert (ctx.tilted(i) == o["tilted"]).all(), f"level {i} tilted integral"
         d = ctx.depth_map(i)
         bad = np.argwhere(d != o["depth"])
         assert len(bad) == 0, f"level {i}: {len(bad)} depth mismatches, first {bad[:3]} gpu {d[tuple(bad[0])]} ora {o['depth'][tuple(bad[0])]}"
@@ -115,6 +117,35 @@ def test_other_cascades(ctx, cascade_dir, name, sf, ms):
     for mn in (0, 2):
         assert rects_equal(ctx.detect_multiscale(ncasc, g, sf, mn, ms), O.detect_multiscale(g, ocasc, sf, mn, ms))
     check_levels(ctx, g, ocasc, sf, ms)
+
+
+@pytest.mark.parametrize("name,sf,ms", [("haarcascade_lefteye_2splits.xml", 1.1, (20, 20)),
+                                        ("haarcascade_righteye_2splits.xml", 1.1, (0, 0)),
+                                        ("haarcascade_smile.xml", 1.1, (1, 1)),
+                                        ("haarcascade_eye_tree_eyeglasses.xml", 1.25, (0, 0)),
+                                        ("haarcascade_frontalface_alt2.xml", 1.2, (0, 0))])
+def test_general_cascades(ctx, cascade_dir, tmp_path, name, sf, ms):
+    """Tree weak classifiers and tilted features (OpenCV's predictOrdered path): tilted integrals, depth maps,
+    candidates and grouped rectangles against the oracle, in the new and the OpenCV-2.x XML layout; then a plain stump
+    cascade on the same context (the tilted buffers come and go with the cascade)."""
+    from cascade_xml_util import write_old_format
+    p = os.path.join(cascade_dir, name)
+    ncasc, ocasc = nv.Cascade(p), O.Cascade(p)
+    assert ncasc.info.general == 1 and ocasc.general
+    g = O.equalize_hist(O.bgr2gray(synth.frame(400, 300, 2, 3, smin=0.5, smax=0.9)))      # faces big enough for their eyes to fire
+    n = 0
+    for mn in (0, 2):
+        got = ctx.detect_multiscale(ncasc, g, sf, mn, ms)
+        assert rects_equal(got, O.detect_multiscale(g, ocasc, sf, mn, ms)), mn
+        n += len(got)
+    assert n > 0
+    nwin, levels = check_levels(ctx, g, ocasc, sf, ms)
+    assert nwin > 1000
+    old = str(tmp_path / "old.xml")
+    write_old_format(old, O.parse_cascade_xml(p))
+    assert rects_equal(ctx.detect_multiscale(nv.Cascade(old), g, sf, 0, ms), O.detect_multiscale(g, ocasc, sf, 0, ms))
+    fp = os.path.join(cascade_dir, FACE_XML)
+    assert rects_equal(ctx.detect_multiscale(nv.Cascade(fp), g, 1.2, 2), O.detect_multiscale(g, O.Cascade(fp), 1.2, 2))
 
 
 @pytest.mark.parametrize("seed", range(6))

@@ -256,6 +256,44 @@ def test_real_cascades_live(name, cascade_dir):
             assert rects_equal(a, O.detect_multiscale(g, oc, sf, mn, ms)), (name, W, H, mn)
 
 
+GENERAL = ["haarcascade_lefteye_2splits.xml", "haarcascade_righteye_2splits.xml", "haarcascade_smile.xml",
+           "haarcascade_eye_tree_eyeglasses.xml", "haarcascade_frontalface_alt2.xml"]
+
+
+@needs_cv2
+def test_tilted_integral_live():
+    """cv::integral's third output, the sums the tilted features read."""
+    rng = np.random.default_rng(5)
+    for (h, w) in [(1, 1), (2, 3), (5, 7), (37, 53), (90, 20), (20, 90), (120, 160)]:
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert (O.integral_tilted(img) == cv2.integral3(img)[2]).all(), (h, w)
+    img = np.full((64, 64), 255, np.uint8)
+    assert (O.integral_tilted(img) == cv2.integral3(img)[2]).all()
+
+
+@needs_cv2
+@pytest.mark.parametrize("name", GENERAL)
+def test_general_cascades_live(name, cascade_dir, tmp_path):
+    """Tree weak classifiers and tilted features (predictOrdered): the eye / smile models the nested elements can
+    load in place of the absent mcs_* files, in the new and in the OpenCV-2.x XML layout."""
+    path = os.path.join(cascade_dir, name)
+    old = str(tmp_path / "old.xml")
+    write_old_format(old, O.parse_cascade_xml(path))
+    cc, oc, cco, oco = cv2.CascadeClassifier(path), O.Cascade(path), cv2.CascadeClassifier(old), O.Cascade(old)
+    assert oc.general and not cco.empty()
+    n = 0
+    for (W, H, k, seed, sf, ms) in [(480, 360, 10, 5, 1.25, (0, 0)), (320, 240, 3, 7, 1.1, (24, 24))]:
+        g = cv2.equalizeHist(cv2.cvtColor(synth.frame(W, H, k, seed, smin=0.3, smax=0.6), cv2.COLOR_BGR2GRAY))
+        for mn in (0, 2):
+            a = cc.detectMultiScale(g, scaleFactor=sf, minNeighbors=mn, minSize=ms)
+            assert rects_equal(a, O.detect_multiscale(g, oc, sf, mn, ms)), (name, W, H, mn)
+            assert rects_equal(cco.detectMultiScale(g, scaleFactor=sf, minNeighbors=mn, minSize=ms),
+                               O.detect_multiscale(g, oco, sf, mn, ms)), (name, "old layout", mn)
+            assert rects_equal(a, O.detect_multiscale(g, oco, sf, mn, ms))
+            n += len(a)
+    assert n > 0, "the test images never fire this cascade"
+
+
 @needs_cv2
 def test_old_format_cascade_live(tmp_path, cascade_dir):
     """cv2 4.13 converts OpenCV-2.x "opencv-haar-classifier" files on load and evaluates them exactly like the
