@@ -191,6 +191,11 @@ NV_API int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int widt
 NV_API int nv_element_get_message(nv_element *e, nv_meta_rect *out, int cap, int *n, int *pushed);
 NV_API int nv_element_get_signal(nv_element *e, char *buf, int cap, int *emitted);
 /* host-logic taps for unit tests: Faces::track_faces (Faces.cpp:78-153) on explicit lists */
+/* cvRectangle(img, (x0, y0), (x1, y1), Scalar(b, g, r, 0), 3, 8, 0) on a 3- or 4-channel host frame: the drawing the
+ * view-faces / view-mouths / view-noses / view-ears properties and the tracker's visual mode perform in place
+ * (BaseFace.cpp:76, kmsmouthdetect.cpp:900, kmsnosedetect.cpp:902, kmseardetect.cpp:754, gstnubotracker.cpp:389). */
+NV_API int nv_debug_draw_rectangle(uint8_t *frame, int width, int height, int stride_bytes, int channels, int x0, int y0,
+                                   int x1, int y1, int b, int g, int r);
 NV_API int nv_debug_track_faces(const nv_rect *prev, const int *prev_ids, int nprev, int next_id, const nv_rect *cur,
                                 int ncur, int track_threshold, int pos_threshold, int area_threshold, nv_rect *out,
                                 int *out_ids, int cap, int *n, int *next_id_out);

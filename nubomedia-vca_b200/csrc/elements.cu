@@ -7,7 +7,8 @@
 // Deliberate deviations: ROIs are clamped to the feature frame instead of letting
 // cv::Mat::operator() throw (EYE:988, MOUTH:867, NOSE:869); nose does not append to /tmp/nose.log; all
 // state is per element (NOSE:151-152 and TRK:108 are process-global in the reference); stdout chatter is
-// dropped (FACES:63).  view-* drawing (K13) is not implemented yet: the property is stored, nothing is drawn.
+// dropped (FACES:63).  view-* drawing: the rectangles (face, mouth, nose, ear, tracker) are drawn into the caller's
+// frame exactly as cvRectangle(.., 3, 8, 0) does; the eye element's cv::circle (EYE:1081,1095) is not drawn.
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -145,6 +146,43 @@ int upload_frame(nv_ctx *ctx, const uint8_t *frame, int stride, int h)
 }
 
 // ------------------------------------------------------------------------------------------------
+// view-* drawing, on the host: the frame is the caller's (GStreamer-mapped) memory and a handful of rectangles are
+// written per frame.  cvRectangle(img, p1, p2, color, 3, 8, 0) (BASEFACE:76, MOUTH:900, NOSE:902, EAR:754, TRK:389)
+// rasterises to the one-pixel outline dilated by the radius-2 diamond |dx| + |dy| <= 2 (each edge is a 3-wide band
+// whose ends carry a filled radius-2 circle), clipped to the image; checked pixel by pixel against cv2.rectangle in
+// tests/test_elements_cpu.py.  The colour is the cv::Scalar as the reference builds it: CV_RGB(r, g, b) = (b, g, r, 0),
+// every channel of the frame is written (the tracker's BGRA alpha becomes 0, as in the reference).
+// ------------------------------------------------------------------------------------------------
+struct Bgr { uint8_t b, g, r; };
+inline Bgr cv_rgb(int r, int g, int b) { return Bgr{(uint8_t)b, (uint8_t)g, (uint8_t)r}; }
+
+void fill_span(uint8_t *frame, int W, int H, int stride, int cn, int y, int xa, int xb, Bgr c)
+{
+    if (y < 0 || y >= H) return;
+    xa = std::max(xa, 0); xb = std::min(xb, W - 1);
+    uint8_t *row = frame + (size_t)y * stride;
+    for (int x = xa; x <= xb; x++) {
+        uint8_t *px = row + (size_t)x * cn;
+        px[0] = c.b; px[1] = c.g; px[2] = c.r;
+        if (cn == 4) px[3] = 0;
+    }
+}
+
+void draw_rectangle3(uint8_t *frame, int W, int H, int stride, int cn, int xa, int ya, int xb, int yb, Bgr c)
+{
+    const int x0 = std::min(xa, xb), x1 = std::max(xa, xb), y0 = std::min(ya, yb), y1 = std::max(ya, yb), R = 2;
+    for (int y = y0 - R; y <= y1 + R; y++) {
+        int dt = abs(y - y0), db = abs(y - y1);
+        if (dt <= R) fill_span(frame, W, H, stride, cn, y, x0 - (R - dt), x1 + (R - dt), c);      // top edge
+        if (db <= R) fill_span(frame, W, H, stride, cn, y, x0 - (R - db), x1 + (R - db), c);      // bottom edge
+        if (y >= y0 && y <= y1) {                                                                  // left and right edges
+            fill_span(frame, W, H, stride, cn, y, x0 - R, x0 + R, c);
+            fill_span(frame, W, H, stride, cn, y, x1 - R, x1 + R, c);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // shared logic
 // ------------------------------------------------------------------------------------------------
 // frame gate common to the five detectors (FACE:797-802, EYE:939-945, MOUTH:827-832, NOSE:825-830, EAR:777-782)
@@ -230,7 +268,7 @@ void track_faces(std::vector<TrackedFace> &faces, int &faces_id, std::vector<Tra
 // ------------------------------------------------------------------------------------------------
 // nubofacedetector (FACE:757-853 + 179-249)
 // ------------------------------------------------------------------------------------------------
-int face_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, double now_ms)
+int face_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double now_ms)
 {
     long w2p = e->get("width-to-process");
     if (w2p <= 0) { nv_set_error("width-to-process=0 divides by zero in the reference (FACE:304)"); return NV_ERR_ARG; }
@@ -263,6 +301,12 @@ int face_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, do
             else { e->frames_with_no_detection = 0; e->faces_tracked.clear(); }
         }
         gate_end(e);
+        if (e->get("view-faces") > 0) {                  // FACE:832-849 -> Faces::draw -> BASEFACE:70-82, colors[1]
+            const int sc = W / (int)w2p;
+            for (auto &f : e->faces_tracked)
+                draw_rectangle3(frame, W, H, stride, 3, f.r.x * sc, f.r.y * sc, (f.r.x + f.r.width - 1) * sc,
+                                (f.r.y + f.r.height - 1) * sc, cv_rgb(0, 128, 255));
+        }
     }
     // kms_face_send_event (FACE:179-249): runs every frame, also on skipped ones
     unsigned norm = (unsigned)(W / w2p);
@@ -368,7 +412,7 @@ Scales detector_scales(nv_element *e, int W)
     return {(double)o2f, (double)o2x, (double)f2x};
 }
 
-int eye_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, double now_ms)
+int eye_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double now_ms)
 {
     if (e->get("width-to-process") <= 0) { nv_set_error("width-to-process must be > 0"); return NV_ERR_ARG; }
     Scales sc = detector_scales(e, W);
@@ -445,7 +489,7 @@ int eye_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, dou
 // ------------------------------------------------------------------------------------------------
 // nubomouthdetector (MOUTH:798-908 + 198-275) and nubonosedetector (NOSE:792-911 + 208-268)
 // ------------------------------------------------------------------------------------------------
-int mouth_nose_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, double now_ms)
+int mouth_nose_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double now_ms)
 {
     if (e->get("width-to-process") <= 0) { nv_set_error("width-to-process must be > 0"); return NV_ERR_ARG; }
     const bool mouth = e->kind == K_MOUTH;
@@ -502,6 +546,19 @@ int mouth_nose_frame(nv_element *e, const uint8_t *frame, int W, int H, int stri
     if (processed) {                     // MOUTH:883-890 / NOSE:886-893: the list is rebuilt on every non-gated-out frame
         e->feat_a = res;
         gate_end(e);
+        if (e->get(mouth ? "view-mouths" : "view-noses") == 1) {        // MOUTH:895-906, NOSE:897-909: colors[j % 8]
+            static const Bgr cm[8] = {cv_rgb(255, 255, 0), cv_rgb(255, 128, 0), cv_rgb(255, 0, 0), cv_rgb(255, 0, 255),
+                                      cv_rgb(0, 128, 255), cv_rgb(0, 0, 255), cv_rgb(0, 255, 255), cv_rgb(0, 255, 0)};
+            static const Bgr cn[8] = {cv_rgb(255, 0, 255), cv_rgb(255, 0, 0), cv_rgb(255, 255, 0), cv_rgb(255, 128, 0),
+                                      cv_rgb(0, 255, 0), cv_rgb(0, 255, 255), cv_rgb(0, 128, 255), cv_rgb(0, 0, 255)};
+            int j = 0;
+            for (auto &m : e->feat_a) {
+                // the nose element's right edge is x + width, the mouth's x + width - 1 (NOSE:903, MOUTH:901)
+                draw_rectangle3(frame, W, H, stride, 3, m.x, m.y, m.x + m.width - (mouth ? 1 : 0), m.y + m.height - 1,
+                                (mouth ? cm : cn)[j % 8]);
+                j++;
+            }
+        }
     }
     std::string s;
     if (mouth) {                          // kms_mouth_send_event: faces (x int(scale_o2f)) then mouths
@@ -555,7 +612,7 @@ int ear_find(nv_element *e, const DevImg &face_img, nv_cascade *ear_cascade, dou
     return NV_OK;
 }
 
-int ear_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, double now_ms)
+int ear_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double now_ms)
 {
     if (e->get("width-to-process") <= 0) { nv_set_error("width-to-process must be > 0"); return NV_ERR_ARG; }
     float f2o_f = (float)W / 160.f, e2o_f = (float)W / (float)e->get("width-to-process"), f2e_f = f2o_f / e2o_f;   // EAR:314-316
@@ -582,6 +639,14 @@ int ear_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, dou
         }();
     }
     gate_end(e);
+    if (e->get("view-ears") == 1) {                                     // EAR:811-817: right ears, then left ears, colors[j % 8] each
+        static const Bgr ce[8] = {cv_rgb(0, 0, 255), cv_rgb(0, 128, 255), cv_rgb(0, 255, 255), cv_rgb(0, 255, 0),
+                                  cv_rgb(255, 128, 0), cv_rgb(255, 255, 0), cv_rgb(255, 0, 0), cv_rgb(255, 0, 255)};
+        for (auto *v : {&e->feat_b, &e->feat_a}) {
+            int j = 0;
+            for (auto &m : *v) { draw_rectangle3(frame, W, H, stride, 3, m.x, m.y, m.x + m.width, m.y + m.height - 1, ce[j % 8]); j++; }
+        }
+    }
     // kms_ear_send_event (EAR:192-290): builds the message (profile faces, right ears, left ears) but never pushes it
     std::string s;
     for (auto &f : e->faces) add_meta(e, "face_profile", "face_profile", f.x, f.y, f.width, f.height);
@@ -596,7 +661,7 @@ int ear_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, dou
 // ------------------------------------------------------------------------------------------------
 // nubotracker (TRK:339-421)
 // ------------------------------------------------------------------------------------------------
-int tracker_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride, uint64_t pts_ns, double now_ms)
+int tracker_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, uint64_t pts_ns, double now_ms)
 {
     nv_tracker_params p;
     p.threshold = (int)e->get("set_threshold"); p.min_area = (int)e->get("set_min_area");
@@ -609,6 +674,9 @@ int tracker_frame(nv_element *e, const uint8_t *frame, int W, int H, int stride,
     std::string s;
     bool build = e->get("set_visual_mode") > 0 || e->get("activate-events") == 1;      // TRK:383
     for (int i = 0; i < n; i++) {
+        if (e->get("set_visual_mode") > 0)                             // TRK:388-389: rec.tl() .. rec.br(), Scalar(0, 0, 255)
+            draw_rectangle3(frame, W, H, stride, 4, out[i].x, out[i].y, out[i].x + out[i].width, out[i].y + out[i].height,
+                            Bgr{0, 0, 255});
         add_meta(e, "object", "object", out[i].x, out[i].y, out[i].width, out[i].height);
         if (build && e->get("activate-events") == 1) add_signal(s, out[i].x, out[i].y, out[i].width, out[i].height);
     }
@@ -780,6 +848,17 @@ extern "C" int nv_element_get_signal(nv_element *e, char *buf, int cap, int *emi
     if (!e) { nv_set_error("null argument"); return NV_ERR_ARG; }
     if (emitted) *emitted = e->emitted ? 1 : 0;
     if (buf && cap > 0) snprintf(buf, (size_t)cap, "%s", e->emitted ? e->signal.c_str() : "");
+    return NV_OK;
+}
+
+extern "C" int nv_debug_draw_rectangle(uint8_t *frame, int width, int height, int stride_bytes, int channels, int x0, int y0,
+                                       int x1, int y1, int b, int g, int r)
+{
+    if (!frame || width <= 0 || height <= 0 || (channels != 3 && channels != 4) || stride_bytes < width * channels) {
+        nv_set_error("bad argument");
+        return NV_ERR_ARG;
+    }
+    draw_rectangle3(frame, width, height, stride_bytes, channels, x0, y0, x1, y1, Bgr{(uint8_t)b, (uint8_t)g, (uint8_t)r});
     return NV_OK;
 }
 

@@ -95,6 +95,7 @@ _SIGS = {
     "nv_event_destroy": (None, [_vp]),
     "nv_debug_cascade_stage": (_i, [_vp, _i, _ip, C.POINTER(C.c_float)]),
     "nv_debug_cascade_stump": (_i, [_vp, _i, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "nv_debug_draw_rectangle": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "nv_debug_cascade_tree": (_i, [_vp, _i, _i, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "nv_debug_cascade_feature": (_i, [_vp, _i, _ip, C.POINTER(C.c_float), _ip]),
     "nv_debug_num_levels": (_i, [_vp]),
@@ -252,6 +253,15 @@ class Element:
         sbuf = C.create_string_buffer(1 << 16); em = C.c_int(0)
         _check(_lib.nv_element_get_signal(self.handle, sbuf, len(sbuf), C.byref(em)), "nv_element_get_signal")
         return msg, bool(pushed.value), (sbuf.value.decode() if em.value else None)
+
+
+def draw_rectangle(frame, x0, y0, x1, y1, bgr):
+    """cvRectangle(frame, (x0, y0), (x1, y1), Scalar(b, g, r, 0), 3, 8, 0) in place on an HxWx3 / HxWx4 uint8 array."""
+    assert frame.dtype == np.uint8 and frame.ndim == 3 and frame.flags["C_CONTIGUOUS"]
+    h, w, cn = frame.shape
+    _check(_lib.nv_debug_draw_rectangle(_p(frame), w, h, frame.strides[0], cn, int(x0), int(y0), int(x1), int(y1),
+                                        int(bgr[0]), int(bgr[1]), int(bgr[2])), "nv_debug_draw_rectangle")
+    return frame
 
 
 def track_faces(prev, prev_ids, next_id, cur, track_threshold=40, pos_threshold=8, area_threshold=500):

@@ -85,3 +85,23 @@ def test_track_faces_random_against_restatement():
         r, oid, nid = nv.track_faces(prev, ids, 10, cur, thr)
         exp, enid = ref_track_faces(list(zip(prev, ids)), 10, cur, thr)
         assert r.tolist() == [list(x[0]) for x in exp] and oid.tolist() == [x[1] for x in exp] and nid == enid
+
+
+def test_view_rectangles_match_cv2():
+    """The view-* drawing (cvRectangle, thickness 3, 8-connected) pixel by pixel against cv2.rectangle: inside,
+    clipped by every border, degenerate, reversed corners, BGR and BGRA frames."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    cases = [(6, 5, 22, 16), (-3, -2, 5, 4), (4, 4, 4, 4), (30, 20, 10, 8), (0, 0, 63, 47), (60, 44, 70, 50),
+             (-10, 10, 80, 12), (5, -20, 7, 80), (-9, -9, -4, -4), (10, 10, 11, 10), (10, 10, 10, 13)]
+    cases += [tuple(int(v) for v in rng.integers(-8, 72, 4)) for _ in range(60)]
+    for cn in (3, 4):
+        for (x0, y0, x1, y1) in cases:
+            base = rng.integers(0, 256, (48, 64, cn), dtype=np.uint8)
+            col = tuple(int(v) for v in rng.integers(0, 256, 3))
+            exp = base.copy()
+            cv2.rectangle(exp, (x0, y0), (x1, y1), col + ((0,) if cn == 4 else ()), 3, 8, 0)
+            got = nv.draw_rectangle(base.copy(), x0, y0, x1, y1, col)
+            assert (got == exp).all(), (cn, x0, y0, x1, y1)
+    with pytest.raises(nv.NuboError):
+        nv.draw_rectangle(np.zeros((4, 4, 2), np.uint8), 0, 0, 1, 1, (1, 2, 3))

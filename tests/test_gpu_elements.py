@@ -153,3 +153,54 @@ def test_tracker_element(cdir):
         assert [list(m[2:]) for m in msg] == exp.tolist(), i
         assert (sig is not None) == (len(exp) > 0)
     e.close()
+
+
+def test_view_properties_draw_into_the_frame(cdir):
+    """view-faces / view-mouths / set_visual_mode: the frame comes back with the reference's cvRectangle drawing
+    (checked against cv2.rectangle on the emitted rectangles), and is untouched when the property is off."""
+    cv2 = pytest.importorskip("cv2")
+    f = synth.frame(640, 480, 4, 1)
+    e = nv.Element("nubofacedetector", 0, cdir)
+    g = f.copy()
+    msg, _, _ = e.process(g)
+    assert (g == f).all() and len(msg) >= 1
+    e.set("view-faces", 1)
+    g = f.copy()
+    msg, _, _ = e.process(g)
+    exp = f.copy()
+    for m in msg:                                  # BaseFace.cpp:76: (x, y) .. (x + w - 1, y + h - 1) in processing units x scale
+        x, y, w, h = (v // 4 for v in m[2:])
+        cv2.rectangle(exp, (x * 4, y * 4), ((x + w - 1) * 4, (y + h - 1) * 4), (255, 128, 0), 3, 8, 0)
+    assert (g == exp).all() and (g != f).any()
+    e.close()
+
+    frames = sequence(1280, 720, 3, 2, 2, smin=0.4, smax=0.6)
+    e = nv.Element("nubomouthdetector", 0, cdir)
+    e.set("view-mouths", 1)
+    cols = [(0, 255, 255), (0, 128, 255), (0, 0, 255), (255, 0, 255), (255, 128, 0), (255, 0, 0), (255, 255, 0), (0, 255, 0)]
+    drawn = 0
+    for fr in frames:
+        g = fr.copy()
+        msg, _, _ = e.process(g)
+        exp = fr.copy()
+        for j, m in enumerate([m for m in msg if m[1] == "mouth"]):
+            cv2.rectangle(exp, (m[2], m[3]), (m[2] + m[4] - 1, m[3] + m[5] - 1), cols[j % 8], 3, 8, 0)
+            drawn += 1
+        assert (g == exp).all()
+    assert drawn > 0
+    e.close()
+
+    seq = synth.tracker_sequence(640, 360, 4, seed=5)
+    e = nv.Element("nubotracker", 0, cdir)
+    e.set("set_visual_mode", 1)
+    drawn = 0
+    for i, fr in enumerate(seq):
+        g = fr.copy()
+        msg, _, _ = e.process(g, now_ms=1e15 + 40.0 * i)
+        exp = fr.copy()
+        for m in msg:
+            cv2.rectangle(exp, (m[2], m[3]), (m[2] + m[4], m[3] + m[5]), (0, 0, 255, 0), 3, 8, 0)
+            drawn += 1
+        assert (g == exp).all(), i
+    assert drawn > 0
+    e.close()
