@@ -464,9 +464,10 @@ def main():
                              % (B, (16 * ab["integral_px"]) >> 20),
                        "levels": len(levels), "windows_per_frame": ctxs[0].counters()["windows"],
                        "faces_found_per_frame": nfaces},
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * W * H * 3,
-                    "d2h_bytes_per_step": B * (16 + 1024 * 16), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches),
+            # whole-job figures: every rank runs the same batch shape, so bytes and launches are rank 0's times world
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": world * B * W * H * 3,
+                    "d2h_bytes_per_step": world * B * (16 + 1024 * 16), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches) * world,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "cascade (k_stage0_rows_p + k_cascade_classes<2> + k_cascade_classes<1> + k_cascade_tail_fast)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
