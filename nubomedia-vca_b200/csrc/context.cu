@@ -263,7 +263,9 @@ extern "C" int nv_ctx_create(int gpu, int max_width, int max_height, nv_ctx **ou
         uint8_t ident[256];
         for (int i = 0; i < 256; i++) ident[i] = (uint8_t)i;
         NV_CUDA(cudaMemcpy(c->d_lut + 256, ident, 256, cudaMemcpyHostToDevice));     // identity LUT
-        NV_CUDA(cudaMalloc(&c->d_plan, sizeof(PlanDev)));
+        c->slots = new PlanSlot[NV_PLAN_SLOTS];
+        c->ps = &c->slots[0];
+        for (int i = 0; i < NV_PLAN_SLOTS; i++) NV_CUDA(cudaMalloc(&c->slots[i].d_plan, sizeof(PlanDev)));
         NV_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(int)));
         return alloc_candidates(c, CAND_CAP, true);
     }();
@@ -278,12 +280,20 @@ extern "C" void nv_ctx_destroy(nv_ctx *c)
     cudaSetDevice(c->gpu);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_frame); cudaFree(c->d_frame); cudaFree(c->d_gray); cudaFree(c->d_hist); cudaFree(c->d_lut);
-    cudaFree(c->d_aux); for (auto &e : c->rtabs) cudaFree(e.d); cudaFree(c->d_plan); cudaFree(c->d_ptab); cudaFree(c->d_sum);
+    cudaFree(c->d_aux); for (auto &e : c->rtabs) cudaFree(e.d); cudaFree(c->d_sum);
+    if (c->slots) {
+        for (int i = 0; i < NV_PLAN_SLOTS; i++) {
+            PlanSlot &sl = c->slots[i];
+            cudaFree(sl.d_plan); cudaFree(sl.d_ptab); cudaFree(sl.d_maps);
+            if (sl.dexec) cudaGraphExecDestroy(sl.dexec);
+        }
+        delete[] c->slots;
+    }
     cudaFree(c->d_sq); cudaFree(c->d_pyr); cudaFree(c->d_tilt); cudaFree(c->d_vnf); cudaFree(c->d_depth);
     cudaFree(c->d_bits_ok); cudaFree(c->d_queue); cudaFree(c->d_counters); cudaFree(c->d_cand);
     cudaFree(c->d_cand_sorted); cudaFree(c->d_cand_rects); cudaFree(c->d_adj); cudaFree(c->d_result);
     cudaFreeHost(c->h_result);
-    cudaFree(c->d_maps); cudaFree(c->d_trk_prev); cudaFree(c->d_trk_mhi); cudaFree(c->d_trk_labels); cudaFree(c->d_trk_mask);
+    cudaFree(c->d_trk_prev); cudaFree(c->d_trk_mhi); cudaFree(c->d_trk_labels); cudaFree(c->d_trk_mask);
     cudaFree(c->d_trk_boxes); cudaFree(c->d_trk_misc); cudaFreeHost(c->h_trk);
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
@@ -298,7 +308,7 @@ extern "C" int nv_ctx_set_debug(nv_ctx *ctx, int debug)
     if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }
     ctx->debug = debug ? 1 : 0;
     ctx->epoch++;
-    ctx->plan_valid = false;       // debug buffers are sized with the plan
+    for (int i = 0; ctx->slots && i < NV_PLAN_SLOTS; i++) ctx->slots[i].plan_valid = false;      // debug buffers are sized with the plan
     return NV_OK;
 }
 
@@ -392,9 +402,26 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
     PlanKey key;
     key.W = W; key.H = H; key.win_w = casc->h.win_w; key.win_h = casc->h.win_h;
     key.min_w = p->min_w; key.min_h = p->min_h; key.max_w = p->max_w; key.max_h = p->max_h; key.sf = p->scale_factor;
-    if (ctx->plan_valid && key == ctx->pkey) return NV_OK;
+    key.casc = casc;
+    if (ctx->ps->plan_valid && key == ctx->ps->pkey) { ctx->ps->last_use = ++ctx->use_clock; return NV_OK; }
+    // another cached plan?  (nested ROI stages: the same few ROI sizes come back frame after frame)
+    PlanSlot *victim = nullptr;
+    for (int i = 0; i < NV_PLAN_SLOTS; i++) {
+        PlanSlot &sl = ctx->slots[i];
+        if (sl.plan_valid && key == sl.pkey) {
+            ctx->ps = &sl;
+            sl.last_use = ++ctx->use_clock;
+            if (sl.buf_gen != ctx->buf_gen) { sl.tp_casc = nullptr; sl.buf_gen = ctx->buf_gen; }   // its tensor maps point into freed buffers
+            return NV_OK;
+        }
+        if (!victim || (!sl.plan_valid && victim->plan_valid) || (sl.plan_valid == victim->plan_valid && sl.last_use < victim->last_use))
+            victim = &sl;
+    }
+    ctx->ps = victim;
+    ctx->ps->plan_valid = false;
+    ctx->ps->last_use = ++ctx->use_clock;
 
-    PlanDev &P = ctx->plan;
+    PlanDev &P = ctx->ps->plan;
     memset(&P, 0, sizeof P);
     P.W = W; P.H = H; P.win_w = key.win_w; P.win_h = key.win_h;
     int max_w = p->max_w, max_h = p->max_h;
@@ -454,8 +481,9 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
             exact_coefs(H, P.lv[l].lh, &tab[P.lv[l].ytab]);
         }
         int rc;
-        if ((rc = ensure(&ctx->d_ptab, &ctx->ptab_cap, (size_t)tofs * 2)) != NV_OK) return rc;
-        NV_CUDA(cudaMemcpy(ctx->d_ptab, tab.data(), (size_t)tofs * sizeof(int2), cudaMemcpyHostToDevice));
+        if ((rc = ensure(&ctx->ps->d_ptab, &ctx->ps->ptab_cap, (size_t)tofs * 2)) != NV_OK) return rc;
+        NV_CUDA(cudaMemcpy(ctx->ps->d_ptab, tab.data(), (size_t)tofs * sizeof(int2), cudaMemcpyHostToDevice));
+        const void *old[8] = {ctx->d_sum, ctx->d_sq, ctx->d_vnf, ctx->d_queue, ctx->d_bits_ok, ctx->d_depth, ctx->d_pyr, ctx->d_tilt};
         size_t icap = ctx->integ_cap;
         if ((rc = ensure(&ctx->d_sum, &icap, (size_t)iofs, true)) != NV_OK) return rc;
         if ((rc = ensure(&ctx->d_sq, &ctx->integ_cap, (size_t)iofs, true)) != NV_OK) return rc;
@@ -472,14 +500,19 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
             if ((rc = ensure(&ctx->d_tilt, &ctx->tilt_cap, ctx->integ_cap)) != NV_OK) return rc;
             if ((rc = ensure(&ctx->d_pyr, &ctx->pyr_cap, (size_t)pofs)) != NV_OK) return rc;
         }
-        ctx->max_lw = 0;
-        for (int l = 0; l < nl; l++) ctx->max_lw = std::max(ctx->max_lw, P.lv[l].lw);
+        ctx->ps->max_lw = 0;
+        for (int l = 0; l < nl; l++) ctx->ps->max_lw = std::max(ctx->ps->max_lw, P.lv[l].lw);
+        const void *now[8] = {ctx->d_sum, ctx->d_sq, ctx->d_vnf, ctx->d_queue, ctx->d_bits_ok, ctx->d_depth, ctx->d_pyr, ctx->d_tilt};
+        if (memcmp(old, now, sizeof old)) { ctx->buf_gen++; ctx->epoch++; }   // a shared buffer moved: tensor maps and graphs of every cached plan are stale
     }
-    NV_CUDA(cudaMemcpy(ctx->d_plan, &P, sizeof(PlanDev), cudaMemcpyHostToDevice));
-    ctx->pkey = key;
-    ctx->plan_valid = true;
-    ctx->tp_casc = nullptr;            // tensor maps and tile geometry follow the plan
-    ctx->epoch++;
+    NV_CUDA(cudaMemcpy(ctx->ps->d_plan, &P, sizeof(PlanDev), cudaMemcpyHostToDevice));
+    ctx->ps->pkey = key;
+    ctx->ps->plan_valid = true;
+    ctx->ps->tp_casc = nullptr;            // tensor maps and tile geometry follow the plan
+    ctx->ps->buf_gen = ctx->buf_gen;
+    ctx->ps->gen++;
+    if (ctx->ps->dexec) { cudaGraphExecDestroy(ctx->ps->dexec); ctx->ps->dexec = nullptr; }
+    ctx->ps->dkey = DetGraphKey(); ctx->ps->dkey_seen = DetGraphKey();
     return NV_OK;
 }
 
@@ -502,26 +535,27 @@ static encode_tiled_fn get_encode_tiled()
 
 static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
 {
-    if (ctx->tp_casc == casc) return NV_OK;
-    const PlanDev &P = ctx->plan;
+    if (ctx->ps->tp_casc == casc) return NV_OK;
+    const PlanDev &P = ctx->ps->plan;
     const DevCascade &m = casc->meta;
-    ctx->tp_casc = casc;
-    ctx->use_tiles = false;
-    ctx->epoch++;
-    ctx->use_s0p = !casc->h.general && P.nlevels > 0 && fill_stage0_params(casc, P, &ctx->s0p);
+    ctx->ps->tp_casc = casc;
+    ctx->ps->use_tiles = false;
+    ctx->ps->gen++;                                              // graphs hold the parameter banks by value
+    if (ctx->ps->dexec) { cudaGraphExecDestroy(ctx->ps->dexec); ctx->ps->dexec = nullptr; }
+    ctx->ps->use_s0p = !casc->h.general && P.nlevels > 0 && fill_stage0_params(casc, P, &ctx->ps->s0p);
     encode_tiled_fn enc = get_encode_tiled();
     if (casc->h.general || !enc || m.win_w > 32 || m.win_h > 32 || P.nlevels == 0) return NV_OK;
     // bulk stages: as many as fit the parameter bank
     int end = 1;
     while (end < m.nstages && end < NV_BULK_MAX_STAGES && m.stage_first[end + 1] - m.stage_first[1] <= NV_BULK_MAX_STUMPS) end++;
-    ctx->bulk_end = end;
+    ctx->ps->bulk_end = end;
     static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
     alignas(64) CUtensorMap maps[NV_MAX_LEVELS];
     memset(maps, 0, sizeof maps);
-    if (!ctx->d_maps) NV_CUDA(cudaMalloc(&ctx->d_maps, sizeof maps));
+    if (!ctx->ps->d_maps) NV_CUDA(cudaMalloc(&ctx->ps->d_maps, sizeof maps));
     for (int c = 0; c < 2; c++) {
         int ys = c == 0 ? 2 : 1;
-        TileParams &tp = ctx->tp[c];
+        TileParams &tp = ctx->ps->tp[c];
         // columns per plane; ys*cp is a multiple of 32 words so that windows of different rows with different
         // lx never share a bank (a raster-ordered batch of 32 alive windows is then conflict-free)
         // the pitch is 4 (mod 8) words, so that the bank class (lx + kskew * ly) & 31 of a window moves by a
@@ -547,8 +581,8 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
         }
     }
     NV_CUDA(cudaStreamSynchronize(ctx->stream));
-    NV_CUDA(cudaMemcpy(ctx->d_maps, maps, sizeof maps, cudaMemcpyHostToDevice));
-    ctx->use_tiles = true;
+    NV_CUDA(cudaMemcpy(ctx->ps->d_maps, maps, sizeof maps, cudaMemcpyHostToDevice));
+    ctx->ps->use_tiles = true;
     return NV_OK;
 }
 
@@ -567,17 +601,19 @@ static int detect_prepare(nv_ctx *ctx, nv_cascade *casc, int W, int H, const nv_
         std::lock_guard<std::mutex> lk(casc->mu);
         ctx->cur_gen = casc->d_gen[ctx->gpu];
     }
-    if ((casc->h.has_tilted != 0) != ctx->need_tilt || (casc->h.has_tilted && ctx->tilt_cap < ctx->integ_cap)) {
-        // the tilted integral and the level images it is built from exist only while a cascade with tilted features is in use
-        NV_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->need_tilt = casc->h.has_tilted != 0;
-        if (ctx->need_tilt) {
+    ctx->cur_tilted = casc->h.has_tilted != 0;
+    if (ctx->cur_tilted) {
+        // the tilted integral and the level images it is built from are allocated when the first cascade with tilted
+        // features shows up (and kept: the eye element alternates between an upright face model and tilted eye models)
+        size_t pyr_px = 0;
+        for (int l = 0; l < ctx->ps->plan.nlevels; l++) pyr_px += (size_t)ctx->ps->plan.lv[l].lw * ctx->ps->plan.lv[l].lh;
+        if (!ctx->need_tilt || ctx->tilt_cap < ctx->integ_cap || ctx->pyr_cap < pyr_px) {
+            NV_CUDA(cudaStreamSynchronize(ctx->stream));
+            ctx->need_tilt = true;
             if ((rc = ensure(&ctx->d_tilt, &ctx->tilt_cap, ctx->integ_cap)) != NV_OK) return rc;
-            size_t pyr_px = 0;
-            for (int l = 0; l < ctx->plan.nlevels; l++) pyr_px += (size_t)ctx->plan.lv[l].lw * ctx->plan.lv[l].lh;
             if ((rc = ensure(&ctx->d_pyr, &ctx->pyr_cap, pyr_px)) != NV_OK) return rc;
+            ctx->epoch++; ctx->buf_gen++;
         }
-        ctx->epoch++;
     }
     if (casc->tail_fast) {
         std::lock_guard<std::mutex> lk(casc->mu);
@@ -597,7 +633,7 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
 {
     const DevStump *stumps = ctx->cur_stumps;
     const DevCascade *meta = ctx->cur_meta;
-    const PlanDev &P = ctx->plan;
+    const PlanDev &P = ctx->ps->plan;
     cudaStream_t st = ctx->stream;
     int nl = 0;
     for (int i = 2; i <= NV_NUM_STAGES; i++) ctx->prof_set[i] = false;
@@ -605,65 +641,65 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
     if (P.nlevels > 0) {
         int16_t *depth = ctx->debug ? ctx->d_depth : nullptr;
         prof_mark(ctx, 2);
-        const uint32_t *tilt = ctx->use_gen && ctx->need_tilt ? ctx->d_tilt : nullptr;
-        NV_CUDA(launch_pyr_rowscan(ctx->d_plan, P.total_rowblk, d_gray, gstride, d_lut, ctx->d_ptab, ctx->d_sum, ctx->d_sq,
+        const uint32_t *tilt = ctx->use_gen && ctx->cur_tilted ? ctx->d_tilt : nullptr;
+        NV_CUDA(launch_pyr_rowscan(ctx->ps->d_plan, P.total_rowblk, d_gray, gstride, d_lut, ctx->ps->d_ptab, ctx->d_sum, ctx->d_sq,
                                    ctx->debug || tilt ? ctx->d_pyr : nullptr, st));
         prof_mark(ctx, 3);
-        NV_CUDA(launch_colscan(ctx->d_plan, P.total_colblk, ctx->d_sum, ctx->d_sq, st));
-        if (tilt) { NV_CUDA(launch_tilted(ctx->d_plan, P.nlevels, ctx->max_lw, ctx->d_pyr, ctx->d_tilt, st)); nl++; }
+        NV_CUDA(launch_colscan(ctx->ps->d_plan, P.total_colblk, ctx->d_sum, ctx->d_sq, st));
+        if (tilt) { NV_CUDA(launch_tilted(ctx->ps->d_plan, P.nlevels, ctx->ps->max_lw, ctx->d_pyr, ctx->d_tilt, st)); nl++; }
         prof_mark(ctx, 4);
         if (ctx->use_gen) {
-            NV_CUDA(launch_stage0_rows_gen(ctx->d_plan, P.total_rows, meta, ctx->cur_gen, ctx->d_sum, ctx->d_sq, tilt, ctx->d_vnf,
+            NV_CUDA(launch_stage0_rows_gen(ctx->ps->d_plan, P.total_rows, meta, ctx->cur_gen, ctx->d_sum, ctx->d_sq, tilt, ctx->d_vnf,
                                            ctx->d_bits_ok, ctx->d_counters, depth, st));
-        } else if (ctx->use_s0p) {
-            Stage0Params &sp = ctx->s0p;
+        } else if (ctx->ps->use_s0p) {
+            Stage0Params &sp = ctx->ps->s0p;
             sp.sum = ctx->d_sum; sp.sq = ctx->d_sq; sp.vnf = ctx->d_vnf; sp.bits_alive = ctx->d_bits_ok;
             sp.counters = ctx->d_counters; sp.depth = depth;
             NV_CUDA(launch_stage0_rows_p(sp, st));
         } else
-            NV_CUDA(launch_stage0_rows(ctx->d_plan, P.total_rows, meta, stumps, ctx->d_sum, ctx->d_sq, ctx->d_vnf,
+            NV_CUDA(launch_stage0_rows(ctx->ps->d_plan, P.total_rows, meta, stumps, ctx->d_sum, ctx->d_sq, ctx->d_vnf,
                                        ctx->d_bits_ok, ctx->d_counters, depth, st));
         prof_mark(ctx, 5);
         nl += 3;
         int qcap = (int)std::min<size_t>(ctx->queue_cap, 0x7fffffff);
-        if (ctx->use_tiles) {
+        if (ctx->ps->use_tiles) {
             for (int c = 0; c < 2; c++) {
-                TileParams &tp = ctx->tp[c];
+                TileParams &tp = ctx->ps->tp[c];
                 int ntiles = c == 0 ? P.ctiles2 : P.ctiles1;
                 if (ntiles == 0) continue;
-                tp.plan = ctx->d_plan; tp.bits_alive = ctx->d_bits_ok; tp.vnf = ctx->d_vnf; tp.depth = depth;
-                tp.tail = ctx->d_queue; tp.cand = ctx->d_cand; tp.counters = ctx->d_counters; tp.maps = ctx->d_maps;
+                tp.plan = ctx->ps->d_plan; tp.bits_alive = ctx->d_bits_ok; tp.vnf = ctx->d_vnf; tp.depth = depth;
+                tp.tail = ctx->d_queue; tp.cand = ctx->d_cand; tp.counters = ctx->d_counters; tp.maps = ctx->ps->d_maps;
                 tp.tail_cap = qcap; tp.cand_cap = ctx->cand_cap;
                 NV_CUDA(launch_cascade_classes(tp, c == 0 ? 2 : 1, ntiles, st));
                 nl++;
             }
             prof_mark(ctx, 6);
-            if (ctx->bulk_end < casc->meta.nstages && ctx->cur_tail) {
-                NV_CUDA(launch_cascade_tail_fast(ctx->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
-                                                 ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, ctx->bulk_end, st,
+            if (ctx->ps->bulk_end < casc->meta.nstages && ctx->cur_tail) {
+                NV_CUDA(launch_cascade_tail_fast(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
+                                                 ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, ctx->ps->bulk_end, st,
                                                  8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));
                 nl++;
-            } else if (ctx->bulk_end < casc->meta.nstages) {
-                NV_CUDA(launch_cascade_tail(ctx->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
-                                            ctx->cand_cap, depth, ctx->bulk_end, casc->h.order_free, 148 * 8, st,
+            } else if (ctx->ps->bulk_end < casc->meta.nstages) {
+                NV_CUDA(launch_cascade_tail(ctx->ps->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
+                                            ctx->cand_cap, depth, ctx->ps->bulk_end, casc->h.order_free, 148 * 8, st,
                                             8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));
                 nl++;
             }
         } else {
-            NV_CUDA(launch_alive_to_queue(ctx->d_plan, P.total_rows, ctx->d_vnf, ctx->d_bits_ok, ctx->d_queue, ctx->d_counters,
+            NV_CUDA(launch_alive_to_queue(ctx->ps->d_plan, P.total_rows, ctx->d_vnf, ctx->d_bits_ok, ctx->d_queue, ctx->d_counters,
                                           qcap, st));
             prof_mark(ctx, 6);
             if (ctx->use_gen)
-                NV_CUDA(launch_queue_stages_gen(ctx->d_plan, meta, ctx->cur_gen, ctx->d_sum, tilt, ctx->d_queue, ctx->d_counters,
+                NV_CUDA(launch_queue_stages_gen(ctx->ps->d_plan, meta, ctx->cur_gen, ctx->d_sum, tilt, ctx->d_queue, ctx->d_counters,
                                                 ctx->d_cand, ctx->cand_cap, depth, 148 * 8, st));
             else
-                NV_CUDA(launch_queue_stages(ctx->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
+                NV_CUDA(launch_queue_stages(ctx->ps->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
                                             ctx->cand_cap, depth, 148 * 8, st));
             nl += 2;
         }
     }
     prof_mark(ctx, 7);
-    NV_CUDA(launch_group(ctx->d_plan, ctx->d_counters, ctx->d_cand, ctx->cand_cap, ctx->d_cand_sorted, ctx->d_cand_rects,
+    NV_CUDA(launch_group(ctx->ps->d_plan, ctx->d_counters, ctx->d_cand, ctx->cand_cap, ctx->d_cand_sorted, ctx->d_cand_rects,
                          ctx->d_adj, ctx->d_grp, p->min_neighbors, 0.2, W, H, ctx->d_result, ctx->result_cap, 148 * 2, st, &nl));
     prof_mark(ctx, 8);
     NV_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(ResultHeader) + NV_RESULT_INLINE * sizeof(nv_rect),
@@ -686,8 +722,41 @@ int nv_detect_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W
 {
     int rc = detect_prepare(ctx, casc, W, H, p);
     if (rc != NV_OK) return rc;
+    // A plan that sees the same (image, cascade, parameters) again replays its launches as one CUDA graph: the nested
+    // ROI stages of the eye / mouth / nose / ear elements call this several times per frame on tiny images, where the
+    // launches cost more than the kernels.  Debug / profiling runs keep individual launches (taps and events).
+    PlanSlot *sl = ctx->ps;
+    DetGraphKey key;
+    key.gray = d_gray; key.gstride = gstride; key.lut = d_lut; key.casc = casc; key.sf = p->scale_factor; key.mn = p->min_neighbors;
+    key.epoch = ctx->epoch;
+    bool graphable = !ctx->debug && !ctx->profile && !ctx->no_graph;
     int nl = 0;
-    if ((rc = detect_enqueue(ctx, casc, d_gray, W, H, gstride, d_lut, p, &nl)) != NV_OK) return rc;
+    if (graphable && sl->dexec && key == sl->dkey) {
+        NV_CUDA(cudaGraphLaunch(sl->dexec, ctx->stream));
+        nl = sl->d_nl;
+    } else if (graphable && key == sl->dkey_seen) {
+        if (sl->dexec) { cudaGraphExecDestroy(sl->dexec); sl->dexec = nullptr; }
+        cudaGraph_t g = nullptr;
+        NV_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        rc = detect_enqueue(ctx, casc, d_gray, W, H, gstride, d_lut, p, &nl);
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        if (rc != NV_OK || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            ctx->no_graph = true;                      // capture is not possible here: stay on plain launches
+            nl = 0;
+            if ((rc = detect_enqueue(ctx, casc, d_gray, W, H, gstride, d_lut, p, &nl)) != NV_OK) return rc;
+        } else {
+            ce = cudaGraphInstantiate(&sl->dexec, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) { sl->dexec = nullptr; nv_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce)); return NV_ERR_CUDA; }
+            sl->dkey = key; sl->d_nl = nl;
+            NV_CUDA(cudaGraphLaunch(sl->dexec, ctx->stream));
+        }
+    } else {
+        sl->dkey_seen = key;
+        if ((rc = detect_enqueue(ctx, casc, d_gray, W, H, gstride, d_lut, p, &nl)) != NV_OK) return rc;
+    }
     ctx->launches += nl;
     detect_bookkeeping(ctx, casc, d_gray, W, H, gstride, d_lut, p);
     return NV_OK;
@@ -840,7 +909,7 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
     // A context that sees the same call shape again replays it as ONE CUDA graph launch (the per-stream steady
     // state of an element); debug / profiling runs keep individual launches so that their events and taps work.
     nv_ctx::GraphKey key = {d_src, width, height, stride, cols, rows, d_rtab, casc, dp.scale_factor, dp.min_neighbors,
-                            dp.min_w, dp.min_h, ctx->epoch};
+                            dp.min_w, dp.min_h, ctx->epoch, ctx->ps, ctx->ps->gen};
     bool graphable = !ctx->debug && !ctx->profile && !ctx->no_graph;
     int nl = 0;
     if (graphable && ctx->gexec && key == ctx->gkey) {
@@ -1089,19 +1158,19 @@ extern "C" int nv_tracker_process(nv_ctx *ctx, const uint8_t *bgra, int width, i
 static int tap_ready(nv_ctx *ctx, int level, bool need_level)
 {
     if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }
-    if (!ctx->plan_valid) { nv_set_error("no detect call has run on this context"); return NV_ERR_STATE; }
-    if (need_level && (level < 0 || level >= ctx->plan.nlevels)) { nv_set_error("level out of range"); return NV_ERR_ARG; }
+    if (!ctx->ps->plan_valid) { nv_set_error("no detect call has run on this context"); return NV_ERR_STATE; }
+    if (need_level && (level < 0 || level >= ctx->ps->plan.nlevels)) { nv_set_error("level out of range"); return NV_ERR_ARG; }
     NV_CUDA(cudaSetDevice(ctx->gpu));
     NV_CUDA(cudaStreamSynchronize(ctx->stream));
     return NV_OK;
 }
 
-extern "C" int nv_debug_num_levels(nv_ctx *ctx) { return ctx && ctx->plan_valid ? ctx->plan.nlevels : 0; }
+extern "C" int nv_debug_num_levels(nv_ctx *ctx) { return ctx && ctx->ps->plan_valid ? ctx->ps->plan.nlevels : 0; }
 
 extern "C" int nv_debug_level_info(nv_ctx *ctx, int level, nv_level_info *info)
 {
-    if (!ctx || !info || !ctx->plan_valid || level < 0 || level >= ctx->plan.nlevels) { nv_set_error("bad argument"); return NV_ERR_ARG; }
-    const LevelDesc &L = ctx->plan.lv[level];
+    if (!ctx || !info || !ctx->ps->plan_valid || level < 0 || level >= ctx->ps->plan.nlevels) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    const LevelDesc &L = ctx->ps->plan.lv[level];
     info->scale = L.scale; info->width = L.lw; info->height = L.lh; info->ystep = L.ystep; info->nx = L.nx; info->ny = L.ny;
     return NV_OK;
 }
@@ -1110,7 +1179,7 @@ extern "C" int nv_debug_get_gray(nv_ctx *ctx, uint8_t *dst, int cap_bytes, int *
 {
     int rc = tap_ready(ctx, 0, false);
     if (rc != NV_OK) return rc;
-    int W = ctx->plan.W, H = ctx->plan.H;
+    int W = ctx->ps->plan.W, H = ctx->ps->plan.H;
     if (width) *width = W;
     if (height) *height = H;
     if (!dst || cap_bytes < W * H) { nv_set_error("destination too small"); return NV_ERR_ARG; }
@@ -1125,7 +1194,7 @@ extern "C" int nv_debug_get_integral(nv_ctx *ctx, int level, int32_t *sum, uint3
 {
     int rc = tap_ready(ctx, level, true);
     if (rc != NV_OK) return rc;
-    const LevelDesc &L = ctx->plan.lv[level];
+    const LevelDesc &L = ctx->ps->plan.lv[level];
     size_t ne = (size_t)L.ipitch * (L.lh + 1);
     std::vector<uint32_t> tmp(ne);
     for (int a = 0; a < 2; a++) {
@@ -1145,8 +1214,8 @@ extern "C" int nv_debug_get_tilted(nv_ctx *ctx, int level, int32_t *tilted)
 {
     int rc = tap_ready(ctx, level, true);
     if (rc != NV_OK) return rc;
-    if (!ctx->need_tilt || !ctx->d_tilt || !tilted) { nv_set_error("no tilted integral: the last cascade has no tilted features"); return NV_ERR_STATE; }
-    const LevelDesc &L = ctx->plan.lv[level];
+    if (!ctx->cur_tilted || !ctx->d_tilt || !tilted) { nv_set_error("no tilted integral: the last cascade has no tilted features"); return NV_ERR_STATE; }
+    const LevelDesc &L = ctx->ps->plan.lv[level];
     NV_CUDA(cudaMemcpy2D(tilted, (size_t)(L.lw + 1) * 4, ctx->d_tilt + L.iofs, (size_t)L.ipitch * 4, (size_t)(L.lw + 1) * 4, L.lh + 1,
                          cudaMemcpyDeviceToHost));
     return NV_OK;
@@ -1157,7 +1226,7 @@ extern "C" int nv_debug_get_depth_map(nv_ctx *ctx, int level, int16_t *depth)
     int rc = tap_ready(ctx, level, true);
     if (rc != NV_OK) return rc;
     if (!ctx->debug || !ctx->d_depth || !depth) { nv_set_error("depth maps need nv_ctx_set_debug(ctx, 1) before the detect call"); return NV_ERR_STATE; }
-    const LevelDesc &L = ctx->plan.lv[level];
+    const LevelDesc &L = ctx->ps->plan.lv[level];
     NV_CUDA(cudaMemcpy(depth, ctx->d_depth + L.wofs, (size_t)L.nx * L.ny * sizeof(int16_t), cudaMemcpyDeviceToHost));
     return NV_OK;
 }
@@ -1178,7 +1247,7 @@ extern "C" int nv_debug_get_counters(nv_ctx *ctx, long long *o)
     if (!ctx || !o) { nv_set_error("null argument"); return NV_ERR_ARG; }
     const ResultHeader *h = reinterpret_cast<const ResultHeader *>(ctx->h_result);
     memset(o, 0, 8 * sizeof(long long));
-    o[0] = ctx->plan_valid ? ctx->plan.total_windows : 0;
+    o[0] = ctx->ps->plan_valid ? ctx->ps->plan.total_windows : 0;
     o[1] = h ? h->n_alive : 0;
     o[2] = h ? h->n_cand : 0;
     o[3] = ctx->launches;

@@ -142,9 +142,10 @@ struct PlanDev {
 struct PlanKey {
     int W = 0, H = 0, win_w = 0, win_h = 0, min_w = 0, min_h = 0, max_w = 0, max_h = 0;
     double sf = 0;
+    const nv_cascade *casc = nullptr;      // the tile / stage-0 parameter banks of a plan are built for one cascade
     bool operator==(const PlanKey &o) const {
         return W == o.W && H == o.H && win_w == o.win_w && win_h == o.win_h && min_w == o.min_w &&
-               min_h == o.min_h && max_w == o.max_w && max_h == o.max_h && sf == o.sf;
+               min_h == o.min_h && max_w == o.max_w && max_h == o.max_h && sf == o.sf && casc == o.casc;
     }
 };
 
@@ -223,6 +224,30 @@ struct ResultHeader {
     int overflow;       // 1 if a capacity was hit
 };
 
+// Everything that depends on one (image size, cascade window, parameters) key.  A context keeps the last
+// NV_PLAN_SLOTS of them: the nested elements run a differently sized ROI through the same context several times per
+// frame, and re-deriving + re-uploading a plan costs more than the detection itself on such small images.
+struct DetGraphKey {
+    const void *gray = nullptr; int gstride = 0; const void *lut = nullptr; const nv_cascade *casc = nullptr;
+    double sf = 0; int mn = 0; unsigned long long epoch = 0;
+    bool operator==(const DetGraphKey &o) const {
+        return gray == o.gray && gstride == o.gstride && lut == o.lut && casc == o.casc && sf == o.sf && mn == o.mn && epoch == o.epoch;
+    }
+};
+struct PlanSlot {
+    PlanKey pkey;  bool plan_valid = false;
+    PlanDev plan;                                            // host copy
+    PlanDev *d_plan = nullptr;
+    int *d_ptab = nullptr;       size_t ptab_cap = 0;       // pyramid coefficient tables
+    TileParams tp[2];  Stage0Params s0p;  bool use_s0p = false;  CUtensorMap *d_maps = nullptr;  bool use_tiles = false;
+    int bulk_end = 0;  const nv_cascade *tp_casc = nullptr;  int max_lw = 0;
+    unsigned long long last_use = 0, buf_gen = 0;            // LRU clock; generation of the shared buffers the tensor maps point into
+    unsigned long long gen = 0;                              // bumped whenever the slot's plan or parameter banks are rebuilt
+    // CUDA graph of detect_enqueue on a device-resident image (the nested ROI stages replay it frame after frame)
+    cudaGraphExec_t dexec = nullptr;  DetGraphKey dkey, dkey_seen;  int d_nl = 0;
+};
+#define NV_PLAN_SLOTS 12
+
 struct nv_ctx {
     int gpu = 0;
     int max_w = 0, max_h = 0;
@@ -243,17 +268,13 @@ struct nv_ctx {
     struct RtabEntry { ResizeKey k; int *d = nullptr; };
     RtabEntry rtabs[16];  int rtab_next = 0;
 
-    // plan
-    PlanKey pkey;  bool plan_valid = false;
-    PlanDev plan;                                            // host copy
-    PlanDev *d_plan = nullptr;
-    int *d_ptab = nullptr;       size_t ptab_cap = 0;       // pyramid coefficient tables
+    // plans (see PlanSlot); ps is the one in use
+    PlanSlot *slots = nullptr;  PlanSlot *ps = nullptr;  unsigned long long use_clock = 0, buf_gen = 1;
     uint32_t *d_sum = nullptr, *d_sq = nullptr;  size_t integ_cap = 0;   // elements
     uint8_t *d_pyr = nullptr;    size_t pyr_cap = 0;        // debug level images
     float *d_vnf = nullptr;      size_t win_cap = 0;
     int16_t *d_depth = nullptr;  size_t depth_cap = 0;      // debug only
     uint32_t *d_bits_ok = nullptr;  size_t bits_cap = 0;         // one "alive after stage 0" bit per window
-    TileParams tp[2];  Stage0Params s0p;  bool use_s0p = false;  CUtensorMap *d_maps = nullptr;  bool use_tiles = false;  int bulk_end = 0;  const nv_cascade *tp_casc = nullptr;
     uint2 *d_queue = nullptr;    size_t queue_cap = 0;
     int *d_counters = nullptr;                              // [0] queue count, [1] cand count, [2] overflow
     uint32_t *d_cand = nullptr;  int cand_cap = 0;          // packed window ids
@@ -267,16 +288,18 @@ struct nv_ctx {
     struct GraphKey {
         const void *src = nullptr; int w = 0, h = 0, stride = 0, cols = 0, rows = 0; const int *rtab = nullptr;
         const nv_cascade *casc = nullptr; double sf = 0; int mn = 0, min_w = 0, min_h = 0; unsigned long long epoch = 0;
+        const PlanSlot *slot = nullptr; unsigned long long slot_gen = 0;
         bool operator==(const GraphKey &o) const {
             return src == o.src && w == o.w && h == o.h && stride == o.stride && cols == o.cols && rows == o.rows &&
                    rtab == o.rtab && casc == o.casc && sf == o.sf && mn == o.mn && min_w == o.min_w && min_h == o.min_h &&
-                   epoch == o.epoch;
+                   epoch == o.epoch && slot == o.slot && slot_gen == o.slot_gen;
         }
     };
     const DevStump *cur_stumps = nullptr;  const DevCascade *cur_meta = nullptr;   // device copies of the cascade in use
     const TailStump *cur_tail = nullptr;  const double *cur_tail_base = nullptr;
-    GenModel cur_gen = {};  bool use_gen = false;  bool need_tilt = false;   // general cascade in use / it has tilted features
-    uint32_t *d_tilt = nullptr;  size_t tilt_cap = 0;  int max_lw = 0;
+    GenModel cur_gen = {};  bool use_gen = false;  bool cur_tilted = false;  // general cascade in use / it has tilted features
+    bool need_tilt = false;                                                  // tilted-integral buffers exist (sticky)
+    uint32_t *d_tilt = nullptr;  size_t tilt_cap = 0;
     cudaGraphExec_t gexec = nullptr;  GraphKey gkey, gkey_seen;  int g_nl = 0;  bool no_graph = false;
     unsigned long long epoch = 1;     // bumped whenever a buffer the pipeline binds is re-allocated or re-planned
 
