@@ -49,6 +49,7 @@ struct nv_element {
     Kind kind;
     std::string factory, dir;
     nv_ctx *ctx = nullptr;  int gpu = 0;
+    std::vector<nv_ctx *> aux;                                          // one stream each: the ROI cascades of a frame run side by side
     std::vector<Prop> props;
     nv_cascade *c_face = nullptr, *c_a = nullptr, *c_b = nullptr;     // face / (right eye, mouth, nose, "lear") / (left eye, "rear")
     // shared detector state (FACE:87-126 and the analogous priv structs)
@@ -127,6 +128,53 @@ int dev_detect(nv_ctx *ctx, nv_cascade *c, const uint8_t *d_img, int w, int h, i
     rc = nv_collect(ctx, out.data(), (int)out.size(), &n);
     out.resize(rc == NV_OK ? n : 0);
     return rc;
+}
+
+// The nested stage of a frame: one detectMultiScale per face ROI (two for the eye element).  Each is a chain of a
+// dozen tiny dependent kernels, so they are issued on the element's auxiliary contexts (one CUDA stream each, ROI i
+// always on context i % NV_ROI_STREAMS so that its cached plan and graph are found again next frame) behind an event
+// on the main stream, and collected together.  The host-side merging that follows consumes them in face order.
+#define NV_ROI_STREAMS 4
+struct RoiJob {
+    nv_cascade *c; const uint8_t *p; int w, h, stride; double sf; int mn, minw, minh;
+    std::vector<nv_rect> out;
+};
+
+int run_roi_jobs(nv_element *e, std::vector<RoiJob> &jobs)
+{
+    if (jobs.empty()) return NV_OK;
+    nv_ctx *ctx = e->ctx;
+    int rc;
+    while (e->aux.size() < std::min<size_t>(jobs.size(), NV_ROI_STREAMS)) {
+        nv_ctx *a = nullptr;
+        if ((rc = nv_ctx_create(e->gpu, 64, 64, &a)) != NV_OK) return rc;
+        e->aux.push_back(a);
+    }
+    NV_CUDA(cudaEventRecord(ctx->ev_done, ctx->stream));              // the feature frame is complete at this point
+    const size_t na = e->aux.size();
+    for (size_t base = 0; base < jobs.size(); base += na) {
+        size_t end = std::min(jobs.size(), base + na);
+        for (size_t i = base; i < end; i++) {
+            RoiJob &j = jobs[i];
+            j.out.clear();
+            if (!j.c || j.w <= 0 || j.h <= 0) continue;               // empty classifier / empty ROI: no detections
+            nv_ctx *a = e->aux[i - base];
+            NV_CUDA(cudaStreamWaitEvent(a->stream, ctx->ev_done, 0));
+            nv_detect_params p;
+            p.scale_factor = j.sf; p.min_neighbors = j.mn; p.flags = 0; p.min_w = j.minw; p.min_h = j.minh; p.max_w = p.max_h = 0;
+            if ((rc = nv_detect_device(a, j.c, j.p, j.w, j.h, j.stride, a->d_lut + 256, &p)) != NV_OK) return rc;
+        }
+        for (size_t i = base; i < end; i++) {
+            RoiJob &j = jobs[i];
+            if (!j.c || j.w <= 0 || j.h <= 0) continue;
+            j.out.resize(4096);
+            int n = 0;
+            rc = nv_collect(e->aux[i - base], j.out.data(), (int)j.out.size(), &n);
+            j.out.resize(rc == NV_OK ? n : 0);
+            if (rc != NV_OK) return rc;
+        }
+    }
+    return NV_OK;
 }
 
 // cv::Mat::operator()(Rect) with the rectangle clamped to the image (the reference does not check)
@@ -438,23 +486,27 @@ int eye_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double no
                 if ((r = dev_resize(ctx, e->gray, e->feat_img, cv_round(W / sc.o2x), cv_round(H / sc.o2x))) != NV_OK) return r;  // EYE:963
                 if ((r = dev_equalize(ctx, e->feat_img)) != NV_OK) return r;                                                     // EYE:964
                 int iscale = (int)sc.o2x;                                  // `int scale` parameters of the helpers
+                std::vector<RoiJob> jobs;                                  // per face: right-eye ROI, left-eye ROI
+                std::vector<nv_rect> rois;
                 for (auto &f : e->faces) {
                     nv_rect ra;
                     ra.x = (int)(f.x * sc.f2x); ra.y = (int)(f.y * sc.f2x); ra.width = (int)(f.width * sc.f2x); ra.height = (int)(f.height * sc.f2x);
                     int down = cv_roundf((float)ra.height * 40 / 100), top = cv_roundf((float)ra.height * 25 / 100);   // EYE:979-980
                     nv_rect fr = {ra.x, ra.y + top, ra.width / 2, ra.height - top - down};
                     nv_rect fl = {ra.x + ra.width / 2, ra.y + top, ra.width / 2, ra.height - top - down};
-                    std::vector<nv_rect> eye_r, eye_l;
-                    nv_rect roi = fr;
-                    if (clamp_roi(roi, e->feat_img.w, e->feat_img.h) &&
-                        (r = dev_detect(ctx, e->c_a, e->feat_img.p + (size_t)roi.y * e->feat_img.w + roi.x, roi.width, roi.height,
-                                        e->feat_img.w, 1.1, 2, 20, 20, eye_r)) != NV_OK) return r;                      // EYE:991-993
-                    fr = roi;
-                    roi = fl;
-                    if (clamp_roi(roi, e->feat_img.w, e->feat_img.h) &&
-                        (r = dev_detect(ctx, e->c_b, e->feat_img.p + (size_t)roi.y * e->feat_img.w + roi.x, roi.width, roi.height,
-                                        e->feat_img.w, 1.1, 2, 20, 20, eye_l)) != NV_OK) return r;                      // EYE:1003-1005
-                    fl = roi;
+                    for (int side = 0; side < 2; side++) {                  // EYE:991-993 (right), EYE:1003-1005 (left)
+                        nv_rect roi = side == 0 ? fr : fl;
+                        bool ok = clamp_roi(roi, e->feat_img.w, e->feat_img.h);
+                        rois.push_back(roi);
+                        jobs.push_back(RoiJob{ok ? (side == 0 ? e->c_a : e->c_b) : nullptr,
+                                              e->feat_img.p + (ok ? (size_t)roi.y * e->feat_img.w + roi.x : 0), roi.width, roi.height,
+                                              e->feat_img.w, 1.1, 2, 20, 20, {}});
+                    }
+                }
+                if ((r = run_roi_jobs(e, jobs)) != NV_OK) return r;
+                for (size_t fi = 0; fi < e->faces.size(); fi++) {
+                    nv_rect fr = rois[2 * fi], fl = rois[2 * fi + 1];
+                    std::vector<nv_rect> eye_r = std::move(jobs[2 * fi].out), eye_l = std::move(jobs[2 * fi + 1].out);
                     for (auto *v : {&eye_r, &eye_l}) {                      // transform_2_global_coordinates, EYE:902-913
                         const nv_rect &fc = v == &eye_r ? fr : fl;
                         for (auto &q : *v) { q.x = (fc.x + q.x) * iscale; q.y = (fc.y + q.y) * iscale; q.width = (q.width - 1) * iscale; q.height = (q.height - 1) * iscale; }
@@ -518,6 +570,8 @@ int mouth_nose_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, do
                 if ((r = dev_resize(ctx, e->gray, e->feat_img, cv_round(W / sc.o2x), cv_round(H / sc.o2x))) != NV_OK) return r;
                 if ((r = dev_equalize(ctx, e->feat_img)) != NV_OK) return r;
                 int iscale = (int)sc.o2x;
+                std::vector<RoiJob> jobs;
+                std::vector<nv_rect> rois;
                 for (auto &f : e->faces) {
                     nv_rect ra;
                     if (mouth) {                                            // MOUTH:859-867: lower part of the face
@@ -530,12 +584,16 @@ int mouth_nose_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, do
                         ra.y = (int)((f.y + top) * sc.f2x); ra.x = (int)((f.x + side) * sc.f2x);
                         ra.height = (int)((f.height - down - top) * sc.f2x); ra.width = (int)((f.width - side) * sc.f2x);
                     }
-                    std::vector<nv_rect> found;
                     if (!clamp_roi(ra, e->feat_img.w, e->feat_img.h)) continue;
-                    if ((r = dev_detect(ctx, e->c_a, e->feat_img.p + (size_t)ra.y * e->feat_img.w + ra.x, ra.width, ra.height,
-                                        e->feat_img.w, 1.1, 3, 1, 1, found)) != NV_OK) return r;          // MOUTH:870-873, NOSE:870-873
+                    rois.push_back(ra);
+                    jobs.push_back(RoiJob{e->c_a, e->feat_img.p + (size_t)ra.y * e->feat_img.w + ra.x, ra.width, ra.height,
+                                          e->feat_img.w, 1.1, 3, 1, 1, {}});            // MOUTH:870-873, NOSE:870-873
+                }
+                if ((r = run_roi_jobs(e, jobs)) != NV_OK) return r;
+                for (size_t i = 0; i < jobs.size(); i++) {
+                    std::vector<nv_rect> &found = jobs[i].out;
                     if (!found.empty()) {
-                        auto m = merge_consecutive(found, e->feat_a, mouth ? 4 : 6, true, ra, iscale);
+                        auto m = merge_consecutive(found, e->feat_a, mouth ? 4 : 6, true, rois[i], iscale);
                         res.insert(res.end(), m.begin(), m.end());
                     }
                 }
@@ -586,6 +644,8 @@ int ear_find(nv_element *e, const DevImg &face_img, nv_cascade *ear_cascade, dou
     if (!ears.empty()) ears.clear();
     else if (e->no_det_a < 4) e->no_det_a += 1;                                                             // MAX_NUM_FPS_WITH_NO_DETECTION
     else { e->no_det_a = 0; ears.clear(); }
+    std::vector<RoiJob> jobs;
+    std::vector<nv_rect> rois;
     for (auto &f : e->faces) {
         const int top = cv_roundf((float)f.height * 20 / 100), down = cv_roundf((float)f.height * 20 / 100);
         if (side == 0) {                                                                                    // LEFT_SIDE, EAR:688-697
@@ -598,17 +658,20 @@ int ear_find(nv_element *e, const DevImg &face_img, nv_cascade *ear_cascade, dou
             if (f.x < 0) f.x = 0;
         }
         nv_rect roi = f;
-        std::vector<nv_rect> found;
         if (!clamp_roi(roi, e->feat_img.w, e->feat_img.h)) continue;
-        if ((r = dev_detect(ctx, ear_cascade, e->feat_img.p + (size_t)roi.y * e->feat_img.w + roi.x, roi.width, roi.height,
-                            e->feat_img.w, 1.1, 3, 1, 1, found)) != NV_OK) return r;                       // EAR:712-715
-        for (auto &q : found) {
+        rois.push_back(roi);
+        jobs.push_back(RoiJob{ear_cascade, e->feat_img.p + (size_t)roi.y * e->feat_img.w + roi.x, roi.width, roi.height,
+                              e->feat_img.w, 1.1, 3, 1, 1, {}});                                           // EAR:712-715
+    }
+    if ((r = run_roi_jobs(e, jobs)) != NV_OK) return r;
+    for (size_t i = 0; i < jobs.size(); i++)
+        for (auto &q : jobs[i].out) {
+            const nv_rect &roi = rois[i];
             nv_rect a;
             a.x = cv_round((roi.x + q.x) * e2o); a.y = cv_round((roi.y + q.y) * e2o);
             a.width = (int)((q.width - 1) * e2o); a.height = (int)((q.height - 1) * e2o);
             ears.push_back(a);
         }
-    }
     return NV_OK;
 }
 
@@ -761,6 +824,7 @@ extern "C" int nv_element_create(const char *factory_name, int gpu, const char *
 
 extern "C" void nv_element_destroy(nv_element *e)
 {
+    if (e) for (nv_ctx *a : e->aux) nv_ctx_destroy(a);
     if (!e) return;
     if (e->ctx) { cudaSetDevice(e->ctx->gpu); cudaStreamSynchronize(e->ctx->stream); }
     for (DevImg *im : {&e->gray, &e->face_img, &e->feat_img, &e->flip_img}) cudaFree(im->p);
