@@ -322,7 +322,12 @@ extern "C" const char *nv_stage_name(int slot) { return slot >= 0 && slot < NV_N
 static inline void prof_mark(nv_ctx *ctx, int idx)
 {
     if (!ctx->profile) return;
-    cudaEventRecord(ctx->prof_ev[idx], ctx->stream);
+    // inside a stream capture the record becomes an event-record NODE of the graph (cudaEventRecordExternal), so that
+    // the stage times can be read after every replay
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ctx->stream, &cs);
+    if (cs == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(ctx->prof_ev[idx], ctx->stream, cudaEventRecordExternal);
+    else cudaEventRecord(ctx->prof_ev[idx], ctx->stream);
     ctx->prof_set[idx] = true;
 }
 
@@ -332,6 +337,7 @@ extern "C" int nv_ctx_set_profile(nv_ctx *ctx, int on)
     NV_CUDA(cudaSetDevice(ctx->gpu));
     if (on && !ctx->prof_ev[0])
         for (int i = 0; i <= NV_NUM_STAGES; i++) NV_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+    if (ctx->profile != (on ? 1 : 0)) ctx->epoch++;       // graphs are captured with or without the event-record nodes
     ctx->profile = on ? 1 : 0;
     return NV_OK;
 }
@@ -910,11 +916,12 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
     // state of an element); debug / profiling runs keep individual launches so that their events and taps work.
     nv_ctx::GraphKey key = {d_src, width, height, stride, cols, rows, d_rtab, casc, dp.scale_factor, dp.min_neighbors,
                             dp.min_w, dp.min_h, ctx->epoch, ctx->ps, ctx->ps->gen};
-    bool graphable = !ctx->debug && !ctx->profile && !ctx->no_graph;
+    bool graphable = !ctx->debug && !ctx->no_graph;
     int nl = 0;
     if (graphable && ctx->gexec && key == ctx->gkey) {
         NV_CUDA(cudaGraphLaunch(ctx->gexec, ctx->stream));
         nl = ctx->g_nl;
+        for (int i = 0; i <= NV_NUM_STAGES; i++) ctx->prof_set[i] = ctx->profile && ((ctx->g_prof_mask >> i) & 1u);
     } else if (graphable && key == ctx->gkey_seen) {
         if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
         cudaGraph_t g = nullptr;
@@ -932,6 +939,8 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
             cudaGraphDestroy(g);
             if (ce != cudaSuccess) { ctx->gexec = nullptr; nv_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce)); return NV_ERR_CUDA; }
             ctx->gkey = key; ctx->g_nl = nl;
+            ctx->g_prof_mask = 0;
+            for (int i = 0; i <= NV_NUM_STAGES; i++) if (ctx->prof_set[i]) ctx->g_prof_mask |= 1u << i;
             NV_CUDA(cudaGraphLaunch(ctx->gexec, ctx->stream));
         }
     } else {

@@ -300,7 +300,7 @@ struct nv_ctx {
     GenModel cur_gen = {};  bool use_gen = false;  bool cur_tilted = false;  // general cascade in use / it has tilted features
     bool need_tilt = false;                                                  // tilted-integral buffers exist (sticky)
     uint32_t *d_tilt = nullptr;  size_t tilt_cap = 0;
-    cudaGraphExec_t gexec = nullptr;  GraphKey gkey, gkey_seen;  int g_nl = 0;  bool no_graph = false;
+    cudaGraphExec_t gexec = nullptr;  GraphKey gkey, gkey_seen;  int g_nl = 0;  bool no_graph = false;  unsigned g_prof_mask = 0;
     unsigned long long epoch = 1;     // bumped whenever a buffer the pipeline binds is re-allocated or re-planned
 
     // last-call bookkeeping (kept so that collect() can re-run a call whose candidate buffers overflowed)
