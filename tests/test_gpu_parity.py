@@ -186,6 +186,37 @@ def test_old_format_and_wide_window_cascade(ctx, tmp_path, cascade_dir):
     check_levels(ctx, g2, ocasc, 1.1, (0, 0))
 
 
+def test_plan_cache_eviction_and_graph_replay(cascade_dir):
+    """A context keeps 12 plans (size, cascade, parameters) with their parameter banks, tensor maps and a CUDA graph of
+    the launches.  20 image sizes x 2 cascades through ONE non-debug context, three passes: the first pass plans, the
+    second captures graphs where a plan survived, the third replays or re-plans after eviction; plus a device-resident
+    ROI whose pointer and size repeat (the nested elements' pattern).  Every result against the oracle."""
+    c = nv.Context(0, 640, 480)
+    cascs = [(nv.Cascade(os.path.join(cascade_dir, n)), O.Cascade(os.path.join(cascade_dir, n)))
+             for n in (FACE_XML, "haarcascade_eye.xml")]
+    base = O.equalize_hist(O.bgr2gray(synth.frame(640, 480, 6, 21, smin=0.15, smax=0.5)))
+    sizes = [(60 + 23 * i, 50 + 17 * i) for i in range(20)]
+    exp = {}
+    hits = 0
+    for rep in range(3):
+        for k, (w, h) in enumerate(sizes):
+            g = np.ascontiguousarray(base[k:k + h, 2 * k:2 * k + w])
+            for ci, (ncasc, ocasc) in enumerate(cascs):
+                if (k, ci) not in exp:
+                    exp[(k, ci)] = O.detect_multiscale(g, ocasc, 1.1, 2, (20, 20))
+                got = c.detect_multiscale(ncasc, g, 1.1, 2, (20, 20))
+                assert rects_equal(got, exp[(k, ci)]), (rep, k, ci)
+                hits += len(got)
+    assert hits > 0
+    # the same two sizes alternating many times: both plans stay cached and their graphs are replayed
+    for rep in range(6):
+        for k in (3, 11):
+            w, h = sizes[k]
+            g = np.ascontiguousarray(base[k:k + h, 2 * k:2 * k + w])
+            assert rects_equal(c.detect_multiscale(cascs[0][0], g, 1.1, 2, (20, 20)), exp[(k, 0)])
+    c.close()
+
+
 def test_edge_cases(ctx, face):
     ncasc, ocasc = face
     rng = np.random.default_rng(1)
