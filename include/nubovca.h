@@ -196,6 +196,10 @@ NV_API int nv_element_get_signal(nv_element *e, char *buf, int cap, int *emitted
  * (BaseFace.cpp:76, kmsmouthdetect.cpp:900, kmsnosedetect.cpp:902, kmseardetect.cpp:754, gstnubotracker.cpp:389). */
 NV_API int nv_debug_draw_rectangle(uint8_t *frame, int width, int height, int stride_bytes, int channels, int x0, int y0,
                                    int x1, int y1, int b, int g, int r);
+/* cv::circle(img, (cx, cy), radius, Scalar(b, g, r, 0), thickness >= 2, 8, 0): the view-eyes drawing
+ * (kmseyedetect.cpp:1081,1095 use thickness 4). */
+NV_API int nv_debug_draw_circle(uint8_t *frame, int width, int height, int stride_bytes, int channels, int cx, int cy,
+                                int radius, int thickness, int b, int g, int r);
 NV_API int nv_debug_track_faces(const nv_rect *prev, const int *prev_ids, int nprev, int next_id, const nv_rect *cur,
                                 int ncur, int track_threshold, int pos_threshold, int area_threshold, nv_rect *out,
                                 int *out_ids, int cap, int *n, int *next_id_out);

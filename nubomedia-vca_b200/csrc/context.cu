@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "internal.h"
 
@@ -32,7 +33,9 @@ extern "C" int nv_cascade_load(const char *xml_path, nv_cascade **out)
 {
     if (!xml_path || !out) { nv_set_error("nv_cascade_load: null argument"); return NV_ERR_ARG; }
     *out = nullptr;
+    static std::atomic<unsigned long long> next_uid{1};
     nv_cascade *c = new nv_cascade();
+    c->uid = next_uid.fetch_add(1);
     int rc = nv_parse_cascade_xml(xml_path, &c->h);
     if (rc != NV_OK) { delete c; return rc; }
     const HostCascade &h = c->h;
@@ -408,7 +411,7 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
     PlanKey key;
     key.W = W; key.H = H; key.win_w = casc->h.win_w; key.win_h = casc->h.win_h;
     key.min_w = p->min_w; key.min_h = p->min_h; key.max_w = p->max_w; key.max_h = p->max_h; key.sf = p->scale_factor;
-    key.casc = casc;
+    key.casc = casc->uid;
     if (ctx->ps->plan_valid && key == ctx->ps->pkey) { ctx->ps->last_use = ++ctx->use_clock; return NV_OK; }
     // another cached plan?  (nested ROI stages: the same few ROI sizes come back frame after frame)
     PlanSlot *victim = nullptr;
@@ -417,7 +420,7 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         if (sl.plan_valid && key == sl.pkey) {
             ctx->ps = &sl;
             sl.last_use = ++ctx->use_clock;
-            if (sl.buf_gen != ctx->buf_gen) { sl.tp_casc = nullptr; sl.buf_gen = ctx->buf_gen; }   // its tensor maps point into freed buffers
+            if (sl.buf_gen != ctx->buf_gen) { sl.tp_casc = 0; sl.buf_gen = ctx->buf_gen; }   // its tensor maps point into freed buffers
             return NV_OK;
         }
         if (!victim || (!sl.plan_valid && victim->plan_valid) || (sl.plan_valid == victim->plan_valid && sl.last_use < victim->last_use))
@@ -514,7 +517,7 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
     NV_CUDA(cudaMemcpy(ctx->ps->d_plan, &P, sizeof(PlanDev), cudaMemcpyHostToDevice));
     ctx->ps->pkey = key;
     ctx->ps->plan_valid = true;
-    ctx->ps->tp_casc = nullptr;            // tensor maps and tile geometry follow the plan
+    ctx->ps->tp_casc = 0;                  // tensor maps and tile geometry follow the plan
     ctx->ps->buf_gen = ctx->buf_gen;
     ctx->ps->gen++;
     if (ctx->ps->dexec) { cudaGraphExecDestroy(ctx->ps->dexec); ctx->ps->dexec = nullptr; }
@@ -541,10 +544,10 @@ static encode_tiled_fn get_encode_tiled()
 
 static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
 {
-    if (ctx->ps->tp_casc == casc) return NV_OK;
+    if (ctx->ps->tp_casc == casc->uid) return NV_OK;
     const PlanDev &P = ctx->ps->plan;
     const DevCascade &m = casc->meta;
-    ctx->ps->tp_casc = casc;
+    ctx->ps->tp_casc = casc->uid;
     ctx->ps->use_tiles = false;
     ctx->ps->gen++;                                              // graphs hold the parameter banks by value
     if (ctx->ps->dexec) { cudaGraphExecDestroy(ctx->ps->dexec); ctx->ps->dexec = nullptr; }
@@ -733,7 +736,7 @@ int nv_detect_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W
     // launches cost more than the kernels.  Debug / profiling runs keep individual launches (taps and events).
     PlanSlot *sl = ctx->ps;
     DetGraphKey key;
-    key.gray = d_gray; key.gstride = gstride; key.lut = d_lut; key.casc = casc; key.sf = p->scale_factor; key.mn = p->min_neighbors;
+    key.gray = d_gray; key.gstride = gstride; key.lut = d_lut; key.casc = casc->uid; key.sf = p->scale_factor; key.mn = p->min_neighbors;
     key.epoch = ctx->epoch;
     bool graphable = !ctx->debug && !ctx->profile && !ctx->no_graph;
     int nl = 0;
@@ -914,7 +917,7 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
     };
     // A context that sees the same call shape again replays it as ONE CUDA graph launch (the per-stream steady
     // state of an element); debug / profiling runs keep individual launches so that their events and taps work.
-    nv_ctx::GraphKey key = {d_src, width, height, stride, cols, rows, d_rtab, casc, dp.scale_factor, dp.min_neighbors,
+    nv_ctx::GraphKey key = {d_src, width, height, stride, cols, rows, d_rtab, casc->uid, dp.scale_factor, dp.min_neighbors,
                             dp.min_w, dp.min_h, ctx->epoch, ctx->ps, ctx->ps->gen};
     bool graphable = !ctx->debug && !ctx->no_graph;
     int nl = 0;

@@ -230,6 +230,189 @@ void draw_rectangle3(uint8_t *frame, int W, int H, int stride, int cn, int xa, i
     }
 }
 
+// cv::circle(img, c, radius, color, thickness > 1, LINE_8, 0) (EYE:1081,1095), restated from OpenCV's drawing code:
+// the circle becomes a polygon (ellipse2Poly on its degree-indexed sine table, step 5 / 18 / 30 / 90 degrees by
+// radius), every edge a thick line = convex quad filled by the 16.16 fixed-point scanline filler after its outline
+// was traced by the fixed-point line (clipped first: the clipped end points are plotted), plus a filled circle of
+// radius thickness/2 at the joints.  Checked pixel by pixel against cv2.circle in tests/test_elements_cpu.py
+// (every radius 0..150, clipped by every border).
+namespace cvdraw {
+const int XS = 16;
+const long long ONE = 1ll << XS;
+struct Img { uint8_t *p; int W, H, stride, cn; Bgr c; };
+struct P2 { long long x, y; };
+
+inline void hline(const Img &im, int y, int xa, int xb) { fill_span(im.p, im.W, im.H, im.stride, im.cn, y, xa, xb, im.c); }
+inline void put(const Img &im, long long x, long long y) { if (x >= 0 && x < im.W && y >= 0 && y < im.H) hline(im, (int)y, (int)x, (int)x); }
+
+void filled_circle(const Img &im, int cx, int cy, int radius)
+{
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    while (dx >= dy) {
+        hline(im, cy - dy, cx - dx, cx + dx); hline(im, cy + dy, cx - dx, cx + dx);
+        hline(im, cy - dx, cx - dy, cx + dy); hline(im, cy + dx, cx - dy, cx + dy);
+        dy++; err += plus; plus += 2;
+        int mask = (err <= 0) - 1;
+        err -= minus & mask; dx += mask; minus -= mask & 2;
+    }
+}
+
+bool clip_line(long long Ws, long long Hs, P2 &a, P2 &b)
+{
+    const long long right = Ws - 1, bottom = Hs - 1;
+    if (Ws <= 0 || Hs <= 0) return false;
+    long long &x1 = a.x, &y1 = a.y, &x2 = b.x, &y2 = b.y;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long t;
+        if (c1 & 12) { t = c1 < 8 ? 0 : bottom; x1 += (long long)((double)(t - y1) * (x2 - x1) / (y2 - y1)); y1 = t; c1 = (x1 < 0) + (x1 > right) * 2; }
+        if (c2 & 12) { t = c2 < 8 ? 0 : bottom; x2 += (long long)((double)(t - y2) * (x2 - x1) / (y2 - y1)); y2 = t; c2 = (x2 < 0) + (x2 > right) * 2; }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) { t = c1 == 1 ? 0 : right; y1 += (long long)((double)(t - x1) * (y2 - y1) / (x2 - x1)); x1 = t; c1 = 0; }
+            if (c2) { t = c2 == 1 ? 0 : right; y2 += (long long)((double)(t - x2) * (y2 - y1) / (x2 - x1)); x2 = t; c2 = 0; }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
+void line2(const Img &im, P2 p1, P2 p2)                           // Line2: 16.16 fixed-point end points
+{
+    if (!clip_line((long long)im.W << XS, (long long)im.H << XS, p1, p2)) return;
+    long long dx = p2.x - p1.x, dy = p2.y - p1.y;
+    long long j = dx < 0 ? -1 : 0, ax = (dx ^ j) - j, i = dy < 0 ? -1 : 0, ay = (dy ^ i) - i;
+    long long x_step, y_step;
+    int ecount;
+    if (ax > ay) {
+        dy = (dy ^ j) - j;
+        if (j) { std::swap(p1, p2); }
+        x_step = ONE; y_step = (dy << XS) / (ax | 1); ecount = (int)((p2.x - p1.x) >> XS);
+    } else {
+        dx = (dx ^ i) - i;
+        if (i) { std::swap(p1, p2); }
+        x_step = (dx << XS) / (ay | 1); y_step = ONE; ecount = (int)((p2.y - p1.y) >> XS);
+    }
+    p1.x += ONE >> 1; p1.y += ONE >> 1;
+    put(im, (p2.x + (ONE >> 1)) >> XS, (p2.y + (ONE >> 1)) >> XS);
+    if (ax > ay) {
+        p1.x >>= XS;
+        for (; ecount >= 0; ecount--) { put(im, p1.x, p1.y >> XS); p1.x++; p1.y += y_step; }
+    } else {
+        p1.y >>= XS;
+        for (; ecount >= 0; ecount--) { put(im, p1.x >> XS, p1.y); p1.x += x_step; p1.y++; }
+    }
+}
+
+void fill_convex(const Img &im, const P2 *v, int npts)              // FillConvexPoly, shift = 16, LINE_8
+{
+    const long long delta = ONE >> 1, delta1 = ONE >> 1, delta2 = ONE >> 1;
+    struct { int idx, di; long long x, dx; int ye; } edge[2];
+    int edges = npts, imin = 0;
+    long long xmin = v[0].x, xmax = v[0].x, ymin = v[0].y, ymax = v[0].y;
+    P2 p0 = v[npts - 1];
+    for (int i = 0; i < npts; i++) {
+        P2 p = v[i];
+        if (p.y < ymin) { ymin = p.y; imin = i; }
+        ymax = std::max(ymax, p.y); xmax = std::max(xmax, p.x); xmin = std::min(xmin, p.x);
+        line2(im, p0, p);
+        p0 = p;
+    }
+    xmin = (xmin + delta) >> XS; xmax = (xmax + delta) >> XS; ymin = (ymin + delta) >> XS; ymax = (ymax + delta) >> XS;
+    if (npts < 3 || (int)xmax < 0 || (int)ymax < 0 || (int)xmin >= im.W || (int)ymin >= im.H) return;
+    ymax = std::min(ymax, (long long)im.H - 1);
+    edge[0].idx = edge[1].idx = imin;
+    int y = (int)ymin;
+    edge[0].ye = edge[1].ye = y;
+    edge[0].di = 1; edge[1].di = npts - 1;
+    edge[0].x = edge[1].x = -ONE;
+    edge[0].dx = edge[1].dx = 0;
+    do {
+        for (int i = 0; i < 2; i++) {
+            if (y >= edge[i].ye) {
+                int idx0 = edge[i].idx, di = edge[i].di, idx = idx0 + di;
+                if (idx >= npts) idx -= npts;
+                for (; edges-- > 0;) {
+                    int ty = (int)((v[idx].y + delta) >> XS);
+                    if (ty > y) {
+                        long long xs = v[idx0].x, xe = v[idx].x;
+                        edge[i].ye = ty;
+                        edge[i].dx = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y));
+                        edge[i].x = xs;
+                        edge[i].idx = idx;
+                        break;
+                    }
+                    idx0 = idx; idx += di;
+                    if (idx >= npts) idx -= npts;
+                }
+            }
+        }
+        if (edges < 0) break;
+        if (y >= 0) {
+            int left = 0, right = 1;
+            if (edge[0].x > edge[1].x) { left = 1; right = 0; }
+            int xx1 = (int)((edge[left].x + delta1) >> XS), xx2 = (int)((edge[right].x + delta2) >> XS);
+            if (xx2 >= 0 && xx1 < im.W) hline(im, y, xx1, xx2);
+        }
+        edge[0].x += edge[0].dx; edge[1].x += edge[1].dx;
+    } while (++y <= (int)ymax);
+}
+
+void thick_line(const Img &im, P2 p0, P2 p1, int thickness, int flags)
+{
+    const double inv = 1. / ONE;
+    double dx = (p0.x - p1.x) * inv, dy = (p1.y - p0.y) * inv, r = dx * dx + dy * dy;
+    const int odd = thickness & 1;
+    long long th = (long long)thickness << (XS - 1);
+    if (fabs(r) > 2.220446049250313e-16) {
+        r = (th + odd * ONE * 0.5) / sqrt(r);
+        P2 dp = {(long long)cv_round(dy * r), (long long)cv_round(dx * r)};
+        P2 pt[4] = {{p0.x + dp.x, p0.y + dp.y}, {p0.x - dp.x, p0.y - dp.y}, {p1.x - dp.x, p1.y - dp.y}, {p1.x + dp.x, p1.y + dp.y}};
+        fill_convex(im, pt, 4);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (flags & (i + 1))
+            filled_circle(im, (int)((p0.x + (ONE >> 1)) >> XS), (int)((p0.y + (ONE >> 1)) >> XS), (int)((th + (ONE >> 1)) >> XS));
+        p0 = p1;
+    }
+}
+
+void circle(uint8_t *frame, int W, int H, int stride, int cn, int cx, int cy, int radius, Bgr c, int thickness)
+{
+    static const std::vector<float> sin_tab = []() {             // OpenCV's SinTable: sine of whole degrees 0..450 written with
+        std::vector<float> t(451);                               // seven decimals and read back as float literals
+        char buf[32];
+        for (int i = 0; i <= 450; i++) {
+            snprintf(buf, sizeof buf, "%.7f", sin(i * (3.141592653589793 / 180.0)));
+            t[i] = (float)strtod(buf, nullptr);
+        }
+        return t;
+    }();
+    if (radius < 0) return;
+    Img im = {frame, W, H, stride, cn, c};
+    const P2 C = {(long long)cx * ONE, (long long)cy * ONE};
+    const long long R = (long long)radius << XS;
+    int d = (int)((R + (ONE >> 1)) >> XS);
+    const int delta = d < 3 ? 90 : d < 10 ? 30 : d < 15 ? 18 : 5;
+    std::vector<P2> v;
+    P2 prev = {-1, -1};
+    bool have_prev = false;
+    for (int a = 0; a < 360 + delta; a += delta) {               // ellipse2Poly(center, axes, 0, 0, 360, delta)
+        int ang = a > 360 ? 360 : a;
+        double x = (double)R * sin_tab[450 - ang], y = (double)R * sin_tab[ang];
+        double px = (double)C.x + x * (double)sin_tab[450] - y * (double)sin_tab[0];
+        double py = (double)C.y + x * (double)sin_tab[0] + y * (double)sin_tab[450];
+        P2 pt;
+        pt.x = (long long)cv_round(px / ONE) * ONE; pt.y = (long long)cv_round(py / ONE) * ONE;
+        pt.x += cv_round(px - (double)pt.x); pt.y += cv_round(py - (double)pt.y);
+        if (!have_prev || pt.x != prev.x || pt.y != prev.y) { v.push_back(pt); prev = pt; have_prev = true; }
+    }
+    if (v.size() <= 1) v.assign(2, C);
+    int flags = 3;
+    P2 p0 = v[0];
+    for (size_t i = 1; i < v.size(); i++) { thick_line(im, p0, v[i], thickness, flags); p0 = v[i]; flags = 2; }
+}
+}  // namespace cvdraw
+
 // ------------------------------------------------------------------------------------------------
 // shared logic
 // ------------------------------------------------------------------------------------------------
@@ -528,6 +711,19 @@ int eye_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double no
             hold(e->feat_b, e->no_det_b, res_l, 1);
         }
         gate_end(e);
+        if (e->get("view-eyes") == 1) {                  // EYE:1069-1101: one circle per side, the radius of the right eye if there is one
+            int radius = -1;
+            if (!e->feat_a.empty()) {
+                const nv_rect &q = e->feat_a[0];
+                radius = cv_round((q.width + q.height) * 0.25);
+                cvdraw::circle(frame, W, H, stride, 3, q.x + q.width / 2, q.y + q.height / 2, radius, Bgr{255, 0, 0}, 4);
+            }
+            if (!e->feat_b.empty()) {
+                const nv_rect &q = e->feat_b[0];
+                if (radius < 0) radius = cv_round((q.width + q.height) * 0.25);
+                cvdraw::circle(frame, W, H, stride, 3, q.x + q.width / 2, q.y + q.height / 2, radius, Bgr{255, 0, 0}, 4);
+            }
+        }
     }
     // kms_eye_send_event (EYE:220-308): left eyes first, then right eyes
     std::string s;
@@ -923,6 +1119,18 @@ extern "C" int nv_debug_draw_rectangle(uint8_t *frame, int width, int height, in
         return NV_ERR_ARG;
     }
     draw_rectangle3(frame, width, height, stride_bytes, channels, x0, y0, x1, y1, Bgr{(uint8_t)b, (uint8_t)g, (uint8_t)r});
+    return NV_OK;
+}
+
+extern "C" int nv_debug_draw_circle(uint8_t *frame, int width, int height, int stride_bytes, int channels, int cx, int cy,
+                                    int radius, int thickness, int b, int g, int r)
+{
+    if (!frame || width <= 0 || height <= 0 || (channels != 3 && channels != 4) || stride_bytes < width * channels ||
+        thickness < 2 || thickness > 255 || radius > 16384 || abs(cx) > (1 << 20) || abs(cy) > (1 << 20)) {
+        nv_set_error("bad argument");
+        return NV_ERR_ARG;
+    }
+    cvdraw::circle(frame, width, height, stride_bytes, channels, cx, cy, radius, Bgr{(uint8_t)b, (uint8_t)g, (uint8_t)r}, thickness);
     return NV_OK;
 }
 

@@ -93,6 +93,7 @@ struct __align__(16) TailStump {
 static_assert(sizeof(TailStump) == 48, "three 16-byte loads");
 
 struct nv_cascade {
+    unsigned long long uid = 0;           // never reused (a freed cascade's ADDRESS can be): what plans and graphs are keyed by
     HostCascade h;
     std::vector<DevStump> stumps;
     DevCascade meta;
@@ -142,7 +143,7 @@ struct PlanDev {
 struct PlanKey {
     int W = 0, H = 0, win_w = 0, win_h = 0, min_w = 0, min_h = 0, max_w = 0, max_h = 0;
     double sf = 0;
-    const nv_cascade *casc = nullptr;      // the tile / stage-0 parameter banks of a plan are built for one cascade
+    unsigned long long casc = 0;           // nv_cascade::uid: the tile / stage-0 parameter banks of a plan are built for one cascade
     bool operator==(const PlanKey &o) const {
         return W == o.W && H == o.H && win_w == o.win_w && win_h == o.win_h && min_w == o.min_w &&
                min_h == o.min_h && max_w == o.max_w && max_h == o.max_h && sf == o.sf && casc == o.casc;
@@ -228,7 +229,7 @@ struct ResultHeader {
 // NV_PLAN_SLOTS of them: the nested elements run a differently sized ROI through the same context several times per
 // frame, and re-deriving + re-uploading a plan costs more than the detection itself on such small images.
 struct DetGraphKey {
-    const void *gray = nullptr; int gstride = 0; const void *lut = nullptr; const nv_cascade *casc = nullptr;
+    const void *gray = nullptr; int gstride = 0; const void *lut = nullptr; unsigned long long casc = 0;     // nv_cascade::uid
     double sf = 0; int mn = 0; unsigned long long epoch = 0;
     bool operator==(const DetGraphKey &o) const {
         return gray == o.gray && gstride == o.gstride && lut == o.lut && casc == o.casc && sf == o.sf && mn == o.mn && epoch == o.epoch;
@@ -240,7 +241,7 @@ struct PlanSlot {
     PlanDev *d_plan = nullptr;
     int *d_ptab = nullptr;       size_t ptab_cap = 0;       // pyramid coefficient tables
     TileParams tp[2];  Stage0Params s0p;  bool use_s0p = false;  CUtensorMap *d_maps = nullptr;  bool use_tiles = false;
-    int bulk_end = 0;  const nv_cascade *tp_casc = nullptr;  int max_lw = 0;
+    int bulk_end = 0;  unsigned long long tp_casc = 0;  int max_lw = 0;       // uid of the cascade the banks were built for (0: none)
     unsigned long long last_use = 0, buf_gen = 0;            // LRU clock; generation of the shared buffers the tensor maps point into
     unsigned long long gen = 0;                              // bumped whenever the slot's plan or parameter banks are rebuilt
     // CUDA graph of detect_enqueue on a device-resident image (the nested ROI stages replay it frame after frame)
@@ -287,7 +288,7 @@ struct nv_ctx {
     // CUDA graph of the steady-state face pipeline (one launch per frame once a call shape repeats)
     struct GraphKey {
         const void *src = nullptr; int w = 0, h = 0, stride = 0, cols = 0, rows = 0; const int *rtab = nullptr;
-        const nv_cascade *casc = nullptr; double sf = 0; int mn = 0, min_w = 0, min_h = 0; unsigned long long epoch = 0;
+        unsigned long long casc = 0; double sf = 0; int mn = 0, min_w = 0, min_h = 0; unsigned long long epoch = 0;
         const PlanSlot *slot = nullptr; unsigned long long slot_gen = 0;
         bool operator==(const GraphKey &o) const {
             return src == o.src && w == o.w && h == o.h && stride == o.stride && cols == o.cols && rows == o.rows &&

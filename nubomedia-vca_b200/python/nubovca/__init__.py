@@ -96,6 +96,7 @@ _SIGS = {
     "nv_debug_cascade_stage": (_i, [_vp, _i, _ip, C.POINTER(C.c_float)]),
     "nv_debug_cascade_stump": (_i, [_vp, _i, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "nv_debug_draw_rectangle": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "nv_debug_draw_circle": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "nv_debug_cascade_tree": (_i, [_vp, _i, _i, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "nv_debug_cascade_feature": (_i, [_vp, _i, _ip, C.POINTER(C.c_float), _ip]),
     "nv_debug_num_levels": (_i, [_vp]),
@@ -261,6 +262,15 @@ def draw_rectangle(frame, x0, y0, x1, y1, bgr):
     h, w, cn = frame.shape
     _check(_lib.nv_debug_draw_rectangle(_p(frame), w, h, frame.strides[0], cn, int(x0), int(y0), int(x1), int(y1),
                                         int(bgr[0]), int(bgr[1]), int(bgr[2])), "nv_debug_draw_rectangle")
+    return frame
+
+
+def draw_circle(frame, cx, cy, radius, bgr, thickness=4):
+    """cv::circle(frame, (cx, cy), radius, Scalar(b, g, r, 0), thickness, 8, 0) in place."""
+    assert frame.dtype == np.uint8 and frame.ndim == 3 and frame.flags["C_CONTIGUOUS"]
+    h, w, cn = frame.shape
+    _check(_lib.nv_debug_draw_circle(_p(frame), w, h, frame.strides[0], cn, int(cx), int(cy), int(radius), int(thickness),
+                                     int(bgr[0]), int(bgr[1]), int(bgr[2])), "nv_debug_draw_circle")
     return frame
 
 

@@ -105,3 +105,28 @@ def test_view_rectangles_match_cv2():
             assert (got == exp).all(), (cn, x0, y0, x1, y1)
     with pytest.raises(nv.NuboError):
         nv.draw_rectangle(np.zeros((4, 4, 2), np.uint8), 0, 0, 1, 1, (1, 2, 3))
+
+
+def test_view_eyes_circle_matches_cv2():
+    """cv::circle(.., thickness 4, LINE_8) — the view-eyes drawing — pixel by pixel against cv2.circle: every radius up to
+    150 at an interior centre, then random radii and centres clipped by every border, BGR and BGRA, and the other
+    thicknesses the rasteriser supports."""
+    cv2 = pytest.importorskip("cv2")
+    for r in list(range(0, 151)) + [195, 240, 263, 274, 287, 313, 322, 326, 353, 364, 365, 367, 375, 386, 391]:
+        S = 2 * r + 40
+        exp = np.zeros((S, S, 3), np.uint8)
+        cv2.circle(exp, (S // 2, S // 2 + 1), r, (255, 0, 0), 4, 8, 0)
+        got = nv.draw_circle(np.zeros((S, S, 3), np.uint8), S // 2, S // 2 + 1, r, (255, 0, 0))
+        assert (got == exp).all(), r
+    rng = np.random.default_rng(8)
+    for t in range(500):
+        W, H, r = int(rng.integers(20, 160)), int(rng.integers(20, 160)), int(rng.integers(0, 90))
+        cx, cy = int(rng.integers(-40, W + 40)), int(rng.integers(-40, H + 40))
+        cn = 3 + t % 2
+        th = 4 if t % 5 else int(rng.integers(2, 9))
+        base = rng.integers(0, 256, (H, W, cn), dtype=np.uint8)
+        col = tuple(int(v) for v in rng.integers(0, 256, 3))
+        exp = base.copy()
+        cv2.circle(exp, (cx, cy), r, col + ((0,) if cn == 4 else ()), th, 8, 0)
+        got = nv.draw_circle(base.copy(), cx, cy, r, col, th)
+        assert (got == exp).all(), (W, H, r, cx, cy, cn, th)

@@ -190,6 +190,26 @@ def test_view_properties_draw_into_the_frame(cdir):
     assert drawn > 0
     e.close()
 
+    e = nv.Element("nuboeyedetector", 0, cdir)
+    e.set("view-eyes", 1)
+    drawn = 0
+    for fr in frames:
+        g = fr.copy()
+        msg, _, _ = e.process(g)
+        exp = fr.copy()
+        rights = [m for m in msg if m[0] == "eye_right"]; lefts = [m for m in msg if m[0] == "eye_left"]
+        radius = -1                                   # kmseyedetect.cpp:1069-1101: first right eye, first left eye, one radius
+        for lst in (rights, lefts):
+            if lst:
+                m = lst[0]
+                if radius < 0:
+                    radius = int(np.rint((m[4] + m[5]) * 0.25))
+                cv2.circle(exp, (m[2] + m[4] // 2, m[3] + m[5] // 2), radius, (255, 0, 0), 4, 8, 0)
+                drawn += 1
+        assert (g == exp).all()
+    assert drawn > 0
+    e.close()
+
     seq = synth.tracker_sequence(640, 360, 4, seed=5)
     e = nv.Element("nubotracker", 0, cdir)
     e.set("set_visual_mode", 1)

@@ -208,6 +208,16 @@ def test_plan_cache_eviction_and_graph_replay(cascade_dir):
                 assert rects_equal(got, exp[(k, ci)]), (rep, k, ci)
                 hits += len(got)
     assert hits > 0
+    # cascades that are freed and re-created in turn (a new one may land on the old one's ADDRESS: plans are keyed by a
+    # never-reused id, not by the pointer), same image and parameters every time
+    g = np.ascontiguousarray(base[:300, :400])
+    names = [FACE_XML, "haarcascade_frontalface_alt2.xml", "haarcascade_eye.xml", "haarcascade_lefteye_2splits.xml"]
+    want = [O.detect_multiscale(g, O.Cascade(os.path.join(cascade_dir, n)), 1.2, 2) for n in names]
+    for rep in range(3):
+        for n, w_ in zip(names, want):
+            tmp = nv.Cascade(os.path.join(cascade_dir, n))
+            assert rects_equal(c.detect_multiscale(tmp, g, 1.2, 2), w_), (rep, n)
+            del tmp
     # the same two sizes alternating many times: both plans stay cached and their graphs are replayed
     for rep in range(6):
         for k in (3, 11):
