@@ -102,6 +102,40 @@ def test_feature_elements_cfg2(cdir, kind, factory, files):
     e.close()
 
 
+def test_feature_elements_with_tree_and_tilted_models(tmp_path, cascade_dir):
+    """The nested elements with REAL feature models under the reference's file names: haarcascade_smile.xml (tilted
+    features) as the mouth model, righteye/lefteye_2splits (trees + tilted features) as the eye models.  These run the
+    predictOrdered kernels and the tilted integral, per ROI, on the auxiliary streams."""
+    d = tmp_path
+    face = "haarcascade_frontalface_alt.xml"
+    shutil.copy(os.path.join(cascade_dir, face), d / face)
+    for src, dst in [("haarcascade_smile.xml", "haarcascade_mcs_mouth.xml"), ("haarcascade_righteye_2splits.xml", "haarcascade_mcs_righteye.xml"),
+                     ("haarcascade_lefteye_2splits.xml", "haarcascade_mcs_lefteye.xml")]:
+        shutil.copy(os.path.join(cascade_dir, src), d / dst)
+    frames = sequence(1280, 720, 3, 2, 3, smin=0.4, smax=0.6)
+    e = nv.Element("nubomouthdetector", 0, str(d))
+    ref = FeatureRef("mouth", oc(str(d), face), oc(str(d), "haarcascade_mcs_mouth.xml"))
+    total = 0
+    for i, f in enumerate(frames):
+        msg, _, _ = e.process(f)
+        assert msg == ref.process(f), i
+        total += sum(1 for m in msg if m[1] == "mouth")
+    assert total > 0
+    e.close()
+    frames = sequence(1280, 720, 2, 3, 3, smin=0.5, smax=0.9)
+    e = nv.Element("nuboeyedetector", 0, str(d))
+    e.set("width-to-process", 640)
+    ref = FeatureRef("eye", oc(str(d), face), oc(str(d), "haarcascade_mcs_righteye.xml"), oc(str(d), "haarcascade_mcs_lefteye.xml"))
+    ref.p["w2p"] = 640
+    total = 0
+    for i, f in enumerate(frames):
+        msg, _, _ = e.process(f)
+        assert msg == ref.process(f), i
+        total += len(msg)
+    assert total > 0
+    e.close()
+
+
 def test_feature_element_faces_from_upstream_event(cdir):
     """ROI nesting through the downstream metadata event: the face element's rectangles (original-image
     coordinates) feed the mouth element in detect-event mode (kmseyedetect.cpp:954-961 pattern)."""
