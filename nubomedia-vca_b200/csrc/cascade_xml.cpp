@@ -175,22 +175,27 @@ static int finish_cascade(HostCascade *hc, const std::vector<ParsedTree> &trees,
     for (size_t f = 0; f < hc->feat_weight.size() / 3; f++)
         if (hc->feat_weight[3 * f + 2] != 0.f) hc->n3rect++;
 
-    // Exactness certificate for parallel stage sums: OpenCV adds the float leaves one by one into a
-    // double.  If, for every stage, (sum of |leaf|) / (smallest unit-in-last-place of any leaf) fits in
-    // 2^52, no addition can round, so any summation order gives the same double.  (Stump cascades only.)
-    hc->order_free = hc->general ? 0 : 1;
-    size_t si = 0;
+    // Exactness certificate for parallel stage sums: OpenCV adds one float leaf per weak classifier, one by one, into
+    // a double.  Every partial sum in ANY order is a sum of one leaf from each of some trees: a multiple of the smallest
+    // unit-in-last-place of any leaf of the stage, bounded by the sum over trees of the largest |leaf|.  If that bound
+    // stays below 2^52 such units, no addition can round and every order gives the same double.
+    hc->order_free = 1;
+    size_t ti = 0, li = 0;
     for (int nt : hc->stage_ntrees) {
         double mag = 0, min_ulp = INFINITY;
-        for (int i = 0; i < nt; i++, si++)
-            for (float leaf : {hc->stump_left[si], hc->stump_right[si]}) {
+        for (int i = 0; i < nt; i++, ti++) {
+            double big = 0;
+            for (int k = 0; k <= hc->tree_nnodes[ti]; k++, li++) {
+                float leaf = hc->leaves[li];
                 if (leaf == 0.f) continue;
                 if (!isfinite(leaf)) { hc->order_free = 0; continue; }
                 int e;
                 frexp((double)leaf, &e);                 // |leaf| in [2^(e-1), 2^e)
-                mag += fabs((double)leaf);
+                big = fmax(big, fabs((double)leaf));
                 min_ulp = fmin(min_ulp, ldexp(1.0, e - 24));
             }
+            mag += big;
+        }
         if (mag > 0 && mag / min_ulp >= 4503599627370496.0) hc->order_free = 0;
     }
     return NV_OK;

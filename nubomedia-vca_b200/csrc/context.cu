@@ -473,6 +473,7 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         L.colblk0 = P.total_colblk; P.total_colblk += (L.ipitch + 31) / 32;
         L.chunk0 = P.total_chunks; P.total_chunks += L.nxw * L.ny;
         L.row0 = P.total_rows; P.total_rows += L.ny;
+        L.dblk0 = P.total_dblk; P.total_dblk += (lw + lh + 255) / 256;
         L.cntx = (L.nx + NV_CTX - 1) / NV_CTX;
         int cnt = L.cntx * ((L.ny + NV_CTY - 1) / NV_CTY);
         if (ystep == 2) { L.ctile0 = P.ctiles2; P.ctiles2 += cnt; P.nlv2 = nl; }
@@ -652,10 +653,10 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         prof_mark(ctx, 2);
         const uint32_t *tilt = ctx->use_gen && ctx->cur_tilted ? ctx->d_tilt : nullptr;
         NV_CUDA(launch_pyr_rowscan(ctx->ps->d_plan, P.total_rowblk, d_gray, gstride, d_lut, ctx->ps->d_ptab, ctx->d_sum, ctx->d_sq,
-                                   ctx->debug || tilt ? ctx->d_pyr : nullptr, st));
+                                   ctx->debug ? ctx->d_pyr : nullptr, st));
         prof_mark(ctx, 3);
         NV_CUDA(launch_colscan(ctx->ps->d_plan, P.total_colblk, ctx->d_sum, ctx->d_sq, st));
-        if (tilt) { NV_CUDA(launch_tilted(ctx->ps->d_plan, P.nlevels, ctx->ps->max_lw, ctx->d_pyr, ctx->d_tilt, st)); nl++; }
+        if (tilt) { NV_CUDA(launch_tilted(ctx->ps->d_plan, P.total_dblk, ctx->d_sum, ctx->d_tilt, st)); nl += 2; }
         prof_mark(ctx, 4);
         if (ctx->use_gen) {
             NV_CUDA(launch_stage0_rows_gen(ctx->ps->d_plan, P.total_rows, meta, ctx->cur_gen, ctx->d_sum, ctx->d_sq, tilt, ctx->d_vnf,
@@ -700,7 +701,7 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
             prof_mark(ctx, 6);
             if (ctx->use_gen)
                 NV_CUDA(launch_queue_stages_gen(ctx->ps->d_plan, meta, ctx->cur_gen, ctx->d_sum, tilt, ctx->d_queue, ctx->d_counters,
-                                                ctx->d_cand, ctx->cand_cap, depth, 148 * 8, st));
+                                                ctx->d_cand, ctx->cand_cap, depth, 148 * 8, casc->h.order_free, st));
             else
                 NV_CUDA(launch_queue_stages(ctx->ps->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
                                             ctx->cand_cap, depth, 148 * 8, st));

@@ -127,6 +127,7 @@ struct LevelDesc {
     int colblk0;           // first column-block (32 physical cols) in k_colscan's grid (per array)
     int chunk0;            // first 32-window chunk (row-major over levels)
     int row0;              // first window row in k_stage0_rows' grid
+    int dblk0;             // first block (256 diagonals) of this level in the tilted-integral kernels' grid
     int ctile0, cntx;      // k_cascade_classes: first 64x32-window tile within the ystep class, tile columns = ceil(nx/64)
 };
 
@@ -137,6 +138,7 @@ struct PlanDev {
     int total_rowblk, total_colblk, total_chunks, total_rows, total_windows;
     int nlv2;              // levels [0, nlv2) have ystep 2, [nlv2, nlevels) ystep 1 (scales ascend)
     int ctiles2, ctiles1;  // 64x32-window tile counts of the two ystep classes
+    int total_dblk;        // blocks of the tilted-integral kernels
     LevelDesc lv[NV_MAX_LEVELS];
 };
 
@@ -343,7 +345,7 @@ enum { RT_COPY = 0, RT_BOX2 = 1, RT_LINEAR = 2 };
 cudaError_t launch_pyr_rowscan(const PlanDev *plan, int total_rowblk, const uint8_t *gray, int gstride, const uint8_t *lut,
                                const int *ptab, uint32_t *sum, uint32_t *sq, uint8_t *pyr_debug, cudaStream_t st);
 cudaError_t launch_colscan(const PlanDev *plan, int total_colblk, uint32_t *sum, uint32_t *sq, cudaStream_t st);
-cudaError_t launch_tilted(const PlanDev *plan, int nlevels, int max_lw, const uint8_t *pyr, uint32_t *tilt, cudaStream_t st);
+cudaError_t launch_tilted(const PlanDev *plan, int total_dblk, const uint32_t *sum, uint32_t *tilt, cudaStream_t st);
 
 // kernels_cascade.cu
 cudaError_t launch_queue_stages(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,
@@ -358,7 +360,7 @@ cudaError_t launch_stage0_rows_gen(const PlanDev *plan, int total_rows, const De
                                    uint32_t *bits_alive, int *counters, int16_t *depth, cudaStream_t st);
 cudaError_t launch_queue_stages_gen(const PlanDev *plan, const DevCascade *meta, const GenModel &g, const uint32_t *sum,
                                     const uint32_t *tilt, const uint2 *queue, int *counters, uint32_t *cand, int cand_cap,
-                                    int16_t *depth, int nblocks, cudaStream_t st);
+                                    int16_t *depth, int nblocks, int order_free, cudaStream_t st);
 cudaError_t launch_cascade_classes(const TileParams &tp, int ystep, int ntiles, cudaStream_t st);
 cudaError_t launch_stage0_rows_p(const Stage0Params &sp, cudaStream_t st);
 bool fill_stage0_params(const nv_cascade *c, const PlanDev &P, Stage0Params *sp);

@@ -233,6 +233,49 @@ k_queue_stages_gen(const PlanDev *__restrict__ plan, const DevCascade *__restric
     }
 }
 
+// The same with one WARP per window and one lane per tree of the stage (exact when the stage sums are order-free,
+// cascade_xml.cpp): a window that passes twenty stages of twenty trees is twenty rounds of tree walks deep instead of
+// four hundred, which is what the latency of a small nested-ROI call is made of.  Windows are handed out dynamically.
+__global__ void __launch_bounds__(256)
+k_queue_stages_gen_warp(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ meta, const GenModel g,
+                        const uint32_t *__restrict__ sum, const uint32_t *__restrict__ tilt, const uint2 *__restrict__ queue,
+                        int *__restrict__ counters, uint32_t *__restrict__ cand, int cand_cap, int16_t *__restrict__ depth)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = counters[0], nstages = meta->nstages;
+    for (;;) {
+        int e = 0;
+        if (lane == 0) e = atomicAdd(&counters[5], 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= n) break;
+        uint2 q = queue[e];
+        int l = q.x >> 26, iy = (q.x >> 13) & 8191, ix = q.x & 8191;
+        float vnf = __uint_as_float(q.y);
+        const LevelDesc &L = plan->lv[l];
+        LevelView v{sum + L.iofs, L.ipitch, L.iplane, L.ystep};
+        size_t rowbase = (size_t)iy * L.ystep * L.ipitch;
+        const uint32_t *wb = v.sum + rowbase + ix;
+        const uint32_t *tb = tilt ? tilt + L.iofs + rowbase + ix * L.ystep : nullptr;
+        int code = NV_DEPTH_PASS;
+        for (int st = 1; st < nstages; st++) {
+            const int t0 = meta->stage_first[st], t1 = meta->stage_first[st + 1];
+            double tmp = 0.;
+            for (int t = t0 + lane; t < t1; t += 32) tmp = __dadd_rn(tmp, gen_stage_sum(g, t, t + 1, wb, v, tb, L.ipitch, vnf));
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) tmp = __dadd_rn(tmp, __shfl_xor_sync(0xffffffffu, tmp, d));
+            if (tmp < (double)meta->stage_thr[st]) { code = -st; break; }
+        }
+        if (lane == 0) {
+            if (depth) depth[L.wofs + iy * L.nx + ix] = (int16_t)code;
+            if (code == NV_DEPTH_PASS) {
+                int pos = atomicAdd(&counters[1], 1);
+                if (pos < cand_cap) cand[pos] = q.x;
+                else counters[2] = 1;
+            }
+        }
+    }
+}
+
 // ================================================================================================
 // pass structure (all levels per launch):
 //   k_stage0_rows      one warp per window ROW: variance + stage 0 for each 32-window chunk, the skip
@@ -1080,9 +1123,10 @@ cudaError_t launch_stage0_rows_gen(const PlanDev *plan, int total_rows, const De
 
 cudaError_t launch_queue_stages_gen(const PlanDev *plan, const DevCascade *meta, const GenModel &g, const uint32_t *sum,
                                     const uint32_t *tilt, const uint2 *queue, int *counters, uint32_t *cand, int cand_cap,
-                                    int16_t *depth, int nblocks, cudaStream_t st)
+                                    int16_t *depth, int nblocks, int order_free, cudaStream_t st)
 {
-    k_queue_stages_gen<<<nblocks, 256, 0, st>>>(plan, meta, g, sum, tilt, queue, counters, cand, cand_cap, depth);
+    if (order_free) k_queue_stages_gen_warp<<<nblocks, 256, 0, st>>>(plan, meta, g, sum, tilt, queue, counters, cand, cand_cap, depth);
+    else k_queue_stages_gen<<<nblocks, 256, 0, st>>>(plan, meta, g, sum, tilt, queue, counters, cand, cand_cap, depth);
     return cudaGetLastError();
 }
 

@@ -112,53 +112,63 @@ k_colscan(const PlanDev *__restrict__ plan, int total_colblk, uint32_t *__restri
 }
 
 // Tilted integral (cv::integral's third output; only for cascades with tilted features).  tilted(X,Y) = sum of the
-// level's pixels in the 45-degree triangle whose apex is pixel (X-1, Y-1); three-term recurrence over rows
-//   T(X,Y) = T(X-1,Y-1) + T(X+1,Y-1) - T(X,Y-2) + img(X-1,Y-1) + img(X-1,Y-2)
-// closed on the columns 0..lw by T(-1,Y) = T(0,Y-1) and T(lw+1,Y) = T(lw,Y-1) (the strips those triangles would add lie
-// outside the image).  Rows depend on the two rows above, so ONE block walks a level top to bottom, its threads
-// striding over the columns with the last two rows kept in shared memory; levels run in parallel blocks.  Plain row
-// layout (no column de-interleave), pitch and level offsets shared with the upright integrals.
-__global__ void __launch_bounds__(1024)
-k_tilted(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ pyr, uint32_t *__restrict__ tilt)
+// level's pixels in the 45-degree triangle whose apex is pixel (X-1, Y-1).  Row y < Y of the triangle is the pixel run
+// [X-1-k, X-1+k], k = Y-1-y, clipped to the image, i.e. R(y, cl(X+k)) - R(y, cl(X-1-k)) with the row prefix
+// R(y, x) = sum[y+1][x] - sum[y][x] taken from the finished upright integral and cl() clamping to [0, lw].  So
+//   tilted(X,Y) = A(X,Y) - B(X,Y),   A = sum_y R(y, cl(X+Y-1-y)),   B = sum_y R(y, cl(X-Y+y)),
+// and A only depends on the anti-diagonal d = X+Y, B on the diagonal e = X-Y: ONE THREAD PER DIAGONAL walks down its
+// diagonal keeping a running sum (a thread's leading rows, where the run is clipped to a whole row or to nothing,
+// collapse to sum[y0][lw] or 0), no synchronisation, consecutive threads on consecutive addresses.  Pass A writes,
+// pass B subtracts.  Plain row layout, pitch and level offsets shared with the upright integrals.
+struct TiltView {
+    const uint32_t *S; uint32_t *T; int lw, lh, pitch, plane, ys;
+    __device__ __forceinline__ uint32_t s(int y, int x) const { return __ldg(S + (size_t)y * pitch + (ys == 2 ? (x & 1) * plane + (x >> 1) : x)); }
+};
+
+__device__ __forceinline__ bool tilt_setup(const PlanDev *__restrict__ plan, const uint32_t *sum, uint32_t *tilt, TiltView &v, int &i)
 {
-    extern __shared__ uint32_t s_rows[];                         // 3 x (lw + 1): rows Y-2, Y-1, Y (rotating)
-    const LevelDesc &L = plan->lv[blockIdx.x];
-    const int lw = L.lw, lh = L.lh, pitch = L.ipitch, n = lw + 1;
-    const uint8_t *img = pyr + L.pofs;
-    uint32_t *out = tilt + L.iofs;
-    uint32_t *r0 = s_rows, *r1 = s_rows + n, *r2 = s_rows + 2 * n;
-    for (int x = threadIdx.x; x < n; x += blockDim.x) { r0[x] = 0; r1[x] = 0; out[x] = 0; }
-    __syncthreads();
-    for (int Y = 1; Y <= lh; Y++) {
-        const uint8_t *i1 = img + (size_t)(Y - 1) * lw, *i2 = Y >= 2 ? img + (size_t)(Y - 2) * lw : nullptr;
-        for (int X = threadIdx.x; X < n; X += blockDim.x) {
-            uint32_t left = X > 0 ? r1[X - 1] : r0[0], right = X < lw ? r1[X + 1] : r0[lw];
-            uint32_t v = left + right - r0[X];
-            if (X > 0) v += (uint32_t)i1[X - 1] + (i2 ? (uint32_t)i2[X - 1] : 0u);
-            r2[X] = v;
-            out[(size_t)Y * pitch + X] = v;
-        }
-        __syncthreads();
-        uint32_t *t = r0; r0 = r1; r1 = r2; r2 = t;
+    int l = find_level(plan, blockIdx.x, &LevelDesc::dblk0);
+    const LevelDesc &L = plan->lv[l];
+    v = TiltView{sum + L.iofs, tilt + L.iofs, L.lw, L.lh, L.ipitch, L.iplane, L.ystep};
+    i = (blockIdx.x - L.dblk0) * 256 + threadIdx.x;              // diagonal index, 0 .. lw + lh - 1
+    return i < L.lw + L.lh;
+}
+
+__global__ void __launch_bounds__(256)
+k_tilt_a(const PlanDev *__restrict__ plan, const uint32_t *__restrict__ sum, uint32_t *__restrict__ tilt)
+{
+    TiltView v; int i;
+    if (!tilt_setup(plan, sum, tilt, v, i)) return;
+    const int d = i + 1;                                         // X + Y, 1 .. lw + lh
+    if (d - 1 <= v.lw) v.T[d - 1] = 0u;                          // row Y = 0
+    int y0 = max(0, d - 1 - v.lw);                               // rows above y0: the run is clipped to the whole row
+    uint32_t acc = v.s(y0, v.lw);
+    for (int y = y0; y < v.lh && y < d; y++) {
+        int X = d - 1 - y;                                       // 0 <= X <= lw here
+        acc += v.s(y + 1, X) - v.s(y, X);
+        v.T[(size_t)(y + 1) * v.pitch + X] = acc;
     }
 }
 
-cudaError_t launch_tilted(const PlanDev *plan, int nlevels, int max_lw, const uint8_t *pyr, uint32_t *tilt, cudaStream_t st)
+__global__ void __launch_bounds__(256)
+k_tilt_b(const PlanDev *__restrict__ plan, const uint32_t *__restrict__ sum, uint32_t *__restrict__ tilt)
 {
-    size_t smem = 3 * (size_t)(max_lw + 1) * sizeof(uint32_t);
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    static std::mutex mu;
-    static unsigned long long attr_set = 0ull;
-    if (smem > 48 * 1024) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        std::lock_guard<std::mutex> lk(mu);
-        if (!((attr_set >> (dev & 63)) & 1ull)) {
-            cudaFuncSetAttribute(k_tilted, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set |= 1ull << (dev & 63);
-        }
+    TiltView v; int i;
+    if (!tilt_setup(plan, sum, tilt, v, i)) return;
+    const int e = i - v.lh;                                      // X - Y, -lh .. lw - 1
+    uint32_t acc = 0u;
+    for (int y = max(0, -e); y < v.lh; y++) {                    // rows above: the run starts left of the image
+        int X = e + y + 1;
+        if (X > v.lw) break;
+        acc += v.s(y + 1, X - 1) - v.s(y, X - 1);                // R(y, X - 1), 0 <= X - 1 < lw
+        v.T[(size_t)(y + 1) * v.pitch + X] -= acc;
     }
-    k_tilted<<<nlevels, 1024, smem, st>>>(plan, pyr, tilt);
+}
+
+cudaError_t launch_tilted(const PlanDev *plan, int total_dblk, const uint32_t *sum, uint32_t *tilt, cudaStream_t st)
+{
+    k_tilt_a<<<total_dblk, 256, 0, st>>>(plan, sum, tilt);
+    k_tilt_b<<<total_dblk, 256, 0, st>>>(plan, sum, tilt);
     return cudaGetLastError();
 }
 

@@ -150,7 +150,7 @@ def test_general_cascade_loader(name, cascade_dir, tmp_path):
         c = nv.Cascade(p)
         assert c.info.general == 1 and c.info.has_tilted == int(d["feat_tilted"].any())
         assert c.info.nstumps == len(d["tree_nnodes"]) and c.info.nnodes == len(d["node_feat"])
-        assert c.info.order_free_sums == 0
+        assert c.info.order_free_sums == 1          # these models' stage sums are exact in any order
         n0 = l0 = 0
         for t in range(c.info.nstumps):
             nodes, thr, leaves = c.tree(t)
