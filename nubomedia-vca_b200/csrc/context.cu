@@ -506,10 +506,7 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
             if ((rc = ensure(&ctx->d_depth, &ctx->depth_cap, (size_t)wofs)) != NV_OK) return rc;
             if ((rc = ensure(&ctx->d_pyr, &ctx->pyr_cap, (size_t)pofs)) != NV_OK) return rc;
         }
-        if (ctx->need_tilt) {
-            if ((rc = ensure(&ctx->d_tilt, &ctx->tilt_cap, ctx->integ_cap)) != NV_OK) return rc;
-            if ((rc = ensure(&ctx->d_pyr, &ctx->pyr_cap, (size_t)pofs)) != NV_OK) return rc;
-        }
+        if (ctx->need_tilt && (rc = ensure(&ctx->d_tilt, &ctx->tilt_cap, ctx->integ_cap)) != NV_OK) return rc;
         ctx->ps->max_lw = 0;
         for (int l = 0; l < nl; l++) ctx->ps->max_lw = std::max(ctx->ps->max_lw, P.lv[l].lw);
         const void *now[8] = {ctx->d_sum, ctx->d_sq, ctx->d_vnf, ctx->d_queue, ctx->d_bits_ok, ctx->d_depth, ctx->d_pyr, ctx->d_tilt};
@@ -613,15 +610,12 @@ static int detect_prepare(nv_ctx *ctx, nv_cascade *casc, int W, int H, const nv_
     }
     ctx->cur_tilted = casc->h.has_tilted != 0;
     if (ctx->cur_tilted) {
-        // the tilted integral and the level images it is built from are allocated when the first cascade with tilted
-        // features shows up (and kept: the eye element alternates between an upright face model and tilted eye models)
-        size_t pyr_px = 0;
-        for (int l = 0; l < ctx->ps->plan.nlevels; l++) pyr_px += (size_t)ctx->ps->plan.lv[l].lw * ctx->ps->plan.lv[l].lh;
-        if (!ctx->need_tilt || ctx->tilt_cap < ctx->integ_cap || ctx->pyr_cap < pyr_px) {
+        // the tilted integral is allocated when the first cascade with tilted features shows up (and kept: the eye
+        // element alternates between an upright face model and tilted eye models)
+        if (!ctx->need_tilt || ctx->tilt_cap < ctx->integ_cap) {
             NV_CUDA(cudaStreamSynchronize(ctx->stream));
             ctx->need_tilt = true;
             if ((rc = ensure(&ctx->d_tilt, &ctx->tilt_cap, ctx->integ_cap)) != NV_OK) return rc;
-            if ((rc = ensure(&ctx->d_pyr, &ctx->pyr_cap, pyr_px)) != NV_OK) return rc;
             ctx->epoch++; ctx->buf_gen++;
         }
     }
