@@ -258,3 +258,40 @@ def test_view_properties_draw_into_the_frame(cdir):
         assert (g == exp).all(), i
     assert drawn > 0
     e.close()
+
+
+def test_elements_on_concurrent_host_threads(cdir):
+    """One streaming thread per element, as GStreamer runs them: four host threads, each driving its own face and
+    mouth element over its own frames at the same time (shared cascade files, separate contexts and streams), must
+    see exactly what the same elements produce one after the other."""
+    import threading
+    nthreads = 4
+    seqs = [sequence(1280, 720, 3, 2 + t, 4, smin=0.4, smax=0.6) for t in range(nthreads)]
+
+    def run(frames):
+        face = nv.Element("nubofacedetector", 0, cdir)
+        mouth = nv.Element("nubomouthdetector", 0, cdir)
+        out = []
+        for f in frames:
+            out.append((face.process(f)[0], mouth.process(f)[0]))
+        face.close(); mouth.close()
+        return out
+
+    want = [run(s_) for s_ in seqs]
+    got = [None] * nthreads
+    errs = []
+
+    def worker(t):
+        try:
+            got[t] = run(seqs[t])
+        except Exception as ex:          # noqa: BLE001
+            errs.append(ex)
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    assert got == want
+    assert sum(len(m) for w in want for (fm, mm) in w for m in (fm, mm)) > 0
