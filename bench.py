@@ -276,6 +276,37 @@ def aux_other_configs(nv, local, world):
             return r
         out["cfg4_tracker_1280x720_bgra"]["cpu_frames_per_s"] = _timeit(cpu4, 200)
         out["cpu"] = {"cores": cv2.getNumThreads(), "via": "cv2 %s, the reference's call sequences" % cv2.__version__}
+    # the same elements as concurrent streams: one host thread per stream (ctypes drops the GIL inside the library),
+    # every stream its own element, contexts and CUDA streams — what a media server with several pipelines does
+    import threading
+
+    def concurrent(factory, frames_of, nstreams, nframes, **props):
+        els = [nv.Element(factory, local, cdir) for _ in range(nstreams)]
+        for e_ in els:
+            for k, v in props.items():
+                e_.set(k, v)
+
+        def loop(i, n):
+            fr = frames_of(i)
+            for j in range(n):
+                els[i].process(fr[j % len(fr)], now_ms=33.3 * (j + 1))
+        for i in range(nstreams):
+            loop(i, 3)
+        th = [threading.Thread(target=loop, args=(i, nframes)) for i in range(nstreams)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        dt = time.perf_counter() - t0
+        for e_ in els:
+            e_.close()
+        return nstreams * nframes / dt
+
+    NS = 8
+    out["cfg2_eyes_in_faces_1280x720"]["frames_per_s_%d_streams" % NS] = concurrent("nuboeyedetector", lambda i: [f2], NS, 150)
+    out["cfg4_tracker_1280x720_bgra"]["frames_per_s_%d_streams" % NS] = concurrent("nubotracker", lambda i: seq, NS, 300)
+    out["cfg1_face_640x480_defaults"]["frames_per_s_%d_streams" % NS] = concurrent("nubofacedetector", lambda i: [f1], NS, 300)
     shutil.rmtree(cdir, ignore_errors=True)
     return out
 
