@@ -176,6 +176,10 @@ NV_API int nv_element_create(const char *factory_name, int gpu, const char *casc
 NV_API void nv_element_destroy(nv_element *e);
 NV_API int nv_element_set_property(nv_element *e, const char *name, long value);
 NV_API int nv_element_get_property(nv_element *e, const char *name, long *value);
+/* property table of the element, for a shell that installs its GObject properties from it (kmsfacedetect.cpp:1043-1102
+ * and the analogous class_init blocks): index 0 .. count-1; returns NV_ERR_ARG past the end.  *name stays valid for
+ * the element's lifetime. */
+NV_API int nv_element_property_info(nv_element *e, int index, const char **name, long *minimum, long *maximum, long *default_value);
 /* sink_event: a queued upstream "message" carrying face rectangles (kmseyedetect.cpp:192-218,680-724),
  * or the "motion" event the face element waits for in detect-event mode (kmsfacedetect.cpp:698-707) */
 NV_API int nv_element_push_faces_event(nv_element *e, const nv_rect *faces, int n);

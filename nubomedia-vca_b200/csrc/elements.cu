@@ -1055,6 +1055,17 @@ extern "C" int nv_element_get_property(nv_element *e, const char *name, long *va
     return NV_ERR_ARG;
 }
 
+extern "C" int nv_element_property_info(nv_element *e, int index, const char **name, long *minimum, long *maximum, long *default_value)
+{
+    if (!e || index < 0 || index >= (int)e->props.size()) { nv_set_error("no such property index"); return NV_ERR_ARG; }
+    const Prop &p = e->props[index];
+    if (name) *name = p.name;
+    if (minimum) *minimum = p.lo;
+    if (maximum) *maximum = p.hi;
+    if (default_value) *default_value = p.def;
+    return NV_OK;
+}
+
 extern "C" int nv_element_push_faces_event(nv_element *e, const nv_rect *faces, int n)
 {
     if (!e || (n > 0 && !faces) || n < 0) { nv_set_error("bad argument"); return NV_ERR_ARG; }

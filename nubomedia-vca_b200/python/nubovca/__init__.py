@@ -80,6 +80,7 @@ _SIGS = {
     "nv_element_destroy": (None, [_vp]),
     "nv_element_set_property": (_i, [_vp, C.c_char_p, C.c_long]),
     "nv_element_get_property": (_i, [_vp, C.c_char_p, C.POINTER(C.c_long)]),
+    "nv_element_property_info": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]),
     "nv_element_push_faces_event": (_i, [_vp, _vp, _i]),
     "nv_element_push_motion_event": (_i, [_vp]),
     "nv_element_transform_frame_ip": (_i, [_vp, _vp, _i, _i, _i, C.c_uint64, C.c_double]),
@@ -234,6 +235,18 @@ class Element:
         v = C.c_long(0)
         _check(_lib.nv_element_get_property(self.handle, name.encode(), C.byref(v)), f"get {name}")
         return v.value
+
+    def properties(self):
+        """[(name, minimum, maximum, default)] — the table a GStreamer shell installs its GObject properties from."""
+        out = []
+        i = 0
+        while True:
+            name = C.c_char_p(); lo, hi, de = C.c_long(0), C.c_long(0), C.c_long(0)
+            if _lib.nv_element_property_info(self.handle, i, C.byref(name), C.byref(lo), C.byref(hi), C.byref(de)) != 0:
+                break
+            out.append((name.value.decode(), lo.value, hi.value, de.value))
+            i += 1
+        return out
 
     def push_faces(self, rects):
         r = np.ascontiguousarray(np.asarray(rects, np.int32).reshape(-1, 4))

@@ -36,6 +36,8 @@ def test_property_surface(factory, tmp_path):
             assert e.get(name) == hi
     with pytest.raises(nv.NuboError):
         e.get("no-such-property")
+    table = {n: (lo, hi, de) for n, lo, hi, de in e.properties()}          # what a shell installs its GObject properties from
+    assert table == {n: (lo, hi, (de if de <= hi else de)) for n, (lo, hi, de) in SURFACE[factory].items()}
     if factory == "nuboeardetector":
         with pytest.raises(nv.NuboError):
             e.set("send-meta-data", 1)                 # the server-side name does not exist on the element
