@@ -272,6 +272,49 @@ def test_cfg3_full_size_1080p(ctx, face):
     assert len(ctx.levels()) == 40
 
 
+def test_full_size_properties_without_the_oracle(face):
+    """Size-independent properties at BASELINE's full sizes, where a second oracle run would only repeat
+    test_cfg3_full_size_1080p: (1) a frame padded to a wider stride gives the same rectangles; (2) the device-resident
+    input path equals the host path; (3) ten replays of the captured graph are identical; (4) raw candidates
+    (minNeighbors 0) contain every grouped rectangle's neighbourhood: each grouped rect has >= 3 raw candidates within
+    the 0.2 similarity bound; (5) 32 contexts on different frames (config 5's shape) agree with one context run alone."""
+    torch = pytest.importorskip("torch")
+    ncasc, _ = face
+    fr = synth.frame(1920, 1080, 6, 3)
+    c = nv.Context(0, 1920, 1080)
+    base = c.face_detect(ncasc, fr, 1920, 1.1, 3, (24, 24))
+    assert len(base) >= 4
+    import ctypes as C
+    pad = np.zeros((1080, 1920 * 3 + 64), np.uint8); pad[:, :5760] = fr.reshape(1080, -1)
+    n = C.c_int(0)
+    a = nv.Context._face_params(1920, 1.1, 3, (24, 24))
+    assert nv._lib.nv_face_detect(c.handle, ncasc.handle, pad.ctypes.data_as(C.c_void_p), 1920, 1080, pad.strides[0], C.byref(a),
+                                  c._out, c._cap, C.byref(n)) == 0
+    assert rects_equal(nv._rects(c._out, n.value), base)
+    d = torch.from_numpy(fr).cuda()
+    for _ in range(10):
+        c.face_submit_device(ncasc, d.data_ptr(), 1920, 1080, 5760, 1920, 1.1, 3, (24, 24))
+        assert rects_equal(c.face_collect(), base)
+    raw = c.face_detect(ncasc, fr, 1920, 1.1, 0, (24, 24)).astype(np.int64)
+    for (x, y, w, h) in base.astype(np.int64):
+        delta = 0.2 * (np.minimum(w, raw[:, 2]) + np.minimum(h, raw[:, 3])) * 0.5
+        near = (np.abs(raw[:, 0] - x) <= delta) & (np.abs(raw[:, 1] - y) <= delta) & \
+               (np.abs(raw[:, 0] + raw[:, 2] - x - w) <= delta) & (np.abs(raw[:, 1] + raw[:, 3] - y - h) <= delta)
+        assert near.sum() >= 3, (x, y, w, h)
+    c.close()
+    frames = [synth.frame(1280, 720, 3, 1000 + i) for i in range(32)]
+    ctxs = [nv.Context(0, 1280, 720) for _ in frames]
+    for rep in range(2):                                        # second round: every context replays its graph
+        for cx, f in zip(ctxs, frames):
+            cx.face_submit(ncasc, f, 640, 1.25, 3, None)
+        outs = [cx.face_collect() for cx in ctxs]
+    solo = nv.Context(0, 1280, 720)
+    for f, o in zip(frames, outs):
+        assert rects_equal(solo.face_detect(ncasc, f, 640, 1.25, 3, None), o)
+    for cx in ctxs + [solo]:
+        cx.close()
+
+
 def test_async_streams_are_independent(face):
     """cfg5 mechanics: many contexts in flight give the same per-stream results as one at a time."""
     ncasc, ocasc = face
