@@ -637,7 +637,6 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
 {
     extern __shared__ __align__(128) uint32_t tile[];           // [YS planes][rt][cp], plane stride ps
     __shared__ __align__(8) unsigned long long mbar;
-    __shared__ float s_vnf[64 * 32];                             // [member][class]
     __shared__ uint32_t s_mask[3][2][32];                        // rotating alive masks: [buffer][member / 32][class]
     __shared__ uint32_t s_words[NV_CTY][2];
     const PlanDev *__restrict__ plan = P.plan;
@@ -676,15 +675,11 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
         }
         if (part) atomicOr(&s_mask[0][warp >> 2][lane], part);
     }
-    for (int i = tid; i < NV_CTX * NV_CTY; i += 256) {
-        int ly = i >> 6, lx = i & 63;
-        if ((s_words[ly][lx >> 5] >> (lx & 31)) & 1u)
-            s_vnf[((ly * 2 + (lx >> 5)) << 5) + ((lx + K * ly) & 31)] = P.vnf[L.wofs + (iy0 + ly) * L.nx + ix0 + lx];
-    }
     __syncthreads();
     mbar_wait(bar, 0);                                           // also before an early exit: the copy targets this CTA's smem
 
     const uint32_t tile_sa = smem_u32(tile);
+    const float *__restrict__ vnf_tile = P.vnf + L.wofs + (size_t)iy0 * L.nx + ix0;
     const int rowb = YS * CP * 4;                                // bytes from one window row to the next
     int cur = 0;
     for (int st = P.stage_begin; st < P.stage_end; st++) {
@@ -705,7 +700,7 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
                 bit[i] = active[i] ? __ffsll((long long)rem) - 1 : 0;
                 ly[i] = bit[i] >> 1; lx[i] = ((lane - K * ly[i]) & 31) + ((bit[i] & 1) << 5);
                 wa[i] = tile_sa + (uint32_t)(ly[i] * rowb + lx[i] * 4);
-                vnf[i] = s_vnf[(bit[i] << 5) + lane];
+                vnf[i] = active[i] ? __ldg(vnf_tile + ly[i] * L.nx + lx[i]) : 0.f;     // per-window factor, L2-resident
 #pragma unroll
                 for (int q = 0; q < 8; q++) rem &= rem - 1ull;
             }
@@ -721,7 +716,7 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
             int bit = active ? __ffsll((long long)rem) - 1 : 0;
             int ly = bit >> 1, lx = ((lane - K * ly) & 31) + ((bit & 1) << 5);
             uint32_t wa[1] = {tile_sa + (uint32_t)(ly * rowb + lx * 4)};
-            float vnf[1] = {s_vnf[(bit << 5) + lane]};
+            float vnf[1] = {active ? __ldg(vnf_tile + ly * L.nx + lx) : 0.f};
             bool pass[1];
             class_stage<FAST, 1>(P, si, wa, vnf, pass);
             if (active && pass[0]) pass_bits |= 1ull << bit;
@@ -760,7 +755,7 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
             P.cand[base] = key;
             if (P.depth) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = NV_DEPTH_PASS;
         } else
-            P.tail[base] = make_uint2(key, __float_as_uint(s_vnf[(bit << 5) + lane]));
+            P.tail[base] = make_uint2(key, __float_as_uint(__ldg(vnf_tile + ly * L.nx + lx)));
     }
 }
 
