@@ -14,7 +14,7 @@
 
 #define NV_VERSION_STR "nubovca-b200 0.1 (sm_100a)"
 #define CAND_CAP 8192              // initial raw-candidate capacity; grows on demand (collect() re-runs the call)
-#define CAND_CAP_GROUPED 32768     // hard limits: the similarity bit-matrix is cap^2/8 bytes
+#define CAND_CAP_GROUPED 65536     // hard limits: the similarity bit-matrix is cap^2/8 bytes (512 MB at the limit, allocated on demand only)
 #define CAND_CAP_RAW 131072
 
 extern "C" const char *nv_version(void) { return NV_VERSION_STR; }

@@ -98,3 +98,105 @@ def write_old_format(path, d, name="haarcascade_converted"):
     s.append('</opencv_storage>')
     with open(path, 'w') as f:
         f.write('\n'.join(s))
+
+
+def random_int_cascade(path, rng, w=20, h=20, nstages=12, max_trees=40, nfeat=200):
+    """A random stump cascade of the kind OpenCV's trainer produces (first rect weight -1, the others small integers,
+    half-rect / third-rect / checkerboard geometries): the shape the exact-integer fast kernels certify."""
+    import numpy as np
+    feats = []
+    for _ in range(nfeat):
+        kind = int(rng.integers(0, 6))
+        ww = int(rng.integers(2, w + 1)); hh = int(rng.integers(2, h + 1))
+        x = int(rng.integers(0, w - ww + 1)); y = int(rng.integers(0, h - hh + 1))
+        if kind == 0 and ww >= 2:      # left / right half
+            half = ww // 2; ww = 2 * half; side = int(rng.integers(0, 2))
+            rects = [(x, y, ww, hh, -1.0), (x + side * half, y, half, hh, 2.0)]
+        elif kind == 1 and hh >= 2:    # top / bottom half
+            half = hh // 2; hh = 2 * half; side = int(rng.integers(0, 2))
+            rects = [(x, y, ww, hh, -1.0), (x, y + side * half, ww, half, 2.0)]
+        elif kind == 2 and ww >= 3:    # middle third, horizontal
+            t = ww // 3; ww = 3 * t
+            rects = [(x, y, ww, hh, -1.0), (x + t, y, t, hh, 3.0)]
+        elif kind == 3 and hh >= 3:    # middle third, vertical
+            t = hh // 3; hh = 3 * t
+            rects = [(x, y, ww, hh, -1.0), (x, y + t, ww, t, 3.0)]
+        elif kind == 4 and ww >= 2 and hh >= 2:   # checkerboard: three rects
+            a = ww // 2; b = hh // 2; ww = 2 * a; hh = 2 * b
+            rects = [(x, y, ww, hh, -1.0), (x, y, a, b, 2.0), (x + a, y + b, a, b, 2.0)]
+        else:                          # an arbitrary second rect inside the first
+            w2 = int(rng.integers(1, ww + 1)); h2 = int(rng.integers(1, hh + 1))
+            rects = [(x, y, ww, hh, -1.0), (x + int(rng.integers(0, ww - w2 + 1)), y + int(rng.integers(0, hh - h2 + 1)), w2, h2, 2.0)]
+        feats.append(rects)
+    stages = []
+    for s in range(nstages):
+        nt = int(rng.integers(2, max_trees + 1))
+        trees = [(int(rng.integers(0, nfeat)), float(np.float32(rng.normal(0, 0.02))),
+                  float(np.float32(rng.uniform(-1, 1))), float(np.float32(rng.uniform(-1, 1)))) for _ in range(nt)]
+        stages.append((float(np.float32(rng.uniform(-0.25, -0.05) * nt)), trees))
+    write_cascade(path, w, h, stages, feats)
+
+
+def random_general_model(rng, w=20, h=20, nstages=5, max_trees=8, max_nodes=3):
+    """A random cascade with tree weak classifiers and (half of them) tilted features, as an oracle.parse_cascade_xml dict
+    (write it with write_old_format)."""
+    import numpy as np
+    rects, weights, tilted, trees, stage_ntrees, stage_thr = [], [], [], [], [], []
+
+    def feature():
+        t = int(rng.integers(0, 2))
+        r = np.zeros((3, 4), np.int32); wt = np.zeros(3, np.float32)
+        nr = int(rng.integers(2, 4))
+        for k in range(nr):
+            while True:
+                if t:   # tilted (x, y, w, h): x - h >= 0, x + w <= W, y + w + h <= H
+                    ww = int(rng.integers(1, 8)); hh = int(rng.integers(1, 8))
+                    if hh + ww > min(w, h):
+                        continue
+                    x = int(rng.integers(hh, w - ww + 1)); y = int(rng.integers(0, h - ww - hh + 1))
+                else:
+                    ww = int(rng.integers(1, w + 1)); hh = int(rng.integers(1, h + 1))
+                    x = int(rng.integers(0, w - ww + 1)); y = int(rng.integers(0, h - hh + 1))
+                break
+            r[k] = [x, y, ww, hh]; wt[k] = np.float32([-1, 2, 3][k] if rng.integers(0, 2) else rng.uniform(-2, 2))
+        rects.append(r); weights.append(wt); tilted.append(t)
+        return len(rects) - 1
+
+    for _ in range(nstages):
+        nt = int(rng.integers(1, max_trees + 1))
+        for _t in range(nt):
+            nn = int(rng.integers(1, max_nodes + 1))
+            nodes, leaves = [], []
+            for i in range(nn):
+                child = []
+                for _side in range(2):
+                    if i + 1 < nn and not any(c == i + 1 for (_, _, a, b) in nodes for c in (a, b)) and len(child) == 0 and rng.integers(0, 2):
+                        child.append(i + 1)
+                    else:
+                        child.append(-len(leaves)); leaves.append(float(np.float32(rng.uniform(-1, 1))))
+                nodes.append((feature(), float(np.float32(rng.normal(0, 0.03))), child[0], child[1]))
+            # unreachable nodes are legal in the file format but make leaf counts ambiguous: keep every node reachable
+            reach = {0}
+            for i, (_, _, a, b) in enumerate(nodes):
+                if i in reach:
+                    reach.update(c for c in (a, b) if c > 0)
+            if len(reach) != nn:
+                nodes = nodes[:1]; leaves = [float(np.float32(rng.uniform(-1, 1))) for _ in range(2)]
+                nodes[0] = (nodes[0][0], nodes[0][1], 0, -1)
+            else:
+                # renumber leaves in node order so that the count is nodes + 1
+                k = 0; new_leaves = []; new_nodes = []
+                for (f, t, a, b) in nodes:
+                    ch = []
+                    for c in (a, b):
+                        if c > 0:
+                            ch.append(c)
+                        else:
+                            ch.append(-k); new_leaves.append(leaves[-c]); k += 1
+                    new_nodes.append((f, t, ch[0], ch[1]))
+                nodes, leaves = new_nodes, new_leaves
+            trees.append((nodes, leaves))
+        stage_ntrees.append(nt)
+        stage_thr.append(float(np.float32(rng.uniform(-0.9, -0.35) * nt)))
+    import oracle as O
+    return O._model(w, h, stage_ntrees, stage_thr, trees, rects, weights, tilted)

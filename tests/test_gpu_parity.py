@@ -11,7 +11,7 @@ import pytest
 
 import nubovca as nv
 import oracle as O
-from cascade_xml_util import random_cascade
+from cascade_xml_util import random_cascade, random_general_model, random_int_cascade, write_old_format
 from nubovca import synth
 
 pytestmark = pytest.mark.gpu
@@ -162,6 +162,34 @@ def test_random_cascades_and_ragged_sizes(ctx, tmp_path, seed):
     for mn in (0, 2):
         assert rects_equal(ctx.detect_multiscale(ncasc, g, sf, mn), O.detect_multiscale(g, ocasc, sf, mn)), (seed, mn)
     check_levels(ctx, g, ocasc, sf, (0, 0))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_trainer_shaped_and_general_cascades(ctx, tmp_path, seed):
+    """The exact-integer fast kernels (bulk bank-class kernel, six-load features, fast tail) on random cascades shaped
+    like the trainer's output — 12 stages of up to 40 classifiers, so the bulk stages AND the tail run — and the
+    predictOrdered kernels on random tree / tilted cascades: integrals, tilted integrals, every depth map, candidates
+    and grouped rectangles against the oracle, on odd image and window sizes."""
+    rng = np.random.default_rng(500 + seed)
+    p = str(tmp_path / "int.xml")
+    random_int_cascade(p, rng, w=[20, 24, 18, 32, 20, 25][seed], h=[20, 24, 15, 20, 30, 15][seed])
+    ncasc, ocasc = nv.Cascade(p), O.Cascade(p)
+    assert ncasc.info.order_free_sums == 1 and ncasc.info.general == 0
+    W, H = int(rng.integers(150, 700)), int(rng.integers(120, 500))
+    g = synth.frame(W, H, 3, seed)[..., 1]
+    sf = float(rng.choice([1.1, 1.2, 1.3]))
+    for mn in (0, 2):
+        assert rects_equal(ctx.detect_multiscale(ncasc, g, sf, mn), O.detect_multiscale(g, ocasc, sf, mn)), (seed, mn)
+    nwin, levels = check_levels(ctx, g, ocasc, sf, (0, 0))
+    codes = np.concatenate([l["depth"].ravel() for l in levels])
+    assert (codes <= -10).any() or (codes == 1).any(), "no window reached the tail stages"
+    q = str(tmp_path / "gen.xml")
+    write_old_format(q, random_general_model(rng))
+    ngen, ogen = nv.Cascade(q), O.Cascade(q)
+    assert ngen.info.general == 1
+    for mn in (0, 2):
+        assert rects_equal(ctx.detect_multiscale(ngen, g, sf, mn), O.detect_multiscale(g, ogen, sf, mn)), (seed, mn)
+    check_levels(ctx, g, ogen, sf, (0, 0))
 
 
 def test_old_format_and_wide_window_cascade(ctx, tmp_path, cascade_dir):

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import oracle as O
-from cascade_xml_util import random_cascade, write_cascade, write_old_format
+from cascade_xml_util import random_cascade, random_general_model, random_int_cascade, write_cascade, write_old_format
 from nubovca import synth
 
 try:
@@ -292,6 +292,27 @@ def test_general_cascades_live(name, cascade_dir, tmp_path):
             assert rects_equal(a, O.detect_multiscale(g, oco, sf, mn, ms))
             n += len(a)
     assert n > 0, "the test images never fire this cascade"
+
+
+@needs_cv2
+@pytest.mark.parametrize("seed", range(6))
+def test_random_trainer_shaped_and_general_cascades_live(tmp_path, seed):
+    """(1) random stump cascades shaped like the trainer's output (-1 / 2 / 3 weights, half, third and checkerboard
+    rects, up to 40 classifiers per stage) — what the exact-integer GPU kernels certify; (2) random cascades with tree
+    weak classifiers and tilted features.  Both against cv2."""
+    rng = np.random.default_rng(500 + seed)
+    p = str(tmp_path / "int.xml")
+    random_int_cascade(p, rng, w=[20, 24, 18, 32, 20, 25][seed], h=[20, 24, 15, 20, 30, 15][seed])
+    g = synth.frame(300, 220, 3, seed)[..., 1]
+    for mn in (0, 2):
+        assert rects_equal(cv2.CascadeClassifier(p).detectMultiScale(g, scaleFactor=1.2, minNeighbors=mn),
+                           O.detect_multiscale(g, O.Cascade(p), 1.2, mn)), (seed, mn)
+    q = str(tmp_path / "gen.xml")
+    write_old_format(q, random_general_model(rng))
+    cc = cv2.CascadeClassifier(q)
+    assert not cc.empty() and O.Cascade(q).general
+    for mn in (0, 2):
+        assert rects_equal(cc.detectMultiScale(g, scaleFactor=1.2, minNeighbors=mn), O.detect_multiscale(g, O.Cascade(q), 1.2, mn)), (seed, mn)
 
 
 @needs_cv2
