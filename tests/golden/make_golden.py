@@ -68,8 +68,27 @@ def tracker_case(W, H, nframes, seed, thr, noise):
     return dict(W=W, H=H, nframes=nframes, seed=seed, threshold=thr, noise=noise, frames=out)
 
 
+def general_case(cascade, W, H, k, seed, smin, smax, sf, mn, min_size):
+    """cv::CascadeClassifier::detectMultiScale with a tree / tilted model (predictOrdered) on an equalised gray frame,
+    plus the sha256 of cv2.integral3's tilted sums of that frame."""
+    eq = cv2.equalizeHist(cv2.cvtColor(synth.frame(W, H, k, seed, smin=smin, smax=smax), cv2.COLOR_BGR2GRAY))
+    cc = cv2.CascadeClassifier(os.path.join(CASC, cascade))
+    raw = np.asarray(cc.detectMultiScale(eq, scaleFactor=sf, minNeighbors=0, minSize=tuple(min_size))).reshape(-1, 4)
+    grp = np.asarray(cc.detectMultiScale(eq, scaleFactor=sf, minNeighbors=mn, minSize=tuple(min_size))).reshape(-1, 4)
+    return dict(cascade=cascade, W=W, H=H, k=k, seed=seed, smin=smin, smax=smax, scale_factor=sf, min_neighbors=mn,
+                min_size=list(min_size), eq_sha=sha(eq), tilted_sha=sha(cv2.integral3(eq)[2].astype(np.int32)),
+                raw=raw.tolist(), grouped=grp.tolist())
+
+
 def main():
     cv2.setNumThreads(1)
+    gen = [general_case(c, 400, 300, 2, 3, 0.5, 0.9, sf, 2, ms) for c, sf, ms in [
+        ("haarcascade_lefteye_2splits.xml", 1.1, (20, 20)), ("haarcascade_righteye_2splits.xml", 1.1, (0, 0)),
+        ("haarcascade_smile.xml", 1.1, (1, 1)), ("haarcascade_eye_tree_eyeglasses.xml", 1.25, (0, 0)),
+        ("haarcascade_frontalface_alt2.xml", 1.2, (0, 0))]]
+    with open(os.path.join(HERE, "general_golden.json"), "w") as f:
+        json.dump(dict(cv2=cv2.__version__, cases=gen), f)
+    print("wrote", len(gen), "tree / tilted cascade cases")
     faces = [
         face_case(640, 480, 4, 1, 160, 1.25, 3, None),                       # cfg1: element defaults
         face_case(640, 480, 4, 1, 640, 1.25, 3, None),

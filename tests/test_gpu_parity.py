@@ -164,6 +164,22 @@ def test_random_cascades_and_ragged_sizes(ctx, tmp_path, seed):
     check_levels(ctx, g, ocasc, sf, (0, 0))
 
 
+@pytest.mark.parametrize("idx", range(5))
+def test_general_golden_cases(ctx, cascade_dir, idx):
+    """Tree / tilted models against the committed cv2 outputs (tests/golden/general_golden.json)."""
+    import hashlib
+    c = json.load(open(os.path.join(HERE, "golden", "general_golden.json")))["cases"][idx]
+    eq = O.equalize_hist(O.bgr2gray(synth.frame(c["W"], c["H"], c["k"], c["seed"], smin=c["smin"], smax=c["smax"])))
+    ncasc = nv.Cascade(os.path.join(cascade_dir, c["cascade"]))
+    ms = tuple(c["min_size"])
+    assert rects_equal(ctx.detect_multiscale(ncasc, eq, c["scale_factor"], c["min_neighbors"], ms), c["grouped"])
+    assert rects_equal(ctx.detect_multiscale(ncasc, eq, c["scale_factor"], 0, ms), c["raw"])
+    if ncasc.info.has_tilted:
+        lv0 = ctx.levels()[0]
+        if (lv0["lw"], lv0["lh"]) == (c["W"], c["H"]):          # the first level is the frame itself when min_size allows scale 1
+            assert hashlib.sha256(ctx.tilted(0).tobytes()).hexdigest() == c["tilted_sha"]
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_random_trainer_shaped_and_general_cascades(ctx, tmp_path, seed):
     """The exact-integer fast kernels (bulk bank-class kernel, six-load features, fast tail) on random cascades shaped

@@ -256,6 +256,20 @@ def test_real_cascades_live(name, cascade_dir):
             assert rects_equal(a, O.detect_multiscale(g, oc, sf, mn, ms)), (name, W, H, mn)
 
 
+@pytest.mark.parametrize("idx", range(5))
+def test_general_golden(idx, cascade_dir):
+    """Tree / tilted models against the committed cv2 outputs (tests/golden/general_golden.json): no cv2 needed."""
+    c = json.load(open(os.path.join(HERE, "golden", "general_golden.json")))["cases"][idx]
+    eq = O.equalize_hist(O.bgr2gray(synth.frame(c["W"], c["H"], c["k"], c["seed"], smin=c["smin"], smax=c["smax"])))
+    assert hashlib.sha256(eq.tobytes()).hexdigest() == c["eq_sha"]
+    assert hashlib.sha256(O.integral_tilted(eq).tobytes()).hexdigest() == c["tilted_sha"]
+    oc = O.Cascade(os.path.join(cascade_dir, c["cascade"]))
+    ms = tuple(c["min_size"])
+    assert rects_equal(O.detect_multiscale(eq, oc, c["scale_factor"], 0, ms), c["raw"])
+    assert rects_equal(O.detect_multiscale(eq, oc, c["scale_factor"], c["min_neighbors"], ms), c["grouped"])
+    assert len(c["raw"]) > 0
+
+
 GENERAL = ["haarcascade_lefteye_2splits.xml", "haarcascade_righteye_2splits.xml", "haarcascade_smile.xml",
            "haarcascade_eye_tree_eyeglasses.xml", "haarcascade_frontalface_alt2.xml"]
 
