@@ -74,7 +74,15 @@ def cpu_baseline(frames, budget_s=20.0, max_frames=40, warm=1):
         while n < max_frames and (time.perf_counter() - t0 < budget_s or n < 2):
             cpu_face_step(cv2, cc, frames[n % len(frames)]); n += 1
         dt = time.perf_counter() - t0
-        return dict(value=n / dt, unit="frames/s", cores=cv2.getNumThreads(), kind="reference",
+        nthr = cv2.getNumThreads()
+        cv2.setNumThreads(1)                              # also the single-thread figure
+        t1 = time.perf_counter(); n1 = 0
+        while n1 < 3 and (time.perf_counter() - t1 < 6.0 or n1 < 1):
+            cpu_face_step(cv2, cc, frames[n1 % len(frames)]); n1 += 1
+        dt1 = time.perf_counter() - t1
+        cv2.setNumThreads(cores)
+        return dict(value=n / dt, unit="frames/s", cores=nthr, kind="reference",
+                    one_thread={"value": n1 / dt1, "unit": "frames/s", "sample": f"{n1} full cfg3 frames, {dt1:.1f} s"},
                     sample=f"{n} full cfg3 frames after {warm} warm-up, wall clock {dt:.1f} s",
                     via="cv2 %s call sequence of kmsfacedetect.cpp:805-811 (the reference C++ needs GStreamer/Kurento and "
                         "cannot be built here; its arithmetic is exactly these OpenCV calls)" % cv2.__version__,
@@ -88,6 +96,43 @@ def cpu_baseline(frames, budget_s=20.0, max_frames=40, warm=1):
     dt = time.perf_counter() - t0
     return dict(value=n / dt, unit="frames/s", cores=1, kind="port",
                 sample=f"{n} full cfg3 frames through oracle/nubo_oracle.c, wall clock {dt:.1f} s")
+
+
+_CFG5_WORKER = r"""
+import sys, time
+sys.path.insert(0, sys.argv[1])
+import cv2, numpy as np
+from nubovca import synth
+cv2.setNumThreads(1)
+cc = cv2.CascadeClassifier(sys.argv[2])
+frames = [synth.frame(1280, 720, 3, 1000 + int(sys.argv[3]) * 4 + i) for i in range(2)]
+def step(f):                                         # kmsfacedetect.cpp:805-811 at width-to-process 640
+    g = cv2.equalizeHist(cv2.cvtColor(cv2.resize(f, (640, 360), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY))
+    return cc.detectMultiScale(g, scaleFactor=1.25, minNeighbors=3, flags=0, minSize=(32, 18))
+step(frames[0])
+t0 = time.perf_counter(); n = 0
+while time.perf_counter() - t0 < float(sys.argv[4]):
+    step(frames[n % 2]); n += 1
+print(n / (time.perf_counter() - t0))
+"""
+
+
+def cpu_cfg5(seconds=6.0):
+    """the cfg5 CPU side = min(cores, streams) single-threaded worker processes, each looping its
+    streams' frames through the reference's call sequence; aggregate frames/s over the workers / 30."""
+    try:
+        import cv2  # noqa: F401
+    except Exception:
+        return None
+    nw = min(os.cpu_count() or 1, 256)
+    procs = [subprocess.Popen([sys.executable, "-c", _CFG5_WORKER, os.path.join(ROOT, "nubomedia-vca_b200", "python"),
+                               FACE_XML, str(i), str(seconds)], stdout=subprocess.PIPE, text=True) for i in range(nw)]
+    fps = 0.0
+    for p_ in procs:
+        out, _ = p_.communicate(timeout=120)
+        fps += float(out.strip().splitlines()[-1])
+    return {"frames_per_s": fps, "streams_at_30fps": fps / 30.0, "workers": nw, "threads_per_worker": 1,
+            "sample": "%d worker processes x %.0f s of 1280x720 -> 640x360 frames" % (nw, seconds), "via": "cv2"}
 
 
 def run_reference(args, rank, world):
@@ -445,28 +490,38 @@ def main():
         c5 = [nv.Context(local, 1280, 720) for _ in mine]
         p5 = dict(width_to_process=640, scale_factor=1.25, min_neighbors=3, min_size=None)
 
-        def step5():
-            for i, c in enumerate(c5):
-                c.face_submit(casc, h5[i % len(h5)], **p5)
-            return [c.face_collect() for c in c5]
-        for _ in range(3):
-            step5()
-        barrier()
-        t5 = time.perf_counter()
-        n5 = 10
-        for _ in range(n5):
-            step5()
-        torch.cuda.synchronize()
-        ms5 = 1e3 * (time.perf_counter() - t5)
-        barrier()
-        fps5, _ = shard.aggregate_throughput(len(c5) * n5, ms5, dist, "cuda")
+        def run5(submit):
+            def step5():
+                for i, c in enumerate(c5):
+                    submit(c, i % len(h5))
+                return [c.face_collect() for c in c5]
+            for _ in range(3):
+                step5()
+            barrier()
+            t5 = time.perf_counter()
+            n5 = 10
+            for _ in range(n5):
+                step5()
+            torch.cuda.synchronize()
+            ms5 = 1e3 * (time.perf_counter() - t5)
+            barrier()
+            return shard.aggregate_throughput(len(c5) * n5, ms5, dist, "cuda")[0]
+        fps5 = run5(lambda c, i: c.face_submit(casc, h5[i], **p5))
         aux = {"metric": "720p streams@30fps (cfg5: 1280x720 -> 640x360, sf 1.25, element defaults otherwise)",
                "streams_per_gpu_in_flight": S5, "frames_per_s": fps5, "streams_at_30fps": fps5 / 30.0,
                "timing": "host wall clock, H2D + D2H included"}
+        # the same streams handed over as the decoder's NV12 planes (nv_face_submit_yuv: 1.5 instead of 3 bytes per
+        # pixel across PCIe; result = the reference block on cvtColor(COLOR_YUV2BGR_NV12), tests/test_yuv_ingest.py)
+        y5 = [_pin(synth.to_yuv420(f, "NV12")) for f in f5]
+        pl5 = [synth.yuv420_planes(b, 1280, 720, "NV12") for b in y5]
+        fps5y = run5(lambda c, i: c.face_submit_yuv(casc, pl5[i], "NV12", **p5))
+        aux["nv12_ingest"] = {"frames_per_s": fps5y, "streams_at_30fps": fps5y / 30.0, "h2d_bytes_per_frame": 1280 * 720 * 3 // 2}
         for c in c5:
             c.close()
         if rank == 0 and world == 1:
             aux["other_configs_one_stream"] = aux_other_configs(nv, local, world)
+            if not args.no_cpu_baseline:
+                aux["cpu_cfg5"] = cpu_cfg5()
 
     total_frames = B * args.steps
     value, ms_dev = shard.aggregate_throughput(total_frames, ms_dev, dist, "cuda")

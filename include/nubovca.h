@@ -34,7 +34,7 @@ typedef enum {
     NV_ERR_CUDA = -2,         /* a CUDA runtime call failed (message in nv_last_error)        */
     NV_ERR_IO = -3,           /* cascade file unreadable                                      */
     NV_ERR_FORMAT = -4,       /* cascade XML malformed                                        */
-    NV_ERR_UNSUPPORTED = -5,  /* cascade uses tilted features / trees / LBP     */
+    NV_ERR_UNSUPPORTED = -5,  /* cascade is not a BOOST/HAAR model (LBP, HOG: SURVEY §8f-3)     */
     NV_ERR_CAPACITY = -6,     /* frame larger than the ctx was created for, or too many levels */
     NV_ERR_NO_DEVICE = -7,    /* no CUDA device: the library never computes on the CPU        */
     NV_ERR_STATE = -8         /* call order violated (collect without submit, ...)            */
@@ -123,6 +123,28 @@ NV_API int nv_face_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n);
 NV_API int nv_face_submit_device(nv_ctx *ctx, const nv_cascade *c, const uint8_t *d_bgr, int width, int height,
                                  int stride_bytes, const nv_face_params *p);
 
+/* ---- 4:2:0 ingest (extension).  The reference elements negotiate BGR only
+ *      (kmsfacedetect.cpp:129-133,1025-1031), so a decoder's I420 / NV12 output passes through a CPU videoconvert
+ *      and twice the bytes cross PCIe.  These entry points take the decoder's planes as they are: the result is
+ *      what nv_face_detect gives on cv::cvtColor(frame, COLOR_YUV2BGR_I420 / _NV12 / _NV21) — the conversion is
+ *      applied per source pixel inside the resize + gray kernel (BT.601, OpenCV's 20-bit fixed point), the BGR
+ *      frame never exists.  YV12 is I420 with plane[1] and plane[2] swapped by the caller.  width and height even.
+ *      plane[2] / stride[2] are ignored for NV12 / NV21.  on_device != 0: the planes are device pointers. --------- */
+typedef enum { NV_FMT_BGR = 0, NV_FMT_I420 = 1, NV_FMT_NV12 = 2, NV_FMT_NV21 = 3 } nv_pixel_format;
+typedef struct {
+    int format;               /* nv_pixel_format, one of the 4:2:0 values */
+    int width, height;
+    const uint8_t *plane[3];
+    int stride[3];
+    int on_device;
+} nv_yuv_frame;
+
+NV_API int nv_face_detect_yuv(nv_ctx *ctx, const nv_cascade *c, const nv_yuv_frame *f, const nv_face_params *p,
+                              nv_rect *out, int cap, int *n);
+NV_API int nv_face_submit_yuv(nv_ctx *ctx, const nv_cascade *c, const nv_yuv_frame *f, const nv_face_params *p);   /* + nv_face_collect */
+/* cvtColor(COLOR_YUV2BGR_*) alone, host in / host out (parity tap of the ingest arithmetic) */
+NV_API int nv_yuv2bgr(nv_ctx *ctx, const nv_yuv_frame *f, uint8_t *dst_bgr, int dst_stride);
+
 /* ---- the nubotracker per-frame block, gstnubotracker.cpp:356-380: BGRA->gray, absdiff with the
  *      previous frame, threshold, updateMotionHistory(ts, 0.2), segmentMotion(ts, 32),
  *      __join_objects.  The reference's timestamp is clock() in ms (:349); it is injected here.
@@ -185,7 +207,7 @@ NV_API int nv_element_property_info(nv_element *e, int index, const char **name,
 NV_API int nv_element_push_faces_event(nv_element *e, const nv_rect *faces, int n);
 NV_API int nv_element_push_motion_event(nv_element *e);
 /* one video buffer.  frame: BGR (detectors) or BGRA (tracker), modified in place only when a view-*
- * property asks for it (drawing is not implemented yet: SURVEY K13).  now_ms < 0 uses gettimeofday for
+ * property asks for it (cvRectangle / cv::circle restated pixel-exactly, see nv_debug_draw_*).  now_ms < 0 uses gettimeofday for
  * the events-ms rate limit; the tracker's MHI timestamp is pts_ns / 1e6 unless now_ms >= 0. */
 NV_API int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int width, int height, int stride_bytes,
                                          uint64_t pts_ns, double now_ms);

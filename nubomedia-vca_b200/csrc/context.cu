@@ -867,13 +867,77 @@ int nv_get_rtab(nv_ctx *ctx, int sw, int sh, int dw, int dh, const int **d_tab)
     return NV_OK;
 }
 
-static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, bool on_device, int width, int height,
-                            int stride, const nv_face_params *p)
+// Source frame of the face block: interleaved BGR (p[0], s[0]) or the planes of a 4:2:0 frame.
+struct FaceSrc { int fmt; const uint8_t *p[3]; int s[3]; bool on_device; };
+
+// Host planes of a 4:2:0 frame -> ctx->d_frame.  Planes that lie in one ascending block of host memory (a GstVideoFrame
+// mapped from a single GstMemory, a cv::Mat of h*3/2 rows) travel as ONE copy and keep their relative offsets; scattered
+// planes are copied one by one to 256-byte aligned offsets.  Fills the device plane pointers.
+static int yuv_h2d(nv_ctx *ctx, const FaceSrc &f, int height, SrcPlanes *d)
 {
+    int np = f.fmt == NV_FMT_I420 ? 3 : 2;
+    size_t bytes[3] = {(size_t)f.s[0] * height, (size_t)f.s[1] * (height / 2), np == 3 ? (size_t)f.s[2] * (height / 2) : 0};
+    // tight end of the last row of a plane does not matter: strides are honoured, the tail padding is copied along
+    const uint8_t *lo = f.p[0], *hi = f.p[0] + bytes[0];
+    bool block = true;
+    for (int i = 1; i < np; i++) {
+        if (f.p[i] < hi || (size_t)(f.p[i] - lo) + bytes[i] > ctx->frame_cap) { block = false; break; }
+        hi = f.p[i] + bytes[i];
+    }
+    size_t off[3] = {0, 0, 0};
+    if (block) {
+        for (int i = 1; i < np; i++) off[i] = (size_t)(f.p[i] - lo);
+        int rc = nv_h2d(ctx, lo, (size_t)(hi - lo));
+        if (rc != NV_OK) return rc;
+    } else {
+        size_t o = 0;
+        for (int i = 0; i < np; i++) { off[i] = o; o += (bytes[i] + 255) & ~(size_t)255; }
+        if (o > ctx->frame_cap) { nv_set_error("4:2:0 frame larger than the context"); return NV_ERR_CAPACITY; }
+        for (int i = 0; i < np; i++) {
+            cudaPointerAttributes at;
+            bool pinned = cudaPointerGetAttributes(&at, f.p[i]) == cudaSuccess && at.type == cudaMemoryTypeHost;
+            if (!pinned) { cudaGetLastError(); memcpy(ctx->h_frame + off[i], f.p[i], bytes[i]); }
+            NV_CUDA(cudaMemcpyAsync(ctx->d_frame + off[i], pinned ? f.p[i] : ctx->h_frame + off[i], bytes[i],
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    d->p0 = ctx->d_frame; d->p1 = ctx->d_frame + off[1]; d->p2 = np == 3 ? ctx->d_frame + off[2] : nullptr;
+    d->s0 = f.s[0]; d->s1 = f.s[1]; d->s2 = f.s[2];
+    return NV_OK;
+}
+
+static int check_yuv(nv_ctx *ctx, const nv_yuv_frame *f, FaceSrc *src)
+{
+    if (!ctx || !f || !f->plane[0] || !f->plane[1]) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    if (f->format != NV_FMT_I420 && f->format != NV_FMT_NV12 && f->format != NV_FMT_NV21) {
+        nv_set_error("format %d is not a 4:2:0 nv_pixel_format", f->format); return NV_ERR_ARG;
+    }
+    bool planar = f->format == NV_FMT_I420;
+    int w = f->width, h = f->height;
+    if (w <= 0 || h <= 0 || (w & 1) || (h & 1)) { nv_set_error("4:2:0 frame needs even, positive width and height (%dx%d)", w, h); return NV_ERR_ARG; }
+    if (f->stride[0] < w || f->stride[1] < (planar ? w / 2 : w) || (planar && (!f->plane[2] || f->stride[2] < w / 2))) {
+        nv_set_error("bad 4:2:0 plane geometry"); return NV_ERR_ARG;
+    }
+    size_t total = (size_t)f->stride[0] * h + (size_t)f->stride[1] * (h / 2) + (planar ? (size_t)f->stride[2] * (h / 2) : 0);
+    if (w > ctx->max_w || h > ctx->max_h || total + 768 > ctx->frame_cap) {
+        nv_set_error("frame %dx%d exceeds the context's %dx%d", w, h, ctx->max_w, ctx->max_h); return NV_ERR_CAPACITY;
+    }
+    src->fmt = f->format; src->on_device = f->on_device != 0;
+    for (int i = 0; i < 3; i++) { src->p[i] = f->plane[i]; src->s[i] = f->stride[i]; }
+    if (!planar) { src->p[2] = nullptr; src->s[2] = 0; }
+    return NV_OK;
+}
+
+static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const FaceSrc &src, int width, int height, const nv_face_params *p)
+{
+    const uint8_t *bgr = src.p[0];
+    const bool on_device = src.on_device, yuv = src.fmt != NV_FMT_BGR;
+    const int stride = src.s[0];
     if (!ctx || !c || !bgr || !p) { nv_set_error("null argument"); return NV_ERR_ARG; }
     if (p->width_to_process <= 0) { nv_set_error("width_to_process must be > 0 (kmsfacedetect.cpp:304 divides by it)"); return NV_ERR_ARG; }
     int rc;
-    if (!on_device) { if ((rc = check_frame(ctx, bgr, width, height, stride, 3)) != NV_OK) return rc; }
+    if (yuv) { /* geometry checked by check_yuv */ }
+    else if (!on_device) { if ((rc = check_frame(ctx, bgr, width, height, stride, 3)) != NV_OK) return rc; }
     else if (width <= 0 || height <= 0 || width > ctx->max_w || height > ctx->max_h || stride < 3 * width) {
         nv_set_error("bad device frame geometry"); return NV_ERR_ARG;
     }
@@ -896,15 +960,18 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
     if ((rc = detect_prepare(ctx, casc, cols, rows, &dp)) != NV_OK) return rc;
 
     const uint8_t *d_src = bgr;
+    SrcPlanes planes = {src.p[0], src.p[1], src.p[2], src.s[0], src.s[1], src.s[2]};
     if (!on_device) {
         // page-locked caller memory is copied straight from the caller; anything else goes through the pinned staging buffer
-        if ((rc = nv_h2d(ctx, bgr, (size_t)stride * height)) != NV_OK) return rc;
+        if (yuv) { if ((rc = yuv_h2d(ctx, src, height, &planes)) != NV_OK) return rc; }
+        else if ((rc = nv_h2d(ctx, bgr, (size_t)stride * height)) != NV_OK) return rc;
         d_src = ctx->d_frame;
     }
     auto enqueue = [&](int *nl) -> int {
         ctx->prof_set[0] = ctx->prof_set[1] = false;
         prof_mark(ctx, 0);
-        NV_CUDA(launch_face_prep(d_src, width, height, stride, 3, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream));
+        if (yuv) NV_CUDA(launch_face_prep_yuv(src.fmt, planes, width, height, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream));
+        else NV_CUDA(launch_face_prep(d_src, width, height, stride, 3, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream));
         prof_mark(ctx, 1);
         NV_CUDA(launch_lut(ctx->d_hist, cols * rows, ctx->d_lut, ctx->stream));
         *nl += 2;
@@ -913,7 +980,8 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
     // A context that sees the same call shape again replays it as ONE CUDA graph launch (the per-stream steady
     // state of an element); debug / profiling runs keep individual launches so that their events and taps work.
     nv_ctx::GraphKey key = {d_src, width, height, stride, cols, rows, d_rtab, casc->uid, dp.scale_factor, dp.min_neighbors,
-                            dp.min_w, dp.min_h, ctx->epoch, ctx->ps, ctx->ps->gen};
+                            dp.min_w, dp.min_h, ctx->epoch, ctx->ps, ctx->ps->gen,
+                            src.fmt, yuv ? planes.p1 : nullptr, yuv ? planes.p2 : nullptr, yuv ? planes.s1 : 0, yuv ? planes.s2 : 0};
     bool graphable = !ctx->debug && !ctx->no_graph;
     int nl = 0;
     if (graphable && ctx->gexec && key == ctx->gkey) {
@@ -953,13 +1021,31 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr
 extern "C" int nv_face_submit(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, int width, int height,
                               int stride_bytes, const nv_face_params *p)
 {
-    return face_submit_impl(ctx, c, bgr, false, width, height, stride_bytes, p);
+    FaceSrc src = {NV_FMT_BGR, {bgr, nullptr, nullptr}, {stride_bytes, 0, 0}, false};
+    return face_submit_impl(ctx, c, src, width, height, p);
 }
 
 extern "C" int nv_face_submit_device(nv_ctx *ctx, const nv_cascade *c, const uint8_t *d_bgr, int width, int height,
                                      int stride_bytes, const nv_face_params *p)
 {
-    return face_submit_impl(ctx, c, d_bgr, true, width, height, stride_bytes, p);
+    FaceSrc src = {NV_FMT_BGR, {d_bgr, nullptr, nullptr}, {stride_bytes, 0, 0}, true};
+    return face_submit_impl(ctx, c, src, width, height, p);
+}
+
+extern "C" int nv_face_submit_yuv(nv_ctx *ctx, const nv_cascade *c, const nv_yuv_frame *f, const nv_face_params *p)
+{
+    FaceSrc src;
+    int rc = check_yuv(ctx, f, &src);
+    if (rc != NV_OK) return rc;
+    return face_submit_impl(ctx, c, src, f->width, f->height, p);
+}
+
+extern "C" int nv_face_detect_yuv(nv_ctx *ctx, const nv_cascade *c, const nv_yuv_frame *f, const nv_face_params *p,
+                                  nv_rect *out, int cap, int *n)
+{
+    int rc = nv_face_submit_yuv(ctx, c, f, p);
+    if (rc != NV_OK) return rc;
+    return nv_face_collect(ctx, out, cap, n);
 }
 
 extern "C" int nv_face_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n)
@@ -993,6 +1079,22 @@ static int download(nv_ctx *ctx, const uint8_t *d_src, int row_bytes, int rows, 
     NV_CUDA(cudaMemcpy2DAsync(dst, dstride, d_src, row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
     NV_CUDA(cudaStreamSynchronize(ctx->stream));
     return NV_OK;
+}
+
+extern "C" int nv_yuv2bgr(nv_ctx *ctx, const nv_yuv_frame *f, uint8_t *dst_bgr, int dst_stride)
+{
+    FaceSrc src;
+    int rc = check_yuv(ctx, f, &src);
+    if (rc != NV_OK) return rc;
+    if (!dst_bgr || dst_stride < 3 * f->width) { nv_set_error("bad destination"); return NV_ERR_ARG; }
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    if (ctx->pending) { NV_CUDA(cudaStreamSynchronize(ctx->stream)); }
+    SrcPlanes planes = {src.p[0], src.p[1], src.p[2], src.s[0], src.s[1], src.s[2]};
+    if (!src.on_device && (rc = yuv_h2d(ctx, src, f->height, &planes)) != NV_OK) return rc;
+    if ((rc = ensure(&ctx->d_aux, &ctx->aux_cap, (size_t)f->width * f->height * 3)) != NV_OK) return rc;
+    NV_CUDA(launch_yuv2bgr(src.fmt, planes, f->width, f->height, ctx->d_aux, 3 * f->width, ctx->stream));
+    ctx->launches += 1;
+    return download(ctx, ctx->d_aux, 3 * f->width, f->height, dst_bgr, dst_stride);
 }
 
 extern "C" int nv_bgr2gray(nv_ctx *ctx, const uint8_t *src, int width, int height, int stride_bytes, int channels,

@@ -292,8 +292,9 @@ struct nv_ctx {
         const void *src = nullptr; int w = 0, h = 0, stride = 0, cols = 0, rows = 0; const int *rtab = nullptr;
         unsigned long long casc = 0; double sf = 0; int mn = 0, min_w = 0, min_h = 0; unsigned long long epoch = 0;
         const PlanSlot *slot = nullptr; unsigned long long slot_gen = 0;
+        int fmt = 0; const void *p1 = nullptr, *p2 = nullptr; int s1 = 0, s2 = 0;      // 4:2:0 input: chroma planes
         bool operator==(const GraphKey &o) const {
-            return src == o.src && w == o.w && h == o.h && stride == o.stride && cols == o.cols && rows == o.rows &&
+            return fmt == o.fmt && p1 == o.p1 && p2 == o.p2 && s1 == o.s1 && s2 == o.s2 && src == o.src && w == o.w && h == o.h && stride == o.stride && cols == o.cols && rows == o.rows &&
                    rtab == o.rtab && casc == o.casc && sf == o.sf && mn == o.mn && min_w == o.min_w && min_h == o.min_h &&
                    epoch == o.epoch && slot == o.slot && slot_gen == o.slot_gen;
         }
@@ -325,6 +326,10 @@ struct nv_ctx {
 // kernel launchers (each returns cudaGetLastError())
 // ----------------------------------------------------------------------------------------------
 // kernels_prep.cu
+struct SrcPlanes { const uint8_t *p0, *p1, *p2; int s0, s1, s2; };    // planes of a 4:2:0 frame: Y, U|UV|VU, V
+cudaError_t launch_face_prep_yuv(int fmt, const SrcPlanes &s, int sw, int sh, uint8_t *gray, int dw, int dh, const int *rtab,
+                                 int *hist, cudaStream_t st);
+cudaError_t launch_yuv2bgr(int fmt, const SrcPlanes &s, int w, int h, uint8_t *dst, int dstride, cudaStream_t st);
 cudaError_t launch_face_prep(const uint8_t *src, int sw, int sh, int sstride, int cn, uint8_t *gray, int dw, int dh,
                              const int *rtab, int *hist, cudaStream_t st);
 cudaError_t launch_bgr2gray(const uint8_t *src, int w, int h, int sstride, int cn, uint8_t *dst, int dstride,

@@ -97,6 +97,96 @@ k_face_prep(const uint8_t *__restrict__ src, int sw, int sh, int sstride, int cn
     if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
 }
 
+// ---- 4:2:0 ingest: the same block fed by I420 / NV12 / NV21 planes.  Every source pixel the
+// resize touches is converted with cvtColor(COLOR_YUV2BGR_*)'s arithmetic (BT.601, 20-bit fixed point, saturated to
+// u8 per pixel; oracle: ora_yuv420_to_bgr), so the result equals the reference block on the converted BGR frame.
+struct YuvTerms { int b, g, r; };                 // chroma contributions incl. the rounding half
+
+template <int FMT>   // 1: I420 (three planes), 2: NV12 (UV interleaved), 3: NV21 (VU interleaved)
+__device__ __forceinline__ YuvTerms yuv_chroma(const SrcPlanes &s, int x, int y)
+{
+    int u, v;
+    if (FMT == 1) {
+        u = s.p1[(size_t)(y >> 1) * s.s1 + (x >> 1)];
+        v = s.p2[(size_t)(y >> 1) * s.s2 + (x >> 1)];
+    } else {
+        const uint8_t *uv = s.p1 + (size_t)(y >> 1) * s.s1 + (x & ~1);
+        u = uv[FMT == 2 ? 0 : 1];
+        v = uv[FMT == 2 ? 1 : 0];
+    }
+    u -= 128; v -= 128;
+    YuvTerms t;
+    t.b = (1 << 19) + 2116026 * u;
+    t.g = (1 << 19) - 852492 * v - 409993 * u;
+    t.r = (1 << 19) + 1673527 * v;
+    return t;
+}
+
+__device__ __forceinline__ int sat_u8(int v) { return min(max(v, 0), 255); }
+
+__device__ __forceinline__ void yuv_pixel(const SrcPlanes &s, const YuvTerms &t, int x, int y, int c3[3])
+{
+    int yy = max(0, (int)s.p0[(size_t)y * s.s0 + x] - 16) * 1220542;
+    c3[0] = sat_u8((yy + t.b) >> 20);
+    c3[1] = sat_u8((yy + t.g) >> 20);
+    c3[2] = sat_u8((yy + t.r) >> 20);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256)
+k_face_prep_yuv(SrcPlanes s, int sw, int sh, uint8_t *__restrict__ gray, int dw, int dh, const int *__restrict__ rtab,
+                int *__restrict__ hist)
+{
+    __shared__ int sh_hist[256];
+    int tid = threadIdx.y * 32 + threadIdx.x;
+    sh_hist[tid] = 0;
+    __syncthreads();
+    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x < dw && y < dh) {
+        int mode = rtab[0], g, c3[3];
+        if (mode == RT_COPY) {
+            yuv_pixel(s, yuv_chroma<FMT>(s, x, y), x, y, c3);
+        } else if (mode == RT_BOX2) {                       // the four source pixels share one chroma sample
+            YuvTerms t = yuv_chroma<FMT>(s, 2 * x, 2 * y);
+            int a[3], b[3], c[3], d[3];
+            yuv_pixel(s, t, 2 * x, 2 * y, a);     yuv_pixel(s, t, 2 * x + 1, 2 * y, b);
+            yuv_pixel(s, t, 2 * x, 2 * y + 1, c); yuv_pixel(s, t, 2 * x + 1, 2 * y + 1, d);
+#pragma unroll
+            for (int k = 0; k < 3; k++) c3[k] = (a[k] + b[k] + c[k] + d[k] + 2) >> 2;
+        } else {
+            const int *xofs = rtab + 1, *xa = xofs + dw, *y0t = xa + dw, *y1t = y0t + dh, *ybt = y1t + dh;
+            int sx = xofs[x], sx1 = min(sx + 1, sw - 1), xav = xa[x], ybv = ybt[y], sy0 = y0t[y], sy1 = y1t[y];
+            int a0 = (short)(xav & 0xFFFF), a1 = xav >> 16, b0 = (short)(ybv & 0xFFFF), b1 = ybv >> 16;
+            int p00[3], p01[3], p10[3], p11[3];
+            yuv_pixel(s, yuv_chroma<FMT>(s, sx, sy0), sx, sy0, p00);   yuv_pixel(s, yuv_chroma<FMT>(s, sx1, sy0), sx1, sy0, p01);
+            yuv_pixel(s, yuv_chroma<FMT>(s, sx, sy1), sx, sy1, p10);   yuv_pixel(s, yuv_chroma<FMT>(s, sx1, sy1), sx1, sy1, p11);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                int h0 = p00[k] * a0 + p01[k] * a1, h1 = p10[k] * a0 + p11[k] * a1;
+                c3[k] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;       // A.2 vertical pass
+            }
+        }
+        g = gray_of(c3[0], c3[1], c3[2]);
+        gray[(size_t)y * dw + x] = (uint8_t)g;
+        atomicAdd(&sh_hist[g], 1);
+    }
+    __syncthreads();
+    if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
+}
+
+// cvtColor(COLOR_YUV2BGR_*) alone (parity tap of the ingest path); one thread per pixel
+template <int FMT>
+__global__ void __launch_bounds__(256)
+k_yuv2bgr(SrcPlanes s, int w, int h, uint8_t *__restrict__ dst, int dstride)
+{
+    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    int c3[3];
+    yuv_pixel(s, yuv_chroma<FMT>(s, x, y), x, y, c3);
+    uint8_t *d = dst + (size_t)y * dstride + 3 * x;
+    d[0] = (uint8_t)c3[0]; d[1] = (uint8_t)c3[1]; d[2] = (uint8_t)c3[2];
+}
+
 __global__ void __launch_bounds__(256)
 k_bgr2gray(const uint8_t *__restrict__ src, int w, int h, int sstride, int cn, uint8_t *__restrict__ dst, int dstride)
 {
@@ -204,6 +294,25 @@ cudaError_t launch_face_prep(const uint8_t *src, int sw, int sh, int sstride, in
                              const int *rtab, int *hist, cudaStream_t st)
 {
     k_face_prep<<<grid2d(dw, dh), dim3(32, 8), 0, st>>>(src, sw, sh, sstride, cn, gray, dw, dh, rtab, hist);
+    return cudaGetLastError();
+}
+cudaError_t launch_face_prep_yuv(int fmt, const SrcPlanes &s, int sw, int sh, uint8_t *gray, int dw, int dh, const int *rtab,
+                                 int *hist, cudaStream_t st)
+{
+    dim3 g = grid2d(dw, dh), b(32, 8);
+    if (fmt == NV_FMT_I420) k_face_prep_yuv<1><<<g, b, 0, st>>>(s, sw, sh, gray, dw, dh, rtab, hist);
+    else if (fmt == NV_FMT_NV12) k_face_prep_yuv<2><<<g, b, 0, st>>>(s, sw, sh, gray, dw, dh, rtab, hist);
+    else if (fmt == NV_FMT_NV21) k_face_prep_yuv<3><<<g, b, 0, st>>>(s, sw, sh, gray, dw, dh, rtab, hist);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+cudaError_t launch_yuv2bgr(int fmt, const SrcPlanes &s, int w, int h, uint8_t *dst, int dstride, cudaStream_t st)
+{
+    dim3 g = grid2d(w, h), b(32, 8);
+    if (fmt == NV_FMT_I420) k_yuv2bgr<1><<<g, b, 0, st>>>(s, w, h, dst, dstride);
+    else if (fmt == NV_FMT_NV12) k_yuv2bgr<2><<<g, b, 0, st>>>(s, w, h, dst, dstride);
+    else if (fmt == NV_FMT_NV21) k_yuv2bgr<3><<<g, b, 0, st>>>(s, w, h, dst, dstride);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 cudaError_t launch_bgr2gray(const uint8_t *src, int w, int h, int sstride, int cn, uint8_t *dst, int dstride,

@@ -45,6 +45,15 @@ class FaceParams(C.Structure):
                 ("min_w", C.c_int), ("min_h", C.c_int)]
 
 
+class YuvFrame(C.Structure):
+    _fields_ = [("format", C.c_int), ("width", C.c_int), ("height", C.c_int), ("plane", C.c_void_p * 3),
+                ("stride", C.c_int * 3), ("on_device", C.c_int)]
+
+
+FMT_BGR, FMT_I420, FMT_NV12, FMT_NV21 = 0, 1, 2, 3
+_FMT = {"I420": FMT_I420, "YV12": FMT_I420, "NV12": FMT_NV12, "NV21": FMT_NV21}
+
+
 class TrackerParams(C.Structure):
     _fields_ = [("threshold", C.c_int), ("min_area", C.c_int), ("max_area", C.c_long), ("distance", C.c_int)]
 
@@ -70,6 +79,9 @@ _SIGS = {
     "nv_face_submit": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(FaceParams)]),
     "nv_face_submit_device": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(FaceParams)]),
     "nv_face_collect": (_i, [_vp, _vp, _i, _ip]),
+    "nv_face_detect_yuv": (_i, [_vp, _vp, C.POINTER(YuvFrame), C.POINTER(FaceParams), _vp, _i, _ip]),
+    "nv_face_submit_yuv": (_i, [_vp, _vp, C.POINTER(YuvFrame), C.POINTER(FaceParams)]),
+    "nv_yuv2bgr": (_i, [_vp, C.POINTER(YuvFrame), _vp, _i]),
     "nv_tracker_process": (_i, [_vp, _vp, _i, _i, _i, C.c_double, C.POINTER(TrackerParams), _vp, _i, _ip]),
     "nv_tracker_reset": (_i, [_vp]),
     "nv_bgr2gray": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i]),
@@ -366,6 +378,45 @@ class Context:
         p = self._face_params(width_to_process, scale_factor, min_neighbors, min_size)
         _check(_lib.nv_face_submit_device(self.handle, casc.handle, _vp(dev_ptr), w, h, stride, C.byref(p)),
                "nv_face_submit_device")
+
+    # ---- 4:2:0 ingest: planes = (y, u, v) for I420 (YV12: pass the planes in I420 meaning), (y, uv) for NV12 / NV21;
+    #      each a 2-D uint8 array with unit column stride (row strides are honoured)
+    @staticmethod
+    def _yuv_frame(planes, fmt):
+        y, c1 = planes[0], planes[1]
+        c2 = planes[2] if len(planes) > 2 and planes[2] is not None else None
+        for a in (y, c1) + ((c2,) if c2 is not None else ()):
+            if a.dtype != np.uint8 or a.ndim != 2 or a.strides[1] != 1:
+                raise ValueError("planes must be 2-D uint8 arrays with contiguous rows")
+        h, w = y.shape
+        f = YuvFrame()
+        f.format, f.width, f.height, f.on_device = _FMT[fmt], w, h, 0
+        f.plane[0], f.plane[1] = y.ctypes.data, c1.ctypes.data
+        f.stride[0], f.stride[1] = y.strides[0], c1.strides[0]
+        if c2 is not None:
+            f.plane[2], f.stride[2] = c2.ctypes.data, c2.strides[0]
+        return f
+
+    def face_detect_yuv(self, casc: Cascade, planes, fmt="I420", width_to_process=160, scale_factor=1.25, min_neighbors=3,
+                        min_size=None):
+        f = self._yuv_frame(planes, fmt)
+        p = self._face_params(width_to_process, scale_factor, min_neighbors, min_size)
+        n = C.c_int(0)
+        _check(_lib.nv_face_detect_yuv(self.handle, casc.handle, C.byref(f), C.byref(p), self._out, self._cap, C.byref(n)),
+               "nv_face_detect_yuv")
+        return _rects(self._out, n.value)
+
+    def face_submit_yuv(self, casc: Cascade, planes, fmt="I420", width_to_process=160, scale_factor=1.25, min_neighbors=3,
+                        min_size=None):
+        f = self._yuv_frame(planes, fmt)
+        p = self._face_params(width_to_process, scale_factor, min_neighbors, min_size)
+        _check(_lib.nv_face_submit_yuv(self.handle, casc.handle, C.byref(f), C.byref(p)), "nv_face_submit_yuv")
+
+    def yuv2bgr(self, planes, fmt="I420"):
+        f = self._yuv_frame(planes, fmt)
+        out = np.empty((f.height, f.width, 3), np.uint8)
+        _check(_lib.nv_yuv2bgr(self.handle, C.byref(f), _p(out), 3 * f.width), "nv_yuv2bgr")
+        return out
 
     def face_collect(self):
         n = C.c_int(0)

@@ -98,3 +98,43 @@ def tracker_sequence(width: int, height: int, nframes: int, seed: int = 4, nsq: 
         out[..., 3] = 255
         frames.append(out)
     return frames
+
+
+def to_yuv420(bgr: np.ndarray, fmt: str = "I420") -> np.ndarray:
+    """Pack a BGR frame (even width and height) as a 4:2:0 buffer of h*3/2 rows of w bytes — the layout a video decoder
+    hands to GStreamer and cv2.cvtColor(.., COLOR_YUV2BGR_<fmt>) reads.  BT.601 studio range, chroma = mean of the 2x2
+    block.  Input generator only: parity of the ingest path is defined on the YUV bytes, not on this conversion."""
+    h, w, _ = bgr.shape
+    assert w % 2 == 0 and h % 2 == 0
+    b, g, r = (bgr[..., c].astype(np.float64) for c in range(3))
+    y = 16 + (65.481 * r + 128.553 * g + 24.966 * b) / 255.0
+    u = 128 + (-37.797 * r - 74.203 * g + 112.0 * b) / 255.0
+    v = 128 + (112.0 * r - 93.786 * g - 18.214 * b) / 255.0
+    sub = lambda a: a.reshape(h // 2, 2, w // 2, 2).mean(axis=(1, 3))
+    q = lambda a: np.clip(np.rint(a), 0, 255).astype(np.uint8)
+    y8, u8, v8 = q(y), q(sub(u)), q(sub(v))
+    out = np.empty(w * h * 3 // 2, np.uint8)
+    out[:w * h] = y8.reshape(-1)
+    c = out[w * h:]
+    if fmt == "I420":
+        c[:w * h // 4] = u8.reshape(-1); c[w * h // 4:] = v8.reshape(-1)
+    elif fmt == "YV12":
+        c[:w * h // 4] = v8.reshape(-1); c[w * h // 4:] = u8.reshape(-1)
+    elif fmt == "NV12":
+        c[0::2] = u8.reshape(-1); c[1::2] = v8.reshape(-1)
+    elif fmt == "NV21":
+        c[0::2] = v8.reshape(-1); c[1::2] = u8.reshape(-1)
+    else:
+        raise ValueError(fmt)
+    return out.reshape(h * 3 // 2, w)
+
+
+def yuv420_planes(buf: np.ndarray, w: int, h: int, fmt: str = "I420"):
+    """Plane views of a packed 4:2:0 buffer: (y, u, v) in I420 meaning for I420 / YV12, (y, uv) for NV12 / NV21."""
+    flat = buf.reshape(-1)
+    y = flat[:w * h].reshape(h, w)
+    if fmt in ("NV12", "NV21"):
+        return y, flat[w * h:].reshape(h // 2, w)
+    a = flat[w * h:w * h + w * h // 4].reshape(h // 2, w // 2)
+    b = flat[w * h + w * h // 4:].reshape(h // 2, w // 2)
+    return (y, a, b) if fmt == "I420" else (y, b, a)

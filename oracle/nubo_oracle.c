@@ -49,6 +49,35 @@ ORA_API void ora_bgr2gray(const uint8_t *src, int w, int h, int sstride, int cn,
 }
 
 /* ---------------------------------------------------------------------------------------
+ * A.1b cvtColor(COLOR_YUV2BGR_I420 / _NV12 / _NV21): the 4:2:0 ingest extension.
+ *      The reference elements only accept BGR caps (kmsfacedetect.cpp:1025-1031), so in a pipeline a
+ *      videoconvert sits in front of them; this is OpenCV 4.13's conversion (ITU-R BT.601, 20-bit fixed
+ *      point, modules/imgproc color_yuv), pinned against cv2 in tests/test_oracle_vs_cv2.py.
+ *      fmt 0: three planes (I420; YV12 = the caller swaps u and v), 1: NV12 (u = interleaved UV plane),
+ *      2: NV21 (u = interleaved VU plane).  w and h even.
+ * ------------------------------------------------------------------------------------- */
+ORA_API void ora_yuv420_to_bgr(int fmt, const uint8_t *yp, int ystride, const uint8_t *up, int ustride,
+                               const uint8_t *vp, int vstride, int w, int h, uint8_t *dst, int dstride)
+{
+    for (int y = 0; y < h; y++) {
+        uint8_t *d = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; x++) {
+            int u, v;
+            if (fmt == 0) { u = up[(size_t)(y / 2) * ustride + x / 2]; v = vp[(size_t)(y / 2) * vstride + x / 2]; }
+            else {
+                const uint8_t *uv = up + (size_t)(y / 2) * ustride + (x / 2) * 2;
+                u = uv[fmt == 1 ? 0 : 1]; v = uv[fmt == 1 ? 1 : 0];
+            }
+            u -= 128; v -= 128;
+            int yy = ora_max(0, (int)yp[(size_t)y * ystride + x] - 16) * 1220542;
+            d[3 * x + 0] = ora_sat_u8((yy + (1 << 19) + 2116026 * u) >> 20);
+            d[3 * x + 1] = ora_sat_u8((yy + (1 << 19) - 852492 * v - 409993 * u) >> 20);
+            d[3 * x + 2] = ora_sat_u8((yy + (1 << 19) + 1673527 * v) >> 20);
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------
  * A.2  cv::resize(INTER_LINEAR), u8, cn interleaved channels (kmsfacedetect.cpp:805,
  *      kmseyedetect.cpp:956,963 ...)
  * ------------------------------------------------------------------------------------- */

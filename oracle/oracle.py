@@ -87,6 +87,8 @@ def lib():
                                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib.ora_update_mhi.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double]
         _lib.ora_absdiff_threshold.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        _lib.ora_yuv420_to_bgr.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                           C.c_int, C.c_int, C.c_void_p, C.c_int]
     return _lib
 
 
@@ -230,6 +232,32 @@ def bgr2gray(img):
     img = _u8(img); h, w, cn = img.shape
     out = np.empty((h, w), np.uint8)
     lib().ora_bgr2gray(_p(img), w, h, img.strides[0], cn, _p(out), w)
+    return out
+
+
+YUV_FORMATS = {"I420": 0, "YV12": 0, "NV12": 1, "NV21": 2}
+
+
+def yuv420_planes(buf, w, h, fmt="I420"):
+    """Views of the planes of a packed 4:2:0 buffer of w*h*3/2 bytes (what cv2.cvtColor takes as a (h*3/2, w) image):
+    (y, u, v) for I420 / YV12 (u, v in I420 meaning), (y, uv, None) for NV12 / NV21."""
+    flat = _u8(buf).reshape(-1)
+    assert w % 2 == 0 and h % 2 == 0 and flat.size == w * h * 3 // 2
+    y = flat[:w * h].reshape(h, w)
+    if fmt in ("NV12", "NV21"):
+        return y, flat[w * h:].reshape(h // 2, w), None
+    a = flat[w * h:w * h + w * h // 4].reshape(h // 2, w // 2)
+    b = flat[w * h + w * h // 4:].reshape(h // 2, w // 2)
+    return (y, a, b) if fmt == "I420" else (y, b, a)
+
+
+def yuv420_to_bgr(y, u, v=None, fmt="I420"):
+    """cv2.cvtColor(.., COLOR_YUV2BGR_I420 / _YV12 / _NV12 / _NV21) on explicit planes (any row strides)."""
+    h, w = y.shape
+    assert y.strides[1] == 1 and u.strides[1] == 1 and (v is None or v.strides[1] == 1)
+    out = np.empty((h, w, 3), np.uint8)
+    lib().ora_yuv420_to_bgr(YUV_FORMATS[fmt], _p(y), y.strides[0], _p(u), u.strides[0],
+                            _p(v) if v is not None else None, v.strides[0] if v is not None else 0, w, h, _p(out), 3 * w)
     return out
 
 

@@ -80,8 +80,33 @@ def general_case(cascade, W, H, k, seed, smin, smax, sf, mn, min_size):
                 raw=raw.tolist(), grouped=grp.tolist())
 
 
+YUV_CODES = {"I420": cv2.COLOR_YUV2BGR_I420, "YV12": cv2.COLOR_YUV2BGR_YV12, "NV12": cv2.COLOR_YUV2BGR_NV12,
+             "NV21": cv2.COLOR_YUV2BGR_NV21}
+
+
+def yuv_case(fmt, W, H, k, seed, w2p, sf, mn, min_size):
+    """4:2:0 ingest: cvtColor(COLOR_YUV2BGR_<fmt>) in front of the face block (kmsfacedetect.cpp:805-811)."""
+    buf = synth.to_yuv420(synth.frame(W, H, k, seed), fmt)
+    bgr = cv2.cvtColor(buf, YUV_CODES[fmt])
+    iscale = W // w2p
+    rows, cols = int(np.rint(H / iscale)), int(np.rint(W / iscale))
+    eq = cv2.equalizeHist(cv2.cvtColor(cv2.resize(bgr, (cols, rows), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY))
+    ms = (cols // 20, rows // 20) if min_size is None else tuple(min_size)
+    cc = cv2.CascadeClassifier(os.path.join(CASC, "haarcascade_frontalface_alt.xml"))
+    grp = np.asarray(cc.detectMultiScale(eq, scaleFactor=sf, minNeighbors=mn, minSize=ms)).reshape(-1, 4)
+    return dict(fmt=fmt, W=W, H=H, k=k, seed=seed, width_to_process=w2p, scale_factor=sf, min_neighbors=mn,
+                min_size=list(ms), yuv_sha=sha(buf), bgr_sha=sha(bgr), eq_sha=sha(eq), grouped=grp.tolist())
+
+
 def main():
     cv2.setNumThreads(1)
+    yuv = [yuv_case("I420", 640, 480, 4, 1, 160, 1.25, 3, None),            # linear resize (4x)
+           yuv_case("NV12", 1280, 720, 3, 1000, 640, 1.25, 3, None),         # cfg5 stream 0: the 2x box path
+           yuv_case("NV21", 640, 360, 6, 3, 640, 1.1, 3, (24, 24)),          # no resize
+           yuv_case("YV12", 642, 362, 4, 7, 214, 1.2, 2, (0, 0))]            # odd chroma width, 3x
+    with open(os.path.join(HERE, "yuv_golden.json"), "w") as f:
+        json.dump(dict(cv2=cv2.__version__, cases=yuv), f)
+    print("wrote", len(yuv), "4:2:0 ingest cases")
     gen = [general_case(c, 400, 300, 2, 3, 0.5, 0.9, sf, 2, ms) for c, sf, ms in [
         ("haarcascade_lefteye_2splits.xml", 1.1, (20, 20)), ("haarcascade_righteye_2splits.xml", 1.1, (0, 0)),
         ("haarcascade_smile.xml", 1.1, (1, 1)), ("haarcascade_eye_tree_eyeglasses.xml", 1.25, (0, 0)),
