@@ -518,6 +518,35 @@ def main():
         aux["nv12_ingest"] = {"frames_per_s": fps5y, "streams_at_30fps": fps5y / 30.0, "h2d_bytes_per_frame": 1280 * 720 * 3 // 2}
         for c in c5:
             c.close()
+        # the same measurement from native host threads (tools/streams_bench.cpp: no interpreter between the calls;
+        # what a media server's streaming threads do), BGR and NV12, checked by the number of rectangles found
+        tool = os.path.join(ROOT, "nubomedia-vca_b200", "lib", "streams_bench")
+        if os.path.exists(tool):
+            import tempfile
+            exp = [len(r) for r in (lambda c: [c.face_detect(casc, f, **p5) for f in f5])(nv.Context(local, 1280, 720))]
+            iters, nthr = 200, 4
+            nat = {}
+            with tempfile.TemporaryDirectory(prefix="nubovca_s5_") as td:
+                for fmt, blobs in (("bgr", f5), ("nv12", y5)):
+                    path = os.path.join(td, fmt + ".raw")
+                    with open(path, "wb") as fh:
+                        for b in blobs:
+                            fh.write(np.ascontiguousarray(b).tobytes())
+                    barrier()
+                    r = subprocess.run([tool, "--frames-file", path, "--nframes", str(len(blobs)), "--fmt", fmt, "--xml", FACE_XML,
+                                        "--gpu", str(local), "--streams", str(S5), "--threads", str(nthr), "--iters", str(iters)],
+                                       capture_output=True, text=True, timeout=300)
+                    if r.returncode != 0:
+                        raise SystemExit("streams_bench failed: " + r.stderr[-500:])
+                    j = json.loads(r.stdout.strip().splitlines()[-1])
+                    if fmt == "bgr":       # NV12 frames are a different image (quantised chroma): only the BGR count is pinned here
+                        want = sum(exp[(s_ + it) % len(exp)] for s_ in range(S5) for it in range(iters))
+                        assert j["rects"] == want, (j["rects"], want)
+                    fps, _ = shard.aggregate_throughput(j["frames"], 1e3 * j["seconds"], dist, "cuda")
+                    nat[fmt] = {"frames_per_s": fps, "streams_at_30fps": fps / 30.0, "h2d_bytes_per_frame": j["h2d_bytes_per_frame"]}
+            nat["host_threads_per_gpu"] = nthr
+            nat["streams_per_gpu_in_flight"] = S5
+            aux["native_host_threads"] = nat
         if rank == 0 and world == 1:
             aux["other_configs_one_stream"] = aux_other_configs(nv, local, world)
             if not args.no_cpu_baseline:

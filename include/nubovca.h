@@ -20,6 +20,7 @@
 #ifndef NUBOVCA_H
 #define NUBOVCA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -122,6 +123,11 @@ NV_API int nv_face_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n);
  * HBM when the timed region starts).  d_bgr must stay valid until collect. */
 NV_API int nv_face_submit_device(nv_ctx *ctx, const nv_cascade *c, const uint8_t *d_bgr, int width, int height,
                                  int stride_bytes, const nv_face_params *p);
+
+/* Page-locked host memory for frames (what a GstAllocator / buffer pool of the shell hands upstream, so that
+ * decoded frames land where the DMA engine reads them without a staging copy).  Portable across devices. */
+NV_API int nv_host_alloc(size_t bytes, void **out);
+NV_API void nv_host_free(void *p);
 
 /* ---- 4:2:0 ingest (extension).  The reference elements negotiate BGR only
  *      (kmsfacedetect.cpp:129-133,1025-1031), so a decoder's I420 / NV12 output passes through a CPU videoconvert

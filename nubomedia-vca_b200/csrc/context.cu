@@ -1032,6 +1032,16 @@ extern "C" int nv_face_submit_device(nv_ctx *ctx, const nv_cascade *c, const uin
     return face_submit_impl(ctx, c, src, width, height, p);
 }
 
+extern "C" int nv_host_alloc(size_t bytes, void **out)
+{
+    if (!out || !bytes) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    if (nv_device_count() < 1) { nv_set_error("no CUDA device"); return NV_ERR_NO_DEVICE; }
+    NV_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return NV_OK;
+}
+
+extern "C" void nv_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 extern "C" int nv_face_submit_yuv(nv_ctx *ctx, const nv_cascade *c, const nv_yuv_frame *f, const nv_face_params *p)
 {
     FaceSrc src;
