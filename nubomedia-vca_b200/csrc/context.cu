@@ -470,7 +470,7 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         L.xtab = (int)tofs; L.ytab = (int)tofs + lw; tofs += lw + lh;
         L.pofs = (int)pofs; pofs += (long long)lw * lh;
         L.rowblk0 = P.total_rowblk; P.total_rowblk += (lh + 7) / 8;
-        L.colblk0 = P.total_colblk; P.total_colblk += (L.ipitch + 31) / 32;
+        L.colblk0 = P.total_colblk; P.total_colblk += (L.ipitch + NV_COLBLK - 1) / NV_COLBLK;
         L.chunk0 = P.total_chunks; P.total_chunks += L.nxw * L.ny;
         L.row0 = P.total_rows; P.total_rows += L.ny;
         L.dblk0 = P.total_dblk; P.total_dblk += (lw + lh + 255) / 256;
@@ -571,6 +571,10 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
         if (tp.cp % 8 == 0) tp.cp += 4;
         tp.rt = (NV_CTY - 1) * ys + m.win_h + 1;
         tp.kskew = (ys * tp.cp) & 31;
+        {   // NUBOVCA_LIST_BIAS: experiments only (a large value keeps every stage in class mode)
+            const char *lb = getenv("NUBOVCA_LIST_BIAS");
+            tp.list_bias = lb ? atoi(lb) : 1;
+        }
         tp.ps = align_up(tp.rt * tp.cp, 32);
         tp.level_begin = c == 0 ? 0 : P.nlv2;
         tp.level_end = c == 0 ? P.nlv2 : P.nlevels;

@@ -11,6 +11,8 @@
 
 #include "nubovca.h"
 
+#define NV_LIST_CAP 1024         // most alive windows of a tile a list-mode stage of k_cascade_classes takes
+#define NV_COLBLK 128            // physical integral columns per block of the column scan
 #define NV_MAX_LEVELS 64          // level index is packed in 6 bits of a window id
 #define NV_MAX_STAGES 64
 #define NV_RESULT_INLINE 1024     // rects copied back with the header in one D2H
@@ -124,7 +126,7 @@ struct LevelDesc {
     int xtab, ytab;        // offsets into the pyramid coefficient tables
     int pofs;              // byte offset of the u8 level image (debug)
     int rowblk0;           // first row-block (8 rows) of this level in k_pyr_rowscan's grid
-    int colblk0;           // first column-block (32 physical cols) in k_colscan's grid (per array)
+    int colblk0;           // first column-block (NV_COLBLK physical cols) in k_colscan's grid (per array)
     int chunk0;            // first 32-window chunk (row-major over levels)
     int row0;              // first window row in k_stage0_rows' grid
     int dblk0;             // first block (256 diagonals) of this level in the tilted-integral kernels' grid
@@ -188,6 +190,7 @@ struct TileParams {
     int level_begin, level_end;
     int cp, rt, ps;                // tile plane geometry: columns, rows, plane stride (words)
     int kskew;                     // bank class of window (lx, ly) = (lx + kskew * ly) & 31
+    int list_bias;                 // a stage runs in list mode when ceil(alive / 32) + list_bias < fullest class (k_cascade_classes)
     const CUtensorMap *maps;       // one per level, in global memory (written by the host before launch)
     const PlanDev *plan;
     const uint32_t *bits_alive;

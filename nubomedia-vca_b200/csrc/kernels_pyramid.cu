@@ -17,8 +17,13 @@ __device__ __forceinline__ int find_level(const PlanDev *__restrict__ plan, int 
     return l;
 }
 
-// One warp per level row: resize (two source rows, 8.8 x 8.8 fixed point) -> equalised value -> warp-shuffle
-// inclusive scan of v and v*v along the row, carried across 32-pixel chunks.
+// One warp per level row, eight integral columns per lane and 256 per chunk: resize (two source rows, 8.8 x 8.8 fixed
+// point) -> equalised value -> running sums of v and v*v inside the lane, ONE warp-shuffle scan of the lane totals per
+// chunk, carried across chunks.  A lane owns integral columns c = 8k .. 8k+7 (pixel x = c - 1; c = 0 is the zero column),
+// so that its results leave as aligned 16-byte stores: four words per plane on de-interleaved (ystep 2) rows, two
+// groups of four on plain rows.  (The first version scanned every 32 pixels with ten shuffles: 100 instructions per
+// pixel, 25.6 M warp instructions per config-3 frame; this one needs about a third.)
+#define RS_PX 8
 __global__ void __launch_bounds__(256)
 k_pyr_rowscan(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ gray, int gstride,
               const uint8_t *__restrict__ lut, const int2 *__restrict__ ptab, uint32_t *__restrict__ sum,
@@ -31,7 +36,7 @@ k_pyr_rowscan(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ gray
 
     int l = find_level(plan, blockIdx.x, &LevelDesc::rowblk0);
     const LevelDesc &L = plan->lv[l];
-    int lw = L.lw, lh = L.lh, ys = L.ystep, pitch = L.ipitch, plane = L.iplane;
+    const int lw = L.lw, lh = L.lh, ys = L.ystep, pitch = L.ipitch, plane = L.iplane;
     int y = (blockIdx.x - L.rowblk0) * 8 + warp;
     if (y >= lh) return;
     uint32_t *srow = sum + L.iofs, *qrow = sq + L.iofs;
@@ -39,76 +44,119 @@ k_pyr_rowscan(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ gray
         for (int c = lane; c < pitch; c += 32) { srow[c] = 0; qrow[c] = 0; }
     srow += (size_t)(y + 1) * pitch;
     qrow += (size_t)(y + 1) * pitch;
-    if (lane == 0) { srow[0] = 0; qrow[0] = 0; }        // first integral column (c = 0 -> plane 0, col 0)
 
     const int2 *xt = ptab + L.xtab, *yt = ptab + L.ytab;
     int2 ty = yt[y];
     const uint8_t *g0 = gray + (size_t)ty.x * gstride, *g1 = ty.y < 0 ? g0 : g0 + gstride;
-    uint32_t r1 = ty.y < 0 ? 0u : (uint32_t)ty.y, r0 = 256u - r1;
+    const uint32_t r1 = ty.y < 0 ? 0u : (uint32_t)ty.y, r0 = 256u - r1;
     uint32_t carry_s = 0, carry_q = 0;
-    for (int x0 = 0; x0 < lw; x0 += 32) {
-        int x = x0 + lane;
-        uint32_t v = 0;
-        if (x < lw) {
-            int2 tx = xt[x];
-            uint32_t h0, h1;
-            if (tx.y < 0) { h0 = (uint32_t)s_lut[g0[tx.x]] << 8; h1 = (uint32_t)s_lut[g1[tx.x]] << 8; }
-            else {
-                uint32_t c1 = (uint32_t)tx.y, c0 = 256u - c1;
-                h0 = s_lut[g0[tx.x]] * c0 + s_lut[g0[tx.x + 1]] * c1;
-                h1 = s_lut[g1[tx.x]] * c0 + s_lut[g1[tx.x + 1]] * c1;
+    for (int c0 = 0; c0 <= lw; c0 += 32 * RS_PX) {
+        const int cb = c0 + lane * RS_PX;
+        uint32_t s[RS_PX], q[RS_PX];
+        uint32_t rs = 0, rq = 0;
+#pragma unroll
+        for (int k = 0; k < RS_PX; k++) {
+            int x = cb + k - 1;
+            uint32_t v = 0;
+            if (x >= 0 && x < lw) {
+                int2 tx = __ldg(xt + x);
+                uint32_t h0, h1;
+                if (tx.y < 0) { h0 = (uint32_t)s_lut[g0[tx.x]] << 8; h1 = (uint32_t)s_lut[g1[tx.x]] << 8; }
+                else {
+                    uint32_t c1 = (uint32_t)tx.y, c0w = 256u - c1;
+                    h0 = s_lut[g0[tx.x]] * c0w + s_lut[g0[tx.x + 1]] * c1;
+                    h1 = s_lut[g1[tx.x]] * c0w + s_lut[g1[tx.x + 1]] * c1;
+                }
+                v = (h0 * r0 + h1 * r1 + 32768u) >> 16;
+                if (pyr_debug) pyr_debug[L.pofs + (size_t)y * lw + x] = (uint8_t)v;
             }
-            v = (h0 * r0 + h1 * r1 + 32768u) >> 16;
-            if (pyr_debug) pyr_debug[L.pofs + (size_t)y * lw + x] = (uint8_t)v;
+            rs += v; rq += v * v;
+            s[k] = rs; q[k] = rq;
         }
-        uint32_t s = v, q = v * v;
+        uint32_t is = rs, iq = rq;                      // inclusive scan of the lane totals
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t ts = __shfl_up_sync(0xffffffffu, s, d), tq = __shfl_up_sync(0xffffffffu, q, d);
-            if (lane >= d) { s += ts; q += tq; }
+            uint32_t ts = __shfl_up_sync(0xffffffffu, is, d), tq = __shfl_up_sync(0xffffffffu, iq, d);
+            if (lane >= d) { is += ts; iq += tq; }
         }
-        s += carry_s; q += carry_q;
-        if (x < lw) {
-            int c = x + 1;
-            int pc = ys == 2 ? (c & 1) * plane + (c >> 1) : c;
-            srow[pc] = s; qrow[pc] = q;
+        const uint32_t os = carry_s + is - rs, oq = carry_q + iq - rq;
+#pragma unroll
+        for (int k = 0; k < RS_PX; k++) { s[k] += os; q[k] += oq; }
+        if (cb + RS_PX - 1 <= lw) {                     // all eight columns exist: aligned 16-byte stores
+            if (ys == 2) {
+                int e = cb >> 1;
+                *reinterpret_cast<uint4 *>(srow + e) = make_uint4(s[0], s[2], s[4], s[6]);
+                *reinterpret_cast<uint4 *>(srow + plane + e) = make_uint4(s[1], s[3], s[5], s[7]);
+                *reinterpret_cast<uint4 *>(qrow + e) = make_uint4(q[0], q[2], q[4], q[6]);
+                *reinterpret_cast<uint4 *>(qrow + plane + e) = make_uint4(q[1], q[3], q[5], q[7]);
+            } else {
+                *reinterpret_cast<uint4 *>(srow + cb) = make_uint4(s[0], s[1], s[2], s[3]);
+                *reinterpret_cast<uint4 *>(srow + cb + 4) = make_uint4(s[4], s[5], s[6], s[7]);
+                *reinterpret_cast<uint4 *>(qrow + cb) = make_uint4(q[0], q[1], q[2], q[3]);
+                *reinterpret_cast<uint4 *>(qrow + cb + 4) = make_uint4(q[4], q[5], q[6], q[7]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < RS_PX; k++) {
+                int c = cb + k;
+                if (c <= lw) {
+                    int pc = ys == 2 ? (c & 1) * plane + (c >> 1) : c;
+                    srow[pc] = s[k]; qrow[pc] = q[k];
+                }
+            }
         }
-        carry_s = __shfl_sync(0xffffffffu, s, 31);
-        carry_q = __shfl_sync(0xffffffffu, q, 31);
+        carry_s += __shfl_sync(0xffffffffu, is, 31);
+        carry_q += __shfl_sync(0xffffffffu, iq, 31);
     }
 }
 
-// Column pass, shared-memory tiled: a block owns 32 physical columns of one array of one level; its 32 warps
-// split the rows into 32 bands.  Pass 1 sums each band, the band totals are exchanged through shared memory
-// and prefixed, pass 2 re-reads the band (L1/L2 hit) and writes the running column sums.  Every global access
-// is a 128-byte row segment.
+// Column pass, shared-memory tiled: a block owns NV_COLBLK = 128 physical columns of one array of one level (four per
+// lane, moved as 16-byte vectors); its 32 warps split the rows into 32 bands.  Pass 1 sums each band, the band totals
+// are exchanged through shared memory and prefixed, pass 2 re-reads the band (L1/L2 hit) and writes the running
+// column sums.  Every global access is a 512-byte row segment.
+__device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
 __global__ void __launch_bounds__(1024)
 k_colscan(const PlanDev *__restrict__ plan, int total_colblk, uint32_t *__restrict__ sum, uint32_t *__restrict__ sq)
 {
-    __shared__ uint32_t tot[32][33];
+    __shared__ uint4 tot[32][33];
     int lane = threadIdx.x & 31, band = threadIdx.x >> 5;
     int b = blockIdx.x;
     uint32_t *arr = sum;
     if (b >= total_colblk) { b -= total_colblk; arr = sq; }
     int l = find_level(plan, b, &LevelDesc::colblk0);
     const LevelDesc &L = plan->lv[l];
-    int pitch = L.ipitch, rows = L.lh + 1;
-    int col = (b - L.colblk0) * 32 + lane;
-    bool ok = col < pitch;
-    uint32_t *p = arr + L.iofs + col;
+    const int pitch = L.ipitch, rows = L.lh + 1;
+    int col = (b - L.colblk0) * NV_COLBLK + lane * 4;
+    bool ok = col < pitch;                              // pitch is a multiple of 4: a lane's four columns exist together
+    uint4 *p = reinterpret_cast<uint4 *>(arr + L.iofs + col);
+    const size_t rs = (size_t)(pitch >> 2);             // row stride in uint4
     int R = (rows + 31) / 32, r0 = band * R, r1 = min(rows, r0 + R);
-    uint32_t acc = 0;
-    if (ok)
-        for (int r = r0; r < r1; r++) acc += p[(size_t)r * pitch];
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    if (ok) {
+        const uint4 *q = p + (size_t)r0 * rs;
+        int r = r0;
+        for (; r + 4 <= r1; r += 4, q += 4 * rs) {
+            uint4 a0 = q[0], a1 = q[rs], a2 = q[2 * rs], a3 = q[3 * rs];
+            acc = add4(acc, add4(add4(a0, a1), add4(a2, a3)));
+        }
+        for (; r < r1; r++, q += rs) acc = add4(acc, q[0]);
+    }
     tot[band][lane] = acc;
     __syncthreads();
-    uint32_t run = 0;
-    for (int k = 0; k < band; k++) run += tot[k][lane];
-    if (ok)
-        for (int r = r0; r < r1; r++) {
-            run += p[(size_t)r * pitch];
-            p[(size_t)r * pitch] = run;
+    uint4 run = make_uint4(0, 0, 0, 0);
+    for (int k = 0; k < band; k++) run = add4(run, tot[k][lane]);
+    if (ok) {
+        uint4 *q = p + (size_t)r0 * rs;
+        int r = r0;
+        for (; r + 4 <= r1; r += 4, q += 4 * rs) {
+            uint4 a0 = q[0], a1 = q[rs], a2 = q[2 * rs], a3 = q[3 * rs];
+            a0 = add4(a0, run); a1 = add4(a1, a0); a2 = add4(a2, a1); a3 = add4(a3, a2);
+            q[0] = a0; q[rs] = a1; q[2 * rs] = a2; q[3 * rs] = a3;
+            run = a3;
         }
+        for (; r < r1; r++, q += rs) { run = add4(run, q[0]); q[0] = run; }
+    }
 }
 
 // Tilted integral (cv::integral's third output; only for cascades with tilted features).  tilted(X,Y) = sum of the

@@ -474,7 +474,8 @@ class Context:
 
     def gray(self):
         w, h = C.c_int(0), C.c_int(0)
-        buf = np.empty(16384 * 16384 // 64, np.uint8)
+        _lib.nv_debug_get_gray(self.handle, None, 0, C.byref(w), C.byref(h))       # size query (reports "too small")
+        buf = np.empty(max(1, w.value * h.value), np.uint8)
         _check(_lib.nv_debug_get_gray(self.handle, _p(buf), buf.size, C.byref(w), C.byref(h)), "nv_debug_get_gray")
         return buf[:w.value * h.value].reshape(h.value, w.value).copy()
 

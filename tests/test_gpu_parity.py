@@ -316,6 +316,27 @@ def test_cfg3_full_size_1080p(ctx, face):
     assert len(ctx.levels()) == 40
 
 
+def test_beyond_1080p_4k_frame(face):
+    """Maximum sizes: a 3840x2160 frame at full processing width (the packed candidate key keeps 13 bits per coordinate),
+    BGR and NV12, with every level's integrals and depth maps against the oracle."""
+    ncasc, ocasc = face
+    c = nv.Context(0, 3840, 2160, debug=True)
+    try:
+        fr = synth.frame(3840, 2160, 5, 21)
+        exp, eq = O.face_process(fr, ocasc, 3840, 1.2, 3, (40, 40))
+        got = c.face_detect(ncasc, fr, 3840, 1.2, 3, (40, 40))
+        assert rects_equal(got, exp) and len(got) >= 4
+        assert (c.gray() == eq).all()
+        nwin, _ = check_levels(c, eq, ocasc, 1.2, (40, 40))
+        assert nwin > 5_000_000
+        buf = synth.to_yuv420(fr, "NV12")
+        exp, eq = O.face_process(O.yuv420_to_bgr(*O.yuv420_planes(buf, 3840, 2160, "NV12"), fmt="NV12"), ocasc, 1920, 1.2, 3, None)
+        got = c.face_detect_yuv(ncasc, synth.yuv420_planes(buf, 3840, 2160, "NV12"), "NV12", 1920, 1.2, 3, None)
+        assert rects_equal(got, exp) and (c.gray() == eq).all()
+    finally:
+        c.close()
+
+
 def test_full_size_properties_without_the_oracle(face):
     """Size-independent properties at BASELINE's full sizes, where a second oracle run would only repeat
     test_cfg3_full_size_1080p: (1) a frame padded to a wider stride gives the same rectangles; (2) the device-resident
