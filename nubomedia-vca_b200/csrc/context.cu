@@ -571,10 +571,6 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
         if (tp.cp % 8 == 0) tp.cp += 4;
         tp.rt = (NV_CTY - 1) * ys + m.win_h + 1;
         tp.kskew = (ys * tp.cp) & 31;
-        {   // NUBOVCA_LIST_BIAS: experiments only (a large value keeps every stage in class mode)
-            const char *lb = getenv("NUBOVCA_LIST_BIAS");
-            tp.list_bias = lb ? atoi(lb) : 1;
-        }
         tp.ps = align_up(tp.rt * tp.cp, 32);
         tp.level_begin = c == 0 ? 0 : P.nlv2;
         tp.level_end = c == 0 ? P.nlv2 : P.nlevels;

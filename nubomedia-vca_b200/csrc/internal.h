@@ -11,7 +11,6 @@
 
 #include "nubovca.h"
 
-#define NV_LIST_CAP 1024         // most alive windows of a tile a list-mode stage of k_cascade_classes takes
 #define NV_COLBLK 128            // physical integral columns per block of the column scan
 #define NV_MAX_LEVELS 64          // level index is packed in 6 bits of a window id
 #define NV_MAX_STAGES 64
@@ -190,7 +189,6 @@ struct TileParams {
     int level_begin, level_end;
     int cp, rt, ps;                // tile plane geometry: columns, rows, plane stride (words)
     int kskew;                     // bank class of window (lx, ly) = (lx + kskew * ly) & 31
-    int list_bias;                 // a stage runs in list mode when ceil(alive / 32) + list_bias < fullest class (k_cascade_classes)
     const CUtensorMap *maps;       // one per level, in global memory (written by the host before launch)
     const PlanDev *plan;
     const uint32_t *bits_alive;

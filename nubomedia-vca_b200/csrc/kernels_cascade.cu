@@ -544,6 +544,11 @@ __device__ __forceinline__ int uniformize(int v, int bits)
 // predicated DADD; (c) two-rect classifiers run before three-rect ones, each in a branch-free loop.  The general
 // variant keeps the reference's float operations and XML order.
 // ================================================================================================
+#ifndef NV_CLS_UNROLL
+#define NV_CLS_UNROLL 2            // weak classifiers in flight per lane in the bulk kernel's inner loops
+#endif
+constexpr int CLS_UNROLL = NV_CLS_UNROLL;
+
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
     uint32_t v;
@@ -579,6 +584,7 @@ __device__ __forceinline__ void class_stage(const TileParams &P, int si, const u
         const int k6 = P.stage_mid6[si], km = P.stage_mid[si];
 #pragma unroll
         for (int i = 0; i < NW; i++) tmp[i] = P.stage_base[si];
+#pragma unroll CLS_UNROLL
         for (int k = k0; k < k6; k++) {                         // two rects sharing two corners: six loads (fill_bulk_stumps)
             const BulkStump &S = P.s[k];
             const double d = __hiloint2double((int)S.d_hi, (int)S.d_lo);
@@ -591,6 +597,7 @@ __device__ __forceinline__ void class_stage(const TileParams &P, int si, const u
                 add_if_lt(tmp[i], __fmul_rn(__int2float_rn((int)S.w1 * r1 + nr0), vnf[i]), sthr, d);
             }
         }
+#pragma unroll CLS_UNROLL
         for (int k = k6; k < km; k++) {                         // two rects, eight loads
             const BulkStump &S = P.s[k];
             const double d = __hiloint2double((int)S.d_hi, (int)S.d_lo);
@@ -601,6 +608,7 @@ __device__ __forceinline__ void class_stage(const TileParams &P, int si, const u
                 add_if_lt(tmp[i], __fmul_rn(__int2float_rn(r), vnf[i]), sthr, d);
             }
         }
+#pragma unroll CLS_UNROLL
         for (int k = km; k < k1; k++) {                         // three rects
             const BulkStump &S = P.s[k];
             const double d = __hiloint2double((int)S.d_hi, (int)S.d_lo);
@@ -639,7 +647,6 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ uint32_t s_mask[3][2][32];                        // rotating alive masks: [buffer][member / 32][class]
     __shared__ uint32_t s_words[NV_CTY][2];
-    __shared__ uint16_t s_list[NV_LIST_CAP];                     // list mode: (class << 6 | member) of the alive windows
     const PlanDev *__restrict__ plan = P.plan;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = uniformize(tid >> 5, 3);
@@ -682,95 +689,48 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
     const uint32_t tile_sa = smem_u32(tile);
     const float *__restrict__ vnf_tile = P.vnf + L.wofs + (size_t)iy0 * L.nx + ix0;
     const int rowb = YS * CP * 4;                                // bytes from one window row to the next
-    const uint32_t lt_mask = (1u << lane) - 1u;
     int cur = 0;
     for (int st = P.stage_begin; st < P.stage_end; st++) {
         const int si = st - P.stage_begin;
         uint32_t mlo = s_mask[cur][0][lane], mhi = s_mask[cur][1][lane];
-        const int cnt = __popc(mlo) + __popc(mhi);
-        int maxc = uniformize(__reduce_max_sync(0xffffffffu, cnt), 7);
+        int maxc = uniformize(__reduce_max_sync(0xffffffffu, __popc(mlo) + __popc(mhi)), 7);
         if (maxc == 0) return;                                   // block-uniform: every warp reads the same masks
         int nxt = cur == 2 ? 0 : cur + 1, zer = nxt == 2 ? 0 : nxt + 1;
         if (warp == 0) { s_mask[zer][0][lane] = 0u; s_mask[zer][1][lane] = 0u; }
         unsigned long long rem = ((unsigned long long)mhi << 32) | mlo, pass_bits = 0ull;
         for (int i = 0; i < warp; i++) rem &= rem - 1ull;        // warp w takes the set bits of rank w, w + 8, ...
-        // Two schedules for a stage.  CLASS mode: lane c walks the alive members of its own bank class, a round per
-        // rank: maxc rounds of 32 lanes, conflict-free, but a round is as full as the classes are even.  LIST mode
-        // (sparse stages): the alive windows are written to a list ordered by (rank, class) and handed out 32 (or 64)
-        // at a time, ceil(T / 32) rounds; consecutive list entries are different classes except where a batch
-        // straddles two ranks, so conflicts stay rare.  On config 3 stages 4..9 run at 21-56 % lane use in class
-        // mode and at 40-92 % in list mode (simulation on the oracle's depth maps).
-        const int T = __reduce_add_sync(0xffffffffu, cnt);
-        const bool list_mode = uniformize((T <= NV_LIST_CAP && ((T + 31) >> 5) + P.list_bias < maxc) ? 1 : 0, 1) != 0;
-        int n2, n1;                                              // this warp's two-window rounds, then 0 / 1 single round
-        if (list_mode) {
-            for (int r = warp; r < maxc; r += 8) {               // positions of the rank-r members of every class
-                const bool has = rem != 0ull;
-                const uint32_t bal = __ballot_sync(0xffffffffu, has);
-                const int below = __reduce_add_sync(0xffffffffu, min(cnt, r));
-                if (has) s_list[below + __popc(bal & lt_mask)] = (uint16_t)((__ffsll((long long)rem) - 1) | (lane << 6));
-#pragma unroll
-                for (int q = 0; q < 8; q++) rem &= rem - 1ull;
-            }
-            __syncthreads();
-            const int b0 = warp * 64;
-            n2 = T > b0 + 32 ? (T - b0 - 32 + 511) >> 9 : 0;
-            n1 = b0 + (n2 << 9) < T ? 1 : 0;
-        } else {
-            n2 = maxc > warp + 8 ? (maxc - warp - 8 + 15) >> 4 : 0;
-            n1 = warp + (n2 << 4) < maxc ? 1 : 0;
-        }
-        n2 = uniformize(n2, 3); n1 = uniformize(n1, 1);
-        for (int it = 0; it < n2; it++) {                        // two windows per lane and round
-            int bit[2], cls[2]; bool active[2], pass[2]; uint32_t wa[2]; float vnf[2]; int ly[2], lx[2];
+        int j = warp;
+        for (; j + 8 < maxc; j += 16) {                          // two windows per lane and round
+            int bit[2]; bool active[2], pass[2]; uint32_t wa[2]; float vnf[2]; int ly[2], lx[2];
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-                if (list_mode) {
-                    int idx = warp * 64 + (it << 9) + 32 * i + lane;
-                    active[i] = idx < T;
-                    uint32_t e = active[i] ? (uint32_t)s_list[idx] : 0u;
-                    bit[i] = e & 63; cls[i] = e >> 6;
-                } else {
-                    active[i] = rem != 0ull;
-                    bit[i] = active[i] ? __ffsll((long long)rem) - 1 : 0; cls[i] = lane;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) rem &= rem - 1ull;
-                }
-                ly[i] = bit[i] >> 1; lx[i] = ((cls[i] - K * ly[i]) & 31) + ((bit[i] & 1) << 5);
+                active[i] = rem != 0ull;
+                bit[i] = active[i] ? __ffsll((long long)rem) - 1 : 0;
+                ly[i] = bit[i] >> 1; lx[i] = ((lane - K * ly[i]) & 31) + ((bit[i] & 1) << 5);
                 wa[i] = tile_sa + (uint32_t)(ly[i] * rowb + lx[i] * 4);
                 vnf[i] = active[i] ? __ldg(vnf_tile + ly[i] * L.nx + lx[i]) : 0.f;     // per-window factor, L2-resident
+#pragma unroll
+                for (int q = 0; q < 8; q++) rem &= rem - 1ull;
             }
             class_stage<FAST, 2>(P, si, wa, vnf, pass);
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-                if (active[i] && pass[i]) {
-                    if (list_mode) atomicOr(&s_mask[nxt][bit[i] >> 5][cls[i]], 1u << (bit[i] & 31));
-                    else pass_bits |= 1ull << bit[i];
-                }
+                if (active[i] && pass[i]) pass_bits |= 1ull << bit[i];
                 if (P.depth && active[i] && !pass[i]) P.depth[L.wofs + (iy0 + ly[i]) * L.nx + ix0 + lx[i]] = (int16_t)(-st);
             }
         }
-        if (n1) {                                                // at most one single-window round
-            bool active; int bit, cls;
-            if (list_mode) {
-                int idx = warp * 64 + (n2 << 9) + lane;
-                active = idx < T;
-                uint32_t e = active ? (uint32_t)s_list[idx] : 0u;
-                bit = e & 63; cls = e >> 6;
-            } else {
-                active = rem != 0ull;
-                bit = active ? __ffsll((long long)rem) - 1 : 0; cls = lane;
-            }
-            int ly = bit >> 1, lx = ((cls - K * ly) & 31) + ((bit & 1) << 5);
+        for (; j < maxc; j += 8) {                               // at most one single-window round
+            bool active = rem != 0ull;
+            int bit = active ? __ffsll((long long)rem) - 1 : 0;
+            int ly = bit >> 1, lx = ((lane - K * ly) & 31) + ((bit & 1) << 5);
             uint32_t wa[1] = {tile_sa + (uint32_t)(ly * rowb + lx * 4)};
             float vnf[1] = {active ? __ldg(vnf_tile + ly * L.nx + lx) : 0.f};
             bool pass[1];
             class_stage<FAST, 1>(P, si, wa, vnf, pass);
-            if (active && pass[0]) {
-                if (list_mode) atomicOr(&s_mask[nxt][bit >> 5][cls], 1u << (bit & 31));
-                else pass_bits |= 1ull << bit;
-            }
+            if (active && pass[0]) pass_bits |= 1ull << bit;
             if (P.depth && active && !pass[0]) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = (int16_t)(-st);
+#pragma unroll
+            for (int q = 0; q < 8; q++) rem &= rem - 1ull;
         }
         if ((uint32_t)pass_bits) atomicOr(&s_mask[nxt][0][lane], (uint32_t)pass_bits);
         if ((uint32_t)(pass_bits >> 32)) atomicOr(&s_mask[nxt][1][lane], (uint32_t)(pass_bits >> 32));

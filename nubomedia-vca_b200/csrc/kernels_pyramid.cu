@@ -56,20 +56,18 @@ k_pyr_rowscan(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ gray
         uint32_t rs = 0, rq = 0;
 #pragma unroll
         for (int k = 0; k < RS_PX; k++) {
-            int x = cb + k - 1;
-            uint32_t v = 0;
-            if (x >= 0 && x < lw) {
-                int2 tx = __ldg(xt + x);
-                uint32_t h0, h1;
-                if (tx.y < 0) { h0 = (uint32_t)s_lut[g0[tx.x]] << 8; h1 = (uint32_t)s_lut[g1[tx.x]] << 8; }
-                else {
-                    uint32_t c1 = (uint32_t)tx.y, c0w = 256u - c1;
-                    h0 = s_lut[g0[tx.x]] * c0w + s_lut[g0[tx.x + 1]] * c1;
-                    h1 = s_lut[g1[tx.x]] * c0w + s_lut[g1[tx.x + 1]] * c1;
-                }
-                v = (h0 * r0 + h1 * r1 + 32768u) >> 16;
-                if (pyr_debug) pyr_debug[L.pofs + (size_t)y * lw + x] = (uint8_t)v;
-            }
+            const int x = cb + k - 1;
+            const bool valid = x >= 0 && x < lw;
+            // unconditional, clamped loads: the eight table reads, then the 32 taps, then the 32 LUT lookups of a lane
+            // are each in flight together
+            const int2 tx = __ldg(xt + min(max(x, 0), lw - 1));
+            const int o1 = tx.y < 0 ? 0 : 1;                         // replicated edge sample: weight 256 on tap 0
+            const uint32_t c1 = tx.y < 0 ? 0u : (uint32_t)tx.y, c0w = 256u - c1;
+            const uint32_t h0 = s_lut[g0[tx.x]] * c0w + s_lut[g0[tx.x + o1]] * c1;
+            const uint32_t h1 = s_lut[g1[tx.x]] * c0w + s_lut[g1[tx.x + o1]] * c1;
+            uint32_t v = (h0 * r0 + h1 * r1 + 32768u) >> 16;
+            if (valid && pyr_debug) pyr_debug[L.pofs + (size_t)y * lw + x] = (uint8_t)v;
+            v = valid ? v : 0u;
             rs += v; rq += v * v;
             s[k] = rs; q[k] = rq;
         }

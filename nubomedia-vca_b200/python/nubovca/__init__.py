@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-LIB_PATH = os.path.join(_PKG, "lib", "libnubovca.so")
+LIB_PATH = os.environ.get("NUBOVCA_LIB") or os.path.join(_PKG, "lib", "libnubovca.so")   # override: kernel A/B experiments
 CASCADE_DIR = os.path.join(_PKG, "cascades")
 
 NV_OK = 0
