@@ -499,7 +499,7 @@ void track_faces(std::vector<TrackedFace> &faces, int &faces_id, std::vector<Tra
 // ------------------------------------------------------------------------------------------------
 // nubofacedetector (FACE:757-853 + 179-249)
 // ------------------------------------------------------------------------------------------------
-int face_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double now_ms)
+int face_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double now_ms, const nv_yuv_frame *yuv = nullptr)
 {
     long w2p = e->get("width-to-process");
     if (w2p <= 0) { nv_set_error("width-to-process=0 divides by zero in the reference (FACE:304)"); return NV_ERR_ARG; }
@@ -520,7 +520,9 @@ int face_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double n
             p.min_neighbors = 3; p.min_w = -1; p.min_h = -1;                          // FACE:809-811
             std::vector<nv_rect> cur(4096);
             int n = 0;
-            rc = e->c_face ? nv_face_detect(e->ctx, e->c_face, frame, W, H, stride, &p, cur.data(), (int)cur.size(), &n) : NV_OK;
+            if (!e->c_face) rc = NV_OK;
+            else if (yuv) rc = nv_face_detect_yuv(e->ctx, e->c_face, yuv, &p, cur.data(), (int)cur.size(), &n);
+            else rc = nv_face_detect(e->ctx, e->c_face, frame, W, H, stride, &p, cur.data(), (int)cur.size(), &n);
             cur.resize(rc == NV_OK ? n : 0);
             if (!cur.empty()) {
                 std::vector<TrackedFace> cf;
@@ -532,7 +534,7 @@ int face_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double n
             else { e->frames_with_no_detection = 0; e->faces_tracked.clear(); }
         }
         gate_end(e);
-        if (e->get("view-faces") > 0) {                  // FACE:832-849 -> Faces::draw -> BASEFACE:70-82, colors[1]
+        if (e->get("view-faces") > 0 && frame) {         // FACE:832-849 -> Faces::draw -> BASEFACE:70-82, colors[1]; BGR frames only
             const int sc = W / (int)w2p;
             for (auto &f : e->faces_tracked)
                 draw_rectangle3(frame, W, H, stride, 3, f.r.x * sc, f.r.y * sc, (f.r.x + f.r.width - 1) * sc,
@@ -1102,6 +1104,23 @@ extern "C" int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int 
     case K_TRACKER: return tracker_frame(e, frame, width, height, stride_bytes, pts_ns, now_ms);
     }
     return NV_ERR_ARG;
+}
+
+// The face element fed with 4:2:0 planes (a shell whose sink caps add I420 / YV12 / NV12 / NV21): same gating, tracking,
+// events and signals; view-faces is ignored — the reference defines its overlay on BGR pixels only.
+extern "C" int nv_element_transform_frame_yuv(nv_element *e, const nv_yuv_frame *f, uint64_t pts_ns, double now_ms)
+{
+    (void)pts_ns;
+    if (!e || !f || f->width <= 0 || f->height <= 0) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    if (e->kind != K_FACE) { nv_set_error("4:2:0 frames are only taken by nubofacedetector"); return NV_ERR_UNSUPPORTED; }
+    if (!e->ctx || f->width > e->ctx->max_w || f->height > e->ctx->max_h) {
+        nv_ctx_destroy(e->ctx); e->ctx = nullptr;
+        int rc = nv_ctx_create(e->gpu, std::max(f->width, 1920), std::max(f->height, 1080), &e->ctx);
+        if (rc != NV_OK) return rc;
+    }
+    NV_CUDA(cudaSetDevice(e->ctx->gpu));
+    e->msg.clear(); e->signal.clear(); e->emitted = false; e->pushed = false;
+    return face_frame(e, nullptr, f->width, f->height, 0, now_ms, f);
 }
 
 extern "C" int nv_element_get_message(nv_element *e, nv_meta_rect *out, int cap, int *n, int *pushed)

@@ -98,6 +98,7 @@ _SIGS = {
     "nv_element_push_faces_event": (_i, [_vp, _vp, _i]),
     "nv_element_push_motion_event": (_i, [_vp]),
     "nv_element_transform_frame_ip": (_i, [_vp, _vp, _i, _i, _i, C.c_uint64, C.c_double]),
+    "nv_element_transform_frame_yuv": (_i, [_vp, C.POINTER(YuvFrame), C.c_uint64, C.c_double]),
     "nv_element_get_message": (_i, [_vp, _vp, _i, _ip, _ip]),
     "nv_element_get_signal": (_i, [_vp, C.c_char_p, _i, _ip]),
     "nv_debug_track_faces": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _ip, _ip]),
@@ -274,6 +275,15 @@ class Element:
         frame = _u8(frame); h, w = frame.shape[:2]
         _check(_lib.nv_element_transform_frame_ip(self.handle, _p(frame), w, h, frame.strides[0], pts_ns, now_ms),
                "nv_element_transform_frame_ip")
+        return self._outputs()
+
+    def process_yuv(self, planes, fmt="I420", pts_ns: int = 0, now_ms: float = -1.0):
+        """One 4:2:0 buffer (nubofacedetector only) through nv_element_transform_frame_yuv; same outputs as process()."""
+        f = Context._yuv_frame(planes, fmt)
+        _check(_lib.nv_element_transform_frame_yuv(self.handle, C.byref(f), pts_ns, now_ms), "nv_element_transform_frame_yuv")
+        return self._outputs()
+
+    def _outputs(self):
         buf = (MetaRect * 4096)(); n = C.c_int(0); pushed = C.c_int(0)
         _check(_lib.nv_element_get_message(self.handle, buf, 4096, C.byref(n), C.byref(pushed)), "nv_element_get_message")
         msg = [(buf[i].name.decode(), buf[i].type.decode(), buf[i].x, buf[i].y, buf[i].width, buf[i].height)

@@ -174,3 +174,32 @@ def test_gpu_yuv_argument_errors(ctx, face):
     big = np.zeros((2162 * 3 // 2, 3842), np.uint8)
     with pytest.raises(nv.NuboError):                      # larger than the context
         ctx.face_detect_yuv(ncasc, synth.yuv420_planes(big, 3842, 2162, "NV12"), "NV12")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["I420", "NV12"])
+def test_gpu_face_element_on_yuv_frames(cascade_dir, fmt):
+    """nv_element_transform_frame_yuv: the nubofacedetector mirror (gating, tracking, message) on 4:2:0 buffers equals the
+    oracle-backed restatement fed with cvtColor's BGR; the other elements refuse 4:2:0 frames."""
+    from element_ref import FaceRef
+    w, h = 640, 480
+    base = synth.frame(w, h, 4, 1)
+    rng = np.random.default_rng(5)
+    frames = [np.clip(base.astype(np.int16) + rng.integers(-3, 4, base.shape, dtype=np.int16), 0, 255).astype(np.uint8)
+              for _ in range(5)] + [np.full((h, w, 3), 90, np.uint8)] * 3
+    e = nv.Element("nubofacedetector", 0, cascade_dir)
+    ref = FaceRef(O.Cascade(os.path.join(cascade_dir, FACE_XML)))
+    e.set("process-x-every-4-frames", 2); ref.p["x4"] = 2
+    seen = 0
+    for i, f in enumerate(frames):
+        buf = synth.to_yuv420(f, fmt)
+        msg, pushed, sig = e.process_yuv(synth.yuv420_planes(buf, w, h, fmt), fmt, pts_ns=i * 33_000_000)
+        assert pushed and sig is None
+        assert msg == ref.process(ora_bgr(buf, w, h, fmt)), i
+        seen += len(msg)
+    assert seen > 0
+    e.close()
+    t = nv.Element("nubotracker", 0, cascade_dir)
+    with pytest.raises(nv.NuboError):
+        t.process_yuv(synth.yuv420_planes(synth.to_yuv420(base, fmt), w, h, fmt), fmt)
+    t.close()
