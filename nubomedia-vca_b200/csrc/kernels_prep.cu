@@ -60,6 +60,9 @@ __device__ __forceinline__ int lin_tap(const uint8_t *__restrict__ r0, const uin
 
 // K1+K2 fused for the face element: resize the BGR(A) frame (3 channels computed), convert to gray,
 // accumulate the histogram equalizeHist needs.  One thread per output pixel.
+// Blocks walk the 32x8-pixel output tiles with a grid stride (the launchers size the grid to a few blocks per SM): the
+// shared histogram is flushed once per block, so the global histogram sees a few hundred atomics per bin and frame
+// instead of one per bin and tile (8100 tiles on a 1080p frame).
 __global__ void __launch_bounds__(256)
 k_face_prep(const uint8_t *__restrict__ src, int sw, int sh, int sstride, int cn, uint8_t *__restrict__ gray, int dw,
             int dh, const int *__restrict__ rtab, int *__restrict__ hist)
@@ -68,9 +71,11 @@ k_face_prep(const uint8_t *__restrict__ src, int sw, int sh, int sstride, int cn
     int tid = threadIdx.y * 32 + threadIdx.x;
     sh_hist[tid] = 0;
     __syncthreads();
-    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x < dw && y < dh) {
-        int mode = rtab[0], g;
+    const int tx_n = (dw + 31) / 32, ntiles = tx_n * ((dh + 7) / 8), mode = rtab[0];
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int x = (t % tx_n) * 32 + threadIdx.x, y = (t / tx_n) * 8 + threadIdx.y;
+        if (x >= dw || y >= dh) continue;
+        int g;
         if (mode == RT_COPY) {
             const uint8_t *p = src + (size_t)y * sstride + x * cn;
             g = gray_of(p[0], p[1], p[2]);
@@ -92,6 +97,61 @@ k_face_prep(const uint8_t *__restrict__ src, int sw, int sh, int sstride, int cn
         }
         gray[(size_t)y * dw + x] = (uint8_t)g;
         atomicAdd(&sh_hist[g], 1);
+    }
+    __syncthreads();
+    if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
+}
+
+// Vectorised forms of the two streaming modes (same size, exact 2x): a lane owns FOUR consecutive output pixels, reads
+// its source bytes as aligned 32-bit words (12 bytes of BGR per row and output quad in copy mode, 24 in box mode) and
+// writes one 32-bit word of gray; a warp's loads are one contiguous 384- / 768-byte run per source row.  Used when
+// the output width is a multiple of 4 and pointer and stride are 4-byte aligned (GStreamer rows are), else the
+// byte-per-lane kernel above runs.
+__device__ __forceinline__ int byte_of(uint32_t w, int i) { return (int)((w >> (8 * i)) & 255u); }
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_face_prep_bgr4(const uint8_t *__restrict__ src, int sstride, uint8_t *__restrict__ gray, int dw, int dh,
+                 int *__restrict__ hist)
+{
+    __shared__ int sh_hist[256];
+    int tid = threadIdx.y * 32 + threadIdx.x;
+    sh_hist[tid] = 0;
+    __syncthreads();
+    const int qw = dw >> 2, tx_n = (qw + 31) / 32, ntiles = tx_n * ((dh + 7) / 8);
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int xq = (t % tx_n) * 32 + threadIdx.x, y = (t / tx_n) * 8 + threadIdx.y;
+        if (xq >= qw || y >= dh) continue;
+        int g[4];
+        if (MODE == RT_COPY) {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(src + (size_t)y * sstride) + 3 * xq;
+            uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+            g[0] = gray_of(byte_of(w0, 0), byte_of(w0, 1), byte_of(w0, 2));
+            g[1] = gray_of(byte_of(w0, 3), byte_of(w1, 0), byte_of(w1, 1));
+            g[2] = gray_of(byte_of(w1, 2), byte_of(w1, 3), byte_of(w2, 0));
+            g[3] = gray_of(byte_of(w2, 1), byte_of(w2, 2), byte_of(w2, 3));
+        } else {
+            const uint32_t *p0 = reinterpret_cast<const uint32_t *>(src + (size_t)(2 * y) * sstride) + 6 * xq;
+            const uint32_t *p1 = reinterpret_cast<const uint32_t *>(src + (size_t)(2 * y + 1) * sstride) + 6 * xq;
+            uint32_t a[6], b[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) { a[i] = __ldg(p0 + i); b[i] = __ldg(p1 + i); }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {                     // output pixel k: source bytes 6k .. 6k+5 of both rows
+                int c3[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const int i0 = 6 * k + c, i1 = i0 + 3;
+                    c3[c] = (byte_of(a[i0 >> 2], i0 & 3) + byte_of(a[i1 >> 2], i1 & 3) + byte_of(b[i0 >> 2], i0 & 3) +
+                             byte_of(b[i1 >> 2], i1 & 3) + 2) >> 2;
+                }
+                g[k] = gray_of(c3[0], c3[1], c3[2]);
+            }
+        }
+        *reinterpret_cast<uint32_t *>(gray + (size_t)y * dw + 4 * xq) =
+            (uint32_t)g[0] | ((uint32_t)g[1] << 8) | ((uint32_t)g[2] << 16) | ((uint32_t)g[3] << 24);
+#pragma unroll
+        for (int k = 0; k < 4; k++) atomicAdd(&sh_hist[g[k]], 1);
     }
     __syncthreads();
     if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
@@ -141,16 +201,18 @@ k_face_prep_yuv(SrcPlanes s, int sw, int sh, uint8_t *__restrict__ gray, int dw,
     int tid = threadIdx.y * 32 + threadIdx.x;
     sh_hist[tid] = 0;
     __syncthreads();
-    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x < dw && y < dh) {
-        int mode = rtab[0], g, c3[3];
+    const int tx_n = (dw + 31) / 32, ntiles = tx_n * ((dh + 7) / 8), mode = rtab[0];
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int x = (t % tx_n) * 32 + threadIdx.x, y = (t / tx_n) * 8 + threadIdx.y;
+        if (x >= dw || y >= dh) continue;
+        int g, c3[3];
         if (mode == RT_COPY) {
             yuv_pixel(s, yuv_chroma<FMT>(s, x, y), x, y, c3);
         } else if (mode == RT_BOX2) {                       // the four source pixels share one chroma sample
-            YuvTerms t = yuv_chroma<FMT>(s, 2 * x, 2 * y);
+            YuvTerms t4 = yuv_chroma<FMT>(s, 2 * x, 2 * y);
             int a[3], b[3], c[3], d[3];
-            yuv_pixel(s, t, 2 * x, 2 * y, a);     yuv_pixel(s, t, 2 * x + 1, 2 * y, b);
-            yuv_pixel(s, t, 2 * x, 2 * y + 1, c); yuv_pixel(s, t, 2 * x + 1, 2 * y + 1, d);
+            yuv_pixel(s, t4, 2 * x, 2 * y, a);     yuv_pixel(s, t4, 2 * x + 1, 2 * y, b);
+            yuv_pixel(s, t4, 2 * x, 2 * y + 1, c); yuv_pixel(s, t4, 2 * x + 1, 2 * y + 1, d);
 #pragma unroll
             for (int k = 0; k < 3; k++) c3[k] = (a[k] + b[k] + c[k] + d[k] + 2) >> 2;
         } else {
@@ -169,6 +231,92 @@ k_face_prep_yuv(SrcPlanes s, int sw, int sh, uint8_t *__restrict__ gray, int dw,
         g = gray_of(c3[0], c3[1], c3[2]);
         gray[(size_t)y * dw + x] = (uint8_t)g;
         atomicAdd(&sh_hist[g], 1);
+    }
+    __syncthreads();
+    if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
+}
+
+// Vectorised 4:2:0 forms: a lane owns four consecutive output pixels.  Copy mode: 4 luma bytes (one word) and their
+// two chroma samples; box mode: 2 x 8 luma bytes and four chroma samples.  Same alignment rule as k_face_prep_bgr4.
+__device__ __forceinline__ YuvTerms yuv_terms(int u, int v)
+{
+    u -= 128; v -= 128;
+    YuvTerms t;
+    t.b = (1 << 19) + 2116026 * u;
+    t.g = (1 << 19) - 852492 * v - 409993 * u;
+    t.r = (1 << 19) + 1673527 * v;
+    return t;
+}
+__device__ __forceinline__ void yuv_px(int yv, const YuvTerms &t, int c3[3])
+{
+    int yy = max(0, yv - 16) * 1220542;
+    c3[0] = sat_u8((yy + t.b) >> 20); c3[1] = sat_u8((yy + t.g) >> 20); c3[2] = sat_u8((yy + t.r) >> 20);
+}
+
+template <int FMT, int MODE>
+__global__ void __launch_bounds__(256)
+k_face_prep_yuv4(SrcPlanes s, uint8_t *__restrict__ gray, int dw, int dh, int *__restrict__ hist)
+{
+    __shared__ int sh_hist[256];
+    int tid = threadIdx.y * 32 + threadIdx.x;
+    sh_hist[tid] = 0;
+    __syncthreads();
+    const int qw = dw >> 2, tx_n = (qw + 31) / 32, ntiles = tx_n * ((dh + 7) / 8);
+    constexpr int NC = MODE == RT_COPY ? 2 : 4;              // chroma samples under a lane's source pixels
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int xq = (t % tx_n) * 32 + threadIdx.x, y = (t / tx_n) * 8 + threadIdx.y;
+        if (xq >= qw || y >= dh) continue;
+        const int sx = MODE == RT_COPY ? 4 * xq : 8 * xq, sy = MODE == RT_COPY ? y : 2 * y;     // first source pixel
+        int u[NC], v[NC];
+        if (FMT == 1) {
+            const uint8_t *pu = s.p1 + (size_t)(sy >> 1) * s.s1 + (sx >> 1), *pv = s.p2 + (size_t)(sy >> 1) * s.s2 + (sx >> 1);
+            if (MODE == RT_COPY) {
+                uint32_t wu = *reinterpret_cast<const uint16_t *>(pu), wv = *reinterpret_cast<const uint16_t *>(pv);
+#pragma unroll
+                for (int i = 0; i < NC; i++) { u[i] = byte_of(wu, i); v[i] = byte_of(wv, i); }
+            } else {
+                uint32_t wu = __ldg(reinterpret_cast<const uint32_t *>(pu)), wv = __ldg(reinterpret_cast<const uint32_t *>(pv));
+#pragma unroll
+                for (int i = 0; i < NC; i++) { u[i] = byte_of(wu, i); v[i] = byte_of(wv, i); }
+            }
+        } else {
+            const uint32_t *pc = reinterpret_cast<const uint32_t *>(s.p1 + (size_t)(sy >> 1) * s.s1 + sx);
+#pragma unroll
+            for (int i = 0; i < NC / 2; i++) {
+                uint32_t w = __ldg(pc + i);                  // two interleaved chroma pairs
+                u[2 * i] = byte_of(w, FMT == 2 ? 0 : 1); v[2 * i] = byte_of(w, FMT == 2 ? 1 : 0);
+                u[2 * i + 1] = byte_of(w, FMT == 2 ? 2 : 3); v[2 * i + 1] = byte_of(w, FMT == 2 ? 3 : 2);
+            }
+        }
+        int g[4];
+        if (MODE == RT_COPY) {
+            uint32_t wy = __ldg(reinterpret_cast<const uint32_t *>(s.p0 + (size_t)sy * s.s0 + sx));
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int c3[3];
+                yuv_px(byte_of(wy, k), yuv_terms(u[k >> 1], v[k >> 1]), c3);
+                g[k] = gray_of(c3[0], c3[1], c3[2]);
+            }
+        } else {
+            const uint32_t *r0 = reinterpret_cast<const uint32_t *>(s.p0 + (size_t)sy * s.s0 + sx);
+            const uint32_t *r1 = reinterpret_cast<const uint32_t *>(s.p0 + (size_t)(sy + 1) * s.s0 + sx);
+            uint32_t a[2] = {__ldg(r0), __ldg(r0 + 1)}, b[2] = {__ldg(r1), __ldg(r1 + 1)};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {                     // output pixel k: luma bytes 2k, 2k+1 of both rows, chroma k
+                const YuvTerms tk = yuv_terms(u[k], v[k]);
+                int p[4][3];
+                yuv_px(byte_of(a[k >> 1], (2 * k) & 3), tk, p[0]); yuv_px(byte_of(a[k >> 1], (2 * k + 1) & 3), tk, p[1]);
+                yuv_px(byte_of(b[k >> 1], (2 * k) & 3), tk, p[2]); yuv_px(byte_of(b[k >> 1], (2 * k + 1) & 3), tk, p[3]);
+                int c3[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) c3[c] = (p[0][c] + p[1][c] + p[2][c] + p[3][c] + 2) >> 2;
+                g[k] = gray_of(c3[0], c3[1], c3[2]);
+            }
+        }
+        *reinterpret_cast<uint32_t *>(gray + (size_t)y * dw + 4 * xq) =
+            (uint32_t)g[0] | ((uint32_t)g[1] << 8) | ((uint32_t)g[2] << 16) | ((uint32_t)g[3] << 24);
+#pragma unroll
+        for (int k = 0; k < 4; k++) atomicAdd(&sh_hist[g[k]], 1);
     }
     __syncthreads();
     if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
@@ -290,21 +438,53 @@ k_flip(const uint8_t *__restrict__ src, int w, int h, int sstride, uint8_t *__re
 // ------------------------------------------------------------------------------------------------
 static inline dim3 grid2d(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
 
+// persistent grids for the prep kernels: a few blocks per SM, every block flushes its histogram once
+static inline int prep_grid(int tiles)
+{
+    if (tiles <= 148 * 6) return tiles > 0 ? tiles : 1;
+    int per_block = (tiles + 148 * 6 - 1) / (148 * 6);          // every block the same number of tiles (+-1)
+    return (tiles + per_block - 1) / per_block;
+}
+static inline bool aligned4(const void *p, int stride) { return (((uintptr_t)p | (uintptr_t)(unsigned)stride) & 3u) == 0; }
+
 cudaError_t launch_face_prep(const uint8_t *src, int sw, int sh, int sstride, int cn, uint8_t *gray, int dw, int dh,
                              const int *rtab, int *hist, cudaStream_t st)
 {
-    k_face_prep<<<grid2d(dw, dh), dim3(32, 8), 0, st>>>(src, sw, sh, sstride, cn, gray, dw, dh, rtab, hist);
+    const int mode = (sw == dw && sh == dh) ? RT_COPY : (sw == 2 * dw && sh == 2 * dh) ? RT_BOX2 : RT_LINEAR;   // = rtab[0]
+    if (mode != RT_LINEAR && cn == 3 && (dw & 3) == 0 && aligned4(src, sstride) && aligned4(gray, 0)) {
+        int tiles = ((dw / 4 + 31) / 32) * ((dh + 7) / 8);
+        if (mode == RT_COPY) k_face_prep_bgr4<RT_COPY><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(src, sstride, gray, dw, dh, hist);
+        else k_face_prep_bgr4<RT_BOX2><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(src, sstride, gray, dw, dh, hist);
+        return cudaGetLastError();
+    }
+    int tiles = ((dw + 31) / 32) * ((dh + 7) / 8);
+    k_face_prep<<<prep_grid(tiles), dim3(32, 8), 0, st>>>(src, sw, sh, sstride, cn, gray, dw, dh, rtab, hist);
     return cudaGetLastError();
 }
+template <int FMT>
+static cudaError_t launch_prep_yuv_fmt(const SrcPlanes &s, int sw, int sh, uint8_t *gray, int dw, int dh, const int *rtab, int *hist,
+                                       cudaStream_t st)
+{
+    const int mode = (sw == dw && sh == dh) ? RT_COPY : (sw == 2 * dw && sh == 2 * dh) ? RT_BOX2 : RT_LINEAR;   // = rtab[0]
+    const bool al = aligned4(s.p0, s.s0) && aligned4(s.p1, s.s1) && (FMT != 1 || aligned4(s.p2, s.s2)) && aligned4(gray, 0);
+    if (mode != RT_LINEAR && (dw & 3) == 0 && al) {
+        int tiles = ((dw / 4 + 31) / 32) * ((dh + 7) / 8);
+        if (mode == RT_COPY) k_face_prep_yuv4<FMT, RT_COPY><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(s, gray, dw, dh, hist);
+        else k_face_prep_yuv4<FMT, RT_BOX2><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(s, gray, dw, dh, hist);
+        return cudaGetLastError();
+    }
+    int tiles = ((dw + 31) / 32) * ((dh + 7) / 8);
+    k_face_prep_yuv<FMT><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(s, sw, sh, gray, dw, dh, rtab, hist);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_face_prep_yuv(int fmt, const SrcPlanes &s, int sw, int sh, uint8_t *gray, int dw, int dh, const int *rtab,
                                  int *hist, cudaStream_t st)
 {
-    dim3 g = grid2d(dw, dh), b(32, 8);
-    if (fmt == NV_FMT_I420) k_face_prep_yuv<1><<<g, b, 0, st>>>(s, sw, sh, gray, dw, dh, rtab, hist);
-    else if (fmt == NV_FMT_NV12) k_face_prep_yuv<2><<<g, b, 0, st>>>(s, sw, sh, gray, dw, dh, rtab, hist);
-    else if (fmt == NV_FMT_NV21) k_face_prep_yuv<3><<<g, b, 0, st>>>(s, sw, sh, gray, dw, dh, rtab, hist);
-    else return cudaErrorInvalidValue;
-    return cudaGetLastError();
+    if (fmt == NV_FMT_I420) return launch_prep_yuv_fmt<1>(s, sw, sh, gray, dw, dh, rtab, hist, st);
+    if (fmt == NV_FMT_NV12) return launch_prep_yuv_fmt<2>(s, sw, sh, gray, dw, dh, rtab, hist, st);
+    if (fmt == NV_FMT_NV21) return launch_prep_yuv_fmt<3>(s, sw, sh, gray, dw, dh, rtab, hist, st);
+    return cudaErrorInvalidValue;
 }
 cudaError_t launch_yuv2bgr(int fmt, const SrcPlanes &s, int w, int h, uint8_t *dst, int dstride, cudaStream_t st)
 {

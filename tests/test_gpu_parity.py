@@ -302,6 +302,27 @@ def test_edge_cases(ctx, face):
         ctx.face_detect(ncasc, np.zeros((2000, 3000, 3), np.uint8), 160)
 
 
+@pytest.mark.parametrize("case", [(648, 480, 648, 0), (642, 480, 642, 0), (1288, 720, 644, 0), (1284, 720, 642, 0),
+                                  (648, 480, 648, 4), (648, 480, 648, 3), (1288, 720, 644, 8), (1288, 720, 644, 2),
+                                  (648, 480, 216, 0)])
+def test_prep_modes_and_alignment(ctx, face, case):
+    """k_face_prep: same-size and exact-2x frames go through the vectorised kernels when output width, pointer and row
+    stride are multiples of 4, else (and for every other ratio) through the byte-per-lane kernel; all against the oracle."""
+    import ctypes as C
+    ncasc, ocasc = face
+    W, H, w2p, pad = case
+    fr = synth.frame(W, H, 3, 30 + W + pad)
+    buf = np.random.default_rng(pad).integers(0, 256, (H, 3 * W + pad), dtype=np.uint8)
+    buf[:, :3 * W] = fr.reshape(H, -1)
+    n = C.c_int(0)
+    a = nv.Context._face_params(w2p, 1.2, 2, None)
+    assert nv._lib.nv_face_detect(ctx.handle, ncasc.handle, buf.ctypes.data_as(C.c_void_p), W, H, buf.strides[0], C.byref(a),
+                                  ctx._out, ctx._cap, C.byref(n)) == 0
+    exp, eq = O.face_process(fr, ocasc, w2p, 1.2, 2, None)
+    assert (ctx.gray() == eq).all()
+    assert rects_equal(nv._rects(ctx._out, n.value), exp)
+
+
 def test_cfg3_full_size_1080p(ctx, face):
     """BASELINE config 3 at full size: 1920x1080, processing width 1920, sf 1.1, min 24x24.
     Full oracle comparison (a few seconds of CPU) including every depth map."""

@@ -128,7 +128,7 @@ def test_gpu_face_detect_yuv_golden(ctx, face, idx):
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt", FMTS)
 @pytest.mark.parametrize("case", [(640, 480, 160), (640, 480, 320), (640, 480, 640), (1280, 720, 640), (1280, 720, 500),
-                                  (322, 242, 100)])
+                                  (322, 242, 100), (322, 242, 322), (644, 484, 322), (1920, 1080, 1920)])
 def test_gpu_face_detect_yuv_vs_oracle(ctx, face, fmt, case):
     """every resize mode (copy, 2x box, linear), random full-range chroma on top of a face frame, padded strides"""
     ncasc, ocasc = face
@@ -138,7 +138,9 @@ def test_gpu_face_detect_yuv_vs_oracle(ctx, face, fmt, case):
     buf[h:] = np.clip(buf[h:].astype(np.int16) + rng.integers(-90, 91, buf[h:].shape), 0, 255).astype(np.uint8)
     exp, eq = O.face_process(ora_bgr(buf, w, h, fmt), ocasc, w2p, 1.2, 2, None)
     planes = synth.yuv420_planes(buf, w, h, fmt)
-    for pl in (planes, strided(planes, 14, rng)):
+    # contiguous planes and 16-byte padded rows take the vectorised kernels when the output width is a multiple of 4,
+    # rows padded by 14 bytes (stride not a multiple of 4) and the other widths the byte-per-lane kernel
+    for pl in (planes, strided(planes, 14, rng), strided(planes, 16, rng)):
         got = ctx.face_detect_yuv(ncasc, pl, fmt, w2p, 1.2, 2, None)
         assert (ctx.gray() == eq).all()
         assert rects_equal(got, exp)
