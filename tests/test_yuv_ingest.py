@@ -205,3 +205,33 @@ def test_gpu_face_element_on_yuv_frames(cascade_dir, fmt):
     with pytest.raises(nv.NuboError):
         t.process_yuv(synth.yuv420_planes(synth.to_yuv420(base, fmt), w, h, fmt), fmt)
     t.close()
+
+
+@pytest.mark.gpu
+def test_gpu_yuv_planes_already_on_the_device(face):
+    """on_device = 1: the planes are device pointers (an NVDEC surface / GstCudaMemory), no host copy at all"""
+    import ctypes as C
+    torch = pytest.importorskip("torch")
+    ncasc, ocasc = face
+    w, h = 1280, 720
+    c = nv.Context(0, w, h)
+    try:
+        for fmt in ("NV12", "I420"):
+            buf = synth.to_yuv420(synth.frame(w, h, 3, 1000), fmt)
+            exp, _ = O.face_process(ora_bgr(buf, w, h, fmt), ocasc, 640, 1.25, 3, None)
+            d = torch.from_numpy(buf.copy()).cuda()
+            f = nv.YuvFrame()
+            f.format, f.width, f.height, f.on_device = nv._FMT[fmt], w, h, 1
+            f.plane[0], f.stride[0] = d.data_ptr(), w
+            f.plane[1] = d.data_ptr() + w * h
+            if fmt == "NV12":
+                f.stride[1] = w
+            else:
+                f.stride[1] = f.stride[2] = w // 2
+                f.plane[2] = d.data_ptr() + w * h + w * h // 4
+            p = nv.Context._face_params(640, 1.25, 3, None)
+            for _ in range(3):                                   # third call replays the graph
+                assert nv._lib.nv_face_submit_yuv(c.handle, ncasc.handle, C.byref(f), C.byref(p)) == 0
+                assert rects_equal(c.face_collect(), exp)
+    finally:
+        c.close()
