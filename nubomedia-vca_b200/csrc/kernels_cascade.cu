@@ -1075,6 +1075,8 @@ cudaError_t launch_alive_to_queue(const PlanDev *plan, int total_rows, const flo
 cudaError_t launch_cascade_classes(const TileParams &tp, int ystep, int ntiles, cudaStream_t st)
 {
     size_t smem = (size_t)ystep * tp.ps * sizeof(uint32_t);
+    if (const char *pad = getenv(ystep == 2 ? "NUBOVCA_YS2_SMEM" : "NUBOVCA_YS1_SMEM"))    // experiments: cap resident blocks
+        smem = std::max(smem, (size_t)atoi(pad));
     static std::mutex mu;
     static unsigned long long attr_set = 0ull;                   // per device: the attribute belongs to the device's function
     int dev = 0;

@@ -109,15 +109,21 @@ k_pyr_rowscan(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ gray
 }
 
 // Column pass, shared-memory tiled: a block owns NV_COLBLK = 128 physical columns of one array of one level (four per
-// lane, moved as 16-byte vectors); its 32 warps split the rows into 32 bands.  Pass 1 sums each band, the band totals
+// lane, moved as 16-byte vectors); its 16 warps split the rows into 16 bands.  Pass 1 sums each band, the band totals
 // are exchanged through shared memory and prefixed, pass 2 re-reads the band (L1/L2 hit) and writes the running
 // column sums.  Every global access is a 512-byte row segment.
 __device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-__global__ void __launch_bounds__(1024)
+// 16 bands = 512 threads x 40 registers, 8 KB of shared memory: small enough to share an SM with resident blocks of the
+// cascade kernel of another stream.  With 32 bands (1024 threads, a whole SM's worth of registers) the column scan had
+// to wait for an SM to drain: bench.py 2418 -> 2536 frames/s from this change alone (profiles/r1_v5_summary.md).
+#ifndef NV_COLBANDS
+#define NV_COLBANDS 16
+#endif
+__global__ void __launch_bounds__(32 * NV_COLBANDS)
 k_colscan(const PlanDev *__restrict__ plan, int total_colblk, uint32_t *__restrict__ sum, uint32_t *__restrict__ sq)
 {
-    __shared__ uint4 tot[32][33];
+    __shared__ uint4 tot[NV_COLBANDS][33];
     int lane = threadIdx.x & 31, band = threadIdx.x >> 5;
     int b = blockIdx.x;
     uint32_t *arr = sum;
@@ -129,7 +135,7 @@ k_colscan(const PlanDev *__restrict__ plan, int total_colblk, uint32_t *__restri
     bool ok = col < pitch;                              // pitch is a multiple of 4: a lane's four columns exist together
     uint4 *p = reinterpret_cast<uint4 *>(arr + L.iofs + col);
     const size_t rs = (size_t)(pitch >> 2);             // row stride in uint4
-    int R = (rows + 31) / 32, r0 = band * R, r1 = min(rows, r0 + R);
+    int R = (rows + NV_COLBANDS - 1) / NV_COLBANDS, r0 = band * R, r1 = min(rows, r0 + R);
     uint4 acc = make_uint4(0, 0, 0, 0);
     if (ok) {
         const uint4 *q = p + (size_t)r0 * rs;
@@ -227,6 +233,6 @@ cudaError_t launch_pyr_rowscan(const PlanDev *plan, int total_rowblk, const uint
 
 cudaError_t launch_colscan(const PlanDev *plan, int total_colblk, uint32_t *sum, uint32_t *sq, cudaStream_t st)
 {
-    k_colscan<<<2 * total_colblk, 1024, 0, st>>>(plan, total_colblk, sum, sq);
+    k_colscan<<<2 * total_colblk, 32 * NV_COLBANDS, 0, st>>>(plan, total_colblk, sum, sq);
     return cudaGetLastError();
 }
