@@ -1113,8 +1113,12 @@ cudaError_t launch_cascade_tail_fast(const PlanDev *plan, const DevCascade *meta
                                      const uint32_t *sum, const uint2 *tail, int *counters, uint32_t *cand, int cand_cap,
                                      int16_t *depth, int stage_begin, cudaStream_t st, int smem_bytes)
 {
-    k_cascade_tail_fast<<<148 * 8, 256, smem_bytes, st>>>(plan, meta, tstumps, tbase, sum, tail, counters, cand, cand_cap, depth,
-                                                          stage_begin);
+#ifndef NV_TAIL_THREADS
+#define NV_TAIL_THREADS 256
+#endif
+    // smem_bytes is sized for eight warps (one patch per warp)
+    k_cascade_tail_fast<<<148 * 8 * (256 / NV_TAIL_THREADS), NV_TAIL_THREADS, smem_bytes / (256 / NV_TAIL_THREADS), st>>>(
+        plan, meta, tstumps, tbase, sum, tail, counters, cand, cand_cap, depth, stage_begin);
     return cudaGetLastError();
 }
 

@@ -9,7 +9,9 @@
 // every component ends up labelled by its first member.
 #include "internal.h"
 
+#ifndef GROUP_SMEM_LABELS
 #define GROUP_SMEM_LABELS 8192
+#endif
 
 __device__ __forceinline__ bool similar_rects(const int4 &a, const int4 &b, double eps)
 {
@@ -59,7 +61,11 @@ k_adj(const int *__restrict__ counters, int cand_cap, const int4 *__restrict__ r
     }
 }
 
-// exclusive rank of a 0/1 flag across a 1024-thread block, with a running carry
+#ifndef NV_GROUP_THREADS
+#define NV_GROUP_THREADS 1024
+#endif
+#define NV_GROUP_WARPS (NV_GROUP_THREADS / 32)
+// exclusive rank of a 0/1 flag across the block, with a running carry
 __device__ __forceinline__ int block_flag_rank(bool flag, int &carry, int *s_warp)
 {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -67,7 +73,7 @@ __device__ __forceinline__ int block_flag_rank(bool flag, int &carry, int *s_war
     if (lane == 0) s_warp[warp] = __popc(m);
     __syncthreads();
     int before = 0, total = 0;
-    for (int k = 0; k < 32; k++) { int c = s_warp[k]; if (k < warp) before += c; total += c; }
+    for (int k = 0; k < NV_GROUP_WARPS; k++) { int c = s_warp[k]; if (k < warp) before += c; total += c; }
     int pos = carry + before + __popc(m & ((1u << lane) - 1u));
     carry += total;
     __syncthreads();
@@ -75,7 +81,7 @@ __device__ __forceinline__ int block_flag_rank(bool flag, int &carry, int *s_war
 }
 
 // grp scratch layout (ints): label[cap] | cls[cap] | acc[5*cap] (x,y,w,h,count) | keep[cap]
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(NV_GROUP_THREADS)
 k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects, const uint32_t *__restrict__ adj,
         int *__restrict__ grp, int min_neighbors, double eps, int img_w, int img_h, uint8_t *__restrict__ result,
         int result_cap)
@@ -94,7 +100,7 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
     if (min_neighbors <= 0) {
         // no grouping: canonical-order candidates, clipped; empty intersections are dropped (A.8)
         int carry = 0;
-        for (int i0 = 0; i0 < n; i0 += 1024) {
+        for (int i0 = 0; i0 < n; i0 += NV_GROUP_THREADS) {
             int i = i0 + tid;
             int4 r = make_int4(0, 0, 0, 0);
             bool k = false;
@@ -109,7 +115,7 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
         }
         nout = carry;
     } else {
-        for (int i = tid; i < n; i += 1024) label[i] = i;
+        for (int i = tid; i < n; i += NV_GROUP_THREADS) label[i] = i;
         __syncthreads();
         // min-label propagation until a fixed point: one warp per candidate row, lanes over the row's adjacency
         // words (the next row is fetched while the current one is reduced)
@@ -122,15 +128,15 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
             if (wpl <= 8 && warp < n)
 #pragma unroll
                 for (int q = 0; q < 8; q++) { int w = lane + 32 * q; nxt[q] = (q < wpl && w < nw) ? adj[(size_t)warp * nw + w] : 0u; }
-            for (int i = warp; i < n; i += 32) {
+            for (int i = warp; i < n; i += NV_GROUP_WARPS) {
                 int m = 0x7fffffff;
                 if (wpl <= 8) {
                     uint32_t cur[8];
 #pragma unroll
                     for (int q = 0; q < 8; q++) cur[q] = nxt[q];
-                    if (i + 32 < n)
+                    if (i + NV_GROUP_WARPS < n)
 #pragma unroll
-                        for (int q = 0; q < 8; q++) { int w = lane + 32 * q; nxt[q] = (q < wpl && w < nw) ? adj[(size_t)(i + 32) * nw + w] : 0u; }
+                        for (int q = 0; q < 8; q++) { int w = lane + 32 * q; nxt[q] = (q < wpl && w < nw) ? adj[(size_t)(i + NV_GROUP_WARPS) * nw + w] : 0u; }
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         uint32_t b = cur[q];
@@ -158,16 +164,16 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
         }
         // classes numbered by their first member (= the component's minimum index)
         int carry = 0;
-        for (int i0 = 0; i0 < n; i0 += 1024) {
+        for (int i0 = 0; i0 < n; i0 += NV_GROUP_THREADS) {
             int i = i0 + tid;
             bool root = i < n && label[i] == i;
             int pos = block_flag_rank(root, carry, s_warp);
             if (root) cls[i] = pos;
         }
         int ncls = carry;
-        for (int i = tid; i < 5 * ncls; i += 1024) acc[i] = 0;
+        for (int i = tid; i < 5 * ncls; i += NV_GROUP_THREADS) acc[i] = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += 1024) {
+        for (int i = tid; i < n; i += NV_GROUP_THREADS) {
             int c = cls[label[i]];
             int4 r = rects[i];
             atomicAdd(&acc[5 * c + 0], r.x); atomicAdd(&acc[5 * c + 1], r.y);
@@ -175,14 +181,14 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
             atomicAdd(&acc[5 * c + 4], 1);
         }
         __syncthreads();
-        for (int c = tid; c < ncls; c += 1024) {
+        for (int c = tid; c < ncls; c += NV_GROUP_THREADS) {
             float s = __fdiv_rn(1.f, __int2float_rn(acc[5 * c + 4]));
             for (int k = 0; k < 4; k++) acc[5 * c + k] = __float2int_rn(__fmul_rn(__int2float_rn(acc[5 * c + k]), s));
         }
         __syncthreads();
         // classes with enough members, in class order (the containment test only ever looks at those)
         int nk = 0;
-        for (int i0 = 0; i0 < ncls; i0 += 1024) {
+        for (int i0 = 0; i0 < ncls; i0 += NV_GROUP_THREADS) {
             int i = i0 + tid;
             bool k = i < ncls && acc[5 * i + 4] > min_neighbors;
             int pos = block_flag_rank(k, nk, s_warp);
@@ -192,7 +198,7 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
         // drop a class that lies inside a clearly stronger one (A.7)
         int *alive = cls;                                   // cls[] is no longer needed: reuse as the survivor flags
         __syncthreads();
-        for (int a = tid; a < nk; a += 1024) {
+        for (int a = tid; a < nk; a += NV_GROUP_THREADS) {
             int i = keep[a];
             int n1 = acc[5 * i + 4], x1 = acc[5 * i], y1 = acc[5 * i + 1], w1 = acc[5 * i + 2], h1 = acc[5 * i + 3];
             bool k = true;
@@ -209,7 +215,7 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
         }
         __syncthreads();
         carry = 0;
-        for (int a0 = 0; a0 < nk; a0 += 1024) {
+        for (int a0 = 0; a0 < nk; a0 += NV_GROUP_THREADS) {
             int a = a0 + tid;
             bool k = false;
             int4 r = make_int4(0, 0, 0, 0);
@@ -243,7 +249,7 @@ cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *can
         k_adj<<<nblocks, 256, 0, st>>>(counters, cand_cap, cand_rects, adj, eps);
         (*nlaunch)++;
     }
-    k_group<<<1, 1024, GROUP_SMEM_LABELS * sizeof(int), st>>>(counters, cand_cap, cand_rects, adj, grp, min_neighbors, eps,
+    k_group<<<1, NV_GROUP_THREADS, GROUP_SMEM_LABELS * sizeof(int), st>>>(counters, cand_cap, cand_rects, adj, grp, min_neighbors, eps,
                                                               img_w, img_h, result, result_cap);
     (*nlaunch)++;
     return cudaGetLastError();
