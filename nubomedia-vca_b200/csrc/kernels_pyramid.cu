@@ -17,13 +17,12 @@ __device__ __forceinline__ int find_level(const PlanDev *__restrict__ plan, int 
     return l;
 }
 
-// One warp per level row, eight integral columns per lane and 256 per chunk: resize (two source rows, 8.8 x 8.8 fixed
-// point) -> equalised value -> running sums of v and v*v inside the lane, ONE warp-shuffle scan of the lane totals per
-// chunk, carried across chunks.  A lane owns integral columns c = 8k .. 8k+7 (pixel x = c - 1; c = 0 is the zero column),
-// so that its results leave as aligned 16-byte stores: four words per plane on de-interleaved (ystep 2) rows, two
-// groups of four on plain rows.  (The first version scanned every 32 pixels with ten shuffles: 100 instructions per
-// pixel, 25.6 M warp instructions per config-3 frame; this one needs about a third.)
-#define RS_PX 8
+// (A variant with eight integral columns per lane, in-lane running sums, one shuffle scan per 256 columns and 16-byte
+// stores needs a third of the instructions but 48 registers and fewer, longer warps: 57 us against 46 us alone, and
+// 2540 against 2600 frames/s in bench.py, where this kernel has to fit beside the resident blocks of another stream's
+// cascade kernel — profiles/r1_v5_summary.md.  Kept: this one.)
+// One warp per level row: resize (two source rows, 8.8 x 8.8 fixed point) -> equalised value -> warp-shuffle
+// inclusive scan of v and v*v along the row, carried across 32-pixel chunks.
 __global__ void __launch_bounds__(256)
 k_pyr_rowscan(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ gray, int gstride,
               const uint8_t *__restrict__ lut, const int2 *__restrict__ ptab, uint32_t *__restrict__ sum,
@@ -36,7 +35,7 @@ k_pyr_rowscan(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ gray
 
     int l = find_level(plan, blockIdx.x, &LevelDesc::rowblk0);
     const LevelDesc &L = plan->lv[l];
-    const int lw = L.lw, lh = L.lh, ys = L.ystep, pitch = L.ipitch, plane = L.iplane;
+    int lw = L.lw, lh = L.lh, ys = L.ystep, pitch = L.ipitch, plane = L.iplane;
     int y = (blockIdx.x - L.rowblk0) * 8 + warp;
     if (y >= lh) return;
     uint32_t *srow = sum + L.iofs, *qrow = sq + L.iofs;
@@ -44,67 +43,42 @@ k_pyr_rowscan(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ gray
         for (int c = lane; c < pitch; c += 32) { srow[c] = 0; qrow[c] = 0; }
     srow += (size_t)(y + 1) * pitch;
     qrow += (size_t)(y + 1) * pitch;
+    if (lane == 0) { srow[0] = 0; qrow[0] = 0; }        // first integral column (c = 0 -> plane 0, col 0)
 
     const int2 *xt = ptab + L.xtab, *yt = ptab + L.ytab;
     int2 ty = yt[y];
     const uint8_t *g0 = gray + (size_t)ty.x * gstride, *g1 = ty.y < 0 ? g0 : g0 + gstride;
-    const uint32_t r1 = ty.y < 0 ? 0u : (uint32_t)ty.y, r0 = 256u - r1;
+    uint32_t r1 = ty.y < 0 ? 0u : (uint32_t)ty.y, r0 = 256u - r1;
     uint32_t carry_s = 0, carry_q = 0;
-    for (int c0 = 0; c0 <= lw; c0 += 32 * RS_PX) {
-        const int cb = c0 + lane * RS_PX;
-        uint32_t s[RS_PX], q[RS_PX];
-        uint32_t rs = 0, rq = 0;
-#pragma unroll
-        for (int k = 0; k < RS_PX; k++) {
-            const int x = cb + k - 1;
-            const bool valid = x >= 0 && x < lw;
-            // unconditional, clamped loads: the eight table reads, then the 32 taps, then the 32 LUT lookups of a lane
-            // are each in flight together
-            const int2 tx = __ldg(xt + min(max(x, 0), lw - 1));
-            const int o1 = tx.y < 0 ? 0 : 1;                         // replicated edge sample: weight 256 on tap 0
-            const uint32_t c1 = tx.y < 0 ? 0u : (uint32_t)tx.y, c0w = 256u - c1;
-            const uint32_t h0 = s_lut[g0[tx.x]] * c0w + s_lut[g0[tx.x + o1]] * c1;
-            const uint32_t h1 = s_lut[g1[tx.x]] * c0w + s_lut[g1[tx.x + o1]] * c1;
-            uint32_t v = (h0 * r0 + h1 * r1 + 32768u) >> 16;
-            if (valid && pyr_debug) pyr_debug[L.pofs + (size_t)y * lw + x] = (uint8_t)v;
-            v = valid ? v : 0u;
-            rs += v; rq += v * v;
-            s[k] = rs; q[k] = rq;
+    for (int x0 = 0; x0 < lw; x0 += 32) {
+        int x = x0 + lane;
+        uint32_t v = 0;
+        if (x < lw) {
+            int2 tx = xt[x];
+            uint32_t h0, h1;
+            if (tx.y < 0) { h0 = (uint32_t)s_lut[g0[tx.x]] << 8; h1 = (uint32_t)s_lut[g1[tx.x]] << 8; }
+            else {
+                uint32_t c1 = (uint32_t)tx.y, c0 = 256u - c1;
+                h0 = s_lut[g0[tx.x]] * c0 + s_lut[g0[tx.x + 1]] * c1;
+                h1 = s_lut[g1[tx.x]] * c0 + s_lut[g1[tx.x + 1]] * c1;
+            }
+            v = (h0 * r0 + h1 * r1 + 32768u) >> 16;
+            if (pyr_debug) pyr_debug[L.pofs + (size_t)y * lw + x] = (uint8_t)v;
         }
-        uint32_t is = rs, iq = rq;                      // inclusive scan of the lane totals
+        uint32_t s = v, q = v * v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t ts = __shfl_up_sync(0xffffffffu, is, d), tq = __shfl_up_sync(0xffffffffu, iq, d);
-            if (lane >= d) { is += ts; iq += tq; }
+            uint32_t ts = __shfl_up_sync(0xffffffffu, s, d), tq = __shfl_up_sync(0xffffffffu, q, d);
+            if (lane >= d) { s += ts; q += tq; }
         }
-        const uint32_t os = carry_s + is - rs, oq = carry_q + iq - rq;
-#pragma unroll
-        for (int k = 0; k < RS_PX; k++) { s[k] += os; q[k] += oq; }
-        if (cb + RS_PX - 1 <= lw) {                     // all eight columns exist: aligned 16-byte stores
-            if (ys == 2) {
-                int e = cb >> 1;
-                *reinterpret_cast<uint4 *>(srow + e) = make_uint4(s[0], s[2], s[4], s[6]);
-                *reinterpret_cast<uint4 *>(srow + plane + e) = make_uint4(s[1], s[3], s[5], s[7]);
-                *reinterpret_cast<uint4 *>(qrow + e) = make_uint4(q[0], q[2], q[4], q[6]);
-                *reinterpret_cast<uint4 *>(qrow + plane + e) = make_uint4(q[1], q[3], q[5], q[7]);
-            } else {
-                *reinterpret_cast<uint4 *>(srow + cb) = make_uint4(s[0], s[1], s[2], s[3]);
-                *reinterpret_cast<uint4 *>(srow + cb + 4) = make_uint4(s[4], s[5], s[6], s[7]);
-                *reinterpret_cast<uint4 *>(qrow + cb) = make_uint4(q[0], q[1], q[2], q[3]);
-                *reinterpret_cast<uint4 *>(qrow + cb + 4) = make_uint4(q[4], q[5], q[6], q[7]);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < RS_PX; k++) {
-                int c = cb + k;
-                if (c <= lw) {
-                    int pc = ys == 2 ? (c & 1) * plane + (c >> 1) : c;
-                    srow[pc] = s[k]; qrow[pc] = q[k];
-                }
-            }
+        s += carry_s; q += carry_q;
+        if (x < lw) {
+            int c = x + 1;
+            int pc = ys == 2 ? (c & 1) * plane + (c >> 1) : c;
+            srow[pc] = s; qrow[pc] = q;
         }
-        carry_s += __shfl_sync(0xffffffffu, is, 31);
-        carry_q += __shfl_sync(0xffffffffu, iq, 31);
+        carry_s = __shfl_sync(0xffffffffu, s, 31);
+        carry_q = __shfl_sync(0xffffffffu, q, 31);
     }
 }
 
