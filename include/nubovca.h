@@ -165,6 +165,10 @@ typedef struct {
 NV_API int nv_tracker_process(nv_ctx *ctx, const uint8_t *bgra, int width, int height, int stride_bytes,
                               double timestamp_ms, const nv_tracker_params *p, nv_rect *out, int cap, int *n);
 NV_API int nv_tracker_reset(nv_ctx *ctx);
+/* The same block fed with 4:2:0 planes (ingest extension, see nv_face_detect_yuv): gray is BGR2GRAY of
+ * cvtColor(COLOR_YUV2BGR_*) per pixel, i.e. the result equals nv_tracker_process on the converted frame. */
+NV_API int nv_tracker_process_yuv(nv_ctx *ctx, const nv_yuv_frame *frame, double timestamp_ms, const nv_tracker_params *p,
+                                  nv_rect *out, int cap, int *n);
 
 /* ---- image ops used by the nested elements (eye/mouth/nose/ear) on host images:
  *      cvtColor BGR2GRAY (kmseyedetect.cpp:949), equalizeHist (:950,964), cv::resize INTER_LINEAR
@@ -217,8 +221,9 @@ NV_API int nv_element_push_motion_event(nv_element *e);
  * the events-ms rate limit; the tracker's MHI timestamp is pts_ns / 1e6 unless now_ms >= 0. */
 NV_API int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int width, int height, int stride_bytes,
                                          uint64_t pts_ns, double now_ms);
-/* nubofacedetector on 4:2:0 planes (see nv_face_detect_yuv): gating, tracking, events and signals as above; view-faces is
- * ignored (the reference's overlay is defined on BGR pixels).  Other elements: NV_ERR_UNSUPPORTED. */
+/* nubofacedetector and nubotracker on 4:2:0 planes (see nv_face_detect_yuv / nv_tracker_process_yuv): gating, tracking,
+ * events and signals as above; view-faces / set_visual_mode are ignored (the reference's overlays are defined on BGR(A)
+ * pixels).  Other elements: NV_ERR_UNSUPPORTED. */
 NV_API int nv_element_transform_frame_yuv(nv_element *e, const nv_yuv_frame *frame, uint64_t pts_ns, double now_ms);
 /* what the last frame produced: the downstream event's sub-structures (pushed != 0 if the element
  * pushed the event; the ear element builds it but never pushes, kmseardetect.cpp:210-290) and the

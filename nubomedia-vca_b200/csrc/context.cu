@@ -1215,13 +1215,14 @@ extern "C" int nv_tracker_reset(nv_ctx *ctx)
     return NV_OK;
 }
 
-extern "C" int nv_tracker_process(nv_ctx *ctx, const uint8_t *bgra, int width, int height, int stride_bytes,
-                                  double timestamp_ms, const nv_tracker_params *p, nv_rect *out, int cap, int *n)
+// src.fmt == NV_FMT_BGR: interleaved BGRA in p[0] / s[0]; else the planes of a 4:2:0 frame (checked by the callers)
+static int tracker_impl(nv_ctx *ctx, const FaceSrc &src, int width, int height, double timestamp_ms, const nv_tracker_params *p,
+                        nv_rect *out, int cap, int *n)
 {
-    int rc = check_frame(ctx, bgra, width, height, stride_bytes, 4);
-    if (rc != NV_OK) return rc;
+    int rc;
+    const uint8_t *bgra = src.p[0];
+    const int stride_bytes = src.s[0];
     if (!p) { nv_set_error("null params"); return NV_ERR_ARG; }
-    if (stride_bytes % 4) { nv_set_error("BGRA stride must be a multiple of 4"); return NV_ERR_ARG; }
     NV_CUDA(cudaSetDevice(ctx->gpu));
     if (ctx->pending) NV_CUDA(cudaStreamSynchronize(ctx->stream));
     size_t np = (size_t)width * height;
@@ -1241,10 +1242,17 @@ extern "C" int nv_tracker_process(nv_ctx *ctx, const uint8_t *bgra, int width, i
         NV_CUDA(cudaMallocHost(&ctx->h_trk, (TRK_MAX_COMPONENTS + 1) * sizeof(int4)));
         ctx->trk_w = width; ctx->trk_h = height; ctx->trk_frames = 0;
     }
-    if ((rc = nv_h2d(ctx, bgra, (size_t)stride_bytes * height)) != NV_OK) return rc;
+    SrcPlanes planes = {src.p[0], src.p[1], src.p[2], src.s[0], src.s[1], src.s[2]};
+    if (!src.on_device) {
+        if (src.fmt != NV_FMT_BGR) { if ((rc = yuv_h2d(ctx, src, height, &planes)) != NV_OK) return rc; }
+        else {
+            if ((rc = nv_h2d(ctx, bgra, (size_t)stride_bytes * height)) != NV_OK) return rc;
+            planes.p0 = ctx->d_frame;
+        }
+    }
     int first = ctx->trk_frames == 0, nl = 0;
     float ts = (float)timestamp_ms, del = (float)(timestamp_ms - 0.2);          // MHI_DURATION, :28
-    NV_CUDA(launch_tracker(ctx, ctx->d_frame, width, height, stride_bytes, first, ts, del, p->threshold, &nl));
+    NV_CUDA(launch_tracker(ctx, src.fmt, planes, width, height, first, ts, del, p->threshold, &nl));
     ctx->launches += nl;
     ctx->trk_frames++;
     int total = 0;
@@ -1269,6 +1277,25 @@ extern "C" int nv_tracker_process(nv_ctx *ctx, const uint8_t *bgra, int width, i
     if (n) *n = m;
     if (total > TRK_MAX_COMPONENTS) { nv_set_error("more than %d motion components", TRK_MAX_COMPONENTS); return NV_ERR_CAPACITY; }
     return NV_OK;
+}
+
+extern "C" int nv_tracker_process(nv_ctx *ctx, const uint8_t *bgra, int width, int height, int stride_bytes,
+                                  double timestamp_ms, const nv_tracker_params *p, nv_rect *out, int cap, int *n)
+{
+    int rc = check_frame(ctx, bgra, width, height, stride_bytes, 4);
+    if (rc != NV_OK) return rc;
+    if (stride_bytes % 4) { nv_set_error("BGRA stride must be a multiple of 4"); return NV_ERR_ARG; }
+    FaceSrc src = {NV_FMT_BGR, {bgra, nullptr, nullptr}, {stride_bytes, 0, 0}, false};
+    return tracker_impl(ctx, src, width, height, timestamp_ms, p, out, cap, n);
+}
+
+extern "C" int nv_tracker_process_yuv(nv_ctx *ctx, const nv_yuv_frame *f, double timestamp_ms, const nv_tracker_params *p,
+                                      nv_rect *out, int cap, int *n)
+{
+    FaceSrc src;
+    int rc = check_yuv(ctx, f, &src);
+    if (rc != NV_OK) return rc;
+    return tracker_impl(ctx, src, f->width, f->height, timestamp_ms, p, out, cap, n);
 }
 
 // ------------------------------------------------------------------------------------------------

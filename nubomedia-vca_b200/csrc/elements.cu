@@ -922,7 +922,7 @@ int ear_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double no
 // ------------------------------------------------------------------------------------------------
 // nubotracker (TRK:339-421)
 // ------------------------------------------------------------------------------------------------
-int tracker_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, uint64_t pts_ns, double now_ms)
+int tracker_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, uint64_t pts_ns, double now_ms, const nv_yuv_frame *yuv = nullptr)
 {
     nv_tracker_params p;
     p.threshold = (int)e->get("set_threshold"); p.min_area = (int)e->get("set_min_area");
@@ -930,12 +930,13 @@ int tracker_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, uint6
     std::vector<nv_rect> out(16384);
     int n = 0;
     double ts = now_ms >= 0 ? now_ms : (double)pts_ns / 1e6;        // the reference uses clock() in ms (TRK:349)
-    int rc = nv_tracker_process(e->ctx, frame, W, H, stride, ts, &p, out.data(), (int)out.size(), &n);
+    int rc = yuv ? nv_tracker_process_yuv(e->ctx, yuv, ts, &p, out.data(), (int)out.size(), &n)
+                 : nv_tracker_process(e->ctx, frame, W, H, stride, ts, &p, out.data(), (int)out.size(), &n);
     if (rc != NV_OK) n = 0;
     std::string s;
     bool build = e->get("set_visual_mode") > 0 || e->get("activate-events") == 1;      // TRK:383
     for (int i = 0; i < n; i++) {
-        if (e->get("set_visual_mode") > 0)                             // TRK:388-389: rec.tl() .. rec.br(), Scalar(0, 0, 255)
+        if (e->get("set_visual_mode") > 0 && frame)                    // TRK:388-389 (BGRA frames only): rec.tl() .. rec.br(), Scalar(0, 0, 255)
             draw_rectangle3(frame, W, H, stride, 4, out[i].x, out[i].y, out[i].x + out[i].width, out[i].y + out[i].height,
                             Bgr{0, 0, 255});
         add_meta(e, "object", "object", out[i].x, out[i].y, out[i].width, out[i].height);
@@ -1106,13 +1107,14 @@ extern "C" int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int 
     return NV_ERR_ARG;
 }
 
-// The face element fed with 4:2:0 planes (a shell whose sink caps add I420 / YV12 / NV12 / NV21): same gating, tracking,
+// The face element and the tracker fed with 4:2:0 planes (a shell whose sink caps add I420 / YV12 / NV12 / NV21): same gating, tracking,
 // events and signals; view-faces is ignored — the reference defines its overlay on BGR pixels only.
 extern "C" int nv_element_transform_frame_yuv(nv_element *e, const nv_yuv_frame *f, uint64_t pts_ns, double now_ms)
 {
-    (void)pts_ns;
     if (!e || !f || f->width <= 0 || f->height <= 0) { nv_set_error("bad argument"); return NV_ERR_ARG; }
-    if (e->kind != K_FACE) { nv_set_error("4:2:0 frames are only taken by nubofacedetector"); return NV_ERR_UNSUPPORTED; }
+    if (e->kind != K_FACE && e->kind != K_TRACKER) {
+        nv_set_error("4:2:0 frames are only taken by nubofacedetector and nubotracker"); return NV_ERR_UNSUPPORTED;
+    }
     if (!e->ctx || f->width > e->ctx->max_w || f->height > e->ctx->max_h) {
         nv_ctx_destroy(e->ctx); e->ctx = nullptr;
         int rc = nv_ctx_create(e->gpu, std::max(f->width, 1920), std::max(f->height, 1080), &e->ctx);
@@ -1120,6 +1122,7 @@ extern "C" int nv_element_transform_frame_yuv(nv_element *e, const nv_yuv_frame 
     }
     NV_CUDA(cudaSetDevice(e->ctx->gpu));
     e->msg.clear(); e->signal.clear(); e->emitted = false; e->pushed = false;
+    if (e->kind == K_TRACKER) return tracker_frame(e, nullptr, f->width, f->height, 0, pts_ns, now_ms, f);
     return face_frame(e, nullptr, f->width, f->height, 0, now_ms, f);
 }
 

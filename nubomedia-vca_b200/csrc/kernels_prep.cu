@@ -160,38 +160,6 @@ k_face_prep_bgr4(const uint8_t *__restrict__ src, int sstride, uint8_t *__restri
 // ---- 4:2:0 ingest: the same block fed by I420 / NV12 / NV21 planes.  Every source pixel the
 // resize touches is converted with cvtColor(COLOR_YUV2BGR_*)'s arithmetic (BT.601, 20-bit fixed point, saturated to
 // u8 per pixel; oracle: ora_yuv420_to_bgr), so the result equals the reference block on the converted BGR frame.
-struct YuvTerms { int b, g, r; };                 // chroma contributions incl. the rounding half
-
-template <int FMT>   // 1: I420 (three planes), 2: NV12 (UV interleaved), 3: NV21 (VU interleaved)
-__device__ __forceinline__ YuvTerms yuv_chroma(const SrcPlanes &s, int x, int y)
-{
-    int u, v;
-    if (FMT == 1) {
-        u = s.p1[(size_t)(y >> 1) * s.s1 + (x >> 1)];
-        v = s.p2[(size_t)(y >> 1) * s.s2 + (x >> 1)];
-    } else {
-        const uint8_t *uv = s.p1 + (size_t)(y >> 1) * s.s1 + (x & ~1);
-        u = uv[FMT == 2 ? 0 : 1];
-        v = uv[FMT == 2 ? 1 : 0];
-    }
-    u -= 128; v -= 128;
-    YuvTerms t;
-    t.b = (1 << 19) + 2116026 * u;
-    t.g = (1 << 19) - 852492 * v - 409993 * u;
-    t.r = (1 << 19) + 1673527 * v;
-    return t;
-}
-
-__device__ __forceinline__ int sat_u8(int v) { return min(max(v, 0), 255); }
-
-__device__ __forceinline__ void yuv_pixel(const SrcPlanes &s, const YuvTerms &t, int x, int y, int c3[3])
-{
-    int yy = max(0, (int)s.p0[(size_t)y * s.s0 + x] - 16) * 1220542;
-    c3[0] = sat_u8((yy + t.b) >> 20);
-    c3[1] = sat_u8((yy + t.g) >> 20);
-    c3[2] = sat_u8((yy + t.r) >> 20);
-}
-
 template <int FMT>
 __global__ void __launch_bounds__(256)
 k_face_prep_yuv(SrcPlanes s, int sw, int sh, uint8_t *__restrict__ gray, int dw, int dh, const int *__restrict__ rtab,

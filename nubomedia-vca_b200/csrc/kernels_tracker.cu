@@ -14,16 +14,26 @@
 
 #define TRK_MAX_COMPONENTS 16384
 
+// FMT 0: BGRA (the reference's caps, gstnubotracker.cpp:57-61); 1 / 2 / 3: I420 / NV12 / NV21 planes — the 4:2:0 ingest
+// extension: gray = BGR2GRAY(cvtColor(COLOR_YUV2BGR_*)) per pixel, the BGRA frame is never built.
+template <int FMT>
 __global__ void __launch_bounds__(256)
-k_trk_point(const uint8_t *__restrict__ bgra, int w, int h, int stride, int first, float ts, float del, int thr,
+k_trk_point(SrcPlanes src, int w, int h, int first, float ts, float del, int thr,
             uint8_t *__restrict__ prev, float *__restrict__ mhi, int *__restrict__ label, int4 *__restrict__ box,
             int *__restrict__ seed, uint8_t *__restrict__ mask_out)
 {
     int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     if (x >= w || y >= h) return;
     int p = y * w + x;
-    uchar4 px = *reinterpret_cast<const uchar4 *>(bgra + (size_t)y * stride + 4 * x);
-    int g = (px.x * 3735 + px.y * 19235 + px.z * 9798 + 16384) >> 15;
+    int g;
+    if (FMT == 0) {
+        uchar4 px = *reinterpret_cast<const uchar4 *>(src.p0 + (size_t)y * src.s0 + 4 * x);
+        g = (px.x * 3735 + px.y * 19235 + px.z * 9798 + 16384) >> 15;
+    } else {
+        int c3[3];
+        yuv_pixel(src, yuv_chroma<FMT == 0 ? 1 : FMT>(src, x, y), x, y, c3);
+        g = (c3[0] * 3735 + c3[1] * 19235 + c3[2] * 9798 + 16384) >> 15;
+    }
     if (!first) {
         int d = abs(g - (int)prev[p]);
         bool silh = d > thr;
@@ -121,7 +131,7 @@ k_trk_sort(int *__restrict__ misc, const int *__restrict__ keys, const int4 *__r
     if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = make_int4(misc[0], 0, 0, 0);
 }
 
-cudaError_t launch_tracker(nv_ctx *ctx, const uint8_t *d_bgra, int w, int h, int stride, int first, float ts, float del,
+cudaError_t launch_tracker(nv_ctx *ctx, int fmt, const SrcPlanes &src, int w, int h, int first, float ts, float del,
                            int thr, int *nlaunch)
 {
     dim3 grid((w + 31) / 32, (h + 7) / 8), block(32, 8);
@@ -130,8 +140,14 @@ cudaError_t launch_tracker(nv_ctx *ctx, const uint8_t *d_bgra, int w, int h, int
     // scratch carved from d_trk_labels: label[n] | seed[n] | keys[MAX] ; boxes: box[n] | rects[MAX] | out[1+MAX]
     int *label = ctx->d_trk_labels, *seed = label + n, *keys = seed + n;
     int4 *box = ctx->d_trk_boxes, *rects = box + n, *out = rects + TRK_MAX_COMPONENTS;
-    k_trk_point<<<grid, block, 0, st>>>(d_bgra, w, h, stride, first, ts, del, thr, ctx->d_trk_prev, ctx->d_trk_mhi, label,
-                                        box, seed, ctx->debug ? ctx->d_trk_mask : nullptr);
+    uint8_t *mask = ctx->debug ? ctx->d_trk_mask : nullptr;
+#define TRK_POINT(F) k_trk_point<F><<<grid, block, 0, st>>>(src, w, h, first, ts, del, thr, ctx->d_trk_prev, ctx->d_trk_mhi, label, box, seed, mask)
+    if (fmt == NV_FMT_BGR) TRK_POINT(0);             // interleaved: BGRA here
+    else if (fmt == NV_FMT_I420) TRK_POINT(1);
+    else if (fmt == NV_FMT_NV12) TRK_POINT(2);
+    else if (fmt == NV_FMT_NV21) TRK_POINT(3);
+    else return cudaErrorInvalidValue;
+#undef TRK_POINT
     (*nlaunch)++;
     if (!first) {
         cudaError_t e = cudaMemsetAsync(ctx->d_trk_misc, 0, 4 * sizeof(int), st);

@@ -86,6 +86,7 @@ _SIGS = {
     "nv_host_free": (None, [_vp]),
     "nv_tracker_process": (_i, [_vp, _vp, _i, _i, _i, C.c_double, C.POINTER(TrackerParams), _vp, _i, _ip]),
     "nv_tracker_reset": (_i, [_vp]),
+    "nv_tracker_process_yuv": (_i, [_vp, C.POINTER(YuvFrame), C.c_double, C.POINTER(TrackerParams), _vp, _i, _ip]),
     "nv_bgr2gray": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i]),
     "nv_equalize_hist": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
     "nv_resize_linear": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i]),
@@ -442,6 +443,14 @@ class Context:
         n = C.c_int(0)
         _check(_lib.nv_tracker_process(self.handle, _p(bgra), w, h, bgra.strides[0], float(ts_ms), C.byref(p),
                                        self._out, self._cap, C.byref(n)), "nv_tracker_process")
+        return _rects(self._out, n.value)
+
+    def tracker_process_yuv(self, planes, fmt, ts_ms, threshold=20, min_area=50, max_area=30000, distance=35):
+        f = self._yuv_frame(planes, fmt)
+        p = TrackerParams(threshold, min_area, max_area, distance)
+        n = C.c_int(0)
+        _check(_lib.nv_tracker_process_yuv(self.handle, C.byref(f), float(ts_ms), C.byref(p), self._out, self._cap, C.byref(n)),
+               "nv_tracker_process_yuv")
         return _rects(self._out, n.value)
 
     def tracker_reset(self):

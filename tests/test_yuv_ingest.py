@@ -201,7 +201,7 @@ def test_gpu_face_element_on_yuv_frames(cascade_dir, fmt):
         seen += len(msg)
     assert seen > 0
     e.close()
-    t = nv.Element("nubotracker", 0, cascade_dir)
+    t = nv.Element("nubomouthdetector", 0, cascade_dir)               # the nested elements take BGR only
     with pytest.raises(nv.NuboError):
         t.process_yuv(synth.yuv420_planes(synth.to_yuv420(base, fmt), w, h, fmt), fmt)
     t.close()
@@ -235,3 +235,42 @@ def test_gpu_yuv_planes_already_on_the_device(face):
                 assert rects_equal(c.face_collect(), exp)
     finally:
         c.close()
+
+
+def _bgra(bgr):
+    out = np.empty(bgr.shape[:2] + (4,), np.uint8)
+    out[..., :3] = bgr; out[..., 3] = 255
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", FMTS)
+def test_gpu_tracker_on_yuv_frames(fmt, cascade_dir):
+    """nv_tracker_process_yuv and the nubotracker mirror on 4:2:0 buffers: the motion objects of every frame equal the
+    oracle's on cvtColor's BGR frame (alpha added), including a switch back to BGRA input on the same context."""
+    w, h = 640, 360
+    frames = synth.tracker_sequence(w, h, 7, seed=9, noise=50)
+    ctx = nv.Context(0, w, h)
+    st = O.TrackerState(w, h)
+    e = nv.Element("nubotracker", 0, cascade_dir)
+    est = O.TrackerState(w, h)
+    nobj = 0
+    try:
+        for i, f in enumerate(frames):
+            ts = 40.0 * (i + 1)
+            buf = synth.to_yuv420(np.ascontiguousarray(f[..., :3]), fmt)
+            bgra = _bgra(ora_bgr(buf, w, h, fmt))
+            planes = synth.yuv420_planes(buf, w, h, fmt)
+            if i == 4:                                                 # one BGRA frame in between: same state, same kernels
+                got = ctx.tracker_process(bgra, ts)
+            else:
+                got = ctx.tracker_process_yuv(planes, fmt, ts)
+            exp, _, _ = st.process(bgra, ts)
+            assert got.shape == exp.shape and (got == exp).all(), i
+            nobj += len(exp)
+            msg, pushed, _ = e.process_yuv(planes, fmt, now_ms=1e15 + ts)
+            eexp, _, _ = est.process(bgra, 1e15 + ts)
+            assert [list(m[2:]) for m in msg] == eexp.tolist() and not pushed, i
+        assert nobj > 0
+    finally:
+        ctx.close(); e.close()
