@@ -325,7 +325,7 @@ def aux_other_configs(nv, local, world):
     # every stream its own element, contexts and CUDA streams — what a media server with several pipelines does
     import threading
 
-    def concurrent(factory, frames_of, nstreams, nframes, **props):
+    def concurrent(factory, frames_of, nstreams, nframes, yuv=None, **props):
         els = [nv.Element(factory, local, cdir) for _ in range(nstreams)]
         for e_ in els:
             for k, v in props.items():
@@ -334,7 +334,10 @@ def aux_other_configs(nv, local, world):
         def loop(i, n):
             fr = frames_of(i)
             for j in range(n):
-                els[i].process(fr[j % len(fr)], now_ms=33.3 * (j + 1))
+                if yuv:
+                    els[i].process_yuv(fr[j % len(fr)], yuv, now_ms=33.3 * (j + 1))
+                else:
+                    els[i].process(fr[j % len(fr)], now_ms=33.3 * (j + 1))
         for i in range(nstreams):
             loop(i, 3)
         th = [threading.Thread(target=loop, args=(i, nframes)) for i in range(nstreams)]
@@ -351,6 +354,10 @@ def aux_other_configs(nv, local, world):
     NS = 8
     out["cfg2_eyes_in_faces_1280x720"]["frames_per_s_%d_streams" % NS] = concurrent("nuboeyedetector", lambda i: [f2], NS, 150)
     out["cfg4_tracker_1280x720_bgra"]["frames_per_s_%d_streams" % NS] = concurrent("nubotracker", lambda i: seq, NS, 300)
+    # the same sequence handed over as NV12 planes (nv_element_transform_frame_yuv): 1.5 instead of 4 bytes per pixel
+    seq_nv12 = [_pin(synth.to_yuv420(np.ascontiguousarray(f[..., :3]), "NV12")) for f in seq]
+    pl_nv12 = [synth.yuv420_planes(b, 1280, 720, "NV12") for b in seq_nv12]
+    out["cfg4_tracker_1280x720_bgra"]["frames_per_s_%d_streams_nv12" % NS] = concurrent("nubotracker", lambda i: pl_nv12, NS, 300, yuv="NV12")
     out["cfg1_face_640x480_defaults"]["frames_per_s_%d_streams" % NS] = concurrent("nubofacedetector", lambda i: [f1], NS, 300)
     shutil.rmtree(cdir, ignore_errors=True)
     return out
