@@ -221,9 +221,10 @@ NV_API int nv_element_push_motion_event(nv_element *e);
  * the events-ms rate limit; the tracker's MHI timestamp is pts_ns / 1e6 unless now_ms >= 0. */
 NV_API int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int width, int height, int stride_bytes,
                                          uint64_t pts_ns, double now_ms);
-/* nubofacedetector and nubotracker on 4:2:0 planes (see nv_face_detect_yuv / nv_tracker_process_yuv): gating, tracking,
- * events and signals as above; view-faces / set_visual_mode are ignored (the reference's overlays are defined on BGR(A)
- * pixels).  Other elements: NV_ERR_UNSUPPORTED. */
+/* Any of the six elements on 4:2:0 planes (see nv_face_detect_yuv / nv_tracker_process_yuv; the nested elements take
+ * their full-resolution gray image as BGR2GRAY(cvtColor(COLOR_YUV2BGR_*)) per pixel): gating, tracking, ROI arithmetic,
+ * events and signals as above; the view-* / set_visual_mode overlays are ignored (the reference defines them on BGR(A)
+ * pixels). */
 NV_API int nv_element_transform_frame_yuv(nv_element *e, const nv_yuv_frame *frame, uint64_t pts_ns, double now_ms);
 /* what the last frame produced: the downstream event's sub-structures (pushed != 0 if the element
  * pushed the event; the ear element builds it but never pushes, kmseardetect.cpp:210-290) and the

@@ -928,6 +928,17 @@ static int check_yuv(nv_ctx *ctx, const nv_yuv_frame *f, FaceSrc *src)
     return NV_OK;
 }
 
+int nv_yuv_upload(nv_ctx *ctx, const nv_yuv_frame *f, SrcPlanes *planes)
+{
+    FaceSrc src;
+    int rc = check_yuv(ctx, f, &src);
+    if (rc != NV_OK) return rc;
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    if (ctx->pending) NV_CUDA(cudaStreamSynchronize(ctx->stream));
+    *planes = SrcPlanes{src.p[0], src.p[1], src.p[2], src.s[0], src.s[1], src.s[2]};
+    return src.on_device ? NV_OK : yuv_h2d(ctx, src, f->height, planes);
+}
+
 static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const FaceSrc &src, int width, int height, const nv_face_params *p)
 {
     const uint8_t *bgr = src.p[0];

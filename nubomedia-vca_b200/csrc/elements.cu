@@ -49,6 +49,7 @@ struct nv_element {
     Kind kind;
     std::string factory, dir;
     nv_ctx *ctx = nullptr;  int gpu = 0;
+    const nv_yuv_frame *yuv = nullptr;                                  // set while a 4:2:0 buffer is being processed
     std::vector<nv_ctx *> aux;                                          // one stream each: the ROI cascades of a frame run side by side
     std::vector<Prop> props;
     nv_cascade *c_face = nullptr, *c_a = nullptr, *c_b = nullptr;     // face / (right eye, mouth, nose, "lear") / (left eye, "rear")
@@ -193,6 +194,23 @@ int upload_frame(nv_ctx *ctx, const uint8_t *frame, int stride, int h)
     return nv_h2d(ctx, frame, (size_t)stride * h);
 }
 
+// first step of the nested elements (EYE:949, MOUTH:836, NOSE:834, EAR:786): the full-resolution gray image, from the BGR
+// frame or — for a 4:2:0 buffer — from cvtColor(COLOR_YUV2BGR_*) of its planes, per pixel
+int frame_to_gray(nv_element *e, nv_ctx *ctx, const uint8_t *frame, int stride, int W, int H, uint8_t *gray)
+{
+    int r;
+    if (e->yuv) {
+        SrcPlanes pl;
+        if ((r = nv_yuv_upload(ctx, e->yuv, &pl)) != NV_OK) return r;
+        NV_CUDA(launch_yuv2gray(e->yuv->format, pl, W, H, gray, W, ctx->stream));
+    } else {
+        if ((r = upload_frame(ctx, frame, stride, H)) != NV_OK) return r;
+        NV_CUDA(launch_bgr2gray(ctx->d_frame, W, H, stride, 3, gray, W, ctx->stream));
+    }
+    ctx->launches++;
+    return NV_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // view-* drawing, on the host: the frame is the caller's (GStreamer-mapped) memory and a handful of rectangles are
 // written per frame.  cvRectangle(img, p1, p2, color, 3, 8, 0) (BASEFACE:76, MOUTH:900, NOSE:902, EAR:754, TRK:389)
@@ -218,6 +236,7 @@ void fill_span(uint8_t *frame, int W, int H, int stride, int cn, int y, int xa, 
 
 void draw_rectangle3(uint8_t *frame, int W, int H, int stride, int cn, int xa, int ya, int xb, int yb, Bgr c)
 {
+    if (!frame) return;                              // 4:2:0 buffers: the overlays are defined on BGR(A) pixels only
     const int x0 = std::min(xa, xb), x1 = std::max(xa, xb), y0 = std::min(ya, yb), y1 = std::max(ya, yb), R = 2;
     for (int y = y0 - R; y <= y1 + R; y++) {
         int dt = abs(y - y0), db = abs(y - y1);
@@ -378,6 +397,7 @@ void thick_line(const Img &im, P2 p0, P2 p1, int thickness, int flags)
 
 void circle(uint8_t *frame, int W, int H, int stride, int cn, int cx, int cy, int radius, Bgr c, int thickness)
 {
+    if (!frame) return;
     static const std::vector<float> sin_tab = []() {             // OpenCV's SinTable: sine of whole degrees 0..450 written with
         std::vector<float> t(451);                               // seven decimals and read back as float literals
         char buf[32];
@@ -657,10 +677,8 @@ int eye_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double no
             std::vector<nv_rect> res_r, res_l;
             rc = [&]() -> int {
                 int r;
-                if ((r = upload_frame(ctx, frame, stride, H)) != NV_OK) return r;
                 if ((r = img_ensure(e->gray, W, H)) != NV_OK) return r;
-                NV_CUDA(launch_bgr2gray(ctx->d_frame, W, H, stride, 3, e->gray.p, W, ctx->stream));     // EYE:949
-                ctx->launches++;
+                if ((r = frame_to_gray(e, ctx, frame, stride, W, H, e->gray.p)) != NV_OK) return r;     // EYE:949
                 if ((r = dev_equalize(ctx, e->gray)) != NV_OK) return r;                                 // EYE:950 (full resolution)
                 if (e->get("detect-event") == 0) {
                     if ((r = dev_resize(ctx, e->gray, e->face_img, cv_round(W / sc.o2f), cv_round(H / sc.o2f))) != NV_OK) return r;
@@ -754,10 +772,8 @@ int mouth_nose_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, do
             e->num_frames_to_process--;
             rc = [&]() -> int {
                 int r;
-                if ((r = upload_frame(ctx, frame, stride, H)) != NV_OK) return r;
                 if ((r = img_ensure(e->gray, W, H)) != NV_OK) return r;
-                NV_CUDA(launch_bgr2gray(ctx->d_frame, W, H, stride, 3, e->gray.p, W, ctx->stream));     // MOUTH:836, NOSE:834
-                ctx->launches++;
+                if ((r = frame_to_gray(e, ctx, frame, stride, W, H, e->gray.p)) != NV_OK) return r;     // MOUTH:836, NOSE:834
                 if (e->get("detect-event") == 0) {
                     if ((r = dev_resize(ctx, e->gray, e->face_img, cv_round(W / sc.o2f), cv_round(H / sc.o2f))) != NV_OK) return r;
                     if ((r = dev_equalize(ctx, e->face_img)) != NV_OK) return r;
@@ -884,10 +900,8 @@ int ear_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double no
         e->num_frames_to_process--;
         rc = [&]() -> int {
             int r;
-            if ((r = upload_frame(ctx, frame, stride, H)) != NV_OK) return r;
             if ((r = img_ensure(e->gray, W, H)) != NV_OK) return r;
-            NV_CUDA(launch_bgr2gray(ctx->d_frame, W, H, stride, 3, e->gray.p, W, ctx->stream));             // EAR:786
-            ctx->launches++;
+            if ((r = frame_to_gray(e, ctx, frame, stride, W, H, e->gray.p)) != NV_OK) return r;             // EAR:786
             if ((r = dev_resize(ctx, e->gray, e->face_img, cv_round(W / f2o), cv_round(H / f2o))) != NV_OK) return r;
             if ((r = dev_equalize(ctx, e->face_img)) != NV_OK) return r;
             if ((r = dev_resize(ctx, e->gray, e->feat_img, cv_round(W / e2o), cv_round(H / e2o))) != NV_OK) return r;
@@ -1107,14 +1121,13 @@ extern "C" int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int 
     return NV_ERR_ARG;
 }
 
-// The face element and the tracker fed with 4:2:0 planes (a shell whose sink caps add I420 / YV12 / NV12 / NV21): same gating, tracking,
-// events and signals; view-faces is ignored — the reference defines its overlay on BGR pixels only.
+// Any of the six elements fed with 4:2:0 planes (a shell whose sink caps add I420 / YV12 / NV12 / NV21): same gating,
+// tracking, ROI arithmetic, events and signals; the view-* overlays are ignored — the reference defines them on BGR(A)
+// pixels only.
 extern "C" int nv_element_transform_frame_yuv(nv_element *e, const nv_yuv_frame *f, uint64_t pts_ns, double now_ms)
 {
     if (!e || !f || f->width <= 0 || f->height <= 0) { nv_set_error("bad argument"); return NV_ERR_ARG; }
-    if (e->kind != K_FACE && e->kind != K_TRACKER) {
-        nv_set_error("4:2:0 frames are only taken by nubofacedetector and nubotracker"); return NV_ERR_UNSUPPORTED;
-    }
+    if ((f->width & 1) || (f->height & 1)) { nv_set_error("4:2:0 frame needs even width and height"); return NV_ERR_ARG; }
     if (!e->ctx || f->width > e->ctx->max_w || f->height > e->ctx->max_h) {
         nv_ctx_destroy(e->ctx); e->ctx = nullptr;
         int rc = nv_ctx_create(e->gpu, std::max(f->width, 1920), std::max(f->height, 1080), &e->ctx);
@@ -1122,8 +1135,19 @@ extern "C" int nv_element_transform_frame_yuv(nv_element *e, const nv_yuv_frame 
     }
     NV_CUDA(cudaSetDevice(e->ctx->gpu));
     e->msg.clear(); e->signal.clear(); e->emitted = false; e->pushed = false;
-    if (e->kind == K_TRACKER) return tracker_frame(e, nullptr, f->width, f->height, 0, pts_ns, now_ms, f);
-    return face_frame(e, nullptr, f->width, f->height, 0, now_ms, f);
+    const int W = f->width, H = f->height;
+    e->yuv = f;
+    int rc = NV_ERR_ARG;
+    switch (e->kind) {
+    case K_FACE: rc = face_frame(e, nullptr, W, H, 0, now_ms, f); break;
+    case K_EYE: rc = eye_frame(e, nullptr, W, H, 0, now_ms); break;
+    case K_MOUTH:
+    case K_NOSE: rc = mouth_nose_frame(e, nullptr, W, H, 0, now_ms); break;
+    case K_EAR: rc = ear_frame(e, nullptr, W, H, 0, now_ms); break;
+    case K_TRACKER: rc = tracker_frame(e, nullptr, W, H, 0, pts_ns, now_ms, f); break;
+    }
+    e->yuv = nullptr;
+    return rc;
 }
 
 extern "C" int nv_element_get_message(nv_element *e, nv_meta_rect *out, int cap, int *n, int *pushed)

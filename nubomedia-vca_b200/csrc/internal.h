@@ -331,6 +331,10 @@ struct SrcPlanes { const uint8_t *p0, *p1, *p2; int s0, s1, s2; };    // planes 
 cudaError_t launch_face_prep_yuv(int fmt, const SrcPlanes &s, int sw, int sh, uint8_t *gray, int dw, int dh, const int *rtab,
                                  int *hist, cudaStream_t st);
 cudaError_t launch_yuv2bgr(int fmt, const SrcPlanes &s, int w, int h, uint8_t *dst, int dstride, cudaStream_t st);
+cudaError_t launch_yuv2gray(int fmt, const SrcPlanes &s, int w, int h, uint8_t *dst, int dstride, cudaStream_t st);
+// context.cu: checks a 4:2:0 frame against the ctx and makes its planes device-resident (one H2D copy when they lie in one
+// block of host memory); fills the device plane pointers
+int nv_yuv_upload(nv_ctx *ctx, const nv_yuv_frame *f, SrcPlanes *planes);
 cudaError_t launch_face_prep(const uint8_t *src, int sw, int sh, int sstride, int cn, uint8_t *gray, int dw, int dh,
                              const int *rtab, int *hist, cudaStream_t st);
 cudaError_t launch_bgr2gray(const uint8_t *src, int w, int h, int sstride, int cn, uint8_t *dst, int dstride,

@@ -290,6 +290,19 @@ k_face_prep_yuv4(SrcPlanes s, uint8_t *__restrict__ gray, int dw, int dh, int *_
     if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
 }
 
+// BGR2GRAY(cvtColor(COLOR_YUV2BGR_*)) at full resolution: the first step of the nested elements on 4:2:0 frames
+// (kmseyedetect.cpp:949 etc. after the conversion); one thread per pixel
+template <int FMT>
+__global__ void __launch_bounds__(256)
+k_yuv2gray(SrcPlanes s, int w, int h, uint8_t *__restrict__ dst, int dstride)
+{
+    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    int c3[3];
+    yuv_pixel(s, yuv_chroma<FMT>(s, x, y), x, y, c3);
+    dst[(size_t)y * dstride + x] = (uint8_t)gray_of(c3[0], c3[1], c3[2]);
+}
+
 // cvtColor(COLOR_YUV2BGR_*) alone (parity tap of the ingest path); one thread per pixel
 template <int FMT>
 __global__ void __launch_bounds__(256)
@@ -453,6 +466,15 @@ cudaError_t launch_face_prep_yuv(int fmt, const SrcPlanes &s, int sw, int sh, ui
     if (fmt == NV_FMT_NV12) return launch_prep_yuv_fmt<2>(s, sw, sh, gray, dw, dh, rtab, hist, st);
     if (fmt == NV_FMT_NV21) return launch_prep_yuv_fmt<3>(s, sw, sh, gray, dw, dh, rtab, hist, st);
     return cudaErrorInvalidValue;
+}
+cudaError_t launch_yuv2gray(int fmt, const SrcPlanes &s, int w, int h, uint8_t *dst, int dstride, cudaStream_t st)
+{
+    dim3 g = grid2d(w, h), b(32, 8);
+    if (fmt == NV_FMT_I420) k_yuv2gray<1><<<g, b, 0, st>>>(s, w, h, dst, dstride);
+    else if (fmt == NV_FMT_NV12) k_yuv2gray<2><<<g, b, 0, st>>>(s, w, h, dst, dstride);
+    else if (fmt == NV_FMT_NV21) k_yuv2gray<3><<<g, b, 0, st>>>(s, w, h, dst, dstride);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
 }
 cudaError_t launch_yuv2bgr(int fmt, const SrcPlanes &s, int w, int h, uint8_t *dst, int dstride, cudaStream_t st)
 {

@@ -201,10 +201,14 @@ def test_gpu_face_element_on_yuv_frames(cascade_dir, fmt):
         seen += len(msg)
     assert seen > 0
     e.close()
-    t = nv.Element("nubomouthdetector", 0, cascade_dir)               # the nested elements take BGR only
-    with pytest.raises(nv.NuboError):
-        t.process_yuv(synth.yuv420_planes(synth.to_yuv420(base, fmt), w, h, fmt), fmt)
-    t.close()
+    with pytest.raises(nv.NuboError):                                  # odd geometry is refused, not crashed on
+        e2 = nv.Element("nubofacedetector", 0, cascade_dir)
+        try:
+            buf = synth.to_yuv420(base, fmt)
+            y, c1 = synth.yuv420_planes(buf, w, h, fmt)[:2]
+            e2.process_yuv((y[:h - 1], c1), "NV12")
+        finally:
+            e2.close()
 
 
 @pytest.mark.gpu
@@ -274,3 +278,41 @@ def test_gpu_tracker_on_yuv_frames(fmt, cascade_dir):
         assert nobj > 0
     finally:
         ctx.close(); e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,factory,files", [
+    ("eye", "nuboeyedetector", ("haarcascade_mcs_righteye.xml", "haarcascade_mcs_lefteye.xml")),
+    ("mouth", "nubomouthdetector", ("haarcascade_mcs_mouth.xml",)),
+    ("nose", "nubonosedetector", ("haarcascade_mcs_nose.xml",)),
+    ("ear", "nuboeardetector", ("haarcascade_mcs_rightear.xml", "haarcascade_mcs_leftear.xml"))])
+def test_gpu_nested_elements_on_yuv_frames(tmp_path, cascade_dir, kind, factory, files):
+    """The nested elements (face stage + ROI cascades + temporal logic) fed with NV12 / I420 buffers: every message equals
+    the oracle-backed restatement's on cvtColor's BGR frame.  Stand-in feature models as in tests/test_gpu_elements.py."""
+    import shutil
+    from cascade_xml_util import permissive_cascade
+    from element_ref import EarRef, FeatureRef
+    d = str(tmp_path)
+    shutil.copy(os.path.join(cascade_dir, FACE_XML), os.path.join(d, FACE_XML))
+    shutil.copy(os.path.join(cascade_dir, FACE_XML), os.path.join(d, "haarcascade_profileface.xml"))
+    sizes = {"eye": (18, 12), "mouth": (25, 15), "nose": (18, 15), "ear": (12, 20)}
+    for i, name in enumerate(files):
+        permissive_cascade(os.path.join(d, name), np.random.default_rng(i), *sizes[kind])
+    oc = lambda n: O.Cascade(os.path.join(d, n))                                                # noqa: E731
+    w, h = 1280, 720
+    base = synth.frame(w, h, 3, 2, smin=0.4, smax=0.6)
+    rng = np.random.default_rng(3)
+    frames = [np.clip(base.astype(np.int16) + rng.integers(-3, 4, base.shape, dtype=np.int16), 0, 255).astype(np.uint8) for _ in range(4)]
+    total = 0
+    for fmt in ("NV12", "I420"):
+        e = nv.Element(factory, 0, d)
+        ref = EarRef(oc("haarcascade_profileface.xml"), oc(files[0]), oc(files[1])) if kind == "ear" else \
+            FeatureRef(kind, oc(FACE_XML), *[oc(f) for f in files])
+        e.set("view-" + {"eye": "eyes", "mouth": "mouths", "nose": "noses", "ear": "ears"}[kind], 1)   # ignored on 4:2:0 buffers
+        for i, f in enumerate(frames):
+            buf = synth.to_yuv420(f, fmt)
+            msg, _, _ = e.process_yuv(synth.yuv420_planes(buf, w, h, fmt), fmt, pts_ns=i * 33_000_000)
+            assert msg == ref.process(ora_bgr(buf, w, h, fmt)), (kind, fmt, i)
+            total += sum(1 for m in msg if m[1] != "face")
+        e.close()
+    assert total > 0
