@@ -666,7 +666,18 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         prof_mark(ctx, 5);
         nl += 3;
         int qcap = (int)std::min<size_t>(ctx->queue_cap, 0x7fffffff);
-        if (ctx->ps->use_tiles) {
+        static const int small_limit = [] { const char *e = getenv("NUBOVCA_SMALL_PLAN"); return e ? atoi(e) : NV_SMALL_PLAN_WINDOWS; }();
+        if (ctx->ps->use_tiles && ctx->cur_tail && P.total_windows <= small_limit && casc->meta.nstages > 1) {
+            // small plan: every window alive after stage 0 goes straight to the warp-per-window kernel (same exactness
+            // certificates as the tail it normally is, nv_cascade::tail_fast)
+            NV_CUDA(launch_alive_to_queue(ctx->ps->d_plan, P.total_rows, ctx->d_vnf, ctx->d_bits_ok, ctx->d_queue, ctx->d_counters,
+                                          qcap, st, 3));
+            prof_mark(ctx, 6);
+            NV_CUDA(launch_cascade_tail_fast(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
+                                             ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, 1, st,
+                                             8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));
+            nl += 2;
+        } else if (ctx->ps->use_tiles) {
             for (int c = 0; c < 2; c++) {
                 TileParams &tp = ctx->ps->tp[c];
                 int ntiles = c == 0 ? P.ctiles2 : P.ctiles1;

@@ -11,6 +11,9 @@
 
 #include "nubovca.h"
 
+// plans with at most this many windows (a config-1 frame, a nested ROI) skip the tile kernels: a lone tile is a 45 us
+// dependent chain, the warp-per-window kernel takes every window at once (profiles/r1_v5_summary.md)
+#define NV_SMALL_PLAN_WINDOWS 16384
 #define NV_COLBLK 128            // physical integral columns per block of the column scan
 #define NV_MAX_LEVELS 64          // level index is packed in 6 bits of a window id
 #define NV_MAX_STAGES 64
@@ -378,7 +381,7 @@ cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, con
                                 const uint2 *tail, int *counters, uint32_t *cand, int cand_cap, int16_t *depth,
                                 int stage_begin, int order_free, int nblocks, cudaStream_t st, int smem_bytes);
 cudaError_t launch_alive_to_queue(const PlanDev *plan, int total_rows, const float *vnf, const uint32_t *bits_alive,
-                                  uint2 *queue, int *counters, int queue_cap, cudaStream_t st);
+                                  uint2 *queue, int *counters, int queue_cap, cudaStream_t st, int cidx = 4);
 void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_end, TileParams *tp);
 void build_tail_stumps(nv_cascade *c);
 cudaError_t launch_cascade_tail_fast(const PlanDev *plan, const DevCascade *meta, const TailStump *tstumps, const double *tbase,

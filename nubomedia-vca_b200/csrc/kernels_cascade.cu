@@ -464,7 +464,7 @@ bool fill_stage0_params(const nv_cascade *c, const PlanDev &P, Stage0Params *sp)
 __global__ void __launch_bounds__(256)
 k_alive_to_queue(const PlanDev *__restrict__ plan, int total_rows, const float *__restrict__ vnf,
                  const uint32_t *__restrict__ bits_alive, uint2 *__restrict__ queue, int *__restrict__ counters,
-                 int queue_cap)
+                 int queue_cap, int cidx)
 {
     int lane = threadIdx.x & 31;
     int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -476,7 +476,7 @@ k_alive_to_queue(const PlanDev *__restrict__ plan, int total_rows, const float *
         uint32_t am = bits_alive[L.bofs + iy * L.nxw + cx];
         if (!am) continue;
         int base = 0;
-        if (lane == 0) base = atomicAdd(&counters[4], __popc(am));
+        if (lane == 0) base = atomicAdd(&counters[cidx], __popc(am));
         base = __shfl_sync(0xffffffffu, base, 0);
         if ((am >> lane) & 1u) {
             int ix = cx * 32 + lane, pos = base + __popc(am & ((1u << lane) - 1u));
@@ -1065,10 +1065,12 @@ cudaError_t launch_stage0_rows(const PlanDev *plan, int total_rows, const DevCas
     return cudaGetLastError();
 }
 
+// cidx: the counter the queue positions are allocated from — 4 for the generic queue kernels (they take their count
+// from counters[0]), 3 when the queue feeds k_cascade_tail_fast (its count)
 cudaError_t launch_alive_to_queue(const PlanDev *plan, int total_rows, const float *vnf, const uint32_t *bits_alive,
-                                  uint2 *queue, int *counters, int queue_cap, cudaStream_t st)
+                                  uint2 *queue, int *counters, int queue_cap, cudaStream_t st, int cidx)
 {
-    k_alive_to_queue<<<(total_rows + 7) / 8, 256, 0, st>>>(plan, total_rows, vnf, bits_alive, queue, counters, queue_cap);
+    k_alive_to_queue<<<(total_rows + 7) / 8, 256, 0, st>>>(plan, total_rows, vnf, bits_alive, queue, counters, queue_cap, cidx);
     return cudaGetLastError();
 }
 
