@@ -843,6 +843,26 @@ k_cascade_tail(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ 
 // weak classifier of the stage, records prefetched one round ahead, integer feature arithmetic, the stage sum as
 // base + sum of (left - right) over the lanes below threshold (DFMA, see add_if_lt) reduced by shuffles.
 // ------------------------------------------------------------------------------------------------
+// -DNV_TAIL_TRACE: per-phase clock64 sums of the windows that pass every stage (tools/tail_trace.py); compiles out otherwise
+#ifdef NV_TAIL_TRACE
+__device__ long long g_tail_trace[64 * 16];
+__device__ int g_tail_trace_n;
+extern "C" __attribute__((visibility("default"))) int nv_debug_tail_trace(long long *out, int cap)
+{
+    int n = 0;
+    cudaMemcpyFromSymbol(&n, g_tail_trace_n, sizeof n);
+    cudaMemcpyFromSymbol(out, g_tail_trace, sizeof(long long) * 16 * (n < cap ? n : cap));
+    int z = 0;
+    cudaMemcpyToSymbol(g_tail_trace_n, &z, sizeof z);
+    return n;
+}
+__device__ __forceinline__ long long clk_after(uint32_t dep)
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep));
+    return t;
+}
+#endif
 struct TailRec { uint4 a, b, c; };
 __device__ __forceinline__ TailRec load_tail(const TailStump *__restrict__ t, int k)
 {
@@ -863,6 +883,10 @@ k_cascade_tail_fast(const PlanDev *__restrict__ plan, const DevCascade *__restri
     uint32_t *win = s_win + warp * npatch;
     const uint32_t wsa = smem_u32(win);
     for (;;) {                                                   // windows are handed out one at a time: depths are very uneven
+#ifdef NV_TAIL_TRACE
+        long long acc_wait = 0, acc_lds = 0, acc_fp = 0, acc_red = 0, acc_thr = 0, acc_top = 0; int nrounds = 0, nst = 0;
+        long long t_begin = clk_after(0);
+#endif
         int e = 0;
         if (lane == 0) e = atomicAdd(&counters[5], 1);
         e = __shfl_sync(0xffffffffu, e, 0);
@@ -880,14 +904,25 @@ k_cascade_tail_fast(const PlanDev *__restrict__ plan, const DevCascade *__restri
             for (int r = 0; r <= wh; r++) win[r * LP + c] = __ldg(wb + (size_t)r * L.ipitch + pc);
         }
         __syncwarp();
+#ifdef NV_TAIL_TRACE
+        long long t_copied = clk_after((uint32_t)win[0]);
+        long long tp = t_copied;
+#endif
         int code = NV_DEPTH_PASS;
         for (int st = stage_begin; st < nstages; st++) {
             int k1 = meta->stage_first[st + 1];
             double tmp = 0.;
+#ifdef NV_TAIL_TRACE
+            { long long t = clk_after((uint32_t)k1); acc_top += t - tp; tp = t; nst++; }
+#endif
             for (int kb = k0; kb < k1; kb += 32) {               // 32 weak classifiers per round, one per lane
                 TailRec cur = rec;
                 int nk = (kb + 32 < k1 ? kb + 32 : k1) + lane;   // next round: same stage, or the head of the next one
                 rec = load_tail(ts, min(nk, nstumps - 1));
+#ifdef NV_TAIL_TRACE
+                { long long t = clk_after(cur.a.x ^ cur.b.x ^ cur.c.y); acc_wait += t - tp; tp = t; nrounds++; }
+                int r_dep = 0;
+#endif
                 if (kb + lane < k1) {
 #define TW(o) lds_u32(wsa + (o))
                     int nr0 = (int)(TW(cur.a.x >> 16) + TW(cur.a.y & 0xffffu) - TW(cur.a.x & 0xffffu) - TW(cur.a.y >> 16));
@@ -899,15 +934,39 @@ k_cascade_tail_fast(const PlanDev *__restrict__ plan, const DevCascade *__restri
                         r += (w12 >> 16) * r2;
                     }
 #undef TW
+#ifdef NV_TAIL_TRACE
+                    r_dep = r;
+                    { long long t = clk_after((uint32_t)r_dep); acc_lds += t - tp; tp = t; }
+#endif
                     add_if_lt(tmp, __fmul_rn(__int2float_rn(r), vnf), __uint_as_float(cur.b.z),
                               __hiloint2double((int)cur.c.y, (int)cur.c.x));
                 }
+#ifdef NV_TAIL_TRACE
+                { long long t = clk_after((uint32_t)__double2hiint(tmp)); acc_fp += t - tp; tp = t; }
+#endif
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) tmp = __dadd_rn(tmp, __shfl_xor_sync(0xffffffffu, tmp, d));
             k0 = k1;
+#ifdef NV_TAIL_TRACE
+            { long long t = clk_after((uint32_t)__double2hiint(tmp)); acc_red += t - tp; tp = t; }
+            bool failed = __dadd_rn(tbase[st], tmp) < (double)meta->stage_thr[st];
+            { long long t = clk_after((uint32_t)failed); acc_thr += t - tp; tp = t; }
+            if (failed) { code = -st; break; }
+#else
             if (__dadd_rn(tbase[st], tmp) < (double)meta->stage_thr[st]) { code = -st; break; }
+#endif
         }
+#ifdef NV_TAIL_TRACE
+        if (lane == 0 && code == NV_DEPTH_PASS) {
+            int slot = atomicAdd(&g_tail_trace_n, 1);
+            if (slot < 64) {
+                long long *o = g_tail_trace + slot * 16;
+                o[0] = tp - t_begin; o[1] = t_copied - t_begin; o[2] = acc_top; o[3] = acc_wait; o[4] = acc_lds; o[5] = acc_fp;
+                o[6] = acc_red; o[7] = acc_thr; o[8] = nrounds; o[9] = nst;
+            }
+        }
+#endif
         if (lane == 0) {
             if (depth) depth[L.wofs + iy * L.nx + ix] = (int16_t)code;
             if (code == NV_DEPTH_PASS) {
