@@ -214,11 +214,26 @@ NV_API int nv_element_get_property(nv_element *e, const char *name, long *value)
 NV_API int nv_element_property_info(nv_element *e, int index, const char **name, long *minimum, long *maximum, long *default_value);
 /* sink_event: a queued upstream "message" carrying face rectangles (kmseyedetect.cpp:192-218,680-724),
  * or the "motion" event the face element waits for in detect-event mode (kmsfacedetect.cpp:698-707) */
+/* General form: one custom downstream event as the element's sink pad saw it.  The reference queues a copy of EVERY such
+ * event (kmsfacedetect.cpp:258-267, kmseyedetect.cpp:198-209) and __receive_event pops exactly one per frame, whatever it
+ * holds (kmsfacedetect.cpp:711-755, kmseyedetect.cpp:726-764): a message without a "timestamp" structure is dropped unread;
+ * the face element re-arms only on a "motion" structure; eye / mouth / nose keep the sub-structures whose "type" is "face"
+ * and accept the message if it holds any structure field.  The ear element and the tracker have no sink_event handler. */
+typedef struct {
+    int has_timestamp;        /* a "timestamp" field of structure type                                   */
+    int has_motion;           /* a field named "motion" of structure type (kmsfacedetect.cpp:698-707)    */
+    int n_other;              /* further structure-typed fields that are neither of the above nor faces  */
+    const nv_rect *faces;     /* sub-structures whose "type" string is "face", in field order            */
+    int nfaces;
+} nv_event;
+NV_API int nv_element_push_event(nv_element *e, const nv_event *ev);
+/* shorthands: a face message {timestamp, faces...} / a motion message {timestamp, motion} */
 NV_API int nv_element_push_faces_event(nv_element *e, const nv_rect *faces, int n);
 NV_API int nv_element_push_motion_event(nv_element *e);
 /* one video buffer.  frame: BGR (detectors) or BGRA (tracker), modified in place only when a view-*
  * property asks for it (cvRectangle / cv::circle restated pixel-exactly, see nv_debug_draw_*).  now_ms < 0 uses gettimeofday for
- * the events-ms rate limit; the tracker's MHI timestamp is pts_ns / 1e6 unless now_ms >= 0. */
+ * the events-ms rate limit.  The tracker's motion-history timestamp is pts_ns / 1e6 ms (the reference uses clock(), the
+ * process's CPU time, gstnubotracker.cpp:349 — not a media clock; deliberate deviation). */
 NV_API int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int width, int height, int stride_bytes,
                                          uint64_t pts_ns, double now_ms);
 /* Any of the six elements on 4:2:0 planes (see nv_face_detect_yuv / nv_tracker_process_yuv; the nested elements take
@@ -241,9 +256,24 @@ NV_API int nv_debug_draw_rectangle(uint8_t *frame, int width, int height, int st
  * (kmseyedetect.cpp:1081,1095 use thickness 4). */
 NV_API int nv_debug_draw_circle(uint8_t *frame, int width, int height, int stride_bytes, int channels, int cx, int cy,
                                 int radius, int thickness, int b, int g, int r);
+/* tests: replace gettimeofday() in the events-ms rate limit and the activate-events setter (kmsfacedetect.cpp:228-236,
+ * 556-560) by a fixed value; negative restores the real clock.  Process-wide. */
+NV_API void nv_debug_set_wall_clock_ms(double ms);
 NV_API int nv_debug_track_faces(const nv_rect *prev, const int *prev_ids, int nprev, int next_id, const nv_rect *cur,
                                 int ncur, int track_threshold, int pos_threshold, int area_threshold, nv_rect *out,
                                 int *out_ids, int cap, int *n, int *next_id_out);
+/* __merge_eyes_current_frame (kmseyedetect.cpp:778-862), in place on `eyes` (*n = resulting count); eye_r_same != 0 is the
+ * right eye's call shape, where the eye_r argument IS the list being merged (kmseyedetect.cpp:1016) */
+NV_API int nv_debug_merge_eyes_current_frame(const nv_rect *face_bb, const nv_rect *eye_r, int n_eye_r, int eye_r_same, nv_rect *eyes,
+                                             int n_eyes, int scale, int eye_left, int cap, int *n);
+/* kind 0: __merge_eyes_consecutives_frames (kmseyedetect.cpp:864-900), 1: __merge_mouths_consecutives_frames
+ * (kmsmouthdetect.cpp:750-796), 2: __merge_noses_consecutives_frames (kmsnosedetect.cpp:745-790) */
+NV_API int nv_debug_merge_consecutive(int kind, const nv_rect *cur, int ncur, const nv_rect *prev, int nprev, const nv_rect *face,
+                                      int scale, nv_rect *out, int cap, int *n);
+/* transform_2_global_coordinates (kmseyedetect.cpp:902-913), in place */
+NV_API int nv_debug_eye_to_global(nv_rect *eyes, int n, const nv_rect *face, int scale);
+/* __join_objects / __merge / calc_dist (gstnubotracker.cpp:119-200), in place (*n = resulting count) */
+NV_API int nv_debug_join_objects(nv_rect *rects, int n_in, int min_area, long max_area, int distance, int *n);
 
 /* ---- device-side timing (bench.py): CUDA events on the ctx's own stream.  With profiling on, every
  *      pipeline stage of a detect call is bracketed by events; times are read after collect.

@@ -1226,6 +1226,17 @@ static void trk_join_objects(std::vector<nv_rect> &v, int min_area, long max_are
     }
 }
 
+// host-logic tap: __join_objects (TRK:171-200) on an explicit list, in place
+extern "C" int nv_debug_join_objects(nv_rect *rects, int n_in, int min_area, long max_area, int distance, int *n)
+{
+    if (n_in < 0 || (n_in > 0 && !rects) || !n) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    std::vector<nv_rect> v(rects, rects + n_in);
+    trk_join_objects(v, min_area, max_area, distance);
+    for (size_t i = 0; i < v.size(); i++) rects[i] = v[i];
+    *n = (int)v.size();
+    return NV_OK;
+}
+
 extern "C" int nv_tracker_reset(nv_ctx *ctx)
 {
     if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }

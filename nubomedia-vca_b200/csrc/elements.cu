@@ -34,8 +34,10 @@ struct DevImg {
 
 inline int cv_round(double v) { return (int)lrint(v); }
 inline int cv_roundf(float v) { return (int)lrintf(v); }
+double g_wall_override_ms = -1;           // nv_debug_set_wall_clock_ms: tests inject the gettimeofday() of FACE:228-236,556-560
 inline double wall_ms()
 {
+    if (g_wall_override_ms >= 0) return g_wall_override_ms;
     struct timeval t;
     gettimeofday(&t, nullptr);
     return t.tv_sec * 1000.0 + t.tv_usec / 1000.0;
@@ -55,8 +57,10 @@ struct nv_element {
     nv_cascade *c_face = nullptr, *c_a = nullptr, *c_b = nullptr;     // face / (right eye, mouth, nose, "lear") / (left eye, "rear")
     // shared detector state (FACE:87-126 and the analogous priv structs)
     int num_frame = 0, num_frames_to_process = 0, num_iter = 0;
-    std::deque<std::vector<nv_rect>> events_queue;                     // queued upstream face messages
-    std::deque<int> motion_queue;
+    // every custom downstream event the sink pad saw, in arrival order (the reference queues a copy of each one,
+    // FACE:258-267, EYE:198-209): what __receive_event reads from a message, nothing more
+    struct Event { bool has_timestamp, has_motion; int n_other; std::vector<nv_rect> faces; };
+    std::deque<Event> events_queue;
     double time_events_ms = 0;
     // face
     std::vector<TrackedFace> faces_tracked;  int faces_id = 0;  int frames_with_no_detection = 0;
@@ -472,14 +476,32 @@ void maybe_emit(nv_element *e, const std::string &payload, bool any, double now_
     }
 }
 
-// __receive_event for eye/mouth/nose (EYE:726-764): pops one queued upstream message, keeps its faces
+// __receive_event for eye/mouth/nose (EYE:726-764, MOUTH:712-748, NOSE:707-743): pops ONE queued message whatever it is.
+// Without a "timestamp" structure it is dropped unread (__get_timestamp fails, EYE:745-750); otherwise
+// __get_event_message (EYE:680-724) clears the face list, keeps the sub-structures whose type is "face" and reports
+// success if the message held any structure-typed field at all.
 bool receive_faces_event(nv_element *e)
+{
+    if (e->get("detect-event") == 0) return true;                  // the queue is left alone (EYE:734)
+    if (e->events_queue.empty()) return false;
+    nv_element::Event ev = std::move(e->events_queue.front());
+    e->events_queue.pop_front();
+    if (!ev.has_timestamp) return false;
+    e->faces = ev.faces;
+    if (ev.faces.empty() && ev.n_other == 0 && !ev.has_motion) return false;
+    e->num_frames_to_process = 10 / (5 - (int)e->get("process-x-every-4-frames"));   // NUM_FRAMES_TO_PROCESS / (5 - p)
+    return true;
+}
+// __receive_event of the face element (FACE:711-755): pops ONE queued message; only one that carries a timestamp and a
+// "motion" structure (FACE:698-707) re-arms the detector — any other message uses up this frame's pop
+bool receive_motion_event(nv_element *e)
 {
     if (e->get("detect-event") == 0) return true;
     if (e->events_queue.empty()) return false;
-    e->faces = e->events_queue.front();          // __get_event_message clears faces, then fills (EYE:691,706-718)
+    nv_element::Event ev = std::move(e->events_queue.front());
     e->events_queue.pop_front();
-    e->num_frames_to_process = 10 / (5 - (int)e->get("process-x-every-4-frames"));   // NUM_FRAMES_TO_PROCESS / (5 - p)
+    if (!(ev.has_timestamp && ev.has_motion)) return false;
+    e->num_frames_to_process = 10;                                  // NUM_FRAMES_TO_PROCESS
     return true;
 }
 
@@ -523,12 +545,7 @@ int face_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double n
 {
     long w2p = e->get("width-to-process");
     if (w2p <= 0) { nv_set_error("width-to-process=0 divides by zero in the reference (FACE:304)"); return NV_ERR_ARG; }
-    // __receive_event (FACE:722-755): detect-event waits for an upstream "motion" event
-    bool got = true;
-    if (e->get("detect-event") != 0) {
-        got = !e->motion_queue.empty();
-        if (got) { e->motion_queue.pop_front(); e->num_frames_to_process = 10; }
-    }
+    bool got = receive_motion_event(e);
     int rc = NV_OK;
     if (got || e->num_frames_to_process > 0) {
         e->num_iter++;
@@ -621,6 +638,12 @@ void merge_eyes_current_frame(const nv_rect &face_bb, const std::vector<nv_rect>
 }
 
 // EYE:864-900 / the common shape of MOUTH:750-796 and NOSE:745-790 (those transform while merging)
+// transform_2_global_coordinates (EYE:902-913)
+void to_global(std::vector<nv_rect> &v, const nv_rect &fc, int scale)
+{
+    for (auto &q : v) { q.x = (fc.x + q.x) * scale; q.y = (fc.y + q.y) * scale; q.width = (q.width - 1) * scale; q.height = (q.height - 1) * scale; }
+}
+
 std::vector<nv_rect> merge_consecutive(std::vector<nv_rect> &cur, const std::vector<nv_rect> &prev, double limit,
                                        bool local, const nv_rect &face, int scale)
 {
@@ -710,10 +733,8 @@ int eye_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double no
                 for (size_t fi = 0; fi < e->faces.size(); fi++) {
                     nv_rect fr = rois[2 * fi], fl = rois[2 * fi + 1];
                     std::vector<nv_rect> eye_r = std::move(jobs[2 * fi].out), eye_l = std::move(jobs[2 * fi + 1].out);
-                    for (auto *v : {&eye_r, &eye_l}) {                      // transform_2_global_coordinates, EYE:902-913
-                        const nv_rect &fc = v == &eye_r ? fr : fl;
-                        for (auto &q : *v) { q.x = (fc.x + q.x) * iscale; q.y = (fc.y + q.y) * iscale; q.width = (q.width - 1) * iscale; q.height = (q.height - 1) * iscale; }
-                    }
+                    to_global(eye_r, fr, iscale);                           // EYE:1010-1011
+                    to_global(eye_l, fl, iscale);
                     if (!eye_r.empty()) {
                         merge_eyes_current_frame(fr, &eye_r, eye_r, iscale, false);
                         auto m = merge_consecutive(eye_r, e->feat_a, 7, false, fr, iscale);
@@ -943,7 +964,9 @@ int tracker_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, uint6
     p.max_area = e->get("set_max_area"); p.distance = (int)e->get("set_distance");
     std::vector<nv_rect> out(16384);
     int n = 0;
-    double ts = now_ms >= 0 ? now_ms : (double)pts_ns / 1e6;        // the reference uses clock() in ms (TRK:349)
+    // The reference stamps the motion history with clock() in ms (TRK:349): CPU time of the PROCESS, which advances with
+    // the work of every other element in it.  The buffer's presentation time is used in its place (deliberate deviation).
+    double ts = (double)pts_ns / 1e6;
     int rc = yuv ? nv_tracker_process_yuv(e->ctx, yuv, ts, &p, out.data(), (int)out.size(), &n)
                  : nv_tracker_process(e->ctx, frame, W, H, stride, ts, &p, out.data(), (int)out.size(), &n);
     if (rc != NV_OK) n = 0;
@@ -1083,18 +1106,27 @@ extern "C" int nv_element_property_info(nv_element *e, int index, const char **n
     return NV_OK;
 }
 
+extern "C" int nv_element_push_event(nv_element *e, const nv_event *ev)
+{
+    if (!e || !ev || ev->nfaces < 0 || (ev->nfaces > 0 && !ev->faces) || ev->n_other < 0) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    if (e->kind == K_EAR || e->kind == K_TRACKER) return NV_OK;        // no sink_event handler of their own: events pass through
+    nv_element::Event q;
+    q.has_timestamp = ev->has_timestamp != 0; q.has_motion = ev->has_motion != 0; q.n_other = ev->n_other;
+    if (ev->nfaces > 0) q.faces.assign(ev->faces, ev->faces + ev->nfaces);
+    e->events_queue.push_back(std::move(q));
+    return NV_OK;
+}
+
 extern "C" int nv_element_push_faces_event(nv_element *e, const nv_rect *faces, int n)
 {
-    if (!e || (n > 0 && !faces) || n < 0) { nv_set_error("bad argument"); return NV_ERR_ARG; }
-    e->events_queue.emplace_back(faces, faces + n);
-    return NV_OK;
+    nv_event ev = {1, 0, 0, faces, n};
+    return nv_element_push_event(e, &ev);
 }
 
 extern "C" int nv_element_push_motion_event(nv_element *e)
 {
-    if (!e) { nv_set_error("null argument"); return NV_ERR_ARG; }
-    e->motion_queue.push_back(1);
-    return NV_OK;
+    nv_event ev = {1, 1, 0, nullptr, 0};
+    return nv_element_push_event(e, &ev);
 }
 
 extern "C" int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int width, int height, int stride_bytes,
@@ -1206,3 +1238,39 @@ extern "C" int nv_debug_track_faces(const nv_rect *prev, const int *prev_ids, in
     if (next_id_out) *next_id_out = next_id;
     return NV_OK;
 }
+
+// host-logic taps (tests/test_ref_glue.py fuzzes them against the reference's own functions, oracle/_ref)
+extern "C" int nv_debug_merge_eyes_current_frame(const nv_rect *face_bb, const nv_rect *eye_r, int n_eye_r, int eye_r_same, nv_rect *eyes,
+                                                 int n_eyes, int scale, int eye_left, int cap, int *n)
+{
+    if (!face_bb || !n || n_eyes < 0 || n_eye_r < 0 || (n_eyes > 0 && !eyes) || (n_eye_r > 0 && !eye_r)) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    std::vector<nv_rect> er(eye_r, eye_r + n_eye_r), ev(eyes, eyes + n_eyes);
+    merge_eyes_current_frame(*face_bb, eye_r_same ? &ev : &er, ev, scale, eye_left != 0);
+    int m = std::min((int)ev.size(), cap);
+    for (int i = 0; i < m; i++) eyes[i] = ev[i];
+    *n = (int)ev.size();
+    return NV_OK;
+}
+
+extern "C" int nv_debug_merge_consecutive(int kind, const nv_rect *cur, int ncur, const nv_rect *prev, int nprev, const nv_rect *face,
+                                          int scale, nv_rect *out, int cap, int *n)
+{
+    if (kind < 0 || kind > 2 || !face || !n || ncur < 0 || nprev < 0 || (ncur > 0 && !cur) || (nprev > 0 && !prev)) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    std::vector<nv_rect> c(cur, cur + ncur), p(prev, prev + nprev);
+    auto r = merge_consecutive(c, p, kind == 0 ? 7 : kind == 1 ? 4 : 6, kind != 0, *face, scale);   // DEFAULT_EUCLIDEAN_DIS: EYE:43, MOUTH:25, NOSE:43
+    int m = std::min((int)r.size(), cap);
+    for (int i = 0; i < m; i++) out[i] = r[i];
+    *n = (int)r.size();
+    return NV_OK;
+}
+
+extern "C" int nv_debug_eye_to_global(nv_rect *eyes, int n, const nv_rect *face, int scale)
+{
+    if (!face || n < 0 || (n > 0 && !eyes)) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    std::vector<nv_rect> v(eyes, eyes + n);
+    to_global(v, *face, scale);
+    for (int i = 0; i < n; i++) eyes[i] = v[i];
+    return NV_OK;
+}
+
+extern "C" void nv_debug_set_wall_clock_ms(double ms) { g_wall_override_ms = ms; }

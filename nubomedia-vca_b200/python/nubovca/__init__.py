@@ -58,6 +58,10 @@ class TrackerParams(C.Structure):
     _fields_ = [("threshold", C.c_int), ("min_area", C.c_int), ("max_area", C.c_long), ("distance", C.c_int)]
 
 
+class EventDesc(C.Structure):
+    _fields_ = [("has_timestamp", C.c_int), ("has_motion", C.c_int), ("n_other", C.c_int), ("faces", C.c_void_p), ("nfaces", C.c_int)]
+
+
 class LevelInfo(C.Structure):
     _fields_ = [("scale", C.c_float), ("width", C.c_int), ("height", C.c_int), ("ystep", C.c_int), ("nx", C.c_int),
                 ("ny", C.c_int)]
@@ -98,6 +102,12 @@ _SIGS = {
     "nv_element_property_info": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]),
     "nv_element_push_faces_event": (_i, [_vp, _vp, _i]),
     "nv_element_push_motion_event": (_i, [_vp]),
+    "nv_element_push_event": (_i, [_vp, _vp]),
+    "nv_debug_set_wall_clock_ms": (None, [C.c_double]),
+    "nv_debug_merge_eyes_current_frame": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _ip]),
+    "nv_debug_merge_consecutive": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _ip]),
+    "nv_debug_eye_to_global": (_i, [_vp, _i, _vp, _i]),
+    "nv_debug_join_objects": (_i, [_vp, _i, _i, C.c_long, _i, _ip]),
     "nv_element_transform_frame_ip": (_i, [_vp, _vp, _i, _i, _i, C.c_uint64, C.c_double]),
     "nv_element_transform_frame_yuv": (_i, [_vp, C.POINTER(YuvFrame), C.c_uint64, C.c_double]),
     "nv_element_get_message": (_i, [_vp, _vp, _i, _ip, _ip]),
@@ -270,6 +280,12 @@ class Element:
 
     def push_motion(self):
         _check(_lib.nv_element_push_motion_event(self.handle), "nv_element_push_motion_event")
+
+    def push_event(self, faces=(), has_timestamp=True, has_motion=False, n_other=0):
+        """One custom downstream event as the sink pad saw it (nv_event)."""
+        r = np.ascontiguousarray(np.asarray(faces, np.int32).reshape(-1, 4))
+        ev = EventDesc(int(has_timestamp), int(has_motion), int(n_other), r.ctypes.data if len(r) else None, len(r))
+        _check(_lib.nv_element_push_event(self.handle, C.byref(ev)), "nv_element_push_event")
 
     def process(self, frame, pts_ns: int = 0, now_ms: float = -1.0):
         """One buffer through transform_frame_ip.  Returns (message [(name, type, x, y, w, h)], pushed, signal or None)."""
