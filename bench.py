@@ -306,7 +306,7 @@ def aux_other_configs(nv, local, world):
 
     def trk():
         st["i"] += 1
-        return e.process(seq[st["i"] % len(seq)], now_ms=33.3 * st["i"])
+        return e.process(seq[st["i"] % len(seq)], pts_ns=33_300_000 * st["i"])
     out["cfg4_tracker_1280x720_bgra"] = {"frames_per_s": _timeit(trk, 300)}
     e.close()
     if cv2 is not None:
@@ -335,9 +335,9 @@ def aux_other_configs(nv, local, world):
             fr = frames_of(i)
             for j in range(n):
                 if yuv:
-                    els[i].process_yuv(fr[j % len(fr)], yuv, now_ms=33.3 * (j + 1))
+                    els[i].process_yuv(fr[j % len(fr)], yuv, pts_ns=33_300_000 * (j + 1))
                 else:
-                    els[i].process(fr[j % len(fr)], now_ms=33.3 * (j + 1))
+                    els[i].process(fr[j % len(fr)], pts_ns=33_300_000 * (j + 1))
         for i in range(nstreams):
             loop(i, 3)
         th = [threading.Thread(target=loop, args=(i, nframes)) for i in range(nstreams)]

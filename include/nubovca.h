@@ -246,6 +246,9 @@ NV_API int nv_element_transform_frame_yuv(nv_element *e, const nv_yuv_frame *fra
  * signal payload ("x:..,y:..,width:..,height:..;" repeated) if the signal fired */
 NV_API int nv_element_get_message(nv_element *e, nv_meta_rect *out, int cap, int *n, int *pushed);
 NV_API int nv_element_get_signal(nv_element *e, char *buf, int cap, int *emitted);
+/* top-level shape of that event: structure name ("message"; "noses" for the nose element, kmsnosedetect.cpp:223) and whether
+ * it starts with timestamp = time{pts} (every element but the nose one); sub-structure i is set under field name "i" */
+NV_API int nv_element_get_message_info(nv_element *e, char *name16, int *has_timestamp);
 /* host-logic taps for unit tests: Faces::track_faces (Faces.cpp:78-153) on explicit lists */
 /* cvRectangle(img, (x0, y0), (x1, y1), Scalar(b, g, r, 0), 3, 8, 0) on a 3- or 4-channel host frame: the drawing the
  * view-faces / view-mouths / view-noses / view-ears properties and the tracker's visual mode perform in place

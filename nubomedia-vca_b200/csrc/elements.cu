@@ -1047,6 +1047,11 @@ extern "C" int nv_element_create(const char *factory_name, int gpu, const char *
         e->c_face = try_load(e->dir, "haarcascade_profileface.xml");
         e->c_a = try_load(e->dir, "haarcascade_mcs_rightear.xml");      // lecascade <- LEAR_CONF_FILE = mcs_rightear (EAR:30-31,179,186)
         e->c_b = try_load(e->dir, "haarcascade_mcs_leftear.xml");       // recascade <- REAR_CONF_FILE = mcs_leftear
+        // kms_ear_detect_init (EAR:930-960) starts view_ears at -1 and never sets events_ms (zero-filled private struct)
+        for (auto &p : e->props) {
+            if (!strcmp(p.name, "view-ears")) p.value = p.def = -1;
+            if (!strcmp(p.name, "events-ms")) p.value = p.def = 0;
+        }
         break;
     case K_TRACKER:
         add_props(e, {{"set_threshold", 0, 255, 20, 0}, {"set_min_area", 0, 10000, 50, 0}, {"set_max_area", 0, 300000, 30000, 0},
@@ -1189,6 +1194,16 @@ extern "C" int nv_element_get_message(nv_element *e, nv_meta_rect *out, int cap,
     if (out && m > 0) memcpy(out, e->msg.data(), (size_t)m * sizeof(nv_meta_rect));
     if (n) *n = m;
     if (pushed) *pushed = e->pushed ? 1 : 0;
+    return NV_OK;
+}
+
+// top-level shape of the downstream event: every element builds "message" with a "timestamp" = time{pts} structure
+// (FACE:196-201, EYE:237-242, MOUTH:215-220, EAR:210-215) except the nose element: "noses", no timestamp (NOSE:223)
+extern "C" int nv_element_get_message_info(nv_element *e, char *name16, int *has_timestamp)
+{
+    if (!e) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    if (name16) snprintf(name16, 16, "%s", e->kind == K_NOSE ? "noses" : "message");
+    if (has_timestamp) *has_timestamp = e->kind == K_NOSE ? 0 : 1;
     return NV_OK;
 }
 

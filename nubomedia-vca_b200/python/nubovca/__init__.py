@@ -112,6 +112,7 @@ _SIGS = {
     "nv_element_transform_frame_yuv": (_i, [_vp, C.POINTER(YuvFrame), C.c_uint64, C.c_double]),
     "nv_element_get_message": (_i, [_vp, _vp, _i, _ip, _ip]),
     "nv_element_get_signal": (_i, [_vp, C.c_char_p, _i, _ip]),
+    "nv_element_get_message_info": (_i, [_vp, C.c_char_p, _ip]),
     "nv_debug_track_faces": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _ip, _ip]),
     "nv_stage_name": (C.c_char_p, [_i]),
     "nv_ctx_set_profile": (_i, [_vp, _i]),

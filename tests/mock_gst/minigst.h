@@ -62,6 +62,7 @@ inline gchar *g_strdup(const gchar *s) { return s ? strdup(s) : NULL; }
 inline void g_free(gpointer p) { free(p); }
 inline int g_strcmp0(const char *a, const char *b) { return !a ? -(a != b) : !b ? 1 : strcmp(a, b); }
 gchar *g_strconcat(const gchar *first, ...);
+#define g_snprintf snprintf
 inline gchar *g_mkdtemp(gchar *tmpl) { return mkdtemp(tmpl); }
 inline int g_remove(const gchar *path) { return remove(path); }
 #define g_return_val_if_fail(expr, val) do { if (!(expr)) return (val); } while (0)

@@ -182,8 +182,8 @@ def test_tracker_element(cdir):
     st = O.TrackerState(640, 360)
     e.set("activate-events", 1); e.set("events-ms", 0)
     for i, f in enumerate(frames):
-        msg, pushed, sig = e.process(f, now_ms=1e15 + 40.0 * i)
-        exp, _, _ = st.process(f, 1e15 + 40.0 * i)
+        msg, pushed, sig = e.process(f, pts_ns=40_000_000 * (i + 1), now_ms=1e15 + 40.0 * i)   # MHI time = buffer PTS
+        exp, _, _ = st.process(f, 40.0 * (i + 1))
         assert [list(m[2:]) for m in msg] == exp.tolist(), i
         assert (sig is not None) == (len(exp) > 0)
     e.close()
@@ -250,7 +250,7 @@ def test_view_properties_draw_into_the_frame(cdir):
     drawn = 0
     for i, fr in enumerate(seq):
         g = fr.copy()
-        msg, _, _ = e.process(g, now_ms=1e15 + 40.0 * i)
+        msg, _, _ = e.process(g, pts_ns=40_000_000 * (i + 1))
         exp = fr.copy()
         for m in msg:
             cv2.rectangle(exp, (m[2], m[3]), (m[2] + m[4], m[3] + m[5]), (0, 0, 255, 0), 3, 8, 0)

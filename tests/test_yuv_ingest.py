@@ -272,8 +272,8 @@ def test_gpu_tracker_on_yuv_frames(fmt, cascade_dir):
             exp, _, _ = st.process(bgra, ts)
             assert got.shape == exp.shape and (got == exp).all(), i
             nobj += len(exp)
-            msg, pushed, _ = e.process_yuv(planes, fmt, now_ms=1e15 + ts)
-            eexp, _, _ = est.process(bgra, 1e15 + ts)
+            msg, pushed, _ = e.process_yuv(planes, fmt, pts_ns=int(ts) * 1_000_000)
+            eexp, _, _ = est.process(bgra, ts)
             assert [list(m[2:]) for m in msg] == eexp.tolist() and not pushed, i
         assert nobj > 0
     finally:
