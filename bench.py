@@ -41,9 +41,40 @@ WORKLOAD = "cfg3: 1920x1080 BGR, nubofacedetector hot block, processing width 19
 METRIC = "1080p face-cascade frames/s"
 
 
+def load_synth():
+    """nubovca/synth.py by file path: importing the package would dlopen libnubovca.so, which the reference arm must not."""
+    import importlib.util
+    if "nubovca_synth_standalone" in sys.modules:
+        return sys.modules["nubovca_synth_standalone"]
+    spec = importlib.util.spec_from_file_location("nubovca_synth_standalone",
+                                                  os.path.join(ROOT, "nubomedia-vca_b200", "python", "nubovca", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["nubovca_synth_standalone"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_frames(n, rank):
-    from nubovca import synth
+    synth = load_synth()
     return [synth.frame(W, H, 6, 3 + 100 * rank + i) for i in range(n)]
+
+
+# (c) one `config` for both arms (the driver compares them); everything arm-specific goes to `config_detail`
+CONFIG = {"workload": WORKLOAD,
+          "frames": "distinct synthetic 1920x1080 BGR frames (6 procedural faces each, seeds 3 + 100*rank + i), cycled",
+          "l2": "no flush needed: a step's working set (8 per-stream contexts x ~130 MB of integral images, plus the frames) exceeds the 126 MB L2"}
+
+
+def rect_set(r):
+    return sorted(tuple(int(v) for v in row) for row in r)
+
+
+def cv2_rects(frames):
+    """The CPU arm's rectangles for `frames` (cv2 4.13 through the reference's call sequence), untimed."""
+    import cv2
+    cv2.setNumThreads(os.cpu_count() or 1)
+    cc = cv2.CascadeClassifier(FACE_XML)
+    return [rect_set(cpu_face_step(cv2, cc, f)) for f in frames]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -99,13 +130,13 @@ def cpu_baseline(frames, budget_s=20.0, max_frames=40, warm=1):
 
 
 _CFG5_WORKER = r"""
-import sys, time
-sys.path.insert(0, sys.argv[1])
+import sys, time, importlib.util
 import cv2, numpy as np
-from nubovca import synth
+spec = importlib.util.spec_from_file_location("synth", sys.argv[1] + "/nubovca/synth.py")
+synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
 cv2.setNumThreads(1)
 cc = cv2.CascadeClassifier(sys.argv[2])
-frames = [synth.frame(1280, 720, 3, 1000 + int(sys.argv[3]) * 4 + i) for i in range(2)]
+frames = [synth.frame(1280, 720, 3, 1000 + int(sys.argv[3]) * 2 + i) for i in range(2)]      # streams 2w, 2w+1 of SURVEY 8(d)
 def step(f):                                         # kmsfacedetect.cpp:805-811 at width-to-process 640
     g = cv2.equalizeHist(cv2.cvtColor(cv2.resize(f, (640, 360), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY))
     return cc.detectMultiScale(g, scaleFactor=1.25, minNeighbors=3, flags=0, minSize=(32, 18))
@@ -138,7 +169,7 @@ def cpu_cfg5(seconds=6.0):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    frames = make_frames(min(4, max(1, args.steps)), 0)
+    frames = make_frames(min(8, max(1, args.steps)), 0)
     per = []
     base = None
     try:
@@ -167,7 +198,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32 integrals, f32 features, f64 stage sums", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": 1}, "cpu_baseline": base,
+        "config": CONFIG, "config_detail": {"frames_per_step": 1}, "cpu_baseline": base,
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 
@@ -475,6 +506,21 @@ def main():
     barrier()
     clocks = sampler.stop()                       # sampled across both timed regions
     assert all((a == b).all() for a, b in zip(out_d, out))
+    # (a) the GPU's rectangles for this rank's frames against the CPU arm's (cv2, the reference's call sequence) in this run
+    parity = None
+    if rank == 0:
+        try:
+            exp = cv2_rects(frames)
+            same = [rect_set(o) == e for o, e in zip(out, exp)]
+            parity = {"frames": len(same), "identical": int(sum(same)), "rectangles": int(sum(len(e) for e in exp)),
+                      "against": "cv2 %s, kmsfacedetect.cpp:805-811 call sequence, same frames, rectangle sets compared exactly" % __import__("cv2").__version__}
+        except ImportError:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle as O
+            oc = O.Cascade(FACE_XML)
+            exp = [rect_set(O.face_process(f, oc, **PARAMS)[0]) for f in frames[:2]]
+            same = [rect_set(o) == e for o, e in zip(out, exp)]
+            parity = {"frames": len(same), "identical": int(sum(same)), "rectangles": int(sum(len(e) for e in exp)), "against": "oracle/nubo_oracle.c (cv2 not importable)"}
 
     # isolated per-stage times: the same step with ONE stream in flight (no interleaving between contexts)
     iso_acc = {}
@@ -489,10 +535,10 @@ def main():
     # width-to-process 640, host frames through the C ABI; streams@30fps = frames/s / 30
     aux = None
     if not args.no_aux:
-        from nubovca import synth
+        synth = load_synth()
         S5 = 32
         mine = shard.streams_of_rank(S5 * world, world, rank)
-        f5 = [synth.frame(1280, 720, 3, 1000 + s) for s in mine[:4]]
+        f5 = [synth.frame(1280, 720, 3, 1000 + s) for s in mine]          # stream i uses seed 1000 + i
         h5 = [torch.from_numpy(f).pin_memory().numpy() for f in f5]
         c5 = [nv.Context(local, 1280, 720) for _ in mine]
         p5 = dict(width_to_process=640, scale_factor=1.25, min_neighbors=3, min_size=None)
@@ -500,7 +546,7 @@ def main():
         def run5(submit):
             def step5():
                 for i, c in enumerate(c5):
-                    submit(c, i % len(h5))
+                    submit(c, i)
                 return [c.face_collect() for c in c5]
             for _ in range(3):
                 step5()
@@ -563,6 +609,53 @@ def main():
             nat["host_threads_per_gpu"] = nthr
             nat["streams_per_gpu_in_flight"] = S5
             aux["native_host_threads"] = nat
+        # the per-GPU ingest rate the figures above imply, and the same streams with the frames already in HBM: the compute
+        # ceiling of a GPU at config 5, which separates "the kernels" from "getting the frames there" at every N
+        aux["h2d_gb_per_s_per_gpu"] = {"bgr_python": fps5 / world * 1280 * 720 * 3 / 1e9, "nv12_python": fps5y / world * 1280 * 720 * 1.5 / 1e9}
+        if "native_host_threads" in aux:
+            for k_ in ("bgr", "nv12"):
+                aux["h2d_gb_per_s_per_gpu"][k_ + "_native"] = aux["native_host_threads"][k_]["frames_per_s"] / world * \
+                    aux["native_host_threads"][k_]["h2d_bytes_per_frame"] / 1e9
+        c5 = [nv.Context(local, 1280, 720) for _ in mine]
+        d5 = [torch.from_numpy(f).cuda() for f in f5]
+        fps5d = run5(lambda c, i: c.face_submit_device(casc, d5[i].data_ptr(), 1280, 720, 3 * 1280, **p5))
+        aux["device_resident"] = {"frames_per_s": fps5d, "streams_at_30fps": fps5d / 30.0,
+                                  "note": "same 32 streams per GPU, frames already in HBM (nv_face_submit_device): no ingest"}
+        for c in c5:
+            c.close()
+        del d5
+        if rank == 0 and world == 1 and os.path.exists(tool):
+            # the element's own call shape: one synchronous nv_face_detect per buffer from T host threads, each
+            # with its own streams, on PAGEABLE frames (what GStreamer hands an element), next to page-locked and
+            # cudaHostRegister'ed memory.  C ABI, native threads, wall clock, copies included.
+            import tempfile
+            shaped = {}
+            with tempfile.TemporaryDirectory(prefix="nubovca_shape_") as td:
+                def blob(name, arrs):
+                    path_ = os.path.join(td, name)
+                    with open(path_, "wb") as fh:
+                        for b_ in arrs:
+                            fh.write(np.ascontiguousarray(b_).tobytes())
+                    return path_, len(arrs)
+                cases = {"cfg5_1280x720_w2p640": (blob("c5.raw", f5), ["--width", "1280", "--height", "720", "--width-to-process", "640"], 40),
+                         "cfg1_640x480_defaults": (blob("c1.raw", [synth.frame(640, 480, 4, 1)]), ["--width", "640", "--height", "480", "--width-to-process", "160"], 200),
+                         "cfg3_1920x1080_full": (blob("c3.raw", frames), ["--width", "1920", "--height", "1080", "--width-to-process", "1920",
+                                                                        "--scale-factor", "1.1", "--min-size", "24"], 25)}
+                for cname, ((path_, nfr), geo, iters_) in cases.items():
+                    shaped[cname] = {}
+                    for mem in ("pageable", "registered", "pinned"):
+                        for thr in (1, 4, 32):
+                            if mem == "registered" and thr != 4:
+                                continue
+                            try:
+                                r = subprocess.run([tool, "--frames-file", path_, "--nframes", str(nfr), "--fmt", "bgr", "--xml", FACE_XML, "--gpu", str(local),
+                                                    "--streams", str(max(thr, 4) if cname.startswith("cfg5") else thr), "--threads", str(thr), "--iters", str(iters_),
+                                                    "--warmup", "3", "--sync", "1", "--memory", mem] + geo, capture_output=True, text=True, timeout=180)
+                                shaped[cname]["%s_%dthr" % (mem, thr)] = json.loads(r.stdout.strip().splitlines()[-1])["frames_per_s"] if r.returncode == 0 else r.stderr[-200:]
+                            except Exception as ex:           # noqa: BLE001
+                                shaped[cname]["%s_%dthr" % (mem, thr)] = repr(ex)
+            shaped["unit"] = "frames/s; one blocking nv_face_detect per buffer, T native host threads with their own streams"
+            aux["element_shaped_sync_calls"] = shaped
         if rank == 0 and world == 1:
             try:                                         # auxiliary figures never take the headline line down
                 aux["other_configs_one_stream"] = aux_other_configs(nv, local, world)
@@ -615,11 +708,12 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8 pixels, int32/u32 integrals, f32 features, f64 stage sums", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "streams": "one CUDA stream + context per frame slot; a slot's previous frame is collected right before its next one is submitted",
-                       "l2": "per-step working set (%d contexts x ~%d MB of integrals/queues) exceeds the 126 MB L2"
-                             % (B, (16 * ab["integral_px"]) >> 20),
-                       "levels": len(levels), "windows_per_frame": ctxs[0].counters()["windows"],
-                       "faces_found_per_frame": nfaces},
+            "config": CONFIG,
+            "config_detail": {"frames_per_step_per_gpu": B, "streams": "one CUDA stream + context per frame slot; a slot's previous frame is collected right before its next one is submitted",
+                              "working_set_mb_per_context": (16 * ab["integral_px"]) >> 20,
+                              "levels": len(levels), "windows_per_frame": ctxs[0].counters()["windows"],
+                              "faces_found_per_frame": nfaces},
+            "parity_in_run": parity,
             # whole-job figures: every rank runs the same batch shape, so bytes and launches are rank 0's times world
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": world * B * W * H * 3,
                     "d2h_bytes_per_step": world * B * (16 + 1024 * 16), "ms_per_step": ms_e2e / args.steps},

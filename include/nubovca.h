@@ -128,6 +128,10 @@ NV_API int nv_face_submit_device(nv_ctx *ctx, const nv_cascade *c, const uint8_t
  * decoded frames land where the DMA engine reads them without a staging copy).  Portable across devices. */
 NV_API int nv_host_alloc(size_t bytes, void **out);
 NV_API void nv_host_free(void *p);
+/* Page-lock memory the caller already owns (cudaHostRegister, portable): what a shell does once per block of the upstream
+ * buffer pool when it cannot hand out nv_host_alloc memory.  Frames inside a registered block take the no-staging path. */
+NV_API int nv_host_register(void *p, size_t bytes);
+NV_API int nv_host_unregister(void *p);
 
 /* ---- 4:2:0 ingest (extension).  The reference elements negotiate BGR only
  *      (kmsfacedetect.cpp:129-133,1025-1031), so a decoder's I420 / NV12 output passes through a CPU videoconvert
@@ -135,7 +139,9 @@ NV_API void nv_host_free(void *p);
  *      what nv_face_detect gives on cv::cvtColor(frame, COLOR_YUV2BGR_I420 / _NV12 / _NV21) — the conversion is
  *      applied per source pixel inside the resize + gray kernel (BT.601, OpenCV's 20-bit fixed point), the BGR
  *      frame never exists.  YV12 is I420 with plane[1] and plane[2] swapped by the caller.  width and height even.
- *      plane[2] / stride[2] are ignored for NV12 / NV21.  on_device != 0: the planes are device pointers. --------- */
+ *      plane[2] / stride[2] are ignored for NV12 / NV21.  on_device != 0: the planes are device pointers.
+ *      The planes need not share an allocation: they travel as one copy only when they follow each other with at most a
+ *      row of padding in between, otherwise plane by plane (each plane's own page-lock state is honoured). ------------- */
 typedef enum { NV_FMT_BGR = 0, NV_FMT_I420 = 1, NV_FMT_NV12 = 2, NV_FMT_NV21 = 3 } nv_pixel_format;
 typedef struct {
     int format;               /* nv_pixel_format, one of the 4:2:0 values */

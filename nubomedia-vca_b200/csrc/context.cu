@@ -296,8 +296,7 @@ extern "C" void nv_ctx_destroy(nv_ctx *c)
     cudaFree(c->d_bits_ok); cudaFree(c->d_queue); cudaFree(c->d_counters); cudaFree(c->d_cand);
     cudaFree(c->d_cand_sorted); cudaFree(c->d_cand_rects); cudaFree(c->d_adj); cudaFree(c->d_result);
     cudaFreeHost(c->h_result);
-    cudaFree(c->d_trk_prev); cudaFree(c->d_trk_mhi); cudaFree(c->d_trk_labels); cudaFree(c->d_trk_mask);
-    cudaFree(c->d_trk_boxes); cudaFree(c->d_trk_misc); cudaFreeHost(c->h_trk);
+    cudaFree(c->d_trk_prev); cudaFree(c->d_trk_hist); cudaFree(c->d_trk_scratch); cudaFreeHost(c->h_trk);
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     for (int i = 0; i <= NV_NUM_STAGES; i++) if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
@@ -889,10 +888,13 @@ static int yuv_h2d(nv_ctx *ctx, const FaceSrc &f, int height, SrcPlanes *d)
     int np = f.fmt == NV_FMT_I420 ? 3 : 2;
     size_t bytes[3] = {(size_t)f.s[0] * height, (size_t)f.s[1] * (height / 2), np == 3 ? (size_t)f.s[2] * (height / 2) : 0};
     // tight end of the last row of a plane does not matter: strides are honoured, the tail padding is copied along
+    // Only planes that follow each other with at most a row (or 256 bytes) of padding between them are taken as one block:
+    // a larger gap means separate allocations that merely happen to ascend, and the bytes between them are not the caller's.
     const uint8_t *lo = f.p[0], *hi = f.p[0] + bytes[0];
     bool block = true;
     for (int i = 1; i < np; i++) {
-        if (f.p[i] < hi || (size_t)(f.p[i] - lo) + bytes[i] > ctx->frame_cap) { block = false; break; }
+        const size_t max_gap = std::max<size_t>(256, (size_t)f.s[i - 1]);
+        if (f.p[i] < hi || (size_t)(f.p[i] - hi) > max_gap || (size_t)(f.p[i] - lo) + bytes[i] > ctx->frame_cap) { block = false; break; }
         hi = f.p[i] + bytes[i];
     }
     size_t off[3] = {0, 0, 0};
@@ -1063,6 +1065,23 @@ extern "C" int nv_host_alloc(size_t bytes, void **out)
 }
 
 extern "C" void nv_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// Page-lock memory the caller already owns (a block of the upstream buffer pool): frames inside it are then read by the
+// DMA engine directly, without the staging copy a pageable frame costs.
+extern "C" int nv_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    if (nv_device_count() < 1) { nv_set_error("no CUDA device"); return NV_ERR_NO_DEVICE; }
+    NV_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return NV_OK;
+}
+
+extern "C" int nv_host_unregister(void *p)
+{
+    if (!p) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    NV_CUDA(cudaHostUnregister(p));
+    return NV_OK;
+}
 
 extern "C" int nv_face_submit_yuv(nv_ctx *ctx, const nv_cascade *c, const nv_yuv_frame *f, const nv_face_params *p)
 {
@@ -1241,9 +1260,10 @@ extern "C" int nv_tracker_reset(nv_ctx *ctx)
 {
     if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }
     ctx->trk_frames = 0;
-    if (ctx->d_trk_mhi) {
+    memset(ctx->trk_val, 0, sizeof ctx->trk_val);
+    if (ctx->d_trk_hist) {
         NV_CUDA(cudaSetDevice(ctx->gpu));
-        NV_CUDA(cudaMemsetAsync(ctx->d_trk_mhi, 0, (size_t)ctx->trk_w * ctx->trk_h * sizeof(float), ctx->stream));
+        NV_CUDA(cudaMemsetAsync(ctx->d_trk_hist, 0, (size_t)ctx->trk_w * ctx->trk_h, ctx->stream));
     }
     return NV_OK;
 }
@@ -1261,18 +1281,17 @@ static int tracker_impl(nv_ctx *ctx, const FaceSrc &src, int width, int height, 
     size_t np = (size_t)width * height;
     if (ctx->trk_w != width || ctx->trk_h != height) {        // (re)configure: gstnubotracker.cpp:202-237
         NV_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->d_trk_prev); cudaFree(ctx->d_trk_mhi); cudaFree(ctx->d_trk_labels); cudaFree(ctx->d_trk_mask);
-        cudaFree(ctx->d_trk_boxes); cudaFree(ctx->d_trk_misc); cudaFreeHost(ctx->h_trk);
-        ctx->d_trk_prev = nullptr; ctx->d_trk_mhi = nullptr; ctx->d_trk_labels = nullptr; ctx->d_trk_mask = nullptr;
-        ctx->d_trk_boxes = nullptr; ctx->d_trk_misc = nullptr; ctx->h_trk = nullptr;
-        NV_CUDA(cudaMalloc(&ctx->d_trk_prev, np));
-        NV_CUDA(cudaMalloc(&ctx->d_trk_mhi, np * sizeof(float)));
-        NV_CUDA(cudaMemset(ctx->d_trk_mhi, 0, np * sizeof(float)));
-        NV_CUDA(cudaMalloc(&ctx->d_trk_labels, (2 * np + TRK_MAX_COMPONENTS) * sizeof(int)));
-        NV_CUDA(cudaMalloc(&ctx->d_trk_mask, np));
-        NV_CUDA(cudaMalloc(&ctx->d_trk_boxes, (np + 2 * TRK_MAX_COMPONENTS + 1) * sizeof(int4)));
-        NV_CUDA(cudaMalloc(&ctx->d_trk_misc, 4 * sizeof(int)));
+        cudaFree(ctx->d_trk_prev); cudaFree(ctx->d_trk_hist); cudaFree(ctx->d_trk_scratch); cudaFreeHost(ctx->h_trk);
+        ctx->d_trk_prev = nullptr; ctx->d_trk_hist = nullptr; ctx->d_trk_scratch = nullptr; ctx->h_trk = nullptr;
+        ctx->trk_w = ctx->trk_h = 0;
+        const size_t sb = tracker_scratch_bytes(width, height, &ctx->trk_lo);
+        NV_CUDA(cudaMalloc(&ctx->d_trk_prev, np + 16));
+        NV_CUDA(cudaMalloc(&ctx->d_trk_hist, np + 16));
+        NV_CUDA(cudaMemset(ctx->d_trk_hist, 0, np + 16));
+        NV_CUDA(cudaMalloc(&ctx->d_trk_scratch, sb));
+        NV_CUDA(cudaMemset(ctx->d_trk_scratch + ctx->trk_lo.zero_begin, 0, ctx->trk_lo.zero_end - ctx->trk_lo.zero_begin));
         NV_CUDA(cudaMallocHost(&ctx->h_trk, (TRK_MAX_COMPONENTS + 1) * sizeof(int4)));
+        memset(ctx->trk_val, 0, sizeof ctx->trk_val);
         ctx->trk_w = width; ctx->trk_h = height; ctx->trk_frames = 0;
     }
     SrcPlanes planes = {src.p[0], src.p[1], src.p[2], src.s[0], src.s[1], src.s[2]};
@@ -1284,14 +1303,28 @@ static int tracker_impl(nv_ctx *ctx, const FaceSrc &src, int width, int height, 
         }
     }
     int first = ctx->trk_frames == 0, nl = 0;
-    float ts = (float)timestamp_ms, del = (float)(timestamp_ms - 0.2);          // MHI_DURATION, :28
-    NV_CUDA(launch_tracker(ctx, src.fmt, planes, width, height, first, ts, del, p->threshold, &nl));
+    // The motion history is stored as an index into the table of live timestamps (kernels_tracker.cu).  updateMotionHistory:
+    // a silhouette pixel takes ts, any other pixel whose value is below ts - MHI_DURATION (0.2, :28) drops to 0 — so an
+    // entry whose value is below `del` dies in this frame; equal float values share an entry.
+    const float ts = (float)timestamp_ms, del = (float)(timestamp_ms - 0.2);
+    float val[256];
+    val[0] = 0.f;
+    for (int k = 1; k < 256; k++) val[k] = (ctx->trk_val[k] != 0.f && !(ctx->trk_val[k] < del)) ? ctx->trk_val[k] : 0.f;
+    int cur = 0;
+    if (!first && ts != 0.f) {                                     // ts == 0: silhouette pixels read as "no history", like every 0
+        for (int k = 1; k < 256 && !cur; k++) if (val[k] == ts) cur = k;
+        for (int k = 1; k < 256 && !cur; k++) if (ctx->trk_val[k] == 0.f) cur = k;       // free BEFORE this frame: no pixel holds it
+        if (!cur) { nv_set_error("more than 255 distinct timestamps inside the motion-history window"); return NV_ERR_CAPACITY; }
+        val[cur] = ts;
+    }
+    NV_CUDA(launch_tracker(ctx, src.fmt, planes, width, height, first, p->threshold, cur, val, &nl));
+    memcpy(ctx->trk_val, val, sizeof val);
     ctx->launches += nl;
     ctx->trk_frames++;
     int total = 0;
     std::vector<nv_rect> v;
     if (!first) {
-        const int4 *d_out = ctx->d_trk_boxes + np + TRK_MAX_COMPONENTS;
+        const int4 *d_out = reinterpret_cast<const int4 *>(ctx->d_trk_scratch + ctx->trk_lo.out);
         NV_CUDA(cudaMemcpyAsync(ctx->h_trk, d_out, (1 + 1024) * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
         NV_CUDA(cudaStreamSynchronize(ctx->stream));
         const int4 *h = reinterpret_cast<const int4 *>(ctx->h_trk);

@@ -255,6 +255,9 @@ struct PlanSlot {
 };
 #define NV_PLAN_SLOTS 12
 
+// byte offsets of the tracker's per-tile scratch inside nv_ctx::d_trk_scratch (kernels_tracker.cu)
+struct TrkLayout { int ntx, nty; size_t bbox, rects, out, bseed, parent, bcount, keys, bslot, counters, edge_flag, zero_begin, zero_end; };
+
 struct nv_ctx {
     int gpu = 0;
     int max_w = 0, max_h = 0;
@@ -320,8 +323,10 @@ struct nv_ctx {
     long long launches = 0;
 
     // tracker state (gstnubotracker.cpp:88-106 priv + the file-static img_prev :108, made per-ctx)
-    uint8_t *d_trk_prev = nullptr;  float *d_trk_mhi = nullptr;  int *d_trk_labels = nullptr;
-    uint8_t *d_trk_mask = nullptr;  int4 *d_trk_boxes = nullptr;  int *d_trk_misc = nullptr;
+    // d_trk_hist: the motion history as one byte per pixel, an index into trk_val (the live timestamps; 0 = no history)
+    uint8_t *d_trk_prev = nullptr, *d_trk_hist = nullptr, *d_trk_scratch = nullptr;
+    TrkLayout trk_lo = {};
+    float trk_val[256] = {};
     int trk_w = 0, trk_h = 0;  long long trk_frames = 0;
     uint8_t *h_trk = nullptr;
 };
@@ -401,8 +406,9 @@ cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *can
                          uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch);
 
 // kernels_tracker.cu
-cudaError_t launch_tracker(nv_ctx *ctx, int fmt, const SrcPlanes &src, int w, int h, int first, float ts, float del,
-                           int thr, int *nlaunch);
+size_t tracker_scratch_bytes(int w, int h, TrkLayout *lo);
+cudaError_t launch_tracker(nv_ctx *ctx, int fmt, const SrcPlanes &src, int w, int h, int first, int thr, int cur, const float *val256,
+                           int *nlaunch);
 
 // ----------------------------------------------------------------------------------------------
 // device helpers shared by the ingest kernels (kernels_prep.cu, kernels_tracker.cu): cvtColor(COLOR_YUV2BGR_*) per pixel

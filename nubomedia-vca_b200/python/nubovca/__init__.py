@@ -88,6 +88,8 @@ _SIGS = {
     "nv_yuv2bgr": (_i, [_vp, C.POINTER(YuvFrame), _vp, _i]),
     "nv_host_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "nv_host_free": (None, [_vp]),
+    "nv_host_register": (_i, [_vp, C.c_size_t]),
+    "nv_host_unregister": (_i, [_vp]),
     "nv_tracker_process": (_i, [_vp, _vp, _i, _i, _i, C.c_double, C.POINTER(TrackerParams), _vp, _i, _ip]),
     "nv_tracker_reset": (_i, [_vp]),
     "nv_tracker_process_yuv": (_i, [_vp, C.POINTER(YuvFrame), C.c_double, C.POINTER(TrackerParams), _vp, _i, _ip]),

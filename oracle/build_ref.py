@@ -66,7 +66,7 @@ def build(verbose=False):
     own, direct = sources()
     inc = ["-I" + os.path.join(ROOT, "tests", "mock_gst"), "-I" + os.path.join(ROOT, "oracle", "refbuild")]
     inc += ["-I" + os.path.join(REF, d) for d in MODS.values()]
-    cxx = ["g++", "-std=c++17", "-O1", "-fPIC", "-fvisibility=hidden", "-w", "-ffp-contract=off", "-DMH_HAVE_REFCV",
+    cxx = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-fvisibility=hidden", "-w", "-ffp-contract=off", "-DMH_HAVE_REFCV",
            "-include", os.path.join(ROOT, "tests", "mock_gst", "prelude.h")] + inc
     objs = []
     jobs = []

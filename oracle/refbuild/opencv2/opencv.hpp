@@ -352,6 +352,10 @@ public:
     {
         (void)flags;
         objects.clear();
+        if (getenv("REFCV_TRACE"))
+            fprintf(stderr, "detectMultiScale %dx%d step %zu sf %.17g mn %d min %dx%d max %dx%d cascade %p win %dx%d stages %d\n", image.cols, image.rows, image.step,
+                    scaleFactor, minNeighbors, minSize.width, minSize.height, maxSize.width, maxSize.height, (const void *)c_, c_ ? ((const int *)c_)[0] : -1,
+                    c_ ? ((const int *)c_)[1] : -1, c_ ? ((const int *)c_)[2] : -1);
         if (!c_ || image.empty()) return;
         if (image.type() != CV_8UC1) throw Exception("detectMultiScale: 8UC1 only");
         int cap = 1 << 14;

@@ -98,8 +98,19 @@ def yuv_case(fmt, W, H, k, seed, w2p, sf, mn, min_size):
                 min_size=list(ms), yuv_sha=sha(buf), bgr_sha=sha(bgr), eq_sha=sha(eq), grouped=grp.tolist())
 
 
+def cfg3_full():
+    """BASELINE config 3 at FULL size (1920x1080, processing width 1920, sf 1.1, min 24x24, the bench.py frames of rank 0):
+    its own file, so that regenerating it does not touch the other fixtures."""
+    cases = [face_case(1920, 1080, 6, 3 + i, 1920, 1.1, 3, (24, 24)) for i in range(2)]
+    with open(os.path.join(HERE, "cfg3_golden.json"), "w") as f:
+        json.dump(dict(cv2=cv2.__version__, cases=cases), f)
+    print("wrote", len(cases), "full-size config-3 cases:", [(len(c["raw"]), len(c["grouped"])) for c in cases])
+
+
 def main():
     cv2.setNumThreads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "--cfg3":
+        return cfg3_full()
     yuv = [yuv_case("I420", 640, 480, 4, 1, 160, 1.25, 3, None),            # linear resize (4x)
            yuv_case("NV12", 1280, 720, 3, 1000, 640, 1.25, 3, None),         # cfg5 stream 0: the 2x box path
            yuv_case("NV21", 640, 360, 6, 3, 640, 1.1, 3, (24, 24)),          # no resize

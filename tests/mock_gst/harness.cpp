@@ -277,3 +277,19 @@ MH_API int mh_emissions(void *e, char *buf, int cap)
     return (int)minigst_emissions(e).size();
 }
 MH_API void mh_clear_emissions(void *e) { minigst_emissions(e).clear(); }
+
+// debugging aid: MH_BACKTRACE_AFTER=<seconds> prints a native backtrace of the calling thread when a harness call runs that long
+#include <execinfo.h>
+#include <signal.h>
+static void mh_alarm_handler(int)
+{
+    void *bt[64];
+    int n = backtrace(bt, 64);
+    backtrace_symbols_fd(bt, n, 2);
+    _exit(97);
+}
+MH_API void mh_arm_backtrace(int seconds)
+{
+    signal(SIGALRM, mh_alarm_handler);
+    alarm((unsigned)seconds);
+}

@@ -80,7 +80,13 @@ class Harness:
     # reference build only: CascadeClassifier::load("/usr/share/opencv/haarcascades/<basename>") resolves to this model
     def register_cascade(self, basename, ocascade):
         assert self.is_ref
-        self._cascades[basename] = ocascade                 # keeps the arrays behind the C struct alive
+        # Keeps the arrays behind the C struct alive FOR THE LIFE OF THE PROCESS: the reference's nose element holds its
+        # cascades in file-static objects loaded by the first instance only (kmsnosedetect.cpp:151-152,1049-1051), so a
+        # model registered once may be referenced for ever.  For the same reason a test process must not re-register
+        # haarcascade_frontalface_alt.xml / haarcascade_mcs_nose.xml with other content and expect the nose element to follow.
+        self._keep = getattr(self, "_keep", [])
+        self._keep.append(ocascade)
+        self._cascades[basename] = ocascade
         self.L.mh_register_cascade(basename.encode(), C.addressof(ocascade.c) if ocascade is not None else None)
 
     def register_cascade_dir(self, cdir):

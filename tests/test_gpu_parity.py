@@ -82,6 +82,23 @@ def test_face_golden_cases(ctx, face, idx):
     assert rects_equal(raw, c["raw"])
 
 
+@pytest.mark.parametrize("idx", range(2))
+def test_cfg3_full_size_golden(face, idx):
+    """BASELINE config 3 at FULL size (the bench.py frames of rank 0) against the committed cv2 output: raw candidates and
+    grouped rectangles of 3.66 M windows."""
+    c = json.load(open(os.path.join(HERE, "golden", "cfg3_golden.json")))["cases"][idx]
+    ncasc, _ = face
+    fr = synth.frame(c["W"], c["H"], c["k"], c["seed"])
+    big = nv.Context(0, 1920, 1080)
+    try:
+        ms = tuple(c["min_size"])
+        assert rects_equal(big.face_detect(ncasc, fr, c["width_to_process"], c["scale_factor"], c["min_neighbors"], ms), c["grouped"])
+        assert rects_equal(big.face_detect(ncasc, fr, c["width_to_process"], c["scale_factor"], 0, ms), c["raw"])
+        assert big.counters()["windows"] > 3_000_000
+    finally:
+        big.close()
+
+
 def test_face_element_min_size_rule(ctx, face):
     # min_size=None -> Size(cols/20, rows/20), kmsfacedetect.cpp:811
     ncasc, ocasc = face

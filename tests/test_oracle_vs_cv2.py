@@ -40,6 +40,18 @@ def _golden(name):
         return json.load(f)
 
 
+def test_cfg3_full_size_golden(cascade_dir):
+    """BASELINE config 3 at full size (1920x1080, 40 levels, 3.66 M windows): the oracle against the committed cv2 output."""
+    c = _golden("cfg3_golden.json")["cases"][0]
+    fr = synth.frame(c["W"], c["H"], c["k"], c["seed"])
+    assert sha(fr) == c["frame_sha"], "synthetic generator drifted"
+    eq = O.equalize_hist(O.bgr2gray(fr))
+    assert sha(eq) == c["eq_sha"]
+    casc = O.Cascade(os.path.join(cascade_dir, c["cascade"]))
+    assert rects_equal(O.detect_multiscale(eq, casc, c["scale_factor"], 0, tuple(c["min_size"])), c["raw"])
+    assert rects_equal(O.detect_multiscale(eq, casc, c["scale_factor"], c["min_neighbors"], tuple(c["min_size"])), c["grouped"])
+
+
 @pytest.mark.parametrize("idx", range(8))
 def test_face_golden(idx, cascade_dir):
     c = _golden("face_golden.json")["cases"][idx]

@@ -96,9 +96,7 @@ class ShellTarget:
         assert len(events) <= 1
         msg = None
         if events:
-            name, pts, rows = events[0]
-            assert pts == pts_ns and [r[0] for r in rows] == [str(i) for i in range(len(rows))], (pts, pts_ns, rows)
-            msg = [tuple(r[1:]) for r in rows]
+            msg = events[0]                           # (structure name, timestamp.pts or ~0, rows with their field names)
         return msg, (sig[0][1] if sig else None)
 
     def close(self):
@@ -110,17 +108,19 @@ def run(budget, seed, targets):
     R = refgst.ref()
     t0 = time.time()
     stats = dict(sequences=0, frames=0, rects=0, signals=0, drawn_frames=0, ref_threw=0, events_sent=0, rejected_sets=0, mismatches=0)
+    # ONE set of stand-in models per process: the reference's nose element keeps its cascades in file-static objects that
+    # only the first instance loads (kmsnosedetect.cpp:151-152,1049-1051), so the models cannot change between sequences
+    d = tempfile.mkdtemp(prefix="nubovca_fzr_")
+    shutil.copy(os.path.join(SRC, "haarcascade_frontalface_alt.xml"), d)
+    shutil.copy(os.path.join(SRC, "haarcascade_frontalface_alt.xml"), os.path.join(d, "haarcascade_profileface.xml"))
+    for name, (w, h) in STANDINS.items():
+        permissive_cascade(os.path.join(d, name), np.random.default_rng(int(rng.integers(1 << 30))), w, h,
+                           bias=float(rng.choice([0.2, 0.35, 0.5])))
+    R.register_cascade_dir(d)
     while time.time() - t0 < budget:
-        d = tempfile.mkdtemp(prefix="nubovca_fzr_")
         els = []
         ref = None
         try:
-            shutil.copy(os.path.join(SRC, "haarcascade_frontalface_alt.xml"), d)
-            shutil.copy(os.path.join(SRC, "haarcascade_frontalface_alt.xml"), os.path.join(d, "haarcascade_profileface.xml"))
-            for name, (w, h) in STANDINS.items():
-                permissive_cascade(os.path.join(d, name), np.random.default_rng(int(rng.integers(1 << 30))), w, h,
-                                   bias=float(rng.choice([0.2, 0.35, 0.5])))
-            R.register_cascade_dir(d)
             factory = refgst.FACTORIES[int(rng.integers(6))]
             trk = factory == "nubotracker"
             W, H = [(640, 480), (1280, 720), (960, 540), (800, 600), (320, 240)][int(rng.integers(5))]
@@ -184,10 +184,11 @@ def run(budget, seed, targets):
                     stats["ref_threw"] += 1          # the replacement clamps instead (documented) — nothing to compare from here on
                     break
                 assert len(events) <= 1 and (fr == f).all()
-                exp_msg = None
+                exp_msg = exp_event = None
                 if events:
-                    name, epts, rows = events[0]
-                    assert epts == pts and [r[0] for r in rows] == [str(j) for j in range(len(rows))]
+                    name, epts, rows = exp_event = events[0]
+                    assert [r[0] for r in rows] == [str(j) for j in range(len(rows))]
+                    assert (name, epts) == (("noses", 2 ** 64 - 1) if factory == "nubonosedetector" else ("message", pts))
                     exp_msg = [tuple(r[1:]) for r in rows]
                 exp_sig = sig[0][1] if sig else None
                 exp_frame = refgst.replay_draws(f.copy(), ref.draws(fr))
@@ -200,7 +201,7 @@ def run(budget, seed, targets):
                     msg, s = e.process(g, pts, wall)
                     if e.name == "mirror" and (trk or factory == "nuboeardetector"):
                         msg = None                   # the mirror reports the message it built; neither element pushes one
-                    if msg != exp_msg or s != exp_sig or not (g == exp_frame).all():
+                    if msg != (exp_event if e.name == "shell" else exp_msg) or s != exp_sig or not (g == exp_frame).all():
                         stats["mismatches"] += 1
                         print("MISMATCH", e.name, factory, (W, H), props, "frame", i, "\n  msg", msg, "\n  exp", exp_msg, "\n  sig", s, "\n  exp", exp_sig,
                               "\n  pixels differ:", int((g != exp_frame).sum()), flush=True)
@@ -211,7 +212,7 @@ def run(budget, seed, targets):
         finally:
             for e in els + ([ref] if ref else []):
                 e.close()
-            shutil.rmtree(d, ignore_errors=True)
+    shutil.rmtree(d, ignore_errors=True)
     nv._lib.nv_debug_set_wall_clock_ms(-1.0)
     return stats, time.time() - t0
 
