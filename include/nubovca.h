@@ -210,6 +210,13 @@ typedef struct {
     unsigned x, y, width, height;
 } nv_meta_rect;
 
+/* cascade_dir: where the haarcascade_*.xml models live (NULL: $NUBOVCA_CASCADE_DIR, else /usr/share/opencv/haarcascades, the
+ * reference's hard-coded directory).  A model that cannot be loaded is not fatal, as in the reference (kmsfacedetect.cpp:
+ * 167-171): the call returns NV_OK and nv_last_error() holds a "warning: ..." text naming the files (empty otherwise).
+ * Known behavioural difference: the reference passes CV_HAAR_FIND_BIGGEST_OBJECT to the mouth / nose / ear ROI cascades;
+ * with the OpenCV 2.x it linked and OLD-format models that flag keeps at most one object per ROI, while OpenCV >= 3 (the
+ * oracle of this library, cv2 4.13) ignores `flags` for new-format models and returns every grouped rectangle — and so
+ * does this library. */
 NV_API int nv_element_create(const char *factory_name, int gpu, const char *cascade_dir, nv_element **out);
 NV_API void nv_element_destroy(nv_element *e);
 NV_API int nv_element_set_property(nv_element *e, const char *name, long value);
@@ -220,19 +227,20 @@ NV_API int nv_element_get_property(nv_element *e, const char *name, long *value)
 NV_API int nv_element_property_info(nv_element *e, int index, const char **name, long *minimum, long *maximum, long *default_value);
 /* sink_event: a queued upstream "message" carrying face rectangles (kmseyedetect.cpp:192-218,680-724),
  * or the "motion" event the face element waits for in detect-event mode (kmsfacedetect.cpp:698-707) */
-/* General form: one custom downstream event as the element's sink pad saw it.  The reference queues a copy of EVERY such
- * event (kmsfacedetect.cpp:258-267, kmseyedetect.cpp:198-209) and __receive_event pops exactly one per frame, whatever it
- * holds (kmsfacedetect.cpp:711-755, kmseyedetect.cpp:726-764): a message without a "timestamp" structure is dropped unread;
- * the face element re-arms only on a "motion" structure; eye / mouth / nose keep the sub-structures whose "type" is "face"
- * and accept the message if it holds any structure field.  The ear element and the tracker have no sink_event handler. */
+/* General form: one custom downstream event as the element's sink pad saw it, field by field.  The reference queues a copy of
+ * EVERY such event (kmsfacedetect.cpp:258-267, kmseyedetect.cpp:198-209) and __receive_event pops exactly one per frame,
+ * whatever it holds (kmsfacedetect.cpp:711-755, kmseyedetect.cpp:726-764): a message without a structure-typed "timestamp"
+ * field is dropped unread; the face element re-arms only on a structure-typed "motion" field; eye and nose keep the
+ * sub-structures whose "type" is "face" and accept the message if it holds any structure field (kmseyedetect.cpp:680-724,
+ * kmsnosedetect.cpp:648-694); the mouth element only looks at fields named "0", "1", ... in that order
+ * (kmsmouthdetect.cpp:655-703).  The ear element and the tracker have no sink_event handler. */
 typedef struct {
-    int has_timestamp;        /* a "timestamp" field of structure type                                   */
-    int has_motion;           /* a field named "motion" of structure type (kmsfacedetect.cpp:698-707)    */
-    int n_other;              /* further structure-typed fields that are neither of the above nor faces  */
-    const nv_rect *faces;     /* sub-structures whose "type" string is "face", in field order            */
-    int nfaces;
-} nv_event;
-NV_API int nv_element_push_event(nv_element *e, const nv_event *ev);
+    const char *name;         /* field name in the message: "timestamp", "0", "1", "motion", ...                 */
+    int is_structure;         /* the field holds a GstStructure                                                   */
+    const char *type;         /* that structure's "type" string; NULL if it has none                              */
+    nv_rect rect;             /* its x / y / width / height (G_TYPE_UINT fields; 0 where absent)                  */
+} nv_event_field;
+NV_API int nv_element_push_message(nv_element *e, const nv_event_field *fields, int nfields);
 /* shorthands: a face message {timestamp, faces...} / a motion message {timestamp, motion} */
 NV_API int nv_element_push_faces_event(nv_element *e, const nv_rect *faces, int n);
 NV_API int nv_element_push_motion_event(nv_element *e);

@@ -146,17 +146,30 @@ extern "C" void nv_cascade_free(nv_cascade *c)
     delete c;
 }
 
+// Uploads a cascade's tables to `gpu` once.  Every table is built into locals and published in the maps only after
+// all uploads succeeded; a failure frees what was allocated, so a later call retries from a clean state.
 static int cascade_on_device(nv_cascade *c, int gpu, cudaStream_t st, const DevStump **stumps, const DevCascade **meta)
 {
     std::lock_guard<std::mutex> lk(c->mu);
-    auto it = c->d_stumps.find(gpu);
-    if (it == c->d_stumps.end()) {
-        DevStump *ds = nullptr; DevCascade *dm = nullptr;
-        NV_CUDA(cudaMalloc(&ds, c->stumps.size() * sizeof(DevStump)));
-        NV_CUDA(cudaMalloc(&dm, sizeof(DevCascade)));
-        NV_CUDA(cudaMemcpy(ds, c->stumps.data(), c->stumps.size() * sizeof(DevStump), cudaMemcpyHostToDevice));
-        NV_CUDA(cudaMemcpy(dm, &c->meta, sizeof(DevCascade), cudaMemcpyHostToDevice));
-        c->d_stumps[gpu] = ds; c->d_meta[gpu] = dm;
+    (void)st;
+    if (c->d_stumps.find(gpu) == c->d_stumps.end()) {
+        std::vector<void *> owned;
+        struct Guard {
+            std::vector<void *> &v; bool keep = false;
+            ~Guard() { if (!keep) for (void *p : v) cudaFree(p); }
+        } guard{owned};
+        auto upload = [&](const void *src, size_t bytes, void **out) -> int {
+            void *d = nullptr;
+            NV_CUDA(cudaMalloc(&d, bytes ? bytes : 1));
+            owned.push_back(d);
+            if (bytes) NV_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+            *out = d;
+            return NV_OK;
+        };
+        int rc;
+        void *ds = nullptr, *dm = nullptr, *dtree = nullptr, *dnode = nullptr, *dleaf = nullptr, *dfeat = nullptr, *dt = nullptr, *db = nullptr;
+        if ((rc = upload(c->stumps.data(), c->stumps.size() * sizeof(DevStump), &ds)) != NV_OK) return rc;
+        if ((rc = upload(&c->meta, sizeof(DevCascade), &dm)) != NV_OK) return rc;
         if (c->h.general) {
             const HostCascade &h = c->h;
             std::vector<int2> trees(h.tree_nnodes.size());
@@ -178,28 +191,22 @@ static int cascade_on_device(nv_cascade *c, int gpu, cudaStream_t st, const DevS
                 }
                 g.tilted = h.feat_tilted[f];
             }
-            int2 *dtree = nullptr; int4 *dnode = nullptr; float *dleaf = nullptr; GenFeat *dfeat = nullptr;
-            NV_CUDA(cudaMalloc(&dtree, trees.size() * sizeof(int2)));
-            NV_CUDA(cudaMalloc(&dnode, nodes.size() * sizeof(int4)));
-            NV_CUDA(cudaMalloc(&dleaf, h.leaves.size() * sizeof(float)));
-            NV_CUDA(cudaMalloc(&dfeat, feats.size() * sizeof(GenFeat)));
-            NV_CUDA(cudaMemcpy(dtree, trees.data(), trees.size() * sizeof(int2), cudaMemcpyHostToDevice));
-            NV_CUDA(cudaMemcpy(dnode, nodes.data(), nodes.size() * sizeof(int4), cudaMemcpyHostToDevice));
-            NV_CUDA(cudaMemcpy(dleaf, h.leaves.data(), h.leaves.size() * sizeof(float), cudaMemcpyHostToDevice));
-            NV_CUDA(cudaMemcpy(dfeat, feats.data(), feats.size() * sizeof(GenFeat), cudaMemcpyHostToDevice));
-            c->d_gen[gpu] = GenModel{dtree, dnode, dleaf, dfeat};
+            if ((rc = upload(trees.data(), trees.size() * sizeof(int2), &dtree)) != NV_OK) return rc;
+            if ((rc = upload(nodes.data(), nodes.size() * sizeof(int4), &dnode)) != NV_OK) return rc;
+            if ((rc = upload(h.leaves.data(), h.leaves.size() * sizeof(float), &dleaf)) != NV_OK) return rc;
+            if ((rc = upload(feats.data(), feats.size() * sizeof(GenFeat), &dfeat)) != NV_OK) return rc;
         }
         if (c->tail_fast) {
-            TailStump *dt = nullptr; double *db = nullptr;
-            NV_CUDA(cudaMalloc(&dt, c->tail_stumps.size() * sizeof(TailStump)));
-            NV_CUDA(cudaMalloc(&db, c->tail_base.size() * sizeof(double)));
-            NV_CUDA(cudaMemcpy(dt, c->tail_stumps.data(), c->tail_stumps.size() * sizeof(TailStump), cudaMemcpyHostToDevice));
-            NV_CUDA(cudaMemcpy(db, c->tail_base.data(), c->tail_base.size() * sizeof(double), cudaMemcpyHostToDevice));
-            c->d_tail[gpu] = dt; c->d_tail_base[gpu] = db;
+            if ((rc = upload(c->tail_stumps.data(), c->tail_stumps.size() * sizeof(TailStump), &dt)) != NV_OK) return rc;
+            if ((rc = upload(c->tail_base.data(), c->tail_base.size() * sizeof(double), &db)) != NV_OK) return rc;
         }
+        guard.keep = true;                                          // everything is on the device: publish
+        if (c->h.general) c->d_gen[gpu] = GenModel{(int2 *)dtree, (int4 *)dnode, (float *)dleaf, (GenFeat *)dfeat};
+        if (c->tail_fast) { c->d_tail[gpu] = (TailStump *)dt; c->d_tail_base[gpu] = (double *)db; }
+        c->d_meta[gpu] = (DevCascade *)dm;
+        c->d_stumps[gpu] = (DevStump *)ds;
     }
     *stumps = c->d_stumps[gpu]; *meta = c->d_meta[gpu];
-    (void)st;
     return NV_OK;
 }
 
@@ -269,7 +276,7 @@ extern "C" int nv_ctx_create(int gpu, int max_width, int max_height, nv_ctx **ou
         c->slots = new PlanSlot[NV_PLAN_SLOTS];
         c->ps = &c->slots[0];
         for (int i = 0; i < NV_PLAN_SLOTS; i++) NV_CUDA(cudaMalloc(&c->slots[i].d_plan, sizeof(PlanDev)));
-        NV_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(int)));
+        NV_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(int)));
         return alloc_candidates(c, CAND_CAP, true);
     }();
     if (rc != NV_OK) { nv_ctx_destroy(c); return rc; }
@@ -293,7 +300,7 @@ extern "C" void nv_ctx_destroy(nv_ctx *c)
         delete[] c->slots;
     }
     cudaFree(c->d_sq); cudaFree(c->d_pyr); cudaFree(c->d_tilt); cudaFree(c->d_vnf); cudaFree(c->d_depth);
-    cudaFree(c->d_bits_ok); cudaFree(c->d_queue); cudaFree(c->d_counters); cudaFree(c->d_cand);
+    cudaFree(c->d_bits_ok); cudaFree(c->d_queue); cudaFree(c->d_queue2); cudaFree(c->d_counters); cudaFree(c->d_cand);
     cudaFree(c->d_cand_sorted); cudaFree(c->d_cand_rects); cudaFree(c->d_adj); cudaFree(c->d_result);
     cudaFreeHost(c->h_result);
     cudaFree(c->d_trk_prev); cudaFree(c->d_trk_hist); cudaFree(c->d_trk_scratch); cudaFreeHost(c->h_trk);
@@ -493,6 +500,16 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         if ((rc = ensure(&ctx->ps->d_ptab, &ctx->ps->ptab_cap, (size_t)tofs * 2)) != NV_OK) return rc;
         NV_CUDA(cudaMemcpy(ctx->ps->d_ptab, tab.data(), (size_t)tofs * sizeof(int2), cudaMemcpyHostToDevice));
         const void *old[8] = {ctx->d_sum, ctx->d_sq, ctx->d_vnf, ctx->d_queue, ctx->d_bits_ok, ctx->d_depth, ctx->d_pyr, ctx->d_tilt};
+        // on EVERY way out of this block — a failed allocation included — cached tensor maps and graphs of the other plan
+        // slots are invalidated if a shared buffer was freed or moved
+        struct MovedGuard {
+            nv_ctx *c; const void *const *old;
+            ~MovedGuard()
+            {
+                const void *now[8] = {c->d_sum, c->d_sq, c->d_vnf, c->d_queue, c->d_bits_ok, c->d_depth, c->d_pyr, c->d_tilt};
+                if (memcmp(old, now, sizeof now)) { c->buf_gen++; c->epoch++; }
+            }
+        } moved_guard{ctx, old};
         size_t icap = ctx->integ_cap;
         if ((rc = ensure(&ctx->d_sum, &icap, (size_t)iofs, true)) != NV_OK) return rc;
         if ((rc = ensure(&ctx->d_sq, &ctx->integ_cap, (size_t)iofs, true)) != NV_OK) return rc;
@@ -508,8 +525,6 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         if (ctx->need_tilt && (rc = ensure(&ctx->d_tilt, &ctx->tilt_cap, ctx->integ_cap)) != NV_OK) return rc;
         ctx->ps->max_lw = 0;
         for (int l = 0; l < nl; l++) ctx->ps->max_lw = std::max(ctx->ps->max_lw, P.lv[l].lw);
-        const void *now[8] = {ctx->d_sum, ctx->d_sq, ctx->d_vnf, ctx->d_queue, ctx->d_bits_ok, ctx->d_depth, ctx->d_pyr, ctx->d_tilt};
-        if (memcmp(old, now, sizeof old)) { ctx->buf_gen++; ctx->epoch++; }   // a shared buffer moved: tensor maps and graphs of every cached plan are stale
     }
     NV_CUDA(cudaMemcpy(ctx->ps->d_plan, &P, sizeof(PlanDev), cudaMemcpyHostToDevice));
     ctx->ps->pkey = key;
@@ -622,6 +637,12 @@ static int detect_prepare(nv_ctx *ctx, nv_cascade *casc, int W, int H, const nv_
         std::lock_guard<std::mutex> lk(casc->mu);
         ctx->cur_tail = casc->d_tail[ctx->gpu]; ctx->cur_tail_base = casc->d_tail_base[ctx->gpu];
     }
+    if (ctx->use_gen && ctx->ps->plan.total_windows > NV_SMALL_PLAN_WINDOWS && ctx->queue2_cap < ctx->queue_cap) {
+        // a tree / tilted model over a large image compacts its survivors between stage ranges: second queue, same size
+        NV_CUDA(cudaStreamSynchronize(ctx->stream));
+        if ((rc = ensure(&ctx->d_queue2, &ctx->queue2_cap, ctx->queue_cap)) != NV_OK) return rc;
+        ctx->epoch++; ctx->buf_gen++;
+    }
     if ((rc = ensure_tile_params(ctx, casc)) != NV_OK) return rc;
     if (p->min_neighbors > 0 && ctx->adj_cap < (size_t)ctx->cand_cap) {      // grown earlier for an ungrouped call
         NV_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -640,7 +661,7 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
     cudaStream_t st = ctx->stream;
     int nl = 0;
     for (int i = 2; i <= NV_NUM_STAGES; i++) ctx->prof_set[i] = false;
-    NV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int), st));
+    NV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(int), st));
     if (P.nlevels > 0) {
         int16_t *depth = ctx->debug ? ctx->d_depth : nullptr;
         prof_mark(ctx, 2);
@@ -703,7 +724,13 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
             NV_CUDA(launch_alive_to_queue(ctx->ps->d_plan, P.total_rows, ctx->d_vnf, ctx->d_bits_ok, ctx->d_queue, ctx->d_counters,
                                           qcap, st));
             prof_mark(ctx, 6);
-            if (ctx->use_gen)
+            if (ctx->use_gen && P.total_windows > small_limit && ctx->d_queue2 && ctx->queue2_cap >= ctx->queue_cap && casc->meta.nstages > 1) {
+                int extra = 0;                                   // large plan: stage-wise compaction between thread-per-window passes
+                NV_CUDA(launch_queue_stages_gen_staged(ctx->ps->d_plan, meta, ctx->cur_gen, ctx->d_sum, tilt, ctx->d_queue, ctx->d_queue2, qcap,
+                                                       ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, casc->meta.nstages,
+                                                       casc->h.order_free, st, &extra));
+                nl += extra - 1;
+            } else if (ctx->use_gen)
                 NV_CUDA(launch_queue_stages_gen(ctx->ps->d_plan, meta, ctx->cur_gen, ctx->d_sum, tilt, ctx->d_queue, ctx->d_counters,
                                                 ctx->d_cand, ctx->cand_cap, depth, 148 * 8, casc->h.order_free, st));
             else

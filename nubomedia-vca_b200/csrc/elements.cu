@@ -59,7 +59,8 @@ struct nv_element {
     int num_frame = 0, num_frames_to_process = 0, num_iter = 0;
     // every custom downstream event the sink pad saw, in arrival order (the reference queues a copy of each one,
     // FACE:258-267, EYE:198-209): what __receive_event reads from a message, nothing more
-    struct Event { bool has_timestamp, has_motion; int n_other; std::vector<nv_rect> faces; };
+    struct Field { std::string name; bool is_structure, has_type; std::string type; nv_rect rect; };
+    typedef std::vector<Field> Event;
     std::deque<Event> events_queue;
     double time_events_ms = 0;
     // face
@@ -476,33 +477,55 @@ void maybe_emit(nv_element *e, const std::string &payload, bool any, double now_
     }
 }
 
-// __receive_event for eye/mouth/nose (EYE:726-764, MOUTH:712-748, NOSE:707-743): pops ONE queued message whatever it is.
-// Without a "timestamp" structure it is dropped unread (__get_timestamp fails, EYE:745-750); otherwise
-// __get_event_message (EYE:680-724) clears the face list, keeps the sub-structures whose type is "face" and reports
-// success if the message held any structure-typed field at all.
+// __get_timestamp (FACE:658-676, EYE:662-678, ...): the message must hold a structure-typed field named "timestamp"
+bool event_has_timestamp(const nv_element::Event &ev)
+{
+    for (auto &f : ev) if (f.name == "timestamp") return f.is_structure;
+    return false;
+}
+
+// __receive_event for eye / mouth / nose (EYE:726-764, MOUTH:705-748, NOSE:702-743): pops ONE queued message whatever it
+// is.  Without a timestamp it is dropped unread; otherwise __get_event_message clears the face list and walks the fields:
+//   eye, nose (EYE:680-724, NOSE:648-694): every structure-typed field other than "timestamp" counts (result = true), those
+//     whose "type" is "face" are kept;
+//   mouth (MOUTH:655-703): only fields named "0", "1", "2", ... IN THAT ORDER are looked at (the expected number advances
+//     on a name match, structure or not), so a "motion" or otherwise named field neither counts nor is read.
 bool receive_faces_event(nv_element *e)
 {
     if (e->get("detect-event") == 0) return true;                  // the queue is left alone (EYE:734)
     if (e->events_queue.empty()) return false;
     nv_element::Event ev = std::move(e->events_queue.front());
     e->events_queue.pop_front();
-    if (!ev.has_timestamp) return false;
-    e->faces = ev.faces;
-    if (ev.faces.empty() && ev.n_other == 0 && !ev.has_motion) return false;
-    e->num_frames_to_process = 10 / (5 - (int)e->get("process-x-every-4-frames"));   // NUM_FRAMES_TO_PROCESS / (5 - p)
-    return true;
+    if (!event_has_timestamp(ev)) return false;
+    e->faces.clear();
+    bool res = false;
+    int id = 0;
+    for (auto &f : ev) {
+        if (f.name == "timestamp") continue;
+        if (e->kind == K_MOUTH) {
+            if (f.name != std::to_string(id)) continue;
+            id++;
+        }
+        if (!f.is_structure) continue;
+        if (f.has_type && f.type == "face") e->faces.push_back(f.rect);
+        res = true;
+    }
+    if (res) e->num_frames_to_process = 10 / (5 - (int)e->get("process-x-every-4-frames"));   // NUM_FRAMES_TO_PROCESS / (5 - p)
+    return res;
 }
 // __receive_event of the face element (FACE:711-755): pops ONE queued message; only one that carries a timestamp and a
-// "motion" structure (FACE:698-707) re-arms the detector — any other message uses up this frame's pop
+// structure-typed "motion" field (FACE:680-709) re-arms the detector — any other message uses up this frame's pop
 bool receive_motion_event(nv_element *e)
 {
     if (e->get("detect-event") == 0) return true;
     if (e->events_queue.empty()) return false;
     nv_element::Event ev = std::move(e->events_queue.front());
     e->events_queue.pop_front();
-    if (!(ev.has_timestamp && ev.has_motion)) return false;
-    e->num_frames_to_process = 10;                                  // NUM_FRAMES_TO_PROCESS
-    return true;
+    if (!event_has_timestamp(ev)) return false;
+    bool motion = false;
+    for (auto &f : ev) if (f.name == "motion" && f.is_structure) motion = true;
+    if (motion) e->num_frames_to_process = 10;                      // NUM_FRAMES_TO_PROCESS
+    return motion;
 }
 
 // ---- Faces::track_faces (FACES:78-153) ---------------------------------------------------------
@@ -572,7 +595,9 @@ int face_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, double n
         }
         gate_end(e);
         if (e->get("view-faces") > 0 && frame) {         // FACE:832-849 -> Faces::draw -> BASEFACE:70-82, colors[1]; BGR frames only
-            const int sc = W / (int)w2p;
+            // `scale` reaches Faces::draw by value AFTER process_frame replaced a useless one (frame narrower than
+            // width-to-process: W / w2p == 0) by 1 (FACE:770-782); kms_face_send_event below keeps the raw quotient
+            const int sc = W / (int)w2p > 0 ? W / (int)w2p : 1;
             for (auto &f : e->faces_tracked)
                 draw_rectangle3(frame, W, H, stride, 3, f.r.x * sc, f.r.y * sc, (f.r.x + f.r.width - 1) * sc,
                                 (f.r.y + f.r.height - 1) * sc, cv_rgb(0, 128, 255));
@@ -986,11 +1011,15 @@ int tracker_frame(nv_element *e, uint8_t *frame, int W, int H, int stride, uint6
 
 void add_props(nv_element *e, std::initializer_list<Prop> l) { for (auto &p : l) { e->props.push_back(p); e->props.back().value = p.def; } }
 
+std::string g_missing;                    // models nv_element_create could not load (reported through nv_last_error)
 nv_cascade *try_load(const std::string &dir, const char *file)
 {
     nv_cascade *c = nullptr;
     std::string path = dir + "/" + file;
-    if (nv_cascade_load(path.c_str(), &c) != NV_OK) return nullptr;      // the reference logs and carries on (FACE:167-171)
+    if (nv_cascade_load(path.c_str(), &c) != NV_OK) {                    // the reference logs and carries on (FACE:167-171)
+        g_missing += (g_missing.empty() ? "" : ", ") + path;
+        return nullptr;
+    }
     return c;
 }
 
@@ -1008,6 +1037,7 @@ extern "C" int nv_element_create(const char *factory_name, int gpu, const char *
     for (int i = 0; i < 6; i++) if (!strcmp(factory_name, names[i])) kind = i;
     if (kind < 0) { nv_set_error("unknown element factory '%s'", factory_name); return NV_ERR_ARG; }
     nv_element *e = new nv_element();
+    g_missing.clear();
     e->kind = (Kind)kind; e->factory = factory_name;
     const char *env = getenv("NUBOVCA_CASCADE_DIR");
     e->dir = cascade_dir ? cascade_dir : (env ? env : "/usr/share/opencv/haarcascades");        // FACE:40
@@ -1060,6 +1090,10 @@ extern "C" int nv_element_create(const char *factory_name, int gpu, const char *
         break;
     }
     *out = e;
+    // like the reference, a missing model is not fatal (the element then detects nothing with it) — but it is said out loud:
+    // NV_OK with a non-empty nv_last_error() that names the files
+    if (!g_missing.empty()) nv_set_error("warning: %s: cascade file(s) not loaded: %s", factory_name, g_missing.c_str());
+    else nv_set_error("%s", "");
     return NV_OK;
 }
 
@@ -1111,27 +1145,36 @@ extern "C" int nv_element_property_info(nv_element *e, int index, const char **n
     return NV_OK;
 }
 
-extern "C" int nv_element_push_event(nv_element *e, const nv_event *ev)
+extern "C" int nv_element_push_message(nv_element *e, const nv_event_field *fields, int nfields)
 {
-    if (!e || !ev || ev->nfaces < 0 || (ev->nfaces > 0 && !ev->faces) || ev->n_other < 0) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    if (!e || nfields < 0 || (nfields > 0 && !fields)) { nv_set_error("bad argument"); return NV_ERR_ARG; }
     if (e->kind == K_EAR || e->kind == K_TRACKER) return NV_OK;        // no sink_event handler of their own: events pass through
     nv_element::Event q;
-    q.has_timestamp = ev->has_timestamp != 0; q.has_motion = ev->has_motion != 0; q.n_other = ev->n_other;
-    if (ev->nfaces > 0) q.faces.assign(ev->faces, ev->faces + ev->nfaces);
+    for (int i = 0; i < nfields; i++) {
+        if (!fields[i].name) { nv_set_error("field without a name"); return NV_ERR_ARG; }
+        q.push_back(nv_element::Field{fields[i].name, fields[i].is_structure != 0, fields[i].type != nullptr,
+                                      fields[i].type ? fields[i].type : "", fields[i].rect});
+    }
     e->events_queue.push_back(std::move(q));
     return NV_OK;
 }
 
+// a face message as the face element emits it (FACE:196-226): {timestamp: time{pts}, "0": face{type "face", x, y, width, height}, ...}
 extern "C" int nv_element_push_faces_event(nv_element *e, const nv_rect *faces, int n)
 {
-    nv_event ev = {1, 0, 0, faces, n};
-    return nv_element_push_event(e, &ev);
+    if (n < 0 || (n > 0 && !faces)) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    std::vector<std::string> names(n);
+    std::vector<nv_event_field> f(n + 1);
+    f[0] = nv_event_field{"timestamp", 1, nullptr, {0, 0, 0, 0}};
+    for (int i = 0; i < n; i++) { names[i] = std::to_string(i); f[i + 1] = nv_event_field{names[i].c_str(), 1, "face", faces[i]}; }
+    return nv_element_push_message(e, f.data(), n + 1);
 }
 
+// a motion message: {timestamp: time{pts}, motion: motion{grid}} (FACE:680-709)
 extern "C" int nv_element_push_motion_event(nv_element *e)
 {
-    nv_event ev = {1, 1, 0, nullptr, 0};
-    return nv_element_push_event(e, &ev);
+    nv_event_field f[2] = {{"timestamp", 1, nullptr, {0, 0, 0, 0}}, {"motion", 1, nullptr, {0, 0, 0, 0}}};
+    return nv_element_push_message(e, f, 2);
 }
 
 extern "C" int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int width, int height, int stride_bytes,

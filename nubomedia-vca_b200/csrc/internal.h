@@ -310,6 +310,7 @@ struct nv_ctx {
     const TailStump *cur_tail = nullptr;  const double *cur_tail_base = nullptr;
     GenModel cur_gen = {};  bool use_gen = false;  bool cur_tilted = false;  // general cascade in use / it has tilted features
     bool need_tilt = false;                                                  // tilted-integral buffers exist (sticky)
+    uint2 *d_queue2 = nullptr;  size_t queue2_cap = 0;                       // second window queue: general cascades on large plans
     uint32_t *d_tilt = nullptr;  size_t tilt_cap = 0;
     cudaGraphExec_t gexec = nullptr;  GraphKey gkey, gkey_seen;  int g_nl = 0;  bool no_graph = false;  unsigned g_prof_mask = 0;
     unsigned long long epoch = 1;     // bumped whenever a buffer the pipeline binds is re-allocated or re-planned
@@ -379,6 +380,10 @@ cudaError_t launch_stage0_rows_gen(const PlanDev *plan, int total_rows, const De
 cudaError_t launch_queue_stages_gen(const PlanDev *plan, const DevCascade *meta, const GenModel &g, const uint32_t *sum,
                                     const uint32_t *tilt, const uint2 *queue, int *counters, uint32_t *cand, int cand_cap,
                                     int16_t *depth, int nblocks, int order_free, cudaStream_t st);
+cudaError_t launch_queue_stages_gen_staged(const PlanDev *plan, const DevCascade *meta, const GenModel &g, const uint32_t *sum,
+                                           const uint32_t *tilt, uint2 *queue_a, uint2 *queue_b, int qcap, int *counters,
+                                           uint32_t *cand, int cand_cap, int16_t *depth, int nstages, int order_free,
+                                           cudaStream_t st, int *nlaunch);
 cudaError_t launch_cascade_classes(const TileParams &tp, int ystep, int ntiles, cudaStream_t st);
 cudaError_t launch_stage0_rows_p(const Stage0Params &sp, cudaStream_t st);
 bool fill_stage0_params(const nv_cascade *c, const PlanDev &P, Stage0Params *sp);

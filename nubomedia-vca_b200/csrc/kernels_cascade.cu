@@ -239,10 +239,11 @@ k_queue_stages_gen(const PlanDev *__restrict__ plan, const DevCascade *__restric
 __global__ void __launch_bounds__(256)
 k_queue_stages_gen_warp(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ meta, const GenModel g,
                         const uint32_t *__restrict__ sum, const uint32_t *__restrict__ tilt, const uint2 *__restrict__ queue,
-                        int *__restrict__ counters, uint32_t *__restrict__ cand, int cand_cap, int16_t *__restrict__ depth)
+                        int *__restrict__ counters, uint32_t *__restrict__ cand, int cand_cap, int16_t *__restrict__ depth,
+                        int stage_begin, int cin)
 {
     const int lane = threadIdx.x & 31;
-    const int n = counters[0], nstages = meta->nstages;
+    const int n = counters[cin], nstages = meta->nstages;
     for (;;) {
         int e = 0;
         if (lane == 0) e = atomicAdd(&counters[5], 1);
@@ -257,7 +258,7 @@ k_queue_stages_gen_warp(const PlanDev *__restrict__ plan, const DevCascade *__re
         const uint32_t *wb = v.sum + rowbase + ix;
         const uint32_t *tb = tilt ? tilt + L.iofs + rowbase + ix * L.ystep : nullptr;
         int code = NV_DEPTH_PASS;
-        for (int st = 1; st < nstages; st++) {
+        for (int st = stage_begin; st < nstages; st++) {
             const int t0 = meta->stage_first[st], t1 = meta->stage_first[st + 1];
             double tmp = 0.;
             for (int t = t0 + lane; t < t1; t += 32) tmp = __dadd_rn(tmp, gen_stage_sum(g, t, t + 1, wb, v, tb, L.ipitch, vnf));
@@ -271,6 +272,52 @@ k_queue_stages_gen_warp(const PlanDev *__restrict__ plan, const DevCascade *__re
                 int pos = atomicAdd(&counters[1], 1);
                 if (pos < cand_cap) cand[pos] = q.x;
                 else counters[2] = 1;
+            }
+        }
+    }
+}
+
+// Large plans (a full frame through a tree / tilted model): one thread per queued window over the stage range
+// [sb, se) only, survivors compacted into the next queue (warp-aggregated append), so that every pass starts with full
+// warps again — the early stages of such a model reject nine windows in ten, and a warp per window (above) spends its
+// 32 lanes on a handful of trees there.  Sums run in XML order: exact for every model, no certificate needed.
+// final != 0: [sb, se) reaches the last stage and survivors are candidates.
+__global__ void __launch_bounds__(256)
+k_queue_range_gen(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ meta, const GenModel g,
+                  const uint32_t *__restrict__ sum, const uint32_t *__restrict__ tilt, const uint2 *__restrict__ qin,
+                  uint2 *__restrict__ qout, int qcap, int *__restrict__ counters, int cin, int cout, uint32_t *__restrict__ cand,
+                  int cand_cap, int16_t *__restrict__ depth, int sb, int se, int final)
+{
+    const int n = counters[cin], lane = threadIdx.x & 31;
+    const int nround = (n + 31) & ~31;                            // whole warps stay in the loop: the append below votes
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+        bool pass = false;
+        uint2 q = make_uint2(0u, 0u);
+        if (i < n) {
+            q = qin[i];
+            int l = q.x >> 26, iy = (q.x >> 13) & 8191, ix = q.x & 8191;
+            float vnf = __uint_as_float(q.y);
+            const LevelDesc &L = plan->lv[l];
+            LevelView v{sum + L.iofs, L.ipitch, L.iplane, L.ystep};
+            size_t rowbase = (size_t)iy * L.ystep * L.ipitch;
+            const uint32_t *wb = v.sum + rowbase + ix;
+            const uint32_t *tb = tilt ? tilt + L.iofs + rowbase + ix * L.ystep : nullptr;
+            int code = NV_DEPTH_PASS;
+            for (int st = sb; st < se; st++)
+                if (gen_stage_sum(g, meta->stage_first[st], meta->stage_first[st + 1], wb, v, tb, L.ipitch, vnf) <
+                    (double)meta->stage_thr[st]) { code = -st; break; }
+            pass = code == NV_DEPTH_PASS;
+            if (depth && (!pass || final)) depth[L.wofs + iy * L.nx + ix] = (int16_t)code;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&counters[final ? 1 : cout], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) {
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                if (final) { if (pos < cand_cap) cand[pos] = q.x; else counters[2] = 1; }
+                else { if (pos < qcap) qout[pos] = q; else counters[2] = 1; }
             }
         }
     }
@@ -1195,8 +1242,40 @@ cudaError_t launch_queue_stages_gen(const PlanDev *plan, const DevCascade *meta,
                                     const uint32_t *tilt, const uint2 *queue, int *counters, uint32_t *cand, int cand_cap,
                                     int16_t *depth, int nblocks, int order_free, cudaStream_t st)
 {
-    if (order_free) k_queue_stages_gen_warp<<<nblocks, 256, 0, st>>>(plan, meta, g, sum, tilt, queue, counters, cand, cand_cap, depth);
+    if (order_free) k_queue_stages_gen_warp<<<nblocks, 256, 0, st>>>(plan, meta, g, sum, tilt, queue, counters, cand, cand_cap, depth, 1, 0);
     else k_queue_stages_gen<<<nblocks, 256, 0, st>>>(plan, meta, g, sum, tilt, queue, counters, cand, cand_cap, depth);
+    return cudaGetLastError();
+}
+
+// Large plans: stages 1 .. nstages-1 in passes of growing depth with compaction in between (k_queue_range_gen), ping-pong
+// between the two queues; the few windows that get past the scheduled ranges finish with one warp each (order-free
+// models) or in one more thread-per-window pass.  counters[8 + i] counts the survivors of pass i.
+cudaError_t launch_queue_stages_gen_staged(const PlanDev *plan, const DevCascade *meta, const GenModel &g, const uint32_t *sum,
+                                           const uint32_t *tilt, uint2 *queue_a, uint2 *queue_b, int qcap, int *counters,
+                                           uint32_t *cand, int cand_cap, int16_t *depth, int nstages, int order_free,
+                                           cudaStream_t st, int *nlaunch)
+{
+    static const int width[] = {1, 1, 1, 2, 4};                  // stages per pass: [1,2) [2,3) [3,4) [4,6) [6,10)
+    const int nblocks = 148 * 8;
+    uint2 *qin = queue_a, *qout = queue_b;
+    int cin = 0, sb = 1, pass = 0;
+    for (; pass < 5 && sb < nstages; pass++) {
+        const int se = sb + width[pass] < nstages ? sb + width[pass] : nstages;
+        const int final = se == nstages;
+        k_queue_range_gen<<<nblocks, 256, 0, st>>>(plan, meta, g, sum, tilt, qin, qout, qcap, counters, cin, 8 + pass, cand, cand_cap,
+                                                   depth, sb, se, final);
+        (*nlaunch)++;
+        cin = 8 + pass; sb = se;
+        uint2 *t = qin; qin = qout; qout = t;
+    }
+    if (sb < nstages) {
+        if (order_free)
+            k_queue_stages_gen_warp<<<nblocks, 256, 0, st>>>(plan, meta, g, sum, tilt, qin, counters, cand, cand_cap, depth, sb, cin);
+        else
+            k_queue_range_gen<<<nblocks, 256, 0, st>>>(plan, meta, g, sum, tilt, qin, qout, qcap, counters, cin, 15, cand, cand_cap, depth,
+                                                       sb, nstages, 1);
+        (*nlaunch)++;
+    }
     return cudaGetLastError();
 }
 

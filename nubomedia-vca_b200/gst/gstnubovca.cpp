@@ -116,40 +116,38 @@ static void gst_nubovca_get_property(GObject *object, guint property_id, GValue 
     g_rec_mutex_unlock(&self->mutex);
 }
 
-// one custom downstream event -> what __receive_event would read from it (see nv_event in nubovca.h)
+// one custom downstream event -> its fields, as __get_timestamp / __get_event_message would read them (nv_event_field)
 static void queue_message(GstNuboVca *self, const GstStructure *message)
 {
     enum { MAXF = 256 };
-    nv_rect faces[MAXF];
-    nv_event ev;
-    memset(&ev, 0, sizeof ev);
-    ev.faces = faces;
+    nv_event_field fields[MAXF] = {};
+    gchar *types[MAXF] = {};
+    int n = 0;
     gint len = gst_structure_n_fields(message);
-    for (gint i = 0; i < len; i++) {
+    for (gint i = 0; i < len && n < MAXF; i++) {
         const gchar *name = gst_structure_nth_field_name(message, i);
+        nv_event_field f;
+        memset(&f, 0, sizeof f);
+        f.name = name;
+        types[n] = NULL;
         GstStructure *data = NULL;
-        if (!gst_structure_get(message, name, GST_TYPE_STRUCTURE, &data, NULL)) continue;      // not a structure-typed field
-        if (g_strcmp0(name, "timestamp") == 0) ev.has_timestamp = 1;
-        else {
-            gchar *type = NULL;
-            gboolean face = data && gst_structure_get(data, "type", G_TYPE_STRING, &type, NULL) && g_strcmp0(type, "face") == 0;
-            if (face && ev.nfaces < MAXF) {                                  // kmseyedetect.cpp:706-718
-                guint x = 0, y = 0, w = 0, h = 0;
-                gst_structure_get(data, "x", G_TYPE_UINT, &x, NULL);
-                gst_structure_get(data, "y", G_TYPE_UINT, &y, NULL);
-                gst_structure_get(data, "width", G_TYPE_UINT, &w, NULL);
-                gst_structure_get(data, "height", G_TYPE_UINT, &h, NULL);
-                nv_rect r = {(int)x, (int)y, (int)w, (int)h};
-                faces[ev.nfaces++] = r;
-            } else if (g_strcmp0(name, "motion") == 0) ev.has_motion = 1;    // kmsfacedetect.cpp:698-707
-            else ev.n_other++;
-            g_free(type);
+        if (gst_structure_get(message, name, GST_TYPE_STRUCTURE, &data, NULL) && data) {
+            guint x = 0, y = 0, w = 0, h = 0;
+            f.is_structure = 1;
+            if (gst_structure_get(data, "type", G_TYPE_STRING, &types[n], NULL)) f.type = types[n];
+            gst_structure_get(data, "x", G_TYPE_UINT, &x, NULL);
+            gst_structure_get(data, "y", G_TYPE_UINT, &y, NULL);
+            gst_structure_get(data, "width", G_TYPE_UINT, &w, NULL);
+            gst_structure_get(data, "height", G_TYPE_UINT, &h, NULL);
+            f.rect.x = (int)x; f.rect.y = (int)y; f.rect.width = (int)w; f.rect.height = (int)h;
+            gst_structure_free(data);
         }
-        if (data) gst_structure_free(data);
+        fields[n++] = f;
     }
     GST_OBJECT_LOCK(self);
-    nv_element_push_event(self->el, &ev);
+    nv_element_push_message(self->el, fields, n);
     GST_OBJECT_UNLOCK(self);
+    for (int i = 0; i < n; i++) g_free(types[i]);
 }
 
 static gboolean gst_nubovca_sink_event(GstBaseTransform *trans, GstEvent *event)
@@ -261,7 +259,8 @@ static void gst_nubovca_init(GTypeInstance *instance, gpointer g_class)
     if (nv_element_create(self->desc->factory, pick_gpu(), NULL, &self->el) != NV_OK) {
         GST_ERROR_OBJECT(self, "nv_element_create: %s", nv_last_error());
         self->el = NULL;
-    }
+    } else if (nv_last_error()[0])
+        GST_WARNING_OBJECT(self, "%s", nv_last_error());          // a cascade file is missing: the element runs without it
 }
 
 static const NuboDesc *desc_of_type(GType t)

@@ -58,8 +58,8 @@ class TrackerParams(C.Structure):
     _fields_ = [("threshold", C.c_int), ("min_area", C.c_int), ("max_area", C.c_long), ("distance", C.c_int)]
 
 
-class EventDesc(C.Structure):
-    _fields_ = [("has_timestamp", C.c_int), ("has_motion", C.c_int), ("n_other", C.c_int), ("faces", C.c_void_p), ("nfaces", C.c_int)]
+class EventField(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("is_structure", C.c_int), ("type", C.c_char_p), ("rect", Rect)]
 
 
 class LevelInfo(C.Structure):
@@ -104,7 +104,7 @@ _SIGS = {
     "nv_element_property_info": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]),
     "nv_element_push_faces_event": (_i, [_vp, _vp, _i]),
     "nv_element_push_motion_event": (_i, [_vp]),
-    "nv_element_push_event": (_i, [_vp, _vp]),
+    "nv_element_push_message": (_i, [_vp, _vp, _i]),
     "nv_debug_set_wall_clock_ms": (None, [C.c_double]),
     "nv_debug_merge_eyes_current_frame": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _ip]),
     "nv_debug_merge_consecutive": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _ip]),
@@ -284,11 +284,12 @@ class Element:
     def push_motion(self):
         _check(_lib.nv_element_push_motion_event(self.handle), "nv_element_push_motion_event")
 
-    def push_event(self, faces=(), has_timestamp=True, has_motion=False, n_other=0):
-        """One custom downstream event as the sink pad saw it (nv_event)."""
-        r = np.ascontiguousarray(np.asarray(faces, np.int32).reshape(-1, 4))
-        ev = EventDesc(int(has_timestamp), int(has_motion), int(n_other), r.ctypes.data if len(r) else None, len(r))
-        _check(_lib.nv_element_push_event(self.handle, C.byref(ev)), "nv_element_push_event")
+    def push_message(self, fields):
+        """One custom downstream event as the sink pad saw it: fields = [(name, is_structure, type or None, (x, y, w, h))]."""
+        arr = (EventField * max(len(fields), 1))()
+        for i, (name, is_st, typ, r) in enumerate(fields):
+            arr[i] = EventField(name.encode(), int(is_st), typ.encode() if typ is not None else None, Rect(*[int(v) for v in r]))
+        _check(_lib.nv_element_push_message(self.handle, arr, len(fields)), "nv_element_push_message")
 
     def process(self, frame, pts_ns: int = 0, now_ms: float = -1.0):
         """One buffer through transform_frame_ip.  Returns (message [(name, type, x, y, w, h)], pushed, signal or None)."""

@@ -12,6 +12,7 @@
 #ifndef REFBUILD_OPENCV_HPP
 #define REFBUILD_OPENCV_HPP
 
+#include <emmintrin.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -126,7 +127,7 @@ struct IplImage {
     int owns_data;
 };
 
-inline int cvRound(double v) { return (int)lrint(v); }
+inline int cvRound(double v) { return _mm_cvtsd_si32(_mm_set_sd(v)); }      // OpenCV's own SSE2 form: INT_MIN for inf / NaN
 inline CvPoint cvPoint(int x, int y) { return CvPoint(x, y); }
 inline CvSize cvSize(int w, int h) { return CvSize(w, h); }
 

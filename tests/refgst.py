@@ -122,7 +122,9 @@ class Harness:
         f = []
         if timestamp:
             f.append(("timestamp", "struct", self.structure("time", [("pts", "uint64", pts)])))
-        f.append(("motion", "struct", self.structure("motion", [("grid", "string", grid)])))
+        # "type" is given so that the eye / nose elements, which read it from every sub-structure into an uninitialised
+        # pointer (kmseyedetect.cpp:703-705), stay defined when a test hands them a motion message
+        f.append(("motion", "struct", self.structure("motion", [("type", "string", "motion"), ("grid", "string", grid)])))
         return self.structure("message", f)
 
     def element(self, factory):

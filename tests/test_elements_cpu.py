@@ -15,7 +15,9 @@ SURFACE = {
     "nuboeyedetector": dict(COMMON, **{"view-eyes": (0, 1, 0), "send-meta-data": (0, 1, 0)}),
     "nubomouthdetector": dict(COMMON, **{"view-mouths": (0, 1, 0), "send-meta-data": (0, 1, 0)}),
     "nubonosedetector": dict(COMMON, **{"view-noses": (0, 1, 0), "send-meta-data": (0, 1, 0)}),
-    "nuboeardetector": dict(COMMON, **{"view-ears": (0, 1, 0), "meta-data": (0, 1, 0)}),           # kmseardetect.cpp:1006
+    # kmseardetect.cpp:1006 (the name), :943 view_ears starts at -1, events_ms is never initialised (0): values confirmed by
+    # the reference's own element (tests/test_ref_elements_cpu.py)
+    "nuboeardetector": dict(COMMON, **{"view-ears": (0, 1, -1), "meta-data": (0, 1, 0), "events-ms": (0, 30000, 0)}),
     "nubotracker": {"set_threshold": (0, 255, 20), "set_min_area": (0, 10000, 50), "set_max_area": (0, 300000, 30000),
                     "set_distance": (0, 2000, 35), "set_visual_mode": (0, 4, 0), "activate-events": (0, 1, 0),
                     "events-ms": (0, 30000, 30001)},

@@ -51,7 +51,14 @@ class MirrorTarget:
         return self.e.get(prop)
 
     def event(self, kind, faces, ts):
-        self.e.push_event(faces if kind == "faces" else (), has_timestamp=ts, has_motion=kind == "motion", n_other=1 if kind == "other" else 0)
+        f = [("timestamp", True, None, (0, 0, 0, 0))] if ts else []
+        if kind == "faces":
+            f += [(str(i), True, "face", r) for i, r in enumerate(faces)]
+        elif kind == "motion":
+            f.append(("motion", True, "motion", (0, 0, 0, 0)))
+        else:
+            f.append(("x", True, "thing", (0, 0, 0, 0)))
+        self.e.push_message(f)
 
     def process(self, frame, pts_ns, wall_ms):
         nv._lib.nv_debug_set_wall_clock_ms(float(wall_ms))
