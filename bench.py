@@ -340,6 +340,28 @@ def aux_other_configs(nv, local, world):
         return e.process(seq[st["i"] % len(seq)], pts_ns=33_300_000 * st["i"])
     out["cfg4_tracker_1280x720_bgra"] = {"frames_per_s": _timeit(trk, 300)}
     e.close()
+    # the fused tracker kernel against the HBM roofline: algorithmic bytes 7 * S (BGRA in 4, previous gray in 1,
+    # gray out 1, mask / labels >= 1) over its CUDA-event time, isolated (one stream)
+    tctx = nv.Context(local, 1280, 720)
+    tctx.set_profile(True)
+    kms = []
+    for i in range(40):
+        tctx.tracker_process(seq[i % len(seq)], 33.3 * (i + 1))
+        if i >= 8:
+            kms.append(tctx.tracker_kernel_ms())
+    tctx.close()
+    if kms:
+        k_ms = statistics.median(kms)
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        ab = 7 * 1280 * 720
+        tj = {}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+        out["cfg4_tracker_1280x720_bgra"]["roofline"] = {
+            "bound": "hbm", "kernel": "k_trk_fused<0> (one launch per frame)", "achieved": ab / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": ab / (k_ms * 1e-3) / 1e9 / peak, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ab,
+            "bytes_moved_by_design": 8 * 1280 * 720, "traffic": tj.get("tracker_dram_bytes_per_frame")}
     if cv2 is not None:
         prev = {"g": cv2.cvtColor(seq[0], cv2.COLOR_BGRA2GRAY), "i": 0}
 
@@ -737,6 +759,19 @@ def main():
         }
         if onchip:
             line["roofline"]["onchip"] = onchip
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("tile_lts_bytes_per_frame") and iso.get("cascade_tiles", 0) > 0:
+                # measured L2 and L1/TEX traffic of the bulk kernel (ncu lts__t_bytes.sum / l1tex__t_bytes.sum, profiles/) over
+                # its isolated CUDA-event time, against the peaks ncu reports for this part in the same capture
+                t = iso["cascade_tiles"] * 1e-3
+                line["roofline"]["l2"] = {"achieved": tj["tile_lts_bytes_per_frame"] / t / 1e9, "peak": tj.get("lts_peak_gbs"), "unit": "GB/s",
+                                          "frac": (tj["tile_lts_bytes_per_frame"] / t / 1e9 / tj["lts_peak_gbs"]) if tj.get("lts_peak_gbs") else None,
+                                          "bytes_per_frame": tj["tile_lts_bytes_per_frame"], "source": tj.get("lts_source")}
+                if tj.get("tile_l1tex_bytes_per_frame"):
+                    line["roofline"]["l1tex"] = {"achieved": tj["tile_l1tex_bytes_per_frame"] / t / 1e9, "unit": "GB/s",
+                                                 "bytes_per_frame": tj["tile_l1tex_bytes_per_frame"], "peak": tj.get("l1tex_peak_gbs"),
+                                                 "frac": (tj["tile_l1tex_bytes_per_frame"] / t / 1e9 / tj["l1tex_peak_gbs"]) if tj.get("l1tex_peak_gbs") else None}
         if aux:
             line["aux"] = aux
         if not args.no_cpu_baseline and world == 1:

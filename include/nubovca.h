@@ -299,6 +299,7 @@ NV_API int nv_debug_join_objects(nv_rect *rects, int n_in, int min_area, long ma
 NV_API const char *nv_stage_name(int slot);
 NV_API int nv_ctx_set_profile(nv_ctx *ctx, int on);
 NV_API int nv_ctx_get_stage_times(nv_ctx *ctx, float *ms, int cap, int *n);   /* last collected call */
+NV_API int nv_ctx_get_tracker_kernel_ms(nv_ctx *ctx, float *ms);              /* the fused kernel of the last nv_tracker_process */
 NV_API int nv_event_create(void **ev);
 NV_API int nv_event_record(nv_ctx *ctx, void *ev);                             /* on the ctx's stream */
 NV_API int nv_event_elapsed_ms(void *ev_start, void *ev_end, float *ms);       /* waits for ev_end   */

@@ -14,7 +14,7 @@
 
 #define NV_VERSION_STR "nubovca-b200 0.1 (sm_100a)"
 #define CAND_CAP 8192              // initial raw-candidate capacity; grows on demand (collect() re-runs the call)
-#define CAND_CAP_GROUPED 65536     // hard limits: the similarity bit-matrix is cap^2/8 bytes (512 MB at the limit, allocated on demand only)
+#define CAND_CAP_GROUPED 65536     // hard limit of a grouped call (rank sort and union-find scratch grow with it; allocated on demand only)
 #define CAND_CAP_RAW 131072
 
 extern "C" const char *nv_version(void) { return NV_VERSION_STR; }
@@ -235,7 +235,9 @@ static int alloc_candidates(nv_ctx *c, int cap, bool with_adj)
     NV_CUDA(cudaMalloc(&c->d_cand, (size_t)cap * sizeof(uint32_t)));
     NV_CUDA(cudaMalloc(&c->d_cand_sorted, (size_t)cap * sizeof(uint32_t)));
     NV_CUDA(cudaMalloc(&c->d_cand_rects, (size_t)cap * sizeof(int4)));
-    size_t adj_words = (with_adj ? (size_t)cap * ((cap + 31) / 32) : 0) + 8 * (size_t)cap;
+    // the similarity bit-matrix only serves frames with at most NV_GROUP_UF_MIN candidates (kernels_group.cu)
+    const size_t acap = std::min<size_t>((size_t)cap, NV_GROUP_UF_MIN);
+    size_t adj_words = (with_adj ? acap * ((acap + 31) / 32) : 0) + 8 * (size_t)cap;
     NV_CUDA(cudaMalloc(&c->d_adj, adj_words * sizeof(uint32_t)));
     c->adj_cap = with_adj ? cap : 0;
     c->d_grp = reinterpret_cast<int *>(c->d_adj + (adj_words - 8 * (size_t)cap));
@@ -277,6 +279,7 @@ extern "C" int nv_ctx_create(int gpu, int max_width, int max_height, nv_ctx **ou
         c->ps = &c->slots[0];
         for (int i = 0; i < NV_PLAN_SLOTS; i++) NV_CUDA(cudaMalloc(&c->slots[i].d_plan, sizeof(PlanDev)));
         NV_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(int)));
+        NV_CUDA(cudaMalloc(&c->d_deepq, NV_DEEPQ_CAP * sizeof(uint2)));
         return alloc_candidates(c, CAND_CAP, true);
     }();
     if (rc != NV_OK) { nv_ctx_destroy(c); return rc; }
@@ -300,7 +303,7 @@ extern "C" void nv_ctx_destroy(nv_ctx *c)
         delete[] c->slots;
     }
     cudaFree(c->d_sq); cudaFree(c->d_pyr); cudaFree(c->d_tilt); cudaFree(c->d_vnf); cudaFree(c->d_depth);
-    cudaFree(c->d_bits_ok); cudaFree(c->d_queue); cudaFree(c->d_queue2); cudaFree(c->d_counters); cudaFree(c->d_cand);
+    cudaFree(c->d_bits_ok); cudaFree(c->d_queue); cudaFree(c->d_queue2); cudaFree(c->d_deepq); cudaFree(c->d_counters); cudaFree(c->d_cand);
     cudaFree(c->d_cand_sorted); cudaFree(c->d_cand_rects); cudaFree(c->d_adj); cudaFree(c->d_result);
     cudaFreeHost(c->h_result);
     cudaFree(c->d_trk_prev); cudaFree(c->d_trk_hist); cudaFree(c->d_trk_scratch); cudaFreeHost(c->h_trk);
@@ -693,10 +696,18 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
             NV_CUDA(launch_alive_to_queue(ctx->ps->d_plan, P.total_rows, ctx->d_vnf, ctx->d_bits_ok, ctx->d_queue, ctx->d_counters,
                                           qcap, st, 3));
             prof_mark(ctx, 6);
+            // stages narrower than NV_TAIL_BLOCK_MIN_STUMPS with a warp per window, the deep ones with a block per window
+            int split = 1;
+            while (split < casc->meta.nstages && casc->meta.stage_first[split + 1] - casc->meta.stage_first[split] < NV_TAIL_BLOCK_MIN_STUMPS) split++;
             NV_CUDA(launch_cascade_tail_fast(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
-                                             ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, 1, st,
+                                             ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, 1, split, ctx->d_deepq, NV_DEEPQ_CAP, st,
                                              8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));
             nl += 2;
+            if (split < casc->meta.nstages) {
+                NV_CUDA(launch_cascade_tail_block(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_deepq,
+                                                  ctx->d_counters, 6, ctx->d_cand, ctx->cand_cap, depth, split, -1, st));
+                nl++;
+            }
         } else if (ctx->ps->use_tiles) {
             for (int c = 0; c < 2; c++) {
                 TileParams &tp = ctx->ps->tp[c];
@@ -710,10 +721,19 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
             }
             prof_mark(ctx, 6);
             if (ctx->ps->bulk_end < casc->meta.nstages && ctx->cur_tail) {
+                // the survivors of the bulk stages (~15 000 per config-3 frame, most of them gone within a few stages): a warp
+                // per window for NV_TAIL_WARP_STAGES stages, then a block per window for the few that go deep — that chain
+                // (one window through every stage) was the latency floor of the frame
+                const int split = std::min(casc->meta.nstages, ctx->ps->bulk_end + NV_TAIL_WARP_STAGES);
                 NV_CUDA(launch_cascade_tail_fast(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
-                                                 ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, ctx->ps->bulk_end, st,
+                                                 ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, ctx->ps->bulk_end, split, nullptr, qcap, st,
                                                  8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));
                 nl++;
+                if (split < casc->meta.nstages) {
+                    NV_CUDA(launch_cascade_tail_block(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
+                                                      ctx->d_counters, 6, ctx->d_cand, ctx->cand_cap, depth, split, 3, st));
+                    nl++;
+                }
             } else if (ctx->ps->bulk_end < casc->meta.nstages) {
                 NV_CUDA(launch_cascade_tail(ctx->ps->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
                                             ctx->cand_cap, depth, ctx->ps->bulk_end, casc->h.order_free, 148 * 8, st,
@@ -1283,6 +1303,17 @@ extern "C" int nv_debug_join_objects(nv_rect *rects, int n_in, int min_area, lon
     return NV_OK;
 }
 
+// device time of the LAST nv_tracker_process kernel on this ctx (profiling on), CUDA events on the ctx's stream
+extern "C" int nv_ctx_get_tracker_kernel_ms(nv_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) { nv_set_error("null argument"); return NV_ERR_ARG; }
+    if (!ctx->profile || !ctx->prof_set[2] || !ctx->prof_set[3]) { nv_set_error("profiling is off or no tracker call has run"); return NV_ERR_STATE; }
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    NV_CUDA(cudaEventSynchronize(ctx->prof_ev[3]));
+    NV_CUDA(cudaEventElapsedTime(ms, ctx->prof_ev[2], ctx->prof_ev[3]));
+    return NV_OK;
+}
+
 extern "C" int nv_tracker_reset(nv_ctx *ctx)
 {
     if (!ctx) { nv_set_error("null ctx"); return NV_ERR_ARG; }
@@ -1344,7 +1375,9 @@ static int tracker_impl(nv_ctx *ctx, const FaceSrc &src, int width, int height, 
         if (!cur) { nv_set_error("more than 255 distinct timestamps inside the motion-history window"); return NV_ERR_CAPACITY; }
         val[cur] = ts;
     }
+    if (ctx->profile) prof_mark(ctx, 2);                           // with profiling on: events around the tracker kernel
     NV_CUDA(launch_tracker(ctx, src.fmt, planes, width, height, first, p->threshold, cur, val, &nl));
+    if (ctx->profile) prof_mark(ctx, 3);
     memcpy(ctx->trk_val, val, sizeof val);
     ctx->launches += nl;
     ctx->trk_frames++;

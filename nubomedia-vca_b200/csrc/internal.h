@@ -13,7 +13,11 @@
 
 // plans with at most this many windows (a config-1 frame, a nested ROI) skip the tile kernels: a lone tile is a 45 us
 // dependent chain, the warp-per-window kernel takes every window at once (profiles/r1_v5_summary.md)
+#define NV_GROUP_UF_MIN 2048        // raw candidates: above this, groupRectangles builds its components by neighbour search + union-find
 #define NV_SMALL_PLAN_WINDOWS 16384
+#define NV_DEEPQ_CAP NV_SMALL_PLAN_WINDOWS   // a small plan has no more windows than that
+#define NV_TAIL_BLOCK_MIN_STUMPS 64            // stages at least this wide go to the block-per-window kernel
+#define NV_TAIL_WARP_STAGES 4                  // large plans: tail stages run with a warp per window before the block-per-window kernel takes over
 #define NV_COLBLK 128            // physical integral columns per block of the column scan
 #define NV_MAX_LEVELS 64          // level index is packed in 6 bits of a window id
 #define NV_MAX_STAGES 64
@@ -256,7 +260,7 @@ struct PlanSlot {
 #define NV_PLAN_SLOTS 12
 
 // byte offsets of the tracker's per-tile scratch inside nv_ctx::d_trk_scratch (kernels_tracker.cu)
-struct TrkLayout { int ntx, nty; size_t bbox, rects, out, bseed, parent, bcount, keys, bslot, counters, edge_flag, zero_begin, zero_end; };
+struct TrkLayout { int ntx, nty; size_t bbox, rects, out, bseed, parent, slotlist, bcount, keys, bslot, counters, edge_flag, zero_begin, zero_end; };
 
 struct nv_ctx {
     int gpu = 0;
@@ -311,6 +315,7 @@ struct nv_ctx {
     GenModel cur_gen = {};  bool use_gen = false;  bool cur_tilted = false;  // general cascade in use / it has tilted features
     bool need_tilt = false;                                                  // tilted-integral buffers exist (sticky)
     uint2 *d_queue2 = nullptr;  size_t queue2_cap = 0;                       // second window queue: general cascades on large plans
+    uint2 *d_deepq = nullptr;                                                // NV_DEEPQ_CAP windows that reach the block-per-window stages (small plans)
     uint32_t *d_tilt = nullptr;  size_t tilt_cap = 0;
     cudaGraphExec_t gexec = nullptr;  GraphKey gkey, gkey_seen;  int g_nl = 0;  bool no_graph = false;  unsigned g_prof_mask = 0;
     unsigned long long epoch = 1;     // bumped whenever a buffer the pipeline binds is re-allocated or re-planned
@@ -396,7 +401,11 @@ void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_
 void build_tail_stumps(nv_cascade *c);
 cudaError_t launch_cascade_tail_fast(const PlanDev *plan, const DevCascade *meta, const TailStump *tstumps, const double *tbase,
                                      const uint32_t *sum, const uint2 *tail, int *counters, uint32_t *cand, int cand_cap,
-                                     int16_t *depth, int stage_begin, cudaStream_t st, int smem_bytes);
+                                     int16_t *depth, int stage_begin, int stage_end, uint2 *deep, int deep_cap, cudaStream_t st,
+                                     int smem_bytes);
+cudaError_t launch_cascade_tail_block(const PlanDev *plan, const DevCascade *meta, const TailStump *tstumps, const double *tbase,
+                                      const uint32_t *sum, const uint2 *queue, int *counters, int cin, uint32_t *cand, int cand_cap,
+                                      int16_t *depth, int stage_begin, int skip_counter, cudaStream_t st);
 
 // context.cu internals shared with elements.cu
 int nv_detect_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W, int H, int gstride, const uint8_t *d_lut,

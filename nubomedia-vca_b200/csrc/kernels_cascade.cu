@@ -921,11 +921,16 @@ __global__ void __launch_bounds__(256)
 k_cascade_tail_fast(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ meta, const TailStump *__restrict__ ts,
                     const double *__restrict__ tbase, const uint32_t *__restrict__ sum, const uint2 *__restrict__ tail,
                     int *__restrict__ counters, uint32_t *__restrict__ cand, int cand_cap, int16_t *__restrict__ depth,
-                    int stage_begin)
+                    int stage_begin, int stage_end, uint2 *__restrict__ deep, int deep_cap)
 {
     extern __shared__ uint32_t s_win[];                          // 8 warps x (win_h+1) x (win_w+1) words
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = counters[3], nstages = meta->nstages, nstumps = meta->nstumps;
+    // stages [stage_begin, stage_end); a window that gets through them with stages left goes to the `deep` queue
+    // (counters[6]) for k_cascade_tail_block.  deep == nullptr: the deep queue is the free part of `tail` itself, behind
+    // its n entries (large plans: n is a small fraction of the queue).
+    const int n = counters[3], nstages = stage_end, nstumps = meta->nstumps;
+    const bool last = stage_end == meta->nstages;
+    if (!deep) { deep = const_cast<uint2 *>(tail) + n; deep_cap -= n; }
     const int ww = plan->win_w, wh = plan->win_h, LP = ww + 1, npatch = (wh + 1) * LP;
     uint32_t *win = s_win + warp * npatch;
     const uint32_t wsa = smem_u32(win);
@@ -1015,9 +1020,101 @@ k_cascade_tail_fast(const PlanDev *__restrict__ plan, const DevCascade *__restri
         }
 #endif
         if (lane == 0) {
+            if (depth && (last || code != NV_DEPTH_PASS)) depth[L.wofs + iy * L.nx + ix] = (int16_t)code;
+            if (code == NV_DEPTH_PASS && last) {
+                int pos = atomicAdd(&counters[1], 1);
+                if (pos < cand_cap) cand[pos] = q.x;
+                else counters[2] = 1;
+            } else if (code == NV_DEPTH_PASS) {
+                int pos = atomicAdd(&counters[6], 1);
+                if (pos < deep_cap) deep[pos] = q;
+                else counters[2] = 1;
+            }
+        }
+    }
+}
+
+// The deep stages (80 .. 213 weak classifiers each in frontalface_alt) with a whole BLOCK per window: one classifier per
+// thread, so a stage is one round (two for the last ones) instead of three to seven, and the stage sum is combined through
+// shared memory with one barrier per stage.  A window that passes all 22 stages costs ~12 short rounds here against ~55 in
+// the warp-per-window kernel: that chain was the floor of every call (41-46 us, profiles/r1_v5_summary.md).  Needs the same
+// order-free certificate as k_cascade_tail_fast (the partial sums are added in another order).
+__global__ void __launch_bounds__(256)
+k_cascade_tail_block(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ meta, const TailStump *__restrict__ ts,
+                     const double *__restrict__ tbase, const uint32_t *__restrict__ sum, const uint2 *__restrict__ queue,
+                     int *__restrict__ counters, int cin, uint32_t *__restrict__ cand, int cand_cap, int16_t *__restrict__ depth,
+                     int stage_begin, int skip_counter)
+{
+    if (skip_counter >= 0) queue += counters[skip_counter];      // the deep queue sits behind the tail queue's entries
+    __shared__ uint32_t s_patch[33 * 33];
+    __shared__ double s_part[2][8];
+    __shared__ int s_first[NV_MAX_STAGES + 1];
+    __shared__ float s_thr[NV_MAX_STAGES];
+    __shared__ double s_base[NV_MAX_STAGES];
+    __shared__ int s_e;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = counters[cin], nstages = meta->nstages, nstumps = meta->nstumps;
+    if (n == 0) return;
+    const int ww = plan->win_w, wh = plan->win_h, LP = ww + 1, npatch = (wh + 1) * LP;
+    for (int i = tid; i <= nstages; i += 256) s_first[i] = meta->stage_first[i];
+    for (int i = tid; i < nstages; i += 256) { s_thr[i] = meta->stage_thr[i]; s_base[i] = tbase[i]; }
+    const uint32_t wsa = smem_u32(s_patch);
+    for (;;) {
+        __syncthreads();                                         // the previous window is done with s_patch and s_e
+        if (tid == 0) s_e = atomicAdd(&counters[7], 1);
+        __syncthreads();
+        const int e = s_e;
+        if (e >= n) break;
+        const uint2 q = queue[e];
+        const int l = q.x >> 26, iy = (q.x >> 13) & 8191, ix = q.x & 8191;
+        const float vnf = __uint_as_float(q.y);
+        const LevelDesc &L = plan->lv[l];
+        const uint32_t *wb = sum + L.iofs + (size_t)iy * L.ystep * L.ipitch + ix;
+        int k0 = s_first[stage_begin];
+        TailRec rec = load_tail(ts, min(k0 + tid, nstumps - 1));
+        for (int idx = tid; idx < npatch; idx += 256) {          // the window's integral patch
+            const int r = idx / LP, c = idx - r * LP;
+            const int pc = L.ystep == 2 ? (c & 1) * L.iplane + (c >> 1) : c;
+            s_patch[idx] = __ldg(wb + (size_t)r * L.ipitch + pc);
+        }
+        __syncthreads();
+        int code = NV_DEPTH_PASS;
+        for (int st = stage_begin; st < nstages; st++) {
+            const int k1 = s_first[st + 1];
+            double tmp = 0.;
+            for (int kb = k0; kb < k1; kb += 256) {
+                const TailRec cur = rec;
+                const int nk = (kb + 256 < k1 ? kb + 256 : k1) + tid;           // next round: same stage, or the head of the next one
+                rec = load_tail(ts, min(nk, nstumps - 1));
+                if (kb + tid < k1) {
+#define TW(o) lds_u32(wsa + (o))
+                    const int nr0 = (int)(TW(cur.a.x >> 16) + TW(cur.a.y & 0xffffu) - TW(cur.a.x & 0xffffu) - TW(cur.a.y >> 16));
+                    const int r1 = (int)(TW(cur.a.z & 0xffffu) - TW(cur.a.z >> 16) - TW(cur.a.w & 0xffffu) + TW(cur.a.w >> 16));
+                    const int w12 = (int)cur.b.w;
+                    int r = (int)(short)(w12 & 0xffff) * r1 + nr0;
+                    if (w12 >> 16) {
+                        const int r2 = (int)(TW(cur.b.x & 0xffffu) - TW(cur.b.x >> 16) - TW(cur.b.y & 0xffffu) + TW(cur.b.y >> 16));
+                        r += (w12 >> 16) * r2;
+                    }
+#undef TW
+                    add_if_lt(tmp, __fmul_rn(__int2float_rn(r), vnf), __uint_as_float(cur.b.z), __hiloint2double((int)cur.c.y, (int)cur.c.x));
+                }
+            }
+            // warps that hold no classifier of this stage contribute an exact 0
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) tmp = __dadd_rn(tmp, __shfl_xor_sync(0xffffffffu, tmp, d));
+            if (lane == 0) s_part[st & 1][warp] = tmp;
+            __syncthreads();
+            double total = s_base[st];
+#pragma unroll
+            for (int w = 0; w < 8; w++) total = __dadd_rn(total, s_part[st & 1][w]);
+            k0 = k1;
+            if (total < (double)s_thr[st]) { code = -st; break; }                  // block-uniform: every thread adds the same values
+        }
+        if (tid == 0) {
             if (depth) depth[L.wofs + iy * L.nx + ix] = (int16_t)code;
             if (code == NV_DEPTH_PASS) {
-                int pos = atomicAdd(&counters[1], 1);
+                const int pos = atomicAdd(&counters[1], 1);
                 if (pos < cand_cap) cand[pos] = q.x;
                 else counters[2] = 1;
             }
@@ -1217,16 +1314,26 @@ cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, con
     return cudaGetLastError();
 }
 
+cudaError_t launch_cascade_tail_block(const PlanDev *plan, const DevCascade *meta, const TailStump *tstumps, const double *tbase,
+                                      const uint32_t *sum, const uint2 *queue, int *counters, int cin, uint32_t *cand, int cand_cap,
+                                      int16_t *depth, int stage_begin, int skip_counter, cudaStream_t st)
+{
+    k_cascade_tail_block<<<148 * 4, 256, 0, st>>>(plan, meta, tstumps, tbase, sum, queue, counters, cin, cand, cand_cap, depth, stage_begin,
+                                                 skip_counter);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_cascade_tail_fast(const PlanDev *plan, const DevCascade *meta, const TailStump *tstumps, const double *tbase,
                                      const uint32_t *sum, const uint2 *tail, int *counters, uint32_t *cand, int cand_cap,
-                                     int16_t *depth, int stage_begin, cudaStream_t st, int smem_bytes)
+                                     int16_t *depth, int stage_begin, int stage_end, uint2 *deep, int deep_cap, cudaStream_t st,
+                                     int smem_bytes)
 {
 #ifndef NV_TAIL_THREADS
 #define NV_TAIL_THREADS 256
 #endif
     // smem_bytes is sized for eight warps (one patch per warp)
     k_cascade_tail_fast<<<148 * 8 * (256 / NV_TAIL_THREADS), NV_TAIL_THREADS, smem_bytes / (256 / NV_TAIL_THREADS), st>>>(
-        plan, meta, tstumps, tbase, sum, tail, counters, cand, cand_cap, depth, stage_begin);
+        plan, meta, tstumps, tbase, sum, tail, counters, cand, cand_cap, depth, stage_begin, stage_end, deep, deep_cap);
     return cudaGetLastError();
 }
 

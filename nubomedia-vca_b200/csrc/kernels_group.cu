@@ -7,11 +7,17 @@
 // similarity bit-matrix built by many blocks, then min-label propagation in one block (labels in shared
 // memory, one warp per matrix row, rows prefetched) — dense clusters converge in two or three sweeps, and
 // every component ends up labelled by its first member.
+//
+// Above NV_GROUP_UF_MIN candidates (a permissive model over a full frame: haarcascade_smile.xml leaves 15 000 on a 1080p
+// image) the n x n matrix is the whole cost, so the components are built another way: every candidate looks for similar
+// ones only where they can be — the canonical order is (level, row, column), similar rectangles differ in size by at most
+// 2 delta, i.e. sit on a few neighbouring levels, and in rows within delta — and links them with a lock-free union-find
+// whose root is the smallest index (k_uf_link, many blocks).  Same components, same labels (first member), so the rest
+// of k_group is shared.
 #include "internal.h"
 
-#ifndef GROUP_SMEM_LABELS
-#define GROUP_SMEM_LABELS 8192
-#endif
+
+#define GROUP_SMEM_LABELS NV_GROUP_UF_MIN      // the matrix path keeps its labels in shared memory
 
 __device__ __forceinline__ bool similar_rects(const int4 &a, const int4 &b, double eps)
 {
@@ -23,7 +29,7 @@ __device__ __forceinline__ bool similar_rects(const int4 &a, const int4 &b, doub
 // rank sort + candidate rectangles (A.6: cvRound of FLOAT products)
 __global__ void __launch_bounds__(256)
 k_cand_sort(const PlanDev *__restrict__ plan, const int *__restrict__ counters, const uint32_t *__restrict__ cand,
-            int cand_cap, uint32_t *__restrict__ sorted, int4 *__restrict__ rects)
+            int cand_cap, uint32_t *__restrict__ sorted, int4 *__restrict__ rects, int *__restrict__ label)
 {
     int n = min(counters[1], cand_cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -40,6 +46,73 @@ k_cand_sort(const PlanDev *__restrict__ plan, const int *__restrict__ counters, 
         r.w = __float2int_rn(__fmul_rn(__int2float_rn(plan->win_h), sc));
         sorted[rank] = key;
         rects[rank] = r;
+        if (label) label[rank] = rank;                            // union-find forest of the large-n path
+    }
+}
+
+__device__ __forceinline__ int uf_find(int *L, int a)
+{
+    int p;
+    while ((p = ((volatile int *)L)[a]) != a) a = p;
+    return a;
+}
+__device__ __forceinline__ void uf_union(int *L, int a, int b)
+{
+    bool done;
+    do {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) { int old = atomicMin(&L[b], a); done = old == b; b = old; }
+        else if (b < a) { int old = atomicMin(&L[a], b); done = old == a; a = old; }
+        else done = true;
+    } while (!done);
+}
+__device__ __forceinline__ int key_lower_bound(const uint32_t *__restrict__ keys, int n, uint32_t key)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// large n: candidate i against the candidates AFTER it in canonical order that can be similar to it
+__global__ void __launch_bounds__(256)
+k_uf_link(const PlanDev *__restrict__ plan, const int *__restrict__ counters, int cand_cap, const uint32_t *__restrict__ sorted,
+          const int4 *__restrict__ rects, int *__restrict__ label, double eps)
+{
+    const int n = min(counters[1], cand_cap);
+    if (n <= NV_GROUP_UF_MIN) return;
+    const int nlevels = plan->nlevels;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t key = sorted[i];
+        const int l = key >> 26;
+        const int4 a = rects[i];
+        for (int l2 = l; l2 < nlevels; l2++) {
+            const LevelDesc &L2 = plan->lv[l2];
+            const int w2 = __float2int_rn(__fmul_rn(__int2float_rn(plan->win_w), L2.scale));
+            const int h2 = __float2int_rn(__fmul_rn(__int2float_rn(plan->win_h), L2.scale));
+            // sizes grow with the level: delta is set by level l, and |w1 - w2| <= 2 delta is necessary for similarity
+            const double delta = eps * (double)(min(a.z, w2) + min(a.w, h2)) * 0.5;
+            if ((double)abs(w2 - a.z) > 2.0 * delta || (double)abs(h2 - a.w) > 2.0 * delta) break;
+            const double step = (double)L2.ystep * (double)L2.scale;
+            int lo = (int)floor(((double)a.y - delta - 1.0) / step) - 1, hi = (int)ceil(((double)a.y + delta + 1.0) / step) + 1;
+            lo = max(lo, 0); hi = min(hi, 8190);
+            int j0 = key_lower_bound(sorted, n, ((uint32_t)l2 << 26) | ((uint32_t)lo << 13));
+            const int j1 = key_lower_bound(sorted, n, ((uint32_t)l2 << 26) | ((uint32_t)(hi + 1) << 13));
+            if (l2 == l) j0 = max(j0, i + 1);
+            for (int j = j0; j < j1; j++)
+                if (similar_rects(a, rects[j], eps)) uf_union(label, i, j);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_uf_flatten(const int *__restrict__ counters, int cand_cap, int *__restrict__ label)
+{
+    const int n = min(counters[1], cand_cap);
+    if (n <= NV_GROUP_UF_MIN) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = uf_find(label, i);
+        if (r != i) label[i] = r;                                 // roots stay put, so concurrent finds only ever get shorter paths
     }
 }
 
@@ -49,6 +122,7 @@ k_adj(const int *__restrict__ counters, int cand_cap, const int4 *__restrict__ r
       double eps)
 {
     int n = min(counters[1], cand_cap), nw = (n + 31) >> 5;
+    if (n > NV_GROUP_UF_MIN) return;                              // large n: k_uf_link builds the components
     long long total = (long long)n * nw;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         int i = (int)(t / nw), w = (int)(t - (long long)i * nw);
@@ -93,7 +167,8 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
     int4 *out = reinterpret_cast<int4 *>(result + sizeof(ResultHeader));
     extern __shared__ int s_label[];                 // min(n, GROUP_SMEM_LABELS) labels; global scratch beyond that
     __shared__ int s_changed;
-    volatile int *label = n <= GROUP_SMEM_LABELS ? s_label : grp;
+    const bool uf = n > NV_GROUP_UF_MIN;                          // labels already final in grp (k_uf_link + k_uf_flatten)
+    volatile int *label = uf ? grp : s_label;
     int *cls = grp + cand_cap, *acc = grp + 2 * cand_cap, *keep = grp + 7 * cand_cap;
     int nout = 0;
 
@@ -115,13 +190,13 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
         }
         nout = carry;
     } else {
-        for (int i = tid; i < n; i += NV_GROUP_THREADS) label[i] = i;
+        if (!uf) for (int i = tid; i < n; i += NV_GROUP_THREADS) label[i] = i;
         __syncthreads();
         // min-label propagation until a fixed point: one warp per candidate row, lanes over the row's adjacency
         // words (the next row is fetched while the current one is reduced)
         const int lane = tid & 31, warp = tid >> 5;
         const int wpl = (nw + 31) >> 5;                  // words per lane (<= 8 for n <= 8192)
-        for (;;) {
+        for (; !uf;) {
             if (tid == 0) s_changed = 0;
             __syncthreads();
             uint32_t nxt[8];
@@ -243,11 +318,16 @@ cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *can
                          int4 *cand_rects, uint32_t *adj, int *grp, int min_neighbors, double eps, int img_w, int img_h,
                          uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch)
 {
-    k_cand_sort<<<nblocks, 256, 0, st>>>(plan, counters, cand, cand_cap, cand_sorted, cand_rects);
+    k_cand_sort<<<nblocks, 256, 0, st>>>(plan, counters, cand, cand_cap, cand_sorted, cand_rects, min_neighbors > 0 ? grp : nullptr);
     (*nlaunch)++;
     if (min_neighbors > 0) {
         k_adj<<<nblocks, 256, 0, st>>>(counters, cand_cap, cand_rects, adj, eps);
         (*nlaunch)++;
+        if (cand_cap > NV_GROUP_UF_MIN) {                         // both return at once unless the frame left that many candidates
+            k_uf_link<<<nblocks, 256, 0, st>>>(plan, counters, cand_cap, cand_sorted, cand_rects, grp, eps);
+            k_uf_flatten<<<nblocks, 256, 0, st>>>(counters, cand_cap, grp);
+            (*nlaunch) += 2;
+        }
     }
     k_group<<<1, NV_GROUP_THREADS, GROUP_SMEM_LABELS * sizeof(int), st>>>(counters, cand_cap, cand_rects, adj, grp, min_neighbors, eps,
                                                               img_w, img_h, result, result_cap);

@@ -18,7 +18,8 @@
 //   1. point operations, the new history values of the tile land in shared memory;
 //   2. block-local labelling in shared memory: horizontal pre-linking inside each thread's four pixels, then lock-free
 //      union-find (atomicMin links, the smaller index wins, so a root is its component's first pixel in raster order);
-//   3. per-root bounding box / first-seed reductions, aggregated per warp before they touch shared-memory atomics;
+//   3. per-root bounding box / first-seed reductions: per run of equal roots inside a thread's four pixels, then per warp
+//      (one REDUX when the warp sees a single component, which is the case inside a blob), then shared-memory atomics;
 //   4. components that stay inside the tile are final: reported at once.  Components on the tile's perimeter go to a
 //      small per-tile table (<= 192 slots), and the tile publishes the slot of each perimeter pixel;
 //   5. each tile edge is stitched by whichever of its two tiles arrives second (an arrival counter per edge): union-find
@@ -47,8 +48,9 @@ struct TrkParams {
     int4 *bbox;                     // [ntiles][TRK_SLOTS]: min x, min y, max x, max y (image coordinates)
     int *bseed;                     // [ntiles][TRK_SLOTS]: first seed pixel (y * w + x) or TRK_NONE
     int *parent;                    // [ntiles * TRK_SLOTS]
+    int *slotlist;                  // [ntiles * TRK_SLOTS]: every used slot (tile * TRK_SLOTS + s), appended tile by tile
     int *edge_flag;                 // arrival counters, one per tile edge
-    int *counters;                  // [0] components appended, [1] blocks done
+    int *counters;                  // [0] components appended, [1] blocks done, [2] slots in use (all tiles)
     int *keys;                      // [TRK_MAX_COMPONENTS]
     int4 *rects;                    // [TRK_MAX_COMPONENTS]
     int4 *out;                      // [1 + TRK_MAX_COMPONENTS]: (count, 0, 0, 0), rects in raster order of the first seed
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
     __shared__ float s_val[256];
     __shared__ union { float m[TRK_NPX]; int minx[TRK_NPX]; } s_a;          // history values, then (labels final) min x per root
     __shared__ int s_lab[TRK_NPX], s_maxx[TRK_NPX], s_maxy[TRK_NPX], s_seed[TRK_NPX];
-    __shared__ int s_nslots, s_edges[4], s_last;
+    __shared__ int s_nslots, s_edges[4], s_last, s_base;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x, tx = tile % P.ntx, ty = tile / P.ntx;
@@ -250,14 +252,25 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
                 cont = cont && root[half][j] == rk;
                 if (cont) { mxx = ux + j; if (sd == TRK_NONE && ((seedbits[half] >> j) & 1u)) sd = li + j; }
             }
-            const int r = start ? rk : -1 - lane;                  // a lane without a run matches nobody
             if (!start) { mnx = TRK_TW; mxx = -1; sd = TRK_NONE; }
-            const unsigned grp = __match_any_sync(0xffffffffu, r);
-            mnx = __reduce_min_sync(grp, mnx); mxx = __reduce_max_sync(grp, mxx); sd = __reduce_min_sync(grp, sd);
-            const int mxy = __reduce_max_sync(grp, start ? ly : -1);
-            if (start && lane == __ffs(grp) - 1) {
-                atomicMin(&s_a.minx[r], mnx); atomicMax(&s_maxx[r], mxx); atomicMax(&s_maxy[r], mxy);
-                if (sd != TRK_NONE) atomicMin(&s_seed[r], sd);
+            const int mxy0 = start ? ly : -1;
+            // a warp covers two 64-pixel rows: inside a blob every run of the round belongs to ONE component, and the whole
+            // warp reduces with the full-mask REDUX (the per-group form of __reduce_*_sync is emulated and slow)
+            const unsigned has = __ballot_sync(0xffffffffu, start);
+            if (has) {
+                const int leader = __ffs(has) - 1;
+                const int r0 = __shfl_sync(0xffffffffu, rk, leader);
+                if (__all_sync(0xffffffffu, !start || rk == r0)) {
+                    const int a = __reduce_min_sync(0xffffffffu, mnx), b = __reduce_max_sync(0xffffffffu, mxx);
+                    const int c = __reduce_max_sync(0xffffffffu, mxy0), d = __reduce_min_sync(0xffffffffu, sd);
+                    if (lane == leader) {
+                        atomicMin(&s_a.minx[r0], a); atomicMax(&s_maxx[r0], b); atomicMax(&s_maxy[r0], c);
+                        if (d != TRK_NONE) atomicMin(&s_seed[r0], d);
+                    }
+                } else if (start) {
+                    atomicMin(&s_a.minx[rk], mnx); atomicMax(&s_maxx[rk], mxx); atomicMax(&s_maxy[rk], mxy0);
+                    if (sd != TRK_NONE) atomicMin(&s_seed[rk], sd);
+                }
             }
         }
     }
@@ -292,7 +305,9 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
         const int r = s_lab[trk_perim_px(tid)];
         P.bslot[(size_t)tile * TRK_PERIM + tid] = r == TRK_NONE ? (unsigned short)0xffff : (unsigned short)s_maxx[r];
     }
-    if (tid == 0) P.bcount[tile] = s_nslots;
+    if (tid == 0) { P.bcount[tile] = s_nslots; s_base = s_nslots ? atomicAdd(&P.counters[2], s_nslots) : 0; }
+    __syncthreads();
+    for (int s2 = tid; s2 < s_nslots; s2 += blockDim.x) P.slotlist[s_base + s2] = tile * TRK_SLOTS + s2;     // for the last block
     __threadfence();
     __syncthreads();
 
@@ -322,34 +337,28 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
 
     // ---- 6. the last block: fold slot records into their roots, collect, order -----------------------------------------------
     __threadfence();
-    const int ntiles = P.ntx * P.nty;
-    for (int t = 0; t < ntiles; t++) {
-        const int ns = __ldcg(P.bcount + t);
-        for (int s = tid; s < ns; s += blockDim.x) {
-            const int gidx = t * TRK_SLOTS + s, r = trk_find(P.parent, gidx);
-            if (r == gidx) continue;
-            const int4 b = __ldcg(P.bbox + gidx);
-            int *rb = reinterpret_cast<int *>(P.bbox + r);
-            atomicMin(rb + 0, b.x); atomicMin(rb + 1, b.y); atomicMax(rb + 2, b.z); atomicMax(rb + 3, b.w);
-            const int sd = __ldcg(P.bseed + gidx);
-            if (sd != TRK_NONE) atomicMin(P.bseed + r, sd);
-        }
+    const int nused = ((volatile int *)P.counters)[2];
+    for (int i = tid; i < nused; i += blockDim.x) {
+        const int gidx = __ldcg(P.slotlist + i), r = trk_find(P.parent, gidx);
+        if (r == gidx) continue;
+        const int4 b = __ldcg(P.bbox + gidx);
+        int *rb = reinterpret_cast<int *>(P.bbox + r);
+        atomicMin(rb + 0, b.x); atomicMin(rb + 1, b.y); atomicMax(rb + 2, b.z); atomicMax(rb + 3, b.w);
+        const int sd = __ldcg(P.bseed + gidx);
+        if (sd != TRK_NONE) atomicMin(P.bseed + r, sd);
     }
     __threadfence();
     __syncthreads();
-    for (int t = 0; t < ntiles; t++) {
-        const int ns = __ldcg(P.bcount + t);
-        for (int s = tid; s < ns; s += blockDim.x) {
-            const int gidx = t * TRK_SLOTS + s;
-            if (((volatile int *)P.parent)[gidx] != gidx) continue;
-            const int sd = ((volatile int *)P.bseed)[gidx];
-            if (sd == TRK_NONE) continue;
-            const int pos = atomicAdd(&P.counters[0], 1);
-            if (pos < TRK_MAX_COMPONENTS) {
-                const volatile int *b = reinterpret_cast<volatile int *>(P.bbox + gidx);
-                P.keys[pos] = sd;
-                P.rects[pos] = make_int4(b[0], b[1], b[2] - b[0] + 1, b[3] - b[1] + 1);
-            }
+    for (int i = tid; i < nused; i += blockDim.x) {
+        const int gidx = __ldcg(P.slotlist + i);
+        if (((volatile int *)P.parent)[gidx] != gidx) continue;
+        const int sd = ((volatile int *)P.bseed)[gidx];
+        if (sd == TRK_NONE) continue;
+        const int pos = atomicAdd(&P.counters[0], 1);
+        if (pos < TRK_MAX_COMPONENTS) {
+            const volatile int *b = reinterpret_cast<volatile int *>(P.bbox + gidx);
+            P.keys[pos] = sd;
+            P.rects[pos] = make_int4(b[0], b[1], b[2] - b[0] + 1, b[3] - b[1] + 1);
         }
     }
     __threadfence();
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
     if (tid == 0) P.out[0] = make_int4(total, 0, 0, 0);
     __syncthreads();
     for (int e = tid; e < nh_edges + P.ntx * (P.nty - 1); e += blockDim.x) P.edge_flag[e] = 0;       // re-arm for the next frame
-    if (tid == 0) { P.counters[0] = 0; P.counters[1] = 0; }
+    if (tid == 0) { P.counters[0] = 0; P.counters[1] = 0; P.counters[2] = 0; }
 }
 
 size_t tracker_scratch_bytes(int w, int h, TrkLayout *lo)
@@ -378,6 +387,7 @@ size_t tracker_scratch_bytes(int w, int h, TrkLayout *lo)
     lo->out = take((size_t)(1 + TRK_MAX_COMPONENTS) * sizeof(int4));
     lo->bseed = take((size_t)nt * TRK_SLOTS * sizeof(int));
     lo->parent = take((size_t)nt * TRK_SLOTS * sizeof(int));
+    lo->slotlist = take((size_t)nt * TRK_SLOTS * sizeof(int));
     lo->bcount = take((size_t)nt * sizeof(int));
     lo->keys = take((size_t)TRK_MAX_COMPONENTS * sizeof(int));
     lo->bslot = take((size_t)nt * TRK_PERIM * sizeof(unsigned short));
@@ -399,6 +409,7 @@ cudaError_t launch_tracker(nv_ctx *ctx, int fmt, const SrcPlanes &src, int w, in
     P.prev = ctx->d_trk_prev; P.hist = ctx->d_trk_hist;
     P.bslot = reinterpret_cast<unsigned short *>(base + lo.bslot); P.bcount = reinterpret_cast<int *>(base + lo.bcount);
     P.bbox = reinterpret_cast<int4 *>(base + lo.bbox); P.bseed = reinterpret_cast<int *>(base + lo.bseed);
+    P.slotlist = reinterpret_cast<int *>(base + lo.slotlist);
     P.parent = reinterpret_cast<int *>(base + lo.parent); P.edge_flag = reinterpret_cast<int *>(base + lo.edge_flag);
     P.counters = reinterpret_cast<int *>(base + lo.counters); P.keys = reinterpret_cast<int *>(base + lo.keys);
     P.rects = reinterpret_cast<int4 *>(base + lo.rects); P.out = reinterpret_cast<int4 *>(base + lo.out);

@@ -119,6 +119,7 @@ _SIGS = {
     "nv_stage_name": (C.c_char_p, [_i]),
     "nv_ctx_set_profile": (_i, [_vp, _i]),
     "nv_ctx_get_stage_times": (_i, [_vp, C.POINTER(C.c_float), _i, _ip]),
+    "nv_ctx_get_tracker_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
     "nv_event_create": (_i, [C.POINTER(_vp)]),
     "nv_event_record": (_i, [_vp, _vp]),
     "nv_event_elapsed_ms": (_i, [_vp, _vp, C.POINTER(C.c_float)]),
@@ -472,6 +473,11 @@ class Context:
         _check(_lib.nv_tracker_process_yuv(self.handle, C.byref(f), float(ts_ms), C.byref(p), self._out, self._cap, C.byref(n)),
                "nv_tracker_process_yuv")
         return _rects(self._out, n.value)
+
+    def tracker_kernel_ms(self):
+        ms = C.c_float(0)
+        _check(_lib.nv_ctx_get_tracker_kernel_ms(self.handle, C.byref(ms)), "nv_ctx_get_tracker_kernel_ms")
+        return ms.value
 
     def tracker_reset(self):
         _check(_lib.nv_tracker_reset(self.handle), "nv_tracker_reset")

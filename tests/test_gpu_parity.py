@@ -99,6 +99,22 @@ def test_cfg3_full_size_golden(face, idx):
         big.close()
 
 
+def test_grouping_with_thousands_of_candidates(cascade_dir):
+    """A permissive model over a large image leaves thousands of raw candidates: groupRectangles then builds its classes by
+    neighbour search + union-find (k_uf_link) instead of the similarity bit-matrix; same classes, same order."""
+    nc = nv.Cascade(os.path.join(cascade_dir, "haarcascade_smile.xml"))
+    oc = O.Cascade(os.path.join(cascade_dir, "haarcascade_smile.xml"))
+    g = O.equalize_hist(O.bgr2gray(synth.frame(1280, 720, 4, 9, smin=0.2, smax=0.5)))
+    big = nv.Context(0, 1280, 720)
+    try:
+        for mn in (3, 1):
+            got = big.detect_multiscale(nc, g, 1.1, mn)
+            assert big.counters()["candidates"] > 2048
+            assert rects_equal(got, O.detect_multiscale(g, oc, 1.1, mn)), mn
+    finally:
+        big.close()
+
+
 def test_face_element_min_size_rule(ctx, face):
     # min_size=None -> Size(cols/20, rows/20), kmsfacedetect.cpp:811
     ncasc, ocasc = face
