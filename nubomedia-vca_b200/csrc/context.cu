@@ -722,18 +722,13 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
             prof_mark(ctx, 6);
             if (ctx->ps->bulk_end < casc->meta.nstages && ctx->cur_tail) {
                 // the survivors of the bulk stages (~15 000 per config-3 frame, most of them gone within a few stages): a warp
-                // per window for NV_TAIL_WARP_STAGES stages, then a block per window for the few that go deep — that chain
-                // (one window through every stage) was the latency floor of the frame
-                const int split = std::min(casc->meta.nstages, ctx->ps->bulk_end + NV_TAIL_WARP_STAGES);
+                // per window.  (Handing the deep ones to the block-per-window kernel after NV_TAIL_WARP_STAGES stages was
+                // measured: 55 us against 45 us isolated, 2538 against 2577 frames/s — with that many windows the warp kernel
+                // is bound by throughput, not by its deepest window; the split pays on small plans only.)
                 NV_CUDA(launch_cascade_tail_fast(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
-                                                 ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, ctx->ps->bulk_end, split, nullptr, qcap, st,
-                                                 8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));
+                                                 ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, ctx->ps->bulk_end, casc->meta.nstages,
+                                                 nullptr, qcap, st, 8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));
                 nl++;
-                if (split < casc->meta.nstages) {
-                    NV_CUDA(launch_cascade_tail_block(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
-                                                      ctx->d_counters, 6, ctx->d_cand, ctx->cand_cap, depth, split, 3, st));
-                    nl++;
-                }
             } else if (ctx->ps->bulk_end < casc->meta.nstages) {
                 NV_CUDA(launch_cascade_tail(ctx->ps->d_plan, meta, stumps, ctx->d_sum, ctx->d_queue, ctx->d_counters, ctx->d_cand,
                                             ctx->cand_cap, depth, ctx->ps->bulk_end, casc->h.order_free, 148 * 8, st,

@@ -594,6 +594,9 @@ __device__ __forceinline__ int uniformize(int v, int bits)
 #ifndef NV_CLS_UNROLL
 #define NV_CLS_UNROLL 2            // weak classifiers in flight per lane in the bulk kernel's inner loops
 #endif
+#ifndef NV_CLS_PACK_GAIN
+#define NV_CLS_PACK_GAIN 2         // a stage of a tile takes the packed schedule when it saves at least this many warp steps
+#endif
 constexpr int CLS_UNROLL = NV_CLS_UNROLL;
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
@@ -694,6 +697,9 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ uint32_t s_mask[3][2][32];                        // rotating alive masks: [buffer][member / 32][class]
     __shared__ uint32_t s_words[NV_CTY][2];
+#ifdef NV_CLS_PACK
+    __shared__ unsigned short s_list[NV_CTX * NV_CTY];           // packed schedule of a stage: (class << 6) | member, rank-major
+#endif
     const PlanDev *__restrict__ plan = P.plan;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = uniformize(tid >> 5, 3);
@@ -746,6 +752,63 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
         if (warp == 0) { s_mask[zer][0][lane] = 0u; s_mask[zer][1][lane] = 0u; }
         unsigned long long rem = ((unsigned long long)mhi << 32) | mlo, pass_bits = 0ull;
         for (int i = 0; i < warp; i++) rem &= rem - 1ull;        // warp w takes the set bits of rank w, w + 8, ...
+#ifdef NV_CLS_PACK
+        // ---- packed schedule (experiment of round 2, OFF by default: measured slower, profiles/r2_summary.md) ---------------
+        // The rank schedule below costs maxc warp steps per weak classifier (one member of every class per step) whatever
+        // the number of windows alive.  When the classes are unbalanced — the sparse later stages: 40 windows, the fullest
+        // class holds 5 — the members are laid out RANK-MAJOR in a list (all first members, then all second members, ...)
+        // and the warps take 32 consecutive entries per step: ceil(N / 32) steps.  Entries of one rank belong to different
+        // classes, so a step only conflicts where it spans several ranks: a class with M members still costs about M
+        // shared-memory wavefronts per load (what it costs below), but the instructions are issued N / 32 times, not M.
+        // Measured on config 3: 12 % fewer warp instructions, but a step that straddles several ranks replays, the
+        // shared-memory pipe (already at 67-74 %) takes 20 % more wavefronts and the list costs a second barrier per stage:
+        // 0.392 ms against 0.346 ms for the bulk stages, 2411 against 2540 frames/s.
+        {
+            const int cnt = __popc(mlo) + __popc(mhi);
+            const int nalive = uniformize(__reduce_add_sync(0xffffffffu, cnt), 12);
+            const int nsteps = (nalive + 31) >> 5;
+            if (maxc - nsteps >= NV_CLS_PACK_GAIN) {
+                int base = 0;
+                for (int r = 0; r < maxc; r++) {                 // every warp counts, warp (r mod 8) writes rank r
+                    const uint32_t b = __ballot_sync(0xffffffffu, cnt > r);
+                    if ((r & 7) == warp) {
+                        if (cnt > r) s_list[base + __popc(b & ((1u << lane) - 1u))] = (unsigned short)((lane << 6) | (__ffsll((long long)rem) - 1));
+#pragma unroll
+                        for (int q = 0; q < 8; q++) rem &= rem - 1ull;
+                    }
+                    base += __popc(b);
+                }
+                __syncthreads();
+                for (int t = warp; t < nsteps; t += 16) {        // two list entries per lane and round: steps t and t + 8
+                    int cls[2], bit[2], ly[2], lx[2]; bool active[2], pass[2]; uint32_t wa[2]; float vnf[2];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const int p = (t + 8 * i) * 32 + lane;
+                        active[i] = p < nalive;
+                        const int e = active[i] ? (int)s_list[p] : (lane << 6);
+                        cls[i] = e >> 6; bit[i] = e & 63;
+                        ly[i] = bit[i] >> 1; lx[i] = ((cls[i] - K * ly[i]) & 31) + ((bit[i] & 1) << 5);
+                        wa[i] = tile_sa + (uint32_t)(ly[i] * rowb + lx[i] * 4);
+                        vnf[i] = active[i] ? __ldg(vnf_tile + ly[i] * L.nx + lx[i]) : 0.f;
+                    }
+                    if (t + 8 < nsteps) class_stage<FAST, 2>(P, si, wa, vnf, pass);
+                    else {
+                        const uint32_t wa1[1] = {wa[0]}; const float vnf1[1] = {vnf[0]}; bool pass1[1];
+                        class_stage<FAST, 1>(P, si, wa1, vnf1, pass1);
+                        pass[0] = pass1[0]; pass[1] = false;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        if (active[i] && pass[i]) atomicOr(&s_mask[nxt][bit[i] >> 5][cls[i]], 1u << (bit[i] & 31));
+                        if (P.depth && active[i] && !pass[i]) P.depth[L.wofs + (iy0 + ly[i]) * L.nx + ix0 + lx[i]] = (int16_t)(-st);
+                    }
+                }
+                __syncthreads();
+                cur = nxt;
+                continue;
+            }
+        }
+#endif
         int j = warp;
         for (; j + 8 < maxc; j += 16) {                          // two windows per lane and round
             int bit[2]; bool active[2], pass[2]; uint32_t wa[2]; float vnf[2]; int ly[2], lx[2];

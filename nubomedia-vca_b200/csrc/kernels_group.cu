@@ -12,7 +12,7 @@
 // image) the n x n matrix is the whole cost, so the components are built another way: every candidate looks for similar
 // ones only where they can be — the canonical order is (level, row, column), similar rectangles differ in size by at most
 // 2 delta, i.e. sit on a few neighbouring levels, and in rows within delta — and links them with a lock-free union-find
-// whose root is the smallest index (k_uf_link, many blocks).  Same components, same labels (first member), so the rest
+// whose root is the smallest index (uf_link inside k_adj, many blocks).  Same components, same labels (first member), so the rest
 // of k_group is shared.
 #include "internal.h"
 
@@ -75,12 +75,9 @@ __device__ __forceinline__ int key_lower_bound(const uint32_t *__restrict__ keys
 }
 
 // large n: candidate i against the candidates AFTER it in canonical order that can be similar to it
-__global__ void __launch_bounds__(256)
-k_uf_link(const PlanDev *__restrict__ plan, const int *__restrict__ counters, int cand_cap, const uint32_t *__restrict__ sorted,
-          const int4 *__restrict__ rects, int *__restrict__ label, double eps)
+__device__ void uf_link(const PlanDev *__restrict__ plan, int n, const uint32_t *__restrict__ sorted,
+                        const int4 *__restrict__ rects, int *__restrict__ label, double eps)
 {
-    const int n = min(counters[1], cand_cap);
-    if (n <= NV_GROUP_UF_MIN) return;
     const int nlevels = plan->nlevels;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t key = sorted[i];
@@ -105,24 +102,13 @@ k_uf_link(const PlanDev *__restrict__ plan, const int *__restrict__ counters, in
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_uf_flatten(const int *__restrict__ counters, int cand_cap, int *__restrict__ label)
-{
-    const int n = min(counters[1], cand_cap);
-    if (n <= NV_GROUP_UF_MIN) return;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int r = uf_find(label, i);
-        if (r != i) label[i] = r;                                 // roots stay put, so concurrent finds only ever get shorter paths
-    }
-}
-
 // similarity bit-matrix: word (i, w) holds the similarity of candidate i with candidates 32w .. 32w+31
 __global__ void __launch_bounds__(256)
-k_adj(const int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects, uint32_t *__restrict__ adj,
-      double eps)
+k_adj(const PlanDev *__restrict__ plan, const int *__restrict__ counters, int cand_cap, const uint32_t *__restrict__ sorted,
+      const int4 *__restrict__ rects, uint32_t *__restrict__ adj, int *__restrict__ label, double eps)
 {
     int n = min(counters[1], cand_cap), nw = (n + 31) >> 5;
-    if (n > NV_GROUP_UF_MIN) return;                              // large n: k_uf_link builds the components
+    if (n > NV_GROUP_UF_MIN) { uf_link(plan, n, sorted, rects, label, eps); return; }     // large n: components by union-find
     long long total = (long long)n * nw;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         int i = (int)(t / nw), w = (int)(t - (long long)i * nw);
@@ -167,7 +153,7 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
     int4 *out = reinterpret_cast<int4 *>(result + sizeof(ResultHeader));
     extern __shared__ int s_label[];                 // min(n, GROUP_SMEM_LABELS) labels; global scratch beyond that
     __shared__ int s_changed;
-    const bool uf = n > NV_GROUP_UF_MIN;                          // labels already final in grp (k_uf_link + k_uf_flatten)
+    const bool uf = n > NV_GROUP_UF_MIN;                          // labels already final in grp (uf_link in k_adj, flattened below)
     volatile int *label = uf ? grp : s_label;
     int *cls = grp + cand_cap, *acc = grp + 2 * cand_cap, *keep = grp + 7 * cand_cap;
     int nout = 0;
@@ -191,6 +177,9 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
         nout = carry;
     } else {
         if (!uf) for (int i = tid; i < n; i += NV_GROUP_THREADS) label[i] = i;
+        else {                                                    // flatten the forest k_adj linked: roots stay put, paths only get shorter
+            for (int i = tid; i < n; i += NV_GROUP_THREADS) { const int r = uf_find(grp, i); if (r != i) grp[i] = r; }
+        }
         __syncthreads();
         // min-label propagation until a fixed point: one warp per candidate row, lanes over the row's adjacency
         // words (the next row is fetched while the current one is reduced)
@@ -321,13 +310,8 @@ cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *can
     k_cand_sort<<<nblocks, 256, 0, st>>>(plan, counters, cand, cand_cap, cand_sorted, cand_rects, min_neighbors > 0 ? grp : nullptr);
     (*nlaunch)++;
     if (min_neighbors > 0) {
-        k_adj<<<nblocks, 256, 0, st>>>(counters, cand_cap, cand_rects, adj, eps);
+        k_adj<<<nblocks, 256, 0, st>>>(plan, counters, cand_cap, cand_sorted, cand_rects, adj, grp, eps);
         (*nlaunch)++;
-        if (cand_cap > NV_GROUP_UF_MIN) {                         // both return at once unless the frame left that many candidates
-            k_uf_link<<<nblocks, 256, 0, st>>>(plan, counters, cand_cap, cand_sorted, cand_rects, grp, eps);
-            k_uf_flatten<<<nblocks, 256, 0, st>>>(counters, cand_cap, grp);
-            (*nlaunch) += 2;
-        }
     }
     k_group<<<1, NV_GROUP_THREADS, GROUP_SMEM_LABELS * sizeof(int), st>>>(counters, cand_cap, cand_rects, adj, grp, min_neighbors, eps,
                                                               img_w, img_h, result, result_cap);

@@ -25,7 +25,8 @@
 //   5. each tile edge is stitched by whichever of its two tiles arrives second (an arrival counter per edge): union-find
 //      over the slots, across tiles, in global memory;
 //   6. the last block to finish folds the slot records into their roots, appends those that own a seed, and writes the
-//      components in raster order of their first seed.  It also re-arms the counters: the kernel cleans up after itself.
+//      components in raster order of their first seed.  Counters and edge flags are re-armed on the way: the kernel cleans
+//      up after itself.
 // No second launch, no grid-wide barrier: nothing ever waits for another block.
 #include <limits.h>
 
@@ -38,6 +39,18 @@
 #define TRK_PERIM (2 * TRK_TW + 2 * TRK_TH)          // top 0..63, bottom 64..127, left 128..159, right 160..191
 #define TRK_SLOTS TRK_PERIM
 #define TRK_NONE 0x7fffffff
+
+// -DNV_TRK_TRACE: clock64 at a dozen checkpoints of every block (tools/trk_trace.py builds that variant and prints the phases)
+#ifdef NV_TRK_TRACE
+__device__ long long g_trk_trace[4096 * 16];
+#define TRK_T(k) do { if (threadIdx.x == 0 && blockIdx.x < 4096) g_trk_trace[blockIdx.x * 16 + (k)] = clock64(); } while (0)
+extern "C" __attribute__((visibility("default"))) int nv_debug_trk_trace(long long *out, int nblocks)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_trk_trace, sizeof(long long) * 16 * (size_t)(nblocks < 4096 ? nblocks : 4096));
+}
+#else
+#define TRK_T(k) do { } while (0)
+#endif
 
 struct TrkParams {
     SrcPlanes src;
@@ -94,21 +107,26 @@ __device__ __forceinline__ int trk_perim_px(int k)
     return (k - 2 * TRK_TW - TRK_TH) * TRK_TW + TRK_TW - 1;
 }
 
-// stitches the edge between tile a (left / upper) and tile b (right / lower); vertical != 0: b lies below a
+// stitches the edge between tile a (left / upper) and tile b (right / lower); vertical != 0: b lies below a.  Runs on the
+// first two warps of the block (an edge is at most 64 pixels long); a pixel pair that repeats its left neighbour's
+// (slot, slot) pair is skipped: along a blob that leaves one union per edge instead of one per pixel.
 __device__ void trk_stitch(const TrkParams &P, const float *s_val, int a, int b, int vertical)
 {
+    if (threadIdx.x >= 64) return;
     const int ax0 = (a % P.ntx) * TRK_TW, ay0 = (a / P.ntx) * TRK_TH, bx0 = (b % P.ntx) * TRK_TW, by0 = (b / P.ntx) * TRK_TH;
-    const int len = vertical ? TRK_TW : TRK_TH;
-    for (int i = threadIdx.x; i < len; i += blockDim.x) {
-        int xa, ya, xb, yb, ka, kb;
-        if (vertical) { xa = ax0 + i; ya = ay0 + TRK_TH - 1; xb = bx0 + i; yb = by0; ka = TRK_TW + i; kb = i; }
-        else { xa = ax0 + TRK_TW - 1; ya = ay0 + i; xb = bx0; yb = by0 + i; ka = 2 * TRK_TW + TRK_TH + i; kb = 2 * TRK_TW + i; }
-        if (xa >= P.w || xb >= P.w || ya >= P.h || yb >= P.h) continue;
-        unsigned sa = __ldcg(P.bslot + (size_t)a * TRK_PERIM + ka), sb = __ldcg(P.bslot + (size_t)b * TRK_PERIM + kb);
-        if (sa == 0xffffu || sb == 0xffffu) continue;
-        float va = s_val[__ldcg(P.hist + (size_t)ya * P.w + xa)], vb = s_val[__ldcg(P.hist + (size_t)yb * P.w + xb)];
-        if (trk_joined(va, vb)) trk_union(P.parent, a * TRK_SLOTS + (int)sa, b * TRK_SLOTS + (int)sb);
+    const int len = vertical ? TRK_TW : TRK_TH, i = threadIdx.x, lane = threadIdx.x & 31;
+    int xa, ya, xb, yb, ka, kb;
+    if (vertical) { xa = ax0 + i; ya = ay0 + TRK_TH - 1; xb = bx0 + i; yb = by0; ka = TRK_TW + i; kb = i; }
+    else { xa = ax0 + TRK_TW - 1; ya = ay0 + i; xb = bx0; yb = by0 + i; ka = 2 * TRK_TW + TRK_TH + i; kb = 2 * TRK_TW + i; }
+    unsigned sa = 0xffffu, sb = 0xffffu;
+    bool joined = false;
+    if (i < len && xa < P.w && xb < P.w && ya < P.h && yb < P.h) {
+        sa = __ldcg(P.bslot + (size_t)a * TRK_PERIM + ka); sb = __ldcg(P.bslot + (size_t)b * TRK_PERIM + kb);
+        if (sa != 0xffffu && sb != 0xffffu)
+            joined = trk_joined(s_val[__ldcg(P.hist + (size_t)ya * P.w + xa)], s_val[__ldcg(P.hist + (size_t)yb * P.w + xb)]);
     }
+    const unsigned key = joined ? (sa << 16) | sb : 0xffffffffu, left = __shfl_up_sync(0xffffffffu, key, 1);
+    if (joined && (lane == 0 || left != key)) trk_union(P.parent, a * TRK_SLOTS + (int)sa, b * TRK_SLOTS + (int)sb);
 }
 
 // FMT 0: BGRA (the reference's caps, gstnubotracker.cpp:57-61); 1 / 2 / 3: I420 / NV12 / NV21 planes — the 4:2:0 ingest
@@ -124,13 +142,16 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x, tx = tile % P.ntx, ty = tile / P.ntx;
     const int x0 = tx * TRK_TW, y0 = ty * TRK_TH;
+    TRK_T(0);
     s_val[tid] = P.val[tid];
     if (tid == 0) s_nslots = 0;
     __syncthreads();
+    TRK_T(1);
 
     // ---- 1. point operations: two units of four pixels per thread (rows ly and ly + 16) ---------------------------------
     const int ux = (tid & 15) * 4;
     unsigned seedbits[2] = {0u, 0u};                               // bit k: pixel k of the unit has mhi == ts
+    int mine = 0;                                                  // does this thread hold any pixel with history?
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         const int ly = (tid >> 4) + half * 16, y = y0 + ly, x = x0 + ux, li = ly * TRK_TW + ux;
@@ -191,39 +212,75 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             s_a.m[li + k] = m[k];
+            mine |= m[k] != 0.f;
             lab = m[k] == 0.f ? TRK_NONE : (k > 0 && lab != TRK_NONE && trk_joined(m[k - 1], m[k])) ? lab : li + k;
             s_lab[li + k] = lab;
         }
     }
     if (P.first) return;                                           // the first frame only primes img_prev (:360)
-    __syncthreads();
+    // a tile without any history (most of a frame, most of the time) has nothing to label: it only publishes an empty
+    // perimeter and takes part in the edge and completion protocol
+    const bool empty = !__syncthreads_or(mine);
+    TRK_T(2);
+    int root[2][4] = {{TRK_NONE, TRK_NONE, TRK_NONE, TRK_NONE}, {TRK_NONE, TRK_NONE, TRK_NONE, TRK_NONE}};
+    if (!empty) {
 
-    // ---- 2b. unions across unit boundaries and between rows ----------------------------------------------------------------
+    // ---- 2b. unions: along the rows first, then between rows, each followed by pointer jumping -----------------------------
+    // Links point at smaller indices, so a blob that fills the tile would leave chains of up to 16 + 32 links (units of a
+    // row, rows of the tile) and every find of the next phase would walk them through shared memory (measured: 31 000
+    // cycles for the flatten of such a tile).  Pointer jumping (label <- label of label until nothing moves) turns the
+    // forest into stars in log2(chain) block-wide steps; roots never move, so it may run between the two union phases.
+    auto jump = [&]() {
+        for (;;) {
+            int moved = 0;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int li = ((tid >> 4) + half * 16) * TRK_TW + ux;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int p = ((volatile int *)s_lab)[li + k];
+                    if (p == TRK_NONE) continue;
+                    const int pp = ((volatile int *)s_lab)[p];
+                    if (pp != p) { s_lab[li + k] = pp; moved = 1; }
+                }
+            }
+            if (!__syncthreads_or(moved)) break;
+        }
+    };
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int li = ((tid >> 4) + half * 16) * TRK_TW + ux;
+        if (ux + 4 < TRK_TW && trk_joined(s_a.m[li + 3], s_a.m[li + 4])) trk_union(s_lab, li + 3, li + 4);
+    }
+    __syncthreads();
+    jump();
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         const int ly = (tid >> 4) + half * 16, li = ly * TRK_TW + ux;
-        if (ux + 4 < TRK_TW && trk_joined(s_a.m[li + 3], s_a.m[li + 4])) trk_union(s_lab, li + 3, li + 4);
         if (ly + 1 < TRK_TH) {
-            bool prev_v = false;                                   // was the vertical edge one pixel to the left joined?
+            // was the vertical edge one pixel to the left joined?  (also across the unit boundary: inside a blob only the
+            // first column of every row pair is linked, one union per pair of runs instead of one per pixel)
+            bool prev_v = ux > 0 && trk_joined(s_a.m[li - 1], s_a.m[li - 1 + TRK_TW]);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const float a = s_a.m[li + k], b = s_a.m[li + k + TRK_TW];
                 const bool v = trk_joined(a, b);
-                // skip an edge that closes a 2x2 cycle whose other three edges are joined (inside the unit only)
-                const bool redundant = v && k > 0 && prev_v && trk_joined(s_a.m[li + k - 1], a) && trk_joined(s_a.m[li + k - 1 + TRK_TW], b);
+                // skip an edge that closes a 2x2 cycle whose other three edges are joined
+                const bool redundant = v && (k > 0 || ux > 0) && prev_v && trk_joined(s_a.m[li + k - 1], a) && trk_joined(s_a.m[li + k - 1 + TRK_TW], b);
                 if (v && !redundant) trk_union(s_lab, li + k, li + k + TRK_TW);
                 prev_v = v;
             }
         }
     }
     __syncthreads();
+    TRK_T(3);
     // ---- 2c. flatten -----------------------------------------------------------------------------------------------------
-    int root[2][4];
+    jump();
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        const int ly = (tid >> 4) + half * 16, li = ly * TRK_TW + ux;
+        const int li = ((tid >> 4) + half * 16) * TRK_TW + ux;
 #pragma unroll
-        for (int k = 0; k < 4; k++) root[half][k] = s_lab[li + k] == TRK_NONE ? TRK_NONE : trk_find(s_lab, li + k);
+        for (int k = 0; k < 4; k++) root[half][k] = s_lab[li + k];
     }
     __syncthreads();                                               // every find is done: s_a.m is dead, s_lab may be rewritten
 #pragma unroll
@@ -236,6 +293,7 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
         }
     }
     __syncthreads();
+    TRK_T(4);
 
     // ---- 3. per-root reductions: runs of equal root inside a unit first, lanes with the same root next, then one atomic ---
 #pragma unroll
@@ -275,6 +333,7 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
         }
     }
     __syncthreads();
+    TRK_T(5);
 
     // ---- 4. roots: final inside the tile, or a slot of the perimeter table ------------------------------------------------
     int *const parent = P.parent + (size_t)tile * TRK_SLOTS;
@@ -301,6 +360,7 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
         }
     }
     __syncthreads();
+    }   // !empty
     if (tid < TRK_PERIM) {
         const int r = s_lab[trk_perim_px(tid)];
         P.bslot[(size_t)tile * TRK_PERIM + tid] = r == TRK_NONE ? (unsigned short)0xffff : (unsigned short)s_maxx[r];
@@ -311,6 +371,7 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
     __threadfence();
     __syncthreads();
 
+    TRK_T(6);
     // ---- 5. stitch the edges this tile is the second to reach ---------------------------------------------------------------
     const int nh_edges = (P.ntx - 1) * P.nty;
     if (tid < 4) {
@@ -319,23 +380,30 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
         if (tid == 1 && tx > 0) e = ty * (P.ntx - 1) + tx - 1;                            // left
         if (tid == 2 && ty + 1 < P.nty) e = nh_edges + ty * P.ntx + tx;                   // below
         if (tid == 3 && ty > 0) e = nh_edges + (ty - 1) * P.ntx + tx;                     // above
-        s_edges[tid] = e >= 0 && atomicAdd(&P.edge_flag[e], 1) == 1 ? 1 : 0;
+        const bool second = e >= 0 && atomicAdd(&P.edge_flag[e], 1) == 1;
+        if (second) P.edge_flag[e] = 0;                            // both tiles have been here: re-armed for the next frame
+        s_edges[tid] = second ? 1 : 0;
     }
     __syncthreads();
+    TRK_T(7);
     if (s_edges[0] || s_edges[1] || s_edges[2] || s_edges[3]) {
-        __threadfence();
+        __threadfence();                                           // the other tile published before it arrived at the edge
         if (s_edges[0]) trk_stitch(P, s_val, tile, tile + 1, 0);
         if (s_edges[1]) trk_stitch(P, s_val, tile - 1, tile, 0);
         if (s_edges[2]) trk_stitch(P, s_val, tile, tile + P.ntx, 1);
         if (s_edges[3]) trk_stitch(P, s_val, tile - P.ntx, tile, 1);
+        __threadfence();
     }
-    __threadfence();
     __syncthreads();
+    TRK_T(8);
     if (tid == 0) s_last = atomicAdd(&P.counters[1], 1) == P.ntx * P.nty - 1;
     __syncthreads();
+    TRK_T(9);
     if (!s_last) return;
 
-    // ---- 6. the last block: fold slot records into their roots, collect, order -----------------------------------------------
+    // ---- 6. the last block: fold slot records into their roots, collect, order ------------------------------------------------
+    // one block from here on: __syncthreads() orders its own global accesses, the fence below is the acquire side of the
+    // other blocks' releases
     __threadfence();
     const int nused = ((volatile int *)P.counters)[2];
     for (int i = tid; i < nused; i += blockDim.x) {
@@ -347,7 +415,6 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
         const int sd = __ldcg(P.bseed + gidx);
         if (sd != TRK_NONE) atomicMin(P.bseed + r, sd);
     }
-    __threadfence();
     __syncthreads();
     for (int i = tid; i < nused; i += blockDim.x) {
         const int gidx = __ldcg(P.slotlist + i);
@@ -361,19 +428,23 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
             P.rects[pos] = make_int4(b[0], b[1], b[2] - b[0] + 1, b[3] - b[1] + 1);
         }
     }
-    __threadfence();
     __syncthreads();
     const int total = ((volatile int *)P.counters)[0], n = min(total, TRK_MAX_COMPONENTS);
-    for (int i = tid; i < n; i += blockDim.x) {                    // rank by first seed pixel (keys are distinct)
-        const int key = __ldcg(P.keys + i);
+    // rank by first seed pixel (keys are distinct); up to a tile's worth of keys is ranked out of shared memory
+    const bool in_smem = n <= TRK_NPX;
+    if (in_smem) {
+        for (int i = tid; i < n; i += blockDim.x) s_lab[i] = __ldcg(P.keys + i);
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += blockDim.x) {
+        const int key = in_smem ? s_lab[i] : __ldcg(P.keys + i);
         int rank = 0;
-        for (int j = 0; j < n; j++) rank += __ldcg(P.keys + j) < key;
+        if (in_smem) for (int j = 0; j < n; j++) rank += s_lab[j] < key;
+        else for (int j = 0; j < n; j++) rank += __ldcg(P.keys + j) < key;
         P.out[1 + rank] = __ldcg(P.rects + i);
     }
-    if (tid == 0) P.out[0] = make_int4(total, 0, 0, 0);
-    __syncthreads();
-    for (int e = tid; e < nh_edges + P.ntx * (P.nty - 1); e += blockDim.x) P.edge_flag[e] = 0;       // re-arm for the next frame
-    if (tid == 0) { P.counters[0] = 0; P.counters[1] = 0; P.counters[2] = 0; }
+    if (tid == 0) { P.out[0] = make_int4(total, 0, 0, 0); P.counters[0] = 0; P.counters[1] = 0; P.counters[2] = 0; }
+    TRK_T(10);
 }
 
 size_t tracker_scratch_bytes(int w, int h, TrkLayout *lo)

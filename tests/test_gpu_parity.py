@@ -101,7 +101,7 @@ def test_cfg3_full_size_golden(face, idx):
 
 def test_grouping_with_thousands_of_candidates(cascade_dir):
     """A permissive model over a large image leaves thousands of raw candidates: groupRectangles then builds its classes by
-    neighbour search + union-find (k_uf_link) instead of the similarity bit-matrix; same classes, same order."""
+    neighbour search + union-find (uf_link, kernels_group.cu) instead of the similarity bit-matrix; same classes, same order."""
     nc = nv.Cascade(os.path.join(cascade_dir, "haarcascade_smile.xml"))
     oc = O.Cascade(os.path.join(cascade_dir, "haarcascade_smile.xml"))
     g = O.equalize_hist(O.bgr2gray(synth.frame(1280, 720, 4, 9, smin=0.2, smax=0.5)))
