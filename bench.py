@@ -765,13 +765,13 @@ def main():
                 # measured L2 and L1/TEX traffic of the bulk kernel (ncu lts__t_bytes.sum / l1tex__t_bytes.sum, profiles/) over
                 # its isolated CUDA-event time, against the peaks ncu reports for this part in the same capture
                 t = iso["cascade_tiles"] * 1e-3
-                line["roofline"]["l2"] = {"achieved": tj["tile_lts_bytes_per_frame"] / t / 1e9, "peak": tj.get("lts_peak_gbs"), "unit": "GB/s",
-                                          "frac": (tj["tile_lts_bytes_per_frame"] / t / 1e9 / tj["lts_peak_gbs"]) if tj.get("lts_peak_gbs") else None,
-                                          "bytes_per_frame": tj["tile_lts_bytes_per_frame"], "source": tj.get("lts_source")}
+                line["roofline"]["l2"] = {"achieved": tj["tile_lts_bytes_per_frame"] / t / 1e9, "unit": "GB/s",
+                                          "bytes_per_frame": tj["tile_lts_bytes_per_frame"],
+                                          "ncu_pct_of_peak_per_launch": tj.get("lts_ncu_pct_of_peak"), "source": tj.get("lts_source")}
                 if tj.get("tile_l1tex_bytes_per_frame"):
                     line["roofline"]["l1tex"] = {"achieved": tj["tile_l1tex_bytes_per_frame"] / t / 1e9, "unit": "GB/s",
-                                                 "bytes_per_frame": tj["tile_l1tex_bytes_per_frame"], "peak": tj.get("l1tex_peak_gbs"),
-                                                 "frac": (tj["tile_l1tex_bytes_per_frame"] / t / 1e9 / tj["l1tex_peak_gbs"]) if tj.get("l1tex_peak_gbs") else None}
+                                                 "bytes_per_frame": tj["tile_l1tex_bytes_per_frame"],
+                                                 "ncu_pct_of_peak_per_launch": tj.get("l1tex_ncu_pct_of_peak")}
         if aux:
             line["aux"] = aux
         if not args.no_cpu_baseline and world == 1:

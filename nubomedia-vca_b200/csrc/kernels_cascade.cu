@@ -753,39 +753,56 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
         unsigned long long rem = ((unsigned long long)mhi << 32) | mlo, pass_bits = 0ull;
         for (int i = 0; i < warp; i++) rem &= rem - 1ull;        // warp w takes the set bits of rank w, w + 8, ...
 #ifdef NV_CLS_PACK
-        // ---- packed schedule (experiment of round 2, OFF by default: measured slower, profiles/r2_summary.md) ---------------
+        // ---- packed schedule (experiment of round 2, OFF by default: measured slower twice, profiles/r2_summary.md) ----------
         // The rank schedule below costs maxc warp steps per weak classifier (one member of every class per step) whatever
         // the number of windows alive.  When the classes are unbalanced — the sparse later stages: 40 windows, the fullest
         // class holds 5 — the members are laid out RANK-MAJOR in a list (all first members, then all second members, ...)
-        // and the warps take 32 consecutive entries per step: ceil(N / 32) steps.  Entries of one rank belong to different
-        // classes, so a step only conflicts where it spans several ranks: a class with M members still costs about M
-        // shared-memory wavefronts per load (what it costs below), but the instructions are issued N / 32 times, not M.
-        // Measured on config 3: 12 % fewer warp instructions, but a step that straddles several ranks replays, the
-        // shared-memory pipe (already at 67-74 %) takes 20 % more wavefronts and the list costs a second barrier per stage:
-        // 0.392 ms against 0.346 ms for the bulk stages, 2411 against 2540 frames/s.
+        // and the warps take 32 consecutive entries per step.  Entries of one rank belong to different classes, so a step
+        // only conflicts where it holds several ranks.
+        //   variant 1, steps of 32 consecutive entries (ceil(N / 32) steps): 9-12 % fewer warp instructions, but steps
+        //     straddle ranks, the shared-memory pipe (already at 67-74 %) took 20 % more wavefronts, 40 % of them replays:
+        //     bulk stages 0.392 ms against 0.346 ms, 2411 against 2540 frames/s;
+        //   variant 2 (below), whole ranks packed into a step while they fit, so that the wavefront count stays what the
+        //     rank schedule pays: 0.43 ms, 2270 against 2628 frames/s — the dry run, the list, the second barrier per stage
+        //     and one shared-memory atomic per surviving window cost more than the idle lanes they remove.
         {
             const int cnt = __popc(mlo) + __popc(mhi);
-            const int nalive = uniformize(__reduce_add_sync(0xffffffffu, cnt), 12);
-            const int nsteps = (nalive + 31) >> 5;
+            // dry run: how many steps if whole ranks are packed into a step while they fit (a step never straddles a rank,
+            // so a class appears at most once per rank in it and the wavefront count stays what the rank schedule pays)
+            int nsteps, fill = 0, steps = 0;
+            for (int r = 0; r < maxc; r++) {
+                const int h = __popc(__ballot_sync(0xffffffffu, cnt > r));
+                if (fill + h > 32) { steps++; fill = 0; }
+                fill += h;
+            }
+            nsteps = steps + (fill > 0);
             if (maxc - nsteps >= NV_CLS_PACK_GAIN) {
                 int base = 0;
                 for (int r = 0; r < maxc; r++) {                 // every warp counts, warp (r mod 8) writes rank r
                     const uint32_t b = __ballot_sync(0xffffffffu, cnt > r);
-                    if ((r & 7) == warp) {
+                    const int h = __popc(b), room = 32 - (base & 31);
+                    const bool mine = (r & 7) == warp;
+                    if ((base & 31) && h > room) {               // close the step: the rest of it stays empty
+                        if (mine && lane < room) s_list[base + lane] = 0xffff;
+                        base += room;
+                    }
+                    if (mine) {
                         if (cnt > r) s_list[base + __popc(b & ((1u << lane) - 1u))] = (unsigned short)((lane << 6) | (__ffsll((long long)rem) - 1));
 #pragma unroll
                         for (int q = 0; q < 8; q++) rem &= rem - 1ull;
                     }
-                    base += __popc(b);
+                    base += h;
                 }
+                const int nalive = base;                          // list length, holes included
                 __syncthreads();
                 for (int t = warp; t < nsteps; t += 16) {        // two list entries per lane and round: steps t and t + 8
                     int cls[2], bit[2], ly[2], lx[2]; bool active[2], pass[2]; uint32_t wa[2]; float vnf[2];
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
                         const int p = (t + 8 * i) * 32 + lane;
-                        active[i] = p < nalive;
-                        const int e = active[i] ? (int)s_list[p] : (lane << 6);
+                        int e = p < nalive ? (int)s_list[p] : 0xffff;
+                        active[i] = e != 0xffff;
+                        if (!active[i]) e = lane << 6;
                         cls[i] = e >> 6; bit[i] = e & 63;
                         ly[i] = bit[i] >> 1; lx[i] = ((cls[i] - K * ly[i]) & 31) + ((bit[i] & 1) << 5);
                         wa[i] = tile_sa + (uint32_t)(ly[i] * rowb + lx[i] * 4);

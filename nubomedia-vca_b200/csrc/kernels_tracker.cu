@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
         }
     }
     __syncthreads();
-    }   // !empty
+    } else { TRK_T(3); TRK_T(4); TRK_T(5); }
     if (tid < TRK_PERIM) {
         const int r = s_lab[trk_perim_px(tid)];
         P.bslot[(size_t)tile * TRK_PERIM + tid] = r == TRK_NONE ? (unsigned short)0xffff : (unsigned short)s_maxx[r];
