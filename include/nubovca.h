@@ -35,7 +35,7 @@ typedef enum {
     NV_ERR_CUDA = -2,         /* a CUDA runtime call failed (message in nv_last_error)        */
     NV_ERR_IO = -3,           /* cascade file unreadable                                      */
     NV_ERR_FORMAT = -4,       /* cascade XML malformed                                        */
-    NV_ERR_UNSUPPORTED = -5,  /* cascade is not a BOOST/HAAR model (LBP, HOG: SURVEY §8f-3)     */
+    NV_ERR_UNSUPPORTED = -5,  /* cascade is neither a BOOST/HAAR nor a BOOST/LBP model (HOG)  */
     NV_ERR_CAPACITY = -6,     /* frame larger than the ctx was created for, or too many levels */
     NV_ERR_NO_DEVICE = -7,    /* no CUDA device: the library never computes on the CPU        */
     NV_ERR_STATE = -8         /* call order violated (collect without submit, ...)            */
@@ -54,7 +54,8 @@ NV_API int nv_device_count(void);                       /* 0 when no CUDA device
 /* ---- cascade model: replaces cv::CascadeClassifier::load (kmsfacedetect.cpp:163-177,
  *      kmseyedetect.cpp:171-183, kmsmouthdetect.cpp:157-163, kmsnosedetect.cpp:166-172,
  *      kmseardetect.cpp:173-186).  Host-side parse only; usable without a GPU.  BOOST/HAAR cascades in
- *      the new or the OpenCV 1.x/2.x XML layout: stumps or trees, upright or tilted features. -- */
+ *      the new or the OpenCV 1.x/2.x XML layout: stumps or trees, upright or tilted features; BOOST/LBP
+ *      cascades (new layout; categorical stumps or trees over the 256 LBP codes). -- */
 typedef struct {
     int win_w, win_h;        /* training window                                   */
     int nstages, nstumps;    /* boosted stages / weak classifiers (stumps)        */
@@ -64,6 +65,7 @@ typedef struct {
     int general;             /* 1: trees of more than one node and/or tilted features (OpenCV's predictOrdered path) */
     int has_tilted;          /* 1: some feature is evaluated on the tilted integral */
     int nnodes;              /* internal tree nodes over all weak classifiers (== nstumps for stump cascades) */
+    int lbp;                 /* 1: LBP features (OpenCV's predictCategorical path; no variance normalisation) */
 } nv_cascade_info;
 
 NV_API int nv_cascade_load(const char *xml_path, nv_cascade **out);
@@ -328,6 +330,9 @@ NV_API int nv_debug_cascade_stump(const nv_cascade *c, int stump, int rects12[12
 NV_API int nv_debug_cascade_tree(const nv_cascade *c, int tree, int cap_nodes, int *nnodes, int *feat_left_right,
                                  float *node_thr, float *leaves);
 NV_API int nv_debug_cascade_feature(const nv_cascade *c, int feature, int rects12[12], float weights3[3], int *tilted);
+/* LBP cascades: the 256-bit subset (eight words, bit `code` set: go to the first child) of internal node `node`, nodes
+ * counted over all weak classifiers in file order; the cell rect of an LBP feature is rects12[0..3] above. */
+NV_API int nv_debug_cascade_subset(const nv_cascade *c, int node, int subset8[8]);
 
 NV_API int nv_debug_num_levels(nv_ctx *ctx);
 NV_API int nv_debug_level_info(nv_ctx *ctx, int level, nv_level_info *info);

@@ -2,7 +2,8 @@
 // reference elements pass to cv::CascadeClassifier::load (kmsfacedetect.cpp:40,163-177;
 // kmseyedetect.cpp:27-29,171-183; kmsmouthdetect.cpp:37-38; kmsnosedetect.cpp:31-32;
 // kmseardetect.cpp:29-31).  Host-only; no OpenCV, no libxml: the grammar is small enough for a
-// purpose-built tokenizer.  Supports BOOST/HAAR cascades: stumps or trees, upright or tilted rectangles.
+// purpose-built tokenizer.  Supports BOOST/HAAR cascades (stumps or trees, upright or tilted rectangles) and BOOST/LBP
+// cascades (categorical stumps or trees over 256 LBP codes).
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -114,7 +115,7 @@ bool parse_floats(const std::string &s, std::vector<double> &out)
 
 // One weak classifier as parsed: internal nodes in file order and nnodes + 1 leaves.
 struct ParsedTree {
-    struct N { int feat; float thr; int left, right; };
+    struct N { int feat; float thr; int left, right; int subset[8]; };
     std::vector<N> nodes;
     std::vector<float> leaves;
 };
@@ -142,7 +143,7 @@ static int parse_rects(const Node *rects, bool tilted, int win_w, int win_h, con
 static int finish_cascade(HostCascade *hc, const std::vector<ParsedTree> &trees, const char *path)
 {
     int nfeat = (int)hc->feat_weight.size() / 3;
-    hc->general = 0;
+    hc->general = hc->lbp ? 1 : 0;
     for (uint8_t t : hc->feat_tilted) if (t) { hc->general = 1; hc->has_tilted = 1; }
     for (const ParsedTree &t : trees) {
         int nn = (int)t.nodes.size();
@@ -164,6 +165,7 @@ static int finish_cascade(HostCascade *hc, const std::vector<ParsedTree> &trees,
         for (const auto &n : t.nodes) {
             hc->node_feat.push_back(n.feat); hc->node_thr.push_back(n.thr);
             hc->node_left.push_back(n.left); hc->node_right.push_back(n.right);
+            if (hc->lbp) hc->node_subset.insert(hc->node_subset.end(), n.subset, n.subset + 8);
         }
         hc->leaves.insert(hc->leaves.end(), t.leaves.begin(), t.leaves.end());
         // the stump arrays stay index-compatible with the weak classifiers; they are only meaningful when !general
@@ -266,7 +268,7 @@ int nv_parse_cascade_xml(const char *path, HostCascade *hc)
                             child[sd] = (int)cv[0];
                         } else { nv_set_error("%s: tree node without children", path); return NV_ERR_FORMAT; }
                     }
-                    pt.nodes.push_back({(int)hc->feat_weight.size() / 3, (float)t[0], child[0], child[1]});
+                    pt.nodes.push_back({(int)hc->feat_weight.size() / 3, (float)t[0], child[0], child[1], {0}});
                     hc->feat_rect.insert(hc->feat_rect.end(), r, r + 12);
                     hc->feat_weight.insert(hc->feat_weight.end(), w, w + 3);
                     hc->feat_tilted.push_back(tilted ? 1 : 0);
@@ -291,10 +293,21 @@ int nv_parse_cascade_xml(const char *path, HostCascade *hc)
         size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
         return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
     };
-    if (trimmed(c->child_text("featureType")) != "HAAR" || trimmed(c->child_text("stageType")) != "BOOST") {
-        nv_set_error("%s: only BOOST/HAAR cascades are supported (LBP/HOG are not)", path);
+    const std::string ftype = trimmed(c->child_text("featureType"));
+    if ((ftype != "HAAR" && ftype != "LBP") || trimmed(c->child_text("stageType")) != "BOOST") {
+        nv_set_error("%s: only BOOST/HAAR and BOOST/LBP cascades are supported (HOG is not)", path);
         return NV_ERR_UNSUPPORTED;
     }
+    hc->lbp = ftype == "LBP";
+    if (hc->lbp) {
+        // OpenCV's subset size is (maxCatCount + 31) / 32 words per node; LBP codes are 8 bits, the trainer writes 256
+        const Node *fp = c->child("featureParams");
+        if (!fp || atoi(fp->child_text("maxCatCount").c_str()) != 256) {
+            nv_set_error("%s: LBP cascade with maxCatCount != 256", path);
+            return NV_ERR_UNSUPPORTED;
+        }
+    }
+    const size_t per_node = hc->lbp ? 11 : 4;                    // left right featureIdx, then the threshold or 8 subset words
     hc->win_w = atoi(c->child_text("width").c_str());
     hc->win_h = atoi(c->child_text("height").c_str());
     if (hc->win_w < 3 || hc->win_h < 3 || hc->win_w > 255 || hc->win_h > 255) {
@@ -312,13 +325,17 @@ int nv_parse_cascade_xml(const char *path, HostCascade *hc)
         for (auto &wc : weak->kids) {
             std::vector<double> nodes, leaves;
             if (!parse_floats(wc->child_text("internalNodes"), nodes) || !parse_floats(wc->child_text("leafValues"), leaves) ||
-                nodes.empty() || nodes.size() % 4 != 0 || leaves.size() != nodes.size() / 4 + 1) {
+                nodes.empty() || nodes.size() % per_node != 0 || leaves.size() != nodes.size() / per_node + 1) {
                 nv_set_error("%s: malformed weak classifier", path);
                 return NV_ERR_FORMAT;
             }
             ParsedTree pt;
-            for (size_t i = 0; i < nodes.size(); i += 4)        // left right featureIdx threshold
-                pt.nodes.push_back({(int)nodes[i + 2], (float)nodes[i + 3], (int)nodes[i], (int)nodes[i + 1]});
+            for (size_t i = 0; i < nodes.size(); i += per_node) {
+                ParsedTree::N n = {(int)nodes[i + 2], hc->lbp ? 0.f : (float)nodes[i + 3], (int)nodes[i], (int)nodes[i + 1], {0}};
+                if (hc->lbp)
+                    for (int k = 0; k < 8; k++) n.subset[k] = (int)(long long)nodes[i + 3 + k];   // written as signed 32-bit ints
+                pt.nodes.push_back(n);
+            }
             for (double l : leaves) pt.leaves.push_back((float)l);
             trees.push_back(std::move(pt));
             nt++;
@@ -331,6 +348,19 @@ int nv_parse_cascade_xml(const char *path, HostCascade *hc)
         return hc->stage_ntrees.empty() ? NV_ERR_FORMAT : NV_ERR_UNSUPPORTED;
     }
     for (auto &ft : c->child("features")->kids) {
+        if (hc->lbp) {                                            // <rect>x y w h</rect>: one cell of the 3 x 3 grid
+            if (!parse_floats(ft->child_text("rect"), v) || v.size() != 4) { nv_set_error("%s: malformed LBP feature", path); return NV_ERR_FORMAT; }
+            int r[12] = {(int)v[0], (int)v[1], (int)v[2], (int)v[3], 0, 0, 0, 0, 0, 0, 0, 0};
+            if (r[0] < 0 || r[1] < 0 || r[2] <= 0 || r[3] <= 0 || r[0] + 3 * r[2] > hc->win_w || r[1] + 3 * r[3] > hc->win_h) {
+                nv_set_error("%s: LBP feature outside the window", path);
+                return NV_ERR_FORMAT;
+            }
+            const float w[3] = {0, 0, 0};
+            hc->feat_rect.insert(hc->feat_rect.end(), r, r + 12);
+            hc->feat_weight.insert(hc->feat_weight.end(), w, w + 3);
+            hc->feat_tilted.push_back(0);
+            continue;
+        }
         const Node *rects = ft->child("rects");
         if (!rects) { nv_set_error("%s: feature without rects", path); return NV_ERR_FORMAT; }
         bool tilted = atoi(ft->child_text("tilted").c_str()) != 0;

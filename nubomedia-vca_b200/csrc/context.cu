@@ -75,6 +75,7 @@ extern "C" int nv_cascade_get_info(const nv_cascade *c, nv_cascade_info *info)
     info->nfeatures = (int)c->h.feat_weight.size() / 3; info->n3rect = c->h.n3rect;
     info->order_free_sums = c->h.order_free;
     info->general = c->h.general; info->has_tilted = c->h.has_tilted; info->nnodes = (int)c->h.node_feat.size();
+    info->lbp = c->h.lbp;
     return NV_OK;
 }
 
@@ -132,6 +133,13 @@ extern "C" int nv_debug_cascade_feature(const nv_cascade *c, int feature, int re
     return NV_OK;
 }
 
+extern "C" int nv_debug_cascade_subset(const nv_cascade *c, int node, int subset8[8])
+{
+    if (!c || !subset8 || !c->h.lbp || node < 0 || (size_t)node * 8 + 8 > c->h.node_subset.size()) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    for (int k = 0; k < 8; k++) subset8[k] = c->h.node_subset[(size_t)node * 8 + k];
+    return NV_OK;
+}
+
 extern "C" void nv_cascade_free(nv_cascade *c)
 {
     if (!c) return;
@@ -142,6 +150,7 @@ extern "C" void nv_cascade_free(nv_cascade *c)
     for (auto &kv : c->d_gen) {
         cudaSetDevice(kv.first);
         cudaFree((void *)kv.second.tree); cudaFree((void *)kv.second.node); cudaFree((void *)kv.second.leaf); cudaFree((void *)kv.second.feat);
+        cudaFree((void *)kv.second.subset);
     }
     delete c;
 }
@@ -167,7 +176,7 @@ static int cascade_on_device(nv_cascade *c, int gpu, cudaStream_t st, const DevS
             return NV_OK;
         };
         int rc;
-        void *ds = nullptr, *dm = nullptr, *dtree = nullptr, *dnode = nullptr, *dleaf = nullptr, *dfeat = nullptr, *dt = nullptr, *db = nullptr;
+        void *ds = nullptr, *dm = nullptr, *dtree = nullptr, *dnode = nullptr, *dleaf = nullptr, *dfeat = nullptr, *dt = nullptr, *db = nullptr, *dsub = nullptr;
         if ((rc = upload(c->stumps.data(), c->stumps.size() * sizeof(DevStump), &ds)) != NV_OK) return rc;
         if ((rc = upload(&c->meta, sizeof(DevCascade), &dm)) != NV_OK) return rc;
         if (c->h.general) {
@@ -195,13 +204,14 @@ static int cascade_on_device(nv_cascade *c, int gpu, cudaStream_t st, const DevS
             if ((rc = upload(nodes.data(), nodes.size() * sizeof(int4), &dnode)) != NV_OK) return rc;
             if ((rc = upload(h.leaves.data(), h.leaves.size() * sizeof(float), &dleaf)) != NV_OK) return rc;
             if ((rc = upload(feats.data(), feats.size() * sizeof(GenFeat), &dfeat)) != NV_OK) return rc;
+            if (h.lbp && (rc = upload(h.node_subset.data(), h.node_subset.size() * sizeof(int), &dsub)) != NV_OK) return rc;
         }
         if (c->tail_fast) {
             if ((rc = upload(c->tail_stumps.data(), c->tail_stumps.size() * sizeof(TailStump), &dt)) != NV_OK) return rc;
             if ((rc = upload(c->tail_base.data(), c->tail_base.size() * sizeof(double), &db)) != NV_OK) return rc;
         }
         guard.keep = true;                                          // everything is on the device: publish
-        if (c->h.general) c->d_gen[gpu] = GenModel{(int2 *)dtree, (int4 *)dnode, (float *)dleaf, (GenFeat *)dfeat};
+        if (c->h.general) c->d_gen[gpu] = GenModel{(int2 *)dtree, (int4 *)dnode, (float *)dleaf, (GenFeat *)dfeat, (uint32_t *)dsub};
         if (c->tail_fast) { c->d_tail[gpu] = (TailStump *)dt; c->d_tail_base[gpu] = (double *)db; }
         c->d_meta[gpu] = (DevCascade *)dm;
         c->d_stumps[gpu] = (DevStump *)ds;

@@ -56,6 +56,10 @@ struct HostCascade {
     std::vector<int> node_feat, node_left, node_right;   // child > 0: node of the same tree; <= 0: leaf -child of the tree
     std::vector<float> node_thr, leaves;   // nnodes + 1 leaves per tree
     std::vector<uint8_t> feat_tilted;
+    // LBP model (always general): a feature is one cell rect (feat_rect[12 f .. 12 f + 3]) of a 3 x 3 grid; a node holds
+    // the 256-bit subset of codes that go left instead of a threshold
+    int lbp = 0;
+    std::vector<int> node_subset;          // 8 words per node
 };
 
 int nv_parse_cascade_xml(const char *path, HostCascade *out);   // cascade_xml.cpp
@@ -80,6 +84,7 @@ struct GenModel {
     const int4 *node;   // feature, threshold (float bits), left, right (> 0: node of the tree; <= 0: leaf -idx)
     const float *leaf;
     const GenFeat *feat;
+    const uint32_t *subset;   // LBP models: 8 words per node (node.y of such a node is unused); nullptr for Haar models
 };
 
 struct DevCascade {

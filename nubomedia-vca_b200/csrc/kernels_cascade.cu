@@ -133,6 +133,26 @@ __device__ __forceinline__ float gen_feature(const GenModel &g, int f, const uin
     return val;
 }
 
+// LBP feature (OpenCV LBPEvaluator::OptFeature::calc): the cell rect spans a 3 x 3 grid of cells; the eight outer cell
+// sums are compared (>=) with the centre one, clockwise from the top-left, most significant bit first.
+__device__ __forceinline__ int lbp_code(const GenModel &g, int f, const uint32_t *__restrict__ wb, const LevelView &v)
+{
+    const uint32_t pr = g.feat[f].r[0];
+    const int x = pr & 255, y = (pr >> 8) & 255, w = (pr >> 16) & 255, h = pr >> 24;
+    uint32_t p[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[j][i] = __ldg(wb + corner(v, x + i * w, y + j * h));
+    auto cell = [&](int j, int i) { return (int)(p[j][i] - p[j][i + 1] - p[j + 1][i] + p[j + 1][i + 1]); };
+    const int c = cell(1, 1);
+    return (cell(0, 0) >= c ? 128 : 0) | (cell(0, 1) >= c ? 64 : 0) | (cell(0, 2) >= c ? 32 : 0) | (cell(1, 2) >= c ? 16 : 0) |
+           (cell(2, 2) >= c ? 8 : 0) | (cell(2, 1) >= c ? 4 : 0) | (cell(2, 0) >= c ? 2 : 0) | (cell(1, 0) >= c ? 1 : 0);
+}
+
+// Stage sum of trees [t0, t1) in XML order, leaves accumulated in double.  Haar models: OpenCV's predictOrdered (float
+// feature value times the variance factor against the node threshold); LBP models (g.subset != nullptr): OpenCV's
+// predictCategorical — the node's feature code goes left when its bit is set in the node's 256-bit subset.
 __device__ __forceinline__ double gen_stage_sum(const GenModel &g, int t0, int t1, const uint32_t *__restrict__ wb,
                                                 const LevelView &v, const uint32_t *__restrict__ tb, int tp, float vnf)
 {
@@ -142,6 +162,11 @@ __device__ __forceinline__ double gen_stage_sum(const GenModel &g, int t0, int t
         int idx = 0;
         do {
             int4 n = g.node[tr.x + idx];                         // feature, threshold bits, left, right
+            if (g.subset) {
+                const int code = lbp_code(g, n.x, wb, v);
+                idx = (__ldg(g.subset + (size_t)(tr.x + idx) * 8 + (code >> 5)) >> (code & 31)) & 1u ? n.z : n.w;
+                continue;
+            }
             float val = __fmul_rn(gen_feature(g, n.x, wb, v, tb, tp), vnf);
             idx = val < __int_as_float(n.y) ? n.z : n.w;
         } while (idx > 0);
@@ -177,14 +202,16 @@ k_stage0_rows_gen(const PlanDev *__restrict__ plan, int total_rows, const DevCas
         int ixc = valid ? ix : L.nx - 1;
         const uint32_t *wb = v.sum + rowbase + ixc, *qb = sq + L.iofs + rowbase + ixc;
         const uint32_t *tb = tilt ? tilt + L.iofs + rowbase + ixc * L.ystep : nullptr;
-        int valsum = (int)(__ldg(wb + c00) - __ldg(wb + c10) - __ldg(wb + c01) + __ldg(wb + c11));
-        uint32_t valsq = __ldg(qb + c00) - __ldg(qb + c10) - __ldg(qb + c01) + __ldg(qb + c11);
-        double nf = __dsub_rn(__dmul_rn(area, (double)valsq), __dmul_rn((double)valsum, (double)valsum));
         float vnf = 0.f;
-        bool ok = false;
-        if (nf > 0.) {
-            vnf = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn(nf)));
-            ok = __dmul_rn(area, (double)vnf) < 1e-1;
+        bool ok = g.subset != nullptr;                            // LBP: no variance normalisation, every window is evaluated
+        if (!ok) {
+            int valsum = (int)(__ldg(wb + c00) - __ldg(wb + c10) - __ldg(wb + c01) + __ldg(wb + c11));
+            uint32_t valsq = __ldg(qb + c00) - __ldg(qb + c10) - __ldg(qb + c01) + __ldg(qb + c11);
+            double nf = __dsub_rn(__dmul_rn(area, (double)valsq), __dmul_rn((double)valsum, (double)valsum));
+            if (nf > 0.) {
+                vnf = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn(nf)));
+                ok = __dmul_rn(area, (double)vnf) < 1e-1;
+            }
         }
         bool fail = false;
         if (ok) fail = gen_stage_sum(g, 0, n0, wb, v, tb, L.ipitch, vnf) < thr0;

@@ -32,7 +32,7 @@ class Rect(C.Structure):
 
 class CascadeInfo(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("win_w", "win_h", "nstages", "nstumps", "nfeatures", "n3rect", "order_free_sums",
-                                         "general", "has_tilted", "nnodes")]
+                                         "general", "has_tilted", "nnodes", "lbp")]
 
 
 class DetectParams(C.Structure):
@@ -130,6 +130,7 @@ _SIGS = {
     "nv_debug_draw_circle": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "nv_debug_cascade_tree": (_i, [_vp, _i, _i, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "nv_debug_cascade_feature": (_i, [_vp, _i, _ip, C.POINTER(C.c_float), _ip]),
+    "nv_debug_cascade_subset": (_i, [_vp, _i, _ip]),
     "nv_debug_num_levels": (_i, [_vp]),
     "nv_debug_level_info": (_i, [_vp, _i, C.POINTER(LevelInfo)]),
     "nv_debug_get_gray": (_i, [_vp, _vp, _i, _ip, _ip]),
@@ -231,6 +232,11 @@ class Cascade:
         r, w, t = (C.c_int * 12)(), (C.c_float * 3)(), C.c_int(0)
         _check(_lib.nv_debug_cascade_feature(self.handle, f, r, w, C.byref(t)), "nv_debug_cascade_feature")
         return np.array(r[:], np.int32).reshape(3, 4), np.array(w[:], np.float32), t.value
+
+    def subset(self, node):
+        s = (C.c_int * 8)()
+        _check(_lib.nv_debug_cascade_subset(self.handle, node, s), "nv_debug_cascade_subset")
+        return np.array(s[:], np.int32)
 
     def stump(self, i):
         r, w, t = (C.c_int * 12)(), (C.c_float * 3)(), (C.c_float * 3)()

@@ -278,6 +278,11 @@ typedef struct {
     const int *node_right;
     const float *leaves;         /* [sum (nnodes + 1)] */
     const unsigned char *feat_tilted;   /* [nfeatures] */
+    /* LBP model (OpenCV featureType LBP, predictCategoricalStump / predictCategorical): a feature is ONE cell rect
+     * (feat_rect[12 f .. 12 f + 3]) spanning a 3 x 3 grid of such cells; a node holds a 256-bit subset instead of a
+     * threshold.  No variance normalisation. */
+    int lbp;
+    const int *node_subset;      /* [sum nnodes * 8] */
 } ora_cascade;
 
 #define ORA_DEPTH_VARREJ  (-100)    /* OpenCV result -1 from the variance test */
@@ -414,6 +419,53 @@ static int ora_run_at_general(const ora_cascade *c, const int32_t *sum, const ui
     return 1;
 }
 
+/* OpenCV LBPEvaluator::OptFeature::calc: the 8 neighbour cells of the 3 x 3 grid compared (>=) with the centre cell,
+ * clockwise from the top-left, most significant bit first. */
+static int ora_lbp_code(const int32_t *w0, int p, const int *r)
+{
+    int x = r[0], y = r[1], w = r[2], h = r[3];
+    int c[3][3];
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++) {
+            const int32_t *a = w0 + (size_t)(y + j * h) * p + x + i * w;
+            c[j][i] = a[0] - a[w] - a[(size_t)h * p] + a[(size_t)h * p + w];
+        }
+    int cv = c[1][1];
+    return (c[0][0] >= cv ? 128 : 0) | (c[0][1] >= cv ? 64 : 0) | (c[0][2] >= cv ? 32 : 0) | (c[1][2] >= cv ? 16 : 0) |
+           (c[2][2] >= cv ? 8 : 0) | (c[2][1] >= cv ? 4 : 0) | (c[2][0] >= cv ? 2 : 0) | (c[1][0] >= cv ? 1 : 0);
+}
+
+ORA_API int ora_lbp_code_at(const ora_cascade *c, const int32_t *sum, int p, int x, int y, int f)
+{
+    return ora_lbp_code(sum + (size_t)y * p + x, p, c->feat_rect + (size_t)f * 12);
+}
+
+/* OpenCV predictCategorical<LBPEvaluator> (and its stump form, which walks one-node trees the same way): the code of
+ * the node's feature picks the left child when its bit is set in the node's subset; leaves accumulate in double
+ * (probed against cv2: tests/test_oracle_vs_cv2.py); no variance test — setWindow only checks the window bounds. */
+static int ora_run_at_lbp(const ora_cascade *c, const int32_t *sum, int p, int x, int y)
+{
+    const int32_t *w0 = sum + (size_t)y * p + x;
+    int ti = 0, node0 = 0, leaf0 = 0;
+    for (int st = 0; st < c->nstages; st++) {
+        double tmp = 0.;
+        for (int i = 0; i < c->stage_ntrees[st]; i++, ti++) {
+            int idx = 0;
+            do {
+                int n = node0 + idx;
+                int code = ora_lbp_code(w0, p, c->feat_rect + (size_t)c->node_feat[n] * 12);
+                const int *subset = c->node_subset + (size_t)n * 8;
+                idx = (subset[code >> 5] & (1 << (code & 31))) ? c->node_left[n] : c->node_right[n];
+            } while (idx > 0);
+            tmp += (double)c->leaves[leaf0 - idx];
+            node0 += c->tree_nnodes[ti]; leaf0 += c->tree_nnodes[ti] + 1;
+        }
+        float thr = c->stage_thr[st] - 1e-5f;
+        if (tmp < (double)thr) return -st;
+    }
+    return 1;
+}
+
 /* Debug tap for the pin tests: normalised value of feature `f` at window (x,y); returns 0 and
  * leaves *out untouched when the variance test rejects the window. */
 ORA_API int ora_feature_value(const ora_cascade *c, const int32_t *sum, const uint32_t *sq, int p,
@@ -479,7 +531,8 @@ ORA_API int ora_eval_level(const ora_cascade *c, const int32_t *sum, const uint3
     for (int y = 0; y < ry; y += ystep, iy++) {
         if (depth) for (int i = 0; i < nx; i++) depth[(size_t)iy * nx + i] = ORA_DEPTH_SKIPPED;
         for (int x = 0; x < rx; x += ystep) {
-            int r = c->general ? ora_run_at_general(c, sum, sq, tilt, p, x, y) : ora_run_at(c, sum, sq, p, x, y);
+            int r = c->lbp ? ora_run_at_lbp(c, sum, p, x, y)
+                  : c->general ? ora_run_at_general(c, sum, sq, tilt, p, x, y) : ora_run_at(c, sum, sq, p, x, y);
             if (depth) depth[(size_t)iy * nx + x / ystep] = (int16_t)r;
             if (r > 0) {
                 npass++;

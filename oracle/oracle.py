@@ -43,6 +43,7 @@ class _CCascade(C.Structure):
         ("tree_nnodes", C.POINTER(C.c_int)), ("node_feat", C.POINTER(C.c_int)), ("node_thr", C.POINTER(C.c_float)),
         ("node_left", C.POINTER(C.c_int)), ("node_right", C.POINTER(C.c_int)), ("leaves", C.POINTER(C.c_float)),
         ("feat_tilted", C.POINTER(C.c_ubyte)),
+        ("lbp", C.c_int), ("node_subset", C.POINTER(C.c_int)),
     ]
 
 
@@ -66,6 +67,8 @@ def lib():
         _lib.ora_feature_value.restype = C.c_int
         _lib.ora_feature_value.argtypes = [C.POINTER(_CCascade), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                            C.c_int, C.c_int, C.c_void_p]
+        _lib.ora_lbp_code_at.restype = C.c_int
+        _lib.ora_lbp_code_at.argtypes = [C.POINTER(_CCascade), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         _lib.ora_group_rectangles.restype = C.c_int
         _lib.ora_group_rectangles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
         _lib.ora_detect_multiscale.restype = C.c_int
@@ -113,8 +116,11 @@ def parse_cascade_xml(path: str) -> dict:
     casc = root.find("cascade")
     if casc is None:
         return _parse_old_format(root)
-    if casc.findtext("featureType", "").strip() != "HAAR":
-        raise NotImplementedError("only HAAR cascades")
+    ftype = casc.findtext("featureType", "").strip()
+    if ftype == "LBP":
+        return _parse_lbp(casc)
+    if ftype != "HAAR":
+        raise NotImplementedError("only HAAR and LBP cascades")
     win_w, win_h = int(casc.findtext("width")), int(casc.findtext("height"))
     stage_ntrees, stage_thr, trees = [], [], []
     for st in casc.find("stages"):
@@ -142,10 +148,40 @@ def parse_cascade_xml(path: str) -> dict:
     return _model(win_w, win_h, stage_ntrees, stage_thr, trees, rects, weights, tilted)
 
 
-def _model(win_w, win_h, stage_ntrees, stage_thr, trees, rects, weights, tilted) -> dict:
-    """trees: list of ([(feat, thr, left, right), ...], [leaf, ...]) per weak classifier."""
+def _parse_lbp(casc) -> dict:
+    """BOOST/LBP cascade (new layout only; OpenCV 1.x had none): a node is `left right feature s0 .. s7` with the
+    256-bit subset of LBP codes that go LEFT; a feature is one cell rect `x y w h` of a 3 x 3 grid of cells."""
+    if int(casc.find("featureParams").findtext("maxCatCount")) != 256:
+        raise NotImplementedError("LBP cascade with maxCatCount != 256")
+    win_w, win_h = int(casc.findtext("width")), int(casc.findtext("height"))
+    stage_ntrees, stage_thr, trees, subsets = [], [], [], []
+    for st in casc.find("stages"):
+        stage_thr.append(float(st.findtext("stageThreshold")))
+        n = 0
+        for wc in st.find("weakClassifiers"):
+            nodes = wc.findtext("internalNodes").split()
+            leaves = [float(v) for v in wc.findtext("leafValues").split()]
+            nn = len(nodes) // 11
+            if len(nodes) != 11 * nn or len(leaves) != nn + 1 or nn < 1:
+                raise ValueError("malformed LBP weak classifier")
+            trees.append(([(int(nodes[11 * i + 2]), 0.0, int(nodes[11 * i]), int(nodes[11 * i + 1])) for i in range(nn)], leaves))
+            for i in range(nn):
+                subsets.append([int(v) for v in nodes[11 * i + 3:11 * i + 11]])
+            n += 1
+        stage_ntrees.append(n)
+    rects, weights, tilted = [], [], []
+    for f in casc.find("features"):
+        t = f.findtext("rect").split()
+        r = np.zeros((3, 4), np.int32); r[0] = [int(t[0]), int(t[1]), int(t[2]), int(t[3])]
+        rects.append(r); weights.append(np.zeros(3, np.float32)); tilted.append(0)
+    return _model(win_w, win_h, stage_ntrees, stage_thr, trees, rects, weights, tilted, subsets=subsets)
+
+
+def _model(win_w, win_h, stage_ntrees, stage_thr, trees, rects, weights, tilted, subsets=None) -> dict:
+    """trees: list of ([(feat, thr, left, right), ...], [leaf, ...]) per weak classifier; subsets (LBP models only): eight
+    int32 words per node, in node order."""
     f32 = lambda a: np.array(a, np.float64).astype(np.float32)      # noqa: E731
-    general = any(tilted) or any(len(nodes) != 1 for nodes, _ in trees)
+    general = subsets is not None or any(tilted) or any(len(nodes) != 1 for nodes, _ in trees)
     d = dict(win_w=win_w, win_h=win_h, stage_ntrees=np.array(stage_ntrees, np.int32), stage_thr=f32(stage_thr),
              feat_rect=np.ascontiguousarray(np.stack(rects)), feat_weight=np.ascontiguousarray(np.stack(weights)),
              general=bool(general),
@@ -155,7 +191,9 @@ def _model(win_w, win_h, stage_ntrees, stage_thr, trees, rects, weights, tilted)
              node_left=np.array([n[2] for nodes, _ in trees for n in nodes], np.int32),
              node_right=np.array([n[3] for nodes, _ in trees for n in nodes], np.int32),
              leaves=f32([v for _, lv in trees for v in lv]),
-             feat_tilted=np.array(tilted, np.uint8))
+             feat_tilted=np.array(tilted, np.uint8), lbp=subsets is not None,
+             node_subset=(np.array(subsets, np.int64).astype(np.uint32).view(np.int32).reshape(-1, 8) if subsets is not None
+                          else np.zeros((0, 8), np.int32)))
     if not general:
         if any(nodes[0][2] != 0 or nodes[0][3] != -1 for nodes, _ in trees):
             raise ValueError("stump with unexpected leaf indices")
@@ -212,6 +250,9 @@ class Cascade:
         self.win_w, self.win_h = d["win_w"], d["win_h"]
         self.nstages, self.nstumps = len(d["stage_ntrees"]), len(d["stump_feat"])
         self.general = bool(d["general"])
+        self.lbp = bool(d.get("lbp", False))
+        if "node_subset" not in d:
+            d["node_subset"] = np.zeros((0, 8), np.int32)
         self.has_tilted = bool(d["feat_tilted"].any())
         ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
         self.c = _CCascade(
@@ -222,7 +263,8 @@ class Cascade:
             len(d["feat_rect"]), d["feat_rect"].ctypes.data_as(ip), d["feat_weight"].ctypes.data_as(fp),
             int(d["general"]), d["tree_nnodes"].ctypes.data_as(ip), d["node_feat"].ctypes.data_as(ip),
             d["node_thr"].ctypes.data_as(fp), d["node_left"].ctypes.data_as(ip), d["node_right"].ctypes.data_as(ip),
-            d["leaves"].ctypes.data_as(fp), d["feat_tilted"].ctypes.data_as(C.POINTER(C.c_ubyte)))
+            d["leaves"].ctypes.data_as(fp), d["feat_tilted"].ctypes.data_as(C.POINTER(C.c_ubyte)),
+            int(self.lbp), d["node_subset"].ctypes.data_as(ip))
 
 
 # ------------------------------------------------------------------------------------------
@@ -353,6 +395,11 @@ def feature_value(casc: Cascade, s, q, x, y, f):
     out = C.c_float(0)
     ok = lib().ora_feature_value(C.byref(casc.c), _p(s), _p(q), s.shape[1], x, y, f, C.byref(out))
     return np.float32(out.value) if ok else None
+
+
+def lbp_code(casc: Cascade, s, x, y, f):
+    """8-bit LBP code of feature f at window (x, y) of a level with integral s (LBPEvaluator::OptFeature::calc)."""
+    return int(lib().ora_lbp_code_at(C.byref(casc.c), _p(s), s.shape[1], x, y, f))
 
 
 def group_rectangles(rects, thr, eps=0.2):

@@ -200,3 +200,57 @@ def random_general_model(rng, w=20, h=20, nstages=5, max_trees=8, max_nodes=3):
         stage_thr.append(float(np.float32(rng.uniform(-0.9, -0.35) * nt)))
     import oracle as O
     return O._model(w, h, stage_ntrees, stage_thr, trees, rects, weights, tilted)
+
+
+def write_lbp_cascade(path, w, h, stages, feats):
+    """BOOST/LBP cascade in OpenCV's new XML layout.  stages: [(stage_thr, [tree, ...])] with tree = ([(left, right,
+    feature, [8 subset words]), ...], [leaf, ...]); feats: [(x, y, cell_w, cell_h)]."""
+    s = ['<?xml version="1.0"?>', '<opencv_storage>',
+         '<cascade type_id="opencv-cascade-classifier"><stageType>BOOST</stageType>',
+         '<featureType>LBP</featureType>', f'<height>{h}</height>', f'<width>{w}</width>',
+         f'<stageParams><maxWeakCount>{max(len(t) for _, t in stages)}</maxWeakCount></stageParams>',
+         '<featureParams><maxCatCount>256</maxCatCount></featureParams>', f'<stageNum>{len(stages)}</stageNum>',
+         '<stages>']
+    for thr, trees in stages:
+        s.append(f'<_><maxWeakCount>{len(trees)}</maxWeakCount><stageThreshold>{float(thr)!r}</stageThreshold>'
+                 '<weakClassifiers>')
+        for nodes, leaves in trees:
+            s.append('<_><internalNodes>' + ' '.join(f'{l} {r} {f} ' + ' '.join(str(int(v)) for v in sub) for (l, r, f, sub) in nodes)
+                     + '</internalNodes><leafValues>' + ' '.join(repr(float(v)) for v in leaves) + '</leafValues></_>')
+        s.append('</weakClassifiers></_>')
+    s.append('</stages><features>')
+    for (x, y, ww, hh) in feats:
+        s.append(f'<_><rect>{x} {y} {ww} {hh}</rect></_>')
+    s.append('</features></cascade></opencv_storage>')
+    with open(path, 'w') as f:
+        f.write('\n'.join(s))
+
+
+def random_lbp_cascade(path, rng, w=24, h=24, nstages=6, max_trees=10, nfeat=60, max_nodes=1, pass_bias=0.0):
+    """A random LBP cascade (stumps, or trees of up to max_nodes nodes) whose stages reject about half of the windows:
+    random cells, random 256-bit subsets, a stage threshold near the mean of the stage sum."""
+    import numpy as np
+    feats = []
+    for _ in range(nfeat):
+        cw = int(rng.integers(1, w // 3 + 1)); ch = int(rng.integers(1, h // 3 + 1))
+        feats.append((int(rng.integers(0, w - 3 * cw + 1)), int(rng.integers(0, h - 3 * ch + 1)), cw, ch))
+    stages = []
+    for _ in range(nstages):
+        nt = int(rng.integers(1, max_trees + 1))
+        trees, mean = [], 0.0
+        for _t in range(nt):
+            nn = int(rng.integers(1, max_nodes + 1))
+            nodes, leaves = [], []
+            for i in range(nn):                      # a chain: one child is the next node (if any), the other a leaf
+                sub = [int(v) for v in rng.integers(-2**31, 2**31, 8)]
+                if i + 1 < nn:
+                    leaves.append(float(np.float32(rng.uniform(-1, 1))))
+                    ch = (i + 1, -(len(leaves) - 1)) if rng.integers(0, 2) else (-(len(leaves) - 1), i + 1)
+                else:
+                    leaves += [float(np.float32(rng.uniform(-1, 1))) for _ in range(2)]
+                    ch = (-(len(leaves) - 2), -(len(leaves) - 1))
+                nodes.append((ch[0], ch[1], int(rng.integers(0, nfeat)), sub))
+            trees.append((nodes, leaves))
+            mean += float(np.mean(leaves))
+        stages.append((float(np.float32(mean - pass_bias * nt + rng.uniform(-0.1, 0.1))), trees))
+    write_lbp_cascade(path, w, h, stages, feats)

@@ -98,6 +98,32 @@ def yuv_case(fmt, W, H, k, seed, w2p, sf, mn, min_size):
                 min_size=list(ms), yuv_sha=sha(buf), bgr_sha=sha(bgr), eq_sha=sha(eq), grouped=grp.tolist())
 
 
+def lbp_cases():
+    """BOOST/LBP cascades (categorical stumps and trees).  No LBP model ships with this image or with the reference, so
+    three random models are written next to this file (tests/cascade_xml_util.random_lbp_cascade, seeded) and cv2's
+    detectMultiScale output on them is the fixture."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cascade_xml_util import random_lbp_cascade
+    cv2.setNumThreads(1)                 # canonical candidate order: scale -> y -> x
+    out = []
+    for i, (seed, w, h, nst, max_nodes, W, H, sf) in enumerate([(41, 24, 24, 7, 1, 320, 240, 1.1), (42, 20, 20, 6, 3, 400, 300, 1.2),
+                                                                (43, 32, 18, 8, 2, 640, 360, 1.1)]):
+        name = f"lbp_random_{i}.xml"
+        random_lbp_cascade(os.path.join(HERE, name), np.random.default_rng(seed), w=w, h=h, nstages=nst, max_trees=10, max_nodes=max_nodes,
+                           pass_bias=0.02)
+        eq = cv2.equalizeHist(cv2.cvtColor(synth.frame(W, H, 3, seed), cv2.COLOR_BGR2GRAY))
+        cc = cv2.CascadeClassifier(os.path.join(HERE, name))
+        assert not cc.empty()
+        raw = np.asarray(cc.detectMultiScale(eq, scaleFactor=sf, minNeighbors=0)).reshape(-1, 4)
+        grp = np.asarray(cc.detectMultiScale(eq, scaleFactor=sf, minNeighbors=2)).reshape(-1, 4)
+        print(name, len(raw), "raw", len(grp), "grouped")
+        out.append(dict(cascade=name, W=W, H=H, k=3, seed=seed, scale_factor=sf, min_neighbors=2, eq_sha=sha(eq),
+                        raw_sha=sha(raw.astype(np.int32)), n_raw=len(raw), raw_head=raw[:200].tolist(), grouped=grp.tolist()))
+    with open(os.path.join(HERE, "lbp_golden.json"), "w") as f:
+        json.dump(dict(cv2=cv2.__version__, cases=out), f)
+    print("wrote", len(out), "LBP cascade cases")
+
+
 def cfg3_full():
     """BASELINE config 3 at FULL size (1920x1080, processing width 1920, sf 1.1, min 24x24, the bench.py frames of rank 0):
     its own file, so that regenerating it does not touch the other fixtures."""
@@ -144,4 +170,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["lbp"]:          # only the LBP fixtures (added in round 2; the others are unchanged)
+        lbp_cases()
+    else:
+        main()
+        lbp_cases()

@@ -10,7 +10,7 @@ import pytest
 
 import nubovca as nv
 import oracle as O
-from cascade_xml_util import random_cascade, write_cascade, write_old_format
+from cascade_xml_util import random_cascade, random_lbp_cascade, write_cascade, write_old_format
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -163,6 +163,46 @@ def test_general_cascade_loader(name, cascade_dir, tmp_path):
                 f = d["node_feat"][n0 + i]
                 assert (r == d["feat_rect"][f]).all() and (w == d["feat_weight"][f]).all() and tilted == d["feat_tilted"][f]
             n0 += nn; l0 += nn + 1
+
+
+@pytest.mark.parametrize("max_nodes", [1, 3])
+def test_lbp_cascade_loader(tmp_path, max_nodes):
+    """BOOST/LBP cascades (categorical stumps and trees): the loader against the oracle's independent parser."""
+    p = str(tmp_path / "lbp.xml")
+    random_lbp_cascade(p, np.random.default_rng(5 + max_nodes), nstages=5, max_trees=9, max_nodes=max_nodes)
+    c = nv.Cascade(p); d = O.parse_cascade_xml(p)
+    assert d["lbp"] and c.info.lbp == 1 and c.info.general == 1 and c.info.has_tilted == 0
+    assert (c.info.win_w, c.info.win_h, c.info.nstages) == (d["win_w"], d["win_h"], len(d["stage_ntrees"]))
+    assert c.info.nstumps == len(d["tree_nnodes"]) and c.info.nnodes == len(d["node_feat"]) and c.info.nfeatures == len(d["feat_rect"])
+    for s in range(c.info.nstages):
+        assert c.stage(s) == (d["stage_ntrees"][s], np.float32(d["stage_thr"][s]) - np.float32(1e-5))
+    n0 = l0 = 0
+    for t in range(c.info.nstumps):
+        nodes, _, leaves = c.tree(t)
+        nn = int(d["tree_nnodes"][t])
+        assert len(nodes) == nn and (nodes[:, 0] == d["node_feat"][n0:n0 + nn]).all()
+        assert (nodes[:, 1] == d["node_left"][n0:n0 + nn]).all() and (nodes[:, 2] == d["node_right"][n0:n0 + nn]).all()
+        assert (leaves == d["leaves"][l0:l0 + nn + 1]).all()
+        for i in range(nn):
+            assert (c.subset(n0 + i) == d["node_subset"][n0 + i]).all()
+        n0 += nn; l0 += nn + 1
+    for f in range(c.info.nfeatures):
+        assert (c.feature(f)[0] == d["feat_rect"][f]).all()
+    # error paths: a cell grid that leaves the window, a category count the evaluator does not have
+    txt = open(p).read()
+    bad = tmp_path / "bad.xml"
+    bad.write_text(txt.replace("</rect></_>", "</rect></_>\n<_><rect>20 0 2 2</rect></_>", 1))     # 20 + 3 * 2 > 24
+    with pytest.raises(nv.NuboError) as e:
+        nv.Cascade(str(bad))
+    assert e.value.code == -4
+    bad.write_text(txt.replace("<maxCatCount>256</maxCatCount>", "<maxCatCount>128</maxCatCount>"))
+    with pytest.raises(nv.NuboError) as e:
+        nv.Cascade(str(bad))
+    assert e.value.code == -5
+    bad.write_text(txt.replace("<featureType>LBP</featureType>", "<featureType>HOG</featureType>"))
+    with pytest.raises(nv.NuboError) as e:
+        nv.Cascade(str(bad))
+    assert e.value.code == -5
 
 
 @pytest.mark.skipif(nv.device_count() > 0, reason="a GPU is visible")

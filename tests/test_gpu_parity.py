@@ -11,7 +11,7 @@ import pytest
 
 import nubovca as nv
 import oracle as O
-from cascade_xml_util import random_cascade, random_general_model, random_int_cascade, write_old_format
+from cascade_xml_util import random_cascade, random_general_model, random_int_cascade, random_lbp_cascade, write_old_format
 from nubovca import synth
 
 pytestmark = pytest.mark.gpu
@@ -239,6 +239,48 @@ def test_random_trainer_shaped_and_general_cascades(ctx, tmp_path, seed):
     for mn in (0, 2):
         assert rects_equal(ctx.detect_multiscale(ngen, g, sf, mn), O.detect_multiscale(g, ogen, sf, mn)), (seed, mn)
     check_levels(ctx, g, ogen, sf, (0, 0))
+
+
+@pytest.mark.parametrize("idx", range(3))
+def test_lbp_golden_cases(ctx, idx):
+    """BOOST/LBP cascades against the committed cv2 outputs (tests/golden/lbp_golden.json)."""
+    import hashlib
+    c = json.load(open(os.path.join(HERE, "golden", "lbp_golden.json")))["cases"][idx]
+    eq = O.equalize_hist(O.bgr2gray(synth.frame(c["W"], c["H"], c["k"], c["seed"])))
+    ncasc = nv.Cascade(os.path.join(HERE, "golden", c["cascade"]))
+    assert ncasc.info.lbp == 1
+    raw = ctx.detect_multiscale(ncasc, eq, c["scale_factor"], 0)
+    assert len(raw) == c["n_raw"] and hashlib.sha256(np.ascontiguousarray(raw, np.int32).tobytes()).hexdigest() == c["raw_sha"]
+    assert rects_equal(ctx.detect_multiscale(ncasc, eq, c["scale_factor"], c["min_neighbors"]), c["grouped"])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_lbp_cascades(ctx, tmp_path, seed):
+    """Random LBP cascades (OpenCV's predictCategorical path; categorical stumps for even seeds, trees of up to three nodes
+    for odd ones), on small plans (warp per window / thread per window) and on plans above 16 384 windows (stage-range
+    passes with compaction): every depth map, candidates and grouped rectangles against the oracle.  A Haar cascade on
+    the same context afterwards (the model kind switches with the cascade)."""
+    rng = np.random.default_rng(700 + seed)
+    p = str(tmp_path / "lbp.xml")
+    w, h = [(24, 24), (20, 20), (32, 18), (18, 30)][seed % 4]
+    random_lbp_cascade(p, rng, w=w, h=h, nstages=int(rng.integers(2, 8)), max_trees=8, max_nodes=1 if seed % 2 == 0 else 3)
+    big = seed >= 4
+    W, H = (int(rng.integers(500, 900)), int(rng.integers(400, 600))) if big else (int(rng.integers(60, 100)), int(rng.integers(60, 100)))
+    g = synth.frame(W, H, 2, seed)[..., 1] if seed % 3 else rng.integers(0, 256, (H, W), dtype=np.uint8)
+    sf = float(rng.choice([1.1, 1.25, 1.4]))
+    ncasc, ocasc = nv.Cascade(p), O.Cascade(p)
+    assert ncasc.info.lbp == 1 and ocasc.lbp
+    n = 0
+    for mn in (0, 2):
+        got = ctx.detect_multiscale(ncasc, g, sf, mn)
+        assert rects_equal(got, O.detect_multiscale(g, ocasc, sf, mn)), (seed, mn)
+        n += len(got)
+    assert n > 0
+    nwin, levels = check_levels(ctx, g, ocasc, sf, (0, 0))
+    assert (nwin > 16384) == big                                                # both routes: small plan / staged large plan
+    assert not any((l["depth"] == O.DEPTH_VARREJ).any() for l in levels)         # LBP has no variance test
+    fp = os.path.join(os.path.dirname(HERE), "nubomedia-vca_b200", "cascades", FACE_XML)
+    assert rects_equal(ctx.detect_multiscale(nv.Cascade(fp), g, 1.2, 2), O.detect_multiscale(g, O.Cascade(fp), 1.2, 2))
 
 
 def test_old_format_and_wide_window_cascade(ctx, tmp_path, cascade_dir):

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 import oracle as O
-from cascade_xml_util import random_cascade, random_general_model, random_int_cascade, write_cascade, write_old_format
+from cascade_xml_util import (random_cascade, random_general_model, random_int_cascade, random_lbp_cascade, write_cascade,
+                              write_lbp_cascade, write_old_format)
 from nubovca import synth
 
 try:
@@ -50,6 +51,18 @@ def test_cfg3_full_size_golden(cascade_dir):
     casc = O.Cascade(os.path.join(cascade_dir, c["cascade"]))
     assert rects_equal(O.detect_multiscale(eq, casc, c["scale_factor"], 0, tuple(c["min_size"])), c["raw"])
     assert rects_equal(O.detect_multiscale(eq, casc, c["scale_factor"], c["min_neighbors"], tuple(c["min_size"])), c["grouped"])
+
+
+@pytest.mark.parametrize("idx", range(3))
+def test_lbp_golden(idx):
+    """BOOST/LBP cascades: the oracle against the committed cv2 output on the committed random models."""
+    c = _golden("lbp_golden.json")["cases"][idx]
+    eq = O.equalize_hist(O.bgr2gray(synth.frame(c["W"], c["H"], c["k"], c["seed"])))
+    assert sha(eq) == c["eq_sha"]
+    casc = O.Cascade(os.path.join(HERE, "golden", c["cascade"]))
+    raw = O.detect_multiscale(eq, casc, c["scale_factor"], 0)
+    assert len(raw) == c["n_raw"] and sha(raw.astype(np.int32)) == c["raw_sha"] and rects_equal(raw[:200], c["raw_head"])
+    assert rects_equal(O.detect_multiscale(eq, casc, c["scale_factor"], c["min_neighbors"]), c["grouped"])
 
 
 @pytest.mark.parametrize("idx", range(8))
@@ -339,6 +352,74 @@ def test_random_trainer_shaped_and_general_cascades_live(tmp_path, seed):
     assert not cc.empty() and O.Cascade(q).general
     for mn in (0, 2):
         assert rects_equal(cc.detectMultiScale(g, scaleFactor=1.2, minNeighbors=mn), O.detect_multiscale(g, O.Cascade(q), 1.2, mn)), (seed, mn)
+
+
+# ---- LBP cascades.  Neither the reference nor this image ships an LBP model, so the oracle's LBP
+# path is pinned on purpose-built and random models that cv2 loads.
+@needs_cv2
+def test_lbp_stage_sum_accumulates_in_double(tmp_path):
+    # leaves 2^24, 1, 1, 1, 1 against a threshold of 2^24 + 2: a float accumulator stays at 2^24 (reject)
+    A = 16777216.0
+    z = [0] * 8
+    trees = [([(0, -1, 0, z)], [A, A])] + [([(0, -1, 0, z)], [1.0, 1.0]) for _ in range(4)]
+    p = str(tmp_path / "acc.xml")
+    write_lbp_cascade(p, 24, 24, [(A + 2.0, trees)], [(0, 0, 3, 3)])
+    g = np.random.default_rng(8).integers(0, 256, (80, 90), dtype=np.uint8)
+    a = cv2.CascadeClassifier(p).detectMultiScale(g, scaleFactor=1.2, minNeighbors=0)
+    b = O.detect_multiscale(g, O.Cascade(p), 1.2, 0)
+    assert len(a) > 0 and rects_equal(a, b)
+
+
+@needs_cv2
+def test_lbp_code_bit_exact(tmp_path):
+    """The 8-bit code of one feature, read out of cv2 through single-code subsets: with subset = {code} the window
+    passes, with subset = all codes but that one it does not — for random cells on random 24x24 images (one window)."""
+    rng = np.random.default_rng(21)
+    p = str(tmp_path / "code.xml")
+    seen = set()
+    for it in range(80):
+        g = rng.integers(0, 256, (24, 24), dtype=np.uint8) if it % 4 else np.full((24, 24), it, np.uint8)   # flat image: code 255
+        if it % 4 == 1:
+            g = (g // 64 * 64).astype(np.uint8)                      # coarse values: ties between cells are common
+        cw, ch = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        cell = (int(rng.integers(0, 24 - 3 * cw + 1)), int(rng.integers(0, 24 - 3 * ch + 1)), cw, ch)
+        write_lbp_cascade(p, 24, 24, [(0.5, [([(0, -1, 0, [0] * 8)], [1.0, 0.0])])], [cell])
+        s, _ = O.integral(g)
+        code = O.lbp_code(O.Cascade(p), s, 0, 0, 0)
+        seen.add(code)
+        only = [0] * 8; only[code >> 5] = 1 << (code & 31)
+        if only[code >> 5] >= 2**31:
+            only[code >> 5] -= 2**32
+        rest = [(-1 if i != code >> 5 else (~(1 << (code & 31))) & 0xffffffff) for i in range(8)]
+        rest = [v - 2**32 if v >= 2**31 else v for v in rest]
+        res = []
+        for sub in (only, rest):
+            write_lbp_cascade(p, 24, 24, [(0.5, [([(0, -1, 0, sub)], [1.0, 0.0])])], [cell])
+            res.append(len(cv2.CascadeClassifier(p).detectMultiScale(g, scaleFactor=1.5, minNeighbors=0)))
+        assert res == [1, 0], (it, code, cell)
+    assert len(seen) > 20 and 255 in seen
+
+
+@needs_cv2
+@pytest.mark.parametrize("seed", range(8))
+def test_random_lbp_cascades_live(tmp_path, seed):
+    """Random LBP cascades — stumps (predictCategoricalStump) for even seeds, trees of up to three nodes
+    (predictCategorical) for odd ones — on noise and on synthetic frames, raw and grouped, against cv2."""
+    rng = np.random.default_rng(700 + seed)
+    p = str(tmp_path / "lbp.xml")
+    w, h = [(24, 24), (20, 20), (32, 18), (18, 30)][seed % 4]
+    random_lbp_cascade(p, rng, w=w, h=h, nstages=int(rng.integers(2, 8)), max_trees=8, max_nodes=1 if seed % 2 == 0 else 3)
+    W, H = int(rng.integers(60, 400)), int(rng.integers(60, 300))
+    g = synth.frame(W, H, 2, seed)[..., 1] if seed % 3 else rng.integers(0, 256, (H, W), dtype=np.uint8)
+    sf = float(rng.choice([1.1, 1.25, 1.4]))
+    cc = cv2.CascadeClassifier(p); oc = O.Cascade(p)
+    assert not cc.empty() and oc.lbp
+    n = 0
+    for mn in (0, 2):
+        a = cc.detectMultiScale(g, scaleFactor=sf, minNeighbors=mn)
+        assert rects_equal(a, O.detect_multiscale(g, oc, sf, mn)), (seed, mn)
+        n += len(a)
+    assert n > 0, "the random model never fires on this image"
 
 
 @needs_cv2

@@ -43,7 +43,9 @@ for (W, H) in [(1280, 720), (640, 360)]:
     print(f"{W}x{H}: {nt} blocks; cycles per phase (median / max over blocks)")
     for k in range(9):
         print(f"  {NAMES[k]:28s} {int(statistics.median(d[:, k])):8d} {int(d[:, k].max()):8d}")
-    last = buf[:, 10].argmax()
+    # checkpoint 10 is written by the frame's last block only; the other rows hold stale values of earlier frames there
+    # (clock64 is per SM, so values of different blocks do not compare): the last block is the row whose 10 follows its 9
+    last = int(np.nonzero(buf[:, 10] > buf[:, 9])[0][0])
     print(f"  {NAMES[9]:28s} {int(buf[last, 10] - buf[last, 9]):8d}  (block {last})")
     print(f"  whole block, median {int(statistics.median(buf[:, 9] - buf[:, 0]))}, max {int((buf[:, 9] - buf[:, 0]).max())} cycles")
     t.close()
