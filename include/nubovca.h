@@ -252,6 +252,16 @@ NV_API int nv_element_push_motion_event(nv_element *e);
  * process's CPU time, gstnubotracker.cpp:349 — not a media clock; deliberate deviation). */
 NV_API int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int width, int height, int stride_bytes,
                                          uint64_t pts_ns, double now_ms);
+/* The same for a BGR / BGRA frame in DEVICE memory (frames decoded and converted on the GPU): read in
+ * place, overlays written by a kernel — the same pixels nv_element_transform_frame_ip writes into a host frame. */
+NV_API int nv_element_transform_frame_device(nv_element *e, uint8_t *d_frame, int width, int height, int stride_bytes,
+                                             uint64_t pts_ns, double now_ms);
+/* cvRectangle(.., thickness 3, 8, 0) / cv::circle(.., thickness, 8, 0) into a BGR(A) frame in device memory, on the ctx's
+ * stream (returns after it is idle): shapes are drawn in array order, the later one wins where they overlap.
+ * kind 0: rectangle with corners (a, b) .. (c, d); kind 1: circle with centre (a, b), radius c, thickness d (> 1). */
+typedef struct { int kind, a, b, c, d; unsigned char blue, green, red, pad; } nv_shape;
+NV_API int nv_draw_shapes_device(nv_ctx *ctx, uint8_t *d_frame, int width, int height, int stride_bytes, int channels,
+                                 const nv_shape *shapes, int n);
 /* Any of the six elements on 4:2:0 planes (see nv_face_detect_yuv / nv_tracker_process_yuv; the nested elements take
  * their full-resolution gray image as BGR2GRAY(cvtColor(COLOR_YUV2BGR_*)) per pixel): gating, tracking, ROI arithmetic,
  * events and signals as above; the view-* / set_visual_mode overlays are ignored (the reference defines them on BGR(A)
@@ -273,6 +283,9 @@ NV_API int nv_debug_draw_rectangle(uint8_t *frame, int width, int height, int st
                                    int x1, int y1, int b, int g, int r);
 /* cv::circle(img, (cx, cy), radius, Scalar(b, g, r, 0), thickness >= 2, 8, 0): the view-eyes drawing
  * (kmseyedetect.cpp:1081,1095 use thickness 4). */
+/* the host half of nv_draw_shapes_device on a HOST frame: shapes -> spans -> disjoint spans -> pixels (CPU test tap) */
+NV_API int nv_debug_draw_shapes_spans(uint8_t *frame, int width, int height, int stride_bytes, int channels,
+                                      const nv_shape *shapes, int n, int *nspans);
 NV_API int nv_debug_draw_circle(uint8_t *frame, int width, int height, int stride_bytes, int channels, int cx, int cy,
                                 int radius, int thickness, int b, int g, int r);
 /* tests: replace gettimeofday() in the events-ms rate limit and the activate-events setter (kmsfacedetect.cpp:228-236,

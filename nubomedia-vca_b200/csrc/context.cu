@@ -872,7 +872,13 @@ int nv_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n)
 int nv_h2d(nv_ctx *ctx, const uint8_t *src, size_t bytes)
 {
     cudaPointerAttributes at;
-    bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    bool known = cudaPointerGetAttributes(&at, src) == cudaSuccess;
+    if (known && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
+        // a frame that already lives in device memory (nv_element_transform_frame_device): one copy inside HBM
+        NV_CUDA(cudaMemcpyAsync(ctx->d_frame, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        return NV_OK;
+    }
+    bool pinned = known && at.type == cudaMemoryTypeHost;
     if (!pinned) { cudaGetLastError(); memcpy(ctx->h_frame, src, bytes); }
     NV_CUDA(cudaMemcpyAsync(ctx->d_frame, pinned ? src : ctx->h_frame, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return NV_OK;

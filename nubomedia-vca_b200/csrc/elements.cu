@@ -47,6 +47,8 @@ struct TrackedFace { nv_rect r; int id; };        // BaseFace (BaseFace.cpp): re
 
 }  // namespace
 
+struct DrawSpan { int y, xa, xb; uint32_t bgr; };                  // one overlay span, xa..xb inclusive; bgr = b | g << 8 | r << 16
+
 struct nv_element {
     Kind kind;
     std::string factory, dir;
@@ -70,6 +72,8 @@ struct nv_element {
     int no_det_a = 0, no_det_b = 0;
     // device images
     DevImg gray, face_img, feat_img, flip_img;
+    // overlays of a device-resident frame (nv_element_transform_frame_device): recorded spans, their device copy
+    std::vector<DrawSpan> spans;  DrawSpan *d_spans = nullptr;  size_t d_spans_cap = 0;
     // outputs of the last frame
     std::vector<nv_meta_rect> msg;  bool pushed = false;
     std::string signal;  bool emitted = false;
@@ -227,10 +231,19 @@ int frame_to_gray(nv_element *e, nv_ctx *ctx, const uint8_t *frame, int stride, 
 struct Bgr { uint8_t b, g, r; };
 inline Bgr cv_rgb(int r, int g, int b) { return Bgr{(uint8_t)b, (uint8_t)g, (uint8_t)r}; }
 
+// Frames that live in device memory: the same rasterisers run on the host, but every span they would write is recorded
+// (the frame pointer is never dereferenced) and k_draw_spans writes them into the device frame afterwards.  Spans are
+// made disjoint first — where two shapes overlap the later one wins, as in the sequential host drawing.
+thread_local std::vector<DrawSpan> *g_span_sink = nullptr;
+
 void fill_span(uint8_t *frame, int W, int H, int stride, int cn, int y, int xa, int xb, Bgr c)
 {
     if (y < 0 || y >= H) return;
     xa = std::max(xa, 0); xb = std::min(xb, W - 1);
+    if (g_span_sink) {
+        if (xa <= xb) g_span_sink->push_back(DrawSpan{y, xa, xb, (uint32_t)c.b | ((uint32_t)c.g << 8) | ((uint32_t)c.r << 16)});
+        return;
+    }
     uint8_t *row = frame + (size_t)y * stride;
     for (int x = xa; x <= xb; x++) {
         uint8_t *px = row + (size_t)x * cn;
@@ -252,6 +265,69 @@ void draw_rectangle3(uint8_t *frame, int W, int H, int stride, int cn, int xa, i
             fill_span(frame, W, H, stride, cn, y, x1 - R, x1 + R, c);
         }
     }
+}
+
+// Painter's order resolved on the host: walking the recorded spans backwards, a span keeps only the parts of its row no
+// later span covers.  The result is a list of disjoint spans that can be written in any order, i.e. in parallel.
+void resolve_spans(const std::vector<DrawSpan> &in, std::vector<DrawSpan> &out)
+{
+    std::map<int, std::vector<std::pair<int, int>>> covered;      // per row: disjoint, sorted [a, b]
+    out.clear();
+    for (size_t k = in.size(); k-- > 0;) {
+        const DrawSpan &s = in[k];
+        auto &cv = covered[s.y];
+        int a = s.xa;
+        std::vector<std::pair<int, int>> merged;
+        merged.reserve(cv.size() + 1);
+        int na = s.xa, nb = s.xb;                                  // the union interval that swallows everything it touches
+        for (auto &iv : cv) {
+            if (iv.second < s.xa - 1 || iv.first > s.xb + 1) { merged.push_back(iv); continue; }
+            if (iv.first > a) out.push_back(DrawSpan{s.y, a, std::min(iv.first - 1, s.xb), s.bgr});
+            a = std::max(a, iv.second + 1);
+            na = std::min(na, iv.first); nb = std::max(nb, iv.second);
+        }
+        if (a <= s.xb) out.push_back(DrawSpan{s.y, a, s.xb, s.bgr});
+        merged.push_back({na, nb});
+        std::sort(merged.begin(), merged.end());
+        cv.swap(merged);
+    }
+}
+
+// one warp per span; every channel of a pixel is written (BGRA: alpha becomes 0, as cvRectangle's Scalar does)
+__global__ void __launch_bounds__(256) k_draw_spans(uint8_t *__restrict__ frame, int stride, int cn, const DrawSpan *__restrict__ spans, int n)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const DrawSpan s = spans[w];
+    uint8_t *row = frame + (size_t)s.y * stride;
+    for (int x = s.xa + lane; x <= s.xb; x += 32) {
+        uint8_t *px = row + (size_t)x * cn;
+        px[0] = (uint8_t)s.bgr; px[1] = (uint8_t)(s.bgr >> 8); px[2] = (uint8_t)(s.bgr >> 16);
+        if (cn == 4) px[3] = 0;
+    }
+}
+
+// writes the recorded spans into a device frame on `st` (spans travel through a small device buffer owned by the caller)
+int draw_spans_device(const std::vector<DrawSpan> &raw, uint8_t *d_frame, int stride, int cn, DrawSpan **d_buf, size_t *d_cap,
+                      cudaStream_t st)
+{
+    if (raw.empty()) return NV_OK;
+    std::vector<DrawSpan> flat;
+    resolve_spans(raw, flat);
+    if (flat.empty()) return NV_OK;
+    if (*d_cap < flat.size()) {
+        if (*d_buf) NV_CUDA(cudaFree(*d_buf));
+        *d_buf = nullptr; *d_cap = 0;
+        const size_t cap = flat.size() * 2 + 1024;
+        NV_CUDA(cudaMalloc(d_buf, cap * sizeof(DrawSpan)));
+        *d_cap = cap;
+    }
+    // pageable source: the copy is staged by the runtime before the call returns, `flat` may die afterwards
+    NV_CUDA(cudaMemcpyAsync(*d_buf, flat.data(), flat.size() * sizeof(DrawSpan), cudaMemcpyHostToDevice, st));
+    const int n = (int)flat.size();
+    k_draw_spans<<<(n * 32 + 255) / 256, 256, 0, st>>>(d_frame, stride, cn, *d_buf, n);
+    NV_CUDA(cudaGetLastError());
+    return NV_OK;
 }
 
 // cv::circle(img, c, radius, color, thickness > 1, LINE_8, 0) (EYE:1081,1095), restated from OpenCV's drawing code:
@@ -1103,6 +1179,7 @@ extern "C" void nv_element_destroy(nv_element *e)
     if (!e) return;
     if (e->ctx) { cudaSetDevice(e->ctx->gpu); cudaStreamSynchronize(e->ctx->stream); }
     for (DevImg *im : {&e->gray, &e->face_img, &e->feat_img, &e->flip_img}) cudaFree(im->p);
+    cudaFree(e->d_spans);
     nv_ctx_destroy(e->ctx);
     nv_cascade_free(e->c_face); nv_cascade_free(e->c_a); nv_cascade_free(e->c_b);
     delete e;
@@ -1199,6 +1276,99 @@ extern "C" int nv_element_transform_frame_ip(nv_element *e, uint8_t *frame, int 
     case K_TRACKER: return tracker_frame(e, frame, width, height, stride_bytes, pts_ns, now_ms);
     }
     return NV_ERR_ARG;
+}
+
+// The same call for a BGR / BGRA frame that lives in DEVICE memory (decoded and converted on the GPU, never mapped to the
+// host): the frame is read where it is, and the view-* / set_visual_mode overlays are written into it by k_draw_spans —
+// pixel for pixel what nv_element_transform_frame_ip draws into a host frame.  Returns after the element's stream is idle.
+extern "C" int nv_element_transform_frame_device(nv_element *e, uint8_t *d_frame, int width, int height, int stride_bytes,
+                                                 uint64_t pts_ns, double now_ms)
+{
+    if (!e || !d_frame) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, d_frame) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        nv_set_error("nv_element_transform_frame_device: the frame is not in device memory");
+        return NV_ERR_ARG;
+    }
+    e->spans.clear();
+    g_span_sink = &e->spans;
+    int rc = nv_element_transform_frame_ip(e, d_frame, width, height, stride_bytes, pts_ns, now_ms);
+    g_span_sink = nullptr;
+    if (rc != NV_OK) return rc;
+    if (!e->spans.empty()) {
+        rc = draw_spans_device(e->spans, d_frame, stride_bytes, e->kind == K_TRACKER ? 4 : 3, &e->d_spans, &e->d_spans_cap, e->ctx->stream);
+        if (rc != NV_OK) return rc;
+        e->ctx->launches++;
+    }
+    NV_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    return NV_OK;
+}
+
+static int record_shapes(uint8_t *frame, int width, int height, int stride_bytes, int channels, const nv_shape *shapes, int n,
+                         std::vector<DrawSpan> &spans)
+{
+    g_span_sink = &spans;
+    for (int i = 0; i < n; i++) {
+        const nv_shape &s = shapes[i];
+        const Bgr c = {s.blue, s.green, s.red};
+        if (s.kind == 0) draw_rectangle3(frame, width, height, stride_bytes, channels, s.a, s.b, s.c, s.d, c);
+        else if (s.kind == 1 && s.d > 1 && s.c >= 0) cvdraw::circle(frame, width, height, stride_bytes, channels, s.a, s.b, s.c, c, s.d);
+        else { g_span_sink = nullptr; nv_set_error("shape %d: unknown kind or bad circle", i); return NV_ERR_ARG; }
+    }
+    g_span_sink = nullptr;
+    return NV_OK;
+}
+
+// CPU tap of the device overlay's host half: the shapes rasterised into spans, the spans made disjoint (resolve_spans),
+// then written into a HOST frame — must equal drawing the shapes one after the other (tests/test_elements_cpu.py).
+extern "C" int nv_debug_draw_shapes_spans(uint8_t *frame, int width, int height, int stride_bytes, int channels,
+                                          const nv_shape *shapes, int n, int *nspans)
+{
+    if (!frame || width <= 0 || height <= 0 || (channels != 3 && channels != 4) || stride_bytes < width * channels || n < 0 ||
+        (n > 0 && !shapes)) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    std::vector<DrawSpan> spans, flat;
+    int rc = record_shapes(frame, width, height, stride_bytes, channels, shapes, n, spans);
+    if (rc != NV_OK) return rc;
+    resolve_spans(spans, flat);
+    for (size_t i = 0; i < flat.size(); i++)                       // disjoint: any order gives the same picture — write them backwards
+        for (size_t j = i + 1; j < flat.size(); j++)
+            if (flat[i].y == flat[j].y && flat[i].xa <= flat[j].xb && flat[j].xa <= flat[i].xb) { nv_set_error("spans overlap"); return NV_ERR_STATE; }
+    for (size_t k = flat.size(); k-- > 0;) {
+        const DrawSpan &s = flat[k];
+        for (int x = s.xa; x <= s.xb; x++) {
+            uint8_t *px = frame + (size_t)s.y * stride_bytes + (size_t)x * channels;
+            px[0] = (uint8_t)s.bgr; px[1] = (uint8_t)(s.bgr >> 8); px[2] = (uint8_t)(s.bgr >> 16);
+            if (channels == 4) px[3] = 0;
+        }
+    }
+    if (nspans) *nspans = (int)flat.size();
+    return NV_OK;
+}
+
+extern "C" int nv_draw_shapes_device(nv_ctx *ctx, uint8_t *d_frame, int width, int height, int stride_bytes, int channels,
+                                     const nv_shape *shapes, int n)
+{
+    if (!ctx || !d_frame || width <= 0 || height <= 0 || (channels != 3 && channels != 4) || stride_bytes < width * channels || n < 0 ||
+        (n > 0 && !shapes)) { nv_set_error("bad argument"); return NV_ERR_ARG; }
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, d_frame) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        nv_set_error("nv_draw_shapes_device: the frame is not in device memory");
+        return NV_ERR_ARG;
+    }
+    std::vector<DrawSpan> spans;
+    int rc = record_shapes(d_frame, width, height, stride_bytes, channels, shapes, n, spans);
+    if (rc != NV_OK) return rc;
+    NV_CUDA(cudaSetDevice(ctx->gpu));
+    DrawSpan *d_buf = nullptr;
+    size_t cap = 0;
+    rc = draw_spans_device(spans, d_frame, stride_bytes, channels, &d_buf, &cap, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_buf);
+    if (rc != NV_OK) return rc;
+    NV_CUDA(e);
+    return NV_OK;
 }
 
 // Any of the six elements fed with 4:2:0 planes (a shell whose sink caps add I420 / YV12 / NV12 / NV21): same gating,

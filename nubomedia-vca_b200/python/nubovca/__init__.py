@@ -62,6 +62,11 @@ class EventField(C.Structure):
     _fields_ = [("name", C.c_char_p), ("is_structure", C.c_int), ("type", C.c_char_p), ("rect", Rect)]
 
 
+class Shape(C.Structure):
+    _fields_ = [("kind", C.c_int), ("a", C.c_int), ("b", C.c_int), ("c", C.c_int), ("d", C.c_int),
+                ("blue", C.c_ubyte), ("green", C.c_ubyte), ("red", C.c_ubyte), ("pad", C.c_ubyte)]
+
+
 class LevelInfo(C.Structure):
     _fields_ = [("scale", C.c_float), ("width", C.c_int), ("height", C.c_int), ("ystep", C.c_int), ("nx", C.c_int),
                 ("ny", C.c_int)]
@@ -131,6 +136,9 @@ _SIGS = {
     "nv_debug_cascade_tree": (_i, [_vp, _i, _i, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "nv_debug_cascade_feature": (_i, [_vp, _i, _ip, C.POINTER(C.c_float), _ip]),
     "nv_debug_cascade_subset": (_i, [_vp, _i, _ip]),
+    "nv_element_transform_frame_device": (_i, [_vp, _vp, _i, _i, _i, C.c_uint64, C.c_double]),
+    "nv_draw_shapes_device": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i]),
+    "nv_debug_draw_shapes_spans": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _ip]),
     "nv_debug_num_levels": (_i, [_vp]),
     "nv_debug_level_info": (_i, [_vp, _i, C.POINTER(LevelInfo)]),
     "nv_debug_get_gray": (_i, [_vp, _vp, _i, _ip, _ip]),
@@ -305,6 +313,13 @@ class Element:
                "nv_element_transform_frame_ip")
         return self._outputs()
 
+    def process_device(self, d_ptr: int, w: int, h: int, stride: int, pts_ns: int = 0, now_ms: float = -1.0):
+        """One BGR(A) buffer that lives in device memory (d_ptr: a CUDA device address, e.g. torch.Tensor.data_ptr()) through
+        nv_element_transform_frame_device; the overlays are written into it on the device.  Same outputs as process()."""
+        _check(_lib.nv_element_transform_frame_device(self.handle, C.c_void_p(d_ptr), w, h, stride, pts_ns, now_ms),
+               "nv_element_transform_frame_device")
+        return self._outputs()
+
     def process_yuv(self, planes, fmt="I420", pts_ns: int = 0, now_ms: float = -1.0):
         """One 4:2:0 buffer (nubofacedetector only) through nv_element_transform_frame_yuv; same outputs as process()."""
         f = Context._yuv_frame(planes, fmt)
@@ -328,6 +343,23 @@ def draw_rectangle(frame, x0, y0, x1, y1, bgr):
     _check(_lib.nv_debug_draw_rectangle(_p(frame), w, h, frame.strides[0], cn, int(x0), int(y0), int(x1), int(y1),
                                         int(bgr[0]), int(bgr[1]), int(bgr[2])), "nv_debug_draw_rectangle")
     return frame
+
+
+def _shape_array(shapes):
+    arr = (Shape * max(len(shapes), 1))()
+    for i, (kind, a, b, c, d, col) in enumerate(shapes):
+        arr[i] = Shape(0 if kind == "rect" else 1, int(a), int(b), int(c), int(d), int(col[0]), int(col[1]), int(col[2]), 0)
+    return arr
+
+
+def draw_shapes_spans(frame, shapes):
+    """The host half of the device overlay on a host frame (nv_debug_draw_shapes_spans); returns the number of disjoint spans."""
+    assert frame.dtype == np.uint8 and frame.ndim == 3 and frame.flags["C_CONTIGUOUS"]
+    h, w, cn = frame.shape
+    n = C.c_int(0)
+    _check(_lib.nv_debug_draw_shapes_spans(_p(frame), w, h, frame.strides[0], cn, _shape_array(shapes), len(shapes), C.byref(n)),
+           "nv_debug_draw_shapes_spans")
+    return n.value
 
 
 def draw_circle(frame, cx, cy, radius, bgr, thickness=4):
@@ -479,6 +511,12 @@ class Context:
         _check(_lib.nv_tracker_process_yuv(self.handle, C.byref(f), float(ts_ms), C.byref(p), self._out, self._cap, C.byref(n)),
                "nv_tracker_process_yuv")
         return _rects(self._out, n.value)
+
+    def draw_shapes_device(self, d_ptr: int, w: int, h: int, stride: int, channels: int, shapes):
+        """shapes: [("rect", x0, y0, x1, y1, (b, g, r))] / [("circle", cx, cy, radius, thickness, (b, g, r))], drawn in order into
+        the BGR(A) frame at device address d_ptr (nv_draw_shapes_device)."""
+        _check(_lib.nv_draw_shapes_device(self.handle, C.c_void_p(d_ptr), w, h, stride, channels, _shape_array(shapes), len(shapes)),
+               "nv_draw_shapes_device")
 
     def tracker_kernel_ms(self):
         ms = C.c_float(0)

@@ -134,3 +134,40 @@ def test_view_eyes_circle_matches_cv2():
         cv2.circle(exp, (cx, cy), r, col + ((0,) if cn == 4 else ()), th, 8, 0)
         got = nv.draw_circle(base.copy(), cx, cy, r, col, th)
         assert (got == exp).all(), (W, H, r, cx, cy, cn, th)
+
+
+def _random_shapes(rng, W, H, n):
+    shapes = []
+    for _ in range(n):
+        col = tuple(int(v) for v in rng.integers(0, 256, 3))
+        if rng.integers(0, 3):
+            x0, x1 = (int(v) for v in rng.integers(-10, W + 10, 2)); y0, y1 = (int(v) for v in rng.integers(-10, H + 10, 2))
+            shapes.append(("rect", x0, y0, x1, y1, col))
+        else:
+            shapes.append(("circle", int(rng.integers(-20, W + 20)), int(rng.integers(-20, H + 20)), int(rng.integers(0, 40)),
+                           4 if rng.integers(0, 4) else int(rng.integers(2, 9)), col))
+    return shapes
+
+
+def test_overlay_spans_match_sequential_drawing():
+    """The host half of the device-side overlay (nv_draw_shapes_device, nv_element_transform_frame_device): shapes are
+    rasterised into spans, the spans made disjoint with the LATER shape winning, then written in arbitrary order — the
+    picture must be the one cv2 draws shape after shape, overlaps in different colours and clipping included."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(17)
+    for t in range(60):
+        W, H, cn = int(rng.integers(30, 200)), int(rng.integers(30, 150)), 3 + t % 2
+        shapes = _random_shapes(rng, W, H, int(rng.integers(1, 12)))
+        base = rng.integers(0, 256, (H, W, cn), dtype=np.uint8)
+        exp = base.copy()
+        for (kind, a, b, c, d, col) in shapes:
+            sc = col + ((0,) if cn == 4 else ())
+            if kind == "rect":
+                cv2.rectangle(exp, (a, b), (c, d), sc, 3, 8, 0)
+            else:
+                cv2.circle(exp, (a, b), c, sc, d, 8, 0)
+        got = base.copy()
+        n = nv.draw_shapes_spans(got, shapes)
+        assert (got == exp).all(), (t, shapes)
+        assert n > 0 or (got == base).all()
+    assert nv.draw_shapes_spans(np.zeros((8, 8, 3), np.uint8), []) == 0

@@ -260,6 +260,74 @@ def test_view_properties_draw_into_the_frame(cdir):
     e.close()
 
 
+def test_device_resident_frames_and_device_side_overlay(cdir):
+    """Frames that never leave the GPU (nv_element_transform_frame_device): every element gives the messages it gives on
+    the same frame in host memory, and its view-* / set_visual_mode overlay — written by k_draw_spans into the device
+    frame — equals the host drawing pixel for pixel (itself pinned to cv2 above).  Then nv_draw_shapes_device against
+    cv2.rectangle / cv2.circle on random overlapping, clipped shapes."""
+    torch = pytest.importorskip("torch")
+    cv2 = pytest.importorskip("cv2")
+    frames = sequence(1280, 720, 3, 2, 3, smin=0.4, smax=0.6)
+    drawn = 0
+    for factory, prop in [("nubofacedetector", "view-faces"), ("nubomouthdetector", "view-mouths"), ("nubonosedetector", "view-noses"),
+                          ("nuboeyedetector", "view-eyes"), ("nuboeardetector", "view-ears")]:
+        eh, ed = nv.Element(factory, 0, cdir), nv.Element(factory, 0, cdir)
+        eh.set(prop, 1); ed.set(prop, 1)
+        for i, fr in enumerate(frames):
+            g = fr.copy()
+            out_h = eh.process(g, pts_ns=i * 40_000_000, now_ms=1e15 + 40.0 * i)
+            d = torch.from_numpy(fr.copy()).cuda()
+            out_d = ed.process_device(d.data_ptr(), fr.shape[1], fr.shape[0], fr.strides[0], pts_ns=i * 40_000_000, now_ms=1e15 + 40.0 * i)
+            assert out_d == out_h, (factory, i)
+            got = d.cpu().numpy()
+            assert (got == g).all(), (factory, i)
+            drawn += int((g != fr).any())
+        eh.close(); ed.close()
+    assert drawn >= 8
+    seq = synth.tracker_sequence(640, 360, 5, seed=5)
+    eh, ed = nv.Element("nubotracker", 0, cdir), nv.Element("nubotracker", 0, cdir)
+    eh.set("set_visual_mode", 1); ed.set("set_visual_mode", 1)
+    drawn = 0
+    for i, fr in enumerate(seq):
+        g = fr.copy()
+        out_h = eh.process(g, pts_ns=40_000_000 * (i + 1))
+        d = torch.from_numpy(fr.copy()).cuda()
+        out_d = ed.process_device(d.data_ptr(), fr.shape[1], fr.shape[0], fr.strides[0], pts_ns=40_000_000 * (i + 1))
+        assert out_d == out_h and (d.cpu().numpy() == g).all(), i
+        drawn += int((g != fr).any())
+    assert drawn > 0
+    eh.close(); ed.close()
+    with pytest.raises(nv.NuboError):                                  # a host pointer is refused, not dereferenced on the device
+        e = nv.Element("nubofacedetector", 0, cdir)
+        e.process_device(frames[0].ctypes.data, 1280, 720, 3840)
+
+    ctx = nv.Context(0, 640, 480)
+    rng = np.random.default_rng(23)
+    for t in range(25):
+        W, H, cn = int(rng.integers(40, 640)), int(rng.integers(40, 480)), 3 + t % 2
+        shapes = []
+        for _ in range(int(rng.integers(1, 14))):
+            col = tuple(int(v) for v in rng.integers(0, 256, 3))
+            if rng.integers(0, 3):
+                x0, x1 = (int(v) for v in rng.integers(-10, W + 10, 2)); y0, y1 = (int(v) for v in rng.integers(-10, H + 10, 2))
+                shapes.append(("rect", x0, y0, x1, y1, col))
+            else:
+                shapes.append(("circle", int(rng.integers(-20, W + 20)), int(rng.integers(-20, H + 20)), int(rng.integers(0, 60)),
+                               4 if rng.integers(0, 4) else int(rng.integers(2, 9)), col))
+        base = rng.integers(0, 256, (H, W, cn), dtype=np.uint8)
+        exp = base.copy()
+        for (kind, a, b, c, dd, col) in shapes:
+            sc = col + ((0,) if cn == 4 else ())
+            if kind == "rect":
+                cv2.rectangle(exp, (a, b), (c, dd), sc, 3, 8, 0)
+            else:
+                cv2.circle(exp, (a, b), c, sc, dd, 8, 0)
+        d = torch.from_numpy(base.copy()).cuda()
+        ctx.draw_shapes_device(d.data_ptr(), W, H, base.strides[0], cn, shapes)
+        assert (d.cpu().numpy() == exp).all(), (t, shapes)
+    ctx.close()
+
+
 def test_elements_on_concurrent_host_threads(cdir):
     """One streaming thread per element, as GStreamer runs them: four host threads, each driving its own face and
     mouth element over its own frames at the same time (shared cascade files, separate contexts and streams), must
