@@ -530,7 +530,9 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         if ((rc = ensure(&ctx->d_vnf, &wcap, (size_t)wofs)) != NV_OK) return rc;
         if ((rc = ensure(&ctx->d_queue, &ctx->queue_cap, (size_t)wofs)) != NV_OK) return rc;
         ctx->win_cap = wcap;
-        if ((rc = ensure(&ctx->d_bits_ok, &ctx->bits_cap, (size_t)bofs)) != NV_OK) return rc;
+        // three bit planes of `bofs` words each: alive after stage 0 and the skip rule | failed stage 0 | valid and passed the variance test
+        if ((rc = ensure(&ctx->d_bits_ok, &ctx->bits_cap, (size_t)bofs * 3)) != NV_OK) return rc;
+        ctx->ps->bits_words = bofs;
         if (ctx->debug) {
             if ((rc = ensure(&ctx->d_depth, &ctx->depth_cap, (size_t)wofs)) != NV_OK) return rc;
             if ((rc = ensure(&ctx->d_pyr, &ctx->pyr_cap, (size_t)pofs)) != NV_OK) return rc;
@@ -573,7 +575,7 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
     const PlanDev &P = ctx->ps->plan;
     const DevCascade &m = casc->meta;
     ctx->ps->tp_casc = casc->uid;
-    ctx->ps->use_tiles = false;
+    ctx->ps->use_tiles = false;  ctx->ps->use_s0t = false;
     ctx->ps->gen++;                                              // graphs hold the parameter banks by value
     if (ctx->ps->dexec) { cudaGraphExecDestroy(ctx->ps->dexec); ctx->ps->dexec = nullptr; }
     ctx->ps->use_s0p = !casc->h.general && P.nlevels > 0 && fill_stage0_params(casc, P, &ctx->ps->s0p);
@@ -601,7 +603,11 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
         tp.ps = align_up(tp.rt * tp.cp, 32);
         tp.level_begin = c == 0 ? 0 : P.nlv2;
         tp.level_end = c == 0 ? P.nlv2 : P.nlevels;
-        fill_bulk_stumps(casc, ys, tp.cp, tp.ps, end, &tp);
+        fill_bulk_stumps(casc, ys, tp.cp, tp.ps, 1, end, &tp);
+        Stage0TileParams &s0 = ctx->ps->s0t[c];
+        const bool s0ok = tp.fast && fill_stage0_tile_params(casc, ys, tp.cp, tp.rt, tp.ps, tp.kskew, &s0);
+        ctx->ps->use_s0t = c == 0 ? s0ok : (ctx->ps->use_s0t && s0ok);
+        s0.level_begin = tp.level_begin; s0.level_end = tp.level_end;
         for (int l = tp.level_begin; l < tp.level_end; l++) {
             const LevelDesc &L = P.lv[l];
             cuuint64_t gdim[2] = {(cuuint64_t)L.ipitch, (cuuint64_t)(L.lh + 1)};
@@ -685,9 +691,24 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         NV_CUDA(launch_colscan(ctx->ps->d_plan, P.total_colblk, ctx->d_sum, ctx->d_sq, st));
         if (tilt) { NV_CUDA(launch_tilted(ctx->ps->d_plan, P.total_dblk, ctx->d_sum, ctx->d_tilt, st)); nl += 2; }
         prof_mark(ctx, 4);
+        static const int small_limit = [] { const char *e = getenv("NUBOVCA_SMALL_PLAN"); return e ? atoi(e) : NV_SMALL_PLAN_WINDOWS; }();
+        static const bool s0_tiles = [] { const char *e = getenv("NUBOVCA_S0_TILES"); return !e || atoi(e) != 0; }();
         if (ctx->use_gen) {
             NV_CUDA(launch_stage0_rows_gen(ctx->ps->d_plan, P.total_rows, meta, ctx->cur_gen, ctx->d_sum, ctx->d_sq, tilt, ctx->d_vnf,
                                            ctx->d_bits_ok, ctx->d_counters, depth, st));
+        } else if (ctx->ps->use_tiles && ctx->ps->use_s0t && s0_tiles && P.total_windows > small_limit) {
+            // large plan, FAST cascade: stage 0 densely on the bulk kernel's tiles, then the skip rule along the rows
+            uint32_t *bits_fail = ctx->d_bits_ok + ctx->ps->bits_words, *bits_okv = ctx->d_bits_ok + 2 * (size_t)ctx->ps->bits_words;
+            for (int c = 0; c < 2; c++) {
+                Stage0TileParams &s0 = ctx->ps->s0t[c];
+                int ntiles = c == 0 ? P.ctiles2 : P.ctiles1;
+                if (ntiles == 0) continue;
+                s0.maps = ctx->ps->d_maps; s0.plan = ctx->ps->d_plan; s0.sq = ctx->d_sq; s0.vnf = ctx->d_vnf;
+                s0.bits_fail = bits_fail; s0.bits_okv = bits_okv;
+                NV_CUDA(launch_stage0_tiles(s0, c == 0 ? 2 : 1, ntiles, st));
+                nl++;
+            }
+            NV_CUDA(launch_stage0_chain(P, bits_fail, bits_okv, ctx->d_bits_ok, ctx->d_counters, depth, st));
         } else if (ctx->ps->use_s0p) {
             Stage0Params &sp = ctx->ps->s0p;
             sp.sum = ctx->d_sum; sp.sq = ctx->d_sq; sp.vnf = ctx->d_vnf; sp.bits_alive = ctx->d_bits_ok;
@@ -699,7 +720,6 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         prof_mark(ctx, 5);
         nl += 3;
         int qcap = (int)std::min<size_t>(ctx->queue_cap, 0x7fffffff);
-        static const int small_limit = [] { const char *e = getenv("NUBOVCA_SMALL_PLAN"); return e ? atoi(e) : NV_SMALL_PLAN_WINDOWS; }();
         if (ctx->ps->use_tiles && ctx->cur_tail && P.total_windows <= small_limit && casc->meta.nstages > 1) {
             // small plan: every window alive after stage 0 goes straight to the warp-per-window kernel (same exactness
             // certificates as the tail it normally is, nv_cascade::tail_fast)

@@ -213,6 +213,27 @@ struct TileParams {
 };
 static_assert(sizeof(TileParams) <= 32000, "kernel parameter space is 32764 bytes");
 
+// ---- k_stage0_tiles parameters (large plans, FAST cascades): stage 0 evaluated DENSELY on the bulk kernel's 64x32-window
+// tiles — same TMA staging, same bank classes, same six / eight-load integer classifiers — writing one "failed stage 0"
+// and one "valid and passes the variance test" bit per window; k_stage0_chain then runs the skip rule along every row.
+#define NV_S0T_MAX_STUMPS 8
+struct Stage0TileParams {
+    BulkStump s[NV_S0T_MAX_STUMPS];
+    uint4 o2[NV_S0T_MAX_STUMPS];
+    int stage_first[2], stage_mid6[1], stage_mid[1];   // the member names class_stage reads (one stage)
+    float stage_thr[1];
+    double stage_base[1];
+    uint4 var;                     // byte offsets of the variance rect's corners from the window origin in the tile
+    int win_w, win_h;
+    int level_begin, level_end;
+    int cp, rt, ps, kskew;
+    const CUtensorMap *maps;
+    const PlanDev *plan;
+    const uint32_t *sq;
+    float *vnf;
+    uint32_t *bits_fail, *bits_okv;
+};
+
 // ---- k_stage0_rows_p parameters: per-level corner offsets of the stage-0 classifiers, so that the whole
 // address arithmetic of stage 0 is warp-uniform and lives in the constant bank ----
 #define NV_S0_MAX_STUMPS 8
@@ -255,6 +276,7 @@ struct PlanSlot {
     PlanDev plan;                                            // host copy
     PlanDev *d_plan = nullptr;
     int *d_ptab = nullptr;       size_t ptab_cap = 0;       // pyramid coefficient tables
+    Stage0TileParams s0t[2];  bool use_s0t = false;  int bits_words = 0;   // dense stage 0 on tiles; 32-window words of this plan
     TileParams tp[2];  Stage0Params s0p;  bool use_s0p = false;  CUtensorMap *d_maps = nullptr;  bool use_tiles = false;
     int bulk_end = 0;  unsigned long long tp_casc = 0;  int max_lw = 0;       // uid of the cascade the banks were built for (0: none)
     unsigned long long last_use = 0, buf_gen = 0;            // LRU clock; generation of the shared buffers the tensor maps point into
@@ -402,7 +424,11 @@ cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, con
                                 int stage_begin, int order_free, int nblocks, cudaStream_t st, int smem_bytes);
 cudaError_t launch_alive_to_queue(const PlanDev *plan, int total_rows, const float *vnf, const uint32_t *bits_alive,
                                   uint2 *queue, int *counters, int queue_cap, cudaStream_t st, int cidx = 4);
-void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_end, TileParams *tp);
+void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_begin, int stage_end, TileParams *tp);
+bool fill_stage0_tile_params(const nv_cascade *c, int ystep, int cp, int rt, int ps, int kskew, Stage0TileParams *sp);
+cudaError_t launch_stage0_tiles(const Stage0TileParams &sp, int ystep, int ntiles, cudaStream_t st);
+cudaError_t launch_stage0_chain(const PlanDev &plan, const uint32_t *bits_fail, const uint32_t *bits_okv,
+                                uint32_t *bits_alive, int *counters, int16_t *depth, cudaStream_t st);
 void build_tail_stumps(nv_cascade *c);
 cudaError_t launch_cascade_tail_fast(const PlanDev *plan, const DevCascade *meta, const TailStump *tstumps, const double *tbase,
                                      const uint32_t *sum, const uint2 *tail, int *counters, uint32_t *cand, int cand_cap,

@@ -650,8 +650,8 @@ __device__ __forceinline__ void add_if_lt(double &tmp, float f, float thr, doubl
 }
 
 // NW windows (1 or 2) of one lane through one stage; pass[i] = "stage passed"
-template <bool FAST, int NW>
-__device__ __forceinline__ void class_stage(const TileParams &P, int si, const uint32_t (&wa)[NW], const float (&vnf)[NW],
+template <bool FAST, int NW, typename PT>
+__device__ __forceinline__ void class_stage(const PT &P, int si, const uint32_t (&wa)[NW], const float (&vnf)[NW],
                                             bool (&pass)[NW])
 {
     const int k0 = P.stage_first[si], k1 = P.stage_first[si + 1];
@@ -919,6 +919,150 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
         } else
             P.tail[base] = make_uint2(key, __float_as_uint(__ldg(vnf_tile + ly * L.nx + lx)));
     }
+}
+
+// ================================================================================================
+// k_stage0_tiles + k_stage0_chain — variance normalisation and stage 0 of a LARGE plan (FAST cascades), round 2.
+// k_stage0_rows_p reads its ~44 integral words per window from global memory with a 64-bit address formed for each
+// (343 warp instructions per 32 windows: 46 M per config-3 frame, 14 % of the frame's issue work).  Here stage 0 runs on
+// the bulk kernel's tiles instead: the integral tile comes in by TMA, every lane is bound to its bank class, all 64
+// members of every class are evaluated (nothing is known about the windows yet, so the schedule is dense and the lane
+// use perfect), two windows per lane share the uniform classifier loads, features in int32.  The skip rule needs the
+// failures of a whole window row in order, so this kernel only writes two bits per window — "valid and passes the
+// variance test" and "failed stage 0" — plus the factor; k_stage0_chain then runs the rule along every row on those
+// bit-words (a warp per row, the 32-window words of a row in parallel: each word maps the incoming "next window is
+// visited" flag to the outgoing one, and the prefix of that composition is a five-step shuffle scan).
+// ================================================================================================
+template <int YS>
+__global__ void __launch_bounds__(256) k_stage0_tiles(const __grid_constant__ Stage0TileParams P)
+{
+    extern __shared__ __align__(128) uint32_t tile[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const PlanDev *__restrict__ plan = P.plan;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = uniformize(tid >> 5, 3);
+    int t = blockIdx.x, l = P.level_begin;
+    while (l + 1 < P.level_end && plan->lv[l + 1].ctile0 <= t) l++;
+    const LevelDesc &L = plan->lv[l];
+    const int rel = t - L.ctile0, ty = rel / L.cntx, tx = rel - ty * L.cntx;
+    const int iy0 = ty * NV_CTY, ix0 = tx * NV_CTX;
+    const int CP = P.cp, PS = P.ps, K = P.kskew;
+    const uint32_t bar = smem_u32(&mbar);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, (uint32_t)(YS * P.rt * CP * 4));
+#pragma unroll
+        for (int p = 0; p < YS; p++)
+            tma_load_2d(smem_u32(tile + p * PS), P.maps + l, ix0 + p * L.iplane, iy0 * YS, bar);
+    }
+    // the squared integral is read from global memory: four corners per window, nothing else uses it
+    const int ww = P.win_w, wh = P.win_h;
+    auto gcorner = [&](int dx, int dy) { return dy * L.ipitch + (YS == 2 ? (dx & 1) * L.iplane + (dx >> 1) : dx); };
+    const int q00 = gcorner(1, 1), q10 = gcorner(ww - 1, 1), q01 = gcorner(1, wh - 1), q11 = gcorner(ww - 1, wh - 1);
+    const uint32_t *__restrict__ sqb = P.sq + L.iofs;
+    const double area = (double)((ww - 2) * (wh - 2));
+    const uint32_t tile_sa = smem_u32(tile);
+    const int rowb = YS * CP * 4;
+    mbar_wait(bar, 0);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {                                // warp w: window rows 4w .. 4w + 3, both halves of a row per round
+        const int ly = warp * 4 + r, iy = iy0 + ly;
+        const int iyc = min(iy, L.ny - 1);
+        uint32_t wa[2]; float vnf[2]; bool ok[2], pass[2]; int lx[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            lx[h] = ((lane - K * ly) & 31) + (h << 5);
+            wa[h] = tile_sa + (uint32_t)(ly * rowb + lx[h] * 4);
+            const int ixc = min(ix0 + lx[h], L.nx - 1);
+            const uint32_t *qb = sqb + (size_t)iyc * YS * L.ipitch + ixc;
+            const int valsum = (int)(lds_u32(wa[h] + P.var.x) - lds_u32(wa[h] + P.var.y) - lds_u32(wa[h] + P.var.z) + lds_u32(wa[h] + P.var.w));
+            const uint32_t valsq = __ldg(qb + q00) - __ldg(qb + q10) - __ldg(qb + q01) + __ldg(qb + q11);
+            const double nf = __dsub_rn(__dmul_rn(area, (double)valsq), __dmul_rn((double)valsum, (double)valsum));
+            vnf[h] = 0.f; ok[h] = false;
+            if (nf > 0.) {
+                vnf[h] = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn(nf)));
+                ok[h] = __dmul_rn(area, (double)vnf[h]) < 1e-1;
+            }
+            ok[h] = ok[h] && iy < L.ny && ix0 + lx[h] < L.nx;
+        }
+        class_stage<true, 2>(P, 0, wa, vnf, pass);
+        const int rot = (K * ly) & 31;                           // lane j holds the window at bit (j - K ly) & 31 of its word
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t om = __ballot_sync(0xffffffffu, ok[h]), fm = __ballot_sync(0xffffffffu, ok[h] && !pass[h]);
+            const int cx = 2 * tx + h;
+            if (iy < L.ny && cx < L.nxw) {
+                if (lane == 0) {
+                    const size_t wi = (size_t)L.bofs + (size_t)iy * L.nxw + cx;
+                    P.bits_okv[wi] = __funnelshift_r(om, om, rot);
+                    P.bits_fail[wi] = __funnelshift_r(fm, fm, rot);
+                }
+                if (ok[h]) P.vnf[L.wofs + (size_t)iy * L.nx + ix0 + lx[h]] = vnf[h];
+            }
+        }
+    }
+}
+
+// the level table of a plan as k_stage0_chain reads it: in the kernel's parameter (constant) bank, so that finding a
+// row's level is a walk over uniform loads and not a chain of dependent global ones (18 us of latency for the last levels)
+struct ChainParams {
+    int4 a[NV_MAX_LEVELS];         // row0, nxw, nx, bofs
+    int wofs[NV_MAX_LEVELS];
+    int nlevels, total_rows;
+    const uint32_t *bits_fail, *bits_okv;
+    uint32_t *bits_alive;
+    int *counters;
+    int16_t *depth;
+};
+
+__global__ void __launch_bounds__(256) k_stage0_chain(const __grid_constant__ ChainParams P)
+{
+    const uint32_t *__restrict__ bits_fail = P.bits_fail, *__restrict__ bits_okv = P.bits_okv;
+    uint32_t *__restrict__ bits_alive = P.bits_alive;
+    int16_t *__restrict__ depth = P.depth;
+    int *__restrict__ counters = P.counters;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + uniformize_s0(threadIdx.x >> 5);
+    if (row >= P.total_rows) return;
+    int l = 0;
+    while (l + 1 < P.nlevels && P.a[l + 1].x <= row) l++;
+    struct { int row0, nxw, nx, bofs, wofs; } L = {P.a[l].x, P.a[l].y, P.a[l].z, P.a[l].w, P.wofs[l]};
+    const int iy = row - L.row0;
+    const size_t wbase = (size_t)L.bofs + (size_t)iy * L.nxw;
+    bool carry = true;                                           // x = 0 is always visited
+    int nalive = 0;
+    for (int c0 = 0; c0 < L.nxw; c0 += 32) {
+        const int cx = c0 + lane;
+        const bool have = cx < L.nxw;
+        const uint32_t f = have ? bits_fail[wbase + cx] : 0u, o = have ? bits_okv[wbase + cx] : 0u;
+        bool e0 = false, e1 = true;
+        const uint32_t em0 = skip_rule_word(f, e0), em1 = skip_rule_word(f, e1);   // e0 / e1: flag after this word for an incoming 0 / 1
+        bool a = e0, b = e1;                                     // inclusive scan of the composition: (out for 0, out for 1) of words 0 .. lane
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const bool pa = __shfl_up_sync(0xffffffffu, (int)a, d), pb = __shfl_up_sync(0xffffffffu, (int)b, d);
+            if (lane >= d) { const bool na = pa ? b : a, nb = pb ? b : a; a = na; b = nb; }
+        }
+        const bool xa = __shfl_up_sync(0xffffffffu, (int)a, 1), xb = __shfl_up_sync(0xffffffffu, (int)b, 1);
+        const bool ein = lane == 0 ? carry : (carry ? xb : xa);
+        const uint32_t em = ein ? em1 : em0;
+        const uint32_t alive = em & o & ~f;
+        if (have) bits_alive[wbase + cx] = alive;
+        nalive += __popc(alive);
+        if (depth && have) {
+            for (int j = 0; j < 32; j++) {
+                const int ix = cx * 32 + j;
+                if (ix < L.nx && !((alive >> j) & 1u))
+                    depth[L.wofs + (size_t)iy * L.nx + ix] = (int16_t)(!((em >> j) & 1u) ? NV_DEPTH_SKIPPED : (!((o >> j) & 1u) ? NV_DEPTH_VARREJ : 0));
+            }
+        }
+        const bool la = __shfl_sync(0xffffffffu, (int)a, 31), lb = __shfl_sync(0xffffffffu, (int)b, 31);
+        carry = carry ? lb : la;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nalive += __shfl_xor_sync(0xffffffffu, nalive, d);
+    if (lane == 0 && nalive) atomicAdd(&counters[0], nalive);
 }
 
 #define TAIL_MAX_WIN 32
@@ -1285,26 +1429,19 @@ void build_tail_stumps(nv_cascade *c)
 // which covers the four sharing patterns by the choice of p (a, b, c, d = corners of rect 0; a1.. of rect 1):
 //   left half  (a = a1, c = c1): p = a, c, b, d, b1, d1        right half  (b = b1, d = d1): p = d, b, c, a, c1, a1
 //   top half   (a = a1, b = b1): p = a, b, c, d, c1, d1        bottom half (c = c1, d = d1): p = d, c, b, a, b1, a1
-void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_end, TileParams *tp)
+// One stage's weak classifiers in the bulk kernels' form, appended at S[n], O2[n].  FAST: group 0 = six-load two-rect,
+// 1 = eight-load two-rect, 2 = three-rect (mid6 / mid = where groups 1 / 2 start); otherwise XML order in one group.
+// base = sum of the stage's right leaves.
+static void fill_stage_stumps(const nv_cascade *c, int ystep, int cp, int ps, int s, bool fast, BulkStump *S, uint4 *O2, int *n_io,
+                              int *mid6, int *mid, double *base)
 {
     const DevCascade &m = c->meta;
-    tp->stage_begin = 1;
-    tp->stage_end = stage_end;
-    tp->final_stage = stage_end == m.nstages;
-    bool fast = c->h.order_free != 0;
-    for (int k = m.stage_first[1]; k < m.stage_first[stage_end] && fast; k++) {
-        const DevStump &d = c->stumps[k];
-        double bound = 0;
-        for (int j = 0; j < 3; j++) {
-            if (d.w[j] != rintf(d.w[j]) || fabsf(d.w[j]) > 4096.f) fast = false;
-            bound += fabs((double)d.w[j]) * ((d.r[j] >> 16) & 255) * (d.r[j] >> 24) * 255.0;
-        }
-        if (bound >= 16777216.0 || d.w[0] != -1.f) fast = false;
-    }
-    tp->fast = fast ? 1 : 0;
     auto off = [&](int dx, int dy) { return 4u * (uint32_t)(ystep == 2 ? (dx & 1) * ps + dy * cp + (dx >> 1) : dy * cp + dx); };
     auto f2u = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
-    struct Corners { uint32_t a, b, c, d; bool eq(const Corners &o, int i) const { return (&a)[i] == (&o.a)[i]; } };
+    struct Corners {
+        uint32_t a, b, c, d;
+        bool eq(const Corners &o, int i) const { return i == 0 ? a == o.a : i == 1 ? b == o.b : i == 2 ? c == o.c : d == o.d; }
+    };
     auto corners = [&](uint32_t r) {
         int x = r & 255, y = (r >> 8) & 255, w = (r >> 16) & 255, h = r >> 24;
         return Corners{off(x, y), off(x + w, y), off(x, y + h), off(x + w, y + h)};
@@ -1320,42 +1457,91 @@ void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_
         if (e[2] && e[3] && !e[0] && !e[1]) return 4;
         return 0;
     };
+    int n = *n_io;
+    double rsum = 0;
+    *mid6 = *mid = n;
+    for (int grp = 0; grp < (fast ? 3 : 1); grp++) {
+        for (int k = m.stage_first[s]; k < m.stage_first[s + 1]; k++) {
+            const DevStump &d = c->stumps[k];
+            bool three = d.w[2] != 0.f;
+            int pat = pattern(d);
+            if (fast && (three ? 2 : (pat ? 0 : 1)) != grp) continue;
+            BulkStump &b = S[n];
+            Corners p = corners(d.r[0]), q = corners(d.r[1]), t = corners(three ? d.r[2] : d.r[0]);
+            b.o0 = make_uint4(p.a, p.b, p.c, p.d); b.o1 = make_uint4(q.a, q.b, q.c, q.d); O2[n] = make_uint4(t.a, t.b, t.c, t.d);
+            if (fast && pat == 1) { b.o0 = make_uint4(p.a, p.c, p.b, p.d); b.o1 = make_uint4(q.b, q.d, 0, 0); }
+            if (fast && pat == 2) { b.o0 = make_uint4(p.d, p.b, p.c, p.a); b.o1 = make_uint4(q.c, q.a, 0, 0); }
+            if (fast && pat == 3) { b.o0 = make_uint4(p.a, p.b, p.c, p.d); b.o1 = make_uint4(q.c, q.d, 0, 0); }
+            if (fast && pat == 4) { b.o0 = make_uint4(p.d, p.c, p.b, p.a); b.o1 = make_uint4(q.b, q.a, 0, 0); }
+            if (fast) { b.w0 = (uint32_t)(int)d.w[0]; b.w1 = (uint32_t)(int)d.w[1]; b.w2 = (uint32_t)(int)d.w[2]; }
+            else { b.w0 = f2u(d.w[0]); b.w1 = f2u(d.w[1]); b.w2 = f2u(d.w[2]); }
+            b.thr = f2u(d.thr); b.left = f2u(d.left); b.right = f2u(d.right);
+            double dd = 128.0 * ((double)d.left - (double)d.right);          // see add_if_lt
+            uint64_t u; memcpy(&u, &dd, 8);
+            b.d_lo = (uint32_t)u; b.d_hi = (uint32_t)(u >> 32);
+            rsum += (double)d.right;
+            n++;
+        }
+        if (grp == 0 && fast) *mid6 = n;
+        if (grp == 1 && fast) *mid = n;
+    }
+    if (!fast) *mid6 = *mid = *n_io;
+    *base = rsum;
+    *n_io = n;
+}
+
+// exactness certificates of stages [stage_begin, stage_end): order-free stage sums (cascade_xml.cpp) and integer feature
+// arithmetic — rect 0 weighs -1, the other weights are small integers and sum |w| * area * 255 < 2^24
+static bool stages_are_fast(const nv_cascade *c, int stage_begin, int stage_end)
+{
+    const DevCascade &m = c->meta;
+    bool fast = c->h.order_free != 0;
+    for (int k = m.stage_first[stage_begin]; k < m.stage_first[stage_end] && fast; k++) {
+        const DevStump &d = c->stumps[k];
+        double bound = 0;
+        for (int j = 0; j < 3; j++) {
+            if (d.w[j] != rintf(d.w[j]) || fabsf(d.w[j]) > 4096.f) fast = false;
+            bound += fabs((double)d.w[j]) * ((d.r[j] >> 16) & 255) * (d.r[j] >> 24) * 255.0;
+        }
+        if (bound >= 16777216.0 || d.w[0] != -1.f) fast = false;
+    }
+    return fast;
+}
+
+void fill_bulk_stumps(const nv_cascade *c, int ystep, int cp, int ps, int stage_begin, int stage_end, TileParams *tp)
+{
+    const DevCascade &m = c->meta;
+    tp->stage_begin = stage_begin;
+    tp->stage_end = stage_end;
+    tp->final_stage = stage_end == m.nstages;
+    const bool fast = stages_are_fast(c, stage_begin, stage_end);
+    tp->fast = fast ? 1 : 0;
     int n = 0;
-    for (int s = 1; s < stage_end; s++) {
-        int si = s - 1;
+    for (int s = stage_begin; s < stage_end; s++) {
+        const int si = s - stage_begin;
         tp->stage_first[si] = n;
         tp->stage_thr[si] = m.stage_thr[s];
-        tp->stage_mid6[si] = tp->stage_mid[si] = n;
-        double rsum = 0;
-        // FAST: group 0 = six-load two-rect, 1 = eight-load two-rect, 2 = three-rect; otherwise XML order in one group
-        for (int grp = 0; grp < (fast ? 3 : 1); grp++) {
-            for (int k = m.stage_first[s]; k < m.stage_first[s + 1]; k++) {
-                const DevStump &d = c->stumps[k];
-                bool three = d.w[2] != 0.f;
-                int pat = pattern(d);
-                if (fast && (three ? 2 : (pat ? 0 : 1)) != grp) continue;
-                BulkStump &b = tp->s[n];
-                Corners p = corners(d.r[0]), q = corners(d.r[1]), t = corners(three ? d.r[2] : d.r[0]);
-                b.o0 = make_uint4(p.a, p.b, p.c, p.d); b.o1 = make_uint4(q.a, q.b, q.c, q.d); tp->o2[n] = make_uint4(t.a, t.b, t.c, t.d);
-                if (fast && pat == 1) { b.o0 = make_uint4(p.a, p.c, p.b, p.d); b.o1 = make_uint4(q.b, q.d, 0, 0); }
-                if (fast && pat == 2) { b.o0 = make_uint4(p.d, p.b, p.c, p.a); b.o1 = make_uint4(q.c, q.a, 0, 0); }
-                if (fast && pat == 3) { b.o0 = make_uint4(p.a, p.b, p.c, p.d); b.o1 = make_uint4(q.c, q.d, 0, 0); }
-                if (fast && pat == 4) { b.o0 = make_uint4(p.d, p.c, p.b, p.a); b.o1 = make_uint4(q.b, q.a, 0, 0); }
-                if (fast) { b.w0 = (uint32_t)(int)d.w[0]; b.w1 = (uint32_t)(int)d.w[1]; b.w2 = (uint32_t)(int)d.w[2]; }
-                else { b.w0 = f2u(d.w[0]); b.w1 = f2u(d.w[1]); b.w2 = f2u(d.w[2]); }
-                b.thr = f2u(d.thr); b.left = f2u(d.left); b.right = f2u(d.right);
-                double dd = 128.0 * ((double)d.left - (double)d.right);          // see add_if_lt
-                uint64_t u; memcpy(&u, &dd, 8);
-                b.d_lo = (uint32_t)u; b.d_hi = (uint32_t)(u >> 32);
-                rsum += (double)d.right;
-                n++;
-            }
-            if (grp == 0 && fast) tp->stage_mid6[si] = n;
-            if (grp == 1 && fast) tp->stage_mid[si] = n;
-        }
-        tp->stage_base[si] = rsum;
+        fill_stage_stumps(c, ystep, cp, ps, s, fast, tp->s, tp->o2, &n, &tp->stage_mid6[si], &tp->stage_mid[si], &tp->stage_base[si]);
     }
-    tp->stage_first[stage_end - 1] = n;
+    tp->stage_first[stage_end - stage_begin] = n;
+}
+
+// stage 0 in the tile layout of one ystep class; false when stage 0 lacks the exactness certificates or is too wide
+bool fill_stage0_tile_params(const nv_cascade *c, int ystep, int cp, int rt, int ps, int kskew, Stage0TileParams *sp)
+{
+    const DevCascade &m = c->meta;
+    const int n0 = m.stage_first[1];
+    if (n0 > NV_S0T_MAX_STUMPS || n0 < 1 || !stages_are_fast(c, 0, 1)) return false;
+    int n = 0;
+    sp->stage_first[0] = 0;
+    sp->stage_thr[0] = m.stage_thr[0];
+    fill_stage_stumps(c, ystep, cp, ps, 0, true, sp->s, sp->o2, &n, &sp->stage_mid6[0], &sp->stage_mid[0], &sp->stage_base[0]);
+    sp->stage_first[1] = n;
+    auto off = [&](int dx, int dy) { return 4u * (uint32_t)(ystep == 2 ? (dx & 1) * ps + dy * cp + (dx >> 1) : dy * cp + dx); };
+    sp->var = make_uint4(off(1, 1), off(m.win_w - 1, 1), off(1, m.win_h - 1), off(m.win_w - 1, m.win_h - 1));
+    sp->win_w = m.win_w; sp->win_h = m.win_h;
+    sp->cp = cp; sp->rt = rt; sp->ps = ps; sp->kskew = kskew;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1381,6 +1567,40 @@ cudaError_t launch_alive_to_queue(const PlanDev *plan, int total_rows, const flo
                                   uint2 *queue, int *counters, int queue_cap, cudaStream_t st, int cidx)
 {
     k_alive_to_queue<<<(total_rows + 7) / 8, 256, 0, st>>>(plan, total_rows, vnf, bits_alive, queue, counters, queue_cap, cidx);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stage0_tiles(const Stage0TileParams &sp, int ystep, int ntiles, cudaStream_t st)
+{
+    const size_t smem = (size_t)ystep * sp.ps * sizeof(uint32_t);
+    static std::mutex mu;
+    static unsigned long long attr_set = 0ull;                   // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!((attr_set >> (dev & 63)) & 1ull)) {
+            cudaFuncSetAttribute(k_stage0_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_stage0_tiles<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            attr_set |= 1ull << (dev & 63);
+        }
+    }
+    if (ystep == 2) k_stage0_tiles<2><<<ntiles, 256, smem, st>>>(sp);
+    else k_stage0_tiles<1><<<ntiles, 256, smem, st>>>(sp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stage0_chain(const PlanDev &plan, const uint32_t *bits_fail, const uint32_t *bits_okv,
+                                uint32_t *bits_alive, int *counters, int16_t *depth, cudaStream_t st)
+{
+    ChainParams cp;
+    for (int l = 0; l < plan.nlevels; l++) {
+        const LevelDesc &L = plan.lv[l];
+        cp.a[l] = make_int4(L.row0, L.nxw, L.nx, L.bofs); cp.wofs[l] = L.wofs;
+    }
+    cp.nlevels = plan.nlevels; cp.total_rows = plan.total_rows;
+    cp.bits_fail = bits_fail; cp.bits_okv = bits_okv; cp.bits_alive = bits_alive; cp.counters = counters; cp.depth = depth;
+    k_stage0_chain<<<(plan.total_rows + 7) / 8, 256, 0, st>>>(cp);
     return cudaGetLastError();
 }
 
