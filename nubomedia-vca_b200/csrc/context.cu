@@ -463,6 +463,7 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         if (scales.size() > 4096) break;
     }
     int nstripes = 1;
+    if (!nv_wide_tile_config(&P.wide_w, &P.wide_h)) P.wide_w = P.wide_h = 0;
     long long iofs = 0, wofs = 0, bofs = 0, tofs = 0, pofs = 0;
     int nl = 0;
     for (size_t k = 0; k < scales.size(); k++) {
@@ -497,6 +498,11 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         int cnt = L.cntx * ((L.ny + NV_CTY - 1) / NV_CTY);
         if (ystep == 2) { L.ctile0 = P.ctiles2; P.ctiles2 += cnt; P.nlv2 = nl; }
         else { L.ctile0 = P.ctiles1; P.ctiles1 += cnt; }
+        L.wtile0 = 0; L.wntx = 0;
+        if (ystep == 1 && P.wide_w > 0) {
+            L.wntx = (L.nx + P.wide_w - 1) / P.wide_w;
+            L.wtile0 = P.wtiles1; P.wtiles1 += L.wntx * ((L.ny + P.wide_h - 1) / P.wide_h);
+        }
         if (iofs > 0x7fffffffLL || wofs > 0x7fffffffLL) { nv_set_error("frame too large"); return NV_ERR_CAPACITY; }
     }
     P.nlevels = nl;
@@ -586,38 +592,51 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
     while (end < m.nstages && end < NV_BULK_MAX_STAGES && m.stage_first[end + 1] - m.stage_first[1] <= NV_BULK_MAX_STUMPS) end++;
     ctx->ps->bulk_end = end;
     static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
-    alignas(64) CUtensorMap maps[NV_MAX_LEVELS];
+    // maps[l]: the bulk kernel's box of level l; maps[NV_MAX_LEVELS + l]: the 64x32-window box of the dense stage-0 kernel
+    // (the same box unless the level's bulk stages run on wide tiles)
+    alignas(64) CUtensorMap maps[2 * NV_MAX_LEVELS];
     memset(maps, 0, sizeof maps);
     if (!ctx->ps->d_maps) NV_CUDA(cudaMalloc(&ctx->ps->d_maps, sizeof maps));
     for (int c = 0; c < 2; c++) {
         int ys = c == 0 ? 2 : 1;
         TileParams &tp = ctx->ps->tp[c];
-        // columns per plane; ys*cp is a multiple of 32 words so that windows of different rows with different
-        // lx never share a bank (a raster-ordered batch of 32 alive windows is then conflict-free)
-        // the pitch is 4 (mod 8) words, so that the bank class (lx + kskew * ly) & 31 of a window moves by a
-        // multiple of 4 that is not a multiple of 32 from one window row to the next
-        tp.cp = align_up(NV_CTX + (ys == 2 ? m.win_w / 2 : m.win_w) + 1, 4);
-        if (tp.cp % 8 == 0) tp.cp += 4;
-        tp.rt = (NV_CTY - 1) * ys + m.win_h + 1;
-        tp.kskew = (ys * tp.cp) & 31;
-        tp.ps = align_up(tp.rt * tp.cp, 32);
+        // tile geometry for tw x th windows.  Columns per plane: the pitch is 4 (mod 8) words, so that the bank class
+        // (lx + kskew * ly) & 31 of a window moves by a multiple of 4 that is not a multiple of 32 from one window row to
+        // the next
+        struct Geo { int cp, rt, ps, kskew; };
+        auto geometry = [&](int tw, int th) {
+            Geo g;
+            g.cp = align_up(tw + (ys == 2 ? m.win_w / 2 : m.win_w) + 1, 4);
+            if (g.cp % 8 == 0) g.cp += 4;
+            g.rt = (th - 1) * ys + m.win_h + 1;
+            g.kskew = (ys * g.cp) & 31;
+            g.ps = align_up(g.rt * g.cp, 32);
+            return g;
+        };
+        const Geo g0 = geometry(NV_CTX, NV_CTY);
+        const bool wide = c == 1 && P.wide_w > 0;
+        const Geo g = wide ? geometry(P.wide_w, P.wide_h) : g0;
+        if (g.cp > 256 || g.rt > 256) return NV_OK;             // TMA box limit: keep the generic queue path
+        tp.cp = g.cp; tp.rt = g.rt; tp.kskew = g.kskew; tp.ps = g.ps;
         tp.level_begin = c == 0 ? 0 : P.nlv2;
         tp.level_end = c == 0 ? P.nlv2 : P.nlevels;
         fill_bulk_stumps(casc, ys, tp.cp, tp.ps, 1, end, &tp);
         Stage0TileParams &s0 = ctx->ps->s0t[c];
-        const bool s0ok = tp.fast && fill_stage0_tile_params(casc, ys, tp.cp, tp.rt, tp.ps, tp.kskew, &s0);
+        const bool s0ok = tp.fast && fill_stage0_tile_params(casc, ys, g0.cp, g0.rt, g0.ps, g0.kskew, &s0);
         ctx->ps->use_s0t = c == 0 ? s0ok : (ctx->ps->use_s0t && s0ok);
         s0.level_begin = tp.level_begin; s0.level_end = tp.level_end;
         for (int l = tp.level_begin; l < tp.level_end; l++) {
             const LevelDesc &L = P.lv[l];
             cuuint64_t gdim[2] = {(cuuint64_t)L.ipitch, (cuuint64_t)(L.lh + 1)};
             cuuint64_t gstr[1] = {(cuuint64_t)L.ipitch * 4};
-            cuuint32_t box[2] = {(cuuint32_t)tp.cp, (cuuint32_t)tp.rt};
             cuuint32_t estr[2] = {1, 1};
-            CUresult r = enc(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, ctx->d_sum + L.iofs, gdim, gstr, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return NV_OK;       // keep the generic queue path for this plan
+            for (int k = 0; k < 2; k++) {
+                cuuint32_t box[2] = {(cuuint32_t)(k == 0 ? g.cp : g0.cp), (cuuint32_t)(k == 0 ? g.rt : g0.rt)};
+                CUresult r = enc(&maps[k * NV_MAX_LEVELS + l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, ctx->d_sum + L.iofs, gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return NV_OK;   // keep the generic queue path for this plan
+            }
         }
     }
     NV_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -703,7 +722,7 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
                 Stage0TileParams &s0 = ctx->ps->s0t[c];
                 int ntiles = c == 0 ? P.ctiles2 : P.ctiles1;
                 if (ntiles == 0) continue;
-                s0.maps = ctx->ps->d_maps; s0.plan = ctx->ps->d_plan; s0.sq = ctx->d_sq; s0.vnf = ctx->d_vnf;
+                s0.maps = ctx->ps->d_maps + NV_MAX_LEVELS; s0.plan = ctx->ps->d_plan; s0.sq = ctx->d_sq; s0.vnf = ctx->d_vnf;
                 s0.bits_fail = bits_fail; s0.bits_okv = bits_okv;
                 NV_CUDA(launch_stage0_tiles(s0, c == 0 ? 2 : 1, ntiles, st));
                 nl++;
@@ -746,7 +765,8 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
                 tp.plan = ctx->ps->d_plan; tp.bits_alive = ctx->d_bits_ok; tp.vnf = ctx->d_vnf; tp.depth = depth;
                 tp.tail = ctx->d_queue; tp.cand = ctx->d_cand; tp.counters = ctx->d_counters; tp.maps = ctx->ps->d_maps;
                 tp.tail_cap = qcap; tp.cand_cap = ctx->cand_cap;
-                NV_CUDA(launch_cascade_classes(tp, c == 0 ? 2 : 1, ntiles, st));
+                if (c == 1 && P.wide_w > 0) NV_CUDA(launch_cascade_wide(tp, P.wide_w, P.wide_h, P.wtiles1, st));
+                else NV_CUDA(launch_cascade_classes(tp, c == 0 ? 2 : 1, ntiles, st));
                 nl++;
             }
             prof_mark(ctx, 6);

@@ -922,6 +922,160 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
 }
 
 // ================================================================================================
+// k_cascade_wide — the bulk stages on WIDE tiles (round 2; ystep-1 levels).  Same bank-class scheme as k_cascade_classes
+// — lane c only evaluates windows of class (lx + kskew * ly) & 31, so corner loads never conflict — but the tile is
+// TW x TH windows with TW * TH / 32 = 128 or 256 members per class.  A stage costs "members of the fullest class" warp
+// steps per weak classifier, so the more members a class has the closer the fullest class is to the average one: on
+// config 3 the ystep-1 levels take 4.30 M steps in 64x32 tiles, 3.83 M in 64x64 and 3.49 M in 128x64 (simulated on the
+// oracle's depth maps; the 64x32 figure equals the DFMA count ncu reports for k_cascade_classes<1>).
+// What changes with the mask width is how a warp finds its windows.  The alive set of a class is TW * TH / 1024 words in
+// shared memory; warp w takes the CONTIGUOUS ranks [w q, (w + 1) q), q = ceil(fullest class / 8) — the same steps per
+// warp as the interleaved ranks of k_cascade_classes, but a lane walks its words once: skip w q set bits at the start of
+// the stage, then one "clear lowest bit" per window instead of eight.
+// ================================================================================================
+template <int YS, bool FAST, int TW, int TH>
+__global__ void __launch_bounds__(256) k_cascade_wide(const __grid_constant__ TileParams P)
+{
+    constexpr int HW = TW / 32;                                  // 32-window words per tile row
+    constexpr int NM = TH * HW;                                  // members per class
+    constexpr int MW = NM / 32;                                  // mask words per class
+    constexpr int MPW = NM / 8;                                  // members whose rows one warp transposes
+    static_assert(MPW <= 32 && 32 % MPW == 0 && TH % 8 == 0, "a warp's rows fill (part of) one mask word");
+    extern __shared__ __align__(128) uint32_t tile[];           // [YS planes][rt][cp], plane stride ps
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ uint32_t s_mask[3][MW][32];                       // rotating alive masks: [buffer][word][class]
+    __shared__ uint32_t s_words[TH][HW];
+    const PlanDev *__restrict__ plan = P.plan;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = uniformize(tid >> 5, 3);
+
+    int t = blockIdx.x, l = P.level_begin;
+    while (l + 1 < P.level_end && plan->lv[l + 1].wtile0 <= t) l++;
+    const LevelDesc &L = plan->lv[l];
+    const int rel = t - L.wtile0, ty = rel / L.wntx, tx = rel - ty * L.wntx;
+    const int iy0 = ty * TH, ix0 = tx * TW;
+    const int CP = P.cp, PS = P.ps, K = P.kskew;
+    const uint32_t bar = smem_u32(&mbar);
+
+    if (tid == 0) mbar_init(bar, 1);
+    for (int i = tid; i < TH * HW; i += 256) {                   // the tile's alive words
+        const int ly = i / HW, h = i - ly * HW, cx = HW * tx + h;
+        s_words[ly][h] = (iy0 + ly < L.ny && cx < L.nxw) ? P.bits_alive[L.bofs + (size_t)(iy0 + ly) * L.nxw + cx] : 0u;
+    }
+    for (int i = tid; i < 3 * MW * 32; i += 256) (&s_mask[0][0][0])[i] = 0u;
+    __syncthreads();
+    if (tid == 0) {                                              // stage the integral tile: one box per plane
+        mbar_expect_tx(bar, (uint32_t)(YS * P.rt * CP * 4));
+#pragma unroll
+        for (int p = 0; p < YS; p++)
+            tma_load_2d(smem_u32(tile + p * PS), P.maps + l, ix0 + p * L.iplane, iy0 * YS, bar);
+    }
+    {   // class masks: warp w transposes window rows [w TH / 8, (w + 1) TH / 8): MPW consecutive members of every class
+        uint32_t part = 0;
+#pragma unroll
+        for (int i = 0; i < MPW; i++) {
+            const int ly = warp * (TH / 8) + i / HW, h = i % HW;
+            const uint32_t b = (s_words[ly][h] >> ((lane - K * ly) & 31)) & 1u;
+            part |= b << i;
+        }
+        const int m0 = warp * MPW;
+        if (part) atomicOr(&s_mask[0][m0 >> 5][lane], part << (m0 & 31));
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);                                           // also before an early exit: the copy targets this CTA's smem
+
+    const uint32_t tile_sa = smem_u32(tile);
+    const float *__restrict__ vnf_tile = P.vnf + L.wofs + (size_t)iy0 * L.nx + ix0;
+    const int rowb = YS * CP * 4;                                // bytes from one window row to the next
+    int cur = 0;
+    for (int st = P.stage_begin; st < P.stage_end; st++) {
+        const int si = st - P.stage_begin;
+        int cnt = 0;
+#pragma unroll
+        for (int w = 0; w < MW; w++) cnt += __popc(s_mask[cur][w][lane]);
+        const int maxc = uniformize(__reduce_max_sync(0xffffffffu, cnt), 9);
+        if (maxc == 0) return;                                   // block-uniform: every warp reads the same masks
+        const int nxt = cur == 2 ? 0 : cur + 1, zer = nxt == 2 ? 0 : nxt + 1;
+        if (warp == 0) {
+#pragma unroll
+            for (int w = 0; w < MW; w++) s_mask[zer][w][lane] = 0u;
+        }
+        const int q = (maxc + 7) >> 3;                           // ranks per warp: warp w takes [w q, (w + 1) q)
+        int skip = warp * q;
+        int mine = min(max(cnt - skip, 0), q);                   // windows of this lane in this stage
+        const int steps = uniformize(min(max(maxc - skip, 0), q), 6);   // = the largest `mine` of the warp
+        int wi = 0;
+        uint32_t curw = 0u;
+        if (mine > 0) {                                          // walk to the first of them
+            curw = s_mask[cur][0][lane];
+            for (int pc = __popc(curw); skip >= pc; pc = __popc(curw)) { skip -= pc; curw = s_mask[cur][++wi][lane]; }
+            for (; skip > 0; skip--) curw &= curw - 1u;
+        }
+        for (int r = 0; r < steps; r += 2) {                     // two windows per lane and round
+            int m[2], ly[2], lx[2]; bool active[2], pass[2]; uint32_t wa[2]; float vnf[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                active[i] = mine > 0;
+                m[i] = 0;
+                if (active[i]) {
+                    while (curw == 0u) curw = s_mask[cur][++wi][lane];
+                    m[i] = (wi << 5) + __ffs((int)curw) - 1;
+                    curw &= curw - 1u;
+                    mine--;
+                }
+                ly[i] = m[i] / HW; lx[i] = ((lane - K * ly[i]) & 31) + ((m[i] % HW) << 5);
+                wa[i] = tile_sa + (uint32_t)(ly[i] * rowb + lx[i] * 4);
+                vnf[i] = active[i] ? __ldg(vnf_tile + ly[i] * L.nx + lx[i]) : 0.f;     // per-window factor, L2-resident
+            }
+            if (r + 1 < steps) class_stage<FAST, 2>(P, si, wa, vnf, pass);
+            else {
+                const uint32_t wa1[1] = {wa[0]}; const float vnf1[1] = {vnf[0]}; bool pass1[1];
+                class_stage<FAST, 1>(P, si, wa1, vnf1, pass1);
+                pass[0] = pass1[0]; pass[1] = false;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (active[i] && pass[i]) atomicOr(&s_mask[nxt][m[i] >> 5][lane], 1u << (m[i] & 31));
+                if (P.depth && active[i] && !pass[i]) P.depth[L.wofs + (iy0 + ly[i]) * L.nx + ix0 + lx[i]] = (int16_t)(-st);
+            }
+        }
+        __syncthreads();
+        cur = nxt;
+    }
+    // survivors: candidates if the bulk stages were the whole cascade, else the tail queue
+    if (warp != 0) return;
+    int cnt = 0;
+#pragma unroll
+    for (int w = 0; w < MW; w++) cnt += __popc(s_mask[cur][w][lane]);
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0) return;
+    int *counter = P.counters + (P.final_stage ? 1 : 3);
+    const int cap = P.final_stage ? P.cand_cap : P.tail_cap;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 0) + inc - cnt;
+    for (int w = 0; w < MW; w++) {
+        for (uint32_t rem = s_mask[cur][w][lane]; rem; rem &= rem - 1u, base++) {
+            const int m = (w << 5) + __ffs((int)rem) - 1;
+            const int ly = m / HW, lx = ((lane - K * ly) & 31) + ((m % HW) << 5);
+            const uint32_t key = ((uint32_t)l << 26) | ((uint32_t)(iy0 + ly) << 13) | (uint32_t)(ix0 + lx);
+            if (base >= cap) { P.counters[2] = 1; continue; }
+            if (P.final_stage) {
+                P.cand[base] = key;
+                if (P.depth) P.depth[L.wofs + (iy0 + ly) * L.nx + ix0 + lx] = NV_DEPTH_PASS;
+            } else
+                P.tail[base] = make_uint2(key, __float_as_uint(__ldg(vnf_tile + ly * L.nx + lx)));
+        }
+    }
+}
+
+// ================================================================================================
 // k_stage0_tiles + k_stage0_chain — variance normalisation and stage 0 of a LARGE plan (FAST cascades), round 2.
 // k_stage0_rows_p reads its ~44 integral words per window from global memory with a 64-bit address formed for each
 // (343 warp instructions per 32 windows: 46 M per config-3 frame, 14 % of the frame's issue work).  Here stage 0 runs on
@@ -1629,6 +1783,49 @@ cudaError_t launch_cascade_classes(const TileParams &tp, int ystep, int ntiles, 
         else k_cascade_classes<1, false><<<ntiles, 256, smem, st>>>(tp);
     }
     return cudaGetLastError();
+}
+
+// NUBOVCA_WIDE=WxH picks the tile shape of the ystep-1 levels (64x64 or 128x64: k_cascade_wide); "0" keeps 64x32 tiles
+bool nv_wide_tile_config(int *tw, int *th)
+{
+    static const int cfg = [] {
+        const char *e = getenv("NUBOVCA_WIDE");
+        if (!e) return NV_WIDE_DEFAULT;
+        int w = 0, h = 0;
+        if (sscanf(e, "%dx%d", &w, &h) == 2 && ((w == 64 && h == 64) || (w == 128 && h == 64) || (w == 64 && h == 32))) return (w << 16) | h;
+        return 0;
+    }();
+    *tw = cfg >> 16; *th = cfg & 0xffff;
+    return cfg != 0;
+}
+
+template <int TW, int TH>
+static cudaError_t launch_wide_t(const TileParams &tp, int ntiles, size_t smem, cudaStream_t st)
+{
+    static std::mutex mu;
+    static unsigned long long attr_set = 0ull;                   // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!((attr_set >> (dev & 63)) & 1ull)) {
+            cudaFuncSetAttribute(k_cascade_wide<1, true, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_cascade_wide<1, false, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            attr_set |= 1ull << (dev & 63);
+        }
+    }
+    if (tp.fast) k_cascade_wide<1, true, TW, TH><<<ntiles, 256, smem, st>>>(tp);
+    else k_cascade_wide<1, false, TW, TH><<<ntiles, 256, smem, st>>>(tp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cascade_wide(const TileParams &tp, int tw, int th, int ntiles, cudaStream_t st)
+{
+    const size_t smem = (size_t)tp.ps * sizeof(uint32_t);        // ystep-1 levels: one plane
+    if (tw == 64 && th == 64) return launch_wide_t<64, 64>(tp, ntiles, smem, st);
+    if (tw == 128 && th == 64) return launch_wide_t<128, 64>(tp, ntiles, smem, st);
+    if (tw == 64 && th == 32) return launch_wide_t<64, 32>(tp, ntiles, smem, st);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,
