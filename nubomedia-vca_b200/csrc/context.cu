@@ -463,7 +463,8 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         if (scales.size() > 4096) break;
     }
     int nstripes = 1;
-    if (!nv_wide_tile_config(&P.wide_w, &P.wide_h)) P.wide_w = P.wide_h = 0;
+    for (int c = 0; c < 2; c++)
+        if (!nv_wide_tile_config(c, &P.wide_w[c], &P.wide_h[c])) P.wide_w[c] = P.wide_h[c] = 0;
     long long iofs = 0, wofs = 0, bofs = 0, tofs = 0, pofs = 0;
     int nl = 0;
     for (size_t k = 0; k < scales.size(); k++) {
@@ -499,9 +500,10 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         if (ystep == 2) { L.ctile0 = P.ctiles2; P.ctiles2 += cnt; P.nlv2 = nl; }
         else { L.ctile0 = P.ctiles1; P.ctiles1 += cnt; }
         L.wtile0 = 0; L.wntx = 0;
-        if (ystep == 1 && P.wide_w > 0) {
-            L.wntx = (L.nx + P.wide_w - 1) / P.wide_w;
-            L.wtile0 = P.wtiles1; P.wtiles1 += L.wntx * ((L.ny + P.wide_h - 1) / P.wide_h);
+        const int wc = ystep == 2 ? 0 : 1;
+        if (P.wide_w[wc] > 0) {
+            L.wntx = (L.nx + P.wide_w[wc] - 1) / P.wide_w[wc];
+            L.wtile0 = P.wtiles[wc]; P.wtiles[wc] += L.wntx * ((L.ny + P.wide_h[wc] - 1) / P.wide_h[wc]);
         }
         if (iofs > 0x7fffffffLL || wofs > 0x7fffffffLL) { nv_set_error("frame too large"); return NV_ERR_CAPACITY; }
     }
@@ -614,8 +616,8 @@ static int ensure_tile_params(nv_ctx *ctx, const nv_cascade *casc)
             return g;
         };
         const Geo g0 = geometry(NV_CTX, NV_CTY);
-        const bool wide = c == 1 && P.wide_w > 0;
-        const Geo g = wide ? geometry(P.wide_w, P.wide_h) : g0;
+        const bool wide = P.wide_w[c] > 0;
+        const Geo g = wide ? geometry(P.wide_w[c], P.wide_h[c]) : g0;
         if (g.cp > 256 || g.rt > 256) return NV_OK;             // TMA box limit: keep the generic queue path
         tp.cp = g.cp; tp.rt = g.rt; tp.kskew = g.kskew; tp.ps = g.ps;
         tp.level_begin = c == 0 ? 0 : P.nlv2;
@@ -765,7 +767,7 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
                 tp.plan = ctx->ps->d_plan; tp.bits_alive = ctx->d_bits_ok; tp.vnf = ctx->d_vnf; tp.depth = depth;
                 tp.tail = ctx->d_queue; tp.cand = ctx->d_cand; tp.counters = ctx->d_counters; tp.maps = ctx->ps->d_maps;
                 tp.tail_cap = qcap; tp.cand_cap = ctx->cand_cap;
-                if (c == 1 && P.wide_w > 0) NV_CUDA(launch_cascade_wide(tp, P.wide_w, P.wide_h, P.wtiles1, st));
+                if (P.wide_w[c] > 0) NV_CUDA(launch_cascade_wide(tp, c == 0 ? 2 : 1, P.wide_w[c], P.wide_h[c], P.wtiles[c], st));
                 else NV_CUDA(launch_cascade_classes(tp, c == 0 ? 2 : 1, ntiles, st));
                 nl++;
             }

@@ -142,7 +142,7 @@ struct LevelDesc {
     int row0;              // first window row in k_stage0_rows' grid
     int dblk0;             // first block (256 diagonals) of this level in the tilted-integral kernels' grid
     int ctile0, cntx;      // k_cascade_classes: first 64x32-window tile within the ystep class, tile columns = ceil(nx/64)
-    int wtile0, wntx;      // k_cascade_wide (ystep-1 levels): first wide tile, tile columns = ceil(nx / wide_w)
+    int wtile0, wntx;      // k_cascade_wide: first tile of the level within its ystep class, tile columns = ceil(nx / wide_w[class])
 };
 
 struct PlanDev {
@@ -152,7 +152,7 @@ struct PlanDev {
     int total_rowblk, total_colblk, total_chunks, total_rows, total_windows;
     int nlv2;              // levels [0, nlv2) have ystep 2, [nlv2, nlevels) ystep 1 (scales ascend)
     int ctiles2, ctiles1;  // 64x32-window tile counts of the two ystep classes
-    int wtiles1, wide_w, wide_h;   // ystep-1 levels cut into wide_w x wide_h-window tiles for k_cascade_wide (0: not used)
+    int wtiles[2], wide_w[2], wide_h[2];   // k_cascade_wide: tile count and tile shape (windows) of the ystep-2 [0] / ystep-1 [1] levels; wide_w 0: class runs k_cascade_classes
     int total_dblk;        // blocks of the tilted-integral kernels
     LevelDesc lv[NV_MAX_LEVELS];
 };
@@ -177,8 +177,12 @@ struct ResizeKey {
 // stages' weak classifiers live in the constant bank, so they cost no load/store-unit bandwidth) ----
 #define NV_BULK_MAX_STUMPS 384
 #define NV_BULK_MAX_STAGES 16
-#ifndef NV_WIDE_DEFAULT
-#define NV_WIDE_DEFAULT 0          // (w << 16) | h of k_cascade_wide's tiles on ystep-1 levels; 0: 64x32 tiles, k_cascade_classes
+#ifndef NV_WIDE_DEFAULT                      // (w << 16) | h of k_cascade_wide's tiles; 0: the class runs k_cascade_classes (64x32)
+#define NV_WIDE_DEFAULT ((128 << 16) | 64)   // ystep-1 levels
+#endif
+#ifndef NV_WIDE2_DEFAULT
+#define NV_WIDE2_DEFAULT 0                   // ystep-2 levels stay on k_cascade_classes: two column planes per tile make a 64x64 tile 89 KB of
+                                             // shared memory (2800 against 2880 frames/s), and at 64x32 the interleaved ranks are 1 % ahead
 #endif
 #define NV_CTX 64                  // tile width and height in windows
 #define NV_CTY 32
@@ -422,8 +426,8 @@ cudaError_t launch_queue_stages_gen_staged(const PlanDev *plan, const DevCascade
                                            uint32_t *cand, int cand_cap, int16_t *depth, int nstages, int order_free,
                                            cudaStream_t st, int *nlaunch);
 cudaError_t launch_cascade_classes(const TileParams &tp, int ystep, int ntiles, cudaStream_t st);
-bool nv_wide_tile_config(int *tw, int *th);          // tile shape of k_cascade_wide on ystep-1 levels (false: 64x32 tiles, k_cascade_classes)
-cudaError_t launch_cascade_wide(const TileParams &tp, int tw, int th, int ntiles, cudaStream_t st);
+bool nv_wide_tile_config(int cls, int *tw, int *th);  // tile shape of k_cascade_wide on ystep-2 (cls 0) / ystep-1 (cls 1) levels; false: k_cascade_classes
+cudaError_t launch_cascade_wide(const TileParams &tp, int ystep, int tw, int th, int ntiles, cudaStream_t st);
 cudaError_t launch_stage0_rows_p(const Stage0Params &sp, cudaStream_t st);
 bool fill_stage0_params(const nv_cascade *c, const PlanDev &P, Stage0Params *sp);
 cudaError_t launch_cascade_tail(const PlanDev *plan, const DevCascade *meta, const DevStump *stumps, const uint32_t *sum,

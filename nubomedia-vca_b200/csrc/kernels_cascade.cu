@@ -1785,21 +1785,28 @@ cudaError_t launch_cascade_classes(const TileParams &tp, int ystep, int ntiles, 
     return cudaGetLastError();
 }
 
-// NUBOVCA_WIDE=WxH picks the tile shape of the ystep-1 levels (64x64 or 128x64: k_cascade_wide); "0" keeps 64x32 tiles
-bool nv_wide_tile_config(int *tw, int *th)
+// NUBOVCA_WIDE=WxH / NUBOVCA_WIDE2=WxH pick the tile shape of the ystep-1 / ystep-2 levels in k_cascade_wide (64x32, 64x64 or
+// 128x64; ystep 2: 64x32 or 64x64); "0" sends the class to k_cascade_classes (64x32 tiles, interleaved ranks)
+bool nv_wide_tile_config(int cls, int *tw, int *th)
 {
-    static const int cfg = [] {
+    static const int cfg[2] = {[] {
+        const char *e = getenv("NUBOVCA_WIDE2");
+        if (!e) return NV_WIDE2_DEFAULT;
+        int w = 0, h = 0;
+        if (sscanf(e, "%dx%d", &w, &h) == 2 && w == 64 && (h == 64 || h == 32)) return (w << 16) | h;
+        return 0;
+    }(), [] {
         const char *e = getenv("NUBOVCA_WIDE");
         if (!e) return NV_WIDE_DEFAULT;
         int w = 0, h = 0;
         if (sscanf(e, "%dx%d", &w, &h) == 2 && ((w == 64 && h == 64) || (w == 128 && h == 64) || (w == 64 && h == 32))) return (w << 16) | h;
         return 0;
-    }();
-    *tw = cfg >> 16; *th = cfg & 0xffff;
-    return cfg != 0;
+    }()};
+    *tw = cfg[cls] >> 16; *th = cfg[cls] & 0xffff;
+    return cfg[cls] != 0;
 }
 
-template <int TW, int TH>
+template <int YS, int TW, int TH>
 static cudaError_t launch_wide_t(const TileParams &tp, int ntiles, size_t smem, cudaStream_t st)
 {
     static std::mutex mu;
@@ -1809,22 +1816,24 @@ static cudaError_t launch_wide_t(const TileParams &tp, int ntiles, size_t smem, 
     {
         std::lock_guard<std::mutex> lk(mu);
         if (!((attr_set >> (dev & 63)) & 1ull)) {
-            cudaFuncSetAttribute(k_cascade_wide<1, true, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            cudaFuncSetAttribute(k_cascade_wide<1, false, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_cascade_wide<YS, true, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_cascade_wide<YS, false, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             attr_set |= 1ull << (dev & 63);
         }
     }
-    if (tp.fast) k_cascade_wide<1, true, TW, TH><<<ntiles, 256, smem, st>>>(tp);
-    else k_cascade_wide<1, false, TW, TH><<<ntiles, 256, smem, st>>>(tp);
+    if (tp.fast) k_cascade_wide<YS, true, TW, TH><<<ntiles, 256, smem, st>>>(tp);
+    else k_cascade_wide<YS, false, TW, TH><<<ntiles, 256, smem, st>>>(tp);
     return cudaGetLastError();
 }
 
-cudaError_t launch_cascade_wide(const TileParams &tp, int tw, int th, int ntiles, cudaStream_t st)
+cudaError_t launch_cascade_wide(const TileParams &tp, int ystep, int tw, int th, int ntiles, cudaStream_t st)
 {
-    const size_t smem = (size_t)tp.ps * sizeof(uint32_t);        // ystep-1 levels: one plane
-    if (tw == 64 && th == 64) return launch_wide_t<64, 64>(tp, ntiles, smem, st);
-    if (tw == 128 && th == 64) return launch_wide_t<128, 64>(tp, ntiles, smem, st);
-    if (tw == 64 && th == 32) return launch_wide_t<64, 32>(tp, ntiles, smem, st);
+    const size_t smem = (size_t)ystep * tp.ps * sizeof(uint32_t);
+    if (ystep == 1 && tw == 64 && th == 64) return launch_wide_t<1, 64, 64>(tp, ntiles, smem, st);
+    if (ystep == 1 && tw == 128 && th == 64) return launch_wide_t<1, 128, 64>(tp, ntiles, smem, st);
+    if (ystep == 1 && tw == 64 && th == 32) return launch_wide_t<1, 64, 32>(tp, ntiles, smem, st);
+    if (ystep == 2 && tw == 64 && th == 64) return launch_wide_t<2, 64, 64>(tp, ntiles, smem, st);
+    if (ystep == 2 && tw == 64 && th == 32) return launch_wide_t<2, 64, 32>(tp, ntiles, smem, st);
     return cudaErrorInvalidValue;
 }
 
