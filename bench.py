@@ -705,14 +705,17 @@ def main():
         iso = {k: statistics.median(v) for k, v in iso_acc.items()}
         iso_casc = iso.get("cascade_stage0", 0) + iso.get("cascade_tiles", 0) + iso.get("cascade_tail", 0)
         traffic, onchip = None, None
+        casc_names = "k_stage0_tiles<2> + k_stage0_tiles<1> + k_stage0_chain + k_cascade_classes<2> + k_cascade_wide<1, 128x64> + k_cascade_tail_fast"
         tpath = os.path.join(ROOT, "profiles", "traffic.json")          # counters from the committed ncu --set full capture
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             traffic = tj.get("cascade_dram_bytes_per_frame")
+            if tj.get("cascade_kernels"):
+                casc_names = " + ".join(tj["cascade_kernels"])
             wf = tj.get("tile_shared_wavefronts_per_frame")
             wi = tj.get("tile_warp_instructions_per_frame")
             if wf and wi and iso.get("cascade_tiles", 0) > 0:
-                # what actually bounds the dominant kernel (k_cascade_classes): warp-instruction issue (4 per SM and
+                # what actually bounds the bulk kernels (k_cascade_classes on ystep-2 levels, k_cascade_wide on ystep-1 levels): warp-instruction issue (4 per SM and
                 # clock) first, the shared-memory pipe (one 128-byte wavefront per SM and clock) second
                 clk = (clocks.get("sm_max_mhz") or 1965.0) * 1e6
                 t = iso["cascade_tiles"] * 1e-3
@@ -741,7 +744,7 @@ def main():
                     "d2h_bytes_per_step": world * B * (16 + 1024 * 16), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches) * world,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "cascade (k_stage0_rows_p + k_cascade_classes<2> + k_cascade_classes<1> + k_cascade_tail_fast)",
+            "roofline": {"bound": "hbm", "kernel": "cascade (" + casc_names + ")",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms_isolated": iso_casc,

@@ -3,6 +3,8 @@
   python tools/summarize_ncu.py launches <launches.csv> [skip_frames frames]   per-kernel average time and share
   python tools/summarize_ncu.py raw <file.ncu-rep> [kernel regex]               the metrics quoted in DESIGN.md / bench.py
   python tools/summarize_ncu.py lines <file.ncu-rep> <kernel substring> [n]     hottest source lines of one kernel
+  python tools/summarize_ncu.py traffic <cascade.ncu-rep> <label> [old.json]    the counters bench.py reads (profiles/traffic.json);
+                                                                               keys it cannot derive (tracker_*) are carried over from old.json
 
 `raw` and `lines` need `ncu` (reading a report needs no GPU)."""
 import collections
@@ -95,8 +97,48 @@ def lines(rep, kernel, n=15):
         break
 
 
+def traffic(rep, label, old=None):
+    """One config-3 frame's cascade kernels (stage 0, bulk, tail) from a --set full capture -> the counters of bench.py's roofline."""
+    import json
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    idx = {h: i for i, h in enumerate(rows[0])}
+    for h, i in list(idx.items()):                               # "SM_B.TriageCompute.l1tex__t_sectors.sum" -> "l1tex__t_sectors.sum"
+        idx.setdefault(h.split("TriageCompute.")[-1], i)
+    num = lambda r, m: float(r[idx[m]].replace(",", ""))      # noqa: E731
+    unit = lambda m: rows[1][idx[m]]                             # noqa: E731
+    casc = [r for r in rows[2:] if re.search(r"k_stage0|k_cascade", r[idx["Kernel Name"]])]
+    names = [short(r[idx["Kernel Name"]]) for r in casc]
+    per_frame = len(set(names))
+    casc, names = casc[:per_frame], names[:per_frame]           # the first frame of the capture
+    bulk = [r for r, n in zip(casc, names) if re.search(r"k_cascade_classes|k_cascade_wide", n)]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    dram = sum(num(r, m) * scale[unit(m)] for r in casc for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    d = json.load(open(old)) if old else {}
+    d.update({
+        "cascade_kernels": names,
+        "cascade_dram_bytes_per_frame": dram,
+        "cascade_warp_instructions_per_frame": sum(num(r, "smsp__inst_executed.sum") for r in casc),
+        "source": f"{label}: dram__bytes_read.sum + dram__bytes_write.sum summed over {', '.join(names)} for one cfg3 frame (ncu --set full --clock-control none)",
+        "tile_kernels": [short(r[idx["Kernel Name"]]) for r in bulk],
+        "tile_shared_wavefronts_per_frame": sum(num(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum") for r in bulk),
+        "tile_shared_bank_conflict_wavefronts_per_frame": sum(num(r, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum") for r in bulk),
+        "tile_warp_instructions_per_frame": sum(num(r, "smsp__inst_executed.sum") for r in bulk),
+        "wavefront_source": f"{label}: l1tex__data_pipe_lsu_wavefronts_mem_shared.sum and smsp__inst_executed.sum of the two bulk kernels, one cfg3 frame",
+        "tile_lts_bytes_per_frame": 32 * sum(num(r, "lts__t_sectors.sum") for r in bulk),
+        "tile_l1tex_bytes_per_frame": 32 * sum(num(r, "l1tex__t_sectors.sum") for r in bulk),
+        "lts_ncu_pct_of_peak": [round(num(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"), 2) for r in bulk],
+        "l1tex_ncu_pct_of_peak": [round(num(r, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"), 2) for r in bulk],
+        "lts_source": f"{label}: 32 B x lts__t_sectors.sum (L2) and 32 B x l1tex__t_sectors.sum (L1/TEX) of the two bulk launches of one cfg3 frame, with ncu's own lts__throughput / l1tex__throughput percentages of peak per launch",
+    })
+    print(json.dumps(d, indent=1))
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1]
+    if cmd == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
+        sys.exit(0)
     if cmd == "launches":
         launches(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     elif cmd == "raw":
