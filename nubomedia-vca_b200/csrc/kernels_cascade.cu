@@ -929,25 +929,26 @@ __global__ void __launch_bounds__(256) k_cascade_classes(const __grid_constant__
 // config 3 the ystep-1 levels take 4.30 M steps in 64x32 tiles, 3.83 M in 64x64 and 3.49 M in 128x64 (simulated on the
 // oracle's depth maps; the 64x32 figure equals the DFMA count ncu reports for k_cascade_classes<1>).
 // What changes with the mask width is how a warp finds its windows.  The alive set of a class is TW * TH / 1024 words in
-// shared memory; warp w takes the CONTIGUOUS ranks [w q, (w + 1) q), q = ceil(fullest class / 8) — the same steps per
+// shared memory; warp w takes the CONTIGUOUS ranks [w q, (w + 1) q), q = ceil(fullest class / warps) — the same steps per
 // warp as the interleaved ranks of k_cascade_classes, but a lane walks its words once: skip w q set bits at the start of
 // the stage, then one "clear lowest bit" per window instead of eight.
 // ================================================================================================
-template <int YS, bool FAST, int TW, int TH>
-__global__ void __launch_bounds__(256) k_cascade_wide(const __grid_constant__ TileParams P)
+template <int YS, bool FAST, int TW, int TH, int NWARP>
+__global__ void __launch_bounds__(32 * NWARP) k_cascade_wide(const __grid_constant__ TileParams P)
 {
     constexpr int HW = TW / 32;                                  // 32-window words per tile row
     constexpr int NM = TH * HW;                                  // members per class
     constexpr int MW = NM / 32;                                  // mask words per class
-    constexpr int MPW = NM / 8;                                  // members whose rows one warp transposes
-    static_assert(MPW <= 32 && 32 % MPW == 0 && TH % 8 == 0, "a warp's rows fill (part of) one mask word");
+    constexpr int MPW = NM / NWARP;                              // members whose rows one warp transposes
+    constexpr int NT = 32 * NWARP;
+    static_assert(MPW <= 32 && 32 % MPW == 0 && TH % NWARP == 0 && (NWARP == 8 || NWARP == 16), "a warp's rows fill (part of) one mask word");
     extern __shared__ __align__(128) uint32_t tile[];           // [YS planes][rt][cp], plane stride ps
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ uint32_t s_mask[3][MW][32];                       // rotating alive masks: [buffer][word][class]
     __shared__ uint32_t s_words[TH][HW];
     const PlanDev *__restrict__ plan = P.plan;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = uniformize(tid >> 5, 3);
+    const int warp = uniformize(tid >> 5, NWARP == 16 ? 4 : 3);
 
     int t = blockIdx.x, l = P.level_begin;
     while (l + 1 < P.level_end && plan->lv[l + 1].wtile0 <= t) l++;
@@ -958,11 +959,11 @@ __global__ void __launch_bounds__(256) k_cascade_wide(const __grid_constant__ Ti
     const uint32_t bar = smem_u32(&mbar);
 
     if (tid == 0) mbar_init(bar, 1);
-    for (int i = tid; i < TH * HW; i += 256) {                   // the tile's alive words
+    for (int i = tid; i < TH * HW; i += NT) {                   // the tile's alive words
         const int ly = i / HW, h = i - ly * HW, cx = HW * tx + h;
         s_words[ly][h] = (iy0 + ly < L.ny && cx < L.nxw) ? P.bits_alive[L.bofs + (size_t)(iy0 + ly) * L.nxw + cx] : 0u;
     }
-    for (int i = tid; i < 3 * MW * 32; i += 256) (&s_mask[0][0][0])[i] = 0u;
+    for (int i = tid; i < 3 * MW * 32; i += NT) (&s_mask[0][0][0])[i] = 0u;
     __syncthreads();
     if (tid == 0) {                                              // stage the integral tile: one box per plane
         mbar_expect_tx(bar, (uint32_t)(YS * P.rt * CP * 4));
@@ -970,11 +971,11 @@ __global__ void __launch_bounds__(256) k_cascade_wide(const __grid_constant__ Ti
         for (int p = 0; p < YS; p++)
             tma_load_2d(smem_u32(tile + p * PS), P.maps + l, ix0 + p * L.iplane, iy0 * YS, bar);
     }
-    {   // class masks: warp w transposes window rows [w TH / 8, (w + 1) TH / 8): MPW consecutive members of every class
+    {   // class masks: warp w transposes window rows [w TH / NWARP, (w + 1) TH / NWARP): MPW consecutive members of every class
         uint32_t part = 0;
 #pragma unroll
         for (int i = 0; i < MPW; i++) {
-            const int ly = warp * (TH / 8) + i / HW, h = i % HW;
+            const int ly = warp * (TH / NWARP) + i / HW, h = i % HW;
             const uint32_t b = (s_words[ly][h] >> ((lane - K * ly) & 31)) & 1u;
             part |= b << i;
         }
@@ -1000,7 +1001,7 @@ __global__ void __launch_bounds__(256) k_cascade_wide(const __grid_constant__ Ti
 #pragma unroll
             for (int w = 0; w < MW; w++) s_mask[zer][w][lane] = 0u;
         }
-        const int q = (maxc + 7) >> 3;                           // ranks per warp: warp w takes [w q, (w + 1) q)
+        const int q = (maxc + NWARP - 1) / NWARP;                // ranks per warp: warp w takes [w q, (w + 1) q)
         int skip = warp * q;
         int mine = min(max(cnt - skip, 0), q);                   // windows of this lane in this stage
         const int steps = uniformize(min(max(maxc - skip, 0), q), 6);   // = the largest `mine` of the warp
@@ -1806,7 +1807,7 @@ bool nv_wide_tile_config(int cls, int *tw, int *th)
     return cfg[cls] != 0;
 }
 
-template <int YS, int TW, int TH>
+template <int YS, int TW, int TH, int NWARP>
 static cudaError_t launch_wide_t(const TileParams &tp, int ntiles, size_t smem, cudaStream_t st)
 {
     static std::mutex mu;
@@ -1816,24 +1817,27 @@ static cudaError_t launch_wide_t(const TileParams &tp, int ntiles, size_t smem, 
     {
         std::lock_guard<std::mutex> lk(mu);
         if (!((attr_set >> (dev & 63)) & 1ull)) {
-            cudaFuncSetAttribute(k_cascade_wide<YS, true, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            cudaFuncSetAttribute(k_cascade_wide<YS, false, TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_cascade_wide<YS, true, TW, TH, NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(k_cascade_wide<YS, false, TW, TH, NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             attr_set |= 1ull << (dev & 63);
         }
     }
-    if (tp.fast) k_cascade_wide<YS, true, TW, TH><<<ntiles, 256, smem, st>>>(tp);
-    else k_cascade_wide<YS, false, TW, TH><<<ntiles, 256, smem, st>>>(tp);
+    if (tp.fast) k_cascade_wide<YS, true, TW, TH, NWARP><<<ntiles, 32 * NWARP, smem, st>>>(tp);
+    else k_cascade_wide<YS, false, TW, TH, NWARP><<<ntiles, 32 * NWARP, smem, st>>>(tp);
     return cudaGetLastError();
 }
 
 cudaError_t launch_cascade_wide(const TileParams &tp, int ystep, int tw, int th, int ntiles, cudaStream_t st)
 {
     const size_t smem = (size_t)ystep * tp.ps * sizeof(uint32_t);
-    if (ystep == 1 && tw == 64 && th == 64) return launch_wide_t<1, 64, 64>(tp, ntiles, smem, st);
-    if (ystep == 1 && tw == 128 && th == 64) return launch_wide_t<1, 128, 64>(tp, ntiles, smem, st);
-    if (ystep == 1 && tw == 64 && th == 32) return launch_wide_t<1, 64, 32>(tp, ntiles, smem, st);
-    if (ystep == 2 && tw == 64 && th == 64) return launch_wide_t<2, 64, 64>(tp, ntiles, smem, st);
-    if (ystep == 2 && tw == 64 && th == 32) return launch_wide_t<2, 64, 32>(tp, ntiles, smem, st);
+    static const int nwarp[2] = {[] { const char *e = getenv("NUBOVCA_WIDE2_WARPS"); return e && atoi(e) == 8 ? 8 : 16; }(),
+                                 [] { const char *e = getenv("NUBOVCA_WIDE_WARPS"); return e && atoi(e) == 16 ? 16 : 8; }()};
+    const int nw = nwarp[ystep == 2 ? 0 : 1];
+    if (ystep == 1 && tw == 64 && th == 64) return nw == 16 ? launch_wide_t<1, 64, 64, 16>(tp, ntiles, smem, st) : launch_wide_t<1, 64, 64, 8>(tp, ntiles, smem, st);
+    if (ystep == 1 && tw == 128 && th == 64) return nw == 16 ? launch_wide_t<1, 128, 64, 16>(tp, ntiles, smem, st) : launch_wide_t<1, 128, 64, 8>(tp, ntiles, smem, st);
+    if (ystep == 1 && tw == 64 && th == 32) return launch_wide_t<1, 64, 32, 8>(tp, ntiles, smem, st);
+    if (ystep == 2 && tw == 64 && th == 64) return nw == 16 ? launch_wide_t<2, 64, 64, 16>(tp, ntiles, smem, st) : launch_wide_t<2, 64, 64, 8>(tp, ntiles, smem, st);
+    if (ystep == 2 && tw == 64 && th == 32) return launch_wide_t<2, 64, 32, 8>(tp, ntiles, smem, st);
     return cudaErrorInvalidValue;
 }
 
