@@ -274,6 +274,11 @@ extern "C" int nv_ctx_create(int gpu, int max_width, int max_height, nv_ctx **ou
     int rc = [&]() -> int {
         NV_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         NV_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+        NV_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            NV_CUDA(cudaEventCreateWithFlags(&c->ev_fork[i], cudaEventDisableTiming));
+            NV_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+        }
         c->frame_cap = (size_t)max_width * max_height * 4 + 4096;
         NV_CUDA(cudaMallocHost(&c->h_frame, c->frame_cap));
         NV_CUDA(cudaMalloc(&c->d_frame, c->frame_cap));
@@ -319,6 +324,8 @@ extern "C" void nv_ctx_destroy(nv_ctx *c)
     cudaFree(c->d_trk_prev); cudaFree(c->d_trk_hist); cudaFree(c->d_trk_scratch); cudaFreeHost(c->h_trk);
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
+    for (int i = 0; i < 2; i++) { if (c->ev_fork[i]) cudaEventDestroy(c->ev_fork[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     for (int i = 0; i <= NV_NUM_STAGES; i++) if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
@@ -714,21 +721,25 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         prof_mark(ctx, 4);
         static const int small_limit = [] { const char *e = getenv("NUBOVCA_SMALL_PLAN"); return e ? atoi(e) : NV_SMALL_PLAN_WINDOWS; }();
         static const bool s0_tiles = [] { const char *e = getenv("NUBOVCA_S0_TILES"); return !e || atoi(e) != 0; }();
+        static const bool two_streams = [] { const char *e = getenv("NUBOVCA_TWO_STREAMS"); return !e || atoi(e) != 0; }();
         if (ctx->use_gen) {
             NV_CUDA(launch_stage0_rows_gen(ctx->ps->d_plan, P.total_rows, meta, ctx->cur_gen, ctx->d_sum, ctx->d_sq, tilt, ctx->d_vnf,
                                            ctx->d_bits_ok, ctx->d_counters, depth, st));
         } else if (ctx->ps->use_tiles && ctx->ps->use_s0t && s0_tiles && P.total_windows > small_limit) {
             // large plan, FAST cascade: stage 0 densely on the bulk kernel's tiles, then the skip rule along the rows
             uint32_t *bits_fail = ctx->d_bits_ok + ctx->ps->bits_words, *bits_okv = ctx->d_bits_ok + 2 * (size_t)ctx->ps->bits_words;
+            const bool fork = two_streams && P.ctiles2 > 0 && P.ctiles1 > 0;      // the ystep-1 levels' launch goes to the side stream
+            if (fork) { NV_CUDA(cudaEventRecord(ctx->ev_fork[0], st)); NV_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork[0], 0)); }
             for (int c = 0; c < 2; c++) {
                 Stage0TileParams &s0 = ctx->ps->s0t[c];
                 int ntiles = c == 0 ? P.ctiles2 : P.ctiles1;
                 if (ntiles == 0) continue;
                 s0.maps = ctx->ps->d_maps + NV_MAX_LEVELS; s0.plan = ctx->ps->d_plan; s0.sq = ctx->d_sq; s0.vnf = ctx->d_vnf;
                 s0.bits_fail = bits_fail; s0.bits_okv = bits_okv;
-                NV_CUDA(launch_stage0_tiles(s0, c == 0 ? 2 : 1, ntiles, st));
+                NV_CUDA(launch_stage0_tiles(s0, c == 0 ? 2 : 1, ntiles, c == 1 && fork ? ctx->stream2 : st));
                 nl++;
             }
+            if (fork) { NV_CUDA(cudaEventRecord(ctx->ev_join[0], ctx->stream2)); NV_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[0], 0)); }
             NV_CUDA(launch_stage0_chain(P, bits_fail, bits_okv, ctx->d_bits_ok, ctx->d_counters, depth, st));
         } else if (ctx->ps->use_s0p) {
             Stage0Params &sp = ctx->ps->s0p;
@@ -760,17 +771,28 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
                 nl++;
             }
         } else if (ctx->ps->use_tiles) {
-            for (int c = 0; c < 2; c++) {
+            const bool fork = two_streams && P.ctiles2 > 0 && P.ctiles1 > 0;
+            if (fork) { NV_CUDA(cudaEventRecord(ctx->ev_fork[1], st)); NV_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork[1], 0)); }
+            // Launch order decides what the two kernels share.  The ystep-2 levels first (default): their 742 blocks fill every
+            // SM's shared memory and the wide blocks of the ystep-1 levels follow as they drain — 2970 frames/s with eight
+            // frames in flight, bulk stages 0.34 ms when a frame is alone.  NUBOVCA_FORK_ORDER=1, the ystep-1 levels first:
+            // their 368 wide blocks leave room for a block of the other kernel on every SM, so a lone frame's bulk stages
+            // take 0.27 ms, but eight frames in flight lose 4 % (2845 frames/s).
+            static const bool wide_first = [] { const char *e = getenv("NUBOVCA_FORK_ORDER"); return e && atoi(e) != 0; }();
+            for (int k = 0; k < 2; k++) {
+                const int c = wide_first ? 1 - k : k;
                 TileParams &tp = ctx->ps->tp[c];
+                const cudaStream_t cst = k == 1 && fork ? ctx->stream2 : st;
                 int ntiles = c == 0 ? P.ctiles2 : P.ctiles1;
                 if (ntiles == 0) continue;
                 tp.plan = ctx->ps->d_plan; tp.bits_alive = ctx->d_bits_ok; tp.vnf = ctx->d_vnf; tp.depth = depth;
                 tp.tail = ctx->d_queue; tp.cand = ctx->d_cand; tp.counters = ctx->d_counters; tp.maps = ctx->ps->d_maps;
                 tp.tail_cap = qcap; tp.cand_cap = ctx->cand_cap;
-                if (P.wide_w[c] > 0) NV_CUDA(launch_cascade_wide(tp, c == 0 ? 2 : 1, P.wide_w[c], P.wide_h[c], P.wtiles[c], st));
-                else NV_CUDA(launch_cascade_classes(tp, c == 0 ? 2 : 1, ntiles, st));
+                if (P.wide_w[c] > 0) NV_CUDA(launch_cascade_wide(tp, c == 0 ? 2 : 1, P.wide_w[c], P.wide_h[c], P.wtiles[c], cst));
+                else NV_CUDA(launch_cascade_classes(tp, c == 0 ? 2 : 1, ntiles, cst));
                 nl++;
             }
+            if (fork) { NV_CUDA(cudaEventRecord(ctx->ev_join[1], ctx->stream2)); NV_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[1], 0)); }
             prof_mark(ctx, 6);
             if (ctx->ps->bulk_end < casc->meta.nstages && ctx->cur_tail) {
                 // the survivors of the bulk stages (~15 000 per config-3 frame, most of them gone within a few stages): a warp

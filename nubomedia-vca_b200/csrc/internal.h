@@ -304,6 +304,10 @@ struct nv_ctx {
     int debug = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_done = nullptr;
+    // side stream of the two-class stages: the ystep-2 and the ystep-1 levels of a frame are independent launches (stage 0 on
+    // tiles, bulk stages), neither fills the GPU alone; forked and joined with events, also inside a captured graph
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork[2] = {}, ev_join[2] = {};
 
     // pinned staging + device frame
     uint8_t *h_frame = nullptr;  size_t frame_cap = 0;     // pinned
