@@ -416,15 +416,20 @@ static inline int cv_round(double v) { return (int)lrint(v); }
 static inline int cv_roundf(float v) { return (int)lrintf(v); }
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-static void exact_coefs(int ssize, int dsize, int2 *tab)
+// INTER_LINEAR_EXACT coefficients (8 fractional bits), branch-free for the kernel: entry = (i, f) means
+// 256 * value = src[i] * (256 - f) + src[i + 1] * f with i + 1 < ssize ALWAYS — the clamped ends, where OpenCV takes a
+// single source sample, are written as (0, 0) and (ssize - 2, 256).  `lead` dummy entries (0, 0) come first (the row
+// kernel indexes the x table by integral column c = x + 1), `total` entries are written in all.
+static void exact_coefs(int ssize, int dsize, int2 *tab, int lead, int total)
 {
     double scale = 1.0 / ((double)dsize / ssize);
+    for (int k = 0; k < total; k++) tab[k] = make_int2(0, 0);
     for (int d = 0; d < dsize; d++) {
         double f = scale * (d + 0.5) - 0.5;
         int i = (int)floor(f);
-        if (i >= 0 && i < ssize - 1) tab[d] = make_int2(i, cv_round((f - i) * 256.0));
-        else if (i < 0) tab[d] = make_int2(0, -1);
-        else tab[d] = make_int2(ssize - 1, -1);
+        if (i >= 0 && i < ssize - 1) tab[lead + d] = make_int2(i, cv_round((f - i) * 256.0));
+        else if (i < 0) tab[lead + d] = make_int2(0, 0);
+        else tab[lead + d] = ssize >= 2 ? make_int2(ssize - 2, 256) : make_int2(0, 0);
     }
 }
 
@@ -495,7 +500,8 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
         L.iofs = (int)iofs; iofs += (long long)L.ipitch * (lh + 1);
         L.wofs = (int)wofs; wofs += (long long)L.nx * L.ny;
         L.bofs = (int)bofs; bofs += (long long)L.nxw * L.ny;
-        L.xtab = (int)tofs; L.ytab = (int)tofs + lw; tofs += lw + lh;
+        // x table: indexed by integral column (one leading dummy), padded to whole groups of four entries; both tables 16-byte aligned
+        L.xtab = (int)tofs; L.ytab = (int)tofs + align_up(lw + 1, 4); tofs += align_up(lw + 1, 4) + align_up(lh, 2);
         L.pofs = (int)pofs; pofs += (long long)lw * lh;
         L.rowblk0 = P.total_rowblk; P.total_rowblk += (lh + 7) / 8;
         L.colblk0 = P.total_colblk; P.total_colblk += (L.ipitch + NV_COLBLK - 1) / NV_COLBLK;
@@ -521,8 +527,8 @@ static int ensure_plan(nv_ctx *ctx, const nv_cascade *casc, int W, int H, const 
     if (nl > 0) {
         std::vector<int2> tab((size_t)tofs);
         for (int l = 0; l < nl; l++) {
-            exact_coefs(W, P.lv[l].lw, &tab[P.lv[l].xtab]);
-            exact_coefs(H, P.lv[l].lh, &tab[P.lv[l].ytab]);
+            exact_coefs(W, P.lv[l].lw, &tab[P.lv[l].xtab], 1, align_up(P.lv[l].lw + 1, 4));
+            exact_coefs(H, P.lv[l].lh, &tab[P.lv[l].ytab], 0, align_up(P.lv[l].lh, 2));
         }
         int rc;
         if ((rc = ensure(&ctx->ps->d_ptab, &ctx->ps->ptab_cap, (size_t)tofs * 2)) != NV_OK) return rc;

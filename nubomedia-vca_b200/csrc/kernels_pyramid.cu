@@ -17,12 +17,13 @@ __device__ __forceinline__ int find_level(const PlanDev *__restrict__ plan, int 
     return l;
 }
 
-// (A variant with eight integral columns per lane, in-lane running sums, one shuffle scan per 256 columns and 16-byte
-// stores needs a third of the instructions but 48 registers and fewer, longer warps: 57 us against 46 us alone, and
-// 2540 against 2600 frames/s in bench.py, where this kernel has to fit beside the resident blocks of another stream's
-// cascade kernel — profiles/r1_v5_summary.md.  Kept: this one.)
-// One warp per level row: resize (two source rows, 8.8 x 8.8 fixed point) -> equalised value -> warp-shuffle
-// inclusive scan of v and v*v along the row, carried across 32-pixel chunks.
+// One warp per level row, FOUR integral columns per lane and iteration (columns c0 + 4 * lane + k, i.e. pixels
+// x = c - 1; column 0 is the zero column, pixel -1 counts 0): resize (two source rows, two source columns, 8.8 x 8.8
+// fixed point, coefficient tables without special cases — see exact_coefs) -> equalised value -> running sums of v and
+// v * v inside the lane, ONE warp-shuffle scan of the lane totals per 128 columns, a 16-byte store per array (two
+// 8-byte stores on the de-interleaved ystep-2 layout: columns c, c + 2 are neighbours in the even plane, c + 1, c + 3
+// in the odd one).  Round 1's kernel did one pixel per lane: 3.4 x the instructions, and a 1920-pixel row was a chain
+// of 60 dependent load -> scan -> carry rounds where this one has 15.
 __global__ void __launch_bounds__(256)
 k_pyr_rowscan(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ gray, int gstride,
               const uint8_t *__restrict__ lut, const int2 *__restrict__ ptab, uint32_t *__restrict__ sum,
@@ -35,47 +36,68 @@ k_pyr_rowscan(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ gray
 
     int l = find_level(plan, blockIdx.x, &LevelDesc::rowblk0);
     const LevelDesc &L = plan->lv[l];
-    int lw = L.lw, lh = L.lh, ys = L.ystep, pitch = L.ipitch, plane = L.iplane;
+    const int lw = L.lw, lh = L.lh, ys = L.ystep, pitch = L.ipitch, plane = L.iplane;
     int y = (blockIdx.x - L.rowblk0) * 8 + warp;
     if (y >= lh) return;
     uint32_t *srow = sum + L.iofs, *qrow = sq + L.iofs;
-    if (y == 0)                                         // first integral row is all zeros
-        for (int c = lane; c < pitch; c += 32) { srow[c] = 0; qrow[c] = 0; }
+    if (y == 0)                                         // first integral row is all zeros (pitch is a multiple of 4)
+        for (int c = lane * 4; c < pitch; c += 128) {
+            *reinterpret_cast<uint4 *>(srow + c) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(qrow + c) = make_uint4(0, 0, 0, 0);
+        }
     srow += (size_t)(y + 1) * pitch;
     qrow += (size_t)(y + 1) * pitch;
-    if (lane == 0) { srow[0] = 0; qrow[0] = 0; }        // first integral column (c = 0 -> plane 0, col 0)
 
-    const int2 *xt = ptab + L.xtab, *yt = ptab + L.ytab;
-    int2 ty = yt[y];
-    const uint8_t *g0 = gray + (size_t)ty.x * gstride, *g1 = ty.y < 0 ? g0 : g0 + gstride;
-    uint32_t r1 = ty.y < 0 ? 0u : (uint32_t)ty.y, r0 = 256u - r1;
+    const int4 *xt = reinterpret_cast<const int4 *>(ptab + L.xtab);     // two (index, fraction) entries per int4
+    int2 ty = (ptab + L.ytab)[y];
+    const uint8_t *g0 = gray + (size_t)ty.x * gstride, *g1 = g0 + gstride;
+    const uint32_t r1 = (uint32_t)ty.y, r0 = 256u - r1;
     uint32_t carry_s = 0, carry_q = 0;
-    for (int x0 = 0; x0 < lw; x0 += 32) {
-        int x = x0 + lane;
-        uint32_t v = 0;
-        if (x < lw) {
-            int2 tx = xt[x];
-            uint32_t h0, h1;
-            if (tx.y < 0) { h0 = (uint32_t)s_lut[g0[tx.x]] << 8; h1 = (uint32_t)s_lut[g1[tx.x]] << 8; }
-            else {
-                uint32_t c1 = (uint32_t)tx.y, c0 = 256u - c1;
-                h0 = s_lut[g0[tx.x]] * c0 + s_lut[g0[tx.x + 1]] * c1;
-                h1 = s_lut[g1[tx.x]] * c0 + s_lut[g1[tx.x + 1]] * c1;
+    for (int c0 = 0; c0 <= lw; c0 += 128) {
+        const int c = c0 + lane * 4;
+        uint32_t v[4] = {0, 0, 0, 0};
+        if (c <= lw) {
+            int4 ta = xt[c >> 1], tb = xt[(c >> 1) + 1];
+            const int ix[4] = {ta.x, ta.z, tb.x, tb.z};
+            const uint32_t fx[4] = {(uint32_t)ta.y, (uint32_t)ta.w, (uint32_t)tb.y, (uint32_t)tb.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t c1 = fx[k], cz = 256u - c1;
+                uint32_t h0 = s_lut[g0[ix[k]]] * cz + s_lut[g0[ix[k] + 1]] * c1;
+                uint32_t h1 = s_lut[g1[ix[k]]] * cz + s_lut[g1[ix[k] + 1]] * c1;
+                uint32_t val = (h0 * r0 + h1 * r1 + 32768u) >> 16;
+                int x = c + k - 1;
+                v[k] = (unsigned)x < (unsigned)lw ? val : 0u;           // pixel -1 (column 0) and the padding columns count 0
             }
-            v = (h0 * r0 + h1 * r1 + 32768u) >> 16;
-            if (pyr_debug) pyr_debug[L.pofs + (size_t)y * lw + x] = (uint8_t)v;
+            if (pyr_debug) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    int x = c + k - 1;
+                    if ((unsigned)x < (unsigned)lw) pyr_debug[L.pofs + (size_t)y * lw + x] = (uint8_t)v[k];
+                }
+            }
         }
-        uint32_t s = v, q = v * v;
+        uint32_t s0 = v[0], s1 = s0 + v[1], s2 = s1 + v[2], s3 = s2 + v[3];
+        uint32_t q0 = v[0] * v[0], q1 = v[1] * v[1] + q0, q2 = v[2] * v[2] + q1, q3 = v[3] * v[3] + q2;
+        uint32_t s = s3, q = q3;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t ts = __shfl_up_sync(0xffffffffu, s, d), tq = __shfl_up_sync(0xffffffffu, q, d);
             if (lane >= d) { s += ts; q += tq; }
         }
-        s += carry_s; q += carry_q;
-        if (x < lw) {
-            int c = x + 1;
-            int pc = ys == 2 ? (c & 1) * plane + (c >> 1) : c;
-            srow[pc] = s; qrow[pc] = q;
+        s += carry_s; q += carry_q;                     // inclusive through this lane's four columns
+        const uint32_t bs = s - s3, bq = q - q3;
+        if (c <= lw) {                                  // the lane's four columns exist together (pitch / plane are multiples of 4)
+            if (ys == 2) {
+                const int pc = c >> 1;
+                *reinterpret_cast<uint2 *>(srow + pc) = make_uint2(bs + s0, bs + s2);
+                *reinterpret_cast<uint2 *>(srow + plane + pc) = make_uint2(bs + s1, s);
+                *reinterpret_cast<uint2 *>(qrow + pc) = make_uint2(bq + q0, bq + q2);
+                *reinterpret_cast<uint2 *>(qrow + plane + pc) = make_uint2(bq + q1, q);
+            } else {
+                *reinterpret_cast<uint4 *>(srow + c) = make_uint4(bs + s0, bs + s1, bs + s2, s);
+                *reinterpret_cast<uint4 *>(qrow + c) = make_uint4(bq + q0, bq + q1, bq + q2, q);
+            }
         }
         carry_s = __shfl_sync(0xffffffffu, s, 31);
         carry_q = __shfl_sync(0xffffffffu, q, 31);
