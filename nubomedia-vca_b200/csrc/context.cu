@@ -727,6 +727,12 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         prof_mark(ctx, 4);
         static const int small_limit = [] { const char *e = getenv("NUBOVCA_SMALL_PLAN"); return e ? atoi(e) : NV_SMALL_PLAN_WINDOWS; }();
         static const bool s0_tiles = [] { const char *e = getenv("NUBOVCA_S0_TILES"); return !e || atoi(e) != 0; }();
+        // k_cascade_tail_tab (classifier table in shared memory): 1 large plans, 2 small plans up to the block-per-window split,
+        // 4 small plans through all stages (no k_cascade_tail_block launch).  Measured (profiles/r2_summary.md section 8):
+        // small plans gain (a 96x64 ROI detect 100.6 -> 88.5 us per call, eyes-in-faces 374 -> 359 us), config 3 does not
+        // (tail 45 -> 49 / 45 / 41 us with 8 / 16 / 32 warps per block, bench.py -1 .. -4 %: fewer resident warps for its
+        // 15 000 shallow windows, and 84 KB blocks queue behind the bulk kernels of the other streams) — default 4.
+        static const int tail_tab = [] { const char *e = getenv("NUBOVCA_TAIL_TAB"); return e ? atoi(e) : 4; }();
         static const bool two_streams = [] { const char *e = getenv("NUBOVCA_TWO_STREAMS"); return !e || atoi(e) != 0; }();
         if (ctx->use_gen) {
             NV_CUDA(launch_stage0_rows_gen(ctx->ps->d_plan, P.total_rows, meta, ctx->cur_gen, ctx->d_sum, ctx->d_sq, tilt, ctx->d_vnf,
@@ -767,6 +773,11 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
             // stages narrower than NV_TAIL_BLOCK_MIN_STUMPS with a warp per window, the deep ones with a block per window
             int split = 1;
             while (split < casc->meta.nstages && casc->meta.stage_first[split + 1] - casc->meta.stage_first[split] < NV_TAIL_BLOCK_MIN_STUMPS) split++;
+            if ((tail_tab & 4) && tail_tab_smem(casc->meta, 1, casc->meta.nstages) <= NV_TAILTAB_MAX_SMEM) split = casc->meta.nstages;
+            if ((tail_tab & 6) && tail_tab_smem(casc->meta, 1, split) <= NV_TAILTAB_MAX_SMEM)
+                NV_CUDA(launch_cascade_tail_tab(ctx->ps->d_plan, meta, casc->meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
+                                                ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, 1, split, ctx->d_deepq, NV_DEEPQ_CAP, st));
+            else
             NV_CUDA(launch_cascade_tail_fast(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
                                              ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, 1, split, ctx->d_deepq, NV_DEEPQ_CAP, st,
                                              8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));
@@ -805,6 +816,11 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
                 // per window.  (Handing the deep ones to the block-per-window kernel after NV_TAIL_WARP_STAGES stages was
                 // measured: 55 us against 45 us isolated, 2538 against 2577 frames/s — with that many windows the warp kernel
                 // is bound by throughput, not by its deepest window; the split pays on small plans only.)
+                if ((tail_tab & 1) && tail_tab_smem(casc->meta, ctx->ps->bulk_end, casc->meta.nstages) <= NV_TAILTAB_MAX_SMEM)
+                    NV_CUDA(launch_cascade_tail_tab(ctx->ps->d_plan, meta, casc->meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
+                                                    ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, ctx->ps->bulk_end, casc->meta.nstages,
+                                                    nullptr, qcap, st));
+                else
                 NV_CUDA(launch_cascade_tail_fast(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
                                                  ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, ctx->ps->bulk_end, casc->meta.nstages,
                                                  nullptr, qcap, st, 8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));

@@ -16,6 +16,7 @@
 #define NV_GROUP_UF_MIN 2048        // raw candidates: above this, groupRectangles builds its components by neighbour search + union-find
 #define NV_SMALL_PLAN_WINDOWS 16384
 #define NV_DEEPQ_CAP NV_SMALL_PLAN_WINDOWS   // a small plan has no more windows than that
+#define NV_TAILTAB_MAX_SMEM (200 * 1024)      // k_cascade_tail_tab: classifier table + window patches per block
 #define NV_TAIL_BLOCK_MIN_STUMPS 64            // stages at least this wide go to the block-per-window kernel
 #define NV_TAIL_WARP_STAGES 4                  // large plans: tail stages run with a warp per window before the block-per-window kernel takes over
 #define NV_COLBLK 128            // physical integral columns per block of the column scan
@@ -449,6 +450,11 @@ cudaError_t launch_cascade_tail_fast(const PlanDev *plan, const DevCascade *meta
                                      const uint32_t *sum, const uint2 *tail, int *counters, uint32_t *cand, int cand_cap,
                                      int16_t *depth, int stage_begin, int stage_end, uint2 *deep, int deep_cap, cudaStream_t st,
                                      int smem_bytes);
+size_t tail_tab_smem(const DevCascade &m, int stage_begin, int stage_end);
+cudaError_t launch_cascade_tail_tab(const PlanDev *plan, const DevCascade *meta, const DevCascade &hmeta, const TailStump *tstumps,
+                                    const double *tbase, const uint32_t *sum, const uint2 *tail, int *counters, uint32_t *cand,
+                                    int cand_cap, int16_t *depth, int stage_begin, int stage_end, uint2 *deep, int deep_cap,
+                                    cudaStream_t st);
 cudaError_t launch_cascade_tail_block(const PlanDev *plan, const DevCascade *meta, const TailStump *tstumps, const double *tbase,
                                       const uint32_t *sum, const uint2 *queue, int *counters, int cin, uint32_t *cand, int cand_cap,
                                       int16_t *depth, int stage_begin, int skip_counter, cudaStream_t st);

@@ -1440,6 +1440,113 @@ k_cascade_tail_fast(const PlanDev *__restrict__ plan, const DevCascade *__restri
     }
 }
 
+// k_cascade_tail_tab: k_cascade_tail_fast with the weak classifiers of its stage range IN SHARED MEMORY.  The clock64
+// timeline of a full-depth window (profiles/r1_v5_summary.md) put a third of every round of 32 classifiers into waiting
+// for the lanes' 48-byte records from L2 — a round is shorter than the L2 round trip, so a one-round prefetch cannot
+// hide it — and that chain (61 rounds for stages 10..21 of frontalface_alt) is what the launch takes whatever the frame
+// holds.  Here a block copies the records of stages [stage_begin, nstages) once (40 bytes each as three arrays: lane k
+// reads element k, no bank conflicts; 70 KB for stages 10..21, 85 KB from stage 1), a lane takes TWO classifiers per round
+// (half the rounds, the two evaluations overlap), and the stage bounds / thresholds / base sums sit in shared memory
+// too.  Fewer, fatter blocks: as many per SM as the table allows, persistent over the window queue.  Same certificates,
+// same arithmetic, same results as k_cascade_tail_fast; used when the table fits (launch_cascade_tail_tab).
+template <int NWARP>
+__global__ void __launch_bounds__(32 * NWARP)
+k_cascade_tail_tab(const PlanDev *__restrict__ plan, const DevCascade *__restrict__ meta, const TailStump *__restrict__ ts,
+                   const double *__restrict__ tbase, const uint32_t *__restrict__ sum, const uint2 *__restrict__ tail,
+                   int *__restrict__ counters, uint32_t *__restrict__ cand, int cand_cap, int16_t *__restrict__ depth,
+                   int stage_begin, int stage_end, uint2 *__restrict__ deep, int deep_cap)
+{
+    extern __shared__ __align__(16) uint32_t s_tab[];            // A[nt] uint4 | B[nt] uint4 | C[nt] double | NWARP patches
+    __shared__ int s_first[NV_MAX_STAGES + 1];
+    __shared__ float s_thr[NV_MAX_STAGES];
+    __shared__ double s_base[NV_MAX_STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = counters[3], nstages = stage_end;
+    if (n == 0) return;
+    const bool last = stage_end == meta->nstages;
+    if (!deep) { deep = const_cast<uint2 *>(tail) + n; deep_cap -= n; }
+    const int kt0 = meta->stage_first[stage_begin], nt = meta->stage_first[stage_end] - kt0;
+    uint4 *sA = reinterpret_cast<uint4 *>(s_tab), *sB = sA + nt;
+    double *sC = reinterpret_cast<double *>(sB + nt);
+    const int ww = plan->win_w, wh = plan->win_h, LP = ww + 1, npatch = (wh + 1) * LP;
+    uint32_t *win = reinterpret_cast<uint32_t *>(sC + nt) + warp * npatch;
+    for (int i = tid; i < nt; i += 32 * NWARP) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(ts + kt0 + i);
+        sA[i] = __ldg(p); sB[i] = __ldg(p + 1);
+        const uint4 c = __ldg(p + 2);
+        sC[i] = __hiloint2double((int)c.y, (int)c.x);
+    }
+    for (int i = tid; i <= meta->nstages; i += 32 * NWARP) s_first[i] = meta->stage_first[i] - kt0;
+    for (int i = tid; i < meta->nstages; i += 32 * NWARP) { s_thr[i] = meta->stage_thr[i]; s_base[i] = tbase[i]; }
+    __syncthreads();
+    const uint32_t wsa = smem_u32(win);
+    for (;;) {                                                   // windows are handed out one at a time: depths are very uneven
+        int e = 0;
+        if (lane == 0) e = atomicAdd(&counters[5], 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= n) break;
+        const uint2 q = tail[e];
+        const int l = q.x >> 26, iy = (q.x >> 13) & 8191, ix = q.x & 8191;
+        const float vnf = __uint_as_float(q.y);
+        const LevelDesc &L = plan->lv[l];
+        const int pitch = L.ipitch;
+        const uint32_t *wb = sum + L.iofs + (size_t)iy * L.ystep * pitch + ix;
+        __syncwarp();                                            // the previous window's reads of the patch are done
+        for (int c = lane; c <= ww; c += 32) {                   // private copy of the window's integral patch, four rows in flight
+            const uint32_t *src = wb + (L.ystep == 2 ? (c & 1) * L.iplane + (c >> 1) : c);
+            int r = 0;
+            for (; r + 4 <= wh + 1; r += 4) {
+                const uint32_t v0 = __ldg(src + (size_t)r * pitch), v1 = __ldg(src + (size_t)(r + 1) * pitch);
+                const uint32_t v2 = __ldg(src + (size_t)(r + 2) * pitch), v3 = __ldg(src + (size_t)(r + 3) * pitch);
+                win[r * LP + c] = v0; win[(r + 1) * LP + c] = v1; win[(r + 2) * LP + c] = v2; win[(r + 3) * LP + c] = v3;
+            }
+            for (; r <= wh; r++) win[r * LP + c] = __ldg(src + (size_t)r * pitch);
+        }
+        __syncwarp();
+        int code = NV_DEPTH_PASS;
+        for (int st = stage_begin; st < nstages; st++) {
+            const int k0 = s_first[st], k1 = s_first[st + 1];
+            double tmp0 = 0., tmp1 = 0.;
+            for (int kb = k0 + lane; kb < k1; kb += 64) {        // 64 weak classifiers per round, two per lane
+#define TW(o) lds_u32(wsa + (o))
+#define TAIL_EVAL(K, ACC)                                                                                              \
+                {                                                                                                      \
+                    const uint4 a = sA[K], b = sB[K];                                                                  \
+                    const int nr0 = (int)(TW(a.x >> 16) + TW(a.y & 0xffffu) - TW(a.x & 0xffffu) - TW(a.y >> 16));      \
+                    const int r1 = (int)(TW(a.z & 0xffffu) - TW(a.z >> 16) - TW(a.w & 0xffffu) + TW(a.w >> 16));      \
+                    const int w12 = (int)b.w;                                                                          \
+                    int r = (int)(short)(w12 & 0xffff) * r1 + nr0;                                                     \
+                    if (w12 >> 16) {                                                                                   \
+                        const int r2 = (int)(TW(b.x & 0xffffu) - TW(b.x >> 16) - TW(b.y & 0xffffu) + TW(b.y >> 16));  \
+                        r += (w12 >> 16) * r2;                                                                         \
+                    }                                                                                                  \
+                    add_if_lt(ACC, __fmul_rn(__int2float_rn(r), vnf), __uint_as_float(b.z), sC[K]);                    \
+                }
+                TAIL_EVAL(kb, tmp0)
+                if (kb + 32 < k1) TAIL_EVAL(kb + 32, tmp1)
+#undef TAIL_EVAL
+#undef TW
+            }
+            double tmp = __dadd_rn(tmp0, tmp1);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) tmp = __dadd_rn(tmp, __shfl_xor_sync(0xffffffffu, tmp, d));
+            if (__dadd_rn(s_base[st], tmp) < (double)s_thr[st]) { code = -st; break; }
+        }
+        if (lane == 0) {
+            if (depth && (last || code != NV_DEPTH_PASS)) depth[L.wofs + iy * L.nx + ix] = (int16_t)code;
+            if (code == NV_DEPTH_PASS && last) {
+                const int pos = atomicAdd(&counters[1], 1);
+                if (pos < cand_cap) cand[pos] = q.x;
+                else counters[2] = 1;
+            } else if (code == NV_DEPTH_PASS) {
+                const int pos = atomicAdd(&counters[6], 1);
+                if (pos < deep_cap) deep[pos] = q;
+                else counters[2] = 1;
+            }
+        }
+    }
+}
+
 // The deep stages (80 .. 213 weak classifiers each in frontalface_alt) with a whole BLOCK per window: one classifier per
 // thread, so a stage is one round (two for the last ones) instead of three to seven, and the stage sum is combined through
 // shared memory with one barrier per stage.  A window that passes all 22 stages costs ~12 short rounds here against ~55 in
@@ -1870,6 +1977,37 @@ cudaError_t launch_cascade_tail_fast(const PlanDev *plan, const DevCascade *meta
 #endif
     // smem_bytes is sized for eight warps (one patch per warp)
     k_cascade_tail_fast<<<148 * 8 * (256 / NV_TAIL_THREADS), NV_TAIL_THREADS, smem_bytes / (256 / NV_TAIL_THREADS), st>>>(
+        plan, meta, tstumps, tbase, sum, tail, counters, cand, cand_cap, depth, stage_begin, stage_end, deep, deep_cap);
+    return cudaGetLastError();
+}
+
+// Shared-memory bytes of k_cascade_tail_tab for the stage range [stage_begin, nstages) of a cascade, and the launch.
+// Returns cudaErrorInvalidConfiguration when the table does not fit: the caller falls back to k_cascade_tail_fast.
+#ifndef NV_TAILTAB_WARPS
+#define NV_TAILTAB_WARPS 8
+#endif
+size_t tail_tab_smem(const DevCascade &m, int stage_begin, int stage_end)
+{
+    const size_t nt = (size_t)(m.stage_first[stage_end] - m.stage_first[stage_begin]);
+    return nt * 40 + (size_t)NV_TAILTAB_WARPS * (m.win_w + 1) * (m.win_h + 1) * 4;
+}
+
+cudaError_t launch_cascade_tail_tab(const PlanDev *plan, const DevCascade *meta, const DevCascade &hmeta, const TailStump *tstumps,
+                                    const double *tbase, const uint32_t *sum, const uint2 *tail, int *counters, uint32_t *cand,
+                                    int cand_cap, int16_t *depth, int stage_begin, int stage_end, uint2 *deep, int deep_cap,
+                                    cudaStream_t st)
+{
+    const size_t smem = tail_tab_smem(hmeta, stage_begin, stage_end);
+    if (smem > NV_TAILTAB_MAX_SMEM) return cudaErrorInvalidConfiguration;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_cascade_tail_tab<NV_TAILTAB_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NV_TAILTAB_MAX_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = NV_TAILTAB_MAX_SMEM;
+    }
+    int per_sm = (int)((227 * 1024) / (smem + 2048));            // static tables + the per-block reserve
+    per_sm = per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm;
+    k_cascade_tail_tab<NV_TAILTAB_WARPS><<<148 * per_sm, 32 * NV_TAILTAB_WARPS, smem, st>>>(
         plan, meta, tstumps, tbase, sum, tail, counters, cand, cand_cap, depth, stage_begin, stage_end, deep, deep_cap);
     return cudaGetLastError();
 }
