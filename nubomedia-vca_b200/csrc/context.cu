@@ -284,8 +284,8 @@ extern "C" int nv_ctx_create(int gpu, int max_width, int max_height, nv_ctx **ou
         NV_CUDA(cudaMalloc(&c->d_frame, c->frame_cap));
         c->gray_cap = (size_t)max_width * max_height + 256;
         NV_CUDA(cudaMalloc(&c->d_gray, c->gray_cap));
-        NV_CUDA(cudaMalloc(&c->d_hist, 256 * sizeof(int)));
-        NV_CUDA(cudaMemset(c->d_hist, 0, 256 * sizeof(int)));
+        NV_CUDA(cudaMalloc(&c->d_hist, 260 * sizeof(int)));     // 256 bins + the prep kernels' last-block ticket
+        NV_CUDA(cudaMemset(c->d_hist, 0, 260 * sizeof(int)));
         NV_CUDA(cudaMalloc(&c->d_lut, 512));
         uint8_t ident[256];
         for (int i = 0; i < 256; i++) ident[i] = (uint8_t)i;
@@ -734,6 +734,11 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         // 15 000 shallow windows, and 84 KB blocks queue behind the bulk kernels of the other streams) — default 4.
         static const int tail_tab = [] { const char *e = getenv("NUBOVCA_TAIL_TAB"); return e ? atoi(e) : 4; }();
         static const bool two_streams = [] { const char *e = getenv("NUBOVCA_TWO_STREAMS"); return !e || atoi(e) != 0; }();
+        // small plan of a cascade with the certificates: every window alive after stage 0 goes to the warp-per-window kernel;
+        // k_stage0_rows_p appends them to its queue itself
+        const bool small_fast = ctx->ps->use_tiles && ctx->cur_tail && P.total_windows <= small_limit && casc->meta.nstages > 1;
+        const int qcap = (int)std::min<size_t>(ctx->queue_cap, 0x7fffffff);
+        bool queued = false;
         if (ctx->use_gen) {
             NV_CUDA(launch_stage0_rows_gen(ctx->ps->d_plan, P.total_rows, meta, ctx->cur_gen, ctx->d_sum, ctx->d_sq, tilt, ctx->d_vnf,
                                            ctx->d_bits_ok, ctx->d_counters, depth, st));
@@ -757,18 +762,22 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
             Stage0Params &sp = ctx->ps->s0p;
             sp.sum = ctx->d_sum; sp.sq = ctx->d_sq; sp.vnf = ctx->d_vnf; sp.bits_alive = ctx->d_bits_ok;
             sp.counters = ctx->d_counters; sp.depth = depth;
+            sp.queue = small_fast ? ctx->d_queue : nullptr; sp.queue_cap = qcap; sp.queue_cidx = 3;
+            queued = small_fast;
             NV_CUDA(launch_stage0_rows_p(sp, st));
         } else
             NV_CUDA(launch_stage0_rows(ctx->ps->d_plan, P.total_rows, meta, stumps, ctx->d_sum, ctx->d_sq, ctx->d_vnf,
                                        ctx->d_bits_ok, ctx->d_counters, depth, st));
         prof_mark(ctx, 5);
         nl += 3;
-        int qcap = (int)std::min<size_t>(ctx->queue_cap, 0x7fffffff);
-        if (ctx->ps->use_tiles && ctx->cur_tail && P.total_windows <= small_limit && casc->meta.nstages > 1) {
+        if (small_fast) {
             // small plan: every window alive after stage 0 goes straight to the warp-per-window kernel (same exactness
             // certificates as the tail it normally is, nv_cascade::tail_fast)
-            NV_CUDA(launch_alive_to_queue(ctx->ps->d_plan, P.total_rows, ctx->d_vnf, ctx->d_bits_ok, ctx->d_queue, ctx->d_counters,
-                                          qcap, st, 3));
+            if (!queued) {
+                NV_CUDA(launch_alive_to_queue(ctx->ps->d_plan, P.total_rows, ctx->d_vnf, ctx->d_bits_ok, ctx->d_queue, ctx->d_counters,
+                                              qcap, st, 3));
+                nl++;
+            }
             prof_mark(ctx, 6);
             // stages narrower than NV_TAIL_BLOCK_MIN_STUMPS with a warp per window, the deep ones with a block per window
             int split = 1;
@@ -781,7 +790,7 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
             NV_CUDA(launch_cascade_tail_fast(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_queue,
                                              ctx->d_counters, ctx->d_cand, ctx->cand_cap, depth, 1, split, ctx->d_deepq, NV_DEEPQ_CAP, st,
                                              8 * (casc->meta.win_w + 1) * (casc->meta.win_h + 1) * 4));
-            nl += 2;
+            nl += 1;
             if (split < casc->meta.nstages) {
                 NV_CUDA(launch_cascade_tail_block(ctx->ps->d_plan, meta, ctx->cur_tail, ctx->cur_tail_base, ctx->d_sum, ctx->d_deepq,
                                                   ctx->d_counters, 6, ctx->d_cand, ctx->cand_cap, depth, split, -1, st));
@@ -851,8 +860,11 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         }
     }
     prof_mark(ctx, 7);
+    // small plans: sort + similarity matrix + grouping in one launch of one block (k_group_fused)
+    static const bool group_fused = [] { const char *e = getenv("NUBOVCA_GROUP_FUSED"); return !e || atoi(e) != 0; }();
+    static const int small_limit_g = [] { const char *e = getenv("NUBOVCA_SMALL_PLAN"); return e ? atoi(e) : NV_SMALL_PLAN_WINDOWS; }();
     NV_CUDA(launch_group(ctx->ps->d_plan, ctx->d_counters, ctx->d_cand, ctx->cand_cap, ctx->d_cand_sorted, ctx->d_cand_rects,
-                         ctx->d_adj, ctx->d_grp, p->min_neighbors, 0.2, W, H, ctx->d_result, ctx->result_cap, 148 * 2, st, &nl));
+                         ctx->d_adj, ctx->d_grp, p->min_neighbors, 0.2, W, H, ctx->d_result, ctx->result_cap, 148 * 2, st, &nl, group_fused && P.total_windows <= small_limit_g));
     prof_mark(ctx, 8);
     NV_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(ResultHeader) + NV_RESULT_INLINE * sizeof(nv_rect),
                             cudaMemcpyDeviceToHost, st));
@@ -998,12 +1010,12 @@ extern "C" int nv_detect_multiscale(nv_ctx *ctx, const nv_cascade *c, const uint
 // ------------------------------------------------------------------------------------------------
 // face element hot block
 // ------------------------------------------------------------------------------------------------
-int nv_get_rtab(nv_ctx *ctx, int sw, int sh, int dw, int dh, const int **d_tab)
+int nv_get_rtab(nv_ctx *ctx, int sw, int sh, int dw, int dh, const int **d_tab, const nv_ctx::RtabEntry **entry)
 {
     ResizeKey k;
     k.sw = sw; k.sh = sh; k.dw = dw; k.dh = dh;
     for (auto &e : ctx->rtabs)
-        if (e.d && e.k == k) { *d_tab = e.d; return NV_OK; }
+        if (e.d && e.k == k) { *d_tab = e.d; if (entry) *entry = &e; return NV_OK; }
     std::vector<int> tab;
     build_resize_tables(sw, sh, dw, dh, tab);
     nv_ctx::RtabEntry &e = ctx->rtabs[ctx->rtab_next];
@@ -1017,7 +1029,34 @@ int nv_get_rtab(nv_ctx *ctx, int sw, int sh, int dw, int dh, const int **d_tab)
     NV_CUDA(cudaMemcpyAsync(e.d, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     NV_CUDA(cudaStreamSynchronize(ctx->stream));           // tab is a local
     e.k = k;
+    e.row_a = e.row_period = 0;
+    if (tab[0] == RT_LINEAR && dh >= 2) {                  // which source rows does the vertical pass read?
+        const int *y0 = &tab[1 + 2 * (size_t)dw], *y1 = y0 + dh;
+        const int per = y0[1] - y0[0];
+        bool regular = per >= 3;
+        for (int dy = 0; dy < dh && regular; dy++) regular = y0[dy] == y0[0] + per * dy && y1[dy] == y0[dy] + 1;
+        if (regular) { e.row_a = y0[0]; e.row_period = per; }
+    }
     *d_tab = e.d;
+    if (entry) *entry = &e;
+    return NV_OK;
+}
+
+// Host frame -> ctx->d_frame, only the row pairs an integer down-scale reads (RtabEntry::row_period): `n` pairs of rows
+// a + k * period, a + k * period + 1, at their own offsets, as one strided copy — half the bytes of a 640x480 frame that
+// is processed at 160x120.  Page-locked caller memory is read in place, anything else goes through the staging buffer.
+static int nv_h2d_row_pairs(nv_ctx *ctx, const uint8_t *src, int stride, int height, int a, int period, int n)
+{
+    cudaPointerAttributes at;
+    bool known = cudaPointerGetAttributes(&at, src) == cudaSuccess;
+    if (known && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) return nv_h2d(ctx, src, (size_t)stride * height);
+    const bool pinned = known && at.type == cudaMemoryTypeHost;
+    const size_t off = (size_t)a * stride, pitch = (size_t)period * stride, run = 2 * (size_t)stride;
+    if (!pinned) {
+        cudaGetLastError();
+        for (int k = 0; k < n; k++) memcpy(ctx->h_frame + off + k * pitch, src + off + k * pitch, run);
+    }
+    NV_CUDA(cudaMemcpy2DAsync(ctx->d_frame + off, pitch, (pinned ? src : ctx->h_frame) + off, pitch, run, n, cudaMemcpyHostToDevice, ctx->stream));
     return NV_OK;
 }
 
@@ -1118,7 +1157,9 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const FaceSrc &src
     if (iscale > 0 && cv_round(height / scale) > 0) rows = cv_round(height / scale); else scale = 1;
     if (scale > 0 && cv_round(width / scale) > 0) cols = cv_round(width / scale); else scale = 1;
     const int *d_rtab;
-    if ((rc = nv_get_rtab(ctx, width, height, cols, rows, &d_rtab)) != NV_OK) return rc;
+    const nv_ctx::RtabEntry *rt = nullptr;
+    if ((rc = nv_get_rtab(ctx, width, height, cols, rows, &d_rtab, &rt)) != NV_OK) return rc;
+    const int row_a = rt->row_a, row_period = rt->row_period;         // (the entry may be evicted by a later call)
     nv_cascade *casc = const_cast<nv_cascade *>(c);
     nv_detect_params dp;
     dp.scale_factor = p->scale_factor; dp.min_neighbors = p->min_neighbors; dp.flags = 0;
@@ -1132,17 +1173,19 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const FaceSrc &src
     if (!on_device) {
         // page-locked caller memory is copied straight from the caller; anything else goes through the pinned staging buffer
         if (yuv) { if ((rc = yuv_h2d(ctx, src, height, &planes)) != NV_OK) return rc; }
+        else if (row_period > 0) { if ((rc = nv_h2d_row_pairs(ctx, bgr, stride, height, row_a, row_period, rows)) != NV_OK) return rc; }
         else if ((rc = nv_h2d(ctx, bgr, (size_t)stride * height)) != NV_OK) return rc;
         d_src = ctx->d_frame;
     }
     auto enqueue = [&](int *nl) -> int {
         ctx->prof_set[0] = ctx->prof_set[1] = false;
         prof_mark(ctx, 0);
-        if (yuv) NV_CUDA(launch_face_prep_yuv(src.fmt, planes, width, height, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream));
-        else NV_CUDA(launch_face_prep(d_src, width, height, stride, 3, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream));
+        // the prep kernel's last block turns the histogram into the equalizeHist LUT (no k_lut launch; the "hist_lut" stage of
+        // the profile is empty)
+        if (yuv) NV_CUDA(launch_face_prep_yuv(src.fmt, planes, width, height, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream, ctx->d_lut));
+        else NV_CUDA(launch_face_prep(d_src, width, height, stride, 3, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream, ctx->d_lut));
         prof_mark(ctx, 1);
-        NV_CUDA(launch_lut(ctx->d_hist, cols * rows, ctx->d_lut, ctx->stream));
-        *nl += 2;
+        *nl += 1;
         return detect_enqueue(ctx, casc, ctx->d_gray, cols, rows, cols, ctx->d_lut, &dp, nl);
     };
     // A context that sees the same call shape again replays it as ONE CUDA graph launch (the per-stream steady

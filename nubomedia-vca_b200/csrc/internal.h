@@ -260,6 +260,8 @@ struct Stage0Params {
     uint32_t *bits_alive;
     int *counters;
     int16_t *depth;
+    uint2 *queue;                                    // small plans: (window id, vnf) of every alive window goes straight to the
+    int queue_cap, queue_cidx;                       // warp-per-window kernel's queue (count in counters[queue_cidx]); else nullptr
 };
 static_assert(sizeof(Stage0Params) <= 32000, "kernel parameter space is 32764 bytes");
 
@@ -320,7 +322,9 @@ struct nv_ctx {
     uint8_t *d_aux = nullptr;    size_t aux_cap = 0;       // scratch image for standalone ops
 
     // resize tables (element-level resize), small cache keyed by (src, dst) size
-    struct RtabEntry { ResizeKey k; int *d = nullptr; };
+    // row_period > 0: the resize reads only the source rows row_a + k * row_period and the one below each (an integer
+    // down-scale by 3 or more: kmsfacedetect.cpp's 640 -> 160), so only those row pairs need to reach the device
+    struct RtabEntry { ResizeKey k; int *d = nullptr; int row_a = 0, row_period = 0; };
     RtabEntry rtabs[16];  int rtab_next = 0;
 
     // plans (see PlanSlot); ps is the one in use
@@ -384,14 +388,14 @@ struct nv_ctx {
 // kernels_prep.cu
 struct SrcPlanes { const uint8_t *p0, *p1, *p2; int s0, s1, s2; };    // planes of a 4:2:0 frame: Y, U|UV|VU, V
 cudaError_t launch_face_prep_yuv(int fmt, const SrcPlanes &s, int sw, int sh, uint8_t *gray, int dw, int dh, const int *rtab,
-                                 int *hist, cudaStream_t st);
+                                 int *hist, cudaStream_t st, uint8_t *lut = nullptr);
 cudaError_t launch_yuv2bgr(int fmt, const SrcPlanes &s, int w, int h, uint8_t *dst, int dstride, cudaStream_t st);
 cudaError_t launch_yuv2gray(int fmt, const SrcPlanes &s, int w, int h, uint8_t *dst, int dstride, cudaStream_t st);
 // context.cu: checks a 4:2:0 frame against the ctx and makes its planes device-resident (one H2D copy when they lie in one
 // block of host memory); fills the device plane pointers
 int nv_yuv_upload(nv_ctx *ctx, const nv_yuv_frame *f, SrcPlanes *planes);
 cudaError_t launch_face_prep(const uint8_t *src, int sw, int sh, int sstride, int cn, uint8_t *gray, int dw, int dh,
-                             const int *rtab, int *hist, cudaStream_t st);
+                             const int *rtab, int *hist, cudaStream_t st, uint8_t *lut = nullptr);   // lut: the last block also writes the equalizeHist LUT (hist holds 257 ints)
 cudaError_t launch_bgr2gray(const uint8_t *src, int w, int h, int sstride, int cn, uint8_t *dst, int dstride,
                             cudaStream_t st);
 cudaError_t launch_resize_linear(const uint8_t *src, int sw, int sh, int sstride, int cn, uint8_t *dst, int dw, int dh,
@@ -464,12 +468,12 @@ int nv_detect_device(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, int W
                      const nv_detect_params *p);
 int nv_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n);
 int nv_h2d(nv_ctx *ctx, const uint8_t *src, size_t bytes);
-int nv_get_rtab(nv_ctx *ctx, int sw, int sh, int dw, int dh, const int **d_tab);
+int nv_get_rtab(nv_ctx *ctx, int sw, int sh, int dw, int dh, const int **d_tab, const nv_ctx::RtabEntry **entry = nullptr);
 
 // kernels_group.cu
 cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *cand, int cand_cap, uint32_t *cand_sorted,
                          int4 *cand_rects, uint32_t *adj, int *grp, int min_neighbors, double eps, int img_w, int img_h,
-                         uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch);
+                         uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch, bool fused = false);
 
 // kernels_tracker.cu
 size_t tracker_scratch_bytes(int w, int h, TrkLayout *lo);

@@ -499,6 +499,16 @@ __global__ void __launch_bounds__(256) k_stage0_rows_p(const __grid_constant__ S
         nalive += __popc(am);
         if (lane == 0) P.bits_alive[lb.z + iy * nxw + cx] = am;
         if (alive) P.vnf[lb.y + iy * nx + ix] = vnf;
+        if (P.queue && am) {                             // small plan: k_alive_to_queue's job, without its launch
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&P.counters[P.queue_cidx], __popc(am));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (alive) {
+                const int pos = base + __popc(am & ((1u << lane) - 1u));
+                if (pos < P.queue_cap) P.queue[pos] = make_uint2(((uint32_t)l << 26) | ((uint32_t)iy << 13) | (uint32_t)ix, __float_as_uint(vnf));
+                else P.counters[2] = 1;
+            }
+        }
         if (P.depth && valid && !alive)
             P.depth[lb.y + iy * nx + ix] = (int16_t)(!visited ? NV_DEPTH_SKIPPED : (!ok ? NV_DEPTH_VARREJ : 0));
     }

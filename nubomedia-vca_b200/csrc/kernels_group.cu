@@ -27,11 +27,9 @@ __device__ __forceinline__ bool similar_rects(const int4 &a, const int4 &b, doub
 }
 
 // rank sort + candidate rectangles (A.6: cvRound of FLOAT products)
-__global__ void __launch_bounds__(256)
-k_cand_sort(const PlanDev *__restrict__ plan, const int *__restrict__ counters, const uint32_t *__restrict__ cand,
-            int cand_cap, uint32_t *__restrict__ sorted, int4 *__restrict__ rects, int *__restrict__ label)
+__device__ __forceinline__ void cand_sort_body(const PlanDev *__restrict__ plan, int n, const uint32_t *__restrict__ cand,
+                                               uint32_t *sorted, int4 *rects, int *label)
 {
-    int n = min(counters[1], cand_cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t key = cand[i];
         int rank = 0;
@@ -48,6 +46,13 @@ k_cand_sort(const PlanDev *__restrict__ plan, const int *__restrict__ counters, 
         rects[rank] = r;
         if (label) label[rank] = rank;                            // union-find forest of the large-n path
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_cand_sort(const PlanDev *__restrict__ plan, const int *__restrict__ counters, const uint32_t *__restrict__ cand,
+            int cand_cap, uint32_t *__restrict__ sorted, int4 *__restrict__ rects, int *__restrict__ label)
+{
+    cand_sort_body(plan, min(counters[1], cand_cap), cand, sorted, rects, label);
 }
 
 __device__ __forceinline__ int uf_find(int *L, int a)
@@ -67,16 +72,15 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b)
         else done = true;
     } while (!done);
 }
-__device__ __forceinline__ int key_lower_bound(const uint32_t *__restrict__ keys, int n, uint32_t key)
+__device__ __forceinline__ int key_lower_bound(const uint32_t *keys, int n, uint32_t key)
 {
     int lo = 0, hi = n;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
     return lo;
 }
 
 // large n: candidate i against the candidates AFTER it in canonical order that can be similar to it
-__device__ void uf_link(const PlanDev *__restrict__ plan, int n, const uint32_t *__restrict__ sorted,
-                        const int4 *__restrict__ rects, int *__restrict__ label, double eps)
+__device__ void uf_link(const PlanDev *__restrict__ plan, int n, const uint32_t *sorted, const int4 *rects, int *label, double eps)
 {
     const int nlevels = plan->nlevels;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -103,11 +107,10 @@ __device__ void uf_link(const PlanDev *__restrict__ plan, int n, const uint32_t 
 }
 
 // similarity bit-matrix: word (i, w) holds the similarity of candidate i with candidates 32w .. 32w+31
-__global__ void __launch_bounds__(256)
-k_adj(const PlanDev *__restrict__ plan, const int *__restrict__ counters, int cand_cap, const uint32_t *__restrict__ sorted,
-      const int4 *__restrict__ rects, uint32_t *__restrict__ adj, int *__restrict__ label, double eps)
+__device__ __forceinline__ void adj_body(const PlanDev *__restrict__ plan, int n, const uint32_t *sorted, const int4 *rects,
+                                         uint32_t *adj, int *label, double eps)
 {
-    int n = min(counters[1], cand_cap), nw = (n + 31) >> 5;
+    const int nw = (n + 31) >> 5;
     if (n > NV_GROUP_UF_MIN) { uf_link(plan, n, sorted, rects, label, eps); return; }     // large n: components by union-find
     long long total = (long long)n * nw;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -119,6 +122,13 @@ k_adj(const PlanDev *__restrict__ plan, const int *__restrict__ counters, int ca
             if (j != i && similar_rects(a, rects[j], eps)) m |= 1u << (j - j0);
         adj[t] = m;
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_adj(const PlanDev *__restrict__ plan, const int *__restrict__ counters, int cand_cap, const uint32_t *__restrict__ sorted,
+      const int4 *__restrict__ rects, uint32_t *__restrict__ adj, int *__restrict__ label, double eps)
+{
+    adj_body(plan, min(counters[1], cand_cap), sorted, rects, adj, label, eps);
 }
 
 #ifndef NV_GROUP_THREADS
@@ -141,10 +151,8 @@ __device__ __forceinline__ int block_flag_rank(bool flag, int &carry, int *s_war
 }
 
 // grp scratch layout (ints): label[cap] | cls[cap] | acc[5*cap] (x,y,w,h,count) | keep[cap]
-__global__ void __launch_bounds__(NV_GROUP_THREADS)
-k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects, const uint32_t *__restrict__ adj,
-        int *__restrict__ grp, int min_neighbors, double eps, int img_w, int img_h, uint8_t *__restrict__ result,
-        int result_cap)
+__device__ __forceinline__ void group_body(int *counters, int cand_cap, const int4 *rects, const uint32_t *adj, int *grp,
+                                           int min_neighbors, double eps, int img_w, int img_h, uint8_t *result, int result_cap)
 {
     __shared__ int s_warp[32];
     int tid = threadIdx.x;
@@ -303,10 +311,43 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
     }
 }
 
+__global__ void __launch_bounds__(NV_GROUP_THREADS)
+k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects, const uint32_t *__restrict__ adj,
+        int *__restrict__ grp, int min_neighbors, double eps, int img_w, int img_h, uint8_t *__restrict__ result,
+        int result_cap)
+{
+    group_body(counters, cand_cap, rects, adj, grp, min_neighbors, eps, img_w, img_h, result, result_cap);
+}
+
+// Small plans (a config-1 frame, a nested ROI: a few dozen candidates): canonical order, similarity matrix and grouping by
+// ONE block in one launch — three launches of a few microseconds each were a sixth of such a call.  The arrays pass
+// between the phases through global memory behind block barriers, so none of them is a read-only (__restrict__ const)
+// parameter here.
+__global__ void __launch_bounds__(NV_GROUP_THREADS)
+k_group_fused(const PlanDev *__restrict__ plan, int *counters, const uint32_t *__restrict__ cand, int cand_cap, uint32_t *sorted,
+              int4 *rects, uint32_t *adj, int *grp, int min_neighbors, double eps, int img_w, int img_h, uint8_t *result,
+              int result_cap)
+{
+    const int n = min(counters[1], cand_cap);
+    cand_sort_body(plan, n, cand, sorted, rects, min_neighbors > 0 ? grp : nullptr);
+    __syncthreads();
+    if (min_neighbors > 0) {
+        adj_body(plan, n, sorted, rects, adj, grp, eps);
+        __syncthreads();
+    }
+    group_body(counters, cand_cap, rects, adj, grp, min_neighbors, eps, img_w, img_h, result, result_cap);
+}
+
 cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *cand, int cand_cap, uint32_t *cand_sorted,
                          int4 *cand_rects, uint32_t *adj, int *grp, int min_neighbors, double eps, int img_w, int img_h,
-                         uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch)
+                         uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch, bool fused)
 {
+    if (fused) {
+        k_group_fused<<<1, NV_GROUP_THREADS, GROUP_SMEM_LABELS * sizeof(int), st>>>(plan, counters, cand, cand_cap, cand_sorted, cand_rects, adj,
+                                                                                  grp, min_neighbors, eps, img_w, img_h, result, result_cap);
+        (*nlaunch)++;
+        return cudaGetLastError();
+    }
     k_cand_sort<<<nblocks, 256, 0, st>>>(plan, counters, cand, cand_cap, cand_sorted, cand_rects, min_neighbors > 0 ? grp : nullptr);
     (*nlaunch)++;
     if (min_neighbors > 0) {

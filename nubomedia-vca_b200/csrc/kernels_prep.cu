@@ -58,6 +58,51 @@ __device__ __forceinline__ int lin_tap(const uint8_t *__restrict__ r0, const uin
     return (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;       // A.2 vertical pass
 }
 
+// histogram -> equalizeHist LUT (A.3), by one block of 256 threads: lut[k] = sat_u8(rint((float)(cum[k] - cum[i0]) *
+// (255.f / (total - hist[i0])))).  cum / s_i0: shared scratch of the caller.
+__device__ __forceinline__ uint8_t lut_entry(int t, int hv, int total, int *cum, int *s_i0)
+{
+    if (t == 0) *s_i0 = 256;
+    cum[t] = hv;
+    __syncthreads();
+    if (hv) atomicMin(s_i0, t);
+    for (int d = 1; d < 256; d <<= 1) {         // Hillis-Steele inclusive scan
+        int v = t >= d ? cum[t - d] : 0;
+        __syncthreads();
+        cum[t] += v;
+        __syncthreads();
+    }
+    const int i0 = *s_i0;
+    if (i0 >= 256) return (uint8_t)t;                                  // empty image: identity
+    const int h0 = cum[i0] - (i0 ? cum[i0 - 1] : 0);
+    if (h0 == total) return (uint8_t)i0;                               // constant image
+    if (t <= i0) return 0;
+    const float scale = __fdiv_rn(255.f, __int2float_rn(total - h0));
+    const int v = __float2int_rn(__fmul_rn(__int2float_rn(cum[t] - cum[i0]), scale));
+    return (uint8_t)min(max(v, 0), 255);
+}
+
+// End of a face-prep kernel: flush the block's histogram; with `lut` set, the block that finishes LAST (a ticket in
+// hist[256]) turns the complete histogram into the LUT and clears histogram and ticket for the next frame — what k_lut
+// does as a launch of its own (one block, ~4 us of a small call's chain) when the histogram comes from elsewhere.
+__device__ __forceinline__ void prep_finish(int tid, int *sh_hist, int *__restrict__ hist, uint8_t *__restrict__ lut, int total)
+{
+    __shared__ int s_i0, s_last;
+    __syncthreads();
+    if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
+    if (!lut) return;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&hist[256], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int hv = __ldcg(&hist[tid]);
+    lut[tid] = lut_entry(tid, hv, total, sh_hist, &s_i0);
+    hist[tid] = 0;
+    if (tid == 0) hist[256] = 0;
+}
+
 // K1+K2 fused for the face element: resize the BGR(A) frame (3 channels computed), convert to gray,
 // accumulate the histogram equalizeHist needs.  One thread per output pixel.
 // Blocks walk the 32x8-pixel output tiles with a grid stride (the launchers size the grid to a few blocks per SM): the
@@ -65,7 +110,7 @@ __device__ __forceinline__ int lin_tap(const uint8_t *__restrict__ r0, const uin
 // instead of one per bin and tile (8100 tiles on a 1080p frame).
 __global__ void __launch_bounds__(256)
 k_face_prep(const uint8_t *__restrict__ src, int sw, int sh, int sstride, int cn, uint8_t *__restrict__ gray, int dw,
-            int dh, const int *__restrict__ rtab, int *__restrict__ hist)
+            int dh, const int *__restrict__ rtab, int *__restrict__ hist, uint8_t *__restrict__ lut)
 {
     __shared__ int sh_hist[256];
     int tid = threadIdx.y * 32 + threadIdx.x;
@@ -98,8 +143,7 @@ k_face_prep(const uint8_t *__restrict__ src, int sw, int sh, int sstride, int cn
         gray[(size_t)y * dw + x] = (uint8_t)g;
         atomicAdd(&sh_hist[g], 1);
     }
-    __syncthreads();
-    if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
+    prep_finish(tid, sh_hist, hist, lut, dw * dh);
 }
 
 // Vectorised forms of the two streaming modes (same size, exact 2x): a lane owns FOUR consecutive output pixels, reads
@@ -112,7 +156,7 @@ __device__ __forceinline__ int byte_of(uint32_t w, int i) { return (int)((w >> (
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_face_prep_bgr4(const uint8_t *__restrict__ src, int sstride, uint8_t *__restrict__ gray, int dw, int dh,
-                 int *__restrict__ hist)
+                 int *__restrict__ hist, uint8_t *__restrict__ lut)
 {
     __shared__ int sh_hist[256];
     int tid = threadIdx.y * 32 + threadIdx.x;
@@ -153,8 +197,7 @@ k_face_prep_bgr4(const uint8_t *__restrict__ src, int sstride, uint8_t *__restri
 #pragma unroll
         for (int k = 0; k < 4; k++) atomicAdd(&sh_hist[g[k]], 1);
     }
-    __syncthreads();
-    if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
+    prep_finish(tid, sh_hist, hist, lut, dw * dh);
 }
 
 // ---- 4:2:0 ingest: the same block fed by I420 / NV12 / NV21 planes.  Every source pixel the
@@ -163,7 +206,7 @@ k_face_prep_bgr4(const uint8_t *__restrict__ src, int sstride, uint8_t *__restri
 template <int FMT>
 __global__ void __launch_bounds__(256)
 k_face_prep_yuv(SrcPlanes s, int sw, int sh, uint8_t *__restrict__ gray, int dw, int dh, const int *__restrict__ rtab,
-                int *__restrict__ hist)
+                int *__restrict__ hist, uint8_t *__restrict__ lut)
 {
     __shared__ int sh_hist[256];
     int tid = threadIdx.y * 32 + threadIdx.x;
@@ -200,8 +243,7 @@ k_face_prep_yuv(SrcPlanes s, int sw, int sh, uint8_t *__restrict__ gray, int dw,
         gray[(size_t)y * dw + x] = (uint8_t)g;
         atomicAdd(&sh_hist[g], 1);
     }
-    __syncthreads();
-    if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
+    prep_finish(tid, sh_hist, hist, lut, dw * dh);
 }
 
 // Vectorised 4:2:0 forms: a lane owns four consecutive output pixels.  Copy mode: 4 luma bytes (one word) and their
@@ -223,7 +265,7 @@ __device__ __forceinline__ void yuv_px(int yv, const YuvTerms &t, int c3[3])
 
 template <int FMT, int MODE>
 __global__ void __launch_bounds__(256)
-k_face_prep_yuv4(SrcPlanes s, uint8_t *__restrict__ gray, int dw, int dh, int *__restrict__ hist)
+k_face_prep_yuv4(SrcPlanes s, uint8_t *__restrict__ gray, int dw, int dh, int *__restrict__ hist, uint8_t *__restrict__ lut)
 {
     __shared__ int sh_hist[256];
     int tid = threadIdx.y * 32 + threadIdx.x;
@@ -286,8 +328,7 @@ k_face_prep_yuv4(SrcPlanes s, uint8_t *__restrict__ gray, int dw, int dh, int *_
 #pragma unroll
         for (int k = 0; k < 4; k++) atomicAdd(&sh_hist[g[k]], 1);
     }
-    __syncthreads();
-    if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
+    prep_finish(tid, sh_hist, hist, lut, dw * dh);
 }
 
 // BGR2GRAY(cvtColor(COLOR_YUV2BGR_*)) at full resolution: the first step of the nested elements on 4:2:0 frames
@@ -368,31 +409,8 @@ __global__ void __launch_bounds__(256) k_lut(int *__restrict__ hist, int total, 
 {
     __shared__ int cum[256];
     __shared__ int s_i0;
-    int t = threadIdx.x, hv = hist[t];
-    if (t == 0) s_i0 = 256;
-    cum[t] = hv;
-    __syncthreads();
-    if (hv) atomicMin(&s_i0, t);
-    for (int d = 1; d < 256; d <<= 1) {         // Hillis-Steele inclusive scan
-        int v = t >= d ? cum[t - d] : 0;
-        __syncthreads();
-        cum[t] += v;
-        __syncthreads();
-    }
-    int i0 = s_i0;
-    uint8_t out;
-    if (i0 >= 256) out = (uint8_t)t;                                  // empty image: identity
-    else {
-        int h0 = cum[i0] - (i0 ? cum[i0 - 1] : 0);
-        if (h0 == total) out = (uint8_t)i0;                            // constant image
-        else if (t <= i0) out = 0;
-        else {
-            float scale = __fdiv_rn(255.f, __int2float_rn(total - h0));
-            int v = __float2int_rn(__fmul_rn(__int2float_rn(cum[t] - cum[i0]), scale));
-            out = (uint8_t)min(max(v, 0), 255);
-        }
-    }
-    lut[t] = out;
+    const int t = threadIdx.x;
+    lut[t] = lut_entry(t, hist[t], total, cum, &s_i0);
     hist[t] = 0;
 }
 
@@ -429,42 +447,42 @@ static inline int prep_grid(int tiles)
 static inline bool aligned4(const void *p, int stride) { return (((uintptr_t)p | (uintptr_t)(unsigned)stride) & 3u) == 0; }
 
 cudaError_t launch_face_prep(const uint8_t *src, int sw, int sh, int sstride, int cn, uint8_t *gray, int dw, int dh,
-                             const int *rtab, int *hist, cudaStream_t st)
+                             const int *rtab, int *hist, cudaStream_t st, uint8_t *lut)
 {
     const int mode = (sw == dw && sh == dh) ? RT_COPY : (sw == 2 * dw && sh == 2 * dh) ? RT_BOX2 : RT_LINEAR;   // = rtab[0]
     if (mode != RT_LINEAR && cn == 3 && (dw & 3) == 0 && aligned4(src, sstride) && aligned4(gray, 0)) {
         int tiles = ((dw / 4 + 31) / 32) * ((dh + 7) / 8);
-        if (mode == RT_COPY) k_face_prep_bgr4<RT_COPY><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(src, sstride, gray, dw, dh, hist);
-        else k_face_prep_bgr4<RT_BOX2><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(src, sstride, gray, dw, dh, hist);
+        if (mode == RT_COPY) k_face_prep_bgr4<RT_COPY><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(src, sstride, gray, dw, dh, hist, lut);
+        else k_face_prep_bgr4<RT_BOX2><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(src, sstride, gray, dw, dh, hist, lut);
         return cudaGetLastError();
     }
     int tiles = ((dw + 31) / 32) * ((dh + 7) / 8);
-    k_face_prep<<<prep_grid(tiles), dim3(32, 8), 0, st>>>(src, sw, sh, sstride, cn, gray, dw, dh, rtab, hist);
+    k_face_prep<<<prep_grid(tiles), dim3(32, 8), 0, st>>>(src, sw, sh, sstride, cn, gray, dw, dh, rtab, hist, lut);
     return cudaGetLastError();
 }
 template <int FMT>
 static cudaError_t launch_prep_yuv_fmt(const SrcPlanes &s, int sw, int sh, uint8_t *gray, int dw, int dh, const int *rtab, int *hist,
-                                       cudaStream_t st)
+                                       cudaStream_t st, uint8_t *lut)
 {
     const int mode = (sw == dw && sh == dh) ? RT_COPY : (sw == 2 * dw && sh == 2 * dh) ? RT_BOX2 : RT_LINEAR;   // = rtab[0]
     const bool al = aligned4(s.p0, s.s0) && aligned4(s.p1, s.s1) && (FMT != 1 || aligned4(s.p2, s.s2)) && aligned4(gray, 0);
     if (mode != RT_LINEAR && (dw & 3) == 0 && al) {
         int tiles = ((dw / 4 + 31) / 32) * ((dh + 7) / 8);
-        if (mode == RT_COPY) k_face_prep_yuv4<FMT, RT_COPY><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(s, gray, dw, dh, hist);
-        else k_face_prep_yuv4<FMT, RT_BOX2><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(s, gray, dw, dh, hist);
+        if (mode == RT_COPY) k_face_prep_yuv4<FMT, RT_COPY><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(s, gray, dw, dh, hist, lut);
+        else k_face_prep_yuv4<FMT, RT_BOX2><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(s, gray, dw, dh, hist, lut);
         return cudaGetLastError();
     }
     int tiles = ((dw + 31) / 32) * ((dh + 7) / 8);
-    k_face_prep_yuv<FMT><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(s, sw, sh, gray, dw, dh, rtab, hist);
+    k_face_prep_yuv<FMT><<<prep_grid(tiles), dim3(32, 8), 0, st>>>(s, sw, sh, gray, dw, dh, rtab, hist, lut);
     return cudaGetLastError();
 }
 
 cudaError_t launch_face_prep_yuv(int fmt, const SrcPlanes &s, int sw, int sh, uint8_t *gray, int dw, int dh, const int *rtab,
-                                 int *hist, cudaStream_t st)
+                                 int *hist, cudaStream_t st, uint8_t *lut)
 {
-    if (fmt == NV_FMT_I420) return launch_prep_yuv_fmt<1>(s, sw, sh, gray, dw, dh, rtab, hist, st);
-    if (fmt == NV_FMT_NV12) return launch_prep_yuv_fmt<2>(s, sw, sh, gray, dw, dh, rtab, hist, st);
-    if (fmt == NV_FMT_NV21) return launch_prep_yuv_fmt<3>(s, sw, sh, gray, dw, dh, rtab, hist, st);
+    if (fmt == NV_FMT_I420) return launch_prep_yuv_fmt<1>(s, sw, sh, gray, dw, dh, rtab, hist, st, lut);
+    if (fmt == NV_FMT_NV12) return launch_prep_yuv_fmt<2>(s, sw, sh, gray, dw, dh, rtab, hist, st, lut);
+    if (fmt == NV_FMT_NV21) return launch_prep_yuv_fmt<3>(s, sw, sh, gray, dw, dh, rtab, hist, st, lut);
     return cudaErrorInvalidValue;
 }
 cudaError_t launch_yuv2gray(int fmt, const SrcPlanes &s, int w, int h, uint8_t *dst, int dstride, cudaStream_t st)
