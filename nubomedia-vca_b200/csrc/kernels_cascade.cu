@@ -1480,11 +1480,21 @@ k_cascade_tail_tab(const PlanDev *__restrict__ plan, const DevCascade *__restric
     double *sC = reinterpret_cast<double *>(sB + nt);
     const int ww = plan->win_w, wh = plan->win_h, LP = ww + 1, npatch = (wh + 1) * LP;
     uint32_t *win = reinterpret_cast<uint32_t *>(sC + nt) + warp * npatch;
-    for (int i = tid; i < nt; i += 32 * NWARP) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(ts + kt0 + i);
-        sA[i] = __ldg(p); sB[i] = __ldg(p + 1);
-        const uint4 c = __ldg(p + 2);
-        sC[i] = __hiloint2double((int)c.y, (int)c.x);
+    for (int i0 = tid; i0 < nt; i0 += 4 * 32 * NWARP) {          // four records per thread in flight (a thread copies ~9 of them)
+        uint4 ra[4], rb[4], rc[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * 32 * NWARP;
+            if (i < nt) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(ts + kt0 + i);
+                ra[u] = __ldg(p); rb[u] = __ldg(p + 1); rc[u] = __ldg(p + 2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * 32 * NWARP;
+            if (i < nt) { sA[i] = ra[u]; sB[i] = rb[u]; sC[i] = __hiloint2double((int)rc[u].y, (int)rc[u].x); }
+        }
     }
     for (int i = tid; i <= meta->nstages; i += 32 * NWARP) s_first[i] = meta->stage_first[i] - kt0;
     for (int i = tid; i < meta->nstages; i += 32 * NWARP) { s_thr[i] = meta->stage_thr[i]; s_base[i] = tbase[i]; }
@@ -2017,6 +2027,8 @@ cudaError_t launch_cascade_tail_tab(const PlanDev *plan, const DevCascade *meta,
     }
     int per_sm = (int)((227 * 1024) / (smem + 2048));            // static tables + the per-block reserve
     per_sm = per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm;
+    // (fewer blocks when the queue is short — every block copies the table — was measured: no gain down to one block per 32
+    // windows of the plan, slower below)
     k_cascade_tail_tab<NV_TAILTAB_WARPS><<<148 * per_sm, 32 * NV_TAILTAB_WARPS, smem, st>>>(
         plan, meta, tstumps, tbase, sum, tail, counters, cand, cand_cap, depth, stage_begin, stage_end, deep, deep_cap);
     return cudaGetLastError();

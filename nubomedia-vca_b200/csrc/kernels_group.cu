@@ -136,6 +136,7 @@ k_adj(const PlanDev *__restrict__ plan, const int *__restrict__ counters, int ca
 #endif
 #define NV_GROUP_WARPS (NV_GROUP_THREADS / 32)
 // exclusive rank of a 0/1 flag across the block, with a running carry
+template <int NT>
 __device__ __forceinline__ int block_flag_rank(bool flag, int &carry, int *s_warp)
 {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,7 +144,7 @@ __device__ __forceinline__ int block_flag_rank(bool flag, int &carry, int *s_war
     if (lane == 0) s_warp[warp] = __popc(m);
     __syncthreads();
     int before = 0, total = 0;
-    for (int k = 0; k < NV_GROUP_WARPS; k++) { int c = s_warp[k]; if (k < warp) before += c; total += c; }
+    for (int k = 0; k < (NT / 32); k++) { int c = s_warp[k]; if (k < warp) before += c; total += c; }
     int pos = carry + before + __popc(m & ((1u << lane) - 1u));
     carry += total;
     __syncthreads();
@@ -151,6 +152,7 @@ __device__ __forceinline__ int block_flag_rank(bool flag, int &carry, int *s_war
 }
 
 // grp scratch layout (ints): label[cap] | cls[cap] | acc[5*cap] (x,y,w,h,count) | keep[cap]
+template <int NT>
 __device__ __forceinline__ void group_body(int *counters, int cand_cap, const int4 *rects, const uint32_t *adj, int *grp,
                                            int min_neighbors, double eps, int img_w, int img_h, uint8_t *result, int result_cap)
 {
@@ -169,7 +171,7 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
     if (min_neighbors <= 0) {
         // no grouping: canonical-order candidates, clipped; empty intersections are dropped (A.8)
         int carry = 0;
-        for (int i0 = 0; i0 < n; i0 += NV_GROUP_THREADS) {
+        for (int i0 = 0; i0 < n; i0 += NT) {
             int i = i0 + tid;
             int4 r = make_int4(0, 0, 0, 0);
             bool k = false;
@@ -179,14 +181,14 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
                 k = x1 > x0 && y1 > y0;
                 r = make_int4(x0, y0, x1 - x0, y1 - y0);
             }
-            int pos = block_flag_rank(k, carry, s_warp);
+            int pos = block_flag_rank<NT>(k, carry, s_warp);
             if (k && pos < result_cap) out[pos] = r;
         }
         nout = carry;
     } else {
-        if (!uf) for (int i = tid; i < n; i += NV_GROUP_THREADS) label[i] = i;
+        if (!uf) for (int i = tid; i < n; i += NT) label[i] = i;
         else {                                                    // flatten the forest k_adj linked: roots stay put, paths only get shorter
-            for (int i = tid; i < n; i += NV_GROUP_THREADS) { const int r = uf_find(grp, i); if (r != i) grp[i] = r; }
+            for (int i = tid; i < n; i += NT) { const int r = uf_find(grp, i); if (r != i) grp[i] = r; }
         }
         __syncthreads();
         // min-label propagation until a fixed point: one warp per candidate row, lanes over the row's adjacency
@@ -200,15 +202,15 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
             if (wpl <= 8 && warp < n)
 #pragma unroll
                 for (int q = 0; q < 8; q++) { int w = lane + 32 * q; nxt[q] = (q < wpl && w < nw) ? adj[(size_t)warp * nw + w] : 0u; }
-            for (int i = warp; i < n; i += NV_GROUP_WARPS) {
+            for (int i = warp; i < n; i += (NT / 32)) {
                 int m = 0x7fffffff;
                 if (wpl <= 8) {
                     uint32_t cur[8];
 #pragma unroll
                     for (int q = 0; q < 8; q++) cur[q] = nxt[q];
-                    if (i + NV_GROUP_WARPS < n)
+                    if (i + (NT / 32) < n)
 #pragma unroll
-                        for (int q = 0; q < 8; q++) { int w = lane + 32 * q; nxt[q] = (q < wpl && w < nw) ? adj[(size_t)(i + NV_GROUP_WARPS) * nw + w] : 0u; }
+                        for (int q = 0; q < 8; q++) { int w = lane + 32 * q; nxt[q] = (q < wpl && w < nw) ? adj[(size_t)(i + (NT / 32)) * nw + w] : 0u; }
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         uint32_t b = cur[q];
@@ -236,16 +238,16 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
         }
         // classes numbered by their first member (= the component's minimum index)
         int carry = 0;
-        for (int i0 = 0; i0 < n; i0 += NV_GROUP_THREADS) {
+        for (int i0 = 0; i0 < n; i0 += NT) {
             int i = i0 + tid;
             bool root = i < n && label[i] == i;
-            int pos = block_flag_rank(root, carry, s_warp);
+            int pos = block_flag_rank<NT>(root, carry, s_warp);
             if (root) cls[i] = pos;
         }
         int ncls = carry;
-        for (int i = tid; i < 5 * ncls; i += NV_GROUP_THREADS) acc[i] = 0;
+        for (int i = tid; i < 5 * ncls; i += NT) acc[i] = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += NV_GROUP_THREADS) {
+        for (int i = tid; i < n; i += NT) {
             int c = cls[label[i]];
             int4 r = rects[i];
             atomicAdd(&acc[5 * c + 0], r.x); atomicAdd(&acc[5 * c + 1], r.y);
@@ -253,24 +255,24 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
             atomicAdd(&acc[5 * c + 4], 1);
         }
         __syncthreads();
-        for (int c = tid; c < ncls; c += NV_GROUP_THREADS) {
+        for (int c = tid; c < ncls; c += NT) {
             float s = __fdiv_rn(1.f, __int2float_rn(acc[5 * c + 4]));
             for (int k = 0; k < 4; k++) acc[5 * c + k] = __float2int_rn(__fmul_rn(__int2float_rn(acc[5 * c + k]), s));
         }
         __syncthreads();
         // classes with enough members, in class order (the containment test only ever looks at those)
         int nk = 0;
-        for (int i0 = 0; i0 < ncls; i0 += NV_GROUP_THREADS) {
+        for (int i0 = 0; i0 < ncls; i0 += NT) {
             int i = i0 + tid;
             bool k = i < ncls && acc[5 * i + 4] > min_neighbors;
-            int pos = block_flag_rank(k, nk, s_warp);
+            int pos = block_flag_rank<NT>(k, nk, s_warp);
             if (k) keep[pos] = i;
         }
         __syncthreads();
         // drop a class that lies inside a clearly stronger one (A.7)
         int *alive = cls;                                   // cls[] is no longer needed: reuse as the survivor flags
         __syncthreads();
-        for (int a = tid; a < nk; a += NV_GROUP_THREADS) {
+        for (int a = tid; a < nk; a += NT) {
             int i = keep[a];
             int n1 = acc[5 * i + 4], x1 = acc[5 * i], y1 = acc[5 * i + 1], w1 = acc[5 * i + 2], h1 = acc[5 * i + 3];
             bool k = true;
@@ -287,7 +289,7 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
         }
         __syncthreads();
         carry = 0;
-        for (int a0 = 0; a0 < nk; a0 += NV_GROUP_THREADS) {
+        for (int a0 = 0; a0 < nk; a0 += NT) {
             int a = a0 + tid;
             bool k = false;
             int4 r = make_int4(0, 0, 0, 0);
@@ -298,7 +300,7 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
                 k = x1 > x0 && y1 > y0;
                 r = make_int4(x0, y0, x1 - x0, y1 - y0);
             }
-            int pos = block_flag_rank(k, carry, s_warp);
+            int pos = block_flag_rank<NT>(k, carry, s_warp);
             if (k && pos < result_cap) out[pos] = r;
         }
         nout = carry;
@@ -316,14 +318,17 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
         int *__restrict__ grp, int min_neighbors, double eps, int img_w, int img_h, uint8_t *__restrict__ result,
         int result_cap)
 {
-    group_body(counters, cand_cap, rects, adj, grp, min_neighbors, eps, img_w, img_h, result, result_cap);
+    group_body<NV_GROUP_THREADS>(counters, cand_cap, rects, adj, grp, min_neighbors, eps, img_w, img_h, result, result_cap);
 }
 
 // Small plans (a config-1 frame, a nested ROI: a few dozen candidates): canonical order, similarity matrix and grouping by
 // ONE block in one launch — three launches of a few microseconds each were a sixth of such a call.  The arrays pass
 // between the phases through global memory behind block barriers, so none of them is a read-only (__restrict__ const)
-// parameter here.
-__global__ void __launch_bounds__(NV_GROUP_THREADS)
+// parameter here.  256 threads: with the few dozen candidates of such a call 24 of a 1024-thread block's warps only run loop
+// control and barriers.  (Keeping keys, rectangles, matrix and class tables of up to 256 candidates in shared memory was
+// measured too: no change, 19 us under ncu either way — the launch is a chain of short dependent phases of one block.)
+#define NV_GROUP_FUSED_THREADS 256
+__global__ void __launch_bounds__(NV_GROUP_FUSED_THREADS)
 k_group_fused(const PlanDev *__restrict__ plan, int *counters, const uint32_t *__restrict__ cand, int cand_cap, uint32_t *sorted,
               int4 *rects, uint32_t *adj, int *grp, int min_neighbors, double eps, int img_w, int img_h, uint8_t *result,
               int result_cap)
@@ -335,7 +340,7 @@ k_group_fused(const PlanDev *__restrict__ plan, int *counters, const uint32_t *_
         adj_body(plan, n, sorted, rects, adj, grp, eps);
         __syncthreads();
     }
-    group_body(counters, cand_cap, rects, adj, grp, min_neighbors, eps, img_w, img_h, result, result_cap);
+    group_body<NV_GROUP_FUSED_THREADS>(counters, cand_cap, rects, adj, grp, min_neighbors, eps, img_w, img_h, result, result_cap);
 }
 
 cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *cand, int cand_cap, uint32_t *cand_sorted,
@@ -343,7 +348,7 @@ cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *can
                          uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch, bool fused)
 {
     if (fused) {
-        k_group_fused<<<1, NV_GROUP_THREADS, GROUP_SMEM_LABELS * sizeof(int), st>>>(plan, counters, cand, cand_cap, cand_sorted, cand_rects, adj,
+        k_group_fused<<<1, NV_GROUP_FUSED_THREADS, GROUP_SMEM_LABELS * sizeof(int), st>>>(plan, counters, cand, cand_cap, cand_sorted, cand_rects, adj,
                                                                                   grp, min_neighbors, eps, img_w, img_h, result, result_cap);
         (*nlaunch)++;
         return cudaGetLastError();
