@@ -2019,11 +2019,17 @@ cudaError_t launch_cascade_tail_tab(const PlanDev *plan, const DevCascade *meta,
 {
     const size_t smem = tail_tab_smem(hmeta, stage_begin, stage_end);
     if (smem > NV_TAILTAB_MAX_SMEM) return cudaErrorInvalidConfiguration;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_cascade_tail_tab<NV_TAILTAB_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NV_TAILTAB_MAX_SMEM);
-        if (e != cudaSuccess) return e;
-        configured = NV_TAILTAB_MAX_SMEM;
+    static std::mutex mu;
+    static unsigned long long attr_set = 0ull;                   // per device: the attribute belongs to the device's function
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!((attr_set >> (dev & 63)) & 1ull)) {
+            cudaError_t e = cudaFuncSetAttribute(k_cascade_tail_tab<NV_TAILTAB_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NV_TAILTAB_MAX_SMEM);
+            if (e != cudaSuccess) return e;
+            attr_set |= 1ull << (dev & 63);
+        }
     }
     int per_sm = (int)((227 * 1024) / (smem + 2048));            // static tables + the per-block reserve
     per_sm = per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm;
