@@ -398,6 +398,48 @@ def test_prep_modes_and_alignment(ctx, face, case):
     assert rects_equal(nv._rects(ctx._out, n.value), exp)
 
 
+@pytest.mark.parametrize("case", [(640, 480, 160, 0), (640, 480, 160, 16), (480, 360, 160, 0), (800, 600, 160, 4),
+                                  (960, 540, 160, 0), (646, 486, 160, 0), (1920, 1080, 320, 0)])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_integer_downscale_uploads_row_pairs(face, case, pinned):
+    """An integer down-scale by 3 or more (the element's default 640 -> 160) reads two of every `scale` source rows; only
+    those row pairs are uploaded (context.cu: nv_h2d_row_pairs; page-locked frames in place, others through the staging
+    buffer).  The rows that stay on the host are POISONED on the device side here by a first, full-size call with a frame of 0xFF, so a
+    kernel that read one of them would not reproduce the oracle's gray image.  646x486 is the irregular case (646 / 160 = 4
+    but 486 rows do not divide: the whole frame travels).  Non-debug context: graph replay on the third call."""
+    import ctypes as C
+    import torch
+    ncasc, ocasc = face
+    W, H, w2p, pad = case
+    c = nv.Context(0, 1920, 1080)
+    try:
+        fr = synth.frame(W, H, 3, 77 + W + pad)
+        stride = 3 * W + pad
+        host = torch.empty((H, stride), dtype=torch.uint8)
+        if pinned:
+            host = host.pin_memory()
+        buf = host.numpy()
+        n = C.c_int(0)
+        a = nv.Context._face_params(w2p, 1.2, 2, None)
+        exp, eq = O.face_process(fr, ocasc, w2p, 1.2, 2, None)
+        for it in range(4):
+            buf[:] = 255 if it == 0 else np.random.default_rng(it).integers(0, 256, buf.shape, dtype=np.uint8)
+            if it > 0:
+                buf[:, :3 * W] = fr.reshape(H, -1)
+            # the poison frame goes up whole (processing width = frame width: same-size mode, every row is read)
+            prm = nv.Context._face_params(W, 1.2, 2, None) if it == 0 else a
+            assert nv._lib.nv_face_detect(c.handle, ncasc.handle, buf.ctypes.data_as(C.c_void_p), W, H, stride, C.byref(prm),
+                                          c._out, c._cap, C.byref(n)) == 0
+            if it > 0:
+                assert rects_equal(nv._rects(c._out, n.value), exp), it
+        c.set_debug(True)
+        assert nv._lib.nv_face_detect(c.handle, ncasc.handle, buf.ctypes.data_as(C.c_void_p), W, H, stride, C.byref(a),
+                                      c._out, c._cap, C.byref(n)) == 0
+        assert (c.gray() == eq).all()
+    finally:
+        c.close()
+
+
 def test_cfg3_full_size_1080p(ctx, face):
     """BASELINE config 3 at full size: 1920x1080, processing width 1920, sf 1.1, min 24x24.
     Full oracle comparison (a few seconds of CPU) including every depth map."""
