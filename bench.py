@@ -726,6 +726,13 @@ def main():
                                             "frac": wf / t / (148 * clk), "wavefronts_per_frame": wf,
                                             "conflict_replays_per_frame": tj.get("tile_shared_bank_conflict_wavefronts_per_frame")},
                           "source": "counts from profiles/traffic.json (ncu), time = stage_ms_isolated.cascade_tiles"}
+                fw = tj.get("frame_warp_instructions_per_frame")
+                if fw and value > 0:
+                    # the same bound for the timed region as a whole: every kernel's warp instructions of a frame x the frames
+                    # one GPU finished per second in it (eight frames in flight: the kernels of different frames share the SMs)
+                    onchip["timed_region"] = {"achieved": fw * (value / world) / 1e9, "frac": fw * (value / world) / (148 * 4 * clk),
+                                              "unit": "G warp-instructions/s", "warp_instructions_per_frame": fw,
+                                              "source": tj.get("frame_warp_instructions_source")}
         casc_ms = med.get("cascade_stage0", 0) + med.get("cascade_tiles", 0) + med.get("cascade_tail", 0)
         frame_ms = sum(med.values())
         achieved = ab["cascade"] / (casc_ms * 1e-3) / 1e9 if casc_ms > 0 else None
