@@ -116,7 +116,9 @@ NV_API int nv_face_detect(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, 
  * first copied into the ctx's pinned staging buffer (the caller may reuse it as soon as submit returns); a
  * frame in page-locked memory (cudaHostAlloc / cudaHostRegister) is read directly by the DMA engine and
  * must stay untouched until collect.  Once a context sees the same call shape twice, the whole per-frame
- * kernel sequence is replayed as a single CUDA graph launch. */
+ * kernel sequence is replayed as a single CUDA graph launch.  When width / width_to_process is 3 or more and divides
+ * both dimensions, cv::resize(INTER_LINEAR) reads only two of every `scale` source rows: only those rows are read from
+ * the caller's frame and copied to the device (half of a 640x480 frame processed at 160x120). */
 NV_API int nv_face_submit(nv_ctx *ctx, const nv_cascade *c, const uint8_t *bgr, int width, int height,
                           int stride_bytes, const nv_face_params *p);
 NV_API int nv_face_collect(nv_ctx *ctx, nv_rect *out, int cap, int *n);
