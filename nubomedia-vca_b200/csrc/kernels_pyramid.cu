@@ -24,7 +24,7 @@ __device__ __forceinline__ int find_level(const PlanDev *__restrict__ plan, int 
 // 8-byte stores on the de-interleaved ystep-2 layout: columns c, c + 2 are neighbours in the even plane, c + 1, c + 3
 // in the odd one).  Round 1's kernel did one pixel per lane: 3.4 x the instructions, and a 1920-pixel row was a chain
 // of 60 dependent load -> scan -> carry rounds where this one has 15.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)                        // 32 registers, no spills: eight blocks per SM (40.3 -> 38.9 us alone)
 k_pyr_rowscan(const PlanDev *__restrict__ plan, const uint8_t *__restrict__ gray, int gstride,
               const uint8_t *__restrict__ lut, const int2 *__restrict__ ptab, uint32_t *__restrict__ sum,
               uint32_t *__restrict__ sq, uint8_t *__restrict__ pyr_debug)
