@@ -14,7 +14,8 @@
 // 0.2 ms duration keeps one).  Per frame and pixel the kernel reads 4 (BGRA) + 1 (prev) + 1 (history) bytes and writes
 // 1 + 1: 8 bytes, against 38 in the round-1 kernels (float history, an int label, an int seed and an int4 box per pixel).
 //
-// One 64 x 32 tile per 256-thread block, four pixels per thread and row (128-bit BGRA loads):
+// One 64 x 16 tile per 256-thread block (64 x 32 with -DTRK_TH=32: the round-2 default until its last session — the smaller
+// tile halves the slowest block and is 2-3 us faster at every frame size), four pixels per thread (128-bit BGRA loads):
 //   1. point operations, the new history values of the tile land in shared memory;
 //   2. block-local labelling in shared memory: horizontal pre-linking inside each thread's four pixels, then lock-free
 //      union-find (atomicMin links, the smaller index wins, so a root is its component's first pixel in raster order);
@@ -34,9 +35,12 @@
 
 #define TRK_MAX_COMPONENTS 16384
 #define TRK_TW 64
-#define TRK_TH 32
+#ifndef TRK_TH
+#define TRK_TH 16                                    // 16 or 32: rows of a tile (a thread owns one unit of four pixels per 16 rows)
+#endif
+#define TRK_NH (TRK_TH / 16)
 #define TRK_NPX (TRK_TW * TRK_TH)
-#define TRK_PERIM (2 * TRK_TW + 2 * TRK_TH)          // top 0..63, bottom 64..127, left 128..159, right 160..191
+#define TRK_PERIM (2 * TRK_TW + 2 * TRK_TH)          // top 0..63, bottom 64..127, then the left and the right column
 #define TRK_SLOTS TRK_PERIM
 #define TRK_NONE 0x7fffffff
 
@@ -148,12 +152,12 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
     __syncthreads();
     TRK_T(1);
 
-    // ---- 1. point operations: two units of four pixels per thread (rows ly and ly + 16) ---------------------------------
+    // ---- 1. point operations: TRK_NH units of four pixels per thread (rows ly, ly + 16) ---------------------------------------
     const int ux = (tid & 15) * 4;
-    unsigned seedbits[2] = {0u, 0u};                               // bit k: pixel k of the unit has mhi == ts
+    unsigned seedbits[TRK_NH] = {};                               // bit k: pixel k of the unit has mhi == ts
     int mine = 0;                                                  // does this thread hold any pixel with history?
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
+    for (int half = 0; half < TRK_NH; half++) {
         const int ly = (tid >> 4) + half * 16, y = y0 + ly, x = x0 + ux, li = ly * TRK_TW + ux;
         int g[4] = {0, 0, 0, 0};
         unsigned hv[4] = {0, 0, 0, 0};
@@ -222,7 +226,11 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
     // perimeter and takes part in the edge and completion protocol
     const bool empty = !__syncthreads_or(mine);
     TRK_T(2);
-    int root[2][4] = {{TRK_NONE, TRK_NONE, TRK_NONE, TRK_NONE}, {TRK_NONE, TRK_NONE, TRK_NONE, TRK_NONE}};
+    int root[TRK_NH][4];
+#pragma unroll
+    for (int half = 0; half < TRK_NH; half++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) root[half][k] = TRK_NONE;
     if (!empty) {
 
     // ---- 2b. unions: along the rows first, then between rows, each followed by pointer jumping -----------------------------
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
         for (;;) {
             int moved = 0;
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
+            for (int half = 0; half < TRK_NH; half++) {
                 const int li = ((tid >> 4) + half * 16) * TRK_TW + ux;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -248,14 +256,14 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
         }
     };
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
+    for (int half = 0; half < TRK_NH; half++) {
         const int li = ((tid >> 4) + half * 16) * TRK_TW + ux;
         if (ux + 4 < TRK_TW && trk_joined(s_a.m[li + 3], s_a.m[li + 4])) trk_union(s_lab, li + 3, li + 4);
     }
     __syncthreads();
     jump();
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
+    for (int half = 0; half < TRK_NH; half++) {
         const int ly = (tid >> 4) + half * 16, li = ly * TRK_TW + ux;
         if (ly + 1 < TRK_TH) {
             // was the vertical edge one pixel to the left joined?  (also across the unit boundary: inside a blob only the
@@ -277,14 +285,14 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
     // ---- 2c. flatten -----------------------------------------------------------------------------------------------------
     jump();
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
+    for (int half = 0; half < TRK_NH; half++) {
         const int li = ((tid >> 4) + half * 16) * TRK_TW + ux;
 #pragma unroll
         for (int k = 0; k < 4; k++) root[half][k] = s_lab[li + k];
     }
     __syncthreads();                                               // every find is done: s_a.m is dead, s_lab may be rewritten
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
+    for (int half = 0; half < TRK_NH; half++) {
         const int ly = (tid >> 4) + half * 16, li = ly * TRK_TW + ux;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -297,7 +305,7 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
 
     // ---- 3. per-root reductions: runs of equal root inside a unit first, lanes with the same root next, then one atomic ---
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
+    for (int half = 0; half < TRK_NH; half++) {
         const int ly = (tid >> 4) + half * 16, li = ly * TRK_TW + ux;
 #pragma unroll
         for (int k = 0; k < 4; k++) {                              // round k: the run of equal roots that STARTS at pixel k, if any
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
     // ---- 4. roots: final inside the tile, or a slot of the perimeter table ------------------------------------------------
     int *const parent = P.parent + (size_t)tile * TRK_SLOTS;
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
+    for (int half = 0; half < TRK_NH; half++) {
         const int ly = (tid >> 4) + half * 16, li = ly * TRK_TW + ux;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
