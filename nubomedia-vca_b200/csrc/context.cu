@@ -860,15 +860,20 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         }
     }
     prof_mark(ctx, 7);
+    static const bool host_writes = [] { const char *e = getenv("NUBOVCA_HOST_WRITES"); return !e || atoi(e) != 0; }();
     // small plans: sort + similarity matrix + grouping in one launch of one block (k_group_fused)
     static const bool group_fused = [] { const char *e = getenv("NUBOVCA_GROUP_FUSED"); return !e || atoi(e) != 0; }();
     static const int small_limit_g = [] { const char *e = getenv("NUBOVCA_SMALL_PLAN"); return e ? atoi(e) : NV_SMALL_PLAN_WINDOWS; }();
     NV_CUDA(launch_group(ctx->ps->d_plan, ctx->d_counters, ctx->d_cand, ctx->cand_cap, ctx->d_cand_sorted, ctx->d_cand_rects,
                          ctx->d_adj, ctx->d_grp, p->min_neighbors, 0.2, W, H, ctx->d_result, ctx->result_cap, 148 * 2, st, &nl,
-                         group_fused && P.total_windows <= small_limit_g));
+                         group_fused && P.total_windows <= small_limit_g, host_writes ? ctx->h_result : nullptr));
     prof_mark(ctx, 8);
-    NV_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(ResultHeader) + NV_RESULT_INLINE * sizeof(nv_rect),
-                            cudaMemcpyDeviceToHost, st));
+    // the grouping kernel writes header and rectangles into the page-locked result block itself (mapped memory, posted
+    // writes over PCIe, visible once the stream has been waited for): no device-to-host copy behind it.
+    // NUBOVCA_HOST_WRITES=0: the copy (what every call did before).
+    if (!host_writes)
+        NV_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(ResultHeader) + NV_RESULT_INLINE * sizeof(nv_rect),
+                                cudaMemcpyDeviceToHost, st));
     *nlaunch += nl;
     return NV_OK;
 }

@@ -154,13 +154,18 @@ __device__ __forceinline__ int block_flag_rank(bool flag, int &carry, int *s_war
 // grp scratch layout (ints): label[cap] | cls[cap] | acc[5*cap] (x,y,w,h,count) | keep[cap]
 template <int NT>
 __device__ __forceinline__ void group_body(int *counters, int cand_cap, const int4 *rects, const uint32_t *adj, int *grp,
-                                           int min_neighbors, double eps, int img_w, int img_h, uint8_t *result, int result_cap)
+                                           int min_neighbors, double eps, int img_w, int img_h, uint8_t *result, int result_cap,
+                                           uint8_t *host_result)
 {
     __shared__ int s_warp[32];
     int tid = threadIdx.x;
     int n = min(counters[1], cand_cap), nw = (n + 31) >> 5;
     ResultHeader *hdr = reinterpret_cast<ResultHeader *>(result);
     int4 *out = reinterpret_cast<int4 *>(result + sizeof(ResultHeader));
+    // host_result: the context's page-locked result block, mapped into the device's address space.  Header and the first
+    // NV_RESULT_INLINE rectangles are written there as well, straight over PCIe, so that no device-to-host copy follows
+    // the launch (one node less in every call's graph).
+    int4 *hout = host_result ? reinterpret_cast<int4 *>(host_result + sizeof(ResultHeader)) : nullptr;
     extern __shared__ int s_label[];                 // min(n, GROUP_SMEM_LABELS) labels; global scratch beyond that
     __shared__ int s_changed;
     const bool uf = n > NV_GROUP_UF_MIN;                          // labels already final in grp (uf_link in k_adj, flattened below)
@@ -182,7 +187,7 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
                 r = make_int4(x0, y0, x1 - x0, y1 - y0);
             }
             int pos = block_flag_rank<NT>(k, carry, s_warp);
-            if (k && pos < result_cap) out[pos] = r;
+            if (k && pos < result_cap) { out[pos] = r; if (hout && pos < NV_RESULT_INLINE) hout[pos] = r; }
         }
         nout = carry;
     } else {
@@ -301,7 +306,7 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
                 r = make_int4(x0, y0, x1 - x0, y1 - y0);
             }
             int pos = block_flag_rank<NT>(k, carry, s_warp);
-            if (k && pos < result_cap) out[pos] = r;
+            if (k && pos < result_cap) { out[pos] = r; if (hout && pos < NV_RESULT_INLINE) hout[pos] = r; }
         }
         nout = carry;
     }
@@ -310,15 +315,16 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
         hdr->n_cand = counters[1];
         hdr->n_alive = counters[0];
         hdr->overflow = counters[2] | (nout > result_cap) | (counters[1] > cand_cap);
+        if (host_result) *reinterpret_cast<ResultHeader *>(host_result) = *hdr;
     }
 }
 
 __global__ void __launch_bounds__(NV_GROUP_THREADS)
 k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects, const uint32_t *__restrict__ adj,
         int *__restrict__ grp, int min_neighbors, double eps, int img_w, int img_h, uint8_t *__restrict__ result,
-        int result_cap)
+        int result_cap, uint8_t *__restrict__ host_result)
 {
-    group_body<NV_GROUP_THREADS>(counters, cand_cap, rects, adj, grp, min_neighbors, eps, img_w, img_h, result, result_cap);
+    group_body<NV_GROUP_THREADS>(counters, cand_cap, rects, adj, grp, min_neighbors, eps, img_w, img_h, result, result_cap, host_result);
 }
 
 // Small plans (a config-1 frame, a nested ROI: a few dozen candidates): canonical order, similarity matrix and grouping by
@@ -331,7 +337,7 @@ k_group(int *__restrict__ counters, int cand_cap, const int4 *__restrict__ rects
 __global__ void __launch_bounds__(NV_GROUP_FUSED_THREADS)
 k_group_fused(const PlanDev *__restrict__ plan, int *counters, const uint32_t *__restrict__ cand, int cand_cap, uint32_t *sorted,
               int4 *rects, uint32_t *adj, int *grp, int min_neighbors, double eps, int img_w, int img_h, uint8_t *result,
-              int result_cap)
+              int result_cap, uint8_t *host_result)
 {
     const int n = min(counters[1], cand_cap);
     cand_sort_body(plan, n, cand, sorted, rects, min_neighbors > 0 ? grp : nullptr);
@@ -340,16 +346,16 @@ k_group_fused(const PlanDev *__restrict__ plan, int *counters, const uint32_t *_
         adj_body(plan, n, sorted, rects, adj, grp, eps);
         __syncthreads();
     }
-    group_body<NV_GROUP_FUSED_THREADS>(counters, cand_cap, rects, adj, grp, min_neighbors, eps, img_w, img_h, result, result_cap);
+    group_body<NV_GROUP_FUSED_THREADS>(counters, cand_cap, rects, adj, grp, min_neighbors, eps, img_w, img_h, result, result_cap, host_result);
 }
 
 cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *cand, int cand_cap, uint32_t *cand_sorted,
                          int4 *cand_rects, uint32_t *adj, int *grp, int min_neighbors, double eps, int img_w, int img_h,
-                         uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch, bool fused)
+                         uint8_t *result, int result_cap, int nblocks, cudaStream_t st, int *nlaunch, bool fused, uint8_t *host_result)
 {
     if (fused) {
         k_group_fused<<<1, NV_GROUP_FUSED_THREADS, GROUP_SMEM_LABELS * sizeof(int), st>>>(plan, counters, cand, cand_cap, cand_sorted, cand_rects, adj,
-                                                                                  grp, min_neighbors, eps, img_w, img_h, result, result_cap);
+                                                                                  grp, min_neighbors, eps, img_w, img_h, result, result_cap, host_result);
         (*nlaunch)++;
         return cudaGetLastError();
     }
@@ -360,7 +366,7 @@ cudaError_t launch_group(const PlanDev *plan, int *counters, const uint32_t *can
         (*nlaunch)++;
     }
     k_group<<<1, NV_GROUP_THREADS, GROUP_SMEM_LABELS * sizeof(int), st>>>(counters, cand_cap, cand_rects, adj, grp, min_neighbors, eps,
-                                                              img_w, img_h, result, result_cap);
+                                                              img_w, img_h, result, result_cap, host_result);
     (*nlaunch)++;
     return cudaGetLastError();
 }
