@@ -294,6 +294,7 @@ extern "C" int nv_ctx_create(int gpu, int max_width, int max_height, nv_ctx **ou
         c->ps = &c->slots[0];
         for (int i = 0; i < NV_PLAN_SLOTS; i++) NV_CUDA(cudaMalloc(&c->slots[i].d_plan, sizeof(PlanDev)));
         NV_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(int)));
+        NV_CUDA(cudaMemset(c->d_counters, 0, 16 * sizeof(int)));     // from here on the grouping kernel leaves them at zero
         NV_CUDA(cudaMalloc(&c->d_deepq, NV_DEEPQ_CAP * sizeof(uint2)));
         return alloc_candidates(c, CAND_CAP, true);
     }();
@@ -714,7 +715,8 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
     cudaStream_t st = ctx->stream;
     int nl = 0;
     for (int i = 2; i <= NV_NUM_STAGES; i++) ctx->prof_set[i] = false;
-    NV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(int), st));
+    // (no memset of the counters here: the last kernel of every call, k_group / k_group_fused, zeroes them when it has read
+    // them — a memset node cost a small call more than any of its kernels' launch gaps)
     if (P.nlevels > 0) {
         int16_t *depth = ctx->debug ? ctx->d_depth : nullptr;
         prof_mark(ctx, 2);

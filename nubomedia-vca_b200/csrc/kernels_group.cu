@@ -310,12 +310,14 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
         }
         nout = carry;
     }
+    __syncthreads();                                     // every thread has read its counters
     if (tid == 0) {
         hdr->n_out = min(nout, result_cap);
         hdr->n_cand = counters[1];
         hdr->n_alive = counters[0];
         hdr->overflow = counters[2] | (nout > result_cap) | (counters[1] > cand_cap);
         if (host_result) *reinterpret_cast<ResultHeader *>(host_result) = *hdr;
+        for (int i = 0; i < 16; i++) counters[i] = 0;    // the call's last kernel leaves the counters ready for the next call
     }
 }
 
