@@ -1533,7 +1533,10 @@ static int tracker_impl(nv_ctx *ctx, const FaceSrc &src, int width, int height, 
     std::vector<nv_rect> v;
     if (!first) {
         const int4 *d_out = reinterpret_cast<const int4 *>(ctx->d_trk_scratch + ctx->trk_lo.out);
-        NV_CUDA(cudaMemcpyAsync(ctx->h_trk, d_out, (1 + 1024) * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
+        // count and the first 1024 rectangles: written into h_trk by the kernel's last block (mapped memory) unless
+        // NUBOVCA_HOST_WRITES=0 asks for the copy
+        static const bool host_writes = [] { const char *e = getenv("NUBOVCA_HOST_WRITES"); return !e || atoi(e) != 0; }();
+        if (!host_writes) NV_CUDA(cudaMemcpyAsync(ctx->h_trk, d_out, (1 + 1024) * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
         NV_CUDA(cudaStreamSynchronize(ctx->stream));
         const int4 *h = reinterpret_cast<const int4 *>(ctx->h_trk);
         total = h[0].x;

@@ -71,6 +71,8 @@ struct TrkParams {
     int *keys;                      // [TRK_MAX_COMPONENTS]
     int4 *rects;                    // [TRK_MAX_COMPONENTS]
     int4 *out;                      // [1 + TRK_MAX_COMPONENTS]: (count, 0, 0, 0), rects in raster order of the first seed
+    int4 *hout;                     // the context's page-locked copy of out[0 .. 1024] (mapped host memory): written by the last block,
+                                    // so that no device-to-host copy follows the launch; nullptr: the host copies
     float val[256];                 // timestamp of history index k after this frame's expiry (0: none / expired)
 };
 
@@ -449,9 +451,15 @@ __global__ void __launch_bounds__(256) k_trk_fused(const __grid_constant__ TrkPa
         int rank = 0;
         if (in_smem) for (int j = 0; j < n; j++) rank += s_lab[j] < key;
         else for (int j = 0; j < n; j++) rank += __ldcg(P.keys + j) < key;
-        P.out[1 + rank] = __ldcg(P.rects + i);
+        const int4 r = __ldcg(P.rects + i);
+        P.out[1 + rank] = r;
+        if (P.hout && rank < 1024) P.hout[1 + rank] = r;
     }
-    if (tid == 0) { P.out[0] = make_int4(total, 0, 0, 0); P.counters[0] = 0; P.counters[1] = 0; P.counters[2] = 0; }
+    if (tid == 0) {
+        P.out[0] = make_int4(total, 0, 0, 0);
+        if (P.hout) P.hout[0] = make_int4(total, 0, 0, 0);
+        P.counters[0] = 0; P.counters[1] = 0; P.counters[2] = 0;
+    }
     TRK_T(10);
 }
 
@@ -492,6 +500,8 @@ cudaError_t launch_tracker(nv_ctx *ctx, int fmt, const SrcPlanes &src, int w, in
     P.parent = reinterpret_cast<int *>(base + lo.parent); P.edge_flag = reinterpret_cast<int *>(base + lo.edge_flag);
     P.counters = reinterpret_cast<int *>(base + lo.counters); P.keys = reinterpret_cast<int *>(base + lo.keys);
     P.rects = reinterpret_cast<int4 *>(base + lo.rects); P.out = reinterpret_cast<int4 *>(base + lo.out);
+    static const bool host_writes = [] { const char *e = getenv("NUBOVCA_HOST_WRITES"); return !e || atoi(e) != 0; }();
+    P.hout = host_writes ? reinterpret_cast<int4 *>(ctx->h_trk) : nullptr;
     for (int i = 0; i < 256; i++) P.val[i] = val256[i];
     const int nt = lo.ntx * lo.nty;
     cudaStream_t st = ctx->stream;
