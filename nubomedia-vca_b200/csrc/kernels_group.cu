@@ -196,36 +196,27 @@ __device__ __forceinline__ void group_body(int *counters, int cand_cap, const in
             for (int i = tid; i < n; i += NT) { const int r = uf_find(grp, i); if (r != i) grp[i] = r; }
         }
         __syncthreads();
-        // min-label propagation until a fixed point: one warp per candidate row, lanes over the row's adjacency
-        // words (the next row is fetched while the current one is reduced)
+        // min-label propagation until a fixed point: one warp per candidate row.  A lane fetches one adjacency word of the row
+        // (the next row's while the current one is reduced); the non-zero words are then taken one at a time by the WHOLE warp,
+        // one bit per lane — in the clusters of a frame with faces a word holds 20-30 set bits, and walking them with a lane per
+        // word (the first version) left 25 lanes idle behind seven that looped: 59 % of the kernel's instructions on config 3.
         const int lane = tid & 31, warp = tid >> 5;
-        const int wpl = (nw + 31) >> 5;                  // words per lane (<= 8 for n <= 8192)
         for (; !uf;) {
             if (tid == 0) s_changed = 0;
             __syncthreads();
-            uint32_t nxt[8];
-            if (wpl <= 8 && warp < n)
-#pragma unroll
-                for (int q = 0; q < 8; q++) { int w = lane + 32 * q; nxt[q] = (q < wpl && w < nw) ? adj[(size_t)warp * nw + w] : 0u; }
+            uint32_t nxt = (warp < n && lane < nw) ? adj[(size_t)warp * nw + lane] : 0u;
             for (int i = warp; i < n; i += (NT / 32)) {
                 int m = 0x7fffffff;
-                if (wpl <= 8) {
-                    uint32_t cur[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) cur[q] = nxt[q];
-                    if (i + (NT / 32) < n)
-#pragma unroll
-                        for (int q = 0; q < 8; q++) { int w = lane + 32 * q; nxt[q] = (q < wpl && w < nw) ? adj[(size_t)(i + (NT / 32)) * nw + w] : 0u; }
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        uint32_t b = cur[q];
-                        int w = lane + 32 * q;
-                        while (b) { int j = w * 32 + __ffs(b) - 1; b &= b - 1; m = min(m, label[j]); }
-                    }
-                } else {
-                    for (int w = lane; w < nw; w += 32) {
-                        uint32_t b = adj[(size_t)i * nw + w];
-                        while (b) { int j = w * 32 + __ffs(b) - 1; b &= b - 1; m = min(m, label[j]); }
+                uint32_t b = nxt;
+                if (i + (NT / 32) < n) nxt = lane < nw ? adj[(size_t)(i + (NT / 32)) * nw + lane] : 0u;
+                for (int w0 = 0; w0 < nw; w0 += 32) {
+                    if (w0 > 0) b = w0 + lane < nw ? adj[(size_t)i * nw + w0 + lane] : 0u;      // more than 1024 candidates
+                    uint32_t nz = __ballot_sync(0xffffffffu, b != 0u);
+                    while (nz) {
+                        const int src = __ffs(nz) - 1;
+                        nz &= nz - 1;
+                        const uint32_t bw = __shfl_sync(0xffffffffu, b, src);
+                        if ((bw >> lane) & 1u) m = min(m, label[(w0 + src) * 32 + lane]);
                     }
                 }
                 m = __reduce_min_sync(0xffffffffu, m);
