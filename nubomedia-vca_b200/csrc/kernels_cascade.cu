@@ -1326,6 +1326,29 @@ __device__ __forceinline__ long long clk_after(uint32_t dep)
     return t;
 }
 #endif
+// A warp copies the (wh + 1) x LP integral patch of one window into its shared-memory slot: every lane busy (element
+// lane + 32 k; row and column carried along, no division in the loop), four loads in flight per lane.  (Lane per column, row by
+// row — 21 of 32 lanes, one load in flight — was 14 % of k_cascade_tail_fast's instructions and 28 % of its stall samples on
+// config 3.)
+__device__ __forceinline__ void copy_patch(uint32_t *win, const uint32_t *__restrict__ wb, int pitch, int ystep, int iplane, int LP,
+                                           int npatch, int lane)
+{
+    int r = lane / LP, c = lane - r * LP;
+    const int dr = 32 / LP, dc = 32 - dr * LP;
+    for (int idx = lane; idx < npatch; idx += 128) {
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (idx + 32 * u < npatch) v[u] = __ldg(wb + r * pitch + (ystep == 2 ? (c & 1) * iplane + (c >> 1) : c));
+            c += dc; r += dr;
+            if (c >= LP) { c -= LP; r++; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (idx + 32 * u < npatch) win[idx + 32 * u] = v[u];
+    }
+}
+
 struct TailRec { uint4 a, b, c; };
 __device__ __forceinline__ TailRec load_tail(const TailStump *__restrict__ t, int k)
 {
@@ -1367,10 +1390,7 @@ k_cascade_tail_fast(const PlanDev *__restrict__ plan, const DevCascade *__restri
         int k0 = meta->stage_first[stage_begin];
         TailRec rec = load_tail(ts, min(k0 + lane, nstumps - 1));
         __syncwarp();
-        for (int c = lane; c <= ww; c += 32) {                   // private copy of the window's integral patch, row by row
-            int pc = L.ystep == 2 ? (c & 1) * L.iplane + (c >> 1) : c;
-            for (int r = 0; r <= wh; r++) win[r * LP + c] = __ldg(wb + (size_t)r * L.ipitch + pc);
-        }
+        copy_patch(win, wb, L.ipitch, L.ystep, L.iplane, LP, npatch, lane);       // private copy of the window's integral patch
         __syncwarp();
 #ifdef NV_TAIL_TRACE
         long long t_copied = clk_after((uint32_t)win[0]);
@@ -1512,16 +1532,7 @@ k_cascade_tail_tab(const PlanDev *__restrict__ plan, const DevCascade *__restric
         const int pitch = L.ipitch;
         const uint32_t *wb = sum + L.iofs + (size_t)iy * L.ystep * pitch + ix;
         __syncwarp();                                            // the previous window's reads of the patch are done
-        for (int c = lane; c <= ww; c += 32) {                   // private copy of the window's integral patch, four rows in flight
-            const uint32_t *src = wb + (L.ystep == 2 ? (c & 1) * L.iplane + (c >> 1) : c);
-            int r = 0;
-            for (; r + 4 <= wh + 1; r += 4) {
-                const uint32_t v0 = __ldg(src + (size_t)r * pitch), v1 = __ldg(src + (size_t)(r + 1) * pitch);
-                const uint32_t v2 = __ldg(src + (size_t)(r + 2) * pitch), v3 = __ldg(src + (size_t)(r + 3) * pitch);
-                win[r * LP + c] = v0; win[(r + 1) * LP + c] = v1; win[(r + 2) * LP + c] = v2; win[(r + 3) * LP + c] = v3;
-            }
-            for (; r <= wh; r++) win[r * LP + c] = __ldg(src + (size_t)r * pitch);
-        }
+        copy_patch(win, wb, pitch, L.ystep, L.iplane, LP, npatch, lane);         // private copy of the window's integral patch
         __syncwarp();
         int code = NV_DEPTH_PASS;
         for (int st = stage_begin; st < nstages; st++) {
