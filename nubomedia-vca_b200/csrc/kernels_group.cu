@@ -30,10 +30,15 @@ __device__ __forceinline__ bool similar_rects(const int4 &a, const int4 &b, doub
 __device__ __forceinline__ void cand_sort_body(const PlanDev *__restrict__ plan, int n, const uint32_t *__restrict__ cand,
                                                uint32_t *sorted, int4 *rects, int *label)
 {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t key = cand[i];
+    // one WARP per candidate: its rank is counted 32 keys at a time and summed by a warp reduction (a thread per candidate
+    // walked all n keys alone — n threads busy, each for n dependent iterations)
+    const int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+        const uint32_t key = __ldg(cand + i);
         int rank = 0;
-        for (int j = 0; j < n; j++) rank += __ldg(cand + j) < key;
+        for (int j = lane; j < n; j += 32) rank += __ldg(cand + j) < key;
+        rank = __reduce_add_sync(0xffffffffu, rank);
+        if (lane) continue;
         int l = key >> 26, iy = (key >> 13) & 8191, ix = key & 8191;
         const LevelDesc &L = plan->lv[l];
         float sc = L.scale;
@@ -112,15 +117,16 @@ __device__ __forceinline__ void adj_body(const PlanDev *__restrict__ plan, int n
 {
     const int nw = (n + 31) >> 5;
     if (n > NV_GROUP_UF_MIN) { uf_link(plan, n, sorted, rects, label, eps); return; }     // large n: components by union-find
-    long long total = (long long)n * nw;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        int i = (int)(t / nw), w = (int)(t - (long long)i * nw);
-        int4 a = rects[i];
-        uint32_t m = 0;
-        int j0 = w * 32, j1 = min(n, j0 + 32);
-        for (int j = j0; j < j1; j++)
-            if (j != i && similar_rects(a, rects[j], eps)) m |= 1u << (j - j0);
-        adj[t] = m;
+    // one WARP per matrix word, one pair per lane, the word assembled by a vote (a thread per word tested its 32 pairs one
+    // after the other: a chain of 32 dependent iterations where this is one)
+    const int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = n * nw;                                     // n <= NV_GROUP_UF_MIN: fits an int
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < total; t += nwarps) {
+        const int i = t / nw, w = t - i * nw, j = w * 32 + lane;
+        const int4 a = rects[i];
+        const bool bit = j < n && j != i && similar_rects(a, rects[min(j, n - 1)], eps);
+        const uint32_t m = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) adj[t] = m;
     }
 }
 
