@@ -1188,7 +1188,7 @@ static int face_submit_impl(nv_ctx *ctx, const nv_cascade *c, const FaceSrc &src
     auto enqueue = [&](int *nl) -> int {
         ctx->prof_set[0] = ctx->prof_set[1] = false;
         prof_mark(ctx, 0);
-        // the prep kernel's last block turns the histogram into the equalizeHist LUT (no k_lut launch; the "hist_lut" stage of
+        // the prep kernel's last block turns the histogram into the equalizeHist LUT (no launch of its own for the LUT; the "hist_lut" stage of
         // the profile is empty)
         if (yuv) NV_CUDA(launch_face_prep_yuv(src.fmt, planes, width, height, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream, ctx->d_lut));
         else NV_CUDA(launch_face_prep(d_src, width, height, stride, 3, ctx->d_gray, cols, rows, d_rtab, ctx->d_hist, ctx->stream, ctx->d_lut));
@@ -1363,10 +1363,9 @@ extern "C" int nv_equalize_hist(nv_ctx *ctx, const uint8_t *src, int width, int 
     if (rc != NV_OK) return rc;
     if (!dst || dst_stride < width) { nv_set_error("bad destination"); return NV_ERR_ARG; }
     if ((rc = upload(ctx, src, (size_t)stride_bytes * height)) != NV_OK) return rc;
-    NV_CUDA(launch_hist(ctx->d_frame, width, height, stride_bytes, ctx->d_hist, ctx->stream));
-    NV_CUDA(launch_lut(ctx->d_hist, width * height, ctx->d_lut, ctx->stream));
+    NV_CUDA(launch_hist(ctx->d_frame, width, height, stride_bytes, ctx->d_hist, ctx->stream, ctx->d_lut));
     NV_CUDA(launch_apply_lut(ctx->d_frame, width, height, stride_bytes, ctx->d_lut, ctx->d_gray, width, ctx->stream));
-    ctx->launches += 3;
+    ctx->launches += 2;
     return download(ctx, ctx->d_gray, width, height, dst, dst_stride);
 }
 

@@ -105,10 +105,9 @@ int img_ensure(DevImg &im, int w, int h)
 
 int dev_equalize(nv_ctx *ctx, DevImg &im)
 {
-    NV_CUDA(launch_hist(im.p, im.w, im.h, im.w, ctx->d_hist, ctx->stream));
-    NV_CUDA(launch_lut(ctx->d_hist, im.w * im.h, ctx->d_lut, ctx->stream));
+    NV_CUDA(launch_hist(im.p, im.w, im.h, im.w, ctx->d_hist, ctx->stream, ctx->d_lut));        // histogram, and the LUT by its last block
     NV_CUDA(launch_apply_lut(im.p, im.w, im.h, im.w, ctx->d_lut, im.p, im.w, ctx->stream));   // element-wise: in place is safe
-    ctx->launches += 3;
+    ctx->launches += 2;
     return NV_OK;
 }
 

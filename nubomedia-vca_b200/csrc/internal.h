@@ -400,8 +400,7 @@ cudaError_t launch_bgr2gray(const uint8_t *src, int w, int h, int sstride, int c
                             cudaStream_t st);
 cudaError_t launch_resize_linear(const uint8_t *src, int sw, int sh, int sstride, int cn, uint8_t *dst, int dw, int dh,
                                  int dstride, const int *rtab, cudaStream_t st);
-cudaError_t launch_hist(const uint8_t *src, int w, int h, int stride, int *hist, cudaStream_t st);
-cudaError_t launch_lut(int *hist, int total, uint8_t *lut, cudaStream_t st);
+cudaError_t launch_hist(const uint8_t *src, int w, int h, int stride, int *hist, cudaStream_t st, uint8_t *lut = nullptr);   // lut: as launch_face_prep (hist holds 257 ints)
 cudaError_t launch_apply_lut(const uint8_t *src, int w, int h, int sstride, const uint8_t *lut, uint8_t *dst, int dstride,
                              cudaStream_t st);
 cudaError_t launch_flip(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride, cudaStream_t st);

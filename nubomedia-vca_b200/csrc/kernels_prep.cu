@@ -83,7 +83,7 @@ __device__ __forceinline__ uint8_t lut_entry(int t, int hv, int total, int *cum,
 }
 
 // End of a face-prep kernel: flush the block's histogram; with `lut` set, the block that finishes LAST (a ticket in
-// hist[256]) turns the complete histogram into the LUT and clears histogram and ticket for the next frame — what k_lut
+// hist[256]) turns the complete histogram into the LUT and clears histogram and ticket for the next frame — what a k_lut
 // does as a launch of its own (one block, ~4 us of a small call's chain) when the histogram comes from elsewhere.
 __device__ __forceinline__ void prep_finish(int tid, int *sh_hist, int *__restrict__ hist, uint8_t *__restrict__ lut, int total)
 {
@@ -93,7 +93,7 @@ __device__ __forceinline__ void prep_finish(int tid, int *sh_hist, int *__restri
     if (!lut) return;
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = atomicAdd(&hist[256], 1) == (int)gridDim.x - 1;
+    if (tid == 0) s_last = atomicAdd(&hist[256], 1) == (int)(gridDim.x * gridDim.y) - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -391,7 +391,7 @@ k_resize_linear(const uint8_t *__restrict__ src, int sw, int sh, int sstride, in
 }
 
 __global__ void __launch_bounds__(256)
-k_hist(const uint8_t *__restrict__ src, int w, int h, int stride, int *__restrict__ hist)
+k_hist(const uint8_t *__restrict__ src, int w, int h, int stride, int *__restrict__ hist, uint8_t *__restrict__ lut)
 {
     __shared__ int sh_hist[256];
     int tid = threadIdx.y * 32 + threadIdx.x;
@@ -399,19 +399,7 @@ k_hist(const uint8_t *__restrict__ src, int w, int h, int stride, int *__restric
     __syncthreads();
     int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     if (x < w && y < h) atomicAdd(&sh_hist[src[(size_t)y * stride + x]], 1);
-    __syncthreads();
-    if (sh_hist[tid]) atomicAdd(&hist[tid], sh_hist[tid]);
-}
-
-// K3: histogram -> equalizeHist LUT (A.3).  One block of 256 threads; clears the histogram for the
-// next frame.  lut[k] = sat_u8(rint((float)(cum[k] - cum[i0]) * (255.f / (total - hist[i0])))).
-__global__ void __launch_bounds__(256) k_lut(int *__restrict__ hist, int total, uint8_t *__restrict__ lut)
-{
-    __shared__ int cum[256];
-    __shared__ int s_i0;
-    const int t = threadIdx.x;
-    lut[t] = lut_entry(t, hist[t], total, cum, &s_i0);
-    hist[t] = 0;
+    prep_finish(tid, sh_hist, hist, lut, w * h);                 // lut: the last block turns the histogram into the LUT (no launch of its own for the LUT)
 }
 
 __global__ void __launch_bounds__(256)
@@ -515,14 +503,9 @@ cudaError_t launch_resize_linear(const uint8_t *src, int sw, int sh, int sstride
     k_resize_linear<<<grid2d(dw, dh), dim3(32, 8), 0, st>>>(src, sw, sh, sstride, cn, dst, dw, dh, dstride, rtab);
     return cudaGetLastError();
 }
-cudaError_t launch_hist(const uint8_t *src, int w, int h, int stride, int *hist, cudaStream_t st)
+cudaError_t launch_hist(const uint8_t *src, int w, int h, int stride, int *hist, cudaStream_t st, uint8_t *lut)
 {
-    k_hist<<<grid2d(w, h), dim3(32, 8), 0, st>>>(src, w, h, stride, hist);
-    return cudaGetLastError();
-}
-cudaError_t launch_lut(int *hist, int total, uint8_t *lut, cudaStream_t st)
-{
-    k_lut<<<1, 256, 0, st>>>(hist, total, lut);
+    k_hist<<<grid2d(w, h), dim3(32, 8), 0, st>>>(src, w, h, stride, hist, lut);
     return cudaGetLastError();
 }
 cudaError_t launch_apply_lut(const uint8_t *src, int w, int h, int sstride, const uint8_t *lut, uint8_t *dst, int dstride,
