@@ -716,7 +716,12 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
     int nl = 0;
     for (int i = 2; i <= NV_NUM_STAGES; i++) ctx->prof_set[i] = false;
     // (no memset of the counters here: the last kernel of every call, k_group / k_group_fused, zeroes them when it has read
-    // them — a memset node cost a small call more than any of its kernels' launch gaps)
+    // them — a memset node cost a small call more than any of its kernels' launch gaps.  Should a launch in between fail, that
+    // kernel never runs: the guard clears them on the way out, best effort.)
+    struct CountersGuard {
+        nv_ctx *c; cudaStream_t s; bool done = false;
+        ~CountersGuard() { if (!done) { cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(int), s); cudaGetLastError(); } }
+    } counters_guard{ctx, st};
     if (P.nlevels > 0) {
         int16_t *depth = ctx->debug ? ctx->d_depth : nullptr;
         prof_mark(ctx, 2);
@@ -877,6 +882,7 @@ static int detect_enqueue(nv_ctx *ctx, nv_cascade *casc, const uint8_t *d_gray, 
         NV_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(ResultHeader) + NV_RESULT_INLINE * sizeof(nv_rect),
                                 cudaMemcpyDeviceToHost, st));
     *nlaunch += nl;
+    counters_guard.done = true;
     return NV_OK;
 }
 
